@@ -1,0 +1,106 @@
+/*
+ * ttx.h -- C ABI of the B200 joint + transducer-loss path (libttx.so).
+ *
+ * Plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless stated
+ * otherwise, `stream` is a cudaStream_t passed as void*, all work is stream-ordered with no hidden
+ * synchronisation and no global state, so the library is re-entrant per stream.  Every function returns
+ * 0 on success, 1 for an argument / shape error, 2 for a CUDA error; ttx_last_error() gives the message of
+ * the calling thread's last failure.
+ *
+ * What each entry point replaces in the reference (zzpDapeng/Transformer-Transducer):
+ *   ttx_joint_act + ttx_joint_lse_fwd   JointNet.forward tanh + project_layer, /root/reference/tt/model.py:33-37,
+ *                                       JointNetwork.forward, espnet/nets/pytorch_backend/transducer/joint_network.py:48-49,
+ *                                       and the log_softmax of warprnnt_pytorch.RNNTLoss (called train.py:53)
+ *   ttx_lattice_fwd_bwd                 the alpha/beta recursion of warprnnt_pytorch (train.py:53; transducer/loss.py:74)
+ *   ttx_grad_coeffs + ttx_joint_grad + ttx_reduce_act_grad
+ *                                       loss.backward() through RNNTLoss, log_softmax, project_layer, tanh and the
+ *                                       broadcast add (train.py:58)
+ *   ttx_dense_lse / ttx_dense_grad      RNNTLoss on an already materialised (B,T,U+1,V) logits tensor (train.py:53)
+ *
+ * Lattice cells are addressed in a compact row space described by the tile table ("meta"): utterance b owns
+ * 128-row tiles [meta[4+b], meta[4+b+1]); row r of the utterance is cell (t,u) = (r / (label_len[b]+1),
+ * r % (label_len[b]+1)).  All per-row arrays below have ttx_tiles_upper_bound(...) * 128 entries.
+ */
+#ifndef TTX_H_
+#define TTX_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ttx_version(void);
+const char* ttx_last_error(void);
+
+/* 1 when the fused tensor-core kernels support joint width H (multiple of 64 up to 256, 384 or 512). */
+int ttx_supported_h(int H);
+/* Upper bound of 128-row lattice tiles for a (B, T, U1 = U + 1) batch; sizes every per-row buffer. */
+int64_t ttx_tiles_upper_bound(int B, int T, int U1);
+/* Number of int32 entries the tile table needs. */
+int64_t ttx_meta_ints(int B, int64_t n_tiles_ub);
+
+/* Builds the tile table from the (device) length vectors.  meta[0] = tiles in use, meta[1] = 0 or
+ * 1 + index of the first utterance whose lengths are out of range (then no kernel does any work). */
+int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int64_t n_tiles_ub,
+                int32_t* meta, int device, void* stream);
+
+/* W_out (V,H) fp32 -> 16-bit tensor-core operand (Vpad = 128 * ceil(V/128) rows, zero padded).
+ * bf16 = 0: fp16 scaled by a power of two w_scale; bf16 = 1: bfloat16.  scal: 4 floats
+ * {w_scale, 1/w_scale, gmax (set by ttx_grad_coeffs), scratch}. */
+int ttx_cast_weight(const float* w_out, int V, int H, int bf16, float* scal, void* w16, int device, void* stream);
+
+/* A16[row,:] = 16-bit(tanh(eproj[b,t,:] + pproj[b,u,:])) for every lattice cell; row_label[row] = label
+ * emitted from the cell's u (labels[b,u]) or -1.  eproj (B,T,H), pproj (B,U1,H) fp32 contiguous;
+ * labels (B, label_stride) int32, entries at u >= label_lens[b] are never read. */
+int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
+                  const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
+                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, int device, void* stream);
+
+/* tcgen05 projection A16 . W16^T + b_out fused with log-softmax statistics: per row lse, log p(blank),
+ * log p(label).  The (B,T,U1,V) logits are never written. */
+int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, const float* scal,
+                      const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
+                      int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream);
+
+/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice.
+ * costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
+int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, float* alpha, float* beta,
+                        float* costs, float* ll_beta, int device, void* stream);
+
+/* Per-row gradient coefficients rowmeta[row] = {lse, rb, rl, gamma * grad_costs[b] / gmax} (float4),
+ * gmax = max_b |grad_costs[b]| stored in scal[2]. */
+int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const float* alpha,
+                    const float* beta, const float* ll_beta, const float* grad_costs, float* scal,
+                    const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
+                    int64_t n_tiles_ub, void* rowmeta, int device, void* stream);
+
+/* Fused gradient: recomputes the joint tile on the tensor cores and accumulates
+ *   d_act (rows,H) fp32 = dL/dA (before the tanh derivative)        if d_act  != NULL
+ *   d_w_out (V,H), d_b_out (V) fp32 += dL/dW_out, dL/db_out          if d_w_out != NULL (caller zero-fills)
+ * `splits` = lattice-row splits of the weight-gradient grid (>= 1). */
+int ttx_joint_grad(const void* a16, const void* w16, const float* b_out, const float* scal,
+                   const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
+                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
+                   void* stream);
+
+/* d_eproj[b,t,:] = sum_u d_act * (1 - tanh^2), d_pproj[b,u,:] = sum_t d_act * (1 - tanh^2); both fully
+ * overwritten (zeros outside the ragged region). */
+int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* pproj, const int32_t* act_lens,
+                        const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H,
+                        float* d_eproj, float* d_pproj, int device, void* stream);
+
+/* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
+int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
+                  const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,
+                  int64_t n_tiles_ub, float* lse, float* lp_blank, float* lp_label, int32_t* row_label, int device,
+                  void* stream);
+int ttx_dense_grad(const float* acts, const void* rowmeta, const int32_t* row_label, const float* scal,
+                   const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                   int V, int blank, float* grads, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTX_H_ */

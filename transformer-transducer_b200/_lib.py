@@ -1,0 +1,88 @@
+"""Loads (and, on request, builds) libttx.so -- the C-ABI CUDA library declared in include/ttx.h.
+
+No fallback: if the library is missing or a call fails the caller gets an exception.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libttx.so")
+SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+c_i32, c_i64, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    "ttx_version": [],
+    "ttx_last_error": [],
+    "ttx_supported_h": [c_i32],
+    "ttx_tiles_upper_bound": [c_i32, c_i32, c_i32],
+    "ttx_meta_ints": [c_i32, c_i64],
+    "ttx_prepare": [c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_i32, c_p],
+    "ttx_cast_weight": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
+    "ttx_joint_act": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_p, c_p,
+                      c_i32, c_p],
+    "ttx_joint_lse_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_lattice_fwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_grad_coeffs": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i64, c_p, c_i32, c_p],
+    "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32,
+                       c_i32, c_p],
+    "ttx_reduce_act_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
+    "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
+                      c_i32, c_p],
+    "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
+}
+_RESTYPES = {"ttx_last_error": ctypes.c_char_p, "ttx_tiles_upper_bound": c_i64, "ttx_meta_ints": c_i64}
+EXPORTS = tuple(_PROTOS)
+
+
+class TTXError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into lib/libttx.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "ttx_common.cuh"), os.path.join(ROOT, "include", "ttx.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+    subprocess.check_call(cmd, cwd=CSRC)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def get():
+    """The loaded library (ctypes.CDLL with prototypes set).  Raises TTXError if it was never built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise TTXError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(there is no CPU / library fallback)" % LIB_PATH)
+                lib = ctypes.CDLL(LIB_PATH)
+                for name, argtypes in _PROTOS.items():
+                    fn = getattr(lib, name)
+                    fn.argtypes = argtypes
+                    fn.restype = _RESTYPES.get(name, c_i32)
+                _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = get().ttx_last_error()
+        raise TTXError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))

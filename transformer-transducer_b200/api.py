@@ -1,0 +1,13 @@
+"""Public surface of the package."""
+from . import _lib
+from .functional import dense_rnnt, fused_joint_rnnt, supported_width
+from .install import install
+from .joint import JointNet, JointNetwork
+from .lazy import LazyJointLogits
+from .loss import RNNTLoss, certify_inputs, rnnt_loss
+
+build = _lib.build
+TTXError = _lib.TTXError
+
+__all__ = ["JointNet", "JointNetwork", "LazyJointLogits", "RNNTLoss", "rnnt_loss", "certify_inputs",
+           "fused_joint_rnnt", "dense_rnnt", "supported_width", "install", "build", "TTXError"]

@@ -1,0 +1,193 @@
+// extern "C" boundary of libttx.so (declared in include/ttx.h): argument checks + kernel launches.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/ttx.h"
+#include "ttx_common.cuh"
+
+namespace ttx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// launchers (ttx_small.cu / ttx_joint_mma.cu)
+int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
+int launch_cast_w(const float*, int, int, int, bool, float*, void*, cudaStream_t);
+int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
+                     int, int, bool, void*, int*, cudaStream_t);
+int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, float*, float*, float*,
+                   float*, cudaStream_t);
+int launch_grad_prep(const float*, const float*, const float*, const float*, const float*, const float*,
+                     const float*, float*, const int*, const int*, const int*, int, int, float4*, cudaStream_t);
+int launch_reduce(const float*, const float*, const float*, const int*, const int*, const int*, int, int, int, int,
+                  float*, float*, cudaStream_t);
+int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
+                     float*, float*, float*, int*, cudaStream_t);
+int launch_dense_grad(const float*, const float4*, const int*, const float*, const int*, const int*, const int*, int,
+                      int, int, int, int, float*, cudaStream_t);
+bool mma_supported_h(int H);
+int launch_joint_fwd(const void*, const void*, uint64_t, int, int, int, int, bool, const int*, const float*,
+                     const float*, const int*, int, float*, float*, float*, cudaStream_t);
+int launch_joint_bwd(const void*, const void*, uint64_t, int, int, int, int, bool, const int*, const float*,
+                     const float*, const int*, int, const float4*, float*, float*, float*, int, cudaStream_t);
+
+static int enter(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+
+}  // namespace ttx
+
+using namespace ttx;
+
+#define TTX_REQUIRE(cond, ...)     \
+    do {                           \
+        if (!(cond)) {             \
+            set_error(__VA_ARGS__); \
+            return 1;              \
+        }                          \
+    } while (0)
+#define TTX_ENTER(device)                 \
+    do {                                  \
+        if (int _rc = enter(device)) return _rc; \
+    } while (0)
+
+extern "C" {
+
+int ttx_version(void) { return 1; }
+
+const char* ttx_last_error(void) { return g_err; }
+
+int ttx_supported_h(int H) { return mma_supported_h(H) ? 1 : 0; }
+
+int64_t ttx_tiles_upper_bound(int B, int T, int U1) {
+    if (B <= 0 || T <= 0 || U1 <= 0) return 0;
+    return (int64_t)B * (((int64_t)T * U1 + kTile - 1) / kTile);
+}
+
+int64_t ttx_meta_ints(int B, int64_t n_tiles_ub) { return kMetaHdr + (int64_t)B + 1 + n_tiles_ub; }
+
+int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int64_t n_tiles_ub,
+                int32_t* meta, int device, void* stream) {
+    TTX_REQUIRE(act_lens && label_lens && meta, "ttx_prepare: null pointer");
+    TTX_REQUIRE(B > 0 && T > 0 && U1 > 0, "ttx_prepare: bad shape B=%d T=%d U1=%d", B, T, U1);
+    TTX_REQUIRE(n_tiles_ub >= ttx_tiles_upper_bound(B, T, U1) && n_tiles_ub < (1 << 24),
+                "ttx_prepare: tile bound %lld out of range", (long long)n_tiles_ub);
+    TTX_ENTER(device);
+    return launch_prep(act_lens, label_lens, B, T, U1, (int)n_tiles_ub, meta, (cudaStream_t)stream);
+}
+
+int ttx_cast_weight(const float* w_out, int V, int H, int bf16, float* scal, void* w16, int device, void* stream) {
+    TTX_REQUIRE(w_out && scal && w16, "ttx_cast_weight: null pointer");
+    TTX_REQUIRE(V > 0 && H > 0 && H % 8 == 0, "ttx_cast_weight: bad shape V=%d H=%d", V, H);
+    TTX_ENTER(device);
+    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    return launch_cast_w(w_out, V, Vpad, H, bf16 != 0, scal, w16, (cudaStream_t)stream);
+}
+
+int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
+                  const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
+                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, int device, void* stream) {
+    TTX_REQUIRE(eproj && pproj && act_lens && label_lens && meta && a16 && row_label, "ttx_joint_act: null pointer");
+    TTX_REQUIRE(labels || U1 == 1, "ttx_joint_act: labels is null");
+    TTX_REQUIRE(H > 0 && H % 8 == 0, "ttx_joint_act: H=%d must be a positive multiple of 8", H);
+    TTX_ENTER(device);
+    return launch_joint_act(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1, H, label_stride,
+                            (int)n_tiles_ub, bf16 != 0, a16, row_label, (cudaStream_t)stream);
+}
+
+int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, const float* scal,
+                      const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
+                      int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream) {
+    TTX_REQUIRE(a16 && w16 && b_out && scal && row_label && meta && lse && lp_blank && lp_label,
+                "ttx_joint_lse_fwd: null pointer");
+    TTX_REQUIRE(mma_supported_h(H), "ttx_joint_lse_fwd: joint width H=%d is not supported by the tensor-core path", H);
+    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_lse_fwd: bad V=%d / blank=%d", V, blank);
+    TTX_ENTER(device);
+    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    return launch_joint_fwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
+                            b_out, scal, row_label, blank, lse, lp_blank, lp_label, (cudaStream_t)stream);
+}
+
+int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, float* alpha, float* beta,
+                        float* costs, float* ll_beta, int device, void* stream) {
+    TTX_REQUIRE(lp_blank && lp_label && act_lens && label_lens && meta && alpha && beta && costs && ll_beta,
+                "ttx_lattice_fwd_bwd: null pointer");
+    TTX_ENTER(device);
+    return launch_lattice(lp_blank, lp_label, act_lens, label_lens, meta, B, U1, alpha, beta, costs, ll_beta,
+                          (cudaStream_t)stream);
+}
+
+int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const float* alpha,
+                    const float* beta, const float* ll_beta, const float* grad_costs, float* scal,
+                    const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
+                    int64_t n_tiles_ub, void* rowmeta, int device, void* stream) {
+    TTX_REQUIRE(lse && lp_blank && lp_label && alpha && beta && ll_beta && grad_costs && scal && rowmeta,
+                "ttx_grad_coeffs: null pointer");
+    TTX_ENTER(device);
+    return launch_grad_prep(lse, lp_blank, lp_label, alpha, beta, ll_beta, grad_costs, scal, act_lens, label_lens,
+                            meta, B, (int)n_tiles_ub, (float4*)rowmeta, (cudaStream_t)stream);
+}
+
+int ttx_joint_grad(const void* a16, const void* w16, const float* b_out, const float* scal,
+                   const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
+                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
+                   void* stream) {
+    TTX_REQUIRE(a16 && w16 && b_out && scal && row_label && meta && rowmeta, "ttx_joint_grad: null pointer");
+    TTX_REQUIRE((d_w_out == nullptr) == (d_b_out == nullptr), "ttx_joint_grad: d_w_out and d_b_out go together");
+    TTX_REQUIRE(mma_supported_h(H), "ttx_joint_grad: joint width H=%d is not supported by the tensor-core path", H);
+    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_grad: bad V=%d / blank=%d", V, blank);
+    TTX_REQUIRE(splits >= 1 && splits <= 65535, "ttx_joint_grad: bad splits=%d", splits);
+    TTX_ENTER(device);
+    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    return launch_joint_bwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
+                            b_out, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
+                            (cudaStream_t)stream);
+}
+
+int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* pproj, const int32_t* act_lens,
+                        const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H,
+                        float* d_eproj, float* d_pproj, int device, void* stream) {
+    TTX_REQUIRE(d_act && eproj && pproj && act_lens && label_lens && meta && d_eproj && d_pproj,
+                "ttx_reduce_act_grad: null pointer");
+    TTX_REQUIRE(H % 4 == 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_reduce_act_grad: bad shape");
+    TTX_ENTER(device);
+    return launch_reduce(d_act, eproj, pproj, act_lens, label_lens, meta, B, T, U1, H, d_eproj, d_pproj,
+                         (cudaStream_t)stream);
+}
+
+int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
+                  const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,
+                  int64_t n_tiles_ub, float* lse, float* lp_blank, float* lp_label, int32_t* row_label, int device,
+                  void* stream) {
+    TTX_REQUIRE(acts && act_lens && label_lens && meta && lse && lp_blank && lp_label && row_label,
+                "ttx_dense_lse: null pointer");
+    TTX_REQUIRE(labels || U1 == 1, "ttx_dense_lse: labels is null");
+    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_dense_lse: bad V=%d / blank=%d", V, blank);
+    TTX_ENTER(device);
+    return launch_dense_lse(acts, labels, act_lens, label_lens, meta, B, T, U1, V, label_stride, blank,
+                            (int)n_tiles_ub, lse, lp_blank, lp_label, row_label, (cudaStream_t)stream);
+}
+
+int ttx_dense_grad(const float* acts, const void* rowmeta, const int32_t* row_label, const float* scal,
+                   const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                   int V, int blank, float* grads, int device, void* stream) {
+    TTX_REQUIRE(acts && rowmeta && row_label && scal && act_lens && label_lens && meta && grads,
+                "ttx_dense_grad: null pointer");
+    TTX_ENTER(device);
+    return launch_dense_grad(acts, (const float4*)rowmeta, row_label, scal, act_lens, label_lens, meta, B, T, U1, V,
+                             blank, grads, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,518 @@
+// The one dense contraction of the path -- the joint's H -> V projection -- on tcgen05 tensor cores.
+//
+// One kernel template, three modes, all "stationary tile x streamed tiles" with the 16-bit operands
+// staged by TMA into 128B-swizzled shared memory and fp32 accumulators in TMEM:
+//
+//   FWD  X = A16 tile (128 lattice rows x H), Y = W16 streamed over V.
+//        S = X . Y^T  -> epilogue: + bias, online log-sum-exp over V, pick blank / label logits.
+//        Writes 3 floats per lattice cell; the (B,T,U1,V) logits never leave the SM.
+//        (replaces the Linear -> log_softmax hand-off, /root/reference/tt/model.py:37 + train.py:53)
+//   DA   X = A16 tile, Y = W16.  Recomputes S, turns it into P' = softmax - transition posteriors
+//        (16-bit, shared memory) and accumulates G = P' . W16[:, half] in TMEM -> dL/dA tile.
+//   DW   X = W16 tile (128 vocab rows), Y = A16 streamed over lattice rows.  Recomputes S^T, builds
+//        Q = gamma * P' and accumulates G = Q . A16[:, half] in TMEM -> dL/dW_out tile (+ dL/db_out).
+//        (DA + DW replace autograd through log_softmax + project_layer, train.py:58)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).
+#include "ttx_common.cuh"
+
+namespace ttx {
+
+enum { MODE_FWD = 0, MODE_DA = 1, MODE_DW = 2 };
+
+struct MmaParams {
+    int H, NKC;            // joint width, H / 64
+    int V;                 // vocabulary size (valid rows of W16)
+    int n_vtiles;          // ceil(V / 128)
+    int n_halves, HH;      // backward: H is processed in n_halves column slabs of HH
+    int NGC, GCH;          // backward: HH / 64 chunks per slab, chunks per G-pass MMA group
+    int NS;                // ring stages
+    int blank;
+    int splits;            // DW: lattice-row splits
+    const int* meta;       // tile table
+    const float* bias;     // (V) fp32
+    const float* scal;     // [0] w_scale, [1] 1 / w_scale, [2] gmax
+    const int* row_label;  // (rows) label emitted from the cell's u, -1 if none / padding
+    float* lse;            // FWD out (rows)
+    float* lpb;            // FWD out (rows) log p(blank)
+    float* lpl;            // FWD out (rows) log p(label)
+    const float4* rowmeta; // BWD in (rows): {lse, rb, rl, gamma * g_b / gmax}
+    float* dA;             // DA out (rows x H)
+    float* dW;             // DW out (V x H), accumulated with red.add
+    float* db;             // DW out (V)
+};
+
+constexpr int kThreads = 192;
+constexpr int kNumBars = 32;
+
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int ns, int n = 1) {
+        stage += n;
+        if (stage >= ns) {
+            stage -= ns;
+            phase ^= 1;
+        }
+    }
+};
+
+template <int MODE, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                 const MmaParams p) {
+    constexpr bool BWD = (MODE != MODE_FWD);
+    const int n_tiles = p.meta[0];
+    // ---- work assignment (uniform per CTA; CTAs without work leave before touching TMEM)
+    int x_row0, j0, j1;
+    if (MODE == MODE_DW) {
+        const int per = (n_tiles + p.splits - 1) / p.splits;
+        x_row0 = blockIdx.x * kTile;
+        j0 = blockIdx.z * per;
+        j1 = min(n_tiles, j0 + per);
+    } else {
+        if ((int)blockIdx.x >= n_tiles) return;
+        x_row0 = blockIdx.x * kTile;
+        j0 = 0;
+        j1 = p.n_vtiles;
+    }
+    if (j0 >= j1) return;
+    const int half = BWD ? blockIdx.y : 0;
+    const int n_iter = j1 - j0;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sX = smem_base;                                  // NKC chunks
+    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // BWD: 2 chunks (128 x 128 16-bit)
+    const uint32_t sRing = sP + (BWD ? 2 * kChunkBytes : 0);        // NS chunks
+    const uint32_t sBar = sRing + p.NS * kChunkBytes;               // barriers
+    const uint32_t sTmemPtr = sBar + kNumBars * 8;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
+
+    // barrier map
+    const uint32_t bar_xfull = sBar;
+    auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
+    auto bar_empty = [&](int s) { return sBar + 8 * (9 + s); };
+    auto bar_sfull = [&](int b) { return sBar + 8 * (17 + b); };
+    auto bar_sempty = [&](int b) { return sBar + 8 * (19 + b); };
+    const uint32_t bar_pfull = sBar + 8 * 21;
+    const uint32_t bar_pempty = sBar + 8 * 22;
+    const uint32_t bar_gfull = sBar + 8 * 23;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = BWD ? 512 : 256;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapY);
+        mbar_init(bar_xfull, 1);
+        for (int s = 0; s < p.NS; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_sfull(b), 1);
+            mbar_init(bar_sempty(b), 128);
+        }
+        mbar_init(bar_pfull, 128);
+        mbar_init(bar_pempty, 1);
+        mbar_init(bar_gfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sTmemPtr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    const uint32_t tmem_G = tmem_base + 256;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_xfull, p.NKC * kChunkBytes);
+            for (int c = 0; c < p.NKC; ++c) tma_load_2d(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            Ring r;
+            auto load_chunk = [&](int col, int row) {
+                mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                mbar_arrive_expect_tx(bar_full(r.stage), kChunkBytes);
+                tma_load_2d(sRing + r.stage * kChunkBytes, &mapY, bar_full(r.stage), col, row);
+                r.advance(p.NS);
+            };
+            auto load_S = [&](int j) {
+                for (int c = 0; c < p.NKC; ++c) load_chunk(c * kKC, j * kTile);
+            };
+            auto load_G = [&](int j) {
+                for (int c = 0; c < p.NGC; ++c) load_chunk(half * p.HH + c * kKC, j * kTile);
+            };
+            if (!BWD) {
+                for (int j = j0; j < j1; ++j) load_S(j);
+            } else {
+                load_S(j0);
+                for (int i = 0; i < n_iter; ++i) {
+                    if (i + 1 < n_iter) load_S(j0 + i + 1);
+                    load_G(j0 + i);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr int fmt = BF16 ? 1 : 0;
+            const uint32_t idescS = make_idesc(fmt, 0, 0, 128, 128);
+            const uint32_t idescG = make_idesc(fmt, 0, 1, 128, 64 * p.GCH);
+            Ring r;
+            mbar_wait(bar_xfull, 0);
+            auto issue_S = [&](int idx) {
+                const int buf = idx & 1;
+                mbar_wait(bar_sempty(buf), ((idx >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * 128;
+                for (int c = 0; c < p.NKC; ++c) {
+                    mbar_wait(bar_full(r.stage), r.phase);
+                    tc_fence_after();
+                    const uint32_t a = sX + c * kChunkBytes;
+                    const uint32_t b = sRing + r.stage * kChunkBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_ss(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
+                    umma_commit(bar_empty(r.stage));
+                    r.advance(p.NS);
+                }
+                umma_commit(bar_sfull(buf));
+            };
+            auto issue_G = [&](int idx) {
+                mbar_wait(bar_pfull, idx & 1);
+                tc_fence_after();
+                for (int g = 0; g < p.NGC; g += p.GCH) {
+                    for (int s = 0; s < p.GCH; ++s) mbar_wait(bar_full(r.stage + s), r.phase);
+                    tc_fence_after();
+                    const uint32_t d = tmem_G + g * 64;
+                    const uint32_t b = sRing + r.stage * kChunkBytes;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_f16_ss(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3),
+                                    desc_mnmajor(b, k, kChunkBytes), idescG, (idx | k) != 0);
+                    for (int s = 0; s < p.GCH; ++s) umma_commit(bar_empty(r.stage + s));
+                    r.advance(p.NS, p.GCH);
+                }
+                umma_commit(bar_pempty);
+            };
+            if (!BWD) {
+                for (int i = 0; i < n_iter; ++i) issue_S(i);
+            } else {
+                issue_S(0);
+                for (int i = 0; i < n_iter; ++i) {
+                    if (i + 1 < n_iter) issue_S(i + 1);
+                    issue_G(i);
+                }
+                umma_commit(bar_gfull);
+            }
+        }
+    } else {
+        // =========================================================== epilogue warps (128 threads)
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                // accumulator row handled by this thread
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float inv_ws = p.scal[1];
+        const float c1 = inv_ws * kLog2e;
+        uint32_t acc[32];
+
+        if (MODE == MODE_FWD) {
+            const int grow = x_row0 + row;
+            const int label = p.row_label[grow];
+            float m2 = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;   // log2 domain running max / sum
+            for (int i = 0; i < n_iter; ++i) {
+                const int buf = i & 1;
+                const int v0 = (j0 + i) * kTile;
+                mbar_wait(bar_sfull(buf), (i >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, acc);
+                    tmem_ld_wait();
+                    const int vb = v0 + cc * 32;
+                    float y[32];
+                    float gmax = -INFINITY;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int v = vb + e;
+                        const float bv = (v < p.V) ? __ldg(p.bias + v) : 0.f;
+                        float yy = fmaf(__uint_as_float(acc[e]), c1, bv * kLog2e);
+                        yy = (v < p.V) ? yy : -INFINITY;
+                        if (v == p.blank) zb = yy;
+                        if (v == label) zl = yy;
+                        y[e] = yy;
+                        gmax = fmaxf(gmax, yy);
+                    }
+                    const float mn = fmaxf(m2, gmax);
+                    if (mn > -INFINITY) {
+                        float part = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) part += ex2f(y[e] - mn);
+                        ssum = ssum * ex2f(m2 - mn) + part;
+                        m2 = mn;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_sempty(buf));
+            }
+            const float lse2 = m2 + lg2f(ssum);
+            p.lse[grow] = lse2 * kLn2;
+            p.lpb[grow] = (zb - lse2) * kLn2;
+            p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+        } else {
+            // ---- backward: S -> 16-bit gradient operand in shared memory (K-major, 128B swizzle)
+            uint8_t* sP_gen = smem_gen + (sP - smem_base);
+            const float pscale = BF16 ? 1.0f : kPScale;
+            float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+            int label = -1;
+            float lse2 = 0.f, bias2 = 0.f, db_acc = 0.f;
+            int vrow = 0;
+            if (MODE == MODE_DA) {
+                rm = p.rowmeta[x_row0 + row];
+                label = p.row_label[x_row0 + row];
+                lse2 = rm.x * kLog2e;
+            } else {
+                vrow = x_row0 + row;
+                bias2 = (vrow < p.V) ? __ldg(p.bias + vrow) * kLog2e : 0.f;
+            }
+            for (int i = 0; i < n_iter; ++i) {
+                const int buf = i & 1;
+                const int c0 = (j0 + i) * kTile;   // first vocab id (DA) / lattice row (DW) of this stream tile
+                mbar_wait(bar_sfull(buf), (i >> 1) & 1);
+                tc_fence_after();
+                uint32_t packed[64];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, acc);
+                    tmem_ld_wait();
+                    float val[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = c0 + cc * 32 + e;
+                        float out;
+                        if (MODE == MODE_DA) {
+                            const bool ok = col < p.V;
+                            const float bv = ok ? __ldg(p.bias + col) : 0.f;
+                            float pr = ex2f(fmaf(__uint_as_float(acc[e]), c1, fmaf(bv, kLog2e, -lse2)));
+                            if (col == p.blank) pr -= rm.y;
+                            if (col == label) pr -= rm.z;
+                            out = ok ? pr * pscale : 0.f;
+                        } else {
+                            const float4 cm = __ldg(p.rowmeta + col);
+                            const int clabel = __ldg(p.row_label + col);
+                            float pr = ex2f(fmaf(__uint_as_float(acc[e]), c1, fmaf(cm.x, -kLog2e, bias2)));
+                            if (vrow == p.blank) pr -= cm.y;
+                            if (vrow == clabel) pr -= cm.z;
+                            pr = (vrow < p.V) ? pr * cm.w : 0.f;
+                            db_acc += pr;
+                            out = pr * pscale;
+                        }
+                        val[e] = out;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) packed[cc * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                }
+                // S buffer is free again as soon as it sits in registers
+                tc_fence_before();
+                mbar_arrive(bar_sempty(buf));
+                // wait until the previous G pass has finished reading the P tile, then overwrite it
+                mbar_wait(bar_pempty, (i & 1) ^ 1);
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {      // 16 chunks of 8 values (16 B) along k
+                    const int blk = ch >> 3, cin = ch & 7;
+                    uint4 v4 = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+                    *reinterpret_cast<uint4*>(sP_gen + blk * kChunkBytes + row * 128 + ((cin ^ (row & 7)) << 4)) = v4;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(bar_pfull);
+            }
+            // ---- final: G (128 x HH fp32 in TMEM) -> global
+            mbar_wait(bar_gfull, 0);
+            tc_fence_after();
+            const float gmax = p.scal[2];
+            if (MODE == MODE_DA) {
+                const float f = rm.w * gmax * inv_ws / pscale;
+                float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
+                for (int cc = 0; cc < p.HH / 32; ++cc) {
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
+                                               __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
+                        *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                    }
+                }
+            } else {
+                const float f = gmax / pscale;
+                const bool ok = vrow < p.V;
+                float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
+                for (int cc = 0; cc < p.HH / 32; ++cc) {
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
+                    }
+                }
+                if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax);
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// 2-D row-major [rows x H] 16-bit matrix, box = 64 columns x 128 rows, 128-byte swizzle.
+int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool bf16) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return 2;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)kTile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu H=%d)", (int)r,
+                  (unsigned long long)rows, H);
+        return 2;
+    }
+    return 0;
+}
+
+bool mma_supported_h(int H) {
+    return H > 0 && H <= 512 && H % 64 == 0 && (H <= 256 || H == 384 || H == 512);
+}
+
+static size_t smem_bytes(int NKC, int NS, bool bwd) {
+    return 1024 + (size_t)(NKC + NS + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16;
+}
+
+// Fills the shape-derived fields of MmaParams; returns dynamic shared memory size.
+static size_t plan(MmaParams& p, int H, int V, bool bwd) {
+    p.H = H;
+    p.NKC = H / 64;
+    p.V = V;
+    p.n_vtiles = (V + kTile - 1) / kTile;
+    p.n_halves = (bwd && H > 256) ? 2 : 1;
+    p.HH = H / p.n_halves;
+    p.NGC = p.HH / 64;
+    const size_t limit = 232448;
+    int ns = 8;
+    while (ns > 2 && smem_bytes(p.NKC, ns, bwd) > limit) --ns;
+    p.GCH = 1;
+    if (bwd) {
+        if (p.NKC % 4 == 0 && p.NGC % 4 == 0 && ns >= 4) {
+            p.GCH = 4;
+            ns = (ns / 4) * 4;
+        } else if (p.NKC % 2 == 0 && p.NGC % 2 == 0) {
+            p.GCH = 2;
+            ns = (ns / 2) * 2;
+        }
+    }
+    p.NS = ns;
+    return smem_bytes(p.NKC, ns, bwd);
+}
+
+template <int MODE, bool BF16>
+static int launch(const CUtensorMap& mx, const CUtensorMap& my, const MmaParams& p, dim3 grid, size_t smem,
+                  cudaStream_t stream) {
+    auto kern = joint_mma_kernel<MODE, BF16>;
+    static bool attr_set = false;   // per instantiation; same value for every device in this process
+    (void)attr_set;
+    TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    kern<<<grid, kThreads, smem, stream>>>(mx, my, p);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
+                     bool bf16, const int* meta, const float* bias, const float* scal, const int* row_label,
+                     int blank, float* lse, float* lpb, float* lpl, cudaStream_t stream) {
+    MmaParams p{};
+    size_t smem = plan(p, H, V, false);
+    p.blank = blank;
+    p.splits = 1;
+    p.meta = meta;
+    p.bias = bias;
+    p.scal = scal;
+    p.row_label = row_label;
+    p.lse = lse;
+    p.lpb = lpb;
+    p.lpl = lpl;
+    CUtensorMap mx, my;
+    if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16)) return rc;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16)) return rc;
+    dim3 grid(n_tiles_ub, 1, 1);
+    return bf16 ? launch<MODE_FWD, true>(mx, my, p, grid, smem, stream)
+                : launch<MODE_FWD, false>(mx, my, p, grid, smem, stream);
+}
+
+int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
+                     bool bf16, const int* meta, const float* bias, const float* scal, const int* row_label,
+                     int blank, const float4* rowmeta, float* dA, float* dW, float* db, int splits,
+                     cudaStream_t stream) {
+    MmaParams p{};
+    size_t smem = plan(p, H, V, true);
+    p.blank = blank;
+    p.meta = meta;
+    p.bias = bias;
+    p.scal = scal;
+    p.row_label = row_label;
+    p.rowmeta = rowmeta;
+    p.dA = dA;
+    p.dW = dW;
+    p.db = db;
+    CUtensorMap ma, mw;
+    if (int rc = make_tile_map(&ma, a16, rows_ub, H, bf16)) return rc;
+    if (int rc = make_tile_map(&mw, w16, (uint64_t)Vpad, H, bf16)) return rc;
+    if (dA) {
+        p.splits = 1;
+        dim3 grid(n_tiles_ub, p.n_halves, 1);
+        int rc = bf16 ? launch<MODE_DA, true>(ma, mw, p, grid, smem, stream)
+                      : launch<MODE_DA, false>(ma, mw, p, grid, smem, stream);
+        if (rc) return rc;
+    }
+    if (dW) {
+        p.splits = splits;
+        dim3 grid(p.n_vtiles, p.n_halves, splits);
+        int rc = bf16 ? launch<MODE_DW, true>(mw, ma, p, grid, smem, stream)
+                      : launch<MODE_DW, false>(mw, ma, p, grid, smem, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace ttx

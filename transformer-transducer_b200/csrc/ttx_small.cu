@@ -1,0 +1,528 @@
+// Memory- and latency-bound kernels around the tensor-core projection: tile table, operand casts,
+// the broadcast-add + tanh producer, the alpha/beta lattice wavefront, gradient coefficients and the
+// reductions back to (B,T,H) / (B,U1,H).  Lattice cells live in a COMPACT row space: utterance b owns
+// tiles [tile0[b], tile0[b+1]) of 128 rows; row r of the utterance is cell (t, u) = (r / U1_b, r % U1_b)
+// with U1_b = label_len[b] + 1, so ragged batches cost no work on padding.
+#include "ttx_common.cuh"
+
+namespace ttx {
+
+// ------------------------------------------------------------------------------------------- tile table
+__global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restrict__ label_lens, int B, int T,
+                            int U1, int n_tiles_ub, int* __restrict__ meta) {
+    __shared__ int part[1024];
+    __shared__ int bad;
+    __shared__ long long cells_sh;
+    const int tid = threadIdx.x;
+    const int per = (B + blockDim.x - 1) / blockDim.x;
+    const int b_lo = min(B, tid * per), b_hi = min(B, b_lo + per);
+    if (tid == 0) {
+        bad = 0x7fffffff;
+        cells_sh = 0;
+    }
+    __syncthreads();
+    int local = 0;
+    long long cells = 0;
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int t = act_lens[b], u1 = label_lens[b] + 1;
+        if (t < 1 || t > T || u1 < 1 || u1 > U1) {
+            atomicMin(&bad, b + 1);  // report the first bad utterance
+            continue;
+        }
+        local += (t * u1 + kTile - 1) / kTile;
+        cells += (long long)t * u1;
+    }
+    part[tid] = local;
+    atomicAdd(reinterpret_cast<unsigned long long*>(&cells_sh), (unsigned long long)cells);
+    __syncthreads();
+    // inclusive Hillis-Steele scan over the per-thread partial tile counts
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+        int v = (tid >= off) ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int tile = part[tid] - local;  // exclusive prefix
+    int* tile0 = meta + kMetaHdr;
+    int* tile_b = meta + kMetaHdr + B + 1;
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int t = act_lens[b], u1 = label_lens[b] + 1;
+        const bool ok = !(t < 1 || t > T || u1 < 1 || u1 > U1);
+        const int nt = ok ? (t * u1 + kTile - 1) / kTile : 0;
+        tile0[b] = tile;
+        for (int i = 0; i < nt; ++i) tile_b[tile + i] = b;
+        tile += nt;
+    }
+    const int total = part[blockDim.x - 1];
+    for (int i = total + tid; i < n_tiles_ub; i += blockDim.x) tile_b[i] = -1;
+    if (tid == 0) {
+        const int first_bad = (bad == 0x7fffffff) ? 0 : bad;
+        tile0[B] = total;
+        meta[0] = first_bad ? 0 : total;
+        meta[1] = first_bad;
+        meta[2] = (int)min(cells_sh, (long long)0x7fffffff);
+        meta[3] = n_tiles_ub;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- W_out -> 16 bit
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// scal[0] = w_scale (power of two putting max|W| into [256, 512) for fp16, 1 for bf16), scal[1] = 1/w_scale
+template <bool BF16>
+__global__ void cast_w_kernel(const float* __restrict__ w, int V, int Vpad, int H, const unsigned int* __restrict__ absmax_bits,
+                              float* __restrict__ scal, uint16_t* __restrict__ w16) {
+    float ws = 1.f;
+    if (!BF16) {
+        const float m = __uint_as_float(*absmax_bits);
+        if (m > 0.f && m < INFINITY) {
+            int e;
+            frexpf(m, &e);
+            ws = ldexpf(1.f, 9 - e);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[0] = ws;
+        scal[1] = 1.f / ws;
+    }
+    const size_t n = (size_t)Vpad * H / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e0 = 2 * i;
+        const int row = (int)(e0 / H);
+        float a = 0.f, b = 0.f;
+        if (row < V) {
+            const float2 v = *reinterpret_cast<const float2*>(w + e0);
+            a = v.x * ws;
+            b = v.y * ws;
+        }
+        reinterpret_cast<uint32_t*>(w16)[i] = pack16<BF16>(a, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- A16 = tanh(E + P)
+// The joint's broadcast-add + tanh (/root/reference/tt/model.py:22-36 after splitting forward_layer,
+// espnet joint_network.py:48) written once per lattice cell as the 16-bit tensor-core operand.
+template <bool BF16>
+__global__ void joint_act_kernel(const float* __restrict__ eproj, const float* __restrict__ pproj,
+                                 const int* __restrict__ labels, const int* __restrict__ act_lens,
+                                 const int* __restrict__ label_lens, const int* __restrict__ meta, int B, int T,
+                                 int U1, int H, int label_stride, uint16_t* __restrict__ a16,
+                                 int* __restrict__ row_label) {
+    const int tile = blockIdx.x;
+    if (tile >= meta[0]) return;
+    const int b = meta[kMetaHdr + B + 1 + tile];
+    const int r0 = (tile - meta[kMetaHdr + b]) * kTile;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    const int nrows = Tb * U1b;
+    const int vec_per_row = H / 8;
+    const float* eb = eproj + (size_t)b * T * H;
+    const float* pb = pproj + (size_t)b * U1 * H;
+    for (int idx = threadIdx.x; idx < kTile * vec_per_row; idx += blockDim.x) {
+        const int lr = idx / vec_per_row, vc = idx - lr * vec_per_row;
+        const int r = r0 + lr;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (r < nrows) {
+            const int t = r / U1b, u = r - t * U1b;
+            const float4* e4 = reinterpret_cast<const float4*>(eb + (size_t)t * H + vc * 8);
+            const float4* p4 = reinterpret_cast<const float4*>(pb + (size_t)u * H + vc * 8);
+            const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
+            out.x = pack16<BF16>(tanhf(e0.x + p0.x), tanhf(e0.y + p0.y));
+            out.y = pack16<BF16>(tanhf(e0.z + p0.z), tanhf(e0.w + p0.w));
+            out.z = pack16<BF16>(tanhf(e1.x + p1.x), tanhf(e1.y + p1.y));
+            out.w = pack16<BF16>(tanhf(e1.z + p1.z), tanhf(e1.w + p1.w));
+        }
+        *reinterpret_cast<uint4*>(a16 + ((size_t)tile * kTile + lr) * H + vc * 8) = out;
+    }
+    for (int lr = threadIdx.x; lr < kTile; lr += blockDim.x) {
+        const int r = r0 + lr;
+        int lab = -1;
+        if (r < nrows) {
+            const int u = r % U1b;
+            if (u < U1b - 1) lab = labels[(size_t)b * label_stride + u];
+        }
+        row_label[(size_t)tile * kTile + lr] = lab;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- lattice
+__device__ __forceinline__ float log_add(float a, float b) {
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    if (mx == -INFINITY) return -INFINITY;
+    return mx + log1pf(expf(mn - mx));
+}
+
+// grid = 2B: block b computes alpha of utterance b, block B + b computes beta.  Thread u owns column u and
+// walks the anti-diagonals; its left / right neighbour's previous value travels through shared memory.
+// (warp-transducer semantics; called train.py:53.)
+__global__ void lattice_kernel(const float* __restrict__ lpb, const float* __restrict__ lpl,
+                               const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                               const int* __restrict__ meta, int B, float* __restrict__ alpha,
+                               float* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_beta) {
+    extern __shared__ float xch[];  // 2 x blockDim.x
+    if (meta[1] != 0) return;
+    const bool is_beta = blockIdx.x >= (unsigned)B;
+    const int b = is_beta ? blockIdx.x - B : blockIdx.x;
+    const int T = act_lens[b], U1 = label_lens[b] + 1;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    const int u = threadIdx.x;
+    const int nd = T + U1 - 1;
+    const bool active = u < U1;
+    float self = -INFINITY;  // my column's value on the previous diagonal
+    constexpr int PD = 4;    // prefetch distance in diagonals
+    float pf_b[PD], pf_l[PD];
+    // operand of diagonal d for column u:  alpha: t = d - u;  beta: t = T-1 - (d - (U1-1-u))
+    auto fetch = [&](int d, float& xb, float& xl) {
+        xb = 0.f;
+        xl = 0.f;
+        if (!active) return;
+        if (!is_beta) {
+            const int t = d - u;
+            if (t < 0 || t >= T) return;
+            if (t > 0) xb = __ldg(lpb + base + (size_t)(t - 1) * U1 + u);
+            if (u > 0) xl = __ldg(lpl + base + (size_t)t * U1 + (u - 1));
+        } else {
+            const int t = T - 1 - (d - (U1 - 1 - u));
+            if (t < 0 || t >= T) return;
+            xb = __ldg(lpb + base + (size_t)t * U1 + u);
+            if (u < U1 - 1) xl = __ldg(lpl + base + (size_t)t * U1 + u);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < PD; ++i) fetch(i, pf_b[i], pf_l[i]);
+    for (int d0 = 0; d0 < nd; d0 += PD) {
+#pragma unroll
+        for (int i = 0; i < PD; ++i) {
+            const int d = d0 + i;
+            if (d >= nd) break;
+            const float xb = pf_b[i], xl = pf_l[i];
+            fetch(d + PD, pf_b[i], pf_l[i]);
+            float* cur = xch + (d & 1) * blockDim.x;
+            const float* prev = xch + ((d & 1) ^ 1) * blockDim.x;
+            float val = -INFINITY;
+            bool on = false;
+            int t = 0;
+            if (active) {
+                t = is_beta ? T - 1 - (d - (U1 - 1 - u)) : d - u;
+                on = (t >= 0 && t < T);
+            }
+            if (on) {
+                if (!is_beta) {
+                    if (t == 0 && u == 0) val = 0.f;
+                    else {
+                        const float from_t = (t > 0) ? self + xb : -INFINITY;
+                        const float from_u = (u > 0) ? prev[u - 1] + xl : -INFINITY;
+                        val = log_add(from_t, from_u);
+                    }
+                    alpha[base + (size_t)t * U1 + u] = val;
+                } else {
+                    if (t == T - 1 && u == U1 - 1) val = xb;
+                    else {
+                        const float from_t = (t < T - 1) ? self + xb : -INFINITY;
+                        const float from_u = (u < U1 - 1) ? prev[u + 1] + xl : -INFINITY;
+                        val = log_add(from_t, from_u);
+                    }
+                    beta[base + (size_t)t * U1 + u] = val;
+                }
+                self = val;
+            }
+            cur[u] = val;
+            __syncthreads();
+            if (d == nd - 1 && on) {
+                if (!is_beta) costs[b] = -(val + __ldg(lpb + base + (size_t)(T - 1) * U1 + (U1 - 1)));
+                else ll_beta[b] = val;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- gradient coefficients
+__global__ void gmax_kernel(const float* __restrict__ grad_costs, int B, float* __restrict__ scal) {
+    __shared__ float sm[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) m = fmaxf(m, fabsf(grad_costs[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sm[i]);
+        scal[2] = (m > 0.f && m < INFINITY) ? m : 1.f;
+    }
+}
+
+// rowmeta[row] = {lse, rb, rl, gamma * g_b / gmax}: rb / rl are the posteriors of leaving the cell by a
+// blank / label arc given that the cell is visited; dL/dz(row, v) = g_b * gamma * (softmax_v - rb[v==blank] - rl[v==label]).
+__global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __restrict__ lpb,
+                                 const float* __restrict__ lpl, const float* __restrict__ alpha,
+                                 const float* __restrict__ beta, const float* __restrict__ ll_beta,
+                                 const float* __restrict__ grad_costs, const float* __restrict__ scal,
+                                 const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                 const int* __restrict__ meta, int B, float4* __restrict__ rowmeta) {
+    const int tile = blockIdx.x;
+    if (tile >= meta[0]) return;
+    const int b = meta[kMetaHdr + B + 1 + tile];
+    const int r = (tile - meta[kMetaHdr + b]) * kTile + threadIdx.x;
+    const int T = act_lens[b], U1 = label_lens[b] + 1;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    float4 out = make_float4(INFINITY, 0.f, 0.f, 0.f);
+    if (r < T * U1) {
+        const int t = r / U1, u = r - t * U1;
+        const float ll = ll_beta[b];
+        const float be = beta[base + r];
+        const float gam = __expf(alpha[base + r] + be - ll);
+        float rb, rl = 0.f;
+        if (t < T - 1) rb = __expf(lpb[base + r] + beta[base + r + U1] - be);
+        else rb = (u == U1 - 1) ? 1.f : 0.f;
+        if (u < U1 - 1) rl = __expf(lpl[base + r] + beta[base + r + 1] - be);
+        out = make_float4(lse[base + r], rb, rl, gam * grad_costs[b] / scal[2]);
+    }
+    rowmeta[(size_t)tile * kTile + threadIdx.x] = out;
+}
+
+// ------------------------------------------------------------------------------------------- dA -> dEproj, dPproj
+__device__ __forceinline__ float sech2(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    const float d = 1.f + e;
+    return 4.f * e / (d * d);
+}
+
+// dEproj[b,t,:] = sum_u dA[b,t,u,:] * (1 - tanh^2(E[b,t,:] + P[b,u,:]));  grid = (T, B), one float4 of h per thread
+__global__ void reduce_enc_kernel(const float* __restrict__ dA, const float* __restrict__ eproj,
+                                  const float* __restrict__ pproj, const int* __restrict__ act_lens,
+                                  const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
+                                  int H, float* __restrict__ d_eproj) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    if (meta[1] != 0) return;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < Tb) {
+            const float4 e = *reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h);
+            for (int u = 0; u < U1b; ++u) {
+                const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (base + (size_t)t * U1b + u) * H + h));
+                acc.x += g.x * sech2(e.x + pp.x);
+                acc.y += g.y * sech2(e.y + pp.y);
+                acc.z += g.z * sech2(e.z + pp.z);
+                acc.w += g.w * sech2(e.w + pp.w);
+            }
+        }
+        *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t) * H + h) = acc;
+    }
+}
+
+// dPproj[b,u,:] += sum over a chunk of t;  grid = (U1, B, t-chunks); d_pproj zero-initialised by the caller
+__global__ void reduce_pred_kernel(const float* __restrict__ dA, const float* __restrict__ eproj,
+                                   const float* __restrict__ pproj, const int* __restrict__ act_lens,
+                                   const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
+                                   int H, int t_chunk, float* __restrict__ d_pproj) {
+    const int u = blockIdx.x, b = blockIdx.y;
+    if (meta[1] != 0) return;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    if (u >= U1b) return;
+    const int t0 = blockIdx.z * t_chunk, t1 = min(Tb, t0 + t_chunk);
+    if (t0 >= t1) return;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
+        const float4 pp = *reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = t0; t < t1; ++t) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (base + (size_t)t * U1b + u) * H + h));
+            acc.x += g.x * sech2(e.x + pp.x);
+            acc.y += g.y * sech2(e.y + pp.y);
+            acc.z += g.z * sech2(e.z + pp.z);
+            acc.w += g.w * sech2(e.w + pp.w);
+        }
+        float* dst = d_pproj + ((size_t)b * U1 + u) * H + h;
+        atomicAdd(dst + 0, acc.x);
+        atomicAdd(dst + 1, acc.y);
+        atomicAdd(dst + 2, acc.z);
+        atomicAdd(dst + 3, acc.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- dense-logits entry
+// rnnt_loss called on a materialised (B,T,U1,V) fp32 logits tensor (someone else's joint): one warp per
+// lattice cell streams the row once (online log-sum-exp) and drops the 3 floats into the compact row space.
+__global__ void dense_lse_kernel(const float* __restrict__ acts, const int* __restrict__ labels,
+                                 const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                 const int* __restrict__ meta, int B, int T, int U1, int V, int label_stride,
+                                 int blank, float* __restrict__ lse, float* __restrict__ lpb,
+                                 float* __restrict__ lpl, int* __restrict__ row_label) {
+    const int tile = blockIdx.x;
+    if (tile >= meta[0]) return;
+    const int b = meta[kMetaHdr + B + 1 + tile];
+    const int r0 = (tile - meta[kMetaHdr + b]) * kTile;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int lr = warp; lr < kTile; lr += nwarps) {
+        const int r = r0 + lr;
+        const size_t grow = (size_t)tile * kTile + lr;
+        if (r >= Tb * U1b) {
+            if (lane == 0) {
+                lse[grow] = 0.f;
+                lpb[grow] = 0.f;
+                lpl[grow] = 0.f;
+                row_label[grow] = -1;
+            }
+            continue;
+        }
+        const int t = r / U1b, u = r - t * U1b;
+        const float* row = acts + (((size_t)b * T + t) * U1 + u) * V;
+        float m = -INFINITY, s = 0.f;
+        for (int v = lane; v < V; v += 32) {
+            const float z = __ldg(row + v);
+            const float mn = fmaxf(m, z);
+            if (mn > -INFINITY) {
+                s = s * __expf(m - mn) + __expf(z - mn);
+                m = mn;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+            const float mn = fmaxf(m, m2);
+            s = ((m > -INFINITY) ? s * __expf(m - mn) : 0.f) + ((m2 > -INFINITY) ? s2 * __expf(m2 - mn) : 0.f);
+            m = mn;
+        }
+        if (lane == 0) {
+            const float l = m + __logf(s);
+            const int lab = (u < U1b - 1) ? labels[(size_t)b * label_stride + u] : -1;
+            lse[grow] = l;
+            lpb[grow] = row[blank] - l;
+            lpl[grow] = (lab >= 0) ? row[lab] - l : 0.f;
+            row_label[grow] = lab;
+        }
+    }
+}
+
+// Dense gradient w.r.t. the logits (what upstream's compute_grad_kernel writes): one warp per (b,t,u) row of the
+// PADDED tensor; rows outside the utterance's lattice get exact zeros.
+__global__ void dense_grad_kernel(const float* __restrict__ acts, const float4* __restrict__ rowmeta,
+                                  const int* __restrict__ row_label, const float* __restrict__ scal,
+                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                  const int* __restrict__ meta, int B, int T, int U1, int V, int blank,
+                                  float* __restrict__ grads) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const size_t cell = (size_t)blockIdx.x * nwarps + warp;
+    if (cell >= (size_t)B * T * U1) return;
+    const int u = (int)(cell % U1);
+    const int t = (int)((cell / U1) % T);
+    const int b = (int)(cell / ((size_t)U1 * T));
+    float* g = grads + cell * V;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    if (meta[1] != 0 || t >= Tb || u >= U1b) {
+        for (int v = lane; v < V; v += 32) g[v] = 0.f;
+        return;
+    }
+    const size_t grow = (size_t)meta[kMetaHdr + b] * kTile + (size_t)t * U1b + u;
+    const float4 rm = rowmeta[grow];
+    const int lab = row_label[grow];
+    const float coef = rm.w * scal[2];
+    const float* row = acts + cell * V;
+    for (int v = lane; v < V; v += 32) {
+        float pr = __expf(__ldg(row + v) - rm.x);
+        if (v == blank) pr -= rm.y;
+        if (v == lab) pr -= rm.z;
+        g[v] = coef * pr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- launchers
+int launch_prep(const int* act_lens, const int* label_lens, int B, int T, int U1, int n_tiles_ub, int* meta,
+                cudaStream_t s) {
+    prep_kernel<<<1, 1024, 0, s>>>(act_lens, label_lens, B, T, U1, n_tiles_ub, meta);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_cast_w(const float* w, int V, int Vpad, int H, bool bf16, float* scal, void* w16, cudaStream_t s) {
+    unsigned int* bits = reinterpret_cast<unsigned int*>(scal + 3);
+    TTX_CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(unsigned int), s));
+    const size_t n = (size_t)V * H;
+    if (!bf16) absmax_kernel<<<296, 256, 0, s>>>(w, n, bits);
+    if (bf16) cast_w_kernel<true><<<592, 256, 0, s>>>(w, V, Vpad, H, bits, scal, (uint16_t*)w16);
+    else cast_w_kernel<false><<<592, 256, 0, s>>>(w, V, Vpad, H, bits, scal, (uint16_t*)w16);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_joint_act(const float* eproj, const float* pproj, const int* labels, const int* act_lens,
+                     const int* label_lens, const int* meta, int B, int T, int U1, int H, int label_stride,
+                     int n_tiles_ub, bool bf16, void* a16, int* row_label, cudaStream_t s) {
+    if (bf16)
+        joint_act_kernel<true><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1,
+                                                         H, label_stride, (uint16_t*)a16, row_label);
+    else
+        joint_act_kernel<false><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T,
+                                                          U1, H, label_stride, (uint16_t*)a16, row_label);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, const int* label_lens, const int* meta,
+                   int B, int U1, float* alpha, float* beta, float* costs, float* ll_beta, cudaStream_t s) {
+    const int threads = ((U1 + 31) / 32) * 32;
+    if (threads > 1024) {
+        set_error("lattice kernel supports at most 1023 labels per utterance (got U+1 = %d)", U1);
+        return 1;
+    }
+    lattice_kernel<<<2 * B, threads, 2 * threads * sizeof(float), s>>>(lpb, lpl, act_lens, label_lens, meta, B, alpha,
+                                                                     beta, costs, ll_beta);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_grad_prep(const float* lse, const float* lpb, const float* lpl, const float* alpha, const float* beta,
+                     const float* ll_beta, const float* grad_costs, float* scal, const int* act_lens,
+                     const int* label_lens, const int* meta, int B, int n_tiles_ub, float4* rowmeta,
+                     cudaStream_t s) {
+    gmax_kernel<<<1, 256, 0, s>>>(grad_costs, B, scal);
+    grad_prep_kernel<<<n_tiles_ub, kTile, 0, s>>>(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, act_lens,
+                                                  label_lens, meta, B, rowmeta);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_reduce(const float* dA, const float* eproj, const float* pproj, const int* act_lens,
+                  const int* label_lens, const int* meta, int B, int T, int U1, int H, float* d_eproj,
+                  float* d_pproj, cudaStream_t s) {
+    const int threads = min(256, max(32, H / 4));
+    reduce_enc_kernel<<<dim3(T, B), threads, 0, s>>>(dA, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
+    TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
+    const int t_chunk = 64;
+    reduce_pred_kernel<<<dim3(U1, B, (T + t_chunk - 1) / t_chunk), threads, 0, s>>>(dA, eproj, pproj, act_lens,
+                                                                                  label_lens, meta, T, U1, H, t_chunk,
+                                                                                  d_pproj);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_dense_lse(const float* acts, const int* labels, const int* act_lens, const int* label_lens,
+                     const int* meta, int B, int T, int U1, int V, int label_stride, int blank, int n_tiles_ub,
+                     float* lse, float* lpb, float* lpl, int* row_label, cudaStream_t s) {
+    dense_lse_kernel<<<n_tiles_ub, 256, 0, s>>>(acts, labels, act_lens, label_lens, meta, B, T, U1, V, label_stride,
+                                               blank, lse, lpb, lpl, row_label);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_dense_grad(const float* acts, const float4* rowmeta, const int* row_label, const float* scal,
+                      const int* act_lens, const int* label_lens, const int* meta, int B, int T, int U1, int V,
+                      int blank, float* grads, cudaStream_t s) {
+    const size_t cells = (size_t)B * T * U1;
+    const int wpb = 8;
+    dense_grad_kernel<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(acts, rowmeta, row_label, scal,
+                                                                              act_lens, label_lens, meta, B, T, U1, V,
+                                                                              blank, grads);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ttx

@@ -1,0 +1,198 @@
+"""Autograd functions that drive the CUDA kernels through the C ABI (include/ttx.h).
+
+``fused_joint_rnnt``  pre-projected encoder / predictor activations + output layer -> per-utterance
+                      costs, never materialising the (B,T,U+1,V) logits.  Replaces
+                      tanh + project_layer + log_softmax + warprnnt_pytorch.RNNTLoss
+                      (/root/reference/tt/model.py:36-37, train.py:53,58).
+``dense_rnnt``        the same loss on an already materialised logits tensor (train.py:53 when the
+                      joint is not ours).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _i32_cuda(t, dev, name):
+    if t.dtype != torch.int32:
+        raise TypeError("%s must be int32" % name)
+    return t.to(device=dev).contiguous()
+
+
+class _Plan:
+    """Shape bookkeeping + the buffers shared by both entry paths."""
+
+    def __init__(self, B, T, U1, dev, act_lens, label_lens):
+        lib = _lib.get()
+        self.lib, self.dev, self.B, self.T, self.U1 = lib, dev, B, T, U1
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.ntub = int(lib.ttx_tiles_upper_bound(B, T, U1))
+        self.rows = self.ntub * 128
+        self.meta = torch.empty(int(lib.ttx_meta_ints(B, self.ntub)), dtype=torch.int32, device=dev)
+        self.act_lens, self.label_lens = act_lens, label_lens
+        _lib.check(lib.ttx_prepare(_p(act_lens), _p(label_lens), B, T, U1, self.ntub, _p(self.meta), self.idx,
+                                   _stream(dev)), "ttx_prepare")
+
+    def rowf(self, n=1):
+        return torch.empty(self.rows * n, dtype=torch.float32, device=self.dev)
+
+    def lattice(self, lse, lpb, lpl):
+        alpha, beta = self.rowf(), self.rowf()
+        costs = torch.empty(self.B, dtype=torch.float32, device=self.dev)
+        ll_beta = torch.empty(self.B, dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
+                                               _p(self.meta), self.B, self.U1, _p(alpha), _p(beta), _p(costs),
+                                               _p(ll_beta), self.idx, _stream(self.dev)), "ttx_lattice_fwd_bwd")
+        return alpha, beta, costs, ll_beta
+
+    def grad_coeffs(self, lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal):
+        rowmeta = self.rowf(4)
+        g = grad_costs.detach().to(torch.float32).contiguous()
+        _lib.check(self.lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(ll_beta), _p(g),
+                                           _p(scal), _p(self.act_lens), _p(self.label_lens), _p(self.meta), self.B,
+                                           self.ntub, _p(rowmeta), self.idx, _stream(self.dev)), "ttx_grad_coeffs")
+        return rowmeta
+
+
+def supported_width(H):
+    return bool(_lib.get().ttx_supported_h(int(H)))
+
+
+class FusedJointRNNT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16):
+        if not eproj.is_cuda:
+            raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
+        dev = eproj.device
+        B, T, H = eproj.shape
+        U1 = pproj.shape[1]
+        V = w_out.shape[0]
+        if pproj.shape[0] != B or pproj.shape[2] != H or w_out.shape[1] != H or b_out.shape[0] != V:
+            raise ValueError("inconsistent joint shapes")
+        lib = _lib.get()
+        if not lib.ttx_supported_h(H):
+            raise ValueError("joint width %d is not supported by the fused tensor-core path" % H)
+        ep = eproj.detach().float().contiguous()
+        pp = pproj.detach().float().contiguous()
+        w = w_out.detach().float().contiguous()
+        b = b_out.detach().float().contiguous()
+        labels = labels.contiguous()
+        with torch.cuda.device(dev):
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            st = _stream(dev)
+            Vpad = (V + 127) // 128 * 128
+            scal = torch.zeros(4, dtype=torch.float32, device=dev)
+            w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
+            _lib.check(lib.ttx_cast_weight(_p(w), V, H, int(bf16), _p(scal), _p(w16), plan.idx, st), "ttx_cast_weight")
+            a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
+            row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
+            lstride = labels.shape[1] if labels.dim() == 2 else 0
+            _lib.check(lib.ttx_joint_act(_p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
+                                         _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
+                                         _p(a16), _p(row_label), plan.idx, st), "ttx_joint_act")
+            lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
+            _lib.check(lib.ttx_joint_lse_fwd(_p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                                             plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
+                                             plan.idx, st), "ttx_joint_lse_fwd")
+            alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
+        ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
+        ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
+        ctx.save_for_backward(ep, pp, b, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        ep, pp, b, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
+        plan, (B, T, U1, H, V) = ctx.plan, ctx.dims
+        lib, dev = plan.lib, plan.dev
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        d_ep = d_pp = d_w = d_b = None
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            scal = scal.clone()
+            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal)
+            d_act = plan.rowf(H) if need_act else None
+            if need_w:
+                d_w = torch.zeros(V, H, dtype=torch.float32, device=dev)
+                d_b = torch.zeros(V, dtype=torch.float32, device=dev)
+            if need_act or need_w:
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                n_vt = (V + 127) // 128
+                halves = 2 if H > 256 else 1
+                splits = max(1, min(plan.ntub, (sms * 4) // (n_vt * halves)))
+                _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                                              _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), _p(d_w),
+                                              _p(d_b), splits, plan.idx, st), "ttx_joint_grad")
+            if need_act:
+                d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+                d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
+                _lib.check(lib.ttx_reduce_act_grad(_p(d_act), _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens),
+                                                   _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st),
+                           "ttx_reduce_act_grad")
+        dt = ctx.in_dtypes
+        cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
+        return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
+                cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
+                None, None, None, None, None)
+
+
+def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False):
+    """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out."""
+    dev = eproj.device
+    return FusedJointRNNT.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
+                                _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"),
+                                blank, bf16)
+
+
+class DenseRNNT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, blank):
+        if not acts.is_cuda:
+            raise RuntimeError("rnnt_loss needs CUDA tensors (there is no CPU fallback)")
+        dev = acts.device
+        B, T, U1, V = acts.shape
+        a = acts.detach().float().contiguous()
+        labels = labels.contiguous()
+        lib = _lib.get()
+        with torch.cuda.device(dev):
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
+            row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
+            lstride = labels.shape[1] if labels.dim() == 2 else 0
+            _lib.check(lib.ttx_dense_lse(_p(a), _p(labels) if labels.numel() else None, _p(act_lens), _p(label_lens),
+                                         _p(plan.meta), B, T, U1, V, lstride, int(blank), plan.ntub, _p(lse), _p(lpb),
+                                         _p(lpl), _p(row_label), plan.idx, _stream(dev)), "ttx_dense_lse")
+            alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
+        ctx.plan, ctx.blank, ctx.in_dtype = plan, int(blank), acts.dtype
+        ctx.save_for_backward(a, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        a, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
+        plan = ctx.plan
+        B, T, U1, V = a.shape
+        with torch.cuda.device(plan.dev):
+            scal = torch.zeros(4, dtype=torch.float32, device=plan.dev)
+            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal)
+            grads = torch.empty_like(a)
+            _lib.check(plan.lib.ttx_dense_grad(_p(a), _p(rowmeta), _p(row_label), _p(scal), _p(plan.act_lens),
+                                               _p(plan.label_lens), _p(plan.meta), B, T, U1, V, ctx.blank, _p(grads),
+                                               plan.idx, _stream(plan.dev)), "ttx_dense_grad")
+        return grads.to(ctx.in_dtype), None, None, None, None
+
+
+def dense_rnnt(acts, labels, act_lens, label_lens, blank=0):
+    dev = acts.device
+    return DenseRNNT.apply(acts, _i32_cuda(labels, dev, "labels"), _i32_cuda(act_lens, dev, "act_lens"),
+                           _i32_cuda(label_lens, dev, "label_lens"), blank)

@@ -1,0 +1,63 @@
+"""``LazyJointLogits`` -- what the drop-in joint modules return instead of the (B,T,U+1,V) logits.
+
+The reference hands the joint's output across user code before it reaches the loss
+(/root/reference/tt/model.py:66-68 -> train.py:51-53; tt_espnet/model.py:73-80), so the handle has to
+look like the logits tensor (shape, dtype, device, ``.to(dtype=...)`` as used by
+espnet/nets/pytorch_backend/transducer/loss.py:57-60) while carrying only the small pre-projected
+operands.  ``RNNTLoss`` recognises it and runs the fused kernels; any other tensor operation
+materialises the logits explicitly (guarded by a size limit) -- nothing allocates B*T*U*V silently.
+"""
+import os
+
+import torch
+
+_ALLOWED_NOOP = ("aten.detach.default", "aten.alias.default")
+
+
+def _limit_bytes():
+    return float(os.environ.get("TTX_MATERIALIZE_LIMIT_GB", "8")) * (1 << 30)
+
+
+class LazyJointLogits(torch.Tensor):
+    @staticmethod
+    def __new__(cls, eproj, pproj, w_out, b_out, dtype=None):
+        B, T, _ = eproj.shape
+        U1 = pproj.shape[1]
+        V = w_out.shape[0]
+        r = torch.Tensor._make_wrapper_subclass(cls, (B, T, U1, V), dtype=dtype or eproj.dtype, device=eproj.device,
+                                                requires_grad=False)
+        r.eproj, r.pproj, r.w_out, r.b_out = eproj, pproj, w_out, b_out
+        return r
+
+    def __repr__(self):
+        return "LazyJointLogits(shape=%s, dtype=%s, device=%s)" % (tuple(self.shape), self.dtype, self.device)
+
+    @property
+    def parts(self):
+        return self.eproj, self.pproj, self.w_out, self.b_out
+
+    def materialize(self):
+        """Dense logits by plain torch ops (differentiable w.r.t. the parts); refuses above the size limit."""
+        nbytes = self.numel() * 4
+        if nbytes > _limit_bytes():
+            raise RuntimeError("refusing to materialise %.1f GB of joint logits (set TTX_MATERIALIZE_LIMIT_GB to "
+                               "override); pass the handle to RNNTLoss instead" % (nbytes / (1 << 30)))
+        h = torch.tanh(self.eproj.unsqueeze(2) + self.pproj.unsqueeze(1))
+        return torch.nn.functional.linear(h, self.w_out, self.b_out).to(self.dtype)
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = str(func)
+        if name in _ALLOWED_NOOP:
+            return args[0]
+        if name == "aten._to_copy.default":
+            src = args[0]
+            dev = kwargs.get("device", None)
+            if dev is None or torch.device(dev) == src.device:
+                return LazyJointLogits(*src.parts, dtype=kwargs.get("dtype", None) or src.dtype)
+
+        def unwrap(x):
+            return x.materialize().detach() if isinstance(x, LazyJointLogits) else x
+
+        return func(*torch.utils._pytree.tree_map(unwrap, args), **torch.utils._pytree.tree_map(unwrap, kwargs))

@@ -1,0 +1,79 @@
+"""Drop-in for the module the reference imports as ``warprnnt_pytorch`` (HawkAaron/warp-transducer's
+PyTorch binding; /root/reference/train.py:13,53,231, espnet/nets/pytorch_backend/transducer/loss.py:22-25,74).
+
+Same names, argument order, reductions and error behaviour as upstream: ``'mean'`` divides by the batch
+size, ``'mean'``/``'sum'`` return shape ``(1,)``, labels / lengths must be int32, ``T == max(act_lens)``
+and ``U + 1 == max(label_lens) + 1`` are checked on the host.  CUDA only -- the CPU path is the oracle,
+which is test infrastructure and not part of the product.
+"""
+import os
+
+import torch
+
+from . import functional as F
+from .lazy import LazyJointLogits
+
+
+def certify_inputs(acts, labels, act_lens, label_lens):
+    for name, t in (("labels", labels), ("act_lens", act_lens), ("label_lens", label_lens)):
+        if t.dtype != torch.int32:
+            raise TypeError("%s must be int32" % name)
+    if acts.dim() != 4:
+        raise ValueError("acts must have 4 dimensions")
+    if labels.dim() != 2:
+        raise ValueError("labels must have 2 dimensions")
+    if act_lens.dim() != 1:
+        raise ValueError("act_lens must have 1 dimension")
+    if label_lens.dim() != 1:
+        raise ValueError("label_lens must have 1 dimension")
+    B = acts.shape[0]
+    if act_lens.shape[0] != B or label_lens.shape[0] != B or labels.shape[0] != B:
+        raise ValueError("must have a length per example.")
+    if os.environ.get("TTX_SKIP_LENGTH_CHECKS", "0") == "1":
+        return
+    mx = torch.stack((act_lens.max(), label_lens.max(), act_lens.min(), label_lens.min())).tolist()  # one sync
+    if mx[0] != acts.shape[1]:
+        raise ValueError("Input length mismatch")
+    if mx[1] + 1 != acts.shape[2]:
+        raise ValueError("Output length mismatch")
+    if mx[2] < 1 or mx[3] < 0:
+        raise ValueError("lengths must be positive")
+    if labels.shape[1] < mx[1]:
+        raise ValueError("labels is shorter than max(label_lens)")
+
+
+def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fastemit_lambda=0.0):
+    """Transducer loss.  ``acts``: (B,T,U+1,V) fp32 CUDA logits or the lazy handle of our joint modules."""
+    if reduction not in ("none", "mean", "sum"):
+        raise ValueError("reduction must be one of none, mean, sum")
+    if fastemit_lambda != 0.0:
+        raise NotImplementedError("fastemit_lambda is not part of the reference's call and is not supported")
+    if not acts.is_cuda:
+        raise RuntimeError("warprnnt_pytorch (B200): acts must be a CUDA tensor -- there is no CPU fallback")
+    certify_inputs(acts, labels, act_lens, label_lens)
+    if isinstance(acts, LazyJointLogits):
+        ep, pp, w, b = acts.parts
+        bf16 = ep.dtype == torch.bfloat16
+        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16)
+    else:
+        costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank)
+    if reduction in ("sum", "mean"):
+        costs = costs.sum().unsqueeze(-1)
+        if reduction == "mean":
+            costs = costs / acts.shape[0]
+    return costs
+
+
+class RNNTLoss(torch.nn.Module):
+    """``RNNTLoss(blank=0, reduction='mean')(acts, labels, act_lens, label_lens)`` as in train.py:231,53."""
+
+    def __init__(self, blank=0, reduction="mean", fastemit_lambda=0.0):
+        super().__init__()
+        if reduction not in ("none", "mean", "sum"):
+            raise ValueError("reduction must be one of none, mean, sum")
+        self.blank = blank
+        self.reduction = reduction
+        self.fastemit_lambda = fastemit_lambda
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        return rnnt_loss(acts, labels, act_lens, label_lens, self.blank, self.reduction, self.fastemit_lambda)
