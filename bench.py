@@ -1,0 +1,313 @@
+"""Benchmark of the hot path: joint network + transducer loss, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+Prints ONE JSON line (rank 0).  A step is one joint -> RNNTLoss -> backward pass over one synthetic
+batch of the named workload (weak scaling: every GPU gets the full per-GPU batch).  See DESIGN.md
+"Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the microbench the headline metric is quoted on (espnet joint dims)
+    "cfg2": dict(B=32, T=400, U=40, V=4232, D=512, H=512, joint="espnet", ragged=False,
+                 desc="joint+RNN-T loss microbench B=32 T=400 U=40 V=4232 D=512 H=512 fp32"),
+    # BASELINE.json configs[0] shapes but with a fused-path joint width (parity-sized smoke workload)
+    "small": dict(B=4, T=200, U=30, V=4232, D=512, H=512, joint="espnet", ragged=False,
+                  desc="B=4 T=200 U=30 V=4232 D=512 H=512 fp32"),
+    # BASELINE.json configs[3]: long-utterance stress (dense logits would be 54 GB)
+    "cfg4": dict(B=16, T=1000, U=200, V=4232, D=512, H=512, joint="espnet", ragged=False,
+                 desc="long-utterance stress B=16 T=1000 U=200 V=4232 D=512 H=512 fp32"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), hbm=float(p["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
+
+
+def synth(w, seed, device=None, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    B, T, U, V, D = w["B"], w["T"], w["U"], w["V"], w["D"]
+    enc = torch.randn(B, T, D, generator=g)
+    pred = torch.randn(B, U + 1, D, generator=g)
+    labels = torch.randint(1, V, (B, U), generator=g, dtype=torch.int32)
+    act_lens = torch.full((B,), T, dtype=torch.int32)
+    label_lens = torch.full((B,), U, dtype=torch.int32)
+    out = [enc, pred, labels, act_lens, label_lens]
+    if pin:
+        out = [t.pin_memory() for t in out]
+    if device is not None:
+        out = [t.to(device) for t in out]
+    return out
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        clocks, maxc, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clocks.append(float(f[0]))
+                maxc = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        load = [c for c, p in zip(clocks, power) if p > 300.0] or clocks
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": maxc,
+                "reasons": sorted(reasons), "samples": len(clocks), "power_w_max": max(power) if power else None}
+
+
+def cpu_port_step(w, B_s, seed=1234):
+    """One step of the reference's CPU path (oracle port) on B_s utterances of workload w; returns seconds."""
+    from oracle import joint_ref, rnnt_oracle
+    ws = dict(w, B=B_s)
+    enc, pred, labels, act_lens, label_lens = synth(ws, seed)
+    torch.manual_seed(seed)
+    joint = joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh")
+    crit = rnnt_oracle.RNNTLoss(blank=0)
+    enc.requires_grad_()
+    pred.requires_grad_()
+    t0 = time.perf_counter()
+    loss = crit(joint(enc[:, :, None], pred[:, None]), labels, act_lens, label_lens)
+    loss.backward()
+    float(loss)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(w, budget_s=12.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    t1 = cpu_port_step(w, 1)                       # warm-up + calibration on one utterance
+    B_s = int(max(1, min(w["B"], budget_s / 2 / max(t1, 1e-3))))
+    ts = [cpu_port_step(w, B_s) for _ in range(2)]
+    t = min(ts)
+    return {"value": B_s / t, "unit": "utt/s", "cores": cores, "kind": "port",
+            "sample": "%d utterances of the workload per step (T=%d U=%d V=%d H=%d), best of 2 steps, "
+                      "oracle/joint_ref.EspnetJointNetwork + oracle/rnnt_cpu.c (OpenMP)" %
+                      (B_s, w["T"], w["U"], w["V"], w["H"])}
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference and
+    its un-vendored warprnnt_pytorch dependency cannot travel to the GPU box), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t1 = cpu_port_step(w, 1)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    B_s = int(max(1, min(w["B"], budget / max(t1, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_port_step(w, B_s)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(w, B_s)
+    dt = time.perf_counter() - t0
+    val = B_s * args.steps / dt
+    sample = "%d utterances per step of %s" % (B_s, w["desc"])
+    print(json.dumps({
+        "impl": "reference", "metric": "joint+RNN-T loss fwd+bwd utterances/s", "value": val, "unit": "utt/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel table to stderr")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    args.warmup = max(args.warmup, 3)
+
+    import transformer_transducer_b200 as ttb
+    from transformer_transducer_b200 import functional as F
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(1234)
+    joint = ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh").to(dev)
+    model = joint
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(joint, device_ids=[local], gradient_as_bucket_view=True)
+    crit = ttb.RNNTLoss(blank=0, reduction="mean")
+    enc, pred, labels, act_lens, label_lens = synth(w, 1234 + rank, device=dev)
+    enc.requires_grad_()
+    pred.requires_grad_()
+    host = synth(w, 1234 + rank, pin=True)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def step_resident():
+        for p_ in joint.parameters():
+            p_.grad = None
+        enc.grad = None
+        pred.grad = None
+        loss = crit(model(enc[:, :, None], pred[:, None]), labels, act_lens, label_lens)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        for p_ in joint.parameters():
+            p_.grad = None
+        e, p_, lab, al, ll = [t.to(dev, non_blocking=True) for t in host]
+        e.requires_grad_()
+        p_.requires_grad_()
+        loss = crit(model(e[:, :, None], p_[:, None]), lab, al, ll)
+        loss.backward()
+        return float(loss)          # device -> host read of the step's result
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    F.PROFILE = prof = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    F.PROFILE = None
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+
+    # end-to-end through the public API with host buffers (H2D of the inputs + D2H of the loss every step)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+
+    # per-kernel table from the events recorded inside the timed region
+    per = {}
+    launches = 0
+    for name, e0, e1, nk in prof:
+        per.setdefault(name, []).append(e0.elapsed_time(e1))
+        launches += nk
+    table = {k: {"calls": len(v), "avg_ms": sum(v) / len(v)} for k, v in per.items()}
+    M = w["B"] * w["T"] * (w["U"] + 1)
+    unit_flops = 2.0 * M * w["H"] * w["V"]           # one M x H x V contraction (F = 3 of these)
+    pk = peaks()
+    dom = max((k for k in table if k.startswith("ttx_joint_")), key=lambda k: table[k]["avg_ms"])
+    dom_ms = table[dom]["avg_ms"]
+    achieved = unit_flops / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_bytes.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    step_ms = ms / args.steps
+    out = {
+        "metric": "joint+RNN-T loss fwd+bwd utterances/s",
+        "value": world * w["B"] * args.steps / (ms * 1e-3), "unit": "utt/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 tensor-core operands, f32 accumulate/softmax/lattice (fp32 variant)",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "global_batch": world * w["B"], "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (A16 %.2f GB + dA %.2f GB) exceeds the 126 MB L2; no explicit flush" %
+                         (M * w["H"] * 2 / 1e9, M * w["H"] * 4 / 1e9)},
+        "e2e": {"value": world * w["B"] * args.steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tflops"], "traffic": traffic, "kernel_ms": dom_ms,
+                     "algorithmic_flops_per_launch": unit_flops, "peak_source": pk["source"]},
+        "roofline_step": {"algorithmic_flops": 3 * unit_flops, "achieved": 3 * unit_flops / (step_ms * 1e-3) / 1e12,
+                          "frac": 3 * unit_flops / (step_ms * 1e-3) / 1e12 / pk["tflops"]},
+        "kernels": table,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w)
+        if args.breakdown:
+            for k, v in sorted(table.items(), key=lambda kv: -kv[1]["avg_ms"]):
+                print("%-28s %8.3f ms x %d" % (k, v["avg_ms"], v["calls"]), file=sys.stderr)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,16 +63,16 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, cons
                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                       int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream);
 
-/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice.
- * costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
+/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried in float64
+ * (alpha / beta: one double per row).  costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
 int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
-                        const int32_t* label_lens, const int32_t* meta, int B, int U1, float* alpha, float* beta,
-                        float* costs, float* ll_beta, int device, void* stream);
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, double* alpha, double* beta,
+                        float* costs, double* ll_beta, int device, void* stream);
 
 /* Per-row gradient coefficients rowmeta[row] = {lse, rb, rl, gamma * grad_costs[b] / gmax} (float4),
  * gmax = max_b |grad_costs[b]| stored in scal[2]. */
-int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const float* alpha,
-                    const float* beta, const float* ll_beta, const float* grad_costs, float* scal,
+int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,
+                    const double* beta, const double* ll_beta, const float* grad_costs, float* scal,
                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
                     int64_t n_tiles_ub, void* rowmeta, int device, void* stream);
 

@@ -25,6 +25,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(_build.build())
         _lib.oracle_rnnt_f32.restype = ctypes.c_int
+        _lib.oracle_rnnt_f64.restype = ctypes.c_int
         _lib.oracle_lattice_f64.restype = ctypes.c_int
     return _lib
 
@@ -56,13 +57,15 @@ class _RNNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, log_probs, labels, act_lens, label_lens, blank, reduction):
         certify_inputs(log_probs, labels, act_lens, label_lens)
-        lp = log_probs.detach().contiguous().float()
+        f64 = log_probs.dtype == torch.float64          # float64 in -> float64 arbiter; otherwise upstream's float32
+        lp = log_probs.detach().contiguous().to(torch.float64 if f64 else torch.float32)
         B, T, U1, V = lp.shape
         labels_c = labels.contiguous()
-        costs = torch.zeros(B, dtype=torch.float32)
+        costs = torch.zeros(B, dtype=lp.dtype)
         grads = torch.empty_like(lp)
-        rc = lib().oracle_rnnt_f32(_p(lp), _p(labels_c), _p(act_lens.contiguous()), _p(label_lens.contiguous()),
-                                   B, T, U1, V, int(blank), _p(costs), _p(grads))
+        fn = lib().oracle_rnnt_f64 if f64 else lib().oracle_rnnt_f32
+        rc = fn(_p(lp), _p(labels_c), _p(act_lens.contiguous()), _p(label_lens.contiguous()),
+                B, T, U1, V, int(blank), _p(costs), _p(grads))
         if rc:
             raise ValueError("bad lengths for utterance %d" % (rc - 1))
         if reduction in ("sum", "mean"):

@@ -121,8 +121,9 @@ def run(stage, B, T, U, V, H):
     lpl_want = torch.where(valid_lab, mm["lpl"], torch.full_like(mm["lpl"], float("nan")))
     fail |= report("lp_label", lpl, compact(mh, lpl_want, al, ll, rows), tol)
 
-    alpha, beta = f32(rows), f32(rows)
-    costs, llb = f32(B), f32(B)
+    alpha = torch.empty(rows, dtype=torch.float64, device=dev)
+    beta = torch.empty(rows, dtype=torch.float64, device=dev)
+    costs, llb = f32(B), torch.empty(B, dtype=torch.float64, device=dev)
     _lib.check(lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(ald), _p(lld), _p(meta), B, U1, _p(alpha), _p(beta),
                                        _p(costs), _p(llb), 0, st), "lattice")
     torch.cuda.synchronize()

@@ -1,0 +1,175 @@
+"""CPU-side tests of the drop-in boundary and host logic (no GPU compute)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import transformer_transducer_b200 as ttb
+import warprnnt_pytorch
+from oracle import ref_import, rnnt_oracle
+from transformer_transducer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _i32(x):
+    return torch.as_tensor(x, dtype=torch.int32)
+
+
+def test_library_exports_every_declared_symbol():
+    ttb.build()
+    header = open(os.path.join(ROOT, "include", "ttx.h")).read()
+    declared = set(re.findall(r"\b(ttx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib = _lib.get()
+    assert lib.ttx_version() == 1
+    assert [h for h in range(32, 1100, 32) if lib.ttx_supported_h(h)] == [64, 128, 192, 256, 384, 512]
+    assert lib.ttx_tiles_upper_bound(32, 400, 41) == 32 * 129
+    assert lib.ttx_meta_ints(32, 32 * 129) == 4 + 33 + 32 * 129
+
+
+def test_c_abi_argument_errors_without_gpu():
+    lib = _lib.get()
+    rc = lib.ttx_joint_lse_fwd(None, None, None, None, None, None, 1, 512, 10, 0, 0, None, None, None, 0, None)
+    assert rc == 1 and b"null pointer" in lib.ttx_last_error()
+    rc = lib.ttx_prepare(None, None, 1, 1, 1, 1, None, 0, None)
+    assert rc == 1
+
+
+def test_warprnnt_pytorch_surface():
+    assert warprnnt_pytorch.RNNTLoss is ttb.RNNTLoss and warprnnt_pytorch.rnnt_loss is ttb.rnnt_loss
+    crit = warprnnt_pytorch.RNNTLoss()
+    assert crit.blank == 0 and crit.reduction == "mean"
+    with pytest.raises(ValueError):
+        warprnnt_pytorch.RNNTLoss(reduction="avg")
+    acts = torch.zeros(2, 3, 2, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(acts, _i32([[1], [1]]), _i32([3, 2]), _i32([1, 1]))
+    with pytest.raises(NotImplementedError):
+        ttb.rnnt_loss(acts, _i32([[1], [1]]), _i32([3, 2]), _i32([1, 1]), fastemit_lambda=0.1)
+
+
+def test_certify_inputs_matches_upstream_conventions():
+    acts = torch.zeros(2, 3, 2, 5)
+    lab, al, ll = _i32([[1], [1]]), _i32([3, 2]), _i32([1, 1])
+    ttb.certify_inputs(acts, lab, al, ll)
+    rnnt_oracle.certify_inputs(acts, lab, al, ll)
+    for bad, exc in (((acts, lab.long(), al, ll), TypeError), ((acts, lab, al.long(), ll), TypeError),
+                     ((acts[0], lab, al, ll), ValueError), ((acts, lab[0], al, ll), ValueError),
+                     ((acts, lab, _i32([3]), ll), ValueError), ((acts, lab, _i32([2, 2]), ll), ValueError),
+                     ((acts, lab, al, _i32([0, 0])), ValueError)):
+        with pytest.raises(exc):
+            ttb.certify_inputs(*bad)
+        with pytest.raises(exc):
+            rnnt_oracle.certify_inputs(*bad)
+
+
+def _load_sd(module, g):
+    module.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd_")})
+
+
+def test_jointnet_dense_fallback_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tt_joint.npz"))
+    m = ttb.JointNet(48, 40, 23)
+    assert list(m.state_dict()) == ["forward_layer.weight", "forward_layer.bias", "project_layer.weight",
+                                    "project_layer.bias"]
+    _load_sd(m, g)
+    out = m(torch.tensor(g["enc"]), torch.tensor(g["dec"]))
+    assert type(out) is torch.Tensor
+    np.testing.assert_allclose(out.detach().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    out1 = m(torch.tensor(g["enc"])[1, 2].view(-1), torch.tensor(g["dec"])[1, 3].view(-1))  # decode call, tt/model.py:77
+    np.testing.assert_allclose(out1.detach().numpy(), g["logits_1d"], rtol=1e-5, atol=1e-6)
+
+
+def test_jointnetwork_dense_fallback_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "espnet_joint.npz"))
+    m = ttb.JointNetwork(19, 24, 20, 32, "tanh")
+    assert list(m.state_dict()) == ["lin_enc.weight", "lin_enc.bias", "lin_dec.weight", "lin_out.weight",
+                                    "lin_out.bias"]
+    _load_sd(m, g)
+    out = m(torch.tensor(g["h_enc"]), torch.tensor(g["h_dec"]))
+    np.testing.assert_allclose(out.detach().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    for act in ("relu", "hardtanh", "selu", "swish"):
+        ttb.JointNetwork(19, 24, 20, 32, act)(torch.tensor(g["h_enc"]), torch.tensor(g["h_dec"]))
+
+
+def test_lazy_handle_looks_like_the_logits():
+    torch.manual_seed(0)
+    ep, pp = torch.randn(2, 5, 16, requires_grad=True), torch.randn(2, 3, 16, requires_grad=True)
+    lin = torch.nn.Linear(16, 7)
+    h = ttb.LazyJointLogits(ep, pp, lin.weight, lin.bias)
+    assert tuple(h.shape) == (2, 5, 3, 7) and h.dim() == 4 and h.size(3) == 7 and h.dtype == torch.float32
+    assert h.is_contiguous() and h.contiguous() is h and not h.is_cuda
+    assert h.to(dtype=torch.float32) is h and h.float() is h
+    hb = h.to(dtype=torch.bfloat16)                       # transducer/loss.py:57-60 style cast keeps it lazy
+    assert isinstance(hb, ttb.LazyJointLogits) and hb.dtype == torch.bfloat16 and hb.parts[0] is ep
+    dense = torch.nn.functional.linear(torch.tanh(ep[:, :, None] + pp[:, None]), lin.weight, lin.bias)
+    assert torch.allclose(h.materialize(), dense)
+    assert torch.allclose(h + 1, dense + 1) and torch.equal(h.argmax(-1), dense.argmax(-1))
+    os.environ["TTX_MATERIALIZE_LIMIT_GB"] = "0.0000001"
+    try:
+        with pytest.raises(RuntimeError, match="refusing to materialise"):
+            h.materialize()
+    finally:
+        del os.environ["TTX_MATERIALIZE_LIMIT_GB"]
+    h.materialize().sum().backward()                      # materialisation is differentiable w.r.t. the parts
+    assert ep.grad is not None and lin.weight.grad is not None
+
+
+def test_algorithm_model_with_rounding_meets_tolerances_against_oracle():
+    """The kernel decomposition + fp16 operand rounding, modelled on CPU, vs the oracle: <=1e-4 loss, <=1e-3 grads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import algo_model
+    torch.manual_seed(0)
+    B, T, U, V, H = 3, 14, 5, 300, 128
+    E = (torch.randn(B, T, H) * 0.6).requires_grad_()
+    P = (torch.randn(B, U + 1, H) * 0.6).requires_grad_()
+    lo = torch.nn.Linear(H, V)
+    W, b = lo.weight.detach().clone().requires_grad_(), lo.bias.detach().clone().requires_grad_()
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    al, ll = _i32([T, T - 6, 1]), _i32([U, U - 2, 0])
+    labels[1, U - 2:] = -1
+    labels[2, :] = -1
+    gc = torch.tensor([0.5, 1.0, 0.25])
+    z = torch.tanh(E[:, :, None] + P[:, None]) @ W.T + b
+    c = rnnt_oracle.rnnt_loss(z, labels, al, ll, 0, "none")
+    (c * gc).sum().backward()
+    rel = lambda a, r: float((a - r.double()).norm() / r.double().norm())  # noqa: E731
+    for emulate, tl, tg in ((False, 1e-6, 5e-5), (True, 1e-4, 1e-3)):
+        m = algo_model.forward_backward(E.detach(), P.detach(), W.detach(), b.detach(), labels, al, ll, gc,
+                                        emulate=emulate)
+        assert float(((m["costs"] - c.detach()) / c.detach()).abs().max()) < tl
+        for k, ref in (("dEproj", E.grad), ("dPproj", P.grad), ("dW", W.grad), ("db", b.grad)):
+            assert rel(m[k], ref) < tg, (emulate, k, rel(m[k], ref))
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree only exists in the build container")
+def test_install_rebinds_reference_classes_and_model_builds_unchanged():
+    tt_model = ref_import.tt_model()
+    ref_import.espnet_joint_module()
+    orig_tt, orig_es = tt_model.JointNet, sys.modules["espnet.nets.pytorch_backend.transducer.joint_network"].JointNetwork
+    try:
+        done = ttb.install()
+        assert "tt.model.JointNet" in done and tt_model.JointNet is ttb.JointNet
+        import yaml
+        from tt.utils import AttrDict
+        cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "aishell.yaml"))))
+        cfg.model.enc.n_layer = 1
+        cfg.model.dec.n_layer = 1
+        cfg.model.vocab_size = 37
+        model = tt_model.Transducer(cfg.model)            # unmodified reference assembly, our joint inside
+        assert isinstance(model.joint, ttb.JointNet)
+        logits = model(torch.randn(2, 12, 512), torch.randint(1, 37, (2, 4)))
+        assert logits.shape == (2, 12, 5, 37)
+        import tt_espnet.model as tem
+        assert tem.JointNetwork is orig_es or tem.JointNetwork is ttb.JointNetwork
+    finally:
+        tt_model.JointNet = orig_tt
+        sys.modules["espnet.nets.pytorch_backend.transducer.joint_network"].JointNetwork = orig_es

@@ -1,0 +1,278 @@
+"""GPU parity gate (-m gpu): the CUDA path through the public drop-in API vs the CPU oracle and the committed
+golden fixtures.  Tolerances (BASELINE.json north_star): fp32 variant <= 1e-4 relative on per-utterance loss,
+<= 1e-3 relative (L2 per tensor) on gradients; bf16-input variant stated separately below; exact zeros outside
+the ragged region.  Nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import transformer_transducer_b200 as ttb
+from oracle import joint_ref, rnnt_oracle
+from transformer_transducer_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
+BF16_LOSS_TOL, BF16_GRAD_TOL = 2e-3, 1.5e-2     # bf16-input variant, vs the oracle fed the same bf16-rounded inputs
+
+
+def _i32(x, dev="cpu"):
+    return torch.as_tensor(x, dtype=torch.int32, device=dev)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_native_library_is_loaded():
+    lib = _lib.get()
+    assert lib.ttx_version() == 1
+    assert any("libttx.so" in l for l in open("/proc/self/maps"))
+
+
+# ----------------------------------------------------------------------------- dense-logits entry (RNNTLoss on acts)
+def test_known_answer_vector_on_gpu(golden_dir):
+    k = json.load(open(os.path.join(golden_dir, "warp_transducer_kat.json")))
+    acts = torch.tensor(k["acts"], device=DEV, requires_grad=True)
+    c = ttb.rnnt_loss(acts, _i32(k["labels"], DEV), _i32(k["act_lens"], DEV), _i32(k["label_lens"], DEV), 0, "none")
+    c.sum().backward()
+    assert abs(float(c[0]) - k["cost_upstream"]) < 5e-6
+    np.testing.assert_allclose(acts.grad.cpu().numpy(), np.array(k["grads_upstream"], dtype=np.float32), atol=2e-6)
+
+
+def test_ragged_fixture_on_gpu_exact_zero_outside(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ragged_loss.npz"))
+    logits = torch.tensor(g["logits"], device=DEV, requires_grad=True)
+    c = ttb.rnnt_loss(logits, _i32(g["labels"], DEV), _i32(g["act_lens"], DEV), _i32(g["label_lens"], DEV), 0, "none")
+    c.sum().backward()
+    np.testing.assert_allclose(c.detach().cpu().numpy(), g["costs"], rtol=LOSS_TOL)
+    assert rel(logits.grad, torch.tensor(g["grads"])) < GRAD_TOL
+    gr = logits.grad
+    assert gr[1, 6:].abs().max() == 0 and gr[1, :, 3:].abs().max() == 0      # t >= T_b, u > U_b
+    assert gr[2, 1:].abs().max() == 0 and gr[2, :, 1:].abs().max() == 0      # T_b = 1, U_b = 0
+
+
+def test_espnet_transloss_fixture_reductions_and_grad_output(golden_dir):
+    g = np.load(os.path.join(golden_dir, "espnet_transloss.npz"))
+    args = (_i32(g["target"], DEV), _i32(g["pred_len"], DEV), _i32(g["target_len"], DEV))
+    pred = torch.tensor(g["pred"], device=DEV, requires_grad=True)
+    loss = ttb.RNNTLoss(blank=0)(pred, *args)
+    assert loss.shape == (1,)
+    loss.backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], rtol=LOSS_TOL)
+    assert rel(pred.grad, torch.tensor(g["grad"])) < GRAD_TOL
+    none = ttb.rnnt_loss(pred, *args, reduction="none")
+    total = ttb.RNNTLoss(reduction="sum")(pred, *args)
+    assert none.shape == (2,) and total.shape == (1,)
+    assert torch.allclose(total, none.sum().view(1), rtol=1e-6) and torch.allclose(loss, total / 2, rtol=1e-6)
+    p2 = torch.tensor(g["pred"], device=DEV, requires_grad=True)
+    (ttb.RNNTLoss(blank=0)(p2, *args) * 3.0).sum().backward()           # backward scales by grad_output
+    assert rel(p2.grad, 3.0 * torch.tensor(g["grad"])) < GRAD_TOL
+
+
+def test_error_conventions_on_gpu():
+    acts = torch.zeros(2, 3, 2, 5, device=DEV)
+    lab, al, ll = _i32([[1], [1]], DEV), _i32([3, 2], DEV), _i32([1, 1], DEV)
+    ttb.rnnt_loss(acts, lab, al, ll)
+    with pytest.raises(TypeError):
+        ttb.rnnt_loss(acts, lab.long(), al, ll)
+    with pytest.raises(ValueError, match="Input length mismatch"):
+        ttb.rnnt_loss(acts, lab, _i32([2, 2], DEV), ll)
+    with pytest.raises(ValueError, match="Output length mismatch"):
+        ttb.rnnt_loss(acts, lab, al, _i32([0, 0], DEV))
+    with pytest.raises(ValueError):
+        ttb.rnnt_loss(acts, lab, al, ll, reduction="avg")
+
+
+# ----------------------------------------------------------------------------- fused path vs oracle
+def _espnet_case(B, T, U, V, D, H, act_lens, label_lens, seed=0, dtype=torch.float32):
+    torch.manual_seed(seed)
+    ref = joint_ref.EspnetJointNetwork(V, D, D, H, "tanh")
+    mine = ttb.JointNetwork(V, D, D, H, "tanh")
+    mine.load_state_dict(ref.state_dict())
+    enc, pred = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    for i, n in enumerate(label_lens):
+        labels[i, n:] = -1                      # tt/dataset.py:46-48 pads with ignore_id = -1
+    return ref, mine, enc, pred, labels, _i32(act_lens), _i32(label_lens)
+
+
+def _run_pair(ref, mine, enc, pred, labels, al, ll, weights=None, dtype=torch.float32, arbiter64=False):
+    mine = mine.to(DEV).to(dtype)
+    if dtype != torch.float32:                  # oracle sees the same rounded parameters / inputs
+        ref.load_state_dict({k: v.float().cpu() for k, v in mine.state_dict().items()})
+        enc, pred = enc.to(dtype).float(), pred.to(dtype).float()
+    if arbiter64:                               # float64 oracle (oracle_rnnt_f64): see test_fused_long_utterance_lattice
+        ref = ref.double()
+    e0 = enc.clone().to(torch.float64 if arbiter64 else torch.float32).requires_grad_()
+    p0 = pred.clone().to(e0.dtype).requires_grad_()
+    want = rnnt_oracle.rnnt_loss(ref(e0[:, :, None], p0[:, None]), labels, al, ll, 0, "none")
+    wts = torch.ones(len(al)) if weights is None else weights
+    (want * wts).sum().backward()
+    e1 = enc.to(DEV).to(dtype).requires_grad_()
+    p1 = pred.to(DEV).to(dtype).requires_grad_()
+    z = mine(e1[:, :, None], p1[:, None])
+    assert isinstance(z, ttb.LazyJointLogits)
+    got = ttb.rnnt_loss(z, labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")
+    (got.float() * wts.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    errs = {"loss": float(((got.double().cpu() - want.detach().double()) / want.detach().double()).abs().max()),
+            "d_enc": rel(e1.grad, e0.grad), "d_pred": rel(p1.grad, p0.grad)}
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        errs["d_" + n] = rel(a.grad, b.grad)
+    return errs, (e1, p1, got)
+
+
+def _check(errs, lt=LOSS_TOL, gt=GRAD_TOL):
+    assert errs["loss"] < lt, errs
+    assert all(v < gt for k, v in errs.items() if k != "loss"), errs
+
+
+@pytest.mark.parametrize("H", [64, 128, 192, 256, 384, 512])
+def test_fused_espnet_joint_matches_oracle_all_widths(H):
+    case = _espnet_case(3, 33, 7, 300, 64, H, [33, 29, 9], [7, 4, 0], seed=H)
+    errs, _ = _run_pair(*case, weights=torch.tensor([1.0, 0.5, 2.0]))
+    _check(errs)
+
+
+def test_fused_edge_lengths_t1_u0_and_zero_grads_outside():
+    case = _espnet_case(4, 20, 5, 150, 32, 128, [20, 1, 1, 7], [5, 0, 3, 0], seed=3)
+    errs, (e1, p1, _) = _run_pair(*case)
+    _check(errs)
+    assert e1.grad[1, 1:].abs().max() == 0 and p1.grad[1, 1:].abs().max() == 0      # T_b = 1, U_b = 0
+    assert e1.grad[3, 7:].abs().max() == 0 and p1.grad[2, 4:].abs().max() == 0
+
+
+def test_fused_microbench_dims_small_batch():
+    """configs[1] dims (D=H=512, V=4232) at a batch the CPU oracle finishes in seconds."""
+    case = _espnet_case(2, 60, 12, 4232, 512, 512, [60, 47], [12, 9], seed=5)
+    errs, _ = _run_pair(*case)
+    _check(errs)
+
+
+def test_fused_long_utterance_lattice():
+    """configs[3]-like lattice extents (T=1000, U=200) with a small vocabulary so the oracle stays fast.
+
+    At this lattice size alpha/beta reach ~6e3 and the reference's float32 recursion itself is only good to
+    ~1.1e-3 on gradients (float32 vs float64 run of the same oracle, checked below), so the arbiter here is the
+    float64 oracle; the CUDA lattice carries alpha/beta in float64 for the same reason."""
+    case = _espnet_case(1, 1000, 200, 130, 32, 64, [1000], [200], seed=6)
+    errs, _ = _run_pair(*case, arbiter64=True)
+    _check(errs)
+    ref, _, enc, pred, labels, al, ll = _espnet_case(1, 1000, 200, 130, 32, 64, [1000], [200], seed=6)
+    z = ref(enc[:, :, None], pred[:, None]).detach()
+    z32, z64 = z.clone().requires_grad_(), z.double().requires_grad_()
+    rnnt_oracle.rnnt_loss(z32, labels, al, ll, 0, "none").sum().backward()
+    rnnt_oracle.rnnt_loss(z64, labels, al, ll, 0, "none").sum().backward()
+    assert 2e-4 < rel(z32.grad, z64.grad) < 5e-3        # the float32 reference's own rounding at this size
+
+
+def test_fused_tt_jointnet_split_first_layer_matches_oracle():
+    torch.manual_seed(7)
+    B, T, U, V, D, H = 2, 25, 6, 211, 48, 256
+    ref = joint_ref.TTJointNet(2 * D, H, V)
+    mine = ttb.JointNet(2 * D, H, V)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    enc, dec = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    al, ll = _i32([T, T - 3]), _i32([U, U - 1])
+    e0, d0 = enc.clone().requires_grad_(), dec.clone().requires_grad_()
+    want = rnnt_oracle.RNNTLoss()(ref(e0, d0), labels, al, ll)          # train.py:51-53
+    want.backward()
+    e1, d1 = enc.to(DEV).requires_grad_(), dec.to(DEV).requires_grad_()
+    z = mine(e1, d1)
+    assert isinstance(z, ttb.LazyJointLogits) and tuple(z.shape) == (B, T, U + 1, V)
+    got = ttb.RNNTLoss()(z, labels.to(DEV), al.to(DEV), ll.to(DEV))
+    got.backward()
+    assert abs(float(got) - float(want)) / float(want) < LOSS_TOL
+    assert rel(e1.grad, e0.grad) < GRAD_TOL and rel(d1.grad, d0.grad) < GRAD_TOL
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert rel(a.grad, b.grad) < GRAD_TOL, n
+
+
+def test_unsupported_width_uses_dense_entry_and_matches_oracle():
+    """aishell.yaml's joint width 1024 is outside the fused kernels: the module returns dense logits and the loss
+    runs through the dense-logits CUDA entry."""
+    torch.manual_seed(8)
+    B, T, U, V, D, H = 2, 12, 4, 97, 32, 1024
+    ref = joint_ref.TTJointNet(2 * D, H, V)
+    mine = ttb.JointNet(2 * D, H, V)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    enc, dec = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    al, ll = _i32([T, T - 2]), _i32([U, U - 2])
+    want = rnnt_oracle.RNNTLoss()(ref(enc, dec), labels, al, ll)
+    want.backward()
+    z = mine(enc.to(DEV), dec.to(DEV))
+    assert type(z) is torch.Tensor
+    got = ttb.RNNTLoss()(z, labels.to(DEV), al.to(DEV), ll.to(DEV))
+    got.backward()
+    assert abs(float(got) - float(want)) / float(want) < LOSS_TOL
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert rel(a.grad, b.grad) < GRAD_TOL, n
+
+
+def test_bf16_input_variant_stated_tolerance():
+    case = _espnet_case(2, 40, 8, 500, 64, 256, [40, 31], [8, 5], seed=9)
+    errs, (_, _, got) = _run_pair(*case, dtype=torch.bfloat16)
+    _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
+
+
+def test_c_abi_rejects_unsupported_width_with_message():
+    lib = _lib.get()
+    x = torch.zeros(16, device=DEV)
+    p = lambda t: t.data_ptr()  # noqa: E731
+    rc = lib.ttx_joint_lse_fwd(p(x), p(x), p(x), p(x), p(x), p(x), 1, 1024, 10, 0, 0, p(x), p(x), p(x), 0, None)
+    assert rc == 1 and b"not supported" in lib.ttx_last_error()
+
+
+# ----------------------------------------------------------------------------- full-size properties (configs[1])
+def test_full_size_properties_cfg2():
+    """B=32, T=400, U=40, V=4232, D=H=512 -- too big for the CPU oracle, so size-independent properties:
+    fused == dense-entry on a sub-batch, duplicate utterances give identical costs, gradients are linear in
+    grad_output, alpha- and beta-side log-likelihoods agree, padding gets exact zeros."""
+    torch.manual_seed(10)
+    B, T, U, V, D, H = 32, 400, 40, 4232, 512, 512
+    joint = ttb.JointNetwork(V, D, D, H, "tanh").to(DEV)
+    enc, pred = torch.randn(B, T, D, device=DEV), torch.randn(B, U + 1, D, device=DEV)
+    enc[1], pred[1] = enc[0], pred[0]
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32, device=DEV)
+    labels[1] = labels[0]
+    al = torch.full((B,), T, dtype=torch.int32, device=DEV)
+    ll = torch.full((B,), U, dtype=torch.int32, device=DEV)
+    al[2], ll[2] = 123, 17
+
+    def run(scale):
+        e, p_ = enc.clone().requires_grad_(), pred.clone().requires_grad_()
+        joint.zero_grad()
+        c = ttb.rnnt_loss(joint(e[:, :, None], p_[:, None]), labels, al, ll, 0, "none")
+        (c * scale).sum().backward()
+        return c.detach(), e.grad, p_.grad, joint.lin_out.weight.grad.clone()
+
+    c1, ge1, gp1, gw1 = run(1.0)
+    c2, ge2, gp2, gw2 = run(0.25)
+    assert torch.isfinite(c1).all() and float(c1.min()) > 0
+    assert float(c1[0]) == float(c1[1])
+    assert torch.equal(c1, c2)
+    assert rel(ge2, 0.25 * ge1) < 1e-5 and rel(gw2, 0.25 * gw1) < 1e-4
+    assert ge1[2, 123:].abs().max() == 0 and gp1[2, 18:].abs().max() == 0
+    # sub-batch through the dense entry (logits materialised by torch on the GPU: 4 x 400 x 41 x 4232 fp32 = 1.1 GB)
+    sub = slice(0, 4)
+    e, p_ = enc[sub].clone().requires_grad_(), pred[sub].clone().requires_grad_()
+    joint.zero_grad()
+    z = joint.lin_out(torch.tanh(joint.lin_enc(e)[:, :, None] + joint.lin_dec(p_)[:, None]))
+    cd = ttb.rnnt_loss(z, labels[sub], al[sub].clamp(max=T), ll[sub], 0, "none")
+    cd.sum().backward()
+    assert float(((cd - c1[sub]) / cd).abs().max()) < LOSS_TOL
+    e3, p3 = enc[sub].clone().requires_grad_(), pred[sub].clone().requires_grad_()
+    gw_dense = joint.lin_out.weight.grad.clone()
+    joint.zero_grad()
+    ttb.rnnt_loss(joint(e3[:, :, None], p3[:, None]), labels[sub], al[sub], ll[sub], 0, "none").sum().backward()
+    assert rel(e3.grad, e.grad) < GRAD_TOL and rel(p3.grad, p_.grad) < GRAD_TOL
+    assert rel(joint.lin_out.weight.grad, gw_dense) < GRAD_TOL

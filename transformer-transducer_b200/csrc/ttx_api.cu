@@ -21,9 +21,9 @@ int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
 int launch_cast_w(const float*, int, int, int, bool, float*, void*, cudaStream_t);
 int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
                      int, int, bool, void*, int*, cudaStream_t);
-int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, float*, float*, float*,
-                   float*, cudaStream_t);
-int launch_grad_prep(const float*, const float*, const float*, const float*, const float*, const float*,
+int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, double*, double*, float*,
+                   double*, cudaStream_t);
+int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
                      const float*, float*, const int*, const int*, const int*, int, int, float4*, cudaStream_t);
 int launch_reduce(const float*, const float*, const float*, const int*, const int*, const int*, int, int, int, int,
                   float*, float*, cudaStream_t);
@@ -120,8 +120,8 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, cons
 }
 
 int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
-                        const int32_t* label_lens, const int32_t* meta, int B, int U1, float* alpha, float* beta,
-                        float* costs, float* ll_beta, int device, void* stream) {
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, double* alpha, double* beta,
+                        float* costs, double* ll_beta, int device, void* stream) {
     TTX_REQUIRE(lp_blank && lp_label && act_lens && label_lens && meta && alpha && beta && costs && ll_beta,
                 "ttx_lattice_fwd_bwd: null pointer");
     TTX_ENTER(device);
@@ -129,8 +129,8 @@ int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int3
                           (cudaStream_t)stream);
 }
 
-int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const float* alpha,
-                    const float* beta, const float* ll_beta, const float* grad_costs, float* scal,
+int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,
+                    const double* beta, const double* ll_beta, const float* grad_costs, float* scal,
                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
                     int64_t n_tiles_ub, void* rowmeta, int device, void* stream) {
     TTX_REQUIRE(lse && lp_blank && lp_label && alpha && beta && ll_beta && grad_costs && scal && rowmeta,

@@ -151,10 +151,12 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
 }
 
 // ------------------------------------------------------------------------------------------- lattice
-__device__ __forceinline__ float log_add(float a, float b) {
-    const float mx = fmaxf(a, b), mn = fminf(a, b);
+// The recursion runs in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
+// ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).
+__device__ __forceinline__ double log_add(double a, double b) {
+    const double mx = fmax(a, b), mn = fmin(a, b);
     if (mx == -INFINITY) return -INFINITY;
-    return mx + log1pf(expf(mn - mx));
+    return mx + log1p(exp(mn - mx));
 }
 
 // grid = 2B: block b computes alpha of utterance b, block B + b computes beta.  Thread u owns column u and
@@ -162,9 +164,9 @@ __device__ __forceinline__ float log_add(float a, float b) {
 // (warp-transducer semantics; called train.py:53.)
 __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __restrict__ lpl,
                                const int* __restrict__ act_lens, const int* __restrict__ label_lens,
-                               const int* __restrict__ meta, int B, float* __restrict__ alpha,
-                               float* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_beta) {
-    extern __shared__ float xch[];  // 2 x blockDim.x
+                               const int* __restrict__ meta, int B, double* __restrict__ alpha,
+                               double* __restrict__ beta, float* __restrict__ costs, double* __restrict__ ll_beta) {
+    extern __shared__ double xch[];  // 2 x blockDim.x
     if (meta[1] != 0) return;
     const bool is_beta = blockIdx.x >= (unsigned)B;
     const int b = is_beta ? blockIdx.x - B : blockIdx.x;
@@ -173,7 +175,7 @@ __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __res
     const int u = threadIdx.x;
     const int nd = T + U1 - 1;
     const bool active = u < U1;
-    float self = -INFINITY;  // my column's value on the previous diagonal
+    double self = -INFINITY;  // my column's value on the previous diagonal
     constexpr int PD = 4;    // prefetch distance in diagonals
     float pf_b[PD], pf_l[PD];
     // operand of diagonal d for column u:  alpha: t = d - u;  beta: t = T-1 - (d - (U1-1-u))
@@ -202,9 +204,9 @@ __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __res
             if (d >= nd) break;
             const float xb = pf_b[i], xl = pf_l[i];
             fetch(d + PD, pf_b[i], pf_l[i]);
-            float* cur = xch + (d & 1) * blockDim.x;
-            const float* prev = xch + ((d & 1) ^ 1) * blockDim.x;
-            float val = -INFINITY;
+            double* cur = xch + (d & 1) * blockDim.x;
+            const double* prev = xch + ((d & 1) ^ 1) * blockDim.x;
+            double val = -INFINITY;
             bool on = false;
             int t = 0;
             if (active) {
@@ -213,18 +215,18 @@ __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __res
             }
             if (on) {
                 if (!is_beta) {
-                    if (t == 0 && u == 0) val = 0.f;
+                    if (t == 0 && u == 0) val = 0.0;
                     else {
-                        const float from_t = (t > 0) ? self + xb : -INFINITY;
-                        const float from_u = (u > 0) ? prev[u - 1] + xl : -INFINITY;
+                        const double from_t = (t > 0) ? self + (double)xb : -INFINITY;
+                        const double from_u = (u > 0) ? prev[u - 1] + (double)xl : -INFINITY;
                         val = log_add(from_t, from_u);
                     }
                     alpha[base + (size_t)t * U1 + u] = val;
                 } else {
-                    if (t == T - 1 && u == U1 - 1) val = xb;
+                    if (t == T - 1 && u == U1 - 1) val = (double)xb;
                     else {
-                        const float from_t = (t < T - 1) ? self + xb : -INFINITY;
-                        const float from_u = (u < U1 - 1) ? prev[u + 1] + xl : -INFINITY;
+                        const double from_t = (t < T - 1) ? self + (double)xb : -INFINITY;
+                        const double from_u = (u < U1 - 1) ? prev[u + 1] + (double)xl : -INFINITY;
                         val = log_add(from_t, from_u);
                     }
                     beta[base + (size_t)t * U1 + u] = val;
@@ -234,7 +236,7 @@ __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __res
             cur[u] = val;
             __syncthreads();
             if (d == nd - 1 && on) {
-                if (!is_beta) costs[b] = -(val + __ldg(lpb + base + (size_t)(T - 1) * U1 + (U1 - 1)));
+                if (!is_beta) costs[b] = (float)-(val + (double)__ldg(lpb + base + (size_t)(T - 1) * U1 + (U1 - 1)));
                 else ll_beta[b] = val;
             }
         }
@@ -258,8 +260,8 @@ __global__ void gmax_kernel(const float* __restrict__ grad_costs, int B, float* 
 // rowmeta[row] = {lse, rb, rl, gamma * g_b / gmax}: rb / rl are the posteriors of leaving the cell by a
 // blank / label arc given that the cell is visited; dL/dz(row, v) = g_b * gamma * (softmax_v - rb[v==blank] - rl[v==label]).
 __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __restrict__ lpb,
-                                 const float* __restrict__ lpl, const float* __restrict__ alpha,
-                                 const float* __restrict__ beta, const float* __restrict__ ll_beta,
+                                 const float* __restrict__ lpl, const double* __restrict__ alpha,
+                                 const double* __restrict__ beta, const double* __restrict__ ll_beta,
                                  const float* __restrict__ grad_costs, const float* __restrict__ scal,
                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,
                                  const int* __restrict__ meta, int B, float4* __restrict__ rowmeta) {
@@ -272,13 +274,13 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
     float4 out = make_float4(INFINITY, 0.f, 0.f, 0.f);
     if (r < T * U1) {
         const int t = r / U1, u = r - t * U1;
-        const float ll = ll_beta[b];
-        const float be = beta[base + r];
-        const float gam = __expf(alpha[base + r] + be - ll);
+        const double ll = ll_beta[b];
+        const double be = beta[base + r];
+        const float gam = expf((float)(alpha[base + r] + be - ll));
         float rb, rl = 0.f;
-        if (t < T - 1) rb = __expf(lpb[base + r] + beta[base + r + U1] - be);
+        if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[base + r + U1] - be));
         else rb = (u == U1 - 1) ? 1.f : 0.f;
-        if (u < U1 - 1) rl = __expf(lpl[base + r] + beta[base + r + 1] - be);
+        if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[base + r + 1] - be));
         out = make_float4(lse[base + r], rb, rl, gam * grad_costs[b] / scal[2]);
     }
     rowmeta[(size_t)tile * kTile + threadIdx.x] = out;
@@ -467,20 +469,20 @@ int launch_joint_act(const float* eproj, const float* pproj, const int* labels, 
 }
 
 int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, const int* label_lens, const int* meta,
-                   int B, int U1, float* alpha, float* beta, float* costs, float* ll_beta, cudaStream_t s) {
+                   int B, int U1, double* alpha, double* beta, float* costs, double* ll_beta, cudaStream_t s) {
     const int threads = ((U1 + 31) / 32) * 32;
     if (threads > 1024) {
         set_error("lattice kernel supports at most 1023 labels per utterance (got U+1 = %d)", U1);
         return 1;
     }
-    lattice_kernel<<<2 * B, threads, 2 * threads * sizeof(float), s>>>(lpb, lpl, act_lens, label_lens, meta, B, alpha,
+    lattice_kernel<<<2 * B, threads, 2 * threads * sizeof(double), s>>>(lpb, lpl, act_lens, label_lens, meta, B, alpha,
                                                                      beta, costs, ll_beta);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int launch_grad_prep(const float* lse, const float* lpb, const float* lpl, const float* alpha, const float* beta,
-                     const float* ll_beta, const float* grad_costs, float* scal, const int* act_lens,
+int launch_grad_prep(const float* lse, const float* lpb, const float* lpl, const double* alpha, const double* beta,
+                     const double* ll_beta, const float* grad_costs, float* scal, const int* act_lens,
                      const int* label_lens, const int* meta, int B, int n_tiles_ub, float4* rowmeta,
                      cudaStream_t s) {
     gmax_kernel<<<1, 256, 0, s>>>(grad_costs, B, scal);

@@ -22,6 +22,27 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+# name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
+KERNELS_PER_CALL = {"ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+                    "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
+                    "ttx_dense_lse": 1, "ttx_dense_grad": 1}
+PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
+
+
+def _call(name, dev, *args, n_kernels=None, label=None):
+    fn = getattr(_lib.get(), name)
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        rc = fn(*args)
+        e1.record(torch.cuda.current_stream(dev))
+        prof.append((label or name, e0, e1, KERNELS_PER_CALL[name] if n_kernels is None else n_kernels))
+    else:
+        rc = fn(*args)
+    _lib.check(rc, name)
+
+
 def _i32_cuda(t, dev, name):
     if t.dtype != torch.int32:
         raise TypeError("%s must be int32" % name)
@@ -39,27 +60,28 @@ class _Plan:
         self.rows = self.ntub * 128
         self.meta = torch.empty(int(lib.ttx_meta_ints(B, self.ntub)), dtype=torch.int32, device=dev)
         self.act_lens, self.label_lens = act_lens, label_lens
-        _lib.check(lib.ttx_prepare(_p(act_lens), _p(label_lens), B, T, U1, self.ntub, _p(self.meta), self.idx,
-                                   _stream(dev)), "ttx_prepare")
+        _call("ttx_prepare", dev, _p(act_lens), _p(label_lens), B, T, U1, self.ntub, _p(self.meta), self.idx,
+                                   _stream(dev))
 
     def rowf(self, n=1):
         return torch.empty(self.rows * n, dtype=torch.float32, device=self.dev)
 
     def lattice(self, lse, lpb, lpl):
-        alpha, beta = self.rowf(), self.rowf()
+        alpha = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
+        beta = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
         costs = torch.empty(self.B, dtype=torch.float32, device=self.dev)
-        ll_beta = torch.empty(self.B, dtype=torch.float32, device=self.dev)
-        _lib.check(self.lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
+        ll_beta = torch.empty(self.B, dtype=torch.float64, device=self.dev)
+        _call("ttx_lattice_fwd_bwd", self.dev, _p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
                                                _p(self.meta), self.B, self.U1, _p(alpha), _p(beta), _p(costs),
-                                               _p(ll_beta), self.idx, _stream(self.dev)), "ttx_lattice_fwd_bwd")
+                                               _p(ll_beta), self.idx, _stream(self.dev))
         return alpha, beta, costs, ll_beta
 
     def grad_coeffs(self, lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal):
         rowmeta = self.rowf(4)
         g = grad_costs.detach().to(torch.float32).contiguous()
-        _lib.check(self.lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(ll_beta), _p(g),
+        _call("ttx_grad_coeffs", self.dev, _p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(ll_beta), _p(g),
                                            _p(scal), _p(self.act_lens), _p(self.label_lens), _p(self.meta), self.B,
-                                           self.ntub, _p(rowmeta), self.idx, _stream(self.dev)), "ttx_grad_coeffs")
+                                           self.ntub, _p(rowmeta), self.idx, _stream(self.dev))
         return rowmeta
 
 
@@ -92,17 +114,17 @@ class FusedJointRNNT(torch.autograd.Function):
             Vpad = (V + 127) // 128 * 128
             scal = torch.zeros(4, dtype=torch.float32, device=dev)
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
-            _lib.check(lib.ttx_cast_weight(_p(w), V, H, int(bf16), _p(scal), _p(w16), plan.idx, st), "ttx_cast_weight")
+            _call("ttx_cast_weight", dev, _p(w), V, H, int(bf16), _p(scal), _p(w16), plan.idx, st)
             a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
-            _lib.check(lib.ttx_joint_act(_p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
+            _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
                                          _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
-                                         _p(a16), _p(row_label), plan.idx, st), "ttx_joint_act")
+                                         _p(a16), _p(row_label), plan.idx, st)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
-            _lib.check(lib.ttx_joint_lse_fwd(_p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+            _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
                                              plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
-                                             plan.idx, st), "ttx_joint_lse_fwd")
+                                             plan.idx, st)
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
@@ -130,15 +152,20 @@ class FusedJointRNNT(torch.autograd.Function):
                 n_vt = (V + 127) // 128
                 halves = 2 if H > 256 else 1
                 splits = max(1, min(plan.ntub, (sms * 4) // (n_vt * halves)))
-                _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
-                                              _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), _p(d_w),
-                                              _p(d_b), splits, plan.idx, st), "ttx_joint_grad")
+                # two launches (activation gradient, weight gradient) so each shows up separately in profiles
+                if need_act:
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
+                          n_kernels=1, label="ttx_joint_grad[dA]")
+                if need_w:
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
+                          st, n_kernels=1, label="ttx_joint_grad[dW]")
             if need_act:
                 d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
                 d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
-                _lib.check(lib.ttx_reduce_act_grad(_p(d_act), _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens),
-                                                   _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st),
-                           "ttx_reduce_act_grad")
+                _call("ttx_reduce_act_grad", dev, _p(d_act), _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens),
+                                                   _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st)
         dt = ctx.in_dtypes
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
@@ -169,9 +196,9 @@ class DenseRNNT(torch.autograd.Function):
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
-            _lib.check(lib.ttx_dense_lse(_p(a), _p(labels) if labels.numel() else None, _p(act_lens), _p(label_lens),
+            _call("ttx_dense_lse", dev, _p(a), _p(labels) if labels.numel() else None, _p(act_lens), _p(label_lens),
                                          _p(plan.meta), B, T, U1, V, lstride, int(blank), plan.ntub, _p(lse), _p(lpb),
-                                         _p(lpl), _p(row_label), plan.idx, _stream(dev)), "ttx_dense_lse")
+                                         _p(lpl), _p(row_label), plan.idx, _stream(dev))
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
         ctx.plan, ctx.blank, ctx.in_dtype = plan, int(blank), acts.dtype
         ctx.save_for_backward(a, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
@@ -186,9 +213,9 @@ class DenseRNNT(torch.autograd.Function):
             scal = torch.zeros(4, dtype=torch.float32, device=plan.dev)
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal)
             grads = torch.empty_like(a)
-            _lib.check(plan.lib.ttx_dense_grad(_p(a), _p(rowmeta), _p(row_label), _p(scal), _p(plan.act_lens),
+            _call("ttx_dense_grad", plan.dev, _p(a), _p(rowmeta), _p(row_label), _p(scal), _p(plan.act_lens),
                                                _p(plan.label_lens), _p(plan.meta), B, T, U1, V, ctx.blank, _p(grads),
-                                               plan.idx, _stream(plan.dev)), "ttx_dense_grad")
+                                               plan.idx, _stream(plan.dev))
         return grads.to(ctx.in_dtype), None, None, None, None
 
 
