@@ -45,10 +45,12 @@ int64_t ttx_meta_ints(int B, int64_t n_tiles_ub);
 int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int64_t n_tiles_ub,
                 int32_t* meta, int device, void* stream);
 
-/* W_out (V,H) fp32 -> 16-bit tensor-core operand (Vpad = 128 * ceil(V/128) rows, zero padded).
- * bf16 = 0: fp16 scaled by a power of two w_scale; bf16 = 1: bfloat16.  scal: 4 floats
- * {w_scale, 1/w_scale, gmax (set by ttx_grad_coeffs), scratch}. */
-int ttx_cast_weight(const float* w_out, int V, int H, int bf16, float* scal, void* w16, int device, void* stream);
+/* W_out (V,H) fp32 -> 16-bit tensor-core operand (Vpad = 128 * ceil(V/128) rows, zero padded), and
+ * bias2 (Vpad) = b_out * log2(e), -inf on the padding rows.
+ * bf16 = 0: fp16 scaled by a power of two w_scale; bf16 = 1: bfloat16.  scal: 8 floats
+ * {w_scale, 1/w_scale, gmax, any-negative-grad flag (both set by ttx_grad_coeffs), scratch...}. */
+int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf16, float* scal, void* w16,
+                    float* bias2, int device, void* stream);
 
 /* A16[row,:] = 16-bit(tanh(eproj[b,t,:] + pproj[b,u,:])) for every lattice cell; row_label[row] = label
  * emitted from the cell's u (labels[b,u]) or -1.  eproj (B,T,H), pproj (B,U1,H) fp32 contiguous;
@@ -59,7 +61,7 @@ int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels,
 
 /* tcgen05 projection A16 . W16^T + b_out fused with log-softmax statistics: per row lse, log p(blank),
  * log p(label).  The (B,T,U1,V) logits are never written. */
-int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, const float* scal,
+int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, const float* scal,
                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                       int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream);
 
@@ -69,18 +71,21 @@ int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int3
                         const int32_t* label_lens, const int32_t* meta, int B, int U1, double* alpha, double* beta,
                         float* costs, double* ll_beta, int device, void* stream);
 
-/* Per-row gradient coefficients rowmeta[row] = {lse, rb, rl, gamma * grad_costs[b] / gmax} (float4),
- * gmax = max_b |grad_costs[b]| stored in scal[2]. */
+/* Per-row gradient coefficients rowmeta[row] = {lse, p_blank - rb, p_label - rl, gamma * grad_costs[b] / gmax}
+ * (float4; rb / rl = posteriors of the blank / label arc out of the cell), gmax = max_b |grad_costs[b]| -> scal[2].
+ * If d_b_out != NULL the sparse (blank / label) part of dL/db_out is accumulated into it. */
 int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,
                     const double* beta, const double* ll_beta, const float* grad_costs, float* scal,
-                    const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
-                    int64_t n_tiles_ub, void* rowmeta, int device, void* stream);
+                    const int32_t* row_label, const int32_t* act_lens, const int32_t* label_lens,
+                    const int32_t* meta, int B, int blank, int64_t n_tiles_ub, void* rowmeta, float* d_b_out,
+                    int device, void* stream);
 
 /* Fused gradient: recomputes the joint tile on the tensor cores and accumulates
  *   d_act (rows,H) fp32 = dL/dA (before the tanh derivative)        if d_act  != NULL
- *   d_w_out (V,H), d_b_out (V) fp32 += dL/dW_out, dL/db_out          if d_w_out != NULL (caller zero-fills)
+ *   d_w_out (V,H), d_b_out (V) fp32 += dL/dW_out, dense part of dL/db_out   if d_w_out != NULL (caller zero-fills
+ *                                      before ttx_grad_coeffs, which adds the sparse part of dL/db_out)
  * `splits` = lattice-row splits of the weight-gradient grid (>= 1). */
-int ttx_joint_grad(const void* a16, const void* w16, const float* b_out, const float* scal,
+int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
                    int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
                    void* stream);

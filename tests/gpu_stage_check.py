@@ -77,9 +77,10 @@ def run(stage, B, T, U, V, H):
     f32 = lambda n: torch.empty(n, dtype=torch.float32, device=dev)  # noqa: E731
     Ed, Pd, Wd, bd = E.to(dev), P.to(dev), W.to(dev).contiguous(), b.to(dev)
     Vpad = (V + 127) // 128 * 128
-    scal = torch.zeros(4, dtype=torch.float32, device=dev)
+    scal = torch.zeros(8, dtype=torch.float32, device=dev)
     w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
-    _lib.check(lib.ttx_cast_weight(_p(Wd), V, H, 0, _p(scal), _p(w16), 0, st), "cast")
+    bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
+    _lib.check(lib.ttx_cast_weight(_p(Wd), _p(bd), V, H, 0, _p(scal), _p(w16), _p(bias2), 0, st), "cast")
     a16 = torch.empty(rows * H, dtype=torch.int16, device=dev)
     row_label = torch.empty(rows, dtype=torch.int32, device=dev)
     _lib.check(lib.ttx_joint_act(_p(Ed), _p(Pd), _p(labd), _p(ald), _p(lld), _p(meta), B, T, U1, H, U, ntub, 0,
@@ -108,7 +109,7 @@ def run(stage, B, T, U, V, H):
         mm = algo_model.forward_backward(E, P, W, b, labels, al, ll, gc, emulate=False)
         tol = 2e-5
     else:
-        _lib.check(lib.ttx_joint_lse_fwd(_p(a16), _p(w16), _p(bd), _p(scal), _p(row_label), _p(meta), ntub, H, V, 0, 0,
+        _lib.check(lib.ttx_joint_lse_fwd(_p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(meta), ntub, H, V, 0, 0,
                                          _p(lse), _p(lpb), _p(lpl), 0, st), "fwd")
         torch.cuda.synchronize()
         mm = m
@@ -135,13 +136,18 @@ def run(stage, B, T, U, V, H):
 
     gcd = gc.to(dev)
     rowmeta = f32(rows * 4)
-    _lib.check(lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(llb), _p(gcd), _p(scal), _p(ald),
-                                   _p(lld), _p(meta), B, ntub, _p(rowmeta), 0, st), "coeffs")
+    db = torch.zeros(V, dtype=torch.float32, device=dev)
+    which = os.environ.get("TTX_BWD", "both")
+    rlab = rl2 if stage == "small" else row_label
+    _lib.check(lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(llb), _p(gcd), _p(scal), _p(rlab),
+                                   _p(ald), _p(lld), _p(meta), B, 0, ntub, _p(rowmeta),
+                                   _p(db) if (stage == "bwd" and which in ("both", "dw")) else None, 0, st), "coeffs")
     torch.cuda.synchronize()
     rm = rowmeta.view(rows, 4).cpu()
     gmax = float(scal[2])
-    fail |= report("rb", rm[:, 1], compact(mh, mm["rb"], al, ll, rows), 1e-4)
-    fail |= report("rl", rm[:, 2], compact(mh, mm["rl"], al, ll, rows), 1e-4)
+    fail |= report("pb-rb", rm[:, 1], compact(mh, torch.exp(mm["lpb"]) - mm["rb"], al, ll, rows), 1e-4)
+    fail |= report("pl-rl", rm[:, 2], compact(mh, torch.where(valid_lab, torch.exp(mm["lpl"]) - mm["rl"],
+                                                              torch.full_like(mm["rl"], float("nan"))), al, ll, rows), 1e-4)
     fail |= report("gamma*g", rm[:, 3] * gmax, compact(mh, mm["gamma"] * gc.double().view(B, 1, 1), al, ll, rows), 1e-4)
 
     if stage == "small":
@@ -161,10 +167,8 @@ def run(stage, B, T, U, V, H):
 
     d_act = f32(rows * H)
     dW = torch.zeros(V, H, dtype=torch.float32, device=dev)
-    db = torch.zeros(V, dtype=torch.float32, device=dev)
     splits = int(os.environ.get("TTX_SPLITS", "2"))
-    which = os.environ.get("TTX_BWD", "both")
-    _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(bd), _p(scal), _p(row_label), _p(meta), _p(rowmeta), ntub, H, V,
+    _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(meta), _p(rowmeta), ntub, H, V,
                                   0, 0, _p(d_act) if which in ("both", "da") else None,
                                   _p(dW) if which in ("both", "dw") else None,
                                   _p(db) if which in ("both", "dw") else None, splits, 0, st), "joint_grad")

@@ -18,13 +18,14 @@ void set_error(const char* fmt, ...) {
 
 // launchers (ttx_small.cu / ttx_joint_mma.cu)
 int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
-int launch_cast_w(const float*, int, int, int, bool, float*, void*, cudaStream_t);
+int launch_cast_w(const float*, const float*, int, int, int, bool, float*, void*, float*, cudaStream_t);
 int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
                      int, int, bool, void*, int*, cudaStream_t);
 int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, double*, double*, float*,
                    double*, cudaStream_t);
 int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
-                     const float*, float*, const int*, const int*, const int*, int, int, float4*, cudaStream_t);
+                     const float*, float*, const int*, const int*, const int*, const int*, int, int, int, float4*,
+                     float*, cudaStream_t);
 int launch_reduce(const float*, const float*, const float*, const int*, const int*, const int*, int, int, int, int,
                   float*, float*, cudaStream_t);
 int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
@@ -87,12 +88,13 @@ int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T
     return launch_prep(act_lens, label_lens, B, T, U1, (int)n_tiles_ub, meta, (cudaStream_t)stream);
 }
 
-int ttx_cast_weight(const float* w_out, int V, int H, int bf16, float* scal, void* w16, int device, void* stream) {
-    TTX_REQUIRE(w_out && scal && w16, "ttx_cast_weight: null pointer");
+int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf16, float* scal, void* w16,
+                    float* bias2, int device, void* stream) {
+    TTX_REQUIRE(w_out && b_out && scal && w16 && bias2, "ttx_cast_weight: null pointer");
     TTX_REQUIRE(V > 0 && H > 0 && H % 8 == 0, "ttx_cast_weight: bad shape V=%d H=%d", V, H);
     TTX_ENTER(device);
     const int Vpad = ((V + kTile - 1) / kTile) * kTile;
-    return launch_cast_w(w_out, V, Vpad, H, bf16 != 0, scal, w16, (cudaStream_t)stream);
+    return launch_cast_w(w_out, b_out, V, Vpad, H, bf16 != 0, scal, w16, bias2, (cudaStream_t)stream);
 }
 
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
@@ -106,17 +108,17 @@ int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels,
                             (int)n_tiles_ub, bf16 != 0, a16, row_label, (cudaStream_t)stream);
 }
 
-int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* b_out, const float* scal,
+int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, const float* scal,
                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                       int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream) {
-    TTX_REQUIRE(a16 && w16 && b_out && scal && row_label && meta && lse && lp_blank && lp_label,
+    TTX_REQUIRE(a16 && w16 && bias2 && scal && row_label && meta && lse && lp_blank && lp_label,
                 "ttx_joint_lse_fwd: null pointer");
     TTX_REQUIRE(mma_supported_h(H), "ttx_joint_lse_fwd: joint width H=%d is not supported by the tensor-core path", H);
     TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_lse_fwd: bad V=%d / blank=%d", V, blank);
     TTX_ENTER(device);
     const int Vpad = ((V + kTile - 1) / kTile) * kTile;
     return launch_joint_fwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
-                            b_out, scal, row_label, blank, lse, lp_blank, lp_label, (cudaStream_t)stream);
+                            bias2, scal, row_label, blank, lse, lp_blank, lp_label, (cudaStream_t)stream);
 }
 
 int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
@@ -131,20 +133,22 @@ int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int3
 
 int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,
                     const double* beta, const double* ll_beta, const float* grad_costs, float* scal,
-                    const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B,
-                    int64_t n_tiles_ub, void* rowmeta, int device, void* stream) {
-    TTX_REQUIRE(lse && lp_blank && lp_label && alpha && beta && ll_beta && grad_costs && scal && rowmeta,
+                    const int32_t* row_label, const int32_t* act_lens, const int32_t* label_lens,
+                    const int32_t* meta, int B, int blank, int64_t n_tiles_ub, void* rowmeta, float* d_b_out,
+                    int device, void* stream) {
+    TTX_REQUIRE(lse && lp_blank && lp_label && alpha && beta && ll_beta && grad_costs && scal && row_label && rowmeta,
                 "ttx_grad_coeffs: null pointer");
     TTX_ENTER(device);
-    return launch_grad_prep(lse, lp_blank, lp_label, alpha, beta, ll_beta, grad_costs, scal, act_lens, label_lens,
-                            meta, B, (int)n_tiles_ub, (float4*)rowmeta, (cudaStream_t)stream);
+    return launch_grad_prep(lse, lp_blank, lp_label, alpha, beta, ll_beta, grad_costs, scal, row_label, act_lens,
+                            label_lens, meta, B, blank, (int)n_tiles_ub, (float4*)rowmeta, d_b_out,
+                            (cudaStream_t)stream);
 }
 
-int ttx_joint_grad(const void* a16, const void* w16, const float* b_out, const float* scal,
+int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
                    int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
                    void* stream) {
-    TTX_REQUIRE(a16 && w16 && b_out && scal && row_label && meta && rowmeta, "ttx_joint_grad: null pointer");
+    TTX_REQUIRE(a16 && w16 && bias2 && scal && row_label && meta && rowmeta, "ttx_joint_grad: null pointer");
     TTX_REQUIRE((d_w_out == nullptr) == (d_b_out == nullptr), "ttx_joint_grad: d_w_out and d_b_out go together");
     TTX_REQUIRE(mma_supported_h(H), "ttx_joint_grad: joint width H=%d is not supported by the tensor-core path", H);
     TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_grad: bad V=%d / blank=%d", V, blank);
@@ -152,7 +156,7 @@ int ttx_joint_grad(const void* a16, const void* w16, const float* b_out, const f
     TTX_ENTER(device);
     const int Vpad = ((V + kTile - 1) / kTile) * kTile;
     return launch_joint_bwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
-                            b_out, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
+                            bias2, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
                             (cudaStream_t)stream);
 }
 

@@ -13,8 +13,8 @@
 //        Q = gamma * P' and accumulates G = Q . A16[:, half] in TMEM -> dL/dW_out tile (+ dL/db_out).
 //        (DA + DW replace autograd through log_softmax + project_layer, train.py:58)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (two per TMEM lane quarter, 64 accumulator columns each).
 #include "ttx_common.cuh"
 
 namespace ttx {
@@ -31,20 +31,23 @@ struct MmaParams {
     int blank;
     int splits;            // DW: lattice-row splits
     const int* meta;       // tile table
-    const float* bias;     // (V) fp32
-    const float* scal;     // [0] w_scale, [1] 1 / w_scale, [2] gmax
+    const float* bias2;    // (Vpad) b_out * log2(e), -inf for v >= V
+    const float* scal;     // [0] w_scale, [1] 1 / w_scale, [2] gmax, [3] != 0 if some grad_costs[b] < 0
     const int* row_label;  // (rows) label emitted from the cell's u, -1 if none / padding
     float* lse;            // FWD out (rows)
     float* lpb;            // FWD out (rows) log p(blank)
     float* lpl;            // FWD out (rows) log p(label)
-    const float4* rowmeta; // BWD in (rows): {lse, rb, rl, gamma * g_b / gmax}
+    const float4* rowmeta; // BWD in (rows): {lse, p_blank - rb, p_label - rl, gamma * g_b / gmax}
     float* dA;             // DA out (rows x H)
     float* dW;             // DW out (V x H), accumulated with red.add
     float* db;             // DW out (V)
 };
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter, 64 accumulator columns each
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;         // + TMA producer warp + MMA issuer warp
 constexpr int kNumBars = 32;
+constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
 
 struct Ring {
     int stage = 0;
@@ -57,6 +60,21 @@ struct Ring {
         }
     }
 };
+
+__device__ __forceinline__ void epi_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(kEpiThreads) : "memory");
+}
+
+// byte offset of 16-bit element (row, col) inside the 128 x 128 K-major / MN-major tile (2 blocks of 64 columns)
+__device__ __forceinline__ uint32_t ptile_off(int row, int col) {
+    return (col >> 6) * kChunkBytes + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t to16(float x) {
+    if (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    return __half_as_ushort(__float2half_rn(x));
+}
 
 template <int MODE, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -81,14 +99,19 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int half = BWD ? blockIdx.y : 0;
     const int n_iter = j1 - j0;
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) {   // 128B-swizzle atoms need 1024-byte alignment
+        if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
+        __trap();
+    }
     const uint32_t sX = smem_base;                                  // NKC chunks
     const uint32_t sP = sX + p.NKC * kChunkBytes;                   // BWD: 2 chunks (128 x 128 16-bit)
     const uint32_t sRing = sP + (BWD ? 2 * kChunkBytes : 0);        // NS chunks
     const uint32_t sBar = sRing + p.NS * kChunkBytes;               // barriers
     const uint32_t sTmemPtr = sBar + kNumBars * 8;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 2 x 128 floats of per-column constants
+    uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
     // barrier map
@@ -115,9 +138,9 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_sfull(b), 1);
-            mbar_init(bar_sempty(b), 128);
+            mbar_init(bar_sempty(b), kEpiThreads);
         }
-        mbar_init(bar_pfull, 128);
+        mbar_init(bar_pfull, kEpiThreads);
         mbar_init(bar_pempty, 1);
         mbar_init(bar_gfull, 1);
         fence_barrier_init();
@@ -212,9 +235,11 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
         }
     } else {
-        // =========================================================== epilogue warps (128 threads)
+        // =========================================================== epilogue warps (256 threads)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int ch = (warp - 2) >> 2;               // which 64-column half of the 128-column accumulator
         const int row = q * 32 + lane;                // accumulator row handled by this thread
+        const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float inv_ws = p.scal[1];
         const float c1 = inv_ws * kLog2e;
@@ -223,98 +248,144 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (MODE == MODE_FWD) {
             const int grow = x_row0 + row;
             const int label = p.row_label[grow];
-            float m2 = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;   // log2 domain running max / sum
+            // log2-domain running reference mref and sum of 2^(y - mref); mref only moves when a logit exceeds it
+            // by more than 2^40, so the usual step is one ex2(fma) + add per element.
+            float mref = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;
             for (int i = 0; i < n_iter; ++i) {
                 const int buf = i & 1;
-                const int v0 = (j0 + i) * kTile;
+                const int v0 = (j0 + i) * kTile + ch * 64;
                 mbar_wait(bar_sfull(buf), (i >> 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, acc);
-                    tmem_ld_wait();
-                    const int vb = v0 + cc * 32;
+                for (int g = 0; g < 2; ++g) {
+                    const int vb = v0 + g * 32;
+                    tmem_ld32(tmem_base + lane_addr + buf * 128 + ch * 64 + g * 32, acc);
                     float y[32];
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + vb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 bv = __ldg(b4 + e);
+                        y[4 * e + 0] = bv.x; y[4 * e + 1] = bv.y; y[4 * e + 2] = bv.z; y[4 * e + 3] = bv.w;
+                    }
+                    tmem_ld_wait();
                     float gmax = -INFINITY;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        const int v = vb + e;
-                        const float bv = (v < p.V) ? __ldg(p.bias + v) : 0.f;
-                        float yy = fmaf(__uint_as_float(acc[e]), c1, bv * kLog2e);
-                        yy = (v < p.V) ? yy : -INFINITY;
-                        if (v == p.blank) zb = yy;
-                        if (v == label) zl = yy;
-                        y[e] = yy;
-                        gmax = fmaxf(gmax, yy);
+                        y[e] = fmaf(__uint_as_float(acc[e]), c1, y[e]);
+                        gmax = fmaxf(gmax, y[e]);
                     }
-                    const float mn = fmaxf(m2, gmax);
-                    if (mn > -INFINITY) {
+                    if (gmax > mref + 40.f) {          // rare: move the reference (first group, or a big outlier)
+                        ssum *= ex2f(mref - gmax);     // ex2(-inf) = 0 on the first group
+                        mref = gmax;
+                    }
+                    if (mref > -INFINITY) {            // false only while every column seen so far is padding
                         float part = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) part += ex2f(y[e] - mn);
-                        ssum = ssum * ex2f(m2 - mn) + part;
-                        m2 = mn;
+                        for (int e = 0; e < 32; ++e) part += ex2f(y[e] - mref);
+                        ssum += part;
+                    }
+                    if (p.blank >= vb && p.blank < vb + 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zb = (vb + e == p.blank) ? y[e] : zb;
+                    }
+                    if (label >= vb && label < vb + 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zl = (vb + e == label) ? y[e] : zl;
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(bar_sempty(buf));
             }
-            const float lse2 = m2 + lg2f(ssum);
-            p.lse[grow] = lse2 * kLn2;
-            p.lpb[grow] = (zb - lse2) * kLn2;
-            p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+            // combine the two column halves of each row through (now idle) ring memory
+            float4* xch = reinterpret_cast<float4*>(smem_gen + (sRing - smem_base));
+            if (ch == 1) xch[row] = make_float4(mref, ssum, zb, zl);
+            epi_sync();
+            if (ch == 0) {
+                const float4 o = xch[row];
+                const float mn = fmaxf(mref, o.x);
+                const float tot = ssum * ex2f(mref - mn) + ((o.x > -INFINITY) ? o.y * ex2f(o.x - mn) : 0.f);
+                const float lse2 = mn + lg2f(tot);
+                const int bl = p.blank & 127;
+                zb = (bl < 64) ? zb : o.z;          // blank / label columns live in exactly one half
+                if (label >= 0) zl = ((label & 127) < 64) ? zl : o.w;
+                p.lse[grow] = lse2 * kLn2;
+                p.lpb[grow] = (zb - lse2) * kLn2;
+                p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+            }
         } else {
-            // ---- backward: S -> 16-bit gradient operand in shared memory (K-major, 128B swizzle)
+            // ---- backward: S -> 16-bit gradient operand in shared memory (128B swizzle), 64 columns per thread
             uint8_t* sP_gen = smem_gen + (sP - smem_base);
+            float* kbuf = reinterpret_cast<float*>(smem_gen + (sKbuf - smem_base));
             const float pscale = BF16 ? 1.0f : kPScale;
+            const float lg_scale = BF16 ? 0.0f : 12.0f;          // log2(kPScale)
+            const bool any_neg = p.scal[3] != 0.f;
             float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
             int label = -1;
-            float lse2 = 0.f, bias2 = 0.f, db_acc = 0.f;
+            float krow = 0.f, db_acc = 0.f;
             int vrow = 0;
             if (MODE == MODE_DA) {
                 rm = p.rowmeta[x_row0 + row];
                 label = p.row_label[x_row0 + row];
-                lse2 = rm.x * kLog2e;
+                krow = fmaf(rm.x, -kLog2e, lg_scale);              // -lse2 + log2(scale); -inf for padding rows
             } else {
                 vrow = x_row0 + row;
-                bias2 = (vrow < p.V) ? __ldg(p.bias + vrow) * kLog2e : 0.f;
+                krow = __ldg(p.bias2 + vrow);                      // -inf for vocabulary padding rows
             }
             for (int i = 0; i < n_iter; ++i) {
                 const int buf = i & 1;
                 const int c0 = (j0 + i) * kTile;   // first vocab id (DA) / lattice row (DW) of this stream tile
+                float4 cm = make_float4(0.f, 0.f, 0.f, 0.f);
+                int clabel = -1;
+                if (MODE == MODE_DW) {
+                    // per-column constant k_m = -lse2_m + log2(|gamma_m| * scale): Q = +-2^(acc*c1 + bias2_v + k_m)
+                    if (et < kTile) {
+                        cm = __ldg(p.rowmeta + c0 + et);
+                        clabel = __ldg(p.row_label + c0 + et);
+                        const float k = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
+                        kbuf[buf * 2 * kTile + et] = k;
+                        kbuf[buf * 2 * kTile + kTile + et] = (cm.w < 0.f) ? -1.f : 1.f;
+                    }
+                    epi_sync();
+                }
                 mbar_wait(bar_sfull(buf), (i >> 1) & 1);
                 tc_fence_after();
-                uint32_t packed[64];
+                uint32_t packed[32];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, acc);
+                for (int g = 0; g < 2; ++g) {
+                    const int cb = ch * 64 + g * 32;           // first accumulator column of this group
+                    tmem_ld32(tmem_base + lane_addr + buf * 128 + cb, acc);
+                    float kc[32];
+                    if (MODE == MODE_DA) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + c0 + cb);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = __ldg(b4 + e);
+                            kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                        }
+                    } else {
+                        const float4* k4 = reinterpret_cast<const float4*>(kbuf + buf * 2 * kTile + cb);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 kv = k4[e];
+                            kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
+                        }
+                    }
                     tmem_ld_wait();
                     float val[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = c0 + cc * 32 + e;
-                        float out;
-                        if (MODE == MODE_DA) {
-                            const bool ok = col < p.V;
-                            const float bv = ok ? __ldg(p.bias + col) : 0.f;
-                            float pr = ex2f(fmaf(__uint_as_float(acc[e]), c1, fmaf(bv, kLog2e, -lse2)));
-                            if (col == p.blank) pr -= rm.y;
-                            if (col == label) pr -= rm.z;
-                            out = ok ? pr * pscale : 0.f;
-                        } else {
-                            const float4 cm = __ldg(p.rowmeta + col);
-                            const int clabel = __ldg(p.row_label + col);
-                            float pr = ex2f(fmaf(__uint_as_float(acc[e]), c1, fmaf(cm.x, -kLog2e, bias2)));
-                            if (vrow == p.blank) pr -= cm.y;
-                            if (vrow == clabel) pr -= cm.z;
-                            pr = (vrow < p.V) ? pr * cm.w : 0.f;
-                            db_acc += pr;
-                            out = pr * pscale;
+                    for (int e = 0; e < 32; ++e)
+                        val[e] = ex2f(fmaf(__uint_as_float(acc[e]), c1, kc[e] + krow));
+                    if (MODE == MODE_DW) {
+                        if (any_neg) {
+                            const float* sg = kbuf + buf * 2 * kTile + kTile + cb;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) val[e] *= sg[e];
                         }
-                        val[e] = out;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) db_acc += val[e];
                     }
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) packed[cc * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                    for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
                 }
                 // S buffer is free again as soon as it sits in registers
                 tc_fence_before();
@@ -322,22 +393,40 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 // wait until the previous G pass has finished reading the P tile, then overwrite it
                 mbar_wait(bar_pempty, (i & 1) ^ 1);
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {      // 16 chunks of 8 values (16 B) along k
-                    const int blk = ch >> 3, cin = ch & 7;
-                    uint4 v4 = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-                    *reinterpret_cast<uint4*>(sP_gen + blk * kChunkBytes + row * 128 + ((cin ^ (row & 7)) << 4)) = v4;
+                for (int cc = 0; cc < 8; ++cc) {       // 8 chunks of 8 values (16 B) = this thread's 64 columns
+                    uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+                    *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                }
+                // sparse corrections: the blank and label entries are p - rb / p - rl, with p = exp(lp) from the
+                // forward pass (rowmeta .y / .z), written exactly instead of being carried through the dense loop
+                if (MODE == MODE_DA) {
+                    const int cbl = p.blank - c0, clb = label - c0;
+                    if (cbl >= ch * 64 && cbl < ch * 64 + 64)
+                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
+                    if (clb >= ch * 64 && clb < ch * 64 + 64)
+                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+                } else {
+                    epi_sync();                        // column owners patch rows written by other threads
+                    if (et < kTile) {
+                        const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
+                        if (rbl >= 0 && rbl < kTile)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et)) = to16<BF16>(cm.y * cm.w * pscale);
+                        if (rlb >= 0 && rlb < kTile)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et)) = to16<BF16>(cm.z * cm.w * pscale);
+                    }
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(bar_pfull);
             }
-            // ---- final: G (128 x HH fp32 in TMEM) -> global
+            // ---- final: G (128 x HH fp32 in TMEM) -> global; the two column halves split the HH columns
             mbar_wait(bar_gfull, 0);
             tc_fence_after();
             const float gmax = p.scal[2];
+            const int ngrp = p.HH / 32;
             if (MODE == MODE_DA) {
                 const float f = rm.w * gmax * inv_ws / pscale;
                 float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
-                for (int cc = 0; cc < p.HH / 32; ++cc) {
+                for (int cc = ch; cc < ngrp; cc += 2) {
                     tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
                     tmem_ld_wait();
 #pragma unroll
@@ -351,7 +440,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 const float f = gmax / pscale;
                 const bool ok = vrow < p.V;
                 float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
-                for (int cc = 0; cc < p.HH / 32; ++cc) {
+                for (int cc = ch; cc < ngrp; cc += 2) {
                     tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
                     tmem_ld_wait();
                     if (ok) {
@@ -359,7 +448,9 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
                     }
                 }
-                if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax);
+                // dense part of db: sum_m gamma_m * softmax(m, v); the sparse -rb / -rl terms are added by
+                // grad_prep_kernel.  (the patched entries above do not enter db_acc.)
+                if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
         }
     }
@@ -417,7 +508,7 @@ bool mma_supported_h(int H) {
 }
 
 static size_t smem_bytes(int NKC, int NS, bool bwd) {
-    return 1024 + (size_t)(NKC + NS + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16;
+    return (size_t)(NKC + NS + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
 }
 
 // Fills the shape-derived fields of MmaParams; returns dynamic shared memory size.
@@ -459,14 +550,14 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& my, const MmaParams&
 }
 
 int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
-                     bool bf16, const int* meta, const float* bias, const float* scal, const int* row_label,
+                     bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
                      int blank, float* lse, float* lpb, float* lpl, cudaStream_t stream) {
     MmaParams p{};
     size_t smem = plan(p, H, V, false);
     p.blank = blank;
     p.splits = 1;
     p.meta = meta;
-    p.bias = bias;
+    p.bias2 = bias2;
     p.scal = scal;
     p.row_label = row_label;
     p.lse = lse;
@@ -481,14 +572,14 @@ int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
-                     bool bf16, const int* meta, const float* bias, const float* scal, const int* row_label,
+                     bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
                      int blank, const float4* rowmeta, float* dA, float* dW, float* db, int splits,
                      cudaStream_t stream) {
     MmaParams p{};
     size_t smem = plan(p, H, V, true);
     p.blank = blank;
     p.meta = meta;
-    p.bias = bias;
+    p.bias2 = bias2;
     p.scal = scal;
     p.row_label = row_label;
     p.rowmeta = rowmeta;

@@ -75,9 +75,11 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
 }
 
 // scal[0] = w_scale (power of two putting max|W| into [256, 512) for fp16, 1 for bf16), scal[1] = 1/w_scale
+// bias2[v] = b_out[v] * log2(e) for v < V, -inf for the padding rows (so padded columns drop out of every softmax)
 template <bool BF16>
-__global__ void cast_w_kernel(const float* __restrict__ w, int V, int Vpad, int H, const unsigned int* __restrict__ absmax_bits,
-                              float* __restrict__ scal, uint16_t* __restrict__ w16) {
+__global__ void cast_w_kernel(const float* __restrict__ w, const float* __restrict__ b_out, int V, int Vpad, int H,
+                              const unsigned int* __restrict__ absmax_bits, float* __restrict__ scal,
+                              uint16_t* __restrict__ w16, float* __restrict__ bias2) {
     float ws = 1.f;
     if (!BF16) {
         const float m = __uint_as_float(*absmax_bits);
@@ -91,6 +93,8 @@ __global__ void cast_w_kernel(const float* __restrict__ w, int V, int Vpad, int 
         scal[0] = ws;
         scal[1] = 1.f / ws;
     }
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vpad; v += gridDim.x * blockDim.x)
+        bias2[v] = (v < V) ? b_out[v] * kLog2e : -INFINITY;
     const size_t n = (size_t)Vpad * H / 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e0 = 2 * i;
@@ -246,25 +250,38 @@ __global__ void lattice_kernel(const float* __restrict__ lpb, const float* __res
 // ------------------------------------------------------------------------------------------- gradient coefficients
 __global__ void gmax_kernel(const float* __restrict__ grad_costs, int B, float* __restrict__ scal) {
     __shared__ float sm[32];
+    __shared__ int neg;
+    if (threadIdx.x == 0) neg = 0;
+    __syncthreads();
     float m = 0.f;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) m = fmaxf(m, fabsf(grad_costs[i]));
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        m = fmaxf(m, fabsf(grad_costs[i]));
+        if (grad_costs[i] < 0.f) neg = 1;
+    }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sm[i]);
         scal[2] = (m > 0.f && m < INFINITY) ? m : 1.f;
+        scal[3] = neg ? 1.f : 0.f;
     }
 }
 
-// rowmeta[row] = {lse, rb, rl, gamma * g_b / gmax}: rb / rl are the posteriors of leaving the cell by a
-// blank / label arc given that the cell is visited; dL/dz(row, v) = g_b * gamma * (softmax_v - rb[v==blank] - rl[v==label]).
+// rowmeta[row] = {lse, p_blank - rb, p_label - rl, w = gamma * g_b / gmax}: rb / rl are the posteriors of leaving
+// the cell by a blank / label arc given that the cell is visited, and
+//   dL/dz(row, v) = gmax * w * (softmax_v - rb [v == blank] - rl [v == label]).
+// .y / .z are the complete bracket at the blank / label column (p from the forward pass: exp(lp)), so the
+// gradient kernels write those two entries exactly and keep the dense loop free of per-element compares.
+// The sparse part of dL/db_out (-w * rb at blank, -w * rl at the label) is accumulated here as well.
 __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __restrict__ lpb,
                                  const float* __restrict__ lpl, const double* __restrict__ alpha,
                                  const double* __restrict__ beta, const double* __restrict__ ll_beta,
                                  const float* __restrict__ grad_costs, const float* __restrict__ scal,
-                                 const int* __restrict__ act_lens, const int* __restrict__ label_lens,
-                                 const int* __restrict__ meta, int B, float4* __restrict__ rowmeta) {
+                                 const int* __restrict__ row_label, const int* __restrict__ act_lens,
+                                 const int* __restrict__ label_lens, const int* __restrict__ meta, int B, int blank,
+                                 float4* __restrict__ rowmeta, float* __restrict__ d_b_out) {
+    __shared__ float blank_sum[kTile / 32];
     const int tile = blockIdx.x;
     if (tile >= meta[0]) return;
     const int b = meta[kMetaHdr + B + 1 + tile];
@@ -272,6 +289,7 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
     const int T = act_lens[b], U1 = label_lens[b] + 1;
     const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
     float4 out = make_float4(INFINITY, 0.f, 0.f, 0.f);
+    float db_blank = 0.f;
     if (r < T * U1) {
         const int t = r / U1, u = r - t * U1;
         const double ll = ll_beta[b];
@@ -281,9 +299,28 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
         if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[base + r + U1] - be));
         else rb = (u == U1 - 1) ? 1.f : 0.f;
         if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[base + r + 1] - be));
-        out = make_float4(lse[base + r], rb, rl, gam * grad_costs[b] / scal[2]);
+        const int lab = row_label[base + r];
+        const float w = gam * grad_costs[b] / scal[2];
+        float fb = expf(lpb[base + r]) - rb;
+        float fl = (lab >= 0) ? expf(lpl[base + r]) - rl : 0.f;
+        if (lab == blank) fb = fl = fb - rl;
+        out = make_float4(lse[base + r], fb, fl, w);
+        if (d_b_out) {
+            db_blank = -w * scal[2] * rb;
+            if (lab >= 0 && rl != 0.f) atomicAdd(d_b_out + lab, -w * scal[2] * rl);
+        }
     }
     rowmeta[(size_t)tile * kTile + threadIdx.x] = out;
+    if (d_b_out) {
+        for (int o = 16; o; o >>= 1) db_blank += __shfl_xor_sync(0xffffffffu, db_blank, o);
+        if ((threadIdx.x & 31) == 0) blank_sum[threadIdx.x >> 5] = db_blank;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float sacc = 0.f;
+            for (int i = 0; i < kTile / 32; ++i) sacc += blank_sum[i];
+            if (sacc != 0.f) atomicAdd(d_b_out + blank, sacc);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------- dA -> dEproj, dPproj
@@ -430,8 +467,8 @@ __global__ void dense_grad_kernel(const float* __restrict__ acts, const float4* 
     const float* row = acts + cell * V;
     for (int v = lane; v < V; v += 32) {
         float pr = __expf(__ldg(row + v) - rm.x);
-        if (v == blank) pr -= rm.y;
-        if (v == lab) pr -= rm.z;
+        if (v == blank) pr = rm.y;
+        if (v == lab) pr = rm.z;
         g[v] = coef * pr;
     }
 }
@@ -444,13 +481,14 @@ int launch_prep(const int* act_lens, const int* label_lens, int B, int T, int U1
     return 0;
 }
 
-int launch_cast_w(const float* w, int V, int Vpad, int H, bool bf16, float* scal, void* w16, cudaStream_t s) {
-    unsigned int* bits = reinterpret_cast<unsigned int*>(scal + 3);
+int launch_cast_w(const float* w, const float* b_out, int V, int Vpad, int H, bool bf16, float* scal, void* w16,
+                  float* bias2, cudaStream_t s) {
+    unsigned int* bits = reinterpret_cast<unsigned int*>(scal + 4);
     TTX_CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(unsigned int), s));
     const size_t n = (size_t)V * H;
     if (!bf16) absmax_kernel<<<296, 256, 0, s>>>(w, n, bits);
-    if (bf16) cast_w_kernel<true><<<592, 256, 0, s>>>(w, V, Vpad, H, bits, scal, (uint16_t*)w16);
-    else cast_w_kernel<false><<<592, 256, 0, s>>>(w, V, Vpad, H, bits, scal, (uint16_t*)w16);
+    if (bf16) cast_w_kernel<true><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2);
+    else cast_w_kernel<false><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -482,12 +520,12 @@ int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, cons
 }
 
 int launch_grad_prep(const float* lse, const float* lpb, const float* lpl, const double* alpha, const double* beta,
-                     const double* ll_beta, const float* grad_costs, float* scal, const int* act_lens,
-                     const int* label_lens, const int* meta, int B, int n_tiles_ub, float4* rowmeta,
-                     cudaStream_t s) {
+                     const double* ll_beta, const float* grad_costs, float* scal, const int* row_label,
+                     const int* act_lens, const int* label_lens, const int* meta, int B, int blank, int n_tiles_ub,
+                     float4* rowmeta, float* d_b_out, cudaStream_t s) {
     gmax_kernel<<<1, 256, 0, s>>>(grad_costs, B, scal);
-    grad_prep_kernel<<<n_tiles_ub, kTile, 0, s>>>(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, act_lens,
-                                                  label_lens, meta, B, rowmeta);
+    grad_prep_kernel<<<n_tiles_ub, kTile, 0, s>>>(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label,
+                                                  act_lens, label_lens, meta, B, blank, rowmeta, d_b_out);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

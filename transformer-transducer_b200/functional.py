@@ -76,12 +76,12 @@ class _Plan:
                                                _p(ll_beta), self.idx, _stream(self.dev))
         return alpha, beta, costs, ll_beta
 
-    def grad_coeffs(self, lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal):
+    def grad_coeffs(self, lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, blank, d_b=None):
         rowmeta = self.rowf(4)
         g = grad_costs.detach().to(torch.float32).contiguous()
         _call("ttx_grad_coeffs", self.dev, _p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(ll_beta), _p(g),
-                                           _p(scal), _p(self.act_lens), _p(self.label_lens), _p(self.meta), self.B,
-                                           self.ntub, _p(rowmeta), self.idx, _stream(self.dev))
+              _p(scal), _p(row_label), _p(self.act_lens), _p(self.label_lens), _p(self.meta), self.B, int(blank),
+              self.ntub, _p(rowmeta), _p(d_b), self.idx, _stream(self.dev))
         return rowmeta
 
 
@@ -112,9 +112,10 @@ class FusedJointRNNT(torch.autograd.Function):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens)
             st = _stream(dev)
             Vpad = (V + 127) // 128 * 128
-            scal = torch.zeros(4, dtype=torch.float32, device=dev)
+            scal = torch.zeros(8, dtype=torch.float32, device=dev)
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
-            _call("ttx_cast_weight", dev, _p(w), V, H, int(bf16), _p(scal), _p(w16), plan.idx, st)
+            bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
+            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), plan.idx, st)
             a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
@@ -122,18 +123,18 @@ class FusedJointRNNT(torch.autograd.Function):
                                          _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
                                          _p(a16), _p(row_label), plan.idx, st)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
-            _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+            _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                                              plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
                                              plan.idx, st)
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
-        ctx.save_for_backward(ep, pp, b, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
+        ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        ep, pp, b, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
+        ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
         plan, (B, T, U1, H, V) = ctx.plan, ctx.dims
         lib, dev = plan.lib, plan.dev
         need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
@@ -142,11 +143,11 @@ class FusedJointRNNT(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _stream(dev)
             scal = scal.clone()
-            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal)
-            d_act = plan.rowf(H) if need_act else None
             if need_w:
                 d_w = torch.zeros(V, H, dtype=torch.float32, device=dev)
                 d_b = torch.zeros(V, dtype=torch.float32, device=dev)
+            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
+            d_act = plan.rowf(H) if need_act else None
             if need_act or need_w:
                 sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 n_vt = (V + 127) // 128
@@ -154,11 +155,11 @@ class FusedJointRNNT(torch.autograd.Function):
                 splits = max(1, min(plan.ntub, (sms * 4) // (n_vt * halves)))
                 # two launches (activation gradient, weight gradient) so each shows up separately in profiles
                 if need_act:
-                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
                 if need_w:
-                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(b), _p(scal), _p(row_label), _p(plan.meta),
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
                           st, n_kernels=1, label="ttx_joint_grad[dW]")
             if need_act:
@@ -210,8 +211,8 @@ class DenseRNNT(torch.autograd.Function):
         plan = ctx.plan
         B, T, U1, V = a.shape
         with torch.cuda.device(plan.dev):
-            scal = torch.zeros(4, dtype=torch.float32, device=plan.dev)
-            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal)
+            scal = torch.zeros(8, dtype=torch.float32, device=plan.dev)
+            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank)
             grads = torch.empty_like(a)
             _call("ttx_dense_grad", plan.dev, _p(a), _p(rowmeta), _p(row_label), _p(scal), _p(plan.act_lens),
                                                _p(plan.label_lens), _p(plan.meta), B, T, U1, V, ctx.blank, _p(grads),
