@@ -173,3 +173,45 @@ def test_install_rebinds_reference_classes_and_model_builds_unchanged():
     finally:
         tt_model.JointNet = orig_tt
         sys.modules["espnet.nets.pytorch_backend.transducer.joint_network"].JointNetwork = orig_es
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree only exists in the build container")
+def test_unmodified_train_loop_runs_with_the_drop_ins():
+    """`import train` resolves `from warprnnt_pytorch import RNNTLoss` (train.py:13) to this repo's package, and the
+    UNMODIFIED train.train() (train.py:22-91) steps a Transducer built with our JointNet.  No GPU here, so the
+    criterion handed to train() is the oracle's CPU RNNTLoss (the product loss is CUDA-only and is checked
+    against the same oracle in tests/test_gpu_parity.py)."""
+    import logging
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    orig = tt_model.JointNet
+    try:
+        ttb.install(patch_espnet=False)
+        import train as ref_train
+        assert ref_train.RNNTLoss is ttb.RNNTLoss
+        import yaml
+        from tt.optim import Optimizer
+        from tt.utils import AttrDict
+        cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "aishell.yaml"))))
+        cfg.model.enc.n_layer = 1
+        cfg.model.dec.n_layer = 1
+        cfg.model.vocab_size = 31
+        cfg.training.num_gpu = 0
+        cfg.training.show_interval = 1
+        torch.manual_seed(0)
+        model = tt_model.Transducer(cfg.model)
+        assert isinstance(model.joint, ttb.JointNet)
+        opt = Optimizer(model.parameters(), cfg.optim)
+        data = [(torch.randn(2, 20, 512), torch.tensor([20, 16]), torch.randint(1, 31, (2, 5)), torch.tensor([5, 3]))
+                for _ in range(3)]
+        log = logging.getLogger("tt-test")
+        records = []
+        handler = logging.Handler()
+        handler.emit = lambda r: records.append(r.getMessage())
+        log.addHandler(handler)
+        log.setLevel(logging.INFO)
+        ref_train.train(0, cfg, model, data, opt, rnnt_oracle.RNNTLoss(), log)
+        losses = [float(m.split(", Loss:")[1].split(",")[0]) for m in records if "Global Step" in m]
+        assert len(losses) == 3 and losses[-1] < losses[0]
+    finally:
+        tt_model.JointNet = orig
