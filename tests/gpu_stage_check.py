@@ -76,7 +76,7 @@ def run(stage, B, T, U, V, H):
     fail = False
     f32 = lambda n: torch.empty(n, dtype=torch.float32, device=dev)  # noqa: E731
     Ed, Pd, Wd, bd = E.to(dev), P.to(dev), W.to(dev).contiguous(), b.to(dev)
-    Vpad = (V + 127) // 128 * 128
+    Vpad = (V + 255) // 256 * 256
     scal = torch.zeros(8, dtype=torch.float32, device=dev)
     w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
     bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)

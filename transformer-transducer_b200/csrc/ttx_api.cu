@@ -93,7 +93,7 @@ int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf
     TTX_REQUIRE(w_out && b_out && scal && w16 && bias2, "ttx_cast_weight: null pointer");
     TTX_REQUIRE(V > 0 && H > 0 && H % 8 == 0, "ttx_cast_weight: bad shape V=%d H=%d", V, H);
     TTX_ENTER(device);
-    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_cast_w(w_out, b_out, V, Vpad, H, bf16 != 0, scal, w16, bias2, (cudaStream_t)stream);
 }
 
@@ -116,7 +116,7 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, cons
     TTX_REQUIRE(mma_supported_h(H), "ttx_joint_lse_fwd: joint width H=%d is not supported by the tensor-core path", H);
     TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_lse_fwd: bad V=%d / blank=%d", V, blank);
     TTX_ENTER(device);
-    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_joint_fwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
                             bias2, scal, row_label, blank, lse, lp_blank, lp_label, (cudaStream_t)stream);
 }
@@ -154,7 +154,7 @@ int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const f
     TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_grad: bad V=%d / blank=%d", V, blank);
     TTX_REQUIRE(splits >= 1 && splits <= 65535, "ttx_joint_grad: bad splits=%d", splits);
     TTX_ENTER(device);
-    const int Vpad = ((V + kTile - 1) / kTile) * kTile;
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_joint_bwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
                             bias2, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
                             (cudaStream_t)stream);

@@ -24,9 +24,9 @@ enum { MODE_FWD = 0, MODE_DA = 1, MODE_DW = 2 };
 struct MmaParams {
     int H, NKC;            // joint width, H / 64
     int V;                 // vocabulary size (valid rows of W16)
-    int n_vtiles;          // ceil(V / 128)
     int n_halves, HH;      // backward: H is processed in n_halves column slabs of HH
-    int NGC, GCH;          // backward: HH / 64 chunks per slab, chunks per G-pass MMA group
+    int NGCL;              // backward: 64-column G chunks this CTA loads per stream tile (HH / 64 / CG)
+    int GCH;               // backward: chunks per G-pass MMA group (CG = 2: all of them)
     int NS;                // ring stages
     int blank;
     int splits;            // DW: lattice-row splits
@@ -43,11 +43,12 @@ struct MmaParams {
     float* db;             // DW out (V)
 };
 
-constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter, 64 accumulator columns each
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;         // + TMA producer warp + MMA issuer warp
 constexpr int kNumBars = 32;
 constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
+constexpr int kMaxStages = 8;
 
 struct Ring {
     int stage = 0;
@@ -76,26 +77,45 @@ __device__ __forceinline__ uint16_t to16(float x) {
     return __half_as_ushort(__float2half_rn(x));
 }
 
-template <int MODE, bool BF16>
+template <int CG>
+__device__ __forceinline__ void bwait(uint32_t bar, uint32_t parity) {
+    if (CG == 2) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+}
+
+// CG = 1: one CTA per 128-row stationary tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2): each CTA
+// keeps its own stationary tile (MMA M = 256), the streamed operand is split between the two CTAs' shared memory
+// (half the TMA bytes and half the operand reads per SM), the leader CTA issues every MMA and its commits are
+// multicast to both CTAs' barriers.
+template <int MODE, bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                  const MmaParams p) {
     constexpr bool BWD = (MODE != MODE_FWD);
+    constexpr int NT = (CG == 2 && !BWD) ? 256 : 128;   // columns of one S accumulator = stream rows per step
+    constexpr int SR = NT / CG;                          // stream rows this CTA loads per S chunk
+    constexpr int STAGE = SR * 128;                      // bytes of one ring stage
+    constexpr int GST = kChunkBytes / STAGE;             // ring stages per 128-row G chunk
+    constexpr int NG = NT / 64;                          // 32-column groups per epilogue thread
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
-    // ---- work assignment (uniform per CTA; CTAs without work leave before touching TMEM)
-    int x_row0, j0, j1;
+    // ---- work assignment (uniform per CTA pair; pairs without work leave before touching TMEM / the cluster barrier)
+    int j0, j1;
+    bool valid_x = true;
     if (MODE == MODE_DW) {
         const int per = (n_tiles + p.splits - 1) / p.splits;
-        x_row0 = blockIdx.x * kTile;
         j0 = blockIdx.z * per;
         j1 = min(n_tiles, j0 + per);
     } else {
-        if ((int)blockIdx.x >= n_tiles) return;
-        x_row0 = blockIdx.x * kTile;
+        const int first = (CG == 2) ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+        if (first >= n_tiles) return;
+        valid_x = (int)blockIdx.x < n_tiles;
         j0 = 0;
-        j1 = p.n_vtiles;
+        j1 = (p.V + NT - 1) / NT;
     }
     if (j0 >= j1) return;
+    const int x_row0 = blockIdx.x * kTile;
     const int half = BWD ? blockIdx.y : 0;
     const int n_iter = j1 - j0;
 
@@ -107,14 +127,14 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
     const uint32_t sX = smem_base;                                  // NKC chunks
     const uint32_t sP = sX + p.NKC * kChunkBytes;                   // BWD: 2 chunks (128 x 128 16-bit)
-    const uint32_t sRing = sP + (BWD ? 2 * kChunkBytes : 0);        // NS chunks
-    const uint32_t sBar = sRing + p.NS * kChunkBytes;               // barriers
+    const uint32_t sRing = sP + (BWD ? 2 * kChunkBytes : 0);        // NS stages
+    const uint32_t sBar = sRing + p.NS * STAGE;                     // barriers
     const uint32_t sTmemPtr = sBar + kNumBars * 8;
-    const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 2 x 128 floats of per-column constants
+    const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 2 x 2 x 128 floats of per-column constants
     uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
-    // barrier map
+    // barrier map (same offsets in both CTAs of a pair)
     const uint32_t bar_xfull = sBar;
     auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
     auto bar_empty = [&](int s) { return sBar + 8 * (9 + s); };
@@ -126,7 +146,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = BWD ? 512 : 256;
+    constexpr uint32_t kTmemCols = (BWD || NT == 256) ? 512 : 256;
+    constexpr uint32_t kEpiArrivals = (CG == 2) ? 2 * kEpiWarps : kEpiThreads;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX);
@@ -138,37 +159,64 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_sfull(b), 1);
-            mbar_init(bar_sempty(b), kEpiThreads);
+            mbar_init(bar_sempty(b), kEpiArrivals);
         }
-        mbar_init(bar_pfull, kEpiThreads);
+        mbar_init(bar_pfull, kEpiArrivals);
         mbar_init(bar_pempty, 1);
         mbar_init(bar_gfull, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(sTmemPtr, kTmemCols);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair(sTmemPtr, kTmemCols);
+        else tmem_alloc(sTmemPtr, kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // peer barriers are initialised before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
     const uint32_t tmem_G = tmem_base + 256;
 
+    // epilogue -> MMA-issuer arrival (the issuer lives in the leader CTA)
+    auto epi_arrive = [&](uint32_t bar) {
+        if (CG == 2) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar, 0);
+        } else {
+            mbar_arrive(bar);
+        }
+    };
+
     if (warp == 0) {
         // =========================================================== TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(bar_xfull, p.NKC * kChunkBytes);
-            for (int c = 0; c < p.NKC; ++c) tma_load_2d(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            if (CG == 2) {
+                if (leader) mbar_arrive_expect_tx(bar_xfull, 2 * p.NKC * kChunkBytes);
+                for (int c = 0; c < p.NKC; ++c)
+                    tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            } else {
+                mbar_arrive_expect_tx(bar_xfull, p.NKC * kChunkBytes);
+                for (int c = 0; c < p.NKC; ++c) tma_load_2d(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            }
             Ring r;
-            auto load_chunk = [&](int col, int row) {
-                mbar_wait(bar_empty(r.stage), r.phase ^ 1);
-                mbar_arrive_expect_tx(bar_full(r.stage), kChunkBytes);
-                tma_load_2d(sRing + r.stage * kChunkBytes, &mapY, bar_full(r.stage), col, row);
+            auto load_stage = [&](int col, int row) {      // one [SR rows x 64 cols] box into the next ring stage
+                bwait<CG>(bar_empty(r.stage), r.phase ^ 1);
+                if (CG == 2) {
+                    if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STAGE);
+                    tma_load_2d_pair(sRing + r.stage * STAGE, &mapY, bar_full(r.stage), col, row);
+                } else {
+                    mbar_arrive_expect_tx(bar_full(r.stage), STAGE);
+                    tma_load_2d(sRing + r.stage * STAGE, &mapY, bar_full(r.stage), col, row);
+                }
                 r.advance(p.NS);
             };
             auto load_S = [&](int j) {
-                for (int c = 0; c < p.NKC; ++c) load_chunk(c * kKC, j * kTile);
+                for (int c = 0; c < p.NKC; ++c) load_stage(c * kKC, j * NT + (int)rank * SR);
             };
-            auto load_G = [&](int j) {
-                for (int c = 0; c < p.NGC; ++c) load_chunk(half * p.HH + c * kKC, j * kTile);
+            auto load_G = [&](int j) {                     // this CTA's share of the h columns, all 128 stream rows
+                const int col0 = half * p.HH + (int)rank * (p.HH / CG);
+                for (int c = 0; c < p.NGCL; ++c)
+                    for (int g = 0; g < GST; ++g) load_stage(col0 + c * kKC, j * kTile + g * SR);
             };
             if (!BWD) {
                 for (int j = j0; j < j1; ++j) load_S(j);
@@ -181,47 +229,56 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // =========================================================== MMA issuer (one thread)
-        if (lane == 0) {
+        // =========================================================== MMA issuer (one thread of the leader CTA)
+        if (lane == 0 && leader) {
             constexpr int fmt = BF16 ? 1 : 0;
-            const uint32_t idescS = make_idesc(fmt, 0, 0, 128, 128);
-            const uint32_t idescG = make_idesc(fmt, 0, 1, 128, 64 * p.GCH);
+            const uint32_t idescS = make_idesc(fmt, 0, 0, 128 * CG, NT);
+            const uint32_t idescG = make_idesc(fmt, 0, 1, 128 * CG, 64 * p.GCH * CG);
+            const int gstages = p.GCH * GST;
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+                if (CG == 2) umma_f16_ss_pair(d, da, db, idesc, acc);
+                else umma_f16_ss(d, da, db, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (CG == 2) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             Ring r;
-            mbar_wait(bar_xfull, 0);
+            bwait<CG>(bar_xfull, 0);
             auto issue_S = [&](int idx) {
                 const int buf = idx & 1;
-                mbar_wait(bar_sempty(buf), ((idx >> 1) & 1) ^ 1);
+                bwait<CG>(bar_sempty(buf), ((idx >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + buf * 128;
+                const uint32_t d = tmem_base + buf * NT;
                 for (int c = 0; c < p.NKC; ++c) {
-                    mbar_wait(bar_full(r.stage), r.phase);
+                    bwait<CG>(bar_full(r.stage), r.phase);
                     tc_fence_after();
                     const uint32_t a = sX + c * kChunkBytes;
-                    const uint32_t b = sRing + r.stage * kChunkBytes;
+                    const uint32_t b = sRing + r.stage * STAGE;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
-                    umma_commit(bar_empty(r.stage));
+                        mma(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
+                    commit(bar_empty(r.stage));
                     r.advance(p.NS);
                 }
-                umma_commit(bar_sfull(buf));
+                commit(bar_sfull(buf));
             };
             auto issue_G = [&](int idx) {
-                mbar_wait(bar_pfull, idx & 1);
+                bwait<CG>(bar_pfull, idx & 1);
                 tc_fence_after();
-                for (int g = 0; g < p.NGC; g += p.GCH) {
-                    for (int s = 0; s < p.GCH; ++s) mbar_wait(bar_full(r.stage + s), r.phase);
+                for (int g = 0; g < p.NGCL; g += p.GCH) {
+                    for (int s = 0; s < gstages; ++s) bwait<CG>(bar_full(r.stage + s), r.phase);
                     tc_fence_after();
                     const uint32_t d = tmem_G + g * 64;
-                    const uint32_t b = sRing + r.stage * kChunkBytes;
+                    const uint32_t b = sRing + r.stage * STAGE;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_f16_ss(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3),
-                                    desc_mnmajor(b, k, kChunkBytes), idescG, (idx | k) != 0);
-                    for (int s = 0; s < p.GCH; ++s) umma_commit(bar_empty(r.stage + s));
-                    r.advance(p.NS, p.GCH);
+                        mma(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3), desc_mnmajor(b, k, kChunkBytes), idescG,
+                            (idx | k) != 0);
+                    for (int s = 0; s < gstages; ++s) commit(bar_empty(r.stage + s));
+                    r.advance(p.NS, gstages);
                 }
-                umma_commit(bar_pempty);
+                commit(bar_pempty);
             };
             if (!BWD) {
                 for (int i = 0; i < n_iter; ++i) issue_S(i);
@@ -231,13 +288,13 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     if (i + 1 < n_iter) issue_S(i + 1);
                     issue_G(i);
                 }
-                umma_commit(bar_gfull);
+                commit(bar_gfull);
             }
         }
     } else {
         // =========================================================== epilogue warps (256 threads)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int ch = (warp - 2) >> 2;               // which 64-column half of the 128-column accumulator
+        const int ch = (warp - 2) >> 2;               // which half of the accumulator columns
         const int row = q * 32 + lane;                // accumulator row handled by this thread
         const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -247,19 +304,19 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
         if (MODE == MODE_FWD) {
             const int grow = x_row0 + row;
-            const int label = p.row_label[grow];
+            const int label = valid_x ? p.row_label[grow] : -1;
             // log2-domain running reference mref and sum of 2^(y - mref); mref only moves when a logit exceeds it
             // by more than 2^40, so the usual step is one ex2(fma) + add per element.
             float mref = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;
             for (int i = 0; i < n_iter; ++i) {
                 const int buf = i & 1;
-                const int v0 = (j0 + i) * kTile + ch * 64;
-                mbar_wait(bar_sfull(buf), (i >> 1) & 1);
+                const int v0 = (j0 + i) * NT + ch * (NT / 2);
+                bwait<CG>(bar_sfull(buf), (i >> 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < NG; ++g) {
                     const int vb = v0 + g * 32;
-                    tmem_ld32(tmem_base + lane_addr + buf * 128 + ch * 64 + g * 32, acc);
+                    tmem_ld32(tmem_base + lane_addr + buf * NT + ch * (NT / 2) + g * 32, acc);
                     float y[32];
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + vb);
 #pragma unroll
@@ -294,20 +351,19 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(bar_sempty(buf));
+                epi_arrive(bar_sempty(buf));
             }
             // combine the two column halves of each row through (now idle) ring memory
             float4* xch = reinterpret_cast<float4*>(smem_gen + (sRing - smem_base));
             if (ch == 1) xch[row] = make_float4(mref, ssum, zb, zl);
             epi_sync();
-            if (ch == 0) {
+            if (ch == 0 && valid_x) {
                 const float4 o = xch[row];
                 const float mn = fmaxf(mref, o.x);
                 const float tot = ssum * ex2f(mref - mn) + ((o.x > -INFINITY) ? o.y * ex2f(o.x - mn) : 0.f);
                 const float lse2 = mn + lg2f(tot);
-                const int bl = p.blank & 127;
-                zb = (bl < 64) ? zb : o.z;          // blank / label columns live in exactly one half
-                if (label >= 0) zl = ((label & 127) < 64) ? zl : o.w;
+                zb = ((p.blank % NT) < NT / 2) ? zb : o.z;          // blank / label columns live in exactly one half
+                if (label >= 0) zl = ((label % NT) < NT / 2) ? zl : o.w;
                 p.lse[grow] = lse2 * kLn2;
                 p.lpb[grow] = (zb - lse2) * kLn2;
                 p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
@@ -324,8 +380,10 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             float krow = 0.f, db_acc = 0.f;
             int vrow = 0;
             if (MODE == MODE_DA) {
-                rm = p.rowmeta[x_row0 + row];
-                label = p.row_label[x_row0 + row];
+                if (valid_x) {
+                    rm = p.rowmeta[x_row0 + row];
+                    label = p.row_label[x_row0 + row];
+                }
                 krow = fmaf(rm.x, -kLog2e, lg_scale);              // -lse2 + log2(scale); -inf for padding rows
             } else {
                 vrow = x_row0 + row;
@@ -337,7 +395,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 float4 cm = make_float4(0.f, 0.f, 0.f, 0.f);
                 int clabel = -1;
                 if (MODE == MODE_DW) {
-                    // per-column constant k_m = -lse2_m + log2(|gamma_m| * scale): Q = +-2^(acc*c1 + bias2_v + k_m)
+                    // per-column constant k_m = -lse2_m + log2(|w_m| * scale): Q = +-2^(acc*c1 + bias2_v + k_m)
                     if (et < kTile) {
                         cm = __ldg(p.rowmeta + c0 + et);
                         clabel = __ldg(p.row_label + c0 + et);
@@ -347,7 +405,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     }
                     epi_sync();
                 }
-                mbar_wait(bar_sfull(buf), (i >> 1) & 1);
+                bwait<CG>(bar_sfull(buf), (i >> 1) & 1);
                 tc_fence_after();
                 uint32_t packed[32];
 #pragma unroll
@@ -389,9 +447,9 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
                 // S buffer is free again as soon as it sits in registers
                 tc_fence_before();
-                mbar_arrive(bar_sempty(buf));
+                epi_arrive(bar_sempty(buf));
                 // wait until the previous G pass has finished reading the P tile, then overwrite it
-                mbar_wait(bar_pempty, (i & 1) ^ 1);
+                bwait<CG>(bar_pempty, (i & 1) ^ 1);
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {       // 8 chunks of 8 values (16 B) = this thread's 64 columns
                     uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
@@ -416,10 +474,10 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     }
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(bar_pfull);
+                epi_arrive(bar_pfull);
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global; the two column halves split the HH columns
-            mbar_wait(bar_gfull, 0);
+            bwait<CG>(bar_gfull, 0);
             tc_fence_after();
             const float gmax = p.scal[2];
             const int ngrp = p.HH / 32;
@@ -429,11 +487,13 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 for (int cc = ch; cc < ngrp; cc += 2) {
                     tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
                     tmem_ld_wait();
+                    if (valid_x) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
-                                               __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
-                        *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                        for (int e = 0; e < 32; e += 4) {
+                            float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
+                                                   __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
+                            *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                        }
                     }
                 }
             } else {
@@ -448,7 +508,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
                     }
                 }
-                // dense part of db: sum_m gamma_m * softmax(m, v); the sparse -rb / -rl terms are added by
+                // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by
                 // grad_prep_kernel.  (the patched entries above do not enter db_acc.)
                 if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
@@ -457,9 +517,11 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     // ---- teardown
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // the leader's MMAs read the peer's shared memory / write its TMEM
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -480,8 +542,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2-D row-major [rows x H] 16-bit matrix, box = 64 columns x 128 rows, 128-byte swizzle.
-int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool bf16) {
+// 2-D row-major [rows x H] 16-bit matrix, box = 64 columns x box_rows rows, 128-byte swizzle.
+int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool bf16, int box_rows) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -489,7 +551,7 @@ int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool
     }
     cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)kTile};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -507,53 +569,91 @@ bool mma_supported_h(int H) {
     return H > 0 && H <= 512 && H % 64 == 0 && (H <= 256 || H == 384 || H == 512);
 }
 
-static size_t smem_bytes(int NKC, int NS, bool bwd) {
-    return (size_t)(NKC + NS + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+static int forced_cg() {
+    const char* e = getenv("TTX_CG");
+    return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 
-// Fills the shape-derived fields of MmaParams; returns dynamic shared memory size.
-static size_t plan(MmaParams& p, int H, int V, bool bwd) {
+struct Plan {
+    MmaParams p;
+    int cg, stage_bytes;
+    size_t smem;
+};
+
+// Shape-derived launch plan.  CTA pairs need every CTA's share of a G slab to be whole 64-column chunks.
+static Plan plan(int H, int V, bool bwd) {
+    Plan pl{};
+    MmaParams& p = pl.p;
     p.H = H;
     p.NKC = H / 64;
     p.V = V;
-    p.n_vtiles = (V + kTile - 1) / kTile;
     p.n_halves = (bwd && H > 256) ? 2 : 1;
     p.HH = H / p.n_halves;
-    p.NGC = p.HH / 64;
+    int cg = (!bwd || (p.HH / 2) % 64 == 0) ? 2 : 1;
+    if (forced_cg() == 1) cg = 1;
+    pl.cg = cg;
+    pl.stage_bytes = (bwd && cg == 2) ? kChunkBytes / 2 : kChunkBytes;
+    const int gst = kChunkBytes / pl.stage_bytes;
+    p.NGCL = p.HH / 64 / (bwd ? cg : 1);
+    const size_t fixed = (size_t)(p.NKC + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     const size_t limit = 232448;
-    int ns = 8;
-    while (ns > 2 && smem_bytes(p.NKC, ns, bwd) > limit) --ns;
+    int ns = kMaxStages;
+    while (ns > 2 && fixed + (size_t)ns * pl.stage_bytes > limit) --ns;
     p.GCH = 1;
     if (bwd) {
-        if (p.NKC % 4 == 0 && p.NGC % 4 == 0 && ns >= 4) {
+        if (cg == 2) {
+            p.GCH = p.NGCL;
+        } else if (p.NKC % 4 == 0 && p.NGCL % 4 == 0 && ns >= 4) {
             p.GCH = 4;
-            ns = (ns / 4) * 4;
-        } else if (p.NKC % 2 == 0 && p.NGC % 2 == 0) {
+        } else if (p.NKC % 2 == 0 && p.NGCL % 2 == 0) {
             p.GCH = 2;
-            ns = (ns / 2) * 2;
         }
+        const int gstages = p.GCH * gst;
+        ns = (ns / gstages) * gstages;
     }
     p.NS = ns;
-    return smem_bytes(p.NKC, ns, bwd);
+    pl.smem = fixed + (size_t)ns * pl.stage_bytes;
+    return pl;
 }
 
-template <int MODE, bool BF16>
+template <int MODE, bool BF16, int CG>
 static int launch(const CUtensorMap& mx, const CUtensorMap& my, const MmaParams& p, dim3 grid, size_t smem,
                   cudaStream_t stream) {
-    auto kern = joint_mma_kernel<MODE, BF16>;
-    static bool attr_set = false;   // per instantiation; same value for every device in this process
-    (void)attr_set;
+    auto kern = joint_mma_kernel<MODE, BF16, CG>;
     TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    kern<<<grid, kThreads, smem, stream>>>(mx, my, p);
-    TTX_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, p));
     return 0;
+}
+
+template <int MODE>
+static int dispatch(bool bf16, int cg, const CUtensorMap& mx, const CUtensorMap& my, const MmaParams& p, dim3 grid,
+                    size_t smem, cudaStream_t stream) {
+    if (cg == 2) {
+        grid.x = (grid.x + 1) & ~1u;
+        return bf16 ? launch<MODE, true, 2>(mx, my, p, grid, smem, stream)
+                    : launch<MODE, false, 2>(mx, my, p, grid, smem, stream);
+    }
+    return bf16 ? launch<MODE, true, 1>(mx, my, p, grid, smem, stream)
+                : launch<MODE, false, 1>(mx, my, p, grid, smem, stream);
 }
 
 int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
                      bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
                      int blank, float* lse, float* lpb, float* lpl, cudaStream_t stream) {
-    MmaParams p{};
-    size_t smem = plan(p, H, V, false);
+    Plan pl = plan(H, V, false);
+    MmaParams& p = pl.p;
     p.blank = blank;
     p.splits = 1;
     p.meta = meta;
@@ -564,19 +664,17 @@ int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
     p.lpb = lpb;
     p.lpl = lpl;
     CUtensorMap mx, my;
-    if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16)) return rc;
-    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16)) return rc;
-    dim3 grid(n_tiles_ub, 1, 1);
-    return bf16 ? launch<MODE_FWD, true>(mx, my, p, grid, smem, stream)
-                : launch<MODE_FWD, false>(mx, my, p, grid, smem, stream);
+    if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, pl.stage_bytes / 128)) return rc;
+    return dispatch<MODE_FWD>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, 1, 1), pl.smem, stream);
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
                      bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
                      int blank, const float4* rowmeta, float* dA, float* dW, float* db, int splits,
                      cudaStream_t stream) {
-    MmaParams p{};
-    size_t smem = plan(p, H, V, true);
+    Plan pl = plan(H, V, true);
+    MmaParams& p = pl.p;
     p.blank = blank;
     p.meta = meta;
     p.bias2 = bias2;
@@ -586,22 +684,23 @@ int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
     p.dA = dA;
     p.dW = dW;
     p.db = db;
-    CUtensorMap ma, mw;
-    if (int rc = make_tile_map(&ma, a16, rows_ub, H, bf16)) return rc;
-    if (int rc = make_tile_map(&mw, w16, (uint64_t)Vpad, H, bf16)) return rc;
+    const int box = pl.stage_bytes / 128;
+    const int n_vtiles = (V + kTile - 1) / kTile;
     if (dA) {
+        CUtensorMap mx, my;
+        if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
+        if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, box)) return rc;
         p.splits = 1;
-        dim3 grid(n_tiles_ub, p.n_halves, 1);
-        int rc = bf16 ? launch<MODE_DA, true>(ma, mw, p, grid, smem, stream)
-                      : launch<MODE_DA, false>(ma, mw, p, grid, smem, stream);
-        if (rc) return rc;
+        if (int rc = dispatch<MODE_DA>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, p.n_halves, 1), pl.smem, stream))
+            return rc;
     }
     if (dW) {
+        CUtensorMap mx, my;
+        if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+        if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, box)) return rc;
         p.splits = splits;
-        dim3 grid(p.n_vtiles, p.n_halves, splits);
-        int rc = bf16 ? launch<MODE_DW, true>(mw, ma, p, grid, smem, stream)
-                      : launch<MODE_DW, false>(mw, ma, p, grid, smem, stream);
-        if (rc) return rc;
+        if (int rc = dispatch<MODE_DW>(bf16, pl.cg, mx, my, p, dim3(n_vtiles, p.n_halves, splits), pl.smem, stream))
+            return rc;
     }
     return 0;
 }

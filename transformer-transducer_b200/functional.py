@@ -111,7 +111,7 @@ class FusedJointRNNT(torch.autograd.Function):
         with torch.cuda.device(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens)
             st = _stream(dev)
-            Vpad = (V + 127) // 128 * 128
+            Vpad = (V + 255) // 256 * 256
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
             bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
