@@ -23,6 +23,9 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the microbench the headline metric is quoted on (espnet joint dims)
     "cfg2": dict(B=32, T=400, U=40, V=4232, D=512, H=512, joint="espnet", ragged=False,
                  desc="joint+RNN-T loss microbench B=32 T=400 U=40 V=4232 D=512 H=512 fp32"),
+    # same lattice, joint width 256 (leaves shared memory for a deeper TMA ring: pipeline experiments)
+    "cfg2h256": dict(B=32, T=400, U=40, V=4232, D=512, H=256, joint="espnet", ragged=False,
+                     desc="B=32 T=400 U=40 V=4232 D=512 H=256 fp32 (experiment)"),
     # BASELINE.json configs[0] shapes but with a fused-path joint width (parity-sized smoke workload)
     "small": dict(B=4, T=200, U=30, V=4232, D=512, H=512, joint="espnet", ragged=False,
                   desc="B=4 T=200 U=30 V=4232 D=512 H=512 fp32"),

@@ -63,12 +63,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-// cluster-scope variants (CTA pairs): remote arrive on the barrier at the same offset in CTA `cta`, acquire.cluster wait
+// CTA pairs: remote arrive on the barrier at the same offset in CTA `cta`.  Default (.cta) semantics on purpose:
+// .release.cluster / .acquire.cluster compile to MEMBAR.ALL.GPU + CCTL.IVALL (an L1 flush per barrier operation,
+// measured at >50% of the kernel's stall samples); ordering of the TMEM reads / shared-memory writes that the
+// barrier publishes is provided by tcgen05.fence::before_thread_sync and fence.proxy.async, as in CUTLASS.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(cta)
         : "memory");
 }

@@ -30,6 +30,8 @@ struct MmaParams {
     int NS;                // ring stages
     int blank;
     int splits;            // DW: lattice-row splits
+    long long* trace;      // timing experiments only (TTX_TRACE): clock64 stamps of CTA (0,0,0), [role][iter][4]
+    int dbg;               // timing experiments only (TTX_DBG): 1 = skip S-pass MMAs, 2 = skip G-pass MMAs, 4 = skip epilogue math
     const int* meta;       // tile table
     const float* bias2;    // (Vpad) b_out * log2(e), -inf for v >= V
     const float* scal;     // [0] w_scale, [1] 1 / w_scale, [2] gmax, [3] != 0 if some grad_costs[b] < 0
@@ -46,9 +48,9 @@ struct MmaParams {
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;         // + TMA producer warp + MMA issuer warp
-constexpr int kNumBars = 32;
+constexpr int kNumBars = 40;
 constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 struct Ring {
     int stage = 0;
@@ -77,10 +79,15 @@ __device__ __forceinline__ uint16_t to16(float x) {
     return __half_as_ushort(__float2half_rn(x));
 }
 
+constexpr int kTraceIters = 40;
+__device__ __forceinline__ void trace_at(const MmaParams& p, int role, int iter, int ev) {
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && iter < kTraceIters)
+        p.trace[(role * kTraceIters + iter) * 4 + ev] = clock64();
+}
+
 template <int CG>
 __device__ __forceinline__ void bwait(uint32_t bar, uint32_t parity) {
-    if (CG == 2) mbar_wait_cluster(bar, parity);
-    else mbar_wait(bar, parity);
+    mbar_wait(bar, parity);
 }
 
 // CG = 1: one CTA per 128-row stationary tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2): each CTA
@@ -137,12 +144,12 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     // barrier map (same offsets in both CTAs of a pair)
     const uint32_t bar_xfull = sBar;
     auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
-    auto bar_empty = [&](int s) { return sBar + 8 * (9 + s); };
-    auto bar_sfull = [&](int b) { return sBar + 8 * (17 + b); };
-    auto bar_sempty = [&](int b) { return sBar + 8 * (19 + b); };
-    const uint32_t bar_pfull = sBar + 8 * 21;
-    const uint32_t bar_pempty = sBar + 8 * 22;
-    const uint32_t bar_gfull = sBar + 8 * 23;
+    auto bar_empty = [&](int s) { return sBar + 8 * (17 + s); };
+    auto bar_sfull = [&](int b) { return sBar + 8 * (33 + b); };
+    auto bar_sempty = [&](int b) { return sBar + 8 * (35 + b); };
+    const uint32_t bar_pfull = sBar + 8 * 37;
+    const uint32_t bar_pempty = sBar + 8 * 38;
+    const uint32_t bar_gfull = sBar + 8 * 39;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -223,8 +230,11 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             } else {
                 load_S(j0);
                 for (int i = 0; i < n_iter; ++i) {
+                    trace_at(p, 0, i, 0);
                     if (i + 1 < n_iter) load_S(j0 + i + 1);
+                    trace_at(p, 0, i, 1);
                     load_G(j0 + i);
+                    trace_at(p, 0, i, 2);
                 }
             }
         }
@@ -255,9 +265,11 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     tc_fence_after();
                     const uint32_t a = sX + c * kChunkBytes;
                     const uint32_t b = sRing + r.stage * STAGE;
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
+                        for (int k = 0; k < 4; ++k)
+                            mma(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
+                    }
                     commit(bar_empty(r.stage));
                     r.advance(p.NS);
                 }
@@ -265,16 +277,19 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             };
             auto issue_G = [&](int idx) {
                 bwait<CG>(bar_pfull, idx & 1);
+                trace_at(p, 1, idx, 2);
                 tc_fence_after();
                 for (int g = 0; g < p.NGCL; g += p.GCH) {
                     for (int s = 0; s < gstages; ++s) bwait<CG>(bar_full(r.stage + s), r.phase);
                     tc_fence_after();
                     const uint32_t d = tmem_G + g * 64;
                     const uint32_t b = sRing + r.stage * STAGE;
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        mma(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3), desc_mnmajor(b, k, kChunkBytes), idescG,
-                            (idx | k) != 0);
+                        for (int k = 0; k < 8; ++k)
+                            mma(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3), desc_mnmajor(b, k, kChunkBytes),
+                                idescG, (idx | k) != 0);
+                    }
                     for (int s = 0; s < gstages; ++s) commit(bar_empty(r.stage + s));
                     r.advance(p.NS, gstages);
                 }
@@ -285,8 +300,11 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             } else {
                 issue_S(0);
                 for (int i = 0; i < n_iter; ++i) {
+                    trace_at(p, 1, i, 0);
                     if (i + 1 < n_iter) issue_S(i + 1);
+                    trace_at(p, 1, i, 1);
                     issue_G(i);
+                    trace_at(p, 1, i, 3);
                 }
                 commit(bar_gfull);
             }
@@ -406,10 +424,16 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     epi_sync();
                 }
                 bwait<CG>(bar_sfull(buf), (i >> 1) & 1);
+                if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t packed[32];
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
+                    if (p.dbg & 4) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
+                        continue;
+                    }
                     const int cb = ch * 64 + g * 32;           // first accumulator column of this group
                     tmem_ld32(tmem_base + lane_addr + buf * 128 + cb, acc);
                     float kc[32];
@@ -448,8 +472,10 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 // S buffer is free again as soon as it sits in registers
                 tc_fence_before();
                 epi_arrive(bar_sempty(buf));
+                if (et == 0) trace_at(p, 2, i, 1);
                 // wait until the previous G pass has finished reading the P tile, then overwrite it
                 bwait<CG>(bar_pempty, (i & 1) ^ 1);
+                if (et == 0) trace_at(p, 2, i, 2);
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {       // 8 chunks of 8 values (16 B) = this thread's 64 columns
                     uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
@@ -475,6 +501,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
                 fence_proxy_async_smem();
                 epi_arrive(bar_pfull);
+                if (et == 0) trace_at(p, 2, i, 3);
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global; the two column halves split the HH columns
             bwait<CG>(bar_gfull, 0);
@@ -574,6 +601,8 @@ static int forced_cg() {
     return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 
+static long long* trace_buffer();
+
 struct Plan {
     MmaParams p;
     int cg, stage_bytes;
@@ -585,6 +614,8 @@ static Plan plan(int H, int V, bool bwd) {
     Plan pl{};
     MmaParams& p = pl.p;
     p.H = H;
+    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
+    p.trace = trace_buffer();
     p.NKC = H / 64;
     p.V = V;
     p.n_halves = (bwd && H > 256) ? 2 : 1;
@@ -598,6 +629,7 @@ static Plan plan(int H, int V, bool bwd) {
     const size_t fixed = (size_t)(p.NKC + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     const size_t limit = 232448;
     int ns = kMaxStages;
+    if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kMaxStages, atoi(e)));
     while (ns > 2 && fixed + (size_t)ns * pl.stage_bytes > limit) --ns;
     p.GCH = 1;
     if (bwd) {
@@ -635,6 +667,40 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& my, const MmaParams&
     cfg.numAttrs = 1;
     TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, p));
     return 0;
+}
+
+static long long* trace_buffer() {
+    static long long* buf = nullptr;
+    if (!buf && getenv("TTX_TRACE")) {
+        cudaMalloc(&buf, sizeof(long long) * 3 * kTraceIters * 4);
+    }
+    return buf;
+}
+
+static void trace_dump(const char* what, cudaStream_t stream) {
+    long long* buf = trace_buffer();
+    if (!buf) return;
+    static int dumps = 0;
+    cudaStreamSynchronize(stream);
+    if (++dumps > 12 || dumps <= 9) { cudaMemset(buf, 0, sizeof(long long) * 3 * kTraceIters * 4); return; }
+    static long long h[3 * kTraceIters * 4];
+    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemset(buf, 0, sizeof(h));
+    long long t0 = h[(1 * kTraceIters + 0) * 4 + 0];
+    fprintf(stderr, "TRACE %s (cycles since first MMA-loop entry)\n", what);
+    fprintf(stderr, " it | prod: loop loadS_done loadG_done | mma: loop S_issued pfull G_issued | epi: sfull math_done pempty pfull_arr\n");
+    for (int i = 0; i < 12; ++i) {
+        fprintf(stderr, "%3d |", i);
+        for (int r = 0; r < 3; ++r) {
+            for (int e = 0; e < 4; ++e) {
+                if (r == 0 && e == 3) continue;
+                long long v = h[(r * kTraceIters + i) * 4 + e];
+                fprintf(stderr, " %7lld", v ? v - t0 : -1);
+            }
+            fprintf(stderr, " |");
+        }
+        fprintf(stderr, "\n");
+    }
 }
 
 template <int MODE>
@@ -693,6 +759,7 @@ int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
         p.splits = 1;
         if (int rc = dispatch<MODE_DA>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, p.n_halves, 1), pl.smem, stream))
             return rc;
+        trace_dump("DA", stream);
     }
     if (dW) {
         CUtensorMap mx, my;
