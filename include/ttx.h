@@ -84,8 +84,15 @@ int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_lab
  *   d_act (rows,H) fp32 = dL/dA (before the tanh derivative)        if d_act  != NULL
  *   d_w_out (V,H), d_b_out (V) fp32 += dL/dW_out, dense part of dL/db_out   if d_w_out != NULL (caller zero-fills
  *                                      before ttx_grad_coeffs, which adds the sparse part of dL/db_out)
- * `splits` = lattice-row splits of the weight-gradient grid (>= 1). */
-int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const float* scal,
+ * `splits` = lattice-row splits of the weight-gradient grid (>= 1).  a16t / w16t (transposed operand copies from
+ * ttx_transpose16) may be NULL: the kernels then read the gradient pass's B operand MN-major from a16 / w16. */
+/* out (cols, rows) = transpose of the row-major 16-bit matrix in (rows, cols); rows, cols multiples of 64.
+ * meta != NULL: `in` is the A16 operand and row blocks beyond the tiles in use (meta[0]) are skipped.  Produces the
+ * K-major operand copies W16^T (H, Vpad) and A16^T (H, rows) streamed by the backward pair kernel. */
+int ttx_transpose16(const void* in, void* out, int rows, int cols, const int32_t* meta, int device, void* stream);
+
+int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const void* w16t, const float* bias2,
+                   const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
                    int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
                    void* stream);

@@ -168,7 +168,13 @@ def run(stage, B, T, U, V, H):
     d_act = f32(rows * H)
     dW = torch.zeros(V, H, dtype=torch.float32, device=dev)
     splits = int(os.environ.get("TTX_SPLITS", "2"))
-    _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(meta), _p(rowmeta), ntub, H, V,
+    a16t = w16t = None
+    if H in (128, 256, 512):
+        w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev)
+        a16t = torch.empty(H * rows, dtype=torch.int16, device=dev)
+        _lib.check(lib.ttx_transpose16(_p(w16), _p(w16t), Vpad, H, None, 0, st), "transpose w")
+        _lib.check(lib.ttx_transpose16(_p(a16), _p(a16t), rows, H, _p(meta), 0, st), "transpose a")
+    _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(meta), _p(rowmeta), ntub, H, V,
                                   0, 0, _p(d_act) if which in ("both", "da") else None,
                                   _p(dW) if which in ("both", "dw") else None,
                                   _p(db) if which in ("both", "dw") else None, splits, 0, st), "joint_grad")

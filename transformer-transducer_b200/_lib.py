@@ -36,8 +36,9 @@ _PROTOS = {
     "ttx_lattice_fwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_p],
     "ttx_grad_coeffs": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_p, c_p,
                         c_i32, c_p],
-    "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32,
-                       c_i32, c_p],
+    "ttx_transpose16": [c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
+    "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p,
+                       c_i32, c_i32, c_p],
     "ttx_reduce_act_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],

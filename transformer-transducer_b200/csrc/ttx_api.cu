@@ -32,11 +32,13 @@ int launch_dense_lse(const float*, const int*, const int*, const int*, const int
                      float*, float*, float*, int*, cudaStream_t);
 int launch_dense_grad(const float*, const float4*, const int*, const float*, const int*, const int*, const int*, int,
                       int, int, int, int, float*, cudaStream_t);
+int launch_transpose16(const void*, void*, int, int, const int*, cudaStream_t);
 bool mma_supported_h(int H);
 int launch_joint_fwd(const void*, const void*, uint64_t, int, int, int, int, bool, const int*, const float*,
                      const float*, const int*, int, float*, float*, float*, cudaStream_t);
-int launch_joint_bwd(const void*, const void*, uint64_t, int, int, int, int, bool, const int*, const float*,
-                     const float*, const int*, int, const float4*, float*, float*, float*, int, cudaStream_t);
+int launch_joint_bwd(const void*, const void*, const void*, const void*, uint64_t, int, int, int, int, bool,
+                     const int*, const float*, const float*, const int*, int, const float4*, float*, float*, float*,
+                     int, cudaStream_t);
 
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
@@ -144,7 +146,15 @@ int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_lab
                             (cudaStream_t)stream);
 }
 
-int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const float* scal,
+int ttx_transpose16(const void* in, void* out, int rows, int cols, const int32_t* meta, int device, void* stream) {
+    TTX_REQUIRE(in && out, "ttx_transpose16: null pointer");
+    TTX_REQUIRE(rows > 0 && cols > 0 && rows % 64 == 0 && cols % 64 == 0, "ttx_transpose16: rows=%d cols=%d must be multiples of 64", rows, cols);
+    TTX_ENTER(device);
+    return launch_transpose16(in, out, rows, cols, meta, (cudaStream_t)stream);
+}
+
+int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const void* w16t, const float* bias2,
+                   const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
                    int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
                    void* stream) {
@@ -155,7 +165,7 @@ int ttx_joint_grad(const void* a16, const void* w16, const float* bias2, const f
     TTX_REQUIRE(splits >= 1 && splits <= 65535, "ttx_joint_grad: bad splits=%d", splits);
     TTX_ENTER(device);
     const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
-    return launch_joint_bwd(a16, w16, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
+    return launch_joint_bwd(a16, w16, a16t, w16t, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
                             bias2, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
                             (cudaStream_t)stream);
 }

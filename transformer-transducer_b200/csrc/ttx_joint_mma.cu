@@ -552,6 +552,362 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
 }
 
+// ===========================================================================================================
+// Backward pair kernel (v3).  Measured on B200: in SS mode every tcgen05.mma (K = 16) costs ~140 cycles however
+// small N is, so the backward modes above (S pass with N = 128, G pass with an MN-major B operand at ~250
+// cycles / instruction) are instruction-issue bound at ~45 % of the tensor rate.  This kernel does the same math
+// with fewer, larger instructions: the pair streams 256-row tiles (S pass: M = 256, N = 256), keeps ONE 256-column
+// S accumulator whose read-out overlaps the previous tile's G pass, feeds the G pass (M = 256, N = HH) from the
+// 128-column P' tile in two sub-passes, and takes the G-pass B operand K-major from a transposed copy of the
+// streamed matrix (W16^T for dA, A16^T for dW).  48 instructions per 256 stream rows instead of 80.
+template <int MODE, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                      const __grid_constant__ CUtensorMap mapYT, const MmaParams p) {
+    constexpr int NT = 256;                 // stream rows per step (pair-wide) = S accumulator columns
+    constexpr int SR = 128;                 // stream rows this CTA loads per S chunk
+    constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int n_tiles = p.meta[0];
+    int j0, j1;
+    bool valid_x = true;
+    if (MODE == MODE_DW) {
+        const int n_st = (n_tiles + 1) / 2;
+        const int per = (n_st + p.splits - 1) / p.splits;
+        j0 = blockIdx.z * per;
+        j1 = min(n_st, j0 + per);
+    } else {
+        if ((int)(blockIdx.x & ~1u) >= n_tiles) return;
+        valid_x = (int)blockIdx.x < n_tiles;
+        j0 = 0;
+        j1 = (p.V + NT - 1) / NT;
+    }
+    if (j0 >= j1) return;
+    const int x_row0 = blockIdx.x * kTile;
+    const int half = blockIdx.y;
+    const int n_iter = j1 - j0;
+    const int hh2 = p.HH / 2;               // G columns (N rows of the K-major B operand) held by this CTA
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) {
+        if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
+        __trap();
+    }
+    const uint32_t sX = smem_base;
+    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // 128 x 128 16-bit, K-major, 2 blocks
+    const uint32_t sRing = sP + 2 * kChunkBytes;
+    const uint32_t sBar = sRing + p.NS * STAGE;
+    const uint32_t sTmemPtr = sBar + kNumBars * 8;
+    const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 256 exponent offsets + 256 signs
+    uint8_t* smem_gen = smem_raw;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
+
+    const uint32_t bar_xfull = sBar;
+    auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
+    auto bar_empty = [&](int s) { return sBar + 8 * (17 + s); };
+    const uint32_t bar_sfull = sBar + 8 * 33;
+    const uint32_t bar_sempty = sBar + 8 * 35;
+    const uint32_t bar_pfull = sBar + 8 * 37;
+    const uint32_t bar_pempty = sBar + 8 * 38;
+    const uint32_t bar_gfull = sBar + 8 * 39;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 512;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapYT);
+        mbar_init(bar_xfull, 1);
+        for (int s = 0; s < p.NS; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_sfull, 1);
+        mbar_init(bar_sempty, 2 * kEpiWarps);       // every epilogue warp of both CTAs
+        mbar_init(bar_pfull, kEpiWarps);            // the 4 warps of one sub-pass, both CTAs
+        mbar_init(bar_pempty, 1);
+        mbar_init(bar_gfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(sTmemPtr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    const uint32_t tmem_G = tmem_base + 256;
+
+    auto epi_arrive = [&](uint32_t bar) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar, 0);
+    };
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            if (leader) mbar_arrive_expect_tx(bar_xfull, 2 * p.NKC * kChunkBytes);
+            for (int c = 0; c < p.NKC; ++c) tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            Ring r;
+            auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
+                mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * bytes);
+                tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
+                r.advance(p.NS);
+            };
+            const int nk2 = p.NKC / 2;
+            auto load_S = [&](int j, int part) {       // half of the S-pass k chunks of stream tile j
+                for (int c = part * nk2; c < (part + 1) * nk2; ++c)
+                    load_stage(&mapY, c * kKC, j * NT + (int)rank * SR, STAGE);
+            };
+            auto load_G = [&](int j, int sp) {         // K-major B chunks: [hh2 joint columns x 64 stream rows]
+                const int h0 = half * p.HH + (int)rank * hh2;
+                for (int c = 2 * sp; c < 2 * sp + 2; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
+            };
+            // same order as the MMA issuer: Sa(i+1), G(i,0), Sb(i+1), G(i,1)
+            load_S(j0, 0);
+            load_S(j0, 1);
+            for (int i = 0; i < n_iter; ++i) {
+                if (i + 1 < n_iter) load_S(j0 + i + 1, 0);
+                load_G(j0 + i, 0);
+                if (i + 1 < n_iter) load_S(j0 + i + 1, 1);
+                load_G(j0 + i, 1);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer (leader CTA)
+        if (lane == 0 && leader) {
+            constexpr int fmt = BF16 ? 1 : 0;
+            const uint32_t idescS = make_idesc(fmt, 0, 0, 256, NT);
+            const uint32_t idescG = make_idesc(fmt, 0, 0, 256, p.HH);
+            Ring r;
+            mbar_wait(bar_xfull, 0);
+            const int nk2 = p.NKC / 2;
+            // S pass of stream tile idx in two halves (k chunks [0, NKC/2) and [NKC/2, NKC)) so that the two G
+            // sub-passes of the previous tile can be interleaved: Sa(i+1), G(i,0), Sb(i+1), G(i,1).  The P' tile is
+            // written for sub-pass 1 while Sb runs, and for the next tile's sub-pass 0 while the next Sa runs.
+            auto issue_S = [&](int idx, int part) {
+                if (part == 0) {
+                    mbar_wait(bar_sempty, (idx & 1) ^ 1);  // the epilogue has read the previous S tile out of TMEM
+                    tc_fence_after();
+                }
+                for (int c = part * nk2; c < (part + 1) * nk2; ++c) {
+                    mbar_wait(bar_full(r.stage), r.phase);
+                    tc_fence_after();
+                    const uint32_t a = sX + c * kChunkBytes;
+                    const uint32_t b = sRing + r.stage * STAGE;
+                    if (!(p.dbg & 1)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss_pair(tmem_base, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
+                    }
+                    umma_commit_pair(bar_empty(r.stage));
+                    r.advance(p.NS);
+                }
+                if (part == 1) umma_commit_pair(bar_sfull);
+            };
+            auto issue_G = [&](int idx, int sp) {
+                mbar_wait(bar_pfull, sp);                      // sub-pass n = 2 idx + sp, parity n & 1
+                tc_fence_after();
+                for (int c = 0; c < 2; ++c) {
+                    mbar_wait(bar_full(r.stage), r.phase);
+                    tc_fence_after();
+                    const uint32_t a = sP + c * kChunkBytes;
+                    const uint32_t b = sRing + r.stage * STAGE;
+                    if (!(p.dbg & 2)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss_pair(tmem_G, desc_kmajor(a, k), desc_kmajor(b, k), idescG,
+                                             (idx | sp | c | k) != 0);
+                    }
+                    umma_commit_pair(bar_empty(r.stage));
+                    r.advance(p.NS);
+                }
+                umma_commit_pair(bar_pempty);
+            };
+            issue_S(0, 0);
+            issue_S(0, 1);
+            for (int i = 0; i < n_iter; ++i) {
+                trace_at(p, 1, i, 0);
+                if (i + 1 < n_iter) issue_S(i + 1, 0);
+                trace_at(p, 1, i, 1);
+                issue_G(i, 0);
+                trace_at(p, 1, i, 2);
+                if (i + 1 < n_iter) issue_S(i + 1, 1);
+                issue_G(i, 1);
+                trace_at(p, 1, i, 3);
+            }
+            umma_commit_pair(bar_gfull);
+        }
+    } else {
+        // =========================================================== epilogue warps: thread = (row, sub-pass ch)
+        const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;               // sub-pass / 128-column half of the S tile
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;              // 0..255
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float inv_ws = p.scal[1];
+        const float c1 = inv_ws * kLog2e;
+        uint8_t* sP_gen = smem_gen + (sP - smem_base);
+        float* kbuf = reinterpret_cast<float*>(smem_gen + (sKbuf - smem_base));
+        const float pscale = BF16 ? 1.0f : kPScale;
+        const float lg_scale = BF16 ? 0.0f : 12.0f;
+        const bool any_neg = p.scal[3] != 0.f;
+        const int n_valid_rows = n_tiles * kTile;
+        auto half_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(kEpiBarrier + 1 + ch) : "memory"); };
+        float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+        int label = -1;
+        float krow = 0.f, db_acc = 0.f;
+        int vrow = 0;
+        uint32_t acc[32];
+        if (MODE == MODE_DA) {
+            if (valid_x) {
+                rm = p.rowmeta[x_row0 + row];
+                label = p.row_label[x_row0 + row];
+            }
+            krow = fmaf(rm.x, -kLog2e, lg_scale);
+        } else {
+            vrow = x_row0 + row;
+            krow = __ldg(p.bias2 + vrow);
+        }
+        for (int i = 0; i < n_iter; ++i) {
+            const int c0 = (j0 + i) * NT + ch * 128;    // first vocab id (DA) / lattice row (DW) of this sub-pass
+            float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+            int clabel = -1;
+            if (MODE == MODE_DW) {
+                const int col = (j0 + i) * NT + et;     // this thread owns column et of the 256-column tile
+                if (col < n_valid_rows) {
+                    cm = __ldg(p.rowmeta + col);
+                    clabel = __ldg(p.row_label + col);
+                }
+                kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
+                kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
+                half_sync();
+            }
+            mbar_wait(bar_sfull, i & 1);
+            if (et == 0) trace_at(p, 2, i, 0);
+            tc_fence_after();
+            uint32_t packed[64];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int cb = ch * 128 + g * 32;       // accumulator column of this group
+                if (p.dbg & 4) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
+                    continue;
+                }
+                tmem_ld32(tmem_base + lane_addr + cb, acc);
+                float kc[32];
+                if (MODE == MODE_DA) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + (j0 + i) * NT + cb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 bv = __ldg(b4 + e);
+                        kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                    }
+                } else {
+                    const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 kv = k4[e];
+                        kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
+                    }
+                }
+                tmem_ld_wait();
+                float val[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) val[e] = ex2f(fmaf(__uint_as_float(acc[e]), c1, kc[e] + krow));
+                if (MODE == MODE_DW) {
+                    if (any_neg) {
+                        const float* sg = kbuf + NT + cb;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) val[e] *= sg[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) db_acc += val[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+            }
+            tc_fence_before();
+            epi_arrive(bar_sempty);
+            if (et == 0) trace_at(p, 2, i, 1);
+            // sub-pass n = 2i + ch may overwrite the P' tile once the G pass of sub-pass n - 1 has completed.  Parity
+            // waits can only look one phase ahead, so the second sub-pass's writers wait for both phases in turn.
+            mbar_wait(bar_pempty, 1);                   // completion #2i  (G of tile i-1, sub-pass 1)
+            if (ch == 1) mbar_wait(bar_pempty, 0);      // completion #2i+1 (G of tile i, sub-pass 0)
+            if (et == 0) trace_at(p, 2, i, 2);
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc) {           // this thread's 128 columns = 16 chunks of 16 B
+                uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+                *reinterpret_cast<uint4*>(sP_gen + (cc >> 3) * kChunkBytes + row * 128 + (((cc & 7) ^ (row & 7)) << 4)) = v4;
+            }
+            if (MODE == MODE_DA) {
+                const int cbl = p.blank - c0, clb = label - c0;
+                if (cbl >= 0 && cbl < 128)
+                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
+                if (clb >= 0 && clb < 128)
+                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+            } else {
+                half_sync();                            // column owners patch rows written by other threads
+                const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
+                if (rbl >= 0 && rbl < kTile)
+                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
+                if (rlb >= 0 && rlb < kTile)
+                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
+            }
+            fence_proxy_async_smem();
+            epi_arrive(bar_pfull);
+            if (et == 0) trace_at(p, 2, i, 3);
+        }
+        // ---- final: G (128 x HH fp32 in TMEM) -> global
+        mbar_wait(bar_gfull, 0);
+        tc_fence_after();
+        const float gmax = p.scal[2];
+        const int ngrp = p.HH / 32;
+        // G columns [0, hh2) came from the leader's B rows, [hh2, HH) from the peer's: column c <-> joint column c
+        if (MODE == MODE_DA) {
+            const float f = rm.w * gmax * inv_ws / pscale;
+            float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
+            for (int cc = ch; cc < ngrp; cc += 2) {
+                tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                tmem_ld_wait();
+                if (valid_x) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
+                                               __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
+                        *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                    }
+                }
+            }
+        } else {
+            const float f = gmax / pscale;
+            const bool ok = vrow < p.V;
+            float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
+            for (int cc = ch; cc < ngrp; cc += 2) {
+                tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
+                }
+            }
+            if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -587,6 +943,29 @@ int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu H=%d)", (int)r,
                   (unsigned long long)rows, H);
+        return 2;
+    }
+    return 0;
+}
+
+// 2-D row-major [rows x cols] 16-bit matrix (transposed operand copies), box = 64 columns x box_rows rows.
+int make_matrix_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, bool bf16, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return 2;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols);
         return 2;
     }
     return 0;
@@ -735,10 +1114,91 @@ int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
     return dispatch<MODE_FWD>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, 1, 1), pl.smem, stream);
 }
 
-int launch_joint_bwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
-                     bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
-                     int blank, const float4* rowmeta, float* dA, float* dW, float* db, int splits,
-                     cudaStream_t stream) {
+template <int MODE, bool BF16>
+static int launch_v3(const CUtensorMap& mx, const CUtensorMap& my, const CUtensorMap& myt, const MmaParams& p,
+                     dim3 grid, size_t smem, cudaStream_t stream) {
+    auto kern = joint_bwd_pair_kernel<MODE, BF16>;
+    TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    cudaLaunchConfig_t cfg{};
+    grid.x = (grid.x + 1) & ~1u;
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, myt, p));
+    return 0;
+}
+
+// v3 applies when both transposed copies exist and every CTA's share of a G slab is a whole number of 64-row
+// chunk rows that fits one 16 KiB stage: HH / 2 in {64, 128}.
+static bool v3_applicable(int H, const void* w16t, const void* a16t) {
+    const char* e = getenv("TTX_BWD_V3");
+    if (e && e[0] == '0') return false;
+    if (!w16t || !a16t || forced_cg() == 1) return false;
+    return H == 128 || H == 256 || H == 512;
+}
+
+int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const void* w16t, uint64_t rows_ub,
+                     int n_tiles_ub, int H, int V, int Vpad, bool bf16, const int* meta, const float* bias2,
+                     const float* scal, const int* row_label, int blank, const float4* rowmeta, float* dA, float* dW,
+                     float* db, int splits, cudaStream_t stream) {
+    if (v3_applicable(H, w16t, a16t)) {
+        MmaParams p{};
+        p.H = H;
+        p.NKC = H / 64;
+        p.V = V;
+        p.n_halves = (H > 256) ? 2 : 1;
+        p.HH = H / p.n_halves;
+        p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
+        p.trace = trace_buffer();
+        const size_t fixed = (size_t)(p.NKC + 2) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+        int ns = 8;
+        if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kMaxStages, atoi(e)));
+        while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
+        p.NS = ns;
+        const size_t smem = fixed + (size_t)ns * kChunkBytes;
+        p.blank = blank;
+        p.meta = meta;
+        p.bias2 = bias2;
+        p.scal = scal;
+        p.row_label = row_label;
+        p.rowmeta = rowmeta;
+        p.dA = dA;
+        p.dW = dW;
+        p.db = db;
+        const int n_vtiles = (V + kTile - 1) / kTile;
+        if (dA) {
+            CUtensorMap mx, my, myt;
+            if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
+            if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+            if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
+            p.splits = 1;
+            dim3 grid(n_tiles_ub, p.n_halves, 1);
+            int rc = bf16 ? launch_v3<MODE_DA, true>(mx, my, myt, p, grid, smem, stream)
+                          : launch_v3<MODE_DA, false>(mx, my, myt, p, grid, smem, stream);
+            if (rc) return rc;
+            trace_dump("DA v3", stream);
+        }
+        if (dW) {
+            CUtensorMap mx, my, myt;
+            if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+            if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile)) return rc;
+            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2)) return rc;
+            p.splits = splits;
+            dim3 grid(n_vtiles, p.n_halves, splits);
+            int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream)
+                          : launch_v3<MODE_DW, false>(mx, my, myt, p, grid, smem, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     Plan pl = plan(H, V, true);
     MmaParams& p = pl.p;
     p.blank = blank;

@@ -119,7 +119,15 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
                                  int U1, int H, int label_stride, uint16_t* __restrict__ a16,
                                  int* __restrict__ row_label) {
     const int tile = blockIdx.x;
-    if (tile >= meta[0]) return;
+    if (tile >= meta[0]) {
+        // CTA pairs work on tile pairs: with an odd tile count the partner of the last tile must read zeros
+        if (tile == meta[0] && (tile & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(a16 + (size_t)tile * kTile * H);
+            for (int idx = threadIdx.x; idx < kTile * H / 8; idx += blockDim.x) dst[idx] = make_uint4(0, 0, 0, 0);
+            for (int lr = threadIdx.x; lr < kTile; lr += blockDim.x) row_label[(size_t)tile * kTile + lr] = -1;
+        }
+        return;
+    }
     const int b = meta[kMetaHdr + B + 1 + tile];
     const int r0 = (tile - meta[kMetaHdr + b]) * kTile;
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
@@ -152,6 +160,33 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
         }
         row_label[(size_t)tile * kTile + lr] = lab;
     }
+}
+
+// out[c][r] = in[r][c] for a row-major [R x C] matrix of 16-bit values (C % 64 == 0, R % 64 == 0): the K-major
+// operand copies (W16^T, A16^T) that the backward pair kernel streams for its G pass.
+__global__ void transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R, int C,
+                                   const int* __restrict__ meta_rows) {
+    __shared__ uint16_t tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    if (meta_rows && r0 >= ((meta_rows[0] + 1) & ~1) * kTile) return;   // lattice rows beyond the tile pairs in use
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int r = i / 32, c2 = i % 32;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(in + (size_t)(r0 + r) * C + c0 + 2 * c2);
+        tile[r][2 * c2] = (uint16_t)(v & 0xffff);
+        tile[r][2 * c2 + 1] = (uint16_t)(v >> 16);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int c = i / 32, r2 = i % 32;
+        const uint32_t v = (uint32_t)tile[2 * r2][c] | ((uint32_t)tile[2 * r2 + 1][c] << 16);
+        *reinterpret_cast<uint32_t*>(out + (size_t)(c0 + c) * R + r0 + 2 * r2) = v;
+    }
+}
+
+int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_rows, cudaStream_t s) {
+    transpose16_kernel<<<dim3(C / 64, R / 64), 256, 0, s>>>((const uint16_t*)in, (uint16_t*)out, R, C, meta_rows);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------- lattice

@@ -23,7 +23,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -149,17 +149,25 @@ class FusedJointRNNT(torch.autograd.Function):
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
             d_act = plan.rowf(H) if need_act else None
             if need_act or need_w:
+                # K-major copies of both operands for the gradient pass of the pair kernel
+                a16t = w16t = None
+                if H in (128, 256, 512):
+                    Vpad = w16.numel() // H
+                    w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev)
+                    a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev)
+                    _call("ttx_transpose16", dev, _p(w16), _p(w16t), Vpad, H, None, plan.idx, st)
+                    _call("ttx_transpose16", dev, _p(a16), _p(a16t), plan.rows, H, _p(plan.meta), plan.idx, st)
                 sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 n_vt = (V + 127) // 128
                 halves = 2 if H > 256 else 1
                 splits = max(1, min(plan.ntub, (sms * 4) // (n_vt * halves)))
                 # two launches (activation gradient, weight gradient) so each shows up separately in profiles
                 if need_act:
-                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
                 if need_w:
-                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
+                    _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
                           st, n_kernels=1, label="ttx_joint_grad[dW]")
             if need_act:
