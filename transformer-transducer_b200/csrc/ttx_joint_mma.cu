@@ -628,7 +628,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         mbar_init(bar_sfull, 1);
         mbar_init(bar_sempty, 2 * kEpiWarps);       // every epilogue warp of both CTAs
-        mbar_init(bar_pfull, kEpiWarps);            // the 4 warps of one sub-pass, both CTAs
+        mbar_init(bar_pfull, 2 * kEpiWarps);        // every epilogue warp of both CTAs, once per sub-pass
         mbar_init(bar_pempty, 1);
         mbar_init(bar_gfull, 1);
         fence_barrier_init();
@@ -743,9 +743,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             umma_commit_pair(bar_gfull);
         }
     } else {
-        // =========================================================== epilogue warps: thread = (row, sub-pass ch)
+        // =========================================================== epilogue warps: thread = (row, column half ch)
         const int q = warp & 3;
-        const int ch = (warp - 2) >> 2;               // sub-pass / 128-column half of the S tile
+        const int ch = (warp - 2) >> 2;               // which 64-column half of each 128-column sub-pass
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;              // 0..255
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -757,7 +757,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         const float lg_scale = BF16 ? 0.0f : 12.0f;
         const bool any_neg = p.scal[3] != 0.f;
         const int n_valid_rows = n_tiles * kTile;
-        auto half_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(kEpiBarrier + 1 + ch) : "memory"); };
         float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
         int label = -1;
         float krow = 0.f, db_acc = 0.f;
@@ -774,94 +773,106 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             krow = __ldg(p.bias2 + vrow);
         }
         for (int i = 0; i < n_iter; ++i) {
-            const int c0 = (j0 + i) * NT + ch * 128;    // first vocab id (DA) / lattice row (DW) of this sub-pass
+            const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
             float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
             int clabel = -1;
             if (MODE == MODE_DW) {
-                const int col = (j0 + i) * NT + et;     // this thread owns column et of the 256-column tile
+                const int col = t0 + et;                // this thread owns column et of the 256-column tile
                 if (col < n_valid_rows) {
                     cm = __ldg(p.rowmeta + col);
                     clabel = __ldg(p.row_label + col);
                 }
                 kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
                 kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
-                half_sync();
+                epi_sync();
             }
             mbar_wait(bar_sfull, i & 1);
             if (et == 0) trace_at(p, 2, i, 0);
             tc_fence_after();
-            uint32_t packed[64];
+            // Pull this thread's share of the S tile (2 sub-passes x 64 columns) into registers and hand the single S
+            // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
+            uint32_t acc[4][32];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int cb = ch * 128 + g * 32;       // accumulator column of this group
-                if (p.dbg & 4) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
-                    continue;
-                }
-                tmem_ld32(tmem_base + lane_addr + cb, acc);
-                float kc[32];
-                if (MODE == MODE_DA) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + (j0 + i) * NT + cb);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 bv = __ldg(b4 + e);
-                        kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
-                    }
-                } else {
-                    const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 kv = k4[e];
-                        kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
-                    }
-                }
-                tmem_ld_wait();
-                float val[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) val[e] = ex2f(fmaf(__uint_as_float(acc[e]), c1, kc[e] + krow));
-                if (MODE == MODE_DW) {
-                    if (any_neg) {
-                        const float* sg = kbuf + NT + cb;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) val[e] *= sg[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) db_acc += val[e];
-                }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
-            }
+            for (int g = 0; g < 4; ++g)
+                tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
+            tmem_ld_wait();
             tc_fence_before();
             epi_arrive(bar_sempty);
             if (et == 0) trace_at(p, 2, i, 1);
-            // sub-pass n = 2i + ch may overwrite the P' tile once the G pass of sub-pass n - 1 has completed.  Parity
-            // waits can only look one phase ahead, so the second sub-pass's writers wait for both phases in turn.
-            mbar_wait(bar_pempty, 1);                   // completion #2i  (G of tile i-1, sub-pass 1)
-            if (ch == 1) mbar_wait(bar_pempty, 0);      // completion #2i+1 (G of tile i, sub-pass 0)
-            if (et == 0) trace_at(p, 2, i, 2);
 #pragma unroll
-            for (int cc = 0; cc < 16; ++cc) {           // this thread's 128 columns = 16 chunks of 16 B
-                uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                *reinterpret_cast<uint4*>(sP_gen + (cc >> 3) * kChunkBytes + row * 128 + (((cc & 7) ^ (row & 7)) << 4)) = v4;
+            for (int sp = 0; sp < 2; ++sp) {
+                const int c0 = t0 + sp * 128;           // first stream index of this sub-pass
+                uint32_t packed[32];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int cb = sp * 128 + ch * 64 + g * 32;   // column inside the 256-column tile
+                    if (p.dbg & 4) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
+                        continue;
+                    }
+                    float kc[32];
+                    if (MODE == MODE_DA) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + cb);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = __ldg(b4 + e);
+                            kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                        }
+                    } else {
+                        const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 kv = k4[e];
+                            kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
+                        }
+                    }
+                    float val[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        val[e] = ex2f(fmaf(__uint_as_float(acc[sp * 2 + g][e]), c1, kc[e] + krow));
+                    if (MODE == MODE_DW) {
+                        if (any_neg) {
+                            const float* sg = kbuf + NT + cb;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) val[e] *= sg[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) db_acc += val[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                }
+                // Sub-pass n = 2i + sp may overwrite the P' tile once the G pass of sub-pass n - 1 has completed
+                // (completion #n of bar_pempty, parity (n - 1) & 1).  Every thread waits for every sub-pass in
+                // order, so the parity wait never has to look more than one phase ahead.
+                mbar_wait(bar_pempty, sp ^ 1);
+                if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {        // this thread's 64 columns = 8 chunks of 16 B in block ch
+                    uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+                    *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                }
+                if (MODE == MODE_DA) {
+                    const int cbl = p.blank - c0, clb = label - c0;
+                    if (cbl >= ch * 64 && cbl < ch * 64 + 64)
+                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
+                    if (clb >= ch * 64 && clb < ch * 64 + 64)
+                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+                } else {
+                    epi_sync();                         // column owners patch rows written by other threads
+                    if ((et >> 7) == sp) {
+                        const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
+                        if (rbl >= 0 && rbl < kTile)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
+                        if (rlb >= 0 && rlb < kTile)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
+                    }
+                }
+                fence_proxy_async_smem();
+                epi_arrive(bar_pfull);
+                if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
             }
-            if (MODE == MODE_DA) {
-                const int cbl = p.blank - c0, clb = label - c0;
-                if (cbl >= 0 && cbl < 128)
-                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
-                if (clb >= 0 && clb < 128)
-                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
-            } else {
-                half_sync();                            // column owners patch rows written by other threads
-                const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
-                if (rbl >= 0 && rbl < kTile)
-                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
-                if (rlb >= 0 && rlb < kTile)
-                    *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
-            }
-            fence_proxy_async_smem();
-            epi_arrive(bar_pfull);
-            if (et == 0) trace_at(p, 2, i, 3);
         }
         // ---- final: G (128 x HH fp32 in TMEM) -> global
         mbar_wait(bar_gfull, 0);
