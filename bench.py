@@ -116,7 +116,7 @@ def cpu_port_step(w, B_s, seed=1234):
     t0 = time.perf_counter()
     loss = crit(joint(enc[:, :, None], pred[:, None]), labels, act_lens, label_lens)
     loss.backward()
-    float(loss)
+    loss.item()
     return time.perf_counter() - t0
 
 
@@ -222,7 +222,7 @@ def main():
         p_.requires_grad_()
         loss = crit(model(e[:, :, None], p_[:, None]), lab, al, ll)
         loss.backward()
-        return float(loss)          # device -> host read of the step's result
+        return loss.item()          # device -> host read of the step's result
 
     def barrier():
         if dist is not None:

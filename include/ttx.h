@@ -45,19 +45,21 @@ int64_t ttx_meta_ints(int B, int64_t n_tiles_ub);
 int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int64_t n_tiles_ub,
                 int32_t* meta, int device, void* stream);
 
-/* W_out (V,H) fp32 -> 16-bit tensor-core operand (Vpad = 128 * ceil(V/128) rows, zero padded), and
+/* W_out (V,H) fp32 -> 16-bit tensor-core operand (Vpad = 256 * ceil(V/256) rows, zero padded), and
  * bias2 (Vpad) = b_out * log2(e), -inf on the padding rows.
  * bf16 = 0: fp16 scaled by a power of two w_scale; bf16 = 1: bfloat16.  scal: 8 floats
  * {w_scale, 1/w_scale, gmax, any-negative-grad flag (both set by ttx_grad_coeffs), scratch...}. */
 int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf16, float* scal, void* w16,
-                    float* bias2, int device, void* stream);
+                    float* bias2, void* w16t /* NULL or (H, Vpad): transposed copy for the gradient pass */,
+                    int device, void* stream);
 
 /* A16[row,:] = 16-bit(tanh(eproj[b,t,:] + pproj[b,u,:])) for every lattice cell; row_label[row] = label
  * emitted from the cell's u (labels[b,u]) or -1.  eproj (B,T,H), pproj (B,U1,H) fp32 contiguous;
  * labels (B, label_stride) int32, entries at u >= label_lens[b] are never read. */
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
-                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, int device, void* stream);
+                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label,
+                  void* a16t /* NULL or (H, rows): transposed copy for the gradient pass */, int device, void* stream);
 
 /* tcgen05 projection A16 . W16^T + b_out fused with log-softmax statistics: per row lse, log p(blank),
  * log p(label).  The (B,T,U1,V) logits are never written. */

@@ -80,11 +80,14 @@ def run(stage, B, T, U, V, H):
     scal = torch.zeros(8, dtype=torch.float32, device=dev)
     w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
     bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
-    _lib.check(lib.ttx_cast_weight(_p(Wd), _p(bd), V, H, 0, _p(scal), _p(w16), _p(bias2), 0, st), "cast")
+    use_t = H in (128, 256, 512) and os.environ.get("TTX_STAGE_TRANSPOSE", "fused") == "fused"
+    w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if use_t else None
+    _lib.check(lib.ttx_cast_weight(_p(Wd), _p(bd), V, H, 0, _p(scal), _p(w16), _p(bias2), _p(w16t), 0, st), "cast")
     a16 = torch.empty(rows * H, dtype=torch.int16, device=dev)
     row_label = torch.empty(rows, dtype=torch.int32, device=dev)
+    a16t = torch.empty(H * rows, dtype=torch.int16, device=dev) if use_t else None
     _lib.check(lib.ttx_joint_act(_p(Ed), _p(Pd), _p(labd), _p(ald), _p(lld), _p(meta), B, T, U1, H, U, ntub, 0,
-                                 _p(a16), _p(row_label), 0, st), "act")
+                                 _p(a16), _p(row_label), _p(a16t), 0, st), "act")
     torch.cuda.synchronize()
     ws = float(scal[0])
     print("w_scale %g (model %g)" % (ws, m["w_scale"]), flush=True)
@@ -168,8 +171,7 @@ def run(stage, B, T, U, V, H):
     d_act = f32(rows * H)
     dW = torch.zeros(V, H, dtype=torch.float32, device=dev)
     splits = int(os.environ.get("TTX_SPLITS", "2"))
-    a16t = w16t = None
-    if H in (128, 256, 512):
+    if H in (128, 256, 512) and not use_t:      # separate-transpose path (ttx_transpose16)
         w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev)
         a16t = torch.empty(H * rows, dtype=torch.int16, device=dev)
         _lib.check(lib.ttx_transpose16(_p(w16), _p(w16t), Vpad, H, None, 0, st), "transpose w")

@@ -18,9 +18,9 @@ void set_error(const char* fmt, ...) {
 
 // launchers (ttx_small.cu / ttx_joint_mma.cu)
 int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
-int launch_cast_w(const float*, const float*, int, int, int, bool, float*, void*, float*, cudaStream_t);
+int launch_cast_w(const float*, const float*, int, int, int, bool, float*, void*, float*, void*, cudaStream_t);
 int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
-                     int, int, bool, void*, int*, cudaStream_t);
+                     int, int, bool, void*, int*, void*, cudaStream_t);
 int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, double*, double*, float*,
                    double*, cudaStream_t);
 int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
@@ -91,23 +91,23 @@ int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T
 }
 
 int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf16, float* scal, void* w16,
-                    float* bias2, int device, void* stream) {
+                    float* bias2, void* w16t, int device, void* stream) {
     TTX_REQUIRE(w_out && b_out && scal && w16 && bias2, "ttx_cast_weight: null pointer");
     TTX_REQUIRE(V > 0 && H > 0 && H % 8 == 0, "ttx_cast_weight: bad shape V=%d H=%d", V, H);
     TTX_ENTER(device);
     const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
-    return launch_cast_w(w_out, b_out, V, Vpad, H, bf16 != 0, scal, w16, bias2, (cudaStream_t)stream);
+    return launch_cast_w(w_out, b_out, V, Vpad, H, bf16 != 0, scal, w16, bias2, w16t, (cudaStream_t)stream);
 }
 
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
-                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, int device, void* stream) {
+                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, void* a16t, int device, void* stream) {
     TTX_REQUIRE(eproj && pproj && act_lens && label_lens && meta && a16 && row_label, "ttx_joint_act: null pointer");
     TTX_REQUIRE(labels || U1 == 1, "ttx_joint_act: labels is null");
-    TTX_REQUIRE(H > 0 && H % 8 == 0, "ttx_joint_act: H=%d must be a positive multiple of 8", H);
+    TTX_REQUIRE(H > 0 && H % 64 == 0, "ttx_joint_act: H=%d must be a positive multiple of 64", H);
     TTX_ENTER(device);
     return launch_joint_act(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1, H, label_stride,
-                            (int)n_tiles_ub, bf16 != 0, a16, row_label, (cudaStream_t)stream);
+                            (int)n_tiles_ub, bf16 != 0, a16, row_label, a16t, (cudaStream_t)stream);
 }
 
 int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, const float* scal,

@@ -79,7 +79,7 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
 template <bool BF16>
 __global__ void cast_w_kernel(const float* __restrict__ w, const float* __restrict__ b_out, int V, int Vpad, int H,
                               const unsigned int* __restrict__ absmax_bits, float* __restrict__ scal,
-                              uint16_t* __restrict__ w16, float* __restrict__ bias2) {
+                              uint16_t* __restrict__ w16, float* __restrict__ bias2, uint16_t* __restrict__ w16t) {
     float ws = 1.f;
     if (!BF16) {
         const float m = __uint_as_float(*absmax_bits);
@@ -105,7 +105,13 @@ __global__ void cast_w_kernel(const float* __restrict__ w, const float* __restri
             a = v.x * ws;
             b = v.y * ws;
         }
-        reinterpret_cast<uint32_t*>(w16)[i] = pack16<BF16>(a, b);
+        const uint32_t pk = pack16<BF16>(a, b);
+        reinterpret_cast<uint32_t*>(w16)[i] = pk;
+        if (w16t) {   // W16^T (H, Vpad): 4 MB, written uncoalesced once per step (the matrix lives in L2)
+            const int col = (int)(e0 - (size_t)row * H);
+            w16t[(size_t)col * Vpad + row] = (uint16_t)(pk & 0xffff);
+            w16t[(size_t)(col + 1) * Vpad + row] = (uint16_t)(pk >> 16);
+        }
     }
 }
 
@@ -117,7 +123,8 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
                                  const int* __restrict__ labels, const int* __restrict__ act_lens,
                                  const int* __restrict__ label_lens, const int* __restrict__ meta, int B, int T,
                                  int U1, int H, int label_stride, uint16_t* __restrict__ a16,
-                                 int* __restrict__ row_label) {
+                                 int* __restrict__ row_label, uint16_t* __restrict__ a16t, size_t rows_total) {
+    __shared__ uint16_t tr[64][kTile + 2];       // one 64-column slab of the tile, for the transposed copy
     const int tile = blockIdx.x;
     if (tile >= meta[0]) {
         // CTA pairs work on tile pairs: with an odd tile count the partner of the last tile must read zeros
@@ -125,6 +132,10 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
             uint4* dst = reinterpret_cast<uint4*>(a16 + (size_t)tile * kTile * H);
             for (int idx = threadIdx.x; idx < kTile * H / 8; idx += blockDim.x) dst[idx] = make_uint4(0, 0, 0, 0);
             for (int lr = threadIdx.x; lr < kTile; lr += blockDim.x) row_label[(size_t)tile * kTile + lr] = -1;
+            if (a16t)
+                for (int idx = threadIdx.x; idx < H * (kTile / 8); idx += blockDim.x)
+                    *reinterpret_cast<uint4*>(a16t + (size_t)(idx / (kTile / 8)) * rows_total + (size_t)tile * kTile +
+                                              (idx % (kTile / 8)) * 8) = make_uint4(0, 0, 0, 0);
         }
         return;
     }
@@ -132,24 +143,45 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
     const int r0 = (tile - meta[kMetaHdr + b]) * kTile;
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
     const int nrows = Tb * U1b;
-    const int vec_per_row = H / 8;
     const float* eb = eproj + (size_t)b * T * H;
     const float* pb = pproj + (size_t)b * U1 * H;
-    for (int idx = threadIdx.x; idx < kTile * vec_per_row; idx += blockDim.x) {
-        const int lr = idx / vec_per_row, vc = idx - lr * vec_per_row;
-        const int r = r0 + lr;
-        uint4 out = make_uint4(0, 0, 0, 0);
-        if (r < nrows) {
-            const int t = r / U1b, u = r - t * U1b;
-            const float4* e4 = reinterpret_cast<const float4*>(eb + (size_t)t * H + vc * 8);
-            const float4* p4 = reinterpret_cast<const float4*>(pb + (size_t)u * H + vc * 8);
-            const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
-            out.x = pack16<BF16>(tanhf(e0.x + p0.x), tanhf(e0.y + p0.y));
-            out.y = pack16<BF16>(tanhf(e0.z + p0.z), tanhf(e0.w + p0.w));
-            out.z = pack16<BF16>(tanhf(e1.x + p1.x), tanhf(e1.y + p1.y));
-            out.w = pack16<BF16>(tanhf(e1.z + p1.z), tanhf(e1.w + p1.w));
+    // 64-column slabs: 8 vectors of 8 columns per row; the slab is also staged in shared memory and written out
+    // transposed (A16^T[h][row], 256 contiguous bytes per joint column) for the gradient pass's K-major operand.
+    for (int h0 = 0; h0 < H; h0 += 64) {
+        for (int idx = threadIdx.x; idx < kTile * 8; idx += blockDim.x) {
+            const int lr = idx >> 3, vc = (h0 >> 3) + (idx & 7);
+            const int r = r0 + lr;
+            uint4 out = make_uint4(0, 0, 0, 0);
+            if (r < nrows) {
+                const int t = r / U1b, u = r - t * U1b;
+                const float4* e4 = reinterpret_cast<const float4*>(eb + (size_t)t * H + vc * 8);
+                const float4* p4 = reinterpret_cast<const float4*>(pb + (size_t)u * H + vc * 8);
+                const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
+                out.x = pack16<BF16>(tanhf(e0.x + p0.x), tanhf(e0.y + p0.y));
+                out.y = pack16<BF16>(tanhf(e0.z + p0.z), tanhf(e0.w + p0.w));
+                out.z = pack16<BF16>(tanhf(e1.x + p1.x), tanhf(e1.y + p1.y));
+                out.w = pack16<BF16>(tanhf(e1.z + p1.z), tanhf(e1.w + p1.w));
+            }
+            *reinterpret_cast<uint4*>(a16 + ((size_t)tile * kTile + lr) * H + vc * 8) = out;
+            if (a16t) {
+                const int c = (idx & 7) * 8;
+                const uint32_t w4[4] = {out.x, out.y, out.z, out.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tr[c + 2 * e][lr] = (uint16_t)(w4[e] & 0xffff);
+                    tr[c + 2 * e + 1][lr] = (uint16_t)(w4[e] >> 16);
+                }
+            }
         }
-        *reinterpret_cast<uint4*>(a16 + ((size_t)tile * kTile + lr) * H + vc * 8) = out;
+        if (a16t) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < 64 * (kTile / 2); idx += blockDim.x) {
+                const int c = idx / (kTile / 2), r2 = idx % (kTile / 2);
+                const uint32_t v = (uint32_t)tr[c][2 * r2] | ((uint32_t)tr[c][2 * r2 + 1] << 16);
+                *reinterpret_cast<uint32_t*>(a16t + (size_t)(h0 + c) * rows_total + (size_t)tile * kTile + 2 * r2) = v;
+            }
+            __syncthreads();
+        }
     }
     for (int lr = threadIdx.x; lr < kTile; lr += blockDim.x) {
         const int r = r0 + lr;
@@ -192,10 +224,12 @@ int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_
 // ------------------------------------------------------------------------------------------- lattice
 // The recursion runs in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
 // ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).
+// The carrier stays float64; the increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 (absolute
+// error ~6e-8 per cell, a random walk of ~2e-6 over a 1200-step lattice).
 __device__ __forceinline__ double log_add(double a, double b) {
     const double mx = fmax(a, b), mn = fmin(a, b);
     if (mx == -INFINITY) return -INFINITY;
-    return mx + log1p(exp(mn - mx));
+    return mx + (double)log1pf(expf((float)(mn - mx)));
 }
 
 // grid = 2B: block b computes alpha of utterance b, block B + b computes beta.  Thread u owns column u and
@@ -517,26 +551,31 @@ int launch_prep(const int* act_lens, const int* label_lens, int B, int T, int U1
 }
 
 int launch_cast_w(const float* w, const float* b_out, int V, int Vpad, int H, bool bf16, float* scal, void* w16,
-                  float* bias2, cudaStream_t s) {
+                  float* bias2, void* w16t, cudaStream_t s) {
     unsigned int* bits = reinterpret_cast<unsigned int*>(scal + 4);
     TTX_CUDA_OK(cudaMemsetAsync(bits, 0, sizeof(unsigned int), s));
     const size_t n = (size_t)V * H;
     if (!bf16) absmax_kernel<<<296, 256, 0, s>>>(w, n, bits);
-    if (bf16) cast_w_kernel<true><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2);
-    else cast_w_kernel<false><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2);
+    if (bf16)
+        cast_w_kernel<true><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2, (uint16_t*)w16t);
+    else
+        cast_w_kernel<false><<<592, 256, 0, s>>>(w, b_out, V, Vpad, H, bits, scal, (uint16_t*)w16, bias2, (uint16_t*)w16t);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_joint_act(const float* eproj, const float* pproj, const int* labels, const int* act_lens,
                      const int* label_lens, const int* meta, int B, int T, int U1, int H, int label_stride,
-                     int n_tiles_ub, bool bf16, void* a16, int* row_label, cudaStream_t s) {
+                     int n_tiles_ub, bool bf16, void* a16, int* row_label, void* a16t, cudaStream_t s) {
+    const size_t rows_total = (size_t)n_tiles_ub * kTile;
     if (bf16)
         joint_act_kernel<true><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1,
-                                                         H, label_stride, (uint16_t*)a16, row_label);
+                                                         H, label_stride, (uint16_t*)a16, row_label, (uint16_t*)a16t,
+                                                         rows_total);
     else
         joint_act_kernel<false><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T,
-                                                          U1, H, label_stride, (uint16_t*)a16, row_label);
+                                                          U1, H, label_stride, (uint16_t*)a16, row_label,
+                                                          (uint16_t*)a16t, rows_total);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

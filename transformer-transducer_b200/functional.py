@@ -85,6 +85,22 @@ class _Plan:
         return rowmeta
 
 
+def _dw_splits(sms, V, H, ntub):
+    """Lattice-row splits of the weight-gradient grid: CTA pairs = ceil(V/256) * slabs * splits should fill whole
+    waves of sms/2 pair slots (the kernel is one pair per SM pair), with enough stream tiles left per CTA."""
+    pairs0 = ((V + 255) // 256) * (2 if H > 256 else 1)
+    slots = max(1, sms // 2)
+    best, best_eff = 1, 0.0
+    for s in range(1, 65):
+        if s > 1 and (ntub + 1) // 2 < 16 * s:
+            break
+        pairs = pairs0 * s
+        eff = pairs / (slots * -(-pairs // slots))
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
 def supported_width(H):
     return bool(_lib.get().ttx_supported_h(int(H)))
 
@@ -92,6 +108,7 @@ def supported_width(H):
 class FusedJointRNNT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16):
+        need_grad = any(ctx.needs_input_grad[:4])      # (grad mode is off inside Function.forward)
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
         dev = eproj.device
@@ -115,13 +132,18 @@ class FusedJointRNNT(torch.autograd.Function):
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
             bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
-            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), plan.idx, st)
+            # K-major (transposed) copies of both operands feed the gradient pass of the backward pair kernel
+            with_t = need_grad and H in (128, 256, 512)
+            w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if with_t else None
+            a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev) if with_t else None
+            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
+                  plan.idx, st)
             a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
                                          _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
-                                         _p(a16), _p(row_label), plan.idx, st)
+                                         _p(a16), _p(row_label), _p(a16t), plan.idx, st)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                                              plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
@@ -129,6 +151,7 @@ class FusedJointRNNT(torch.autograd.Function):
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
+        ctx.transposed = (a16t, w16t)
         ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
         return costs
 
@@ -149,18 +172,8 @@ class FusedJointRNNT(torch.autograd.Function):
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
             d_act = plan.rowf(H) if need_act else None
             if need_act or need_w:
-                # K-major copies of both operands for the gradient pass of the pair kernel
-                a16t = w16t = None
-                if H in (128, 256, 512):
-                    Vpad = w16.numel() // H
-                    w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev)
-                    a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev)
-                    _call("ttx_transpose16", dev, _p(w16), _p(w16t), Vpad, H, None, plan.idx, st)
-                    _call("ttx_transpose16", dev, _p(a16), _p(a16t), plan.rows, H, _p(plan.meta), plan.idx, st)
-                sms = torch.cuda.get_device_properties(dev).multi_processor_count
-                n_vt = (V + 127) // 128
-                halves = 2 if H > 256 else 1
-                splits = max(1, min(plan.ntub, (sms * 4) // (n_vt * halves)))
+                a16t, w16t = ctx.transposed
+                splits = _dw_splits(torch.cuda.get_device_properties(dev).multi_processor_count, V, H, plan.ntub)
                 # two launches (activation gradient, weight gradient) so each shows up separately in profiles
                 if need_act:
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
