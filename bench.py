@@ -32,6 +32,9 @@ WORKLOADS = {
     # BASELINE.json configs[3]: long-utterance stress (dense logits would be 54 GB)
     "cfg4": dict(B=16, T=1000, U=200, V=4232, D=512, H=512, joint="espnet", ragged=False,
                  desc="long-utterance stress B=16 T=1000 U=200 V=4232 D=512 H=512 fp32"),
+    # BASELINE.json configs[4]: ragged batch, T in [50,1000], U in [5,200], bf16 joint inputs (espnet dims, V=4233)
+    "cfg5": dict(B=32, T=1000, U=200, V=4233, D=512, H=512, joint="espnet", ragged=True, bf16=True,
+                 desc="ragged batch B=32 T~U[50,1000] U~U[5,200] V=4233 D=512 H=512 bf16 joint inputs"),
 }
 
 
@@ -52,6 +55,14 @@ def synth(w, seed, device=None, pin=False):
     labels = torch.randint(1, V, (B, U), generator=g, dtype=torch.int32)
     act_lens = torch.full((B,), T, dtype=torch.int32)
     label_lens = torch.full((B,), U, dtype=torch.int32)
+    if w.get("ragged"):
+        act_lens = torch.randint(50, T + 1, (B,), generator=g, dtype=torch.int32)
+        label_lens = torch.randint(5, U + 1, (B,), generator=g, dtype=torch.int32)
+        act_lens[0], label_lens[0] = T, U          # one utterance at the maxima so the length checks pass
+        for i in range(B):
+            labels[i, int(label_lens[i]):] = -1      # tt/dataset.py:46-48 padding
+    if w.get("bf16"):
+        enc, pred = enc.bfloat16(), pred.bfloat16()
     out = [enc, pred, labels, act_lens, label_lens]
     if pin:
         out = [t.pin_memory() for t in out]
@@ -195,6 +206,8 @@ def main():
 
     torch.manual_seed(1234)
     joint = ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh").to(dev)
+    if w.get("bf16"):
+        joint = joint.bfloat16()
     model = joint
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(joint, device_ids=[local], gradient_as_bucket_view=True)
@@ -269,7 +282,7 @@ def main():
         per.setdefault(name, []).append(e0.elapsed_time(e1))
         launches += nk
     table = {k: {"calls": len(v), "avg_ms": sum(v) / len(v)} for k, v in per.items()}
-    M = w["B"] * w["T"] * (w["U"] + 1)
+    M = int((act_lens.long() * (label_lens.long() + 1)).sum())      # lattice cells actually present
     unit_flops = 2.0 * M * w["H"] * w["V"]           # one M x H x V contraction (F = 3 of these)
     pk = peaks()
     dom = max((k for k in table if k.startswith("ttx_joint_")), key=lambda k: table[k]["avg_ms"])
