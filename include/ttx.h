@@ -88,6 +88,16 @@ int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_lab
  *                                      before ttx_grad_coeffs, which adds the sparse part of dL/db_out)
  * `splits` = lattice-row splits of the weight-gradient grid (>= 1).  a16t / w16t (transposed operand copies from
  * ttx_transpose16) may be NULL: the kernels then read the gradient pass's B operand MN-major from a16 / w16. */
+/* Wide-joint (H outside the fused kernels) chunked path.  z (rows, Vpad) fp32 = A16[chunk] . W16^T from a library GEMM
+ * (un-biased, scaled by w_scale).  ttx_rows_lse: per-row lse / log p(blank) / log p(label).  ttx_rows_grad: q (rows, Vpad)
+ * 16-bit = scale * w * (softmax - rb [blank] - rl [label]), the operand of both gradient GEMMs.  Replaces the same
+ * reference lines as ttx_joint_lse_fwd / ttx_joint_grad for those widths. */
+int ttx_rows_lse(const float* z, int rows, int Vpad, int V, const float* bias2, const float* scal,
+                 const int32_t* row_label, int blank, float* lse, float* lp_blank, float* lp_label, int device,
+                 void* stream);
+int ttx_rows_grad(const float* z, const void* rowmeta, const int32_t* row_label, const float* bias2,
+                  const float* scal, int rows, int Vpad, int V, int blank, int bf16, void* q, int device, void* stream);
+
 /* out (cols, rows) = transpose of the row-major 16-bit matrix in (rows, cols); rows, cols multiples of 64.
  * meta != NULL: `in` is the A16 operand and row blocks beyond the tiles in use (meta[0]) are skipped.  Produces the
  * K-major operand copies W16^T (H, Vpad) and A16^T (H, rows) streamed by the backward pair kernel. */

@@ -195,11 +195,43 @@ def test_fused_tt_jointnet_split_first_layer_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
+@pytest.mark.parametrize("H,V", [(1024, 4232), (2048, 700)])
+def test_wide_joint_chunked_path_matches_oracle(H, V, monkeypatch):
+    """aishell.yaml (H=1024) / joint_streaming.yaml (H=2048) joint widths: lazy handle + chunked path (library GEMM on
+    the 16-bit operands + our row kernels), several chunks, ragged lengths."""
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setattr(Fn.ChunkedJointRNNT, "CHUNK_BYTES", 3 * 128 * ((V + 255) // 256 * 256) * 4)   # 3 tiles / chunk
+    torch.manual_seed(H)
+    B, T, U, D = 3, 40, 9, 64
+    ref = joint_ref.TTJointNet(2 * D, H, V)
+    mine = ttb.JointNet(2 * D, H, V)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    enc, dec = torch.randn(B, T, D), torch.randn(B, U + 1, D)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    al, ll = _i32([T, T - 9, 7]), _i32([U, U - 4, 0])
+    labels[1, U - 4:] = -1
+    labels[2, :] = -1
+    e0, d0 = enc.clone().requires_grad_(), dec.clone().requires_grad_()
+    want = rnnt_oracle.rnnt_loss(ref(e0, d0), labels, al, ll, 0, "none")
+    (want * torch.tensor([1.0, 2.0, 0.5])).sum().backward()
+    e1, d1 = enc.to(DEV).requires_grad_(), dec.to(DEV).requires_grad_()
+    z = mine(e1, d1)
+    assert isinstance(z, ttb.LazyJointLogits)
+    got = ttb.rnnt_loss(z, labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")
+    (got * torch.tensor([1.0, 2.0, 0.5], device=DEV)).sum().backward()
+    assert float(((got.cpu() - want.detach()) / want.detach()).abs().max()) < LOSS_TOL
+    assert rel(e1.grad, e0.grad) < GRAD_TOL and rel(d1.grad, d0.grad) < GRAD_TOL
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert rel(a.grad, b.grad) < GRAD_TOL, n
+    assert e1.grad[2, 7:].abs().max() == 0 and d1.grad[2, 1:].abs().max() == 0
+
+
 def test_unsupported_width_uses_dense_entry_and_matches_oracle():
-    """aishell.yaml's joint width 1024 is outside the fused kernels: the module returns dense logits and the loss
-    runs through the dense-logits CUDA entry."""
+    """A joint width that is not a multiple of 64 is outside every fused path: the module returns dense logits and
+    the loss runs through the dense-logits CUDA entry."""
     torch.manual_seed(8)
-    B, T, U, V, D, H = 2, 12, 4, 97, 32, 1024
+    B, T, U, V, D, H = 2, 12, 4, 97, 32, 1000
     ref = joint_ref.TTJointNet(2 * D, H, V)
     mine = ttb.JointNet(2 * D, H, V)
     mine.load_state_dict(ref.state_dict())
@@ -230,6 +262,17 @@ def test_c_abi_rejects_unsupported_width_with_message():
     p = lambda t: t.data_ptr()  # noqa: E731
     rc = lib.ttx_joint_lse_fwd(p(x), p(x), p(x), p(x), p(x), p(x), 1, 1024, 10, 0, 0, p(x), p(x), p(x), 0, None)
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
+
+
+@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {}])
+def test_kernel_variants_agree_with_oracle(env, monkeypatch):
+    """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0) and the default pair kernels all
+    meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)
+    errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))                 # a negative grad_output too
+    _check(errs)
 
 
 # ----------------------------------------------------------------------------- full-size properties (configs[1])

@@ -33,6 +33,10 @@ int launch_dense_lse(const float*, const int*, const int*, const int*, const int
 int launch_dense_grad(const float*, const float4*, const int*, const float*, const int*, const int*, const int*, int,
                       int, int, int, int, float*, cudaStream_t);
 int launch_transpose16(const void*, void*, int, int, const int*, cudaStream_t);
+int launch_rows_lse(const float*, int, int, int, const float*, const float*, const int*, int, float*, float*, float*,
+                    cudaStream_t);
+int launch_rows_grad(const float*, const float4*, const int*, const float*, const float*, int, int, int, int, bool,
+                     void*, cudaStream_t);
 bool mma_supported_h(int H);
 int launch_joint_fwd(const void*, const void*, uint64_t, int, int, int, int, bool, const int*, const float*,
                      const float*, const int*, int, float*, float*, float*, cudaStream_t);
@@ -143,6 +147,24 @@ int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_lab
     TTX_ENTER(device);
     return launch_grad_prep(lse, lp_blank, lp_label, alpha, beta, ll_beta, grad_costs, scal, row_label, act_lens,
                             label_lens, meta, B, blank, (int)n_tiles_ub, (float4*)rowmeta, d_b_out,
+                            (cudaStream_t)stream);
+}
+
+int ttx_rows_lse(const float* z, int rows, int Vpad, int V, const float* bias2, const float* scal,
+                 const int32_t* row_label, int blank, float* lse, float* lp_blank, float* lp_label, int device,
+                 void* stream) {
+    TTX_REQUIRE(z && bias2 && scal && row_label && lse && lp_blank && lp_label, "ttx_rows_lse: null pointer");
+    TTX_REQUIRE(rows > 0 && V > 0 && Vpad >= V && blank >= 0 && blank < V, "ttx_rows_lse: bad shape");
+    TTX_ENTER(device);
+    return launch_rows_lse(z, rows, Vpad, V, bias2, scal, row_label, blank, lse, lp_blank, lp_label, (cudaStream_t)stream);
+}
+
+int ttx_rows_grad(const float* z, const void* rowmeta, const int32_t* row_label, const float* bias2,
+                  const float* scal, int rows, int Vpad, int V, int blank, int bf16, void* q, int device, void* stream) {
+    TTX_REQUIRE(z && rowmeta && row_label && bias2 && scal && q, "ttx_rows_grad: null pointer");
+    TTX_REQUIRE(rows > 0 && V > 0 && Vpad >= V && Vpad % 2 == 0, "ttx_rows_grad: bad shape");
+    TTX_ENTER(device);
+    return launch_rows_grad(z, (const float4*)rowmeta, row_label, bias2, scal, rows, Vpad, V, blank, bf16 != 0, q,
                             (cudaStream_t)stream);
 }
 

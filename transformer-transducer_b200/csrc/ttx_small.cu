@@ -542,6 +542,98 @@ __global__ void dense_grad_kernel(const float* __restrict__ acts, const float4* 
     }
 }
 
+// ------------------------------------------------------------------------------------------- chunked wide-joint path
+// Joint widths outside the fused tensor-core kernels (H = 1024, 2048 in the reference's configs): the host loops over
+// chunks of lattice rows, the projection of a chunk runs as a library GEMM on the 16-bit operands (fp32 out), and
+// these two kernels do everything else on the chunk, so memory stays bounded by the chunk, never B*T*U*V.
+//   z: (R, Vpad) fp32 = A16[chunk] . W16^T  (un-biased, still scaled by w_scale);  one warp per row.
+__global__ void rows_lse_kernel(const float* __restrict__ z, int R, int Vpad, int V, const float* __restrict__ bias2,
+                                const float* __restrict__ scal, const int* __restrict__ row_label, int blank,
+                                float* __restrict__ lse, float* __restrict__ lpb, float* __restrict__ lpl) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= R) return;
+    const float c1 = scal[1] * kLog2e;
+    const float* row = z + (size_t)r * Vpad;
+    float m = -INFINITY, s = 0.f;
+    for (int v = lane; v < V; v += 32) {
+        const float y = fmaf(__ldg(row + v), c1, __ldg(bias2 + v));
+        const float mn = fmaxf(m, y);
+        s = s * ex2f(m - mn) + ex2f(y - mn);
+        m = mn;
+    }
+    for (int o = 16; o; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mn = fmaxf(m, m2);
+        s = ((m > -INFINITY) ? s * ex2f(m - mn) : 0.f) + ((m2 > -INFINITY) ? s2 * ex2f(m2 - mn) : 0.f);
+        m = mn;
+    }
+    if (lane == 0) {
+        const float l2 = m + lg2f(s);
+        const int lab = row_label[r];
+        lse[r] = l2 * kLn2;
+        lpb[r] = (fmaf(row[blank], c1, bias2[blank]) - l2) * kLn2;
+        lpl[r] = (lab >= 0) ? (fmaf(row[lab], c1, bias2[lab]) - l2) * kLn2 : 0.f;
+    }
+}
+
+// q[r, v] = 16-bit(scale * w_r * (softmax(r, v) - rb [v == blank] - rl [v == label])) for v < V, 0 on the padding
+// columns: the operand of both gradient GEMMs (dA = q . W16, dW = q^T . A16).  Also db[v] += w_r * gmax * (...).
+template <bool BF16>
+__global__ void rows_grad_kernel(const float* __restrict__ z, const float4* __restrict__ rowmeta,
+                                 const int* __restrict__ row_label, const float* __restrict__ bias2,
+                                 const float* __restrict__ scal, int R, int Vpad, int V, int blank,
+                                 uint16_t* __restrict__ q) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= R) return;
+    const float c1 = scal[1] * kLog2e;
+    const float pscale = BF16 ? 1.f : kPScale;
+    const float4 rm = rowmeta[r];
+    const int lab = row_label[r];
+    const float k = fmaf(rm.x, -kLog2e, 0.f);       // -lse2 (+inf lse on padding rows -> -inf -> zeros)
+    const float wq = rm.w * pscale;
+    const float* row = z + (size_t)r * Vpad;
+    uint16_t* out = q + (size_t)r * Vpad;
+    for (int v = lane * 2; v < Vpad; v += 64) {
+        float a = 0.f, b = 0.f;
+        if (v < V) {
+            a = ex2f(fmaf(__ldg(row + v), c1, __ldg(bias2 + v) + k));
+            if (v == blank) a = rm.y;
+            if (v == lab) a = rm.z;
+            a *= wq;
+        }
+        if (v + 1 < V) {
+            b = ex2f(fmaf(__ldg(row + v + 1), c1, __ldg(bias2 + v + 1) + k));
+            if (v + 1 == blank) b = rm.y;
+            if (v + 1 == lab) b = rm.z;
+            b *= wq;
+        }
+        *reinterpret_cast<uint32_t*>(out + v) = pack16<BF16>(a, b);
+    }
+}
+
+int launch_rows_lse(const float* z, int R, int Vpad, int V, const float* bias2, const float* scal,
+                    const int* row_label, int blank, float* lse, float* lpb, float* lpl, cudaStream_t s) {
+    const int wpb = 8;
+    rows_lse_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, s>>>(z, R, Vpad, V, bias2, scal, row_label, blank, lse, lpb, lpl);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_rows_grad(const float* z, const float4* rowmeta, const int* row_label, const float* bias2,
+                     const float* scal, int R, int Vpad, int V, int blank, bool bf16, void* q, cudaStream_t s) {
+    const int wpb = 8;
+    if (bf16)
+        rows_grad_kernel<true><<<(R + wpb - 1) / wpb, wpb * 32, 0, s>>>(z, rowmeta, row_label, bias2, scal, R, Vpad, V,
+                                                                        blank, (uint16_t*)q);
+    else
+        rows_grad_kernel<false><<<(R + wpb - 1) / wpb, wpb * 32, 0, s>>>(z, rowmeta, row_label, bias2, scal, R, Vpad, V,
+                                                                         blank, (uint16_t*)q);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- launchers
 int launch_prep(const int* act_lens, const int* label_lens, int B, int T, int U1, int n_tiles_ub, int* meta,
                 cudaStream_t s) {

@@ -23,7 +23,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -195,12 +195,123 @@ class FusedJointRNNT(torch.autograd.Function):
                 None, None, None, None, None)
 
 
+class ChunkedJointRNNT(torch.autograd.Function):
+    """Same contract as FusedJointRNNT for joint widths the fused tensor-core kernels do not cover (any multiple of
+    64, e.g. aishell.yaml's 1024 and joint_streaming.yaml's 2048): lattice rows are processed in chunks, the
+    projection of a chunk is a library GEMM on the same 16-bit operands (fp32 accumulate), our row kernels do the
+    log-softmax statistics / the gradient operand, and memory stays bounded by the chunk."""
+
+    CHUNK_BYTES = 512 << 20
+
+    @staticmethod
+    def _chunks(plan, Vpad):
+        tiles = max(1, ChunkedJointRNNT.CHUNK_BYTES // (128 * Vpad * 4))
+        return [(t0, min(plan.ntub, t0 + tiles)) for t0 in range(0, plan.ntub, tiles)]
+
+    @staticmethod
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16):
+        if not eproj.is_cuda:
+            raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
+        dev = eproj.device
+        B, T, H = eproj.shape
+        U1 = pproj.shape[1]
+        V = w_out.shape[0]
+        if H % 64 != 0:
+            raise ValueError("joint width %d must be a multiple of 64" % H)
+        ep, pp = eproj.detach().float().contiguous(), pproj.detach().float().contiguous()
+        w, b = w_out.detach().float().contiguous(), b_out.detach().float().contiguous()
+        labels = labels.contiguous()
+        dt16 = torch.bfloat16 if bf16 else torch.float16
+        with torch.cuda.device(dev):
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            st = _stream(dev)
+            Vpad = (V + 255) // 256 * 256
+            scal = torch.zeros(8, dtype=torch.float32, device=dev)
+            w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
+            bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
+            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), None, plan.idx, st)
+            a16 = torch.zeros(plan.rows * H, dtype=torch.int16, device=dev)   # unused tiles must be zeros, not NaNs
+            row_label = torch.full((plan.rows,), -1, dtype=torch.int32, device=dev)
+            lstride = labels.shape[1] if labels.dim() == 2 else 0
+            _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
+                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
+                  None, plan.idx, st)
+            lse, lpb, lpl = (torch.zeros(plan.rows, dtype=torch.float32, device=dev) for _ in range(3))
+            a2, w2 = a16.view(dt16).view(plan.rows, H), w16.view(dt16).view(Vpad, H)
+            for t0, t1 in ChunkedJointRNNT._chunks(plan, Vpad):
+                r0, r1 = t0 * 128, t1 * 128
+                z = torch.mm(a2[r0:r1], w2.t(), out_dtype=torch.float32)
+                _call("ttx_rows_lse", dev, _p(z), r1 - r0, Vpad, V, _p(bias2), _p(scal), _p(row_label[r0:]), int(blank),
+                      _p(lse[r0:]), _p(lpb[r0:]), _p(lpl[r0:]), plan.idx, st)
+                del z
+            alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
+        ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
+        ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
+        ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
+        plan, (B, T, U1, H, V) = ctx.plan, ctx.dims
+        dev = plan.dev
+        dt16 = torch.bfloat16 if ctx.bf16 else torch.float16
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        d_ep = d_pp = d_w = d_b = None
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            scal = scal.clone()
+            Vpad = w16.numel() // H
+            rowmeta = torch.zeros(plan.rows * 4, dtype=torch.float32, device=dev)
+            rm_new = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, None)
+            # rows of tiles not in use keep w = 0 (grad_coeffs only writes the tiles in use)
+            n_rows_used = plan.meta[0].to(torch.int64) * 128
+            used = (torch.arange(plan.rows, device=dev) < n_rows_used).view(-1, 1)
+            rowmeta = torch.where(used, rm_new.view(-1, 4), rowmeta.view(-1, 4)).contiguous().view(-1)
+            pscale = 1.0 if ctx.bf16 else 4096.0
+            a2, w2 = a16.view(dt16).view(plan.rows, H), w16.view(dt16).view(Vpad, H)
+            d_act = torch.empty(plan.rows, H, dtype=torch.float32, device=dev) if need_act else None
+            if need_w:
+                d_w_pad = torch.zeros(Vpad, H, dtype=torch.float32, device=dev)
+                d_b_pad = torch.zeros(Vpad, dtype=torch.float32, device=dev)
+            for t0, t1 in ChunkedJointRNNT._chunks(plan, Vpad):
+                r0, r1 = t0 * 128, t1 * 128
+                z = torch.mm(a2[r0:r1], w2.t(), out_dtype=torch.float32)
+                q = torch.empty(r1 - r0, Vpad, dtype=dt16, device=dev)
+                _call("ttx_rows_grad", dev, _p(z), _p(rowmeta[4 * r0:]), _p(row_label[r0:]), _p(bias2), _p(scal),
+                      r1 - r0, Vpad, V, ctx.blank, ctx.bf16, _p(q), plan.idx, st)
+                del z
+                if need_act:
+                    torch.mm(q, w2, out_dtype=torch.float32, out=d_act[r0:r1])
+                if need_w:
+                    d_w_pad += torch.mm(q.t(), a2[r0:r1], out_dtype=torch.float32)
+                    d_b_pad += q.sum(0, dtype=torch.float32)
+                del q
+            if need_act:
+                d_act.mul_(scal[2] * scal[1] / pscale)
+                d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+                d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
+                _call("ttx_reduce_act_grad", dev, _p(d_act), _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens),
+                      _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st)
+            if need_w:
+                d_w = d_w_pad[:V] * (scal[2] / pscale)
+                d_b = d_b_pad[:V] * (scal[2] / pscale)
+        dt = ctx.in_dtypes
+        cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
+        return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
+                cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
+                None, None, None, None, None)
+
+
 def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False):
-    """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out."""
+    """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out.
+
+    Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
     dev = eproj.device
-    return FusedJointRNNT.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
-                                _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"),
-                                blank, bf16)
+    fn = FusedJointRNNT if supported_width(eproj.shape[-1]) else ChunkedJointRNNT
+    return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
+                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16)
 
 
 class DenseRNNT(torch.autograd.Function):

@@ -7,7 +7,8 @@
 For batched CUDA inputs with a tanh joint of a supported width they return a ``LazyJointLogits`` handle
 (the first Linear is split algebraically: cat(e,d) W^T = e W[:, :De]^T + d W[:, De:]^T, so it runs on
 B*T + B*U rows instead of the reference's B*T*U).  Everything else -- 1-D decode inputs
-(tt/model.py:77), CPU tensors, other activations or widths -- is the reference's dense math.
+(tt/model.py:77), CPU tensors, other activations, widths that are not a multiple of 64 -- is the reference's
+dense math.
 """
 import torch
 
@@ -16,7 +17,8 @@ from .lazy import LazyJointLogits
 
 
 def _fusable(x, width):
-    return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and F.supported_width(width)
+    # widths covered by the fused tcgen05 kernels, or any other multiple of 64 (chunked path, see functional.py)
+    return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and width % 64 == 0
 
 
 class JointNet(torch.nn.Module):
