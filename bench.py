@@ -26,6 +26,12 @@ WORKLOADS = {
     # same lattice, joint width 256 (leaves shared memory for a deeper TMA ring: pipeline experiments)
     "cfg2h256": dict(B=32, T=400, U=40, V=4232, D=512, H=256, joint="espnet", ragged=False,
                      desc="B=32 T=400 U=40 V=4232 D=512 H=256 fp32 (experiment)"),
+    # BASELINE.json configs[0]: aishell.yaml joint (tt JointNet 1024 -> 1024 -> V), the reference's CPU-runnable case
+    "cfg1": dict(B=4, T=200, U=30, V=4232, D=512, H=1024, joint="tt", ragged=False,
+                 desc="aishell.yaml joint B=4 T=200 U=30 V=4232 D=512 H=1024 fp32 (chunked wide-joint path)"),
+    # BASELINE.json configs[2]: joint_streaming.yaml joint dims (H=2048, V=6485) at the global batch of 64
+    "cfg3": dict(B=64, T=410, U=42, V=6485, D=512, H=2048, joint="tt", ragged=False,
+                 desc="joint_streaming.yaml joint B=64 T=410 U=42 V=6485 D=512 H=2048 fp32 (chunked wide-joint path)"),
     # BASELINE.json configs[0] shapes but with a fused-path joint width (parity-sized smoke workload)
     "small": dict(B=4, T=200, U=30, V=4232, D=512, H=512, joint="espnet", ragged=False,
                   desc="B=4 T=200 U=30 V=4232 D=512 H=512 fp32"),
@@ -120,12 +126,15 @@ def cpu_port_step(w, B_s, seed=1234):
     ws = dict(w, B=B_s)
     enc, pred, labels, act_lens, label_lens = synth(ws, seed)
     torch.manual_seed(seed)
-    joint = joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh")
+    tt = w.get("joint") == "tt"
+    joint = (joint_ref.TTJointNet(2 * w["D"], w["H"], w["V"]) if tt else
+             joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh"))
     crit = rnnt_oracle.RNNTLoss(blank=0)
     enc.requires_grad_()
     pred.requires_grad_()
     t0 = time.perf_counter()
-    loss = crit(joint(enc[:, :, None], pred[:, None]), labels, act_lens, label_lens)
+    logits = joint(enc, pred) if tt else joint(enc[:, :, None], pred[:, None])
+    loss = crit(logits, labels, act_lens, label_lens)
     loss.backward()
     loss.item()
     return time.perf_counter() - t0
@@ -205,9 +214,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
-    joint = ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh").to(dev)
+    tt = w.get("joint") == "tt"
+    joint = (ttb.JointNet(2 * w["D"], w["H"], w["V"]) if tt else
+             ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh")).to(dev)
     if w.get("bf16"):
         joint = joint.bfloat16()
+
+    def logits_of(e, p_):
+        return model(e, p_) if tt else model(e[:, :, None], p_[:, None])
     model = joint
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(joint, device_ids=[local], gradient_as_bucket_view=True)
@@ -223,7 +237,7 @@ def main():
             p_.grad = None
         enc.grad = None
         pred.grad = None
-        loss = crit(model(enc[:, :, None], pred[:, None]), labels, act_lens, label_lens)
+        loss = crit(logits_of(enc, pred), labels, act_lens, label_lens)
         loss.backward()
         return loss
 
@@ -233,7 +247,7 @@ def main():
         e, p_, lab, al, ll = [t.to(dev, non_blocking=True) for t in host]
         e.requires_grad_()
         p_.requires_grad_()
-        loss = crit(model(e[:, :, None], p_[:, None]), lab, al, ll)
+        loss = crit(logits_of(e, p_), lab, al, ll)
         loss.backward()
         return loss.item()          # device -> host read of the step's result
 
@@ -285,7 +299,8 @@ def main():
     M = int((act_lens.long() * (label_lens.long() + 1)).sum())      # lattice cells actually present
     unit_flops = 2.0 * M * w["H"] * w["V"]           # one M x H x V contraction (F = 3 of these)
     pk = peaks()
-    dom = max((k for k in table if k.startswith("ttx_joint_")), key=lambda k: table[k]["avg_ms"])
+    dom = max((k for k in table if k.startswith("ttx_joint_") or k.startswith("ttx_rows_")),
+              key=lambda k: table[k]["avg_ms"] * table[k]["calls"])
     dom_ms = table[dom]["avg_ms"]
     achieved = unit_flops / (dom_ms * 1e-3) / 1e12
     traffic = None

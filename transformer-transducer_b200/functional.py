@@ -8,6 +8,7 @@
                       joint is not ours).
 """
 import ctypes
+import os
 
 import torch
 
@@ -309,7 +310,8 @@ def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, b
 
     Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
     dev = eproj.device
-    fn = FusedJointRNNT if supported_width(eproj.shape[-1]) else ChunkedJointRNNT
+    fused = supported_width(eproj.shape[-1]) and os.environ.get("TTX_FORCE_CHUNKED", "0") != "1"
+    fn = FusedJointRNNT if fused else ChunkedJointRNNT
     return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
                     _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16)
 
