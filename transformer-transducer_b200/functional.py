@@ -202,7 +202,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
     projection of a chunk is a library GEMM on the same 16-bit operands (fp32 accumulate), our row kernels do the
     log-softmax statistics / the gradient operand, and memory stays bounded by the chunk."""
 
-    CHUNK_BYTES = 512 << 20
+    CHUNK_BYTES = int(os.environ.get("TTX_CHUNK_MB", "512")) << 20
 
     @staticmethod
     def _chunks(plan, Vpad):
