@@ -115,6 +115,20 @@ int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* ppr
                         const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H,
                         float* d_eproj, float* d_pproj, int device, void* stream);
 
+/* Forward with the activation-gradient contraction fused in (flash-attention style): same outputs as
+ * ttx_joint_lse_fwd plus ew (rows, H) fp32 = sum_v softmax_v * W_out[v, :] over all v except the blank and the
+ * cell's label.  With it the backward needs no activation-gradient tensor-core pass: ttx_reduce_act_grad_ew forms
+ * dL/dA = gmax * w * (ew + (p_b - rb) W_out[blank] + (p_l - rl) W_out[label]) from the lattice coefficients
+ * (rowmeta of ttx_grad_coeffs) on the fly.  H in {128, 256, 512} (ttx_fwd_grad_supported_h); needs w16t. */
+int ttx_fwd_grad_supported_h(int H);
+int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
+                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
+                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream);
+int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
+                           const float* scal, int blank, const float* eproj, const float* pproj,
+                           const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                           int H, float* d_eproj, float* d_pproj, int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

@@ -1,6 +1,6 @@
 """Stage-by-stage check of the C-ABI kernels on a GPU against tests/algo_model.py (float64 CPU model).
 
-    python tests/gpu_stage_check.py <stage> [B T U V H]      stage in: small fwd bwd all
+    python tests/gpu_stage_check.py <stage> [B T U V H]      stage in: small fwd fg bwd
 
 Run by hand / from gpurun while bringing kernels up; the pytest suite (tests/test_gpu_*.py) is the gate.
 """
@@ -111,6 +111,34 @@ def run(stage, B, T, U, V, H):
         torch.cuda.synchronize()
         mm = algo_model.forward_backward(E, P, W, b, labels, al, ll, gc, emulate=False)
         tol = 2e-5
+    elif stage == "fg":
+        ew = f32(rows * H)
+        _lib.check(lib.ttx_joint_fwd_grad(_p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(meta), ntub,
+                                          H, V, 0, 0, _p(lse), _p(lpb), _p(lpl), _p(ew), 0, st), "fwd_grad")
+        torch.cuda.synchronize()
+        mm = m
+        tol = 2e-5
+        # EW model: sum_v p_v W16_v / w_scale without the blank and label columns
+        soft = torch.exp(m["z"] - m["lse"][..., None])
+        soft[..., 0] = 0.0
+        lab_full = torch.zeros(B, U1, dtype=torch.long)
+        for i in range(B):
+            lab_full[i, : int(ll[i])] = labels[i, : int(ll[i])].long()
+        mask = torch.zeros(B, U1, dtype=torch.bool)
+        for i in range(B):
+            mask[i, : int(ll[i])] = True
+        idx = lab_full.view(B, 1, U1, 1).expand(B, T, U1, 1)
+        keep = soft.gather(3, idx)
+        soft.scatter_(3, idx, torch.where(mask.view(B, 1, U1, 1), torch.zeros_like(keep), keep))
+        soft[..., 0] = 0.0
+        W16m = algo_model._r16(W.double() * m["w_scale"], True) / m["w_scale"]
+        EW_model = torch.full((rows, H), float("nan"), dtype=torch.float64)
+        ewm = soft @ W16m
+        for i in range(B):
+            Tb, U1b = int(al[i]), int(ll[i]) + 1
+            base = int(mh[4 + i]) * 128
+            EW_model[base: base + Tb * U1b] = ewm[i, :Tb, :U1b].reshape(-1, H)
+        fail |= report("EW", ew.view(rows, H).cpu().reshape(-1), EW_model.reshape(-1), 5e-4)
     else:
         _lib.check(lib.ttx_joint_lse_fwd(_p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(meta), ntub, H, V, 0, 0,
                                          _p(lse), _p(lpb), _p(lpl), 0, st), "fwd")
@@ -166,6 +194,14 @@ def run(stage, B, T, U, V, H):
         fail |= report("dense grad", grads.reshape(-1), zc.grad.double().reshape(-1), 1e-4)
         return fail
     if stage == "fwd":
+        return fail
+    if stage == "fg":
+        dE, dP = f32(B * T * H), f32(B * U1 * H)
+        _lib.check(lib.ttx_reduce_act_grad_ew(_p(ew), _p(rowmeta), _p(row_label), _p(Wd), _p(scal), 0, _p(Ed), _p(Pd),
+                                              _p(ald), _p(lld), _p(meta), B, T, U1, H, _p(dE), _p(dP), 0, st), "reduce_ew")
+        torch.cuda.synchronize()
+        fail |= report("dEproj", dE, m["dEproj"].reshape(-1), 3e-4)
+        fail |= report("dPproj", dP, m["dPproj"].reshape(-1), 3e-4)
         return fail
 
     d_act = f32(rows * H)

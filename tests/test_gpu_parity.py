@@ -139,6 +139,23 @@ def test_fused_espnet_joint_matches_oracle_all_widths(H):
     _check(errs)
 
 
+@pytest.mark.parametrize("H", [128, 512])
+def test_fused_forward_grad_rescale_path_with_outlier_logits(H):
+    """Peaked distributions whose largest logits sit in LATE vocabulary tiles: the forward's running reference has to
+    move after the first tile, which rescales the TMEM accumulator of the fused forward+gradient mode."""
+    ref, mine, enc, pred, labels, al, ll = _espnet_case(2, 30, 6, 1500, 64, H, [30, 22], [6, 3], seed=77)
+    with torch.no_grad():
+        ref.lin_out.bias[700] += 9.0            # tile 2 of 6 (256-wide tiles)
+        ref.lin_out.bias[1490] += 14.0          # last tile
+        ref.lin_out.bias[0] += 5.0              # blank, first tile
+        ref.lin_out.weight[1301] *= 6.0         # row-dependent outliers in tile 5
+    labels[0, 2] = 1490
+    labels[1, 0] = 700
+    mine.load_state_dict(ref.state_dict())
+    errs, _ = _run_pair(ref, mine, enc, pred, labels, al, ll, weights=torch.tensor([1.0, 3.0]))
+    _check(errs)
+
+
 def test_fused_edge_lengths_t1_u0_and_zero_grads_outside():
     case = _espnet_case(4, 20, 5, 150, 32, 128, [20, 1, 1, 7], [5, 0, 3, 0], seed=3)
     errs, (e1, p1, _) = _run_pair(*case)
@@ -264,10 +281,10 @@ def test_c_abi_rejects_unsupported_width_with_message():
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
-@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {}])
+@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"}, {}])
 def test_kernel_variants_agree_with_oracle(env, monkeypatch):
-    """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0) and the default pair kernels all
-    meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair)."""
+    """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
+    kernel (TTX_NO_FWD_GRAD=1) and the default kernels (fused forward+gradient, pair backward) all meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)

@@ -11,7 +11,7 @@ run() {
   echo "exit $?" | tee -a $LOG
 }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv | tee -a $LOG
-STAGES=${1:-"small fwd bwd"}
+STAGES=${1:-"small fwd fg bwd"}
 for s in $STAGES; do
   case $s in
     small) run small 3 40 6 300 128 ;;
@@ -19,6 +19,10 @@ for s in $STAGES; do
       run fwd 2 40 6 300 64
       run fwd 2 40 6 300 128
       run fwd 2 40 6 1000 512 ;;
+    fg)
+      run fg 2 40 6 300 128
+      run fg 2 40 6 300 256
+      run fg 3 50 9 1000 512 ;;
     bwd)
       TTX_BWD=da run bwd 2 40 6 300 64
       TTX_BWD=dw run bwd 2 40 6 300 64

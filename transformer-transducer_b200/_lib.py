@@ -37,6 +37,11 @@ _PROTOS = {
     "ttx_grad_coeffs": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_p, c_p,
                         c_i32, c_p],
     "ttx_transpose16": [c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
+    "ttx_fwd_grad_supported_h": [c_i32],
+    "ttx_joint_fwd_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
+                           c_i32, c_p],
+    "ttx_reduce_act_grad_ew": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
+                               c_p, c_p, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_grad": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p,

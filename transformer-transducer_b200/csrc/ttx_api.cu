@@ -26,8 +26,11 @@ int launch_lattice(const float*, const float*, const int*, const int*, const int
 int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
                      const float*, float*, const int*, const int*, const int*, const int*, int, int, int, float4*,
                      float*, cudaStream_t);
-int launch_reduce(const float*, const float*, const float*, const int*, const int*, const int*, int, int, int, int,
-                  float*, float*, cudaStream_t);
+int launch_reduce(const float*, const float4*, const int*, const float*, const float*, int, const float*, const float*,
+                  const int*, const int*, const int*, int, int, int, int, float*, float*, cudaStream_t);
+bool fwd_grad_supported_h(int H);
+int launch_joint_fwd_grad(const void*, const void*, const void*, uint64_t, int, int, int, int, bool, const int*,
+                          const float*, const float*, const int*, int, float*, float*, float*, float*, cudaStream_t);
 int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
                      float*, float*, float*, int*, cudaStream_t);
 int launch_dense_grad(const float*, const float4*, const int*, const float*, const int*, const int*, const int*, int,
@@ -199,8 +202,35 @@ int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* ppr
                 "ttx_reduce_act_grad: null pointer");
     TTX_REQUIRE(H % 4 == 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_reduce_act_grad: bad shape");
     TTX_ENTER(device);
-    return launch_reduce(d_act, eproj, pproj, act_lens, label_lens, meta, B, T, U1, H, d_eproj, d_pproj,
-                         (cudaStream_t)stream);
+    return launch_reduce(d_act, nullptr, nullptr, nullptr, nullptr, 0, eproj, pproj, act_lens, label_lens, meta, B, T,
+                         U1, H, d_eproj, d_pproj, (cudaStream_t)stream);
+}
+
+int ttx_fwd_grad_supported_h(int H) { return fwd_grad_supported_h(H) ? 1 : 0; }
+
+int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
+                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
+                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream) {
+    TTX_REQUIRE(a16 && w16 && w16t && bias2 && scal && row_label && meta && lse && lp_blank && lp_label && ew,
+                "ttx_joint_fwd_grad: null pointer");
+    TTX_REQUIRE(fwd_grad_supported_h(H), "ttx_joint_fwd_grad: joint width H=%d is not supported (128, 256, 512)", H);
+    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_fwd_grad: bad V=%d / blank=%d", V, blank);
+    TTX_ENTER(device);
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
+    return launch_joint_fwd_grad(a16, w16, w16t, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0,
+                                 meta, bias2, scal, row_label, blank, lse, lp_blank, lp_label, ew, (cudaStream_t)stream);
+}
+
+int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
+                           const float* scal, int blank, const float* eproj, const float* pproj,
+                           const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                           int H, float* d_eproj, float* d_pproj, int device, void* stream) {
+    TTX_REQUIRE(ew && rowmeta && row_label && w_out && scal && eproj && pproj && act_lens && label_lens && meta &&
+                    d_eproj && d_pproj, "ttx_reduce_act_grad_ew: null pointer");
+    TTX_REQUIRE(H % 4 == 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_reduce_act_grad_ew: bad shape");
+    TTX_ENTER(device);
+    return launch_reduce(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens, label_lens,
+                         meta, B, T, U1, H, d_eproj, d_pproj, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

@@ -19,7 +19,7 @@
 
 namespace ttx {
 
-enum { MODE_FWD = 0, MODE_DA = 1, MODE_DW = 2 };
+enum { MODE_FWD = 0, MODE_DA = 1, MODE_DW = 2, MODE_FG = 3 };
 
 struct MmaParams {
     int H, NKC;            // joint width, H / 64
@@ -757,132 +757,142 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         const float lg_scale = BF16 ? 0.0f : 12.0f;
         const bool any_neg = p.scal[3] != 0.f;
         const int n_valid_rows = n_tiles * kTile;
-        float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-        int label = -1;
-        float krow = 0.f, db_acc = 0.f;
-        int vrow = 0;
-        uint32_t acc[32];
-        if (MODE == MODE_DA) {
-            if (valid_x) {
-                rm = p.rowmeta[x_row0 + row];
-                label = p.row_label[x_row0 + row];
-            }
-            krow = fmaf(rm.x, -kLog2e, lg_scale);
-        } else {
-            vrow = x_row0 + row;
-            krow = __ldg(p.bias2 + vrow);
-        }
-        for (int i = 0; i < n_iter; ++i) {
-            const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
-            float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-            int clabel = -1;
-            if (MODE == MODE_DW) {
-                const int col = t0 + et;                // this thread owns column et of the 256-column tile
-                if (col < n_valid_rows) {
-                    cm = __ldg(p.rowmeta + col);
-                    clabel = __ldg(p.row_label + col);
+        if (MODE == MODE_FG) {
+            // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
+            // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
+            // mref (log2 units).  mref only moves when a later tile's row maximum exceeds it by 2^3; then the rows'
+            // accumulators are rescaled in TMEM before the next sub-pass (rare: first tiles / outlier logits).
+            // The blank and label columns are left out of G: their exact contribution (p - rb) W_blank + (p - rl) W_label
+            // is added after the lattice by the reduction kernels.  EW = G * 2^(mref - lse2) / w_scale = sum_v p_v W_v.
+            const int grow = x_row0 + row;
+            const int label = valid_x ? p.row_label[grow] : -1;
+            float mref = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;
+            float* xg = kbuf;                                                   // [2][128] row maxima of the two halves
+            volatile int* flag = reinterpret_cast<volatile int*>(kbuf + 2 * kTile);   // [2] by tile parity
+            const int ngrp = p.HH / 32;
+            if (et < 2) flag[et] = 0;
+            epi_sync();
+            for (int i = 0; i < n_iter; ++i) {
+                const int t0 = (j0 + i) * NT;
+                mbar_wait(bar_sfull, i & 1);
+                tc_fence_after();
+                uint32_t acc[4][32];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
+                tmem_ld_wait();
+                tc_fence_before();
+                epi_arrive(bar_sempty);
+                float gmax = -INFINITY;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + (g >> 1) * 128 + ch * 64 + (g & 1) * 32);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 bv = __ldg(b4 + e);
+                        const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x);
+                        const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y);
+                        const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z);
+                        const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w);
+                        acc[g][4 * e + 0] = __float_as_uint(y0);
+                        acc[g][4 * e + 1] = __float_as_uint(y1);
+                        acc[g][4 * e + 2] = __float_as_uint(y2);
+                        acc[g][4 * e + 3] = __float_as_uint(y3);
+                        gmax = fmaxf(gmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                    }
                 }
-                kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
-                kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
+                xg[ch * kTile + row] = gmax;
                 epi_sync();
-            }
-            mbar_wait(bar_sfull, i & 1);
-            if (et == 0) trace_at(p, 2, i, 0);
-            tc_fence_after();
-            // Pull this thread's share of the S tile (2 sub-passes x 64 columns) into registers and hand the single S
-            // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
-            uint32_t acc[4][32];
+                const float rowmax = fmaxf(xg[row], xg[kTile + row]);
+                const bool need = rowmax > mref + 3.f;            // true on the first tile (mref = -inf)
+                const float nref = need ? rowmax + 2.f : mref;
+                const float fsc = need ? ex2f(mref - nref) : 1.f; // 0 on the first tile
+                if (need && i > 0) flag[i & 1] = 1;
+                ssum *= fsc;
+                epi_sync();
+                const bool rescale = flag[i & 1] != 0;            // uniform over the CTA
+                if (et == 0) flag[(i + 1) & 1] = 0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
-            tmem_ld_wait();
-            tc_fence_before();
-            epi_arrive(bar_sempty);
-            if (et == 0) trace_at(p, 2, i, 1);
+                for (int sp = 0; sp < 2; ++sp) {
+                    const int c0 = t0 + sp * 128;
+                    uint32_t packed[32];
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                const int c0 = t0 + sp * 128;           // first stream index of this sub-pass
-                uint32_t packed[32];
+                    for (int g = 0; g < 2; ++g) {
+                        const int vb = c0 + ch * 64 + g * 32;
+                        float val[32];
+                        float part = 0.f;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int cb = sp * 128 + ch * 64 + g * 32;   // column inside the 256-column tile
-                    if (p.dbg & 4) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
-                        continue;
-                    }
-                    float kc[32];
-                    if (MODE == MODE_DA) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + cb);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float4 bv = __ldg(b4 + e);
-                            kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                        for (int e = 0; e < 32; ++e) {
+                            val[e] = ex2f(__uint_as_float(acc[sp * 2 + g][e]) - nref + lg_scale);
+                            part += val[e];
                         }
-                    } else {
-                        const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
+                        ssum += part;
+                        if (p.blank >= vb && p.blank < vb + 32) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float4 kv = k4[e];
-                            kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
+                            for (int e = 0; e < 32; ++e) zb = (vb + e == p.blank) ? __uint_as_float(acc[sp * 2 + g][e]) : zb;
                         }
-                    }
-                    float val[32];
+                        if (label >= vb && label < vb + 32) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        val[e] = ex2f(fmaf(__uint_as_float(acc[sp * 2 + g][e]), c1, kc[e] + krow));
-                    if (MODE == MODE_DW) {
-                        if (any_neg) {
-                            const float* sg = kbuf + NT + cb;
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) val[e] *= sg[e];
+                            for (int e = 0; e < 32; ++e) zl = (vb + e == label) ? __uint_as_float(acc[sp * 2 + g][e]) : zl;
                         }
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) db_acc += val[e];
+                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                    }
+                    mbar_wait(bar_pempty, sp ^ 1);
+                    if (sp == 0 && rescale) {
+                        // every G pass issued so far has completed (bar_pempty): scale this row's accumulators
+                        tc_fence_after();
+                        uint32_t gacc[32];
+                        for (int cc = ch; cc < ngrp; cc += 2) {
+                            tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
+                            tmem_st32(tmem_G + lane_addr + cc * 32, gacc);
+                        }
+                        tmem_st_wait();
+                        tc_fence_before();
                     }
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
-                }
-                // Sub-pass n = 2i + sp may overwrite the P' tile once the G pass of sub-pass n - 1 has completed
-                // (completion #n of bar_pempty, parity (n - 1) & 1).  Every thread waits for every sub-pass in
-                // order, so the parity wait never has to look more than one phase ahead.
-                mbar_wait(bar_pempty, sp ^ 1);
-                if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {        // this thread's 64 columns = 8 chunks of 16 B in block ch
-                    uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                    *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
-                }
-                if (MODE == MODE_DA) {
+                    for (int cc = 0; cc < 8; ++cc) {
+                        uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+                        *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                    }
                     const int cbl = p.blank - c0, clb = label - c0;
-                    if (cbl >= ch * 64 && cbl < ch * 64 + 64)
-                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
-                    if (clb >= ch * 64 && clb < ch * 64 + 64)
-                        *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
-                } else {
-                    epi_sync();                         // column owners patch rows written by other threads
-                    if ((et >> 7) == sp) {
-                        const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
-                        if (rbl >= 0 && rbl < kTile)
-                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
-                        if (rlb >= 0 && rlb < kTile)
-                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
-                    }
+                    if (cbl >= ch * 64 && cbl < ch * 64 + 64) *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = 0;
+                    if (clb >= ch * 64 && clb < ch * 64 + 64) *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = 0;
+                    fence_proxy_async_smem();
+                    epi_arrive(bar_pfull);
                 }
-                fence_proxy_async_smem();
-                epi_arrive(bar_pfull);
-                if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
+                mref = nref;
             }
-        }
-        // ---- final: G (128 x HH fp32 in TMEM) -> global
-        mbar_wait(bar_gfull, 0);
-        tc_fence_after();
-        const float gmax = p.scal[2];
-        const int ngrp = p.HH / 32;
-        // G columns [0, hh2) came from the leader's B rows, [hh2, HH) from the peer's: column c <-> joint column c
-        if (MODE == MODE_DA) {
-            const float f = rm.w * gmax * inv_ws / pscale;
-            float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
+            mbar_wait(bar_gfull, 0);
+            tc_fence_after();
+            // combine the two column halves of each row: ch 1 hands (sum, z_blank, z_label) to ch 0, ch 0 returns lse2
+            float4* xch = reinterpret_cast<float4*>(kbuf);
+            epi_sync();
+            if (ch == 1) xch[row] = make_float4(ssum, zb, zl, 0.f);
+            epi_sync();
+            float lse2 = 0.f;
+            if (ch == 0) {
+                const float4 o = xch[row];
+                lse2 = mref - lg_scale + lg2f(ssum + o.x);
+                const int cb_in = p.blank % NT;                   // column of blank / label inside its 256-column tile
+                zb = ((cb_in & 127) < 64) ? zb : o.y;
+                if (label >= 0) zl = (((label % NT) & 127) < 64) ? zl : o.z;
+                if (valid_x && half == 0) {
+                    p.lse[grow] = lse2 * kLn2;
+                    p.lpb[grow] = (zb - lse2) * kLn2;
+                    p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+                }
+            }
+            epi_sync();
+            if (ch == 0) xch[row].x = lse2;
+            epi_sync();
+            if (ch == 1) lse2 = xch[row].x;
+            const float f = ex2f(mref - lg_scale - lse2) * inv_ws;
+            float* dst = p.dA + (size_t)grow * p.H + half * p.HH;
+            uint32_t acc[32];
             for (int cc = ch; cc < ngrp; cc += 2) {
                 tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
                 tmem_ld_wait();
@@ -896,18 +906,158 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 }
             }
         } else {
-            const float f = gmax / pscale;
-            const bool ok = vrow < p.V;
-            float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
-            for (int cc = ch; cc < ngrp; cc += 2) {
-                tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+            float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+            int label = -1;
+            float krow = 0.f, db_acc = 0.f;
+            int vrow = 0;
+            uint32_t acc[32];
+            if (MODE == MODE_DA) {
+                if (valid_x) {
+                    rm = p.rowmeta[x_row0 + row];
+                    label = p.row_label[x_row0 + row];
+                }
+                krow = fmaf(rm.x, -kLog2e, lg_scale);
+            } else {
+                vrow = x_row0 + row;
+                krow = __ldg(p.bias2 + vrow);
+            }
+            for (int i = 0; i < n_iter; ++i) {
+                const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
+                float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+                int clabel = -1;
+                if (MODE == MODE_DW) {
+                    const int col = t0 + et;                // this thread owns column et of the 256-column tile
+                    if (col < n_valid_rows) {
+                        cm = __ldg(p.rowmeta + col);
+                        clabel = __ldg(p.row_label + col);
+                    }
+                    kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
+                    kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
+                    epi_sync();
+                }
+                mbar_wait(bar_sfull, i & 1);
+                if (et == 0) trace_at(p, 2, i, 0);
+                tc_fence_after();
+                // Pull this thread's share of the S tile (2 sub-passes x 64 columns) into registers and hand the single S
+                // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
+                uint32_t acc[4][32];
+    #pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
                 tmem_ld_wait();
-                if (ok) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
+                tc_fence_before();
+                epi_arrive(bar_sempty);
+                if (et == 0) trace_at(p, 2, i, 1);
+    #pragma unroll
+                for (int sp = 0; sp < 2; ++sp) {
+                    const int c0 = t0 + sp * 128;           // first stream index of this sub-pass
+                    uint32_t packed[32];
+    #pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int cb = sp * 128 + ch * 64 + g * 32;   // column inside the 256-column tile
+                        if (p.dbg & 4) {
+    #pragma unroll
+                            for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
+                            continue;
+                        }
+                        float kc[32];
+                        if (MODE == MODE_DA) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + cb);
+    #pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float4 bv = __ldg(b4 + e);
+                                kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                            }
+                        } else {
+                            const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
+    #pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float4 kv = k4[e];
+                                kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
+                            }
+                        }
+                        float val[32];
+    #pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            val[e] = ex2f(fmaf(__uint_as_float(acc[sp * 2 + g][e]), c1, kc[e] + krow));
+                        if (MODE == MODE_DW) {
+                            if (any_neg) {
+                                const float* sg = kbuf + NT + cb;
+    #pragma unroll
+                                for (int e = 0; e < 32; ++e) val[e] *= sg[e];
+                            }
+    #pragma unroll
+                            for (int e = 0; e < 32; ++e) db_acc += val[e];
+                        }
+    #pragma unroll
+                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                    }
+                    // Sub-pass n = 2i + sp may overwrite the P' tile once the G pass of sub-pass n - 1 has completed
+                    // (completion #n of bar_pempty, parity (n - 1) & 1).  Every thread waits for every sub-pass in
+                    // order, so the parity wait never has to look more than one phase ahead.
+                    mbar_wait(bar_pempty, sp ^ 1);
+                    if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
+    #pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {        // this thread's 64 columns = 8 chunks of 16 B in block ch
+                        uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+                        *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                    }
+                    if (MODE == MODE_DA) {
+                        const int cbl = p.blank - c0, clb = label - c0;
+                        if (cbl >= ch * 64 && cbl < ch * 64 + 64)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
+                        if (clb >= ch * 64 && clb < ch * 64 + 64)
+                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+                    } else {
+                        epi_sync();                         // column owners patch rows written by other threads
+                        if ((et >> 7) == sp) {
+                            const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
+                            if (rbl >= 0 && rbl < kTile)
+                                *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
+                            if (rlb >= 0 && rlb < kTile)
+                                *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    epi_arrive(bar_pfull);
+                    if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
                 }
             }
-            if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+            // ---- final: G (128 x HH fp32 in TMEM) -> global
+            mbar_wait(bar_gfull, 0);
+            tc_fence_after();
+            const float gmax = p.scal[2];
+            const int ngrp = p.HH / 32;
+            // G columns [0, hh2) came from the leader's B rows, [hh2, HH) from the peer's: column c <-> joint column c
+            if (MODE == MODE_DA) {
+                const float f = rm.w * gmax * inv_ws / pscale;
+                float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
+                for (int cc = ch; cc < ngrp; cc += 2) {
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld_wait();
+                    if (valid_x) {
+    #pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
+                                                   __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
+                            *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                        }
+                    }
+                }
+            } else {
+                const float f = gmax / pscale;
+                const bool ok = vrow < p.V;
+                float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
+                for (int cc = ch; cc < ngrp; cc += 2) {
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld_wait();
+                    if (ok) {
+    #pragma unroll
+                        for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
+                    }
+                }
+                if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+            }
         }
     }
     tc_fence_before();
@@ -1154,6 +1304,45 @@ static bool v3_applicable(int H, const void* w16t, const void* a16t) {
     if (e && e[0] == '0') return false;
     if (!w16t || !a16t || forced_cg() == 1) return false;
     return H == 128 || H == 256 || H == 512;
+}
+
+bool fwd_grad_supported_h(int H) { return H == 128 || H == 256 || H == 512; }
+
+// Forward statistics + EW = sum_v p_v W_v (blank / label columns excluded) in one pass (MODE_FG of the pair kernel).
+int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, uint64_t rows_ub, int n_tiles_ub, int H,
+                          int V, int Vpad, bool bf16, const int* meta, const float* bias2, const float* scal,
+                          const int* row_label, int blank, float* lse, float* lpb, float* lpl, float* ew,
+                          cudaStream_t stream) {
+    MmaParams p{};
+    p.H = H;
+    p.NKC = H / 64;
+    p.V = V;
+    p.n_halves = (H > 256) ? 2 : 1;
+    p.HH = H / p.n_halves;
+    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
+    p.trace = nullptr;
+    const size_t fixed = (size_t)(p.NKC + 2) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+    int ns = 8;
+    while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
+    p.NS = ns;
+    const size_t smem = fixed + (size_t)ns * kChunkBytes;
+    p.blank = blank;
+    p.splits = 1;
+    p.meta = meta;
+    p.bias2 = bias2;
+    p.scal = scal;
+    p.row_label = row_label;
+    p.lse = lse;
+    p.lpb = lpb;
+    p.lpl = lpl;
+    p.dA = ew;
+    CUtensorMap mx, my, myt;
+    if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+    if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
+    dim3 grid(n_tiles_ub, p.n_halves, 1);
+    return bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
+                : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const void* w16t, uint64_t rows_ub,

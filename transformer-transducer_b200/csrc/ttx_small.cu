@@ -399,8 +399,39 @@ __device__ __forceinline__ float sech2(float x) {
     return 4.f * e / (d * d);
 }
 
+// Source of dL/dA for the two reductions below.  EW = false: `src` already holds dL/dA.  EW = true: `src` holds
+// EW = sum_v p_v W_out[v] without the blank / label columns (forward pass, MODE_FG) and
+//   dL/dA[row] = gmax * w * (EW[row] + (p_b - rb) W_out[blank] + (p_l - rl) W_out[label])
+// with the bracketed coefficients from rowmeta (.y, .z; identical when label == blank) and fp32 W_out rows.
+struct ActGradSrc {
+    const float* src;
+    const float4* rowmeta;
+    const int* row_label;
+    const float* w_out;
+    const float* scal;
+    int blank;
+};
+
+template <bool EW>
+__device__ __forceinline__ float4 act_grad_at(const ActGradSrc& a, size_t grow, int H, int h, const float4& wb) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
+    if (EW) {
+        const float4 rm = __ldg(a.rowmeta + grow);
+        const int lab = __ldg(a.row_label + grow);
+        const float coef = rm.w * a.scal[2];
+        g.x = fmaf(rm.y, wb.x, g.x); g.y = fmaf(rm.y, wb.y, g.y); g.z = fmaf(rm.y, wb.z, g.z); g.w = fmaf(rm.y, wb.w, g.w);
+        if (lab >= 0 && lab != a.blank) {
+            const float4 wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+            g.x = fmaf(rm.z, wl.x, g.x); g.y = fmaf(rm.z, wl.y, g.y); g.z = fmaf(rm.z, wl.z, g.z); g.w = fmaf(rm.z, wl.w, g.w);
+        }
+        g.x *= coef; g.y *= coef; g.z *= coef; g.w *= coef;
+    }
+    return g;
+}
+
 // dEproj[b,t,:] = sum_u dA[b,t,u,:] * (1 - tanh^2(E[b,t,:] + P[b,u,:]));  grid = (T, B), one float4 of h per thread
-__global__ void reduce_enc_kernel(const float* __restrict__ dA, const float* __restrict__ eproj,
+template <bool EW>
+__global__ void reduce_enc_kernel(const ActGradSrc a, const float* __restrict__ eproj,
                                   const float* __restrict__ pproj, const int* __restrict__ act_lens,
                                   const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
                                   int H, float* __restrict__ d_eproj) {
@@ -412,9 +443,11 @@ __global__ void reduce_enc_kernel(const float* __restrict__ dA, const float* __r
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < Tb) {
             const float4 e = *reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h);
+            float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
             for (int u = 0; u < U1b; ++u) {
                 const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
-                const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (base + (size_t)t * U1b + u) * H + h));
+                const float4 g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
                 acc.x += g.x * sech2(e.x + pp.x);
                 acc.y += g.y * sech2(e.y + pp.y);
                 acc.z += g.z * sech2(e.z + pp.z);
@@ -426,7 +459,8 @@ __global__ void reduce_enc_kernel(const float* __restrict__ dA, const float* __r
 }
 
 // dPproj[b,u,:] += sum over a chunk of t;  grid = (U1, B, t-chunks); d_pproj zero-initialised by the caller
-__global__ void reduce_pred_kernel(const float* __restrict__ dA, const float* __restrict__ eproj,
+template <bool EW>
+__global__ void reduce_pred_kernel(const ActGradSrc a, const float* __restrict__ eproj,
                                    const float* __restrict__ pproj, const int* __restrict__ act_lens,
                                    const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
                                    int H, int t_chunk, float* __restrict__ d_pproj) {
@@ -439,10 +473,12 @@ __global__ void reduce_pred_kernel(const float* __restrict__ dA, const float* __
     const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
     for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
         const float4 pp = *reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h);
+        float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = t0; t < t1; ++t) {
             const float4 e = __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h));
-            const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (base + (size_t)t * U1b + u) * H + h));
+            const float4 g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
             acc.x += g.x * sech2(e.x + pp.x);
             acc.y += g.y * sech2(e.y + pp.y);
             acc.z += g.z * sech2(e.z + pp.z);
@@ -696,16 +732,20 @@ int launch_grad_prep(const float* lse, const float* lpb, const float* lpl, const
     return 0;
 }
 
-int launch_reduce(const float* dA, const float* eproj, const float* pproj, const int* act_lens,
+int launch_reduce(const float* src, const float4* rowmeta, const int* row_label, const float* w_out,
+                  const float* scal, int blank, const float* eproj, const float* pproj, const int* act_lens,
                   const int* label_lens, const int* meta, int B, int T, int U1, int H, float* d_eproj,
                   float* d_pproj, cudaStream_t s) {
     const int threads = min(256, max(32, H / 4));
-    reduce_enc_kernel<<<dim3(T, B), threads, 0, s>>>(dA, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
+    const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
+    const bool ew = rowmeta != nullptr;
+    if (ew) reduce_enc_kernel<true><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
+    else reduce_enc_kernel<false><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
     TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
     const int t_chunk = 64;
-    reduce_pred_kernel<<<dim3(U1, B, (T + t_chunk - 1) / t_chunk), threads, 0, s>>>(dA, eproj, pproj, act_lens,
-                                                                                  label_lens, meta, T, U1, H, t_chunk,
-                                                                                  d_pproj);
+    const dim3 grid(U1, B, (T + t_chunk - 1) / t_chunk);
+    if (ew) reduce_pred_kernel<true><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, t_chunk, d_pproj);
+    else reduce_pred_kernel<false><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, t_chunk, d_pproj);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -24,7 +24,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_reduce_act_grad_ew": 2, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -146,13 +146,23 @@ class FusedJointRNNT(torch.autograd.Function):
                                          _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
                                          _p(a16), _p(row_label), _p(a16t), plan.idx, st)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
-            _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
-                                             plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
-                                             plan.idx, st)
+            # When the activations need gradients the forward also accumulates EW = sum_v p_v W_out[v] (minus the
+            # blank / label columns) on the tensor cores, so the backward has no activation-gradient MMA pass.
+            ew = None
+            if (with_t and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and lib.ttx_fwd_grad_supported_h(H)
+                    and os.environ.get("TTX_NO_FWD_GRAD", "0") != "1"):
+                ew = plan.rowf(H)
+                _call("ttx_joint_fwd_grad", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label),
+                      _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(ew),
+                      plan.idx, st)
+            else:
+                _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
+                      plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), plan.idx, st)
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
         ctx.transposed = (a16t, w16t)
+        ctx.ew, ctx.w32 = ew, (w if ew is not None else None)
         ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
         return costs
 
@@ -171,12 +181,13 @@ class FusedJointRNNT(torch.autograd.Function):
                 d_w = torch.zeros(V, H, dtype=torch.float32, device=dev)
                 d_b = torch.zeros(V, dtype=torch.float32, device=dev)
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
-            d_act = plan.rowf(H) if need_act else None
+            ew = ctx.ew
+            d_act = plan.rowf(H) if (need_act and ew is None) else None
             if need_act or need_w:
                 a16t, w16t = ctx.transposed
                 splits = _dw_splits(torch.cuda.get_device_properties(dev).multi_processor_count, V, H, plan.ntub)
                 # two launches (activation gradient, weight gradient) so each shows up separately in profiles
-                if need_act:
+                if need_act and ew is None:
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
@@ -187,8 +198,13 @@ class FusedJointRNNT(torch.autograd.Function):
             if need_act:
                 d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
                 d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
-                _call("ttx_reduce_act_grad", dev, _p(d_act), _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens),
-                                                   _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st)
+                if ew is not None:
+                    _call("ttx_reduce_act_grad_ew", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
+                          ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
+                          _p(d_ep), _p(d_pp), plan.idx, st)
+                else:
+                    _call("ttx_reduce_act_grad", dev, _p(d_act), _p(ep), _p(pp), _p(plan.act_lens),
+                          _p(plan.label_lens), _p(plan.meta), B, T, U1, H, _p(d_ep), _p(d_pp), plan.idx, st)
         dt = ctx.in_dtypes
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
