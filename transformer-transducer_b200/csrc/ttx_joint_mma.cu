@@ -767,14 +767,12 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const int grow = x_row0 + row;
             const int label = valid_x ? p.row_label[grow] : -1;
             float mref = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;
-            float* xg = kbuf;                                                   // [2][128] row maxima of the two halves
-            volatile int* flag = reinterpret_cast<volatile int*>(kbuf + 2 * kTile);   // [2] by tile parity
+            float* xg = kbuf;                                                   // [2 parities][2 halves][128] row maxima
             const int ngrp = p.HH / 32;
-            if (et < 2) flag[et] = 0;
-            epi_sync();
             for (int i = 0; i < n_iter; ++i) {
                 const int t0 = (j0 + i) * NT;
                 mbar_wait(bar_sfull, i & 1);
+                if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t acc[4][32];
 #pragma unroll
@@ -783,38 +781,43 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
-                float gmax = -INFINITY;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + (g >> 1) * 128 + ch * 64 + (g & 1) * 32);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 bv = __ldg(b4 + e);
-                        const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x);
-                        const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y);
-                        const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z);
-                        const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w);
-                        acc[g][4 * e + 0] = __float_as_uint(y0);
-                        acc[g][4 * e + 1] = __float_as_uint(y1);
-                        acc[g][4 * e + 2] = __float_as_uint(y2);
-                        acc[g][4 * e + 3] = __float_as_uint(y3);
-                        gmax = fmaxf(gmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                    }
-                }
-                xg[ch * kTile + row] = gmax;
-                epi_sync();
-                const float rowmax = fmaxf(xg[row], xg[kTile + row]);
-                const bool need = rowmax > mref + 3.f;            // true on the first tile (mref = -inf)
-                const float nref = need ? rowmax + 2.f : mref;
-                const float fsc = need ? ex2f(mref - nref) : 1.f; // 0 on the first tile
-                if (need && i > 0) flag[i & 1] = 1;
-                ssum *= fsc;
-                epi_sync();
-                const bool rescale = flag[i & 1] != 0;            // uniform over the CTA
-                if (et == 0) flag[(i + 1) & 1] = 0;
 #pragma unroll
                 for (int sp = 0; sp < 2; ++sp) {
+                    // ---- logits (log2 units) of this sub-pass and the row maximum over its 128 columns
                     const int c0 = t0 + sp * 128;
+                    float gmax = -INFINITY;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + c0 + ch * 64 + g * 32);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = __ldg(b4 + e);
+                            const float y0 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 0]), c1, bv.x);
+                            const float y1 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 1]), c1, bv.y);
+                            const float y2 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 2]), c1, bv.z);
+                            const float y3 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 3]), c1, bv.w);
+                            acc[sp * 2 + g][4 * e + 0] = __float_as_uint(y0);
+                            acc[sp * 2 + g][4 * e + 1] = __float_as_uint(y1);
+                            acc[sp * 2 + g][4 * e + 2] = __float_as_uint(y2);
+                            acc[sp * 2 + g][4 * e + 3] = __float_as_uint(y3);
+                            gmax = fmaxf(gmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                        }
+                    }
+                    // The two warps that share a lane quarter (column halves ch = 0 / 1 of the same 32 rows) exchange
+                    // their maxima through shared memory behind a 64-thread named barrier; both then take the same
+                    // decision, so the TMEM rescale below only needs warp-level agreement (tcgen05.ld/st are
+                    // warp-collective), not a CTA-wide one.
+                    const int n = 2 * i + sp;                         // sub-pass counter
+                    xg[(n & 1) * 2 * kTile + ch * kTile + row] = gmax;
+                    asm volatile("bar.sync %0, 64;" ::"r"(kEpiBarrier + 1 + q) : "memory");
+                    const float rowmax = fmaxf(gmax, xg[(n & 1) * 2 * kTile + (ch ^ 1) * kTile + row]);
+                    const bool need = rowmax > mref + 3.f;            // true on the first sub-pass (mref = -inf)
+                    const float nref = need ? rowmax + 2.f : mref;
+                    const float fsc = need ? ex2f(mref - nref) : 1.f; // 0 on the first sub-pass
+                    const bool rescale = __any_sync(0xffffffffu, need && n > 0);   // same in both partner warps
+                    ssum *= fsc;
+                    mref = nref;
+                    if (et == 0 && sp == 0) trace_at(p, 2, i, 1);
                     uint32_t packed[32];
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
@@ -823,7 +826,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                         float part = 0.f;
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            val[e] = ex2f(__uint_as_float(acc[sp * 2 + g][e]) - nref + lg_scale);
+                            val[e] = ex2f(__uint_as_float(acc[sp * 2 + g][e]) - mref + lg_scale);
                             part += val[e];
                         }
                         ssum += part;
@@ -839,7 +842,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                         for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
                     }
                     mbar_wait(bar_pempty, sp ^ 1);
-                    if (sp == 0 && rescale) {
+                    if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
+                    if (rescale) {
                         // every G pass issued so far has completed (bar_pempty): scale this row's accumulators
                         tc_fence_after();
                         uint32_t gacc[32];
@@ -863,8 +867,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     if (clb >= ch * 64 && clb < ch * 64 + 64) *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = 0;
                     fence_proxy_async_smem();
                     epi_arrive(bar_pfull);
+                    if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
                 }
-                mref = nref;
             }
             mbar_wait(bar_gfull, 0);
             tc_fence_after();
@@ -1228,7 +1232,7 @@ static void trace_dump(const char* what, cudaStream_t stream) {
     cudaMemset(buf, 0, sizeof(h));
     long long t0 = h[(1 * kTraceIters + 0) * 4 + 0];
     fprintf(stderr, "TRACE %s (cycles since first MMA-loop entry)\n", what);
-    fprintf(stderr, " it | prod: loop loadS_done loadG_done | mma: loop S_issued pfull G_issued | epi: sfull math_done pempty pfull_arr\n");
+    fprintf(stderr, " it | prod (unused in pair kernels) | mma: loop Sa_issued G0_issued Sb+G1_issued | epi: sfull S_released/ref_done pempty0 pfull1_arrived\n");
     for (int i = 0; i < 12; ++i) {
         fprintf(stderr, "%3d |", i);
         for (int r = 0; r < 3; ++r) {
@@ -1320,7 +1324,7 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     p.n_halves = (H > 256) ? 2 : 1;
     p.HH = H / p.n_halves;
     p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-    p.trace = nullptr;
+    p.trace = trace_buffer();
     const size_t fixed = (size_t)(p.NKC + 2) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     int ns = 8;
     while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
@@ -1341,8 +1345,10 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
     if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
     dim3 grid(n_tiles_ub, p.n_halves, 1);
-    return bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
-                : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
+    int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
+                  : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
+    if (rc == 0) trace_dump("FG", stream);
+    return rc;
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const void* w16t, uint64_t rows_ub,
