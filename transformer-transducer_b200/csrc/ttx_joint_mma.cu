@@ -596,7 +596,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         __trap();
     }
     const uint32_t sX = smem_base;
-    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // 128 x 128 16-bit, K-major, 2 blocks
+    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // 2 x [128 x 64] 16-bit, K-major: ping-pong halves
     const uint32_t sRing = sP + 2 * kChunkBytes;
     const uint32_t sBar = sRing + p.NS * STAGE;
     const uint32_t sTmemPtr = sBar + kNumBars * 8;
@@ -608,9 +608,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
     auto bar_empty = [&](int s) { return sBar + 8 * (17 + s); };
     const uint32_t bar_sfull = sBar + 8 * 33;
-    const uint32_t bar_sempty = sBar + 8 * 35;
-    const uint32_t bar_pfull = sBar + 8 * 37;
-    const uint32_t bar_pempty = sBar + 8 * 38;
+    const uint32_t bar_sempty = sBar + 8 * 34;
+    auto bar_pfull = [&](int b) { return sBar + 8 * (35 + b); };     // one barrier pair per half of the P' buffer
+    auto bar_pempty = [&](int b) { return sBar + 8 * (37 + b); };
     const uint32_t bar_gfull = sBar + 8 * 39;
 
     const int warp = threadIdx.x >> 5;
@@ -628,8 +628,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         mbar_init(bar_sfull, 1);
         mbar_init(bar_sempty, 2 * kEpiWarps);       // every epilogue warp of both CTAs
-        mbar_init(bar_pfull, 2 * kEpiWarps);        // every epilogue warp of both CTAs, once per sub-pass
-        mbar_init(bar_pempty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_pfull(b), 2 * kEpiWarps);  // every epilogue warp of both CTAs, once per sub-pass
+            mbar_init(bar_pempty(b), 1);
+        }
         mbar_init(bar_gfull, 1);
         fence_barrier_init();
     }
@@ -658,23 +660,18 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
                 r.advance(p.NS);
             };
-            const int nk2 = p.NKC / 2;
-            auto load_S = [&](int j, int part) {       // half of the S-pass k chunks of stream tile j
-                for (int c = part * nk2; c < (part + 1) * nk2; ++c)
-                    load_stage(&mapY, c * kKC, j * NT + (int)rank * SR, STAGE);
+            auto load_S = [&](int j) {
+                for (int c = 0; c < p.NKC; ++c) load_stage(&mapY, c * kKC, j * NT + (int)rank * SR, STAGE);
             };
-            auto load_G = [&](int j, int sp) {         // K-major B chunks: [hh2 joint columns x 64 stream rows]
+            auto load_G = [&](int j) {                 // K-major B chunks: [hh2 joint columns x 64 stream rows]
                 const int h0 = half * p.HH + (int)rank * hh2;
-                for (int c = 2 * sp; c < 2 * sp + 2; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
+                for (int c = 0; c < 4; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
             };
-            // same order as the MMA issuer: Sa(i+1), G(i,0), Sb(i+1), G(i,1)
-            load_S(j0, 0);
-            load_S(j0, 1);
+            // same order as the MMA issuer: S(i+1), then the four G sub-passes of tile i
+            load_S(j0);
             for (int i = 0; i < n_iter; ++i) {
-                if (i + 1 < n_iter) load_S(j0 + i + 1, 0);
-                load_G(j0 + i, 0);
-                if (i + 1 < n_iter) load_S(j0 + i + 1, 1);
-                load_G(j0 + i, 1);
+                if (i + 1 < n_iter) load_S(j0 + i + 1);
+                load_G(j0 + i);
             }
         }
     } else if (warp == 1) {
@@ -685,16 +682,13 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const uint32_t idescG = make_idesc(fmt, 0, 0, 256, p.HH);
             Ring r;
             mbar_wait(bar_xfull, 0);
-            const int nk2 = p.NKC / 2;
-            // S pass of stream tile idx in two halves (k chunks [0, NKC/2) and [NKC/2, NKC)) so that the two G
-            // sub-passes of the previous tile can be interleaved: Sa(i+1), G(i,0), Sb(i+1), G(i,1).  The P' tile is
-            // written for sub-pass 1 while Sb runs, and for the next tile's sub-pass 0 while the next Sa runs.
-            auto issue_S = [&](int idx, int part) {
-                if (part == 0) {
-                    mbar_wait(bar_sempty, (idx & 1) ^ 1);  // the epilogue has read the previous S tile out of TMEM
-                    tc_fence_after();
-                }
-                for (int c = part * nk2; c < (part + 1) * nk2; ++c) {
+            // Issue order S(i+1), G(i,0..3).  The epilogue needs ~2000 cycles to read an S tile out of TMEM before
+            // the next S pass may overwrite it; the four G sub-passes of the previous tile (64 stream columns = one
+            // 16 KiB half of the ping-pong P' buffer each) are issued right behind the S pass to cover that window.
+            auto issue_S = [&](int idx) {
+                mbar_wait(bar_sempty, (idx & 1) ^ 1);          // the epilogue has read the previous S tile out of TMEM
+                tc_fence_after();
+                for (int c = 0; c < p.NKC; ++c) {
                     mbar_wait(bar_full(r.stage), r.phase);
                     tc_fence_after();
                     const uint32_t a = sX + c * kChunkBytes;
@@ -707,37 +701,32 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     umma_commit_pair(bar_empty(r.stage));
                     r.advance(p.NS);
                 }
-                if (part == 1) umma_commit_pair(bar_sfull);
+                umma_commit_pair(bar_sfull);
             };
-            auto issue_G = [&](int idx, int sp) {
-                mbar_wait(bar_pfull, sp);                      // sub-pass n = 2 idx + sp, parity n & 1
-                tc_fence_after();
-                for (int c = 0; c < 2; ++c) {
+            auto issue_G = [&](int idx) {
+                for (int sp = 0; sp < 4; ++sp) {
+                    const int pb = sp & 1;                      // P' half; this is its use number 2 idx + (sp >> 1)
+                    mbar_wait(bar_pfull(pb), (sp >> 1) & 1);
                     mbar_wait(bar_full(r.stage), r.phase);
                     tc_fence_after();
-                    const uint32_t a = sP + c * kChunkBytes;
+                    const uint32_t a = sP + pb * kChunkBytes;
                     const uint32_t b = sRing + r.stage * STAGE;
                     if (!(p.dbg & 2)) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_f16_ss_pair(tmem_G, desc_kmajor(a, k), desc_kmajor(b, k), idescG,
-                                             (idx | sp | c | k) != 0);
+                            umma_f16_ss_pair(tmem_G, desc_kmajor(a, k), desc_kmajor(b, k), idescG, (idx | sp | k) != 0);
                     }
                     umma_commit_pair(bar_empty(r.stage));
+                    umma_commit_pair(bar_pempty(pb));
                     r.advance(p.NS);
                 }
-                umma_commit_pair(bar_pempty);
             };
-            issue_S(0, 0);
-            issue_S(0, 1);
+            issue_S(0);
             for (int i = 0; i < n_iter; ++i) {
                 trace_at(p, 1, i, 0);
-                if (i + 1 < n_iter) issue_S(i + 1, 0);
+                if (i + 1 < n_iter) issue_S(i + 1);
                 trace_at(p, 1, i, 1);
-                issue_G(i, 0);
-                trace_at(p, 1, i, 2);
-                if (i + 1 < n_iter) issue_S(i + 1, 1);
-                issue_G(i, 1);
+                issue_G(i);
                 trace_at(p, 1, i, 3);
             }
             umma_commit_pair(bar_gfull);
@@ -766,7 +755,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             // is added after the lattice by the reduction kernels.  EW = G * 2^(mref - lse2) / w_scale = sum_v p_v W_v.
             const int grow = x_row0 + row;
             const int label = valid_x ? p.row_label[grow] : -1;
-            float mref = -INFINITY, ssum = 0.f, zb = 0.f, zl = 0.f;
+            float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;     // mref: finite start, fixed by the first sub-pass
             float* xg = kbuf;                                                   // [2 parities][2 halves][128] row maxima
             const int ngrp = p.HH / 32;
             for (int i = 0; i < n_iter; ++i) {
@@ -777,97 +766,98 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 uint32_t acc[4][32];
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                    tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
+                    tmem_ld32(tmem_base + lane_addr + g * 64 + ch * 32, acc[g]);   // sub-pass g: columns g*64 + ch*32 ..
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
 #pragma unroll
-                for (int sp = 0; sp < 2; ++sp) {
-                    // ---- logits (log2 units) of this sub-pass and the row maximum over its 128 columns
-                    const int c0 = t0 + sp * 128;
-                    float gmax = -INFINITY;
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + c0 + ch * 64 + g * 32);
+                for (int sp = 0; sp < 4; ++sp) {
+                    // ---- optimistic single pass over this sub-pass's 32 columns: yq = y - mref + lg_scale with the
+                    // CURRENT reference; the partner warps (column halves of the same 32 rows) exchange their maxima
+                    // and only when a row exceeds the fp16 headroom (y > mref + 3) -- always on the very first
+                    // sub-pass -- the reference moves and the rows' accumulators are rescaled in TMEM.
+                    const int pb = sp & 1;
+                    const int n = 4 * i + sp;                         // global sub-pass counter
+                    const int c0 = t0 + sp * 64;                      // first stream column of this sub-pass
+                    const int vb = c0 + ch * 32;
+                    const float krow = lg_scale - mref;
+                    float yq[32];
+                    float lmax = -INFINITY;
+                    {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + vb);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const float4 bv = __ldg(b4 + e);
-                            const float y0 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 0]), c1, bv.x);
-                            const float y1 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 1]), c1, bv.y);
-                            const float y2 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 2]), c1, bv.z);
-                            const float y3 = fmaf(__uint_as_float(acc[sp * 2 + g][4 * e + 3]), c1, bv.w);
-                            acc[sp * 2 + g][4 * e + 0] = __float_as_uint(y0);
-                            acc[sp * 2 + g][4 * e + 1] = __float_as_uint(y1);
-                            acc[sp * 2 + g][4 * e + 2] = __float_as_uint(y2);
-                            acc[sp * 2 + g][4 * e + 3] = __float_as_uint(y3);
-                            gmax = fmaxf(gmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                            yq[4 * e + 0] = fmaf(__uint_as_float(acc[sp][4 * e + 0]), c1, bv.x + krow);
+                            yq[4 * e + 1] = fmaf(__uint_as_float(acc[sp][4 * e + 1]), c1, bv.y + krow);
+                            yq[4 * e + 2] = fmaf(__uint_as_float(acc[sp][4 * e + 2]), c1, bv.z + krow);
+                            yq[4 * e + 3] = fmaf(__uint_as_float(acc[sp][4 * e + 3]), c1, bv.w + krow);
+                            lmax = fmaxf(lmax, fmaxf(fmaxf(yq[4 * e + 0], yq[4 * e + 1]), fmaxf(yq[4 * e + 2], yq[4 * e + 3])));
                         }
                     }
-                    // The two warps that share a lane quarter (column halves ch = 0 / 1 of the same 32 rows) exchange
-                    // their maxima through shared memory behind a 64-thread named barrier; both then take the same
-                    // decision, so the TMEM rescale below only needs warp-level agreement (tcgen05.ld/st are
-                    // warp-collective), not a CTA-wide one.
-                    const int n = 2 * i + sp;                         // sub-pass counter
-                    xg[(n & 1) * 2 * kTile + ch * kTile + row] = gmax;
+                    xg[(n & 1) * 2 * kTile + ch * kTile + row] = lmax;
                     asm volatile("bar.sync %0, 64;" ::"r"(kEpiBarrier + 1 + q) : "memory");
-                    const float rowmax = fmaxf(gmax, xg[(n & 1) * 2 * kTile + (ch ^ 1) * kTile + row]);
-                    const bool need = rowmax > mref + 3.f;            // true on the first sub-pass (mref = -inf)
-                    const float nref = need ? rowmax + 2.f : mref;
-                    const float fsc = need ? ex2f(mref - nref) : 1.f; // 0 on the first sub-pass
-                    const bool rescale = __any_sync(0xffffffffu, need && n > 0);   // same in both partner warps
-                    ssum *= fsc;
-                    mref = nref;
-                    if (et == 0 && sp == 0) trace_at(p, 2, i, 1);
-                    uint32_t packed[32];
+                    const float rmax = fmaxf(lmax, xg[(n & 1) * 2 * kTile + (ch ^ 1) * kTile + row]);
+                    const bool need = (n == 0) || (rmax > lg_scale + 3.f);      // (rmax = -inf on all-padding columns)
+                    if (__any_sync(0xffffffffu, need)) {                       // same outcome in both partner warps
+                        // new reference = row maximum + 2 (log2 units): yq shifts by -delta, sums and accumulators by 2^-delta
+                        const float delta = (need && rmax > -INFINITY) ? (rmax - lg_scale + 2.f) : 0.f;
+                        const float fsc = ex2f(-delta);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int vb = c0 + ch * 64 + g * 32;
-                        float val[32];
+                        for (int e = 0; e < 32; ++e) yq[e] -= delta;
+                        ssum *= fsc;
+                        mref += delta;
+                        if (n > 0) {
+                            // all G sub-passes issued so far must have completed before the accumulators are scaled
+                            mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);
+                            mbar_wait(bar_pempty(pb ^ 1), (((sp + 1) >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                            uint32_t gacc[32];
+                            for (int cc = ch; cc < ngrp; cc += 2) {
+                                tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
+                                tmem_st32(tmem_G + lane_addr + cc * 32, gacc);
+                            }
+                            tmem_st_wait();
+                            tc_fence_before();
+                        }
+                    }
+                    if (p.blank >= vb && p.blank < vb + 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zb = (vb + e == p.blank) ? yq[e] + mref - lg_scale : zb;
+                    }
+                    if (label >= vb && label < vb + 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zl = (vb + e == label) ? yq[e] + mref - lg_scale : zl;
+                    }
+                    uint32_t packed[16];
+                    {
                         float part = 0.f;
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            val[e] = ex2f(__uint_as_float(acc[sp * 2 + g][e]) - mref + lg_scale);
-                            part += val[e];
+                            yq[e] = ex2f(yq[e]);
+                            part += yq[e];
                         }
                         ssum += part;
-                        if (p.blank >= vb && p.blank < vb + 32) {
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) zb = (vb + e == p.blank) ? __uint_as_float(acc[sp * 2 + g][e]) : zb;
-                        }
-                        if (label >= vb && label < vb + 32) {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) zl = (vb + e == label) ? __uint_as_float(acc[sp * 2 + g][e]) : zl;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+                        for (int e = 0; e < 16; ++e) packed[e] = pack16<BF16>(yq[2 * e], yq[2 * e + 1]);
                     }
-                    mbar_wait(bar_pempty, sp ^ 1);
+                    mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);   // use 2i + (sp >> 1) of this half
                     if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
-                    if (rescale) {
-                        // every G pass issued so far has completed (bar_pempty): scale this row's accumulators
-                        tc_fence_after();
-                        uint32_t gacc[32];
-                        for (int cc = ch; cc < ngrp; cc += 2) {
-                            tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
-                            tmem_ld_wait();
+                    uint8_t* dstP = sP_gen + pb * kChunkBytes;
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
-                            tmem_st32(tmem_G + lane_addr + cc * 32, gacc);
-                        }
-                        tmem_st_wait();
-                        tc_fence_before();
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {
+                    for (int cc = 0; cc < 4; ++cc) {
                         uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                        *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                        *reinterpret_cast<uint4*>(dstP + row * 128 + (((ch * 4 + cc) ^ (row & 7)) << 4)) = v4;
                     }
                     const int cbl = p.blank - c0, clb = label - c0;
-                    if (cbl >= ch * 64 && cbl < ch * 64 + 64) *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = 0;
-                    if (clb >= ch * 64 && clb < ch * 64 + 64) *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = 0;
+                    if (cbl >= ch * 32 && cbl < ch * 32 + 32) *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, cbl)) = 0;
+                    if (clb >= ch * 32 && clb < ch * 32 + 32) *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, clb)) = 0;
                     fence_proxy_async_smem();
-                    epi_arrive(bar_pfull);
-                    if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
+                    epi_arrive(bar_pfull(pb));
+                    if (et == 0 && sp == 3) trace_at(p, 2, i, 3);
                 }
             }
             mbar_wait(bar_gfull, 0);
@@ -881,9 +871,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             if (ch == 0) {
                 const float4 o = xch[row];
                 lse2 = mref - lg_scale + lg2f(ssum + o.x);
-                const int cb_in = p.blank % NT;                   // column of blank / label inside its 256-column tile
-                zb = ((cb_in & 127) < 64) ? zb : o.y;
-                if (label >= 0) zl = (((label % NT) & 127) < 64) ? zl : o.z;
+                zb = ((p.blank & 63) < 32) ? zb : o.y;            // which column half (ch) owns the blank / label column
+                if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
                 if (valid_x && half == 0) {
                     p.lse[grow] = lse2 * kLn2;
                     p.lpb[grow] = (zb - lse2) * kLn2;
@@ -942,89 +931,87 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 mbar_wait(bar_sfull, i & 1);
                 if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
-                // Pull this thread's share of the S tile (2 sub-passes x 64 columns) into registers and hand the single S
+                // Pull this thread's share of the S tile (4 sub-passes x 32 columns) into registers and hand the single S
                 // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
                 uint32_t acc[4][32];
-    #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    tmem_ld32(tmem_base + lane_addr + (g >> 1) * 128 + ch * 64 + (g & 1) * 32, acc[g]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tmem_ld32(tmem_base + lane_addr + g * 64 + ch * 32, acc[g]);
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
                 if (et == 0) trace_at(p, 2, i, 1);
-    #pragma unroll
-                for (int sp = 0; sp < 2; ++sp) {
-                    const int c0 = t0 + sp * 128;           // first stream index of this sub-pass
-                    uint32_t packed[32];
-    #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int cb = sp * 128 + ch * 64 + g * 32;   // column inside the 256-column tile
-                        if (p.dbg & 4) {
-    #pragma unroll
-                            for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
-                            continue;
-                        }
+#pragma unroll
+                for (int sp = 0; sp < 4; ++sp) {
+                    const int pb = sp & 1;
+                    const int c0 = t0 + sp * 64;            // first stream index of this sub-pass
+                    const int cb = sp * 64 + ch * 32;       // this thread's first column inside the 256-column tile
+                    uint32_t packed[16];
+                    if (p.dbg & 4) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) packed[e] = 0;
+                    } else {
                         float kc[32];
                         if (MODE == MODE_DA) {
                             const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + cb);
-    #pragma unroll
+#pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float4 bv = __ldg(b4 + e);
                                 kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
                             }
                         } else {
                             const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
-    #pragma unroll
+#pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float4 kv = k4[e];
                                 kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
                             }
                         }
                         float val[32];
-    #pragma unroll
+#pragma unroll
                         for (int e = 0; e < 32; ++e)
-                            val[e] = ex2f(fmaf(__uint_as_float(acc[sp * 2 + g][e]), c1, kc[e] + krow));
+                            val[e] = ex2f(fmaf(__uint_as_float(acc[sp][e]), c1, kc[e] + krow));
                         if (MODE == MODE_DW) {
                             if (any_neg) {
                                 const float* sg = kbuf + NT + cb;
-    #pragma unroll
+#pragma unroll
                                 for (int e = 0; e < 32; ++e) val[e] *= sg[e];
                             }
-    #pragma unroll
+#pragma unroll
                             for (int e = 0; e < 32; ++e) db_acc += val[e];
                         }
-    #pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) packed[e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
                     }
-                    // Sub-pass n = 2i + sp may overwrite the P' tile once the G pass of sub-pass n - 1 has completed
-                    // (completion #n of bar_pempty, parity (n - 1) & 1).  Every thread waits for every sub-pass in
-                    // order, so the parity wait never has to look more than one phase ahead.
-                    mbar_wait(bar_pempty, sp ^ 1);
+                    // This is use number 2i + (sp >> 1) of P' half pb: it may be overwritten once the G sub-pass of the
+                    // previous use has completed.  Every thread visits every use in order, so the parity wait never has
+                    // to look more than one phase ahead.
+                    mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);
                     if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
-    #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {        // this thread's 64 columns = 8 chunks of 16 B in block ch
+                    uint8_t* dstP = sP_gen + pb * kChunkBytes;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {        // this thread's 32 columns = 4 chunks of 16 B
                         uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                        *reinterpret_cast<uint4*>(sP_gen + ch * kChunkBytes + row * 128 + ((cc ^ (row & 7)) << 4)) = v4;
+                        *reinterpret_cast<uint4*>(dstP + row * 128 + (((ch * 4 + cc) ^ (row & 7)) << 4)) = v4;
                     }
                     if (MODE == MODE_DA) {
                         const int cbl = p.blank - c0, clb = label - c0;
-                        if (cbl >= ch * 64 && cbl < ch * 64 + 64)
-                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
-                        if (clb >= ch * 64 && clb < ch * 64 + 64)
-                            *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+                        if (cbl >= ch * 32 && cbl < ch * 32 + 32)
+                            *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
+                        if (clb >= ch * 32 && clb < ch * 32 + 32)
+                            *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
                     } else {
                         epi_sync();                         // column owners patch rows written by other threads
-                        if ((et >> 7) == sp) {
+                        if ((et >> 6) == sp) {
                             const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
                             if (rbl >= 0 && rbl < kTile)
-                                *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rbl, et & 127)) = to16<BF16>(cm.y * cm.w * pscale);
+                                *reinterpret_cast<uint16_t*>(dstP + ptile_off(rbl, et & 63)) = to16<BF16>(cm.y * cm.w * pscale);
                             if (rlb >= 0 && rlb < kTile)
-                                *reinterpret_cast<uint16_t*>(sP_gen + ptile_off(rlb, et & 127)) = to16<BF16>(cm.z * cm.w * pscale);
+                                *reinterpret_cast<uint16_t*>(dstP + ptile_off(rlb, et & 63)) = to16<BF16>(cm.z * cm.w * pscale);
                         }
                     }
                     fence_proxy_async_smem();
-                    epi_arrive(bar_pfull);
-                    if (et == 0 && sp == 1) trace_at(p, 2, i, 3);
+                    epi_arrive(bar_pfull(pb));
+                    if (et == 0 && sp == 3) trace_at(p, 2, i, 3);
                 }
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global
