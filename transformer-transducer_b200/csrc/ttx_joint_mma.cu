@@ -48,7 +48,8 @@ struct MmaParams {
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;         // + TMA producer warp + MMA issuer warp
-constexpr int kNumBars = 40;
+constexpr int kNumBars = 44;
+constexpr int kPB = 2;                             // pair kernel: P' sub-tile buffers (16 KiB each)
 constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
 constexpr int kMaxStages = 16;
 
@@ -63,6 +64,50 @@ struct Ring {
         }
     }
 };
+
+// Position in the pair kernel's ring of P' sub-tile buffers: sub-pass n uses buffer n % kPB; `phase` = parity of its
+// use count n / kPB.  The MMA issuer and every epilogue thread step through the sub-passes in the same order.
+struct PRing {
+    int buf = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++buf == kPB) {
+            buf = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+constexpr int kPairEpiWarps = 8;                   // pair kernel: two epilogue warps per TMEM lane quarter
+constexpr int kPairEpiThreads = kPairEpiWarps * 32;
+constexpr int kPairThreads = kPairEpiThreads + 128;   // + one control warpgroup: TMA producer, MMA issuer, two idle warps
+constexpr int kPairCtrlRegs = 72;                  // setmaxnreg: the control warpgroup gives its registers ...
+constexpr int kPairEpiRegs = 216;                  // ... to the epilogue warps (12 warps x 168 = 4 x 72 + 8 x 216)
+// The two single-thread control warps get the HIGHEST warp ids: the issue arbiter prefers high warp ids, and a TMA
+// producer / MMA issuer starved by spinning epilogue warps stalls the whole pipeline (measured: 1.5x slower with ids 0, 1).
+constexpr int kPairProducerWarp = kPairEpiWarps;
+constexpr int kPairMmaWarp = kPairEpiWarps + 1;
+constexpr int kQuarterBarrier = 2;                 // named barriers 2..5: the four epilogue warps of lane quarter q
+
+__device__ __forceinline__ void pair_epi_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(kPairEpiThreads) : "memory");
+}
+__device__ __forceinline__ void quarter_sync(int q) {
+    asm volatile("bar.sync %0, %1;" ::"r"(kQuarterBarrier + q), "n"(kPairEpiThreads / 4) : "memory");
+}
+// Barrier over the epilogue threads of lane quarter q that also ORs a predicate across them.
+__device__ __forceinline__ bool quarter_any(int q, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred pin, pout;\n\t"
+        "setp.ne.b32 pin, %2, 0;\n\t"
+        "bar.red.or.pred pout, %1, %3, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t}"
+        : "=r"(r)
+        : "r"(kQuarterBarrier + q), "r"((uint32_t)pred), "n"(kPairEpiThreads / 4)
+        : "memory");
+    return r != 0;
+}
 
 __device__ __forceinline__ void epi_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(kEpiThreads) : "memory");
@@ -561,7 +606,7 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 // 128-column P' tile in two sub-passes, and takes the G-pass B operand K-major from a transposed copy of the
 // streamed matrix (W16^T for dA, A16^T for dW).  48 instructions per 256 stream rows instead of 80.
 template <int MODE, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                       const __grid_constant__ CUtensorMap mapYT, const MmaParams p) {
     constexpr int NT = 256;                 // stream rows per step (pair-wide) = S accumulator columns
@@ -596,8 +641,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         __trap();
     }
     const uint32_t sX = smem_base;
-    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // 2 x [128 x 64] 16-bit, K-major: ping-pong halves
-    const uint32_t sRing = sP + 2 * kChunkBytes;
+    const uint32_t sP = sX + p.NKC * kChunkBytes;                   // kPB x [128 x 64] 16-bit, K-major: P' sub-tile ring
+    const uint32_t sRing = sP + kPB * kChunkBytes;
     const uint32_t sBar = sRing + p.NS * STAGE;
     const uint32_t sTmemPtr = sBar + kNumBars * 8;
     const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 256 exponent offsets + 256 signs
@@ -609,15 +654,15 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     auto bar_empty = [&](int s) { return sBar + 8 * (17 + s); };
     const uint32_t bar_sfull = sBar + 8 * 33;
     const uint32_t bar_sempty = sBar + 8 * 34;
-    auto bar_pfull = [&](int b) { return sBar + 8 * (35 + b); };     // one barrier pair per half of the P' buffer
-    auto bar_pempty = [&](int b) { return sBar + 8 * (37 + b); };
-    const uint32_t bar_gfull = sBar + 8 * 39;
+    const uint32_t bar_gfull = sBar + 8 * 35;
+    auto bar_pfull = [&](int b) { return sBar + 8 * (36 + b); };     // one barrier pair per P' sub-tile buffer
+    auto bar_pempty = [&](int b) { return sBar + 8 * (36 + kPB + b); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 512;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kPairProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapYT);
@@ -627,15 +672,15 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_sfull, 1);
-        mbar_init(bar_sempty, 2 * kEpiWarps);       // every epilogue warp of both CTAs
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_pfull(b), 2 * kEpiWarps);  // every epilogue warp of both CTAs, once per sub-pass
+        mbar_init(bar_sempty, 2 * kPairEpiWarps);       // every epilogue warp of both CTAs
+        for (int b = 0; b < kPB; ++b) {
+            mbar_init(bar_pfull(b), 2 * kPairEpiWarps);  // every epilogue warp of both CTAs, once per sub-pass
             mbar_init(bar_pempty(b), 1);
         }
         mbar_init(bar_gfull, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_pair(sTmemPtr, kTmemCols);
+    if (warp == kPairMmaWarp) tmem_alloc_pair(sTmemPtr, kTmemCols);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -648,7 +693,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         if (lane == 0) mbar_arrive_cluster(bar, 0);
     };
 
-    if (warp == 0) {
+    if (warp >= kPairEpiWarps) {
+        // =========================================================== control warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPairCtrlRegs));
+      if (warp == kPairProducerWarp) {
         // =========================================================== TMA producer
         if (lane == 0) {
             if (leader) mbar_arrive_expect_tx(bar_xfull, 2 * p.NKC * kChunkBytes);
@@ -656,6 +704,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             Ring r;
             auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
                 mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                if (p.dbg & 8) bytes >>= 1;        // timing experiment: the tensor maps' boxes are half as tall
                 if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * bytes);
                 tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
                 r.advance(p.NS);
@@ -674,7 +723,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 load_G(j0 + i);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == kPairMmaWarp) {
         // =========================================================== MMA issuer (leader CTA)
         if (lane == 0 && leader) {
             constexpr int fmt = BF16 ? 1 : 0;
@@ -703,10 +752,11 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 }
                 umma_commit_pair(bar_sfull);
             };
+            PRing pr;                                           // P' sub-tile ring: sub-pass n uses buffer n % kPB
             auto issue_G = [&](int idx) {
                 for (int sp = 0; sp < 4; ++sp) {
-                    const int pb = sp & 1;                      // P' half; this is its use number 2 idx + (sp >> 1)
-                    mbar_wait(bar_pfull(pb), (sp >> 1) & 1);
+                    const int pb = pr.buf;
+                    mbar_wait(bar_pfull(pb), pr.phase);
                     mbar_wait(bar_full(r.stage), r.phase);
                     tc_fence_after();
                     const uint32_t a = sP + pb * kChunkBytes;
@@ -719,6 +769,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     umma_commit_pair(bar_empty(r.stage));
                     umma_commit_pair(bar_pempty(pb));
                     r.advance(p.NS);
+                    pr.advance();
                 }
             };
             issue_S(0);
@@ -731,12 +782,20 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             }
             umma_commit_pair(bar_gfull);
         }
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPairEpiRegs));
         // =========================================================== epilogue warps: thread = (row, column half ch)
+        // Eight warps, two per TMEM lane quarter: thread (row, ch) owns columns ch*32 .. ch*32+31 of each of the tile's
+        // four 64-column sub-tiles.  A whole 256-column S tile is processed in registers in ONE pass per warp: one
+        // TMEM read-out (the S accumulator is handed back immediately), one reference vote (forward+gradient mode),
+        // and two store rounds (sub-tiles 0..2 into buffers that are already free, sub-tile 3 once the first G
+        // sub-pass of this tile has released a buffer) -- every synchronisation point costs a few hundred cycles of
+        // latency per warp, so there are as few of them per tile as the three P' buffers allow.
         const int q = warp & 3;
-        const int ch = (warp - 2) >> 2;               // which 64-column half of each 128-column sub-pass
+        const int ch = warp >> 2;
         const int row = q * 32 + lane;
-        const int et = threadIdx.x - 64;              // 0..255
+        const int et = threadIdx.x;                   // 0..255
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float inv_ws = p.scal[1];
         const float c1 = inv_ws * kLog2e;
@@ -746,155 +805,232 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         const float lg_scale = BF16 ? 0.0f : 12.0f;
         const bool any_neg = p.scal[3] != 0.f;
         const int n_valid_rows = n_tiles * kTile;
+        PRing pr;                                     // buffer of the tile's sub-tile 0 (sub-pass n = 4 i)
+        // this thread's 32 columns of sub-tile g: four 16-byte chunks at swizzled positions (ch*4 + c) ^ (row & 7)
+        auto store_p = [&](uint8_t* dstP, const uint32_t* packed) {
+            uint8_t* r0 = dstP + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
+                    make_uint4(packed[4 * c + 0], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        };
+        // Store rounds.  `patch(g, dstP)` fixes up the blank / label entries of sub-tile g after the dense stores.
+        auto store_rounds = [&](const uint32_t (&packed)[4][16], auto&& patch, const int i) {
+            PRing r = pr;
+            uint8_t* dst[4];
+            int bufs[4];
+            // round A: the first kPB sub-tiles go into buffers released by the previous tile's G sub-passes
+#pragma unroll
+            for (int g = 0; g < kPB; ++g) {
+                mbar_wait(bar_pempty(r.buf), r.phase ^ 1);    // the G sub-pass of this buffer's previous use is done
+                bufs[g] = r.buf;
+                dst[g] = sP_gen + r.buf * kChunkBytes;
+                store_p(dst[g], packed[g]);
+                r.advance();
+            }
+            if (et == 0) trace_at(p, 2, i, 2);
+            patch(0, kPB, dst);
+            fence_proxy_async_smem();
+#pragma unroll
+            for (int g = 0; g < kPB; ++g) epi_arrive(bar_pfull(bufs[g]));
+            // later rounds: one sub-tile each, as this tile's own G sub-passes release the buffers
+#pragma unroll
+            for (int g = kPB; g < 4; ++g) {
+                mbar_wait(bar_pempty(r.buf), r.phase ^ 1);
+                bufs[g] = r.buf;
+                dst[g] = sP_gen + r.buf * kChunkBytes;
+                store_p(dst[g], packed[g]);
+                r.advance();
+                patch(g, g + 1, dst);
+                fence_proxy_async_smem();
+                epi_arrive(bar_pfull(bufs[g]));
+            }
+            if (et == 0) trace_at(p, 2, i, 3);
+            pr = r;
+        };
         if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
             // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
-            // mref (log2 units).  mref only moves when a later tile's row maximum exceeds it by 2^3; then the rows'
-            // accumulators are rescaled in TMEM before the next sub-pass (rare: first tiles / outlier logits).
+            // mref (log2 units).  The reference is fixed by the first tile and only moves when a later tile would
+            // overflow the 16-bit operand; then the rows' accumulators are rescaled in TMEM (rare).
             // The blank and label columns are left out of G: their exact contribution (p - rb) W_blank + (p - rl) W_label
             // is added after the lattice by the reduction kernels.  EW = G * 2^(mref - lse2) / w_scale = sum_v p_v W_v.
             const int grow = x_row0 + row;
             const int label = valid_x ? p.row_label[grow] : -1;
-            float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;     // mref: finite start, fixed by the first sub-pass
-            float* xg = kbuf;                                                   // [2 parities][2 halves][128] row maxima
+            float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;     // mref: finite start, fixed by the first tile
+            float* xg = kbuf;                                      // [2 column halves][128] row maxima (rare path)
             const int ngrp = p.HH / 32;
             for (int i = 0; i < n_iter; ++i) {
                 const int t0 = (j0 + i) * NT;
+                const float* bias_t = p.bias2 + t0 + ch * 32;
+                float4 bpre[8];                               // bias of sub-tile 0, fetched while waiting for the S tile
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
                 mbar_wait(bar_sfull, i & 1);
                 if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t acc[4][32];
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    tmem_ld32(tmem_base + lane_addr + g * 64 + ch * 32, acc[g]);   // sub-pass g: columns g*64 + ch*32 ..
+                for (int g = 0; g < 4; ++g) tmem_ld32(tmem_base + lane_addr + g * 64 + ch * 32, acc[g]);
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
+                if (et == 0) trace_at(p, 2, i, 1);
+                float lmax = -INFINITY;
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                if (i == 0) {
+                    // First tile: exact two-step (row maximum first, then the exponentials against the new reference).
 #pragma unroll
-                for (int sp = 0; sp < 4; ++sp) {
-                    // ---- optimistic single pass over this sub-pass's 32 columns: yq = y - mref + lg_scale with the
-                    // CURRENT reference; the partner warps (column halves of the same 32 rows) exchange their maxima
-                    // and only when a row exceeds the fp16 headroom (y > mref + 3) -- always on the very first
-                    // sub-pass -- the reference moves and the rows' accumulators are rescaled in TMEM.
-                    const int pb = sp & 1;
-                    const int n = 4 * i + sp;                         // global sub-pass counter
-                    const int c0 = t0 + sp * 64;                      // first stream column of this sub-pass
-                    const int vb = c0 + ch * 32;
-                    const float krow = lg_scale - mref;
-                    float yq[32];
-                    float lmax = -INFINITY;
-                    {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + vb);
+                    for (int g = 0; g < 4; ++g) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float4 bv = __ldg(b4 + e);
-                            yq[4 * e + 0] = fmaf(__uint_as_float(acc[sp][4 * e + 0]), c1, bv.x + krow);
-                            yq[4 * e + 1] = fmaf(__uint_as_float(acc[sp][4 * e + 1]), c1, bv.y + krow);
-                            yq[4 * e + 2] = fmaf(__uint_as_float(acc[sp][4 * e + 2]), c1, bv.z + krow);
-                            yq[4 * e + 3] = fmaf(__uint_as_float(acc[sp][4 * e + 3]), c1, bv.w + krow);
-                            lmax = fmaxf(lmax, fmaxf(fmaxf(yq[4 * e + 0], yq[4 * e + 1]), fmaxf(yq[4 * e + 2], yq[4 * e + 3])));
+                            const float4 bv = (g == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + g * 64) + e);
+                            const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x + lg_scale);
+                            const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y + lg_scale);
+                            const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z + lg_scale);
+                            const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w + lg_scale);
+                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                            acc[g][4 * e + 0] = __float_as_uint(y0); acc[g][4 * e + 1] = __float_as_uint(y1);
+                            acc[g][4 * e + 2] = __float_as_uint(y2); acc[g][4 * e + 3] = __float_as_uint(y3);
                         }
                     }
-                    xg[(n & 1) * 2 * kTile + ch * kTile + row] = lmax;
-                    asm volatile("bar.sync %0, 64;" ::"r"(kEpiBarrier + 1 + q) : "memory");
-                    const float rmax = fmaxf(lmax, xg[(n & 1) * 2 * kTile + (ch ^ 1) * kTile + row]);
-                    const bool need = (n == 0) || (rmax > lg_scale + 3.f);      // (rmax = -inf on all-padding columns)
-                    if (__any_sync(0xffffffffu, need)) {                       // same outcome in both partner warps
-                        // new reference = row maximum + 2 (log2 units): yq shifts by -delta, sums and accumulators by 2^-delta
-                        const float delta = (need && rmax > -INFINITY) ? (rmax - lg_scale + 2.f) : 0.f;
+                    xg[ch * kTile + row] = lmax;
+                    quarter_sync(q);
+                    const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                    // reference = row maximum of the first tile + 2 (log2 units); -inf only on all-padding columns
+                    mref = (rmax > -INFINITY) ? (rmax - lg_scale + 2.f) : 0.f;
+                    quarter_sync(q);                              // xg may be rewritten
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float e0 = ex2f(__uint_as_float(acc[g][e]) - mref), e1 = ex2f(__uint_as_float(acc[g][e + 1]) - mref);
+                            const float e2 = ex2f(__uint_as_float(acc[g][e + 2]) - mref), e3 = ex2f(__uint_as_float(acc[g][e + 3]) - mref);
+                            p0 += e0; p1 += e1; p2 += e2; p3 += e3;
+                            acc[g][e] = __float_as_uint(e0); acc[g][e + 1] = __float_as_uint(e1);
+                            acc[g][e + 2] = __float_as_uint(e2); acc[g][e + 3] = __float_as_uint(e3);
+                        }
+                    }
+                    ssum = (p0 + p1) + (p2 + p3);
+                } else {
+                    // Later tiles, optimistic single pass: exponentials against the CURRENT reference, fused with the
+                    // logits so that FMA-pipe and MUFU work interleave; the partner warps then vote on the row maxima
+                    // and only if a value came near the 16-bit range limit (rare: the reference is the first tile's
+                    // maximum) the reference moves and everything computed so far is rescaled by a power of two.
+                    const float krow = lg_scale - mref;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = (g == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + g * 64) + e);
+                            const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x + krow);
+                            const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y + krow);
+                            const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z + krow);
+                            const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w + krow);
+                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                            const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
+                            p0 += e0; p1 += e1; p2 += e2; p3 += e3;
+                            acc[g][4 * e + 0] = __float_as_uint(e0); acc[g][4 * e + 1] = __float_as_uint(e1);
+                            acc[g][4 * e + 2] = __float_as_uint(e2); acc[g][4 * e + 3] = __float_as_uint(e3);
+                        }
+                    }
+                    float part = (p0 + p1) + (p2 + p3);
+                    if (quarter_any(q, lmax > lg_scale + 3.f)) {
+                        xg[ch * kTile + row] = lmax;
+                        quarter_sync(q);
+                        const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                        // new reference = row maximum + 2 (log2 units): values, sums and accumulators scale by 2^-delta
+                        const float delta = (rmax > lg_scale + 3.f) ? (rmax - lg_scale + 2.f) : 0.f;
                         const float fsc = ex2f(-delta);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) yq[e] -= delta;
                         ssum *= fsc;
+                        part *= fsc;
                         mref += delta;
-                        if (n > 0) {
-                            // all G sub-passes issued so far must have completed before the accumulators are scaled
-                            mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);
-                            mbar_wait(bar_pempty(pb ^ 1), (((sp + 1) >> 1) & 1) ^ 1);
-                            tc_fence_after();
-                            uint32_t gacc[32];
-                            for (int cc = ch; cc < ngrp; cc += 2) {
-                                tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
-                                tmem_ld_wait();
 #pragma unroll
-                                for (int e = 0; e < 32; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
-                                tmem_st32(tmem_G + lane_addr + cc * 32, gacc);
-                            }
-                            tmem_st_wait();
-                            tc_fence_before();
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) acc[g][e] = __float_as_uint(__uint_as_float(acc[g][e]) * fsc);
+                        // every G sub-pass issued so far (up to the previous tile's last one, which used the buffer
+                        // before pr.buf) must have completed before the accumulators are scaled
+                        mbar_wait(bar_pempty(pr.buf == 0 ? kPB - 1 : pr.buf - 1), pr.buf == 0 ? pr.phase ^ 1 : pr.phase);
+                        tc_fence_after();
+                        uint32_t gacc[16];
+                        for (int cc = ch; cc < 2 * ngrp; cc += 2) {
+                            tmem_ld16(tmem_G + lane_addr + cc * 16, gacc);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
+                            tmem_st16(tmem_G + lane_addr + cc * 16, gacc);
                         }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        quarter_sync(q);                          // xg may be rewritten
                     }
-                    if (p.blank >= vb && p.blank < vb + 32) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) zb = (vb + e == p.blank) ? yq[e] + mref - lg_scale : zb;
-                    }
-                    if (label >= vb && label < vb + 32) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) zl = (vb + e == label) ? yq[e] + mref - lg_scale : zl;
-                    }
-                    uint32_t packed[16];
-                    {
-                        float part = 0.f;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            yq[e] = ex2f(yq[e]);
-                            part += yq[e];
-                        }
-                        ssum += part;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[e] = pack16<BF16>(yq[2 * e], yq[2 * e + 1]);
-                    }
-                    mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);   // use 2i + (sp >> 1) of this half
-                    if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
-                    uint8_t* dstP = sP_gen + pb * kChunkBytes;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                        *reinterpret_cast<uint4*>(dstP + row * 128 + (((ch * 4 + cc) ^ (row & 7)) << 4)) = v4;
-                    }
-                    const int cbl = p.blank - c0, clb = label - c0;
-                    if (cbl >= ch * 32 && cbl < ch * 32 + 32) *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, cbl)) = 0;
-                    if (clb >= ch * 32 && clb < ch * 32 + 32) *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, clb)) = 0;
-                    fence_proxy_async_smem();
-                    epi_arrive(bar_pfull(pb));
-                    if (et == 0 && sp == 3) trace_at(p, 2, i, 3);
+                    ssum += part;
                 }
+                {
+                    // blank / label logits (log2 units) of this row, recovered from the exponentials: once per row
+                    const int cbl = p.blank - t0, clb = label - t0;   // column inside this tile, if any
+                    if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v = (g * 64 + ch * 32 + e == cbl) ? __uint_as_float(acc[g][e]) : v;
+                        zb = lg2f(v) + mref - lg_scale;
+                    }
+                    if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v = (g * 64 + ch * 32 + e == clb) ? __uint_as_float(acc[g][e]) : v;
+                        zl = lg2f(v) + mref - lg_scale;
+                    }
+                }
+                uint32_t packed[4][16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        packed[g][e] = pack16<BF16>(__uint_as_float(acc[g][2 * e]), __uint_as_float(acc[g][2 * e + 1]));
+                store_rounds(packed, [&](const int g0, const int g1, uint8_t* const* dst) {
+                    const int cbl = p.blank - t0, clb = label - t0;
+#pragma unroll
+                    for (int g = g0; g < g1; ++g) {
+                        const int lo = g * 64 + ch * 32;
+                        if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dst[g] + ptile_off(row, cbl - g * 64)) = 0;
+                        if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dst[g] + ptile_off(row, clb - g * 64)) = 0;
+                    }
+                }, i);
             }
             mbar_wait(bar_gfull, 0);
             tc_fence_after();
-            // combine the two column halves of each row: ch 1 hands (sum, z_blank, z_label) to ch 0, ch 0 returns lse2
-            float4* xch = reinterpret_cast<float4*>(kbuf);
-            epi_sync();
-            if (ch == 1) xch[row] = make_float4(ssum, zb, zl, 0.f);
-            epi_sync();
-            float lse2 = 0.f;
-            if (ch == 0) {
-                const float4 o = xch[row];
-                lse2 = mref - lg_scale + lg2f(ssum + o.x);
-                zb = ((p.blank & 63) < 32) ? zb : o.y;            // which column half (ch) owns the blank / label column
+            // combine the two column halves of each row through the (now idle) P' buffers
+            float4* xch = reinterpret_cast<float4*>(sP_gen);
+            pair_epi_sync();
+            xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
+            pair_epi_sync();
+            const float4 o = xch[(ch ^ 1) * kTile + row];
+            const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
+            if (ch == 0 && valid_x && half == 0) {
+                zb = ((p.blank & 63) < 32) ? zb : o.y;            // which column half owns the blank / label column
                 if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
-                if (valid_x && half == 0) {
-                    p.lse[grow] = lse2 * kLn2;
-                    p.lpb[grow] = (zb - lse2) * kLn2;
-                    p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
-                }
+                p.lse[grow] = lse2 * kLn2;
+                p.lpb[grow] = (zb - lse2) * kLn2;
+                p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
             }
-            epi_sync();
-            if (ch == 0) xch[row].x = lse2;
-            epi_sync();
-            if (ch == 1) lse2 = xch[row].x;
             const float f = ex2f(mref - lg_scale - lse2) * inv_ws;
             float* dst = p.dA + (size_t)grow * p.H + half * p.HH;
-            uint32_t acc[32];
+            uint32_t gacc[32];
             for (int cc = ch; cc < ngrp; cc += 2) {
-                tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
                 tmem_ld_wait();
                 if (valid_x) {
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
-                        float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
-                                               __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
-                        *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
+                        float4 o4 = make_float4(__uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                                __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
+                        *reinterpret_cast<float4*>(dst + cc * 32 + e) = o4;
                     }
                 }
             }
@@ -903,7 +1039,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             int label = -1;
             float krow = 0.f, db_acc = 0.f;
             int vrow = 0;
-            uint32_t acc[32];
             if (MODE == MODE_DA) {
                 if (valid_x) {
                     rm = p.rowmeta[x_row0 + row];
@@ -926,12 +1061,12 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                     kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
                     kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
-                    epi_sync();
+                    pair_epi_sync();
                 }
                 mbar_wait(bar_sfull, i & 1);
                 if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
-                // Pull this thread's share of the S tile (4 sub-passes x 32 columns) into registers and hand the single S
+                // Pull this thread's share of the S tile (4 sub-tiles x 32 columns) into registers and hand the single S
                 // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
                 uint32_t acc[4][32];
 #pragma unroll
@@ -940,97 +1075,80 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 tc_fence_before();
                 epi_arrive(bar_sempty);
                 if (et == 0) trace_at(p, 2, i, 1);
+                uint32_t packed[4][16];
+                {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-                for (int sp = 0; sp < 4; ++sp) {
-                    const int pb = sp & 1;
-                    const int c0 = t0 + sp * 64;            // first stream index of this sub-pass
-                    const int cb = sp * 64 + ch * 32;       // this thread's first column inside the 256-column tile
-                    uint32_t packed[16];
-                    if (p.dbg & 4) {
+                    for (int g = 0; g < 4; ++g) {
+                        const int cb = g * 64 + ch * 32;    // this thread's first column of sub-tile g inside the tile
+                        const float4* k4 = (MODE == MODE_DA) ? reinterpret_cast<const float4*>(p.bias2 + t0 + cb)
+                                                             : reinterpret_cast<const float4*>(kbuf + cb);
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[e] = 0;
-                    } else {
-                        float kc[32];
-                        if (MODE == MODE_DA) {
-                            const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + t0 + cb);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 bv = __ldg(b4 + e);
-                                kc[4 * e + 0] = bv.x; kc[4 * e + 1] = bv.y; kc[4 * e + 2] = bv.z; kc[4 * e + 3] = bv.w;
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 kv = (MODE == MODE_DA) ? __ldg(k4 + e) : k4[e];
+                            float v0 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, kv.x + krow));
+                            float v1 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, kv.y + krow));
+                            float v2 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, kv.z + krow));
+                            float v3 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, kv.w + krow));
+                            if (p.dbg & 4) v0 = v1 = v2 = v3 = 0.f;
+                            if (MODE == MODE_DW) {
+                                if (any_neg) {
+                                    const float4 sg = *reinterpret_cast<const float4*>(kbuf + NT + cb + 4 * e);
+                                    v0 *= sg.x; v1 *= sg.y; v2 *= sg.z; v3 *= sg.w;
+                                }
+                                d0 += v0; d1 += v1; d2 += v2; d3 += v3;
                             }
-                        } else {
-                            const float4* k4 = reinterpret_cast<const float4*>(kbuf + cb);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 kv = k4[e];
-                                kc[4 * e + 0] = kv.x; kc[4 * e + 1] = kv.y; kc[4 * e + 2] = kv.z; kc[4 * e + 3] = kv.w;
-                            }
+                            packed[g][2 * e] = pack16<BF16>(v0, v1);
+                            packed[g][2 * e + 1] = pack16<BF16>(v2, v3);
                         }
-                        float val[32];
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            val[e] = ex2f(fmaf(__uint_as_float(acc[sp][e]), c1, kc[e] + krow));
-                        if (MODE == MODE_DW) {
-                            if (any_neg) {
-                                const float* sg = kbuf + NT + cb;
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) val[e] *= sg[e];
-                            }
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) db_acc += val[e];
-                        }
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[e] = pack16<BF16>(val[2 * e], val[2 * e + 1]);
                     }
-                    // This is use number 2i + (sp >> 1) of P' half pb: it may be overwritten once the G sub-pass of the
-                    // previous use has completed.  Every thread visits every use in order, so the parity wait never has
-                    // to look more than one phase ahead.
-                    mbar_wait(bar_pempty(pb), ((sp >> 1) & 1) ^ 1);
-                    if (et == 0 && sp == 0) trace_at(p, 2, i, 2);
-                    uint8_t* dstP = sP_gen + pb * kChunkBytes;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {        // this thread's 32 columns = 4 chunks of 16 B
-                        uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-                        *reinterpret_cast<uint4*>(dstP + row * 128 + (((ch * 4 + cc) ^ (row & 7)) << 4)) = v4;
-                    }
+                    if (MODE == MODE_DW) db_acc += (d0 + d1) + (d2 + d3);
+                }
+                // sparse corrections: the blank and label entries are p - rb / p - rl, with p = exp(lp) from the
+                // forward pass (rowmeta .y / .z), written exactly instead of being carried through the dense loop
+                store_rounds(packed, [&](const int g0, const int g1, uint8_t* const* dst) {
                     if (MODE == MODE_DA) {
-                        const int cbl = p.blank - c0, clb = label - c0;
-                        if (cbl >= ch * 32 && cbl < ch * 32 + 32)
-                            *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, cbl)) = to16<BF16>(rm.y * pscale);
-                        if (clb >= ch * 32 && clb < ch * 32 + 32)
-                            *reinterpret_cast<uint16_t*>(dstP + ptile_off(row, clb)) = to16<BF16>(rm.z * pscale);
+                        const int cbl = p.blank - t0, clb = label - t0;
+#pragma unroll
+                        for (int g = g0; g < g1; ++g) {
+                            const int lo = g * 64 + ch * 32;
+                            if (cbl >= lo && cbl < lo + 32)
+                                *reinterpret_cast<uint16_t*>(dst[g] + ptile_off(row, cbl - g * 64)) = to16<BF16>(rm.y * pscale);
+                            if (clb >= lo && clb < lo + 32)
+                                *reinterpret_cast<uint16_t*>(dst[g] + ptile_off(row, clb - g * 64)) = to16<BF16>(rm.z * pscale);
+                        }
                     } else {
-                        epi_sync();                         // column owners patch rows written by other threads
-                        if ((et >> 6) == sp) {
+                        pair_epi_sync();                    // column owners patch rows written by other threads
+                        const int g = et >> 6;
+                        if (g >= g0 && g < g1) {
+                            uint8_t* d = (g == 0) ? dst[0] : (g == 1) ? dst[1] : (g == 2) ? dst[2] : dst[3];
                             const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
                             if (rbl >= 0 && rbl < kTile)
-                                *reinterpret_cast<uint16_t*>(dstP + ptile_off(rbl, et & 63)) = to16<BF16>(cm.y * cm.w * pscale);
+                                *reinterpret_cast<uint16_t*>(d + ptile_off(rbl, et & 63)) = to16<BF16>(cm.y * cm.w * pscale);
                             if (rlb >= 0 && rlb < kTile)
-                                *reinterpret_cast<uint16_t*>(dstP + ptile_off(rlb, et & 63)) = to16<BF16>(cm.z * cm.w * pscale);
+                                *reinterpret_cast<uint16_t*>(d + ptile_off(rlb, et & 63)) = to16<BF16>(cm.z * cm.w * pscale);
                         }
                     }
-                    fence_proxy_async_smem();
-                    epi_arrive(bar_pfull(pb));
-                    if (et == 0 && sp == 3) trace_at(p, 2, i, 3);
-                }
+                }, i);
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global
             mbar_wait(bar_gfull, 0);
             tc_fence_after();
             const float gmax = p.scal[2];
             const int ngrp = p.HH / 32;
+            uint32_t gacc[32];
             // G columns [0, hh2) came from the leader's B rows, [hh2, HH) from the peer's: column c <-> joint column c
             if (MODE == MODE_DA) {
                 const float f = rm.w * gmax * inv_ws / pscale;
                 float* dst = p.dA + (size_t)(x_row0 + row) * p.H + half * p.HH;
                 for (int cc = ch; cc < ngrp; cc += 2) {
-                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
                     tmem_ld_wait();
                     if (valid_x) {
-    #pragma unroll
+#pragma unroll
                         for (int e = 0; e < 32; e += 4) {
-                            float4 o = make_float4(__uint_as_float(acc[e]) * f, __uint_as_float(acc[e + 1]) * f,
-                                                   __uint_as_float(acc[e + 2]) * f, __uint_as_float(acc[e + 3]) * f);
+                            float4 o = make_float4(__uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                                   __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
                             *reinterpret_cast<float4*>(dst + cc * 32 + e) = o;
                         }
                     }
@@ -1040,13 +1158,14 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 const bool ok = vrow < p.V;
                 float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
                 for (int cc = ch; cc < ngrp; cc += 2) {
-                    tmem_ld32(tmem_G + lane_addr + cc * 32, acc);
+                    tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
                     tmem_ld_wait();
                     if (ok) {
-    #pragma unroll
-                        for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(acc[e]) * f);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(gacc[e]) * f);
                     }
                 }
+                // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
                 if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
         }
@@ -1054,7 +1173,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) {
+    if (warp == kPairMmaWarp) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, kTmemCols);
     }
@@ -1219,12 +1338,11 @@ static void trace_dump(const char* what, cudaStream_t stream) {
     cudaMemset(buf, 0, sizeof(h));
     long long t0 = h[(1 * kTraceIters + 0) * 4 + 0];
     fprintf(stderr, "TRACE %s (cycles since first MMA-loop entry)\n", what);
-    fprintf(stderr, " it | prod (unused in pair kernels) | mma: loop Sa_issued G0_issued Sb+G1_issued | epi: sfull S_released/ref_done pempty0 pfull1_arrived\n");
+    fprintf(stderr, " it | epi sub-pass 1: entry voted packed pempty_ok | mma: loop S_issued (epi sp1 arrived) G_issued | epi: sfull S_released pempty(sp0) pfull(sp3)\n");
     for (int i = 0; i < 12; ++i) {
         fprintf(stderr, "%3d |", i);
         for (int r = 0; r < 3; ++r) {
             for (int e = 0; e < 4; ++e) {
-                if (r == 0 && e == 3) continue;
                 long long v = h[(r * kTraceIters + i) * 4 + e];
                 fprintf(stderr, " %7lld", v ? v - t0 : -1);
             }
@@ -1274,7 +1392,7 @@ static int launch_v3(const CUtensorMap& mx, const CUtensorMap& my, const CUtenso
     cudaLaunchConfig_t cfg{};
     grid.x = (grid.x + 1) & ~1u;
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kPairThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1312,7 +1430,7 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     p.HH = H / p.n_halves;
     p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
     p.trace = trace_buffer();
-    const size_t fixed = (size_t)(p.NKC + 2) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+    const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     int ns = 8;
     while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
     p.NS = ns;
@@ -1329,8 +1447,9 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     p.dA = ew;
     CUtensorMap mx, my, myt;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
-    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-    if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
+    const int hs = (p.dbg & 8) ? 2 : 1;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile / hs)) return rc;
+    if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2 / hs)) return rc;
     dim3 grid(n_tiles_ub, p.n_halves, 1);
     int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
                   : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
@@ -1351,7 +1470,7 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         p.HH = H / p.n_halves;
         p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
         p.trace = trace_buffer();
-        const size_t fixed = (size_t)(p.NKC + 2) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+        const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
         int ns = 8;
         if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kMaxStages, atoi(e)));
         while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
@@ -1382,8 +1501,9 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         if (dW) {
             CUtensorMap mx, my, myt;
             if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-            if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile)) return rc;
-            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2)) return rc;
+            const int hs = (p.dbg & 8) ? 2 : 1;
+            if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile / hs)) return rc;
+            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2 / hs)) return rc;
             p.splits = splits;
             dim3 grid(n_vtiles, p.n_halves, splits);
             int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream)
