@@ -165,7 +165,128 @@ static void run(const char* name, int M, int N, int mode, int n_mma, int ld_warp
     }
 }
 
+
+// ---- DSMEM throughput: CTA 0 of a pair sends `reps` x 64 KiB to CTA 1's shared memory.
+// mode 0: st.shared::cluster.v4 from 256 threads, fence.acq_rel.cluster once per 64 KiB
+// mode 1: st.async.v4 with complete_tx on a barrier in the destination CTA
+// mode 2: cp.async.bulk.shared::cluster from local shared memory, 16 KiB per copy, complete_tx at the destination
+__global__ void __launch_bounds__(256, 1) dsmem_bench(int mode, int reps, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t sBuf = base;                 // 64 KiB
+    const uint32_t sBar = base + 65536;         // barrier (in the destination: counts bytes)
+    const uint32_t sBack = sBar + 8;            // barrier (in the source: destination says "received")
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        mbar_init(sBar, 1);
+        mbar_init(sBack, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = i;
+    fence_proxy_async_smem();
+    __syncthreads();
+    cluster_sync_all();
+    uint32_t rBuf, rBar, rBack;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rBuf) : "r"(sBuf), "r"(1));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rBar) : "r"(sBar), "r"(1));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rBack) : "r"(sBack), "r"(0));
+    long long t0 = clock64();
+    if (rank == 0) {
+        for (int r = 0; r < reps; ++r) {
+            if (mode == 0) {
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t off = (k * 256 + threadIdx.x) * 16;
+                    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rBuf + off), "r"(r), "r"(k), "r"(off), "r"(1) : "memory");
+                }
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rBar) : "memory");
+            } else if (mode == 1) {
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t off = (k * 256 + threadIdx.x) * 16;
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                 ::"r"(rBuf + off), "r"(r), "r"(k), "r"(off), "r"(1), "r"(rBar) : "memory");
+                }
+            } else {
+                if (threadIdx.x == 0) {
+                    for (int k = 0; k < 4; ++k)
+                        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(rBuf + k * 16384), "r"(sBuf + k * 16384), "r"(16384), "r"(rBar) : "memory");
+                }
+            }
+            // wait until the destination has everything (so at most one 64 KiB block is in flight, as in the kernel)
+            mbar_wait(sBack, r & 1);
+        }
+    } else {
+        for (int r = 0; r < reps; ++r) {
+            if (threadIdx.x == 0) {
+                if (mode != 0) mbar_arrive_expect_tx(sBar, 65536);
+                mbar_wait(sBar, r & 1);
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rBack) : "memory");
+            }
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && rank == 0) out[blockIdx.x / 2] = t1 - t0;
+    __syncthreads();
+    cluster_sync_all();
+}
+
+static void run_dsmem(int mode, long long* d_out) {
+    cudaFuncSetAttribute(dsmem_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 65536 + 64;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int reps = 64;
+    cudaMemset(d_out, 0, 148 * sizeof(long long));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, dsmem_bench, mode, reps, d_out);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        printf("dsmem mode %d FAILED: %s / %s\n", mode, cudaGetErrorString(e), cudaGetErrorString(e2));
+        return;
+    }
+    std::vector<long long> h(74);
+    cudaMemcpy(h.data(), d_out, 74 * sizeof(long long), cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    printf("dsmem mode %d: %.0f cycles per 64 KiB (median over pairs) -> %.1f B/cycle  [min %.0f max %.0f]\n", mode,
+           (double)h[37] / reps, 65536.0 * reps / h[37], (double)h[0] / reps, (double)h[73] / reps);
+}
+
+__global__ void __cluster_dims__(1, 1, 1) dummy_kernel(int* x) { if (x) *x = 1; }
+template <int CS>
+static void occupancy() {
+    auto kern = bench<2>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CS * 64);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = 226 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    printf("cluster size %d: max active clusters %d (%d SMs) [%s]\n", CS, n, n * CS, cudaGetErrorString(e));
+}
+
 int main() {
+    { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_dsmem(0, d); run_dsmem(1, d); run_dsmem(2, d); cudaFree(d); }
+    occupancy<2>();
+    occupancy<4>();
+    occupancy<8>();
     long long* d_out;
     cudaMalloc(&d_out, 148 * sizeof(long long));
     const int n = 4096;
