@@ -260,6 +260,114 @@ static void run_dsmem(int mode, long long* d_out) {
            (double)h[37] / reps, 65536.0 * reps / h[37], (double)h[0] / reps, (double)h[73] / reps);
 }
 
+
+// ---- issue-pattern test (cg2, M = 256, N = 256): groups of 4 MMAs with a commit after each group.
+// pat 0: commits only.  pat 1: ring of `ns` stages -- the issuer waits full[s] before a group and commits empty[s]
+// after it; a producer thread waits empty[s] and re-arms full[s] at once (no data movement).
+__global__ void __launch_bounds__(128, 1) ring_bench(int pat, int ns, int groups, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t sA = base, sB = base + 4 * 16384;
+    const uint32_t sBar = sB + 4 * 32768;
+    const uint32_t sTp = sBar + 256;
+    volatile uint32_t* tp = reinterpret_cast<volatile uint32_t*>(smem_raw + (sTp - base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    auto full = [&](int i) { return sBar + 8 * i; };
+    auto empty = [&](int i) { return sBar + 8 * (8 + i); };
+    const uint32_t done = sBar + 8 * 16;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+        mbar_init(done, 1);
+        *reinterpret_cast<volatile int*>(smem_raw + (sBar + 8 * 20 - base)) = 0;
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    if (warp == 1) tmem_alloc_pair(sTp, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tp;
+    if (warp == 2 && lane == 0 && rank == 0 && pat == 3) {
+        // helper: waits the full barriers in order and publishes how many groups are ready
+        int st = 0; uint32_t ph = 0;
+        for (int g = 0; g < groups; ++g) {
+            mbar_wait(full(st), ph);
+            *reinterpret_cast<volatile int*>(smem_raw + (sBar + 8 * 20 - base)) = g + 1;
+            if (++st == ns) { st = 0; ph ^= 1; }
+        }
+    }
+    if (warp == 0 && lane == 0 && rank == 0 && pat != 0) {
+        // producer: re-arm full[s] as soon as the stage was released
+        int st = 0; uint32_t ph = 0;
+        for (int g = 0; g < groups; ++g) {
+            mbar_wait(empty(st), ph ^ 1);
+            mbar_arrive(full(st));
+            if (++st == ns) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        const uint32_t idesc = make_idesc(0, 0, 0, 256, 256);
+        int st = 0; uint32_t ph = 0;
+        int ready = 0;
+        long long t0 = clock64();
+        for (int g = 0; g < groups; ++g) {
+            if (pat == 1) { mbar_wait(full(st), ph); tc_fence_after(); }
+            if (pat == 2) { mbar_wait(full(st), ph); }
+            if (pat == 4) {
+                uint32_t ok = 0;
+                while (!ok) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(full(st)), "r"(ph) : "memory");
+                }
+                tc_fence_after();
+            }
+            if (pat == 3) {
+                // readiness counter published by a helper warp: touch shared memory only when the cached value is used up
+                while (ready <= g) ready = *reinterpret_cast<volatile int*>(smem_raw + (sBar + 8 * 20 - base));
+                tc_fence_after();
+            }
+            const int c = g & 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16_ss_pair(tmem, desc_kmajor(sA + c * 16384, k), desc_kmajor(sB + c * 32768, k), idesc, (g | k) != 0);
+            umma_commit_pair(empty(st));
+            if (++st == ns) { st = 0; ph ^= 1; }
+        }
+        umma_commit_pair(done);
+        mbar_wait(done, 0);
+        out[blockIdx.x / 2] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem, 512); }
+}
+
+static void run_ring(int pat, int ns, long long* d_out) {
+    cudaFuncSetAttribute(ring_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 4 * 16384 + 4 * 32768 + 512;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int groups = 1024;
+    cudaMemset(d_out, 0, 148 * sizeof(long long));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ring_bench, pat, ns, groups, d_out);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e != cudaSuccess || e2 != cudaSuccess) { printf("ring pat %d FAILED: %s / %s\n", pat, cudaGetErrorString(e), cudaGetErrorString(e2)); return; }
+    std::vector<long long> h(74);
+    cudaMemcpy(h.data(), d_out, 74 * sizeof(long long), cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    printf("ring pat %d ns %d: %.1f cycles per MMA (4 per group, commit per group)\n", pat, ns, (double)h[37] / groups / 4);
+}
+
 __global__ void __cluster_dims__(1, 1, 1) dummy_kernel(int* x) { if (x) *x = 1; }
 template <int CS>
 static void occupancy() {
@@ -284,6 +392,7 @@ static void occupancy() {
 
 int main() {
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_dsmem(0, d); run_dsmem(1, d); run_dsmem(2, d); cudaFree(d); }
+    { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_ring(0, 4, d); run_ring(1, 4, d); run_ring(2, 4, d); run_ring(3, 4, d); run_ring(4, 4, d); cudaFree(d); }
     occupancy<2>();
     occupancy<4>();
     occupancy<8>();

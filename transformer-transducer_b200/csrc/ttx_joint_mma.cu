@@ -48,7 +48,7 @@ struct MmaParams {
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;         // + TMA producer warp + MMA issuer warp
-constexpr int kNumBars = 44;
+constexpr int kNumBars = 52;
 constexpr int kPB = 2;                             // pair kernel: P' sub-tile buffers (16 KiB each)
 constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
 constexpr int kMaxStages = 16;
@@ -122,6 +122,11 @@ template <bool BF16>
 __device__ __forceinline__ uint16_t to16(float x) {
     if (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
     return __half_as_ushort(__float2half_rn(x));
+}
+
+// one 16-byte reduction into global memory (no return value)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 constexpr int kTraceIters = 40;
@@ -649,7 +654,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
-    const uint32_t bar_xfull = sBar;
+    auto bar_xfull = [&](int k) { return sBar + 8 * (kNumBars - 8 + k); };   // one per 64-column chunk of the X tile
     auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
     auto bar_empty = [&](int s) { return sBar + 8 * (17 + s); };
     const uint32_t bar_sfull = sBar + 8 * 33;
@@ -666,7 +671,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapYT);
-        mbar_init(bar_xfull, 1);
+        for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
@@ -699,8 +704,11 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if (warp == kPairProducerWarp) {
         // =========================================================== TMA producer
         if (lane == 0) {
-            if (leader) mbar_arrive_expect_tx(bar_xfull, 2 * p.NKC * kChunkBytes);
-            for (int c = 0; c < p.NKC; ++c) tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull, c * kKC, x_row0);
+            // the stationary tile arrives chunk by chunk (own barrier each), so the first S pass starts after 16 KiB
+            for (int c = 0; c < p.NKC; ++c) {
+                if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
+                tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
+            }
             Ring r;
             auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
                 mbar_wait(bar_empty(r.stage), r.phase ^ 1);
@@ -730,7 +738,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const uint32_t idescS = make_idesc(fmt, 0, 0, 256, NT);
             const uint32_t idescG = make_idesc(fmt, 0, 0, 256, p.HH);
             Ring r;
-            mbar_wait(bar_xfull, 0);
             // Issue order S(i+1), G(i,0..3).  The epilogue needs ~2000 cycles to read an S tile out of TMEM before
             // the next S pass may overwrite it; the four G sub-passes of the previous tile (64 stream columns = one
             // 16 KiB half of the ping-pong P' buffer each) are issued right behind the S pass to cover that window.
@@ -738,6 +745,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 mbar_wait(bar_sempty, (idx & 1) ^ 1);          // the epilogue has read the previous S tile out of TMEM
                 tc_fence_after();
                 for (int c = 0; c < p.NKC; ++c) {
+                    if (idx == 0) mbar_wait(bar_xfull(c), 0);
                     mbar_wait(bar_full(r.stage), r.phase);
                     tc_fence_after();
                     const uint32_t a = sX + c * kChunkBytes;
@@ -1179,7 +1187,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     tmem_ld_wait();
                     if (ok) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) atomicAdd(dst + cc * 32 + e, __uint_as_float(gacc[e]) * f);
+                        for (int e = 0; e < 32; e += 4)
+                            red_add_v4(dst + cc * 32 + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                       __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
                     }
                 }
                 // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
@@ -1803,7 +1813,9 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 if (ok) {
                     if (MODE == MODE_DW) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) atomicAdd(dst + col + e, __uint_as_float(gacc[e]) * f);
+                        for (int e = 0; e < 32; e += 4)
+                            red_add_v4(dst + col + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                       __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; e += 4) {

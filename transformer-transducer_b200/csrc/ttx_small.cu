@@ -739,9 +739,9 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
     const int threads = min(256, max(32, H / 4));
     const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
     const bool ew = rowmeta != nullptr;
+    TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
     if (ew) reduce_enc_kernel<true><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
     else reduce_enc_kernel<false><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
-    TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
     const int t_chunk = 64;
     const dim3 grid(U1, B, (T + t_chunk - 1) / t_chunk);
     if (ew) reduce_pred_kernel<true><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, t_chunk, d_pproj);
