@@ -172,6 +172,20 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, from the low words of the two K-major 128B-swizzle descriptors (high word is constant: SBO = 1024 B, version 1,
+// SWIZZLE_128B); desc_lo(addr) + 1024 * chunk + 2 * k16 steps through chunks / k slices with one add each.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_ss_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                    uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+        : "memory");
+}
 // Arrive on the barrier at this offset in BOTH CTAs of the pair once the pair's previously issued MMAs completed.
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile(

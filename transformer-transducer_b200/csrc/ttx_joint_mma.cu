@@ -87,6 +87,7 @@ constexpr int kPairEpiRegs = 216;                  // ... to the epilogue warps 
 // producer / MMA issuer starved by spinning epilogue warps stalls the whole pipeline (measured: 1.5x slower with ids 0, 1).
 constexpr int kPairProducerWarp = kPairEpiWarps;
 constexpr int kPairMmaWarp = kPairEpiWarps + 1;
+constexpr int kPairWatchWarp = kPairEpiWarps + 2;
 constexpr int kQuarterBarrier = 2;                 // named barriers 2..5: the four epilogue warps of lane quarter q
 
 __device__ __forceinline__ void pair_epi_sync() {
@@ -651,6 +652,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t sBar = sRing + p.NS * STAGE;
     const uint32_t sTmemPtr = sBar + kNumBars * 8;
     const uint32_t sKbuf = sTmemPtr + 16;                           // DW: 256 exponent offsets + 256 signs
+    const uint32_t sWatch = sTmemPtr + 8;                           // barrier watcher's event counter
     uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
@@ -672,6 +674,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapYT);
         for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
+        *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
@@ -731,53 +734,96 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 load_G(j0 + i);
             }
         }
+      } else if (warp == kPairWatchWarp) {
+        // =========================================================== barrier watcher (leader CTA)
+        // A tcgen05.mma is accepted only when the previous one has left the issue stage, so whatever the issuing
+        // thread does between two MMAs must fit into the ~128 cycles one of them takes; an mbarrier try_wait alone
+        // costs ~90 (measured: 128 -> 142..172 cycles per MMA with one wait per four).  This thread does the waiting
+        // instead: it walks the issuer's barriers in the issuer's order and publishes how many have completed; the
+        // issuer compares a register copy of that counter and touches shared memory only when it has run out.
+        if (lane == 0 && leader) {
+            volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+            int done = 0;
+            Ring r;
+            PRing pr;
+            auto publish = [&]() { *ready = ++done; };
+            auto watch_S = [&](int idx) {
+                mbar_wait(bar_sempty, (idx & 1) ^ 1);
+                publish();
+                for (int c = 0; c < p.NKC; ++c) {
+                    if (idx == 0) mbar_wait(bar_xfull(c), 0);
+                    mbar_wait(bar_full(r.stage), r.phase);
+                    publish();
+                    r.advance(p.NS);
+                }
+            };
+            auto watch_G = [&]() {
+                for (int sp = 0; sp < 4; ++sp) {
+                    mbar_wait(bar_pfull(pr.buf), pr.phase);
+                    mbar_wait(bar_full(r.stage), r.phase);
+                    publish();
+                    r.advance(p.NS);
+                    pr.advance();
+                }
+            };
+            watch_S(0);
+            for (int i = 0; i < n_iter; ++i) {
+                if (i + 1 < n_iter) watch_S(i + 1);
+                watch_G();
+            }
+        }
       } else if (warp == kPairMmaWarp) {
         // =========================================================== MMA issuer (leader CTA)
         if (lane == 0 && leader) {
             constexpr int fmt = BF16 ? 1 : 0;
             const uint32_t idescS = make_idesc(fmt, 0, 0, 256, NT);
             const uint32_t idescG = make_idesc(fmt, 0, 0, 256, p.HH);
-            Ring r;
-            // Issue order S(i+1), G(i,0..3).  The epilogue needs ~2000 cycles to read an S tile out of TMEM before
-            // the next S pass may overwrite it; the four G sub-passes of the previous tile (64 stream columns = one
-            // 16 KiB half of the ping-pong P' buffer each) are issued right behind the S pass to cover that window.
+            // low descriptor words (start address >> 4 | LBO); a 16 KiB chunk / stage is +1024, a 16-element k slice +2
+            const uint32_t xlo = desc_lo(sX), plo = desc_lo(sP), rlo = desc_lo(sRing);
+            volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+            int need = 0, have = 0;
+            auto wait_event = [&]() {
+                ++need;
+                if (have < need) {
+                    uint32_t spins = 0;
+                    while ((have = *ready) < need) {
+                        if (++spins > (1u << 26)) {
+                            printf("ttx: MMA issuer timed out waiting for event %d (block %d,%d,%d)\n", need, blockIdx.x,
+                                   blockIdx.y, blockIdx.z);
+                            __trap();
+                        }
+                    }
+                }
+            };
+            int stage = 0;
+            // Issue order S(i+1), G(i,0..3): the epilogue's read-out of S(i) and its exponentials run behind the next S
+            // pass; the four G sub-passes of tile i (one 64-column P' sub-tile each) follow as their operands arrive.
             auto issue_S = [&](int idx) {
-                mbar_wait(bar_sempty, (idx & 1) ^ 1);          // the epilogue has read the previous S tile out of TMEM
+                wait_event();                                   // the epilogue has read the previous S tile out of TMEM
                 tc_fence_after();
                 for (int c = 0; c < p.NKC; ++c) {
-                    if (idx == 0) mbar_wait(bar_xfull(c), 0);
-                    mbar_wait(bar_full(r.stage), r.phase);
+                    wait_event();                               // ring stage (and, first tile, X chunk c) has landed
                     tc_fence_after();
-                    const uint32_t a = sX + c * kChunkBytes;
-                    const uint32_t b = sRing + r.stage * STAGE;
-                    if (!(p.dbg & 1)) {
+                    const uint32_t a = xlo + c * 1024, b = rlo + stage * 1024;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ss_pair(tmem_base, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
-                    }
-                    umma_commit_pair(bar_empty(r.stage));
-                    r.advance(p.NS);
+                    for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(tmem_base, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
+                    umma_commit_pair(bar_empty(stage));
+                    if (++stage == p.NS) stage = 0;
                 }
                 umma_commit_pair(bar_sfull);
             };
-            PRing pr;                                           // P' sub-tile ring: sub-pass n uses buffer n % kPB
+            int pb = 0;                                         // P' sub-tile ring: sub-pass n uses buffer n % kPB
             auto issue_G = [&](int idx) {
                 for (int sp = 0; sp < 4; ++sp) {
-                    const int pb = pr.buf;
-                    mbar_wait(bar_pfull(pb), pr.phase);
-                    mbar_wait(bar_full(r.stage), r.phase);
+                    wait_event();                               // P' sub-tile stored and ring stage landed
                     tc_fence_after();
-                    const uint32_t a = sP + pb * kChunkBytes;
-                    const uint32_t b = sRing + r.stage * STAGE;
-                    if (!(p.dbg & 2)) {
+                    const uint32_t a = plo + pb * 1024, b = rlo + stage * 1024;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ss_pair(tmem_G, desc_kmajor(a, k), desc_kmajor(b, k), idescG, (idx | sp | k) != 0);
-                    }
-                    umma_commit_pair(bar_empty(r.stage));
+                    for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(tmem_G, a + 2 * k, b + 2 * k, idescG, (idx | sp | k) != 0);
+                    umma_commit_pair(bar_empty(stage));
                     umma_commit_pair(bar_pempty(pb));
-                    r.advance(p.NS);
-                    pr.advance();
+                    if (++stage == p.NS) stage = 0;
+                    if (++pb == kPB) pb = 0;
                 }
             };
             issue_S(0);
