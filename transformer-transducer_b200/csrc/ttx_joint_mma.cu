@@ -1253,53 +1253,46 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
 }
 
 // ===========================================================================================================
-// Quad kernel: the pair kernel's work split over a cluster of FOUR CTAs = two CTA pairs with different roles, so that
-// the softmax operand is computed ONCE per (lattice row, vocabulary column) instead of once per 256-column slab of H:
+// Quad kernel (H = 512, modes DA and DW): the pair kernel's work split over a cluster of FOUR CTAs = two CTA pairs
+// with different roles, so that the softmax operand is computed ONCE per (stationary row, stream row) instead of once
+// per 256-column slab of H:
 //
 //   S pair (cluster ranks 0, 1)   X tile stationary in shared memory, streams Y, S = X . Y^T into a DOUBLE-buffered
-//                                  TMEM accumulator (the pair holds no G, so TMEM has room), epilogue = exponentials ->
-//                                  16-bit operand P', written straight into the G pair's shared memory (DSMEM).
+//                                  TMEM accumulator (the pair holds no G, so TMEM has room).  Sixteen epilogue warps in
+//                                  two groups -- group g owns accumulator g and the chunks of parity g -- turn S into
+//                                  the 16-bit operand P' sub-tile by sub-tile and push it with asynchronous DSMEM
+//                                  stores (st.async, completion counted in bytes on a barrier of the receiver)
+//                                  straight into the G pair's shared memory.
 //   G pair (cluster ranks 2, 3)   no X tile: its shared memory holds two 256-column P' chunks (64 KiB each per CTA)
-//                                  and a ring for the K-major transposed stream; G = P' . Y^T-chunks accumulates for
-//                                  ALL of H (2 x 256 TMEM columns), read out once at the end.
+//                                  and a ring for the K-major transposed stream; its epilogue warps write the exact
+//                                  blank / label entries into a landed chunk, then G = P' . Y^T-chunks accumulates
+//                                  for ALL of H (2 x 256 TMEM columns), read out once at the end.
 //
-// Per 256 x 256 block of (stationary rows x stream rows) the quad executes 2 H V MMA work once for S and once for G
-// (the pair kernel: S twice), streams each operand chunk once (2/3 of the pair kernel's L2 -> shared-memory bytes),
-// and evaluates each exponential once (half).  CTA c of the S pair and CTA c of the G pair own the same 128 rows.
-// Modes as in the pair kernel (FG, DA, DW).  Supported: H = 128, 256, 512.
-constexpr int kQuadThreads = 384;                  // 8 epilogue warps + control warpgroup (producer, MMA issuer, 2 idle)
+// CTA c of the S pair and CTA c of the G pair own the same 128 rows.  Per 256 x 256 block the quad executes the S
+// contraction and the exponentials once (the pair kernel: once per slab) and streams each operand chunk from L2 once.
+// Measured inputs to this design (tools/mma_bench.cu): tcgen05 issue floor, DSMEM 16-18 B/cycle whatever the
+// instruction, 33 clusters of four per B200.
+constexpr int kQuadEpiWarps = 16;
+constexpr int kQuadThreads = (kQuadEpiWarps + 4) * 32;
+constexpr int kQuadProducerWarp = kQuadEpiWarps;
+constexpr int kQuadMmaWarp = kQuadEpiWarps + 1;
+constexpr int kQuadWatchWarp = kQuadEpiWarps + 2;
+constexpr int kQuadCtrlRegs = 56;                  // 20 warps x 96 = 4 x 56 + 16 x 104 (setmaxnreg needs multiples of 8)
+constexpr int kQuadEpiRegs = 104;
 constexpr int kQuadRing0 = 8 * kChunkBytes;        // [0, 128 KiB): X tile (S pair) / two P' chunks (G pair); ring behind
 constexpr int kQuadMaxStages = 6;
 constexpr int kQuadBars = 40;
-constexpr int kQuadAux = 2560;                     // S pair: 512 floats of per-column constants; G pair: scales + flags
+constexpr int kQuadAux = 2560;                     // S pair: per group 256 exponent offsets + 8 words of sign bits
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void st_cluster_u16(uint32_t addr, uint16_t v) {
-    asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-// arrive on a barrier given by its shared::cluster address
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void fence_cluster() {
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() {
-    asm volatile("fence.proxy.async;" ::: "memory");
+// asynchronous 16-byte store into another CTA's shared memory; the receiver's barrier counts the bytes
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar) : "memory");
 }
 // commit of the calling pair's MMAs, arriving on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
@@ -1313,6 +1306,7 @@ template <int MODE, bool BF16>
 __global__ void __launch_bounds__(kQuadThreads, 1)
 joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                   const __grid_constant__ CUtensorMap mapYT, const MmaParams p) {
+    static_assert(MODE == MODE_DA || MODE == MODE_DW, "the quad kernel has no forward+gradient mode");
     constexpr int NT = 256;                 // stream rows per chunk = S accumulator columns
     constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
     constexpr int PCHUNK = 4 * kChunkBytes; // one 256-column P' chunk of this CTA's 128 rows
@@ -1339,9 +1333,6 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     if (j0 >= j1) return;
     const int x_row0 = (quad * 2 + (int)c) * kTile;
     const int n_iter = j1 - j0;
-    const int n_slabs = (p.H > 256) ? 2 : 1;
-    const int HH = p.H / n_slabs;           // G columns per slab (MMA N)
-    const int hh2 = HH / 2;                 // rows of the K-major B operand chunk held by this CTA
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
@@ -1353,496 +1344,330 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const uint32_t sRing = smem_base + kQuadRing0;
     const uint32_t sBar = sRing + p.NS * STAGE;
     const uint32_t sTmemPtr = sBar + kQuadBars * 8;
+    const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sAux = sTmemPtr + 16;
     uint8_t* smem_gen = smem_raw;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
-    float* aux = reinterpret_cast<float*>(smem_gen + (sAux - smem_base));
-    // G-pair aux layout (floats): [0,256) gscale[2][128], [256,384) final row scale, [384,392) flags[2][4] (uint32)
-    constexpr int kAuxScale = 0, kAuxFinal = 256, kAuxFlag = 384;
 
-    const uint32_t bar_xfull = sBar;
-    auto bar_full = [&](int s) { return sBar + 8 * (1 + s); };
-    auto bar_empty = [&](int s) { return sBar + 8 * (9 + s); };
-    auto bar_sfull = [&](int b) { return sBar + 8 * (17 + b); };
-    auto bar_sempty = [&](int b) { return sBar + 8 * (19 + b); };
-    auto bar_pfull = [&](int b) { return sBar + 8 * (21 + b); };     // G leader: both S CTAs' epilogue warps
-    auto bar_pfull_l = [&](int b) { return sBar + 8 * (23 + b); };   // each G CTA: its S sibling's epilogue warps
-    auto bar_pempty = [&](int b) { return sBar + 8 * (25 + b); };    // every CTA: G leader's commit
-    auto bar_gscaled = [&](int b) { return sBar + 8 * (27 + b); };   // G leader: rescale warps of both G CTAs
-    const uint32_t bar_gfull = sBar + 8 * 29;
-    const uint32_t bar_fin = sBar + 8 * 30;                           // each G CTA: its S sibling's final row scales
+    auto bar_xfull = [&](int k) { return sBar + 8 * k; };            // 0..7
+    auto bar_full = [&](int s) { return sBar + 8 * (8 + s); };       // 8..13
+    auto bar_empty = [&](int s) { return sBar + 8 * (14 + s); };     // 14..19
+    auto bar_sfull = [&](int b) { return sBar + 8 * (20 + b); };     // S pair
+    auto bar_sempty = [&](int b) { return sBar + 8 * (22 + b); };    // S leader: the 16 warps of group b (both CTAs)
+    auto bar_pland = [&](int b) { return sBar + 8 * (24 + b); };     // each G CTA: bytes of chunk buffer b have landed
+    auto bar_pready = [&](int b) { return sBar + 8 * (26 + b); };    // G leader: both G CTAs patched chunk buffer b
+    auto bar_pempty = [&](int b) { return sBar + 8 * (28 + b); };    // every CTA: the G pair has consumed chunk buffer b
+    const uint32_t bar_gfull = sBar + 8 * 30;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == kPairProducerWarp && lane == 0) {
+    if (warp == kQuadProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapYT);
-        mbar_init(bar_xfull, 1);
+        for (int k = 0; k < 8; ++k) mbar_init(bar_xfull(k), 1);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_sfull(b), 1);
-            mbar_init(bar_sempty(b), 2 * kPairEpiWarps);
-            mbar_init(bar_pfull(b), 2 * kPairEpiWarps);
-            mbar_init(bar_pfull_l(b), kPairEpiWarps);
+            mbar_init(bar_sempty(b), 16);
+            mbar_init(bar_pland(b), 1);
+            mbar_init(bar_pready(b), 16);
             mbar_init(bar_pempty(b), 1);
-            mbar_init(bar_gscaled(b), 8);
         }
         mbar_init(bar_gfull, 1);
-        mbar_init(bar_fin, kPairEpiWarps);
+        *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
         fence_barrier_init();
     }
-    if (threadIdx.x < 8) reinterpret_cast<volatile uint32_t*>(aux + kAuxFlag)[threadIdx.x] = 0;
-    if (warp == kPairMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
+    if (warp == kQuadMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
-    if (warp >= kPairEpiWarps) {
+    if (warp >= kQuadEpiWarps) {
         // =========================================================== control warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPairCtrlRegs));
-        if (warp == kPairProducerWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kQuadCtrlRegs));
+        if (warp == kQuadProducerWarp) {
             if (lane == 0) {
                 Ring r;
-                auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
+                auto load_stage = [&](const CUtensorMap* map, int col, int row) {
                     mbar_wait(bar_empty(r.stage), r.phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * bytes);
+                    if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STAGE);
                     tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
                     r.advance(p.NS);
                 };
                 if (!g_role) {
-                    if (leader) mbar_arrive_expect_tx(bar_xfull, 2 * p.NKC * kChunkBytes);
-                    for (int k = 0; k < p.NKC; ++k) tma_load_2d_pair(sX + k * kChunkBytes, &mapX, bar_xfull, k * kKC, x_row0);
-                    for (int j = j0; j < j1; ++j)
-                        for (int k = 0; k < p.NKC; ++k) load_stage(&mapY, k * kKC, j * NT + (int)c * kTile, STAGE);
+                    for (int k = 0; k < p.NKC; ++k) {
+                        if (leader) mbar_arrive_expect_tx(bar_xfull(k), 2 * kChunkBytes);
+                        tma_load_2d_pair(sX + k * kChunkBytes, &mapX, bar_xfull(k), k * kKC, x_row0);
+                    }
+                    for (int i = 0; i < n_iter; ++i)
+                        for (int k = 0; k < p.NKC; ++k) load_stage(&mapY, k * kKC, (j0 + i) * NT + (int)c * kTile);
                 } else {
-                    for (int j = j0; j < j1; ++j)
+                    for (int i = 0; i < n_iter; ++i)
                         for (int sp = 0; sp < 4; ++sp)
-                            for (int sl = 0; sl < n_slabs; ++sl)
-                                load_stage(&mapYT, j * NT + sp * kKC, sl * HH + (int)c * hh2, hh2 * 128);
+                            for (int sl = 0; sl < 2; ++sl)
+                                load_stage(&mapYT, (j0 + i) * NT + sp * kKC, sl * 256 + (int)c * kTile);
                 }
             }
-        } else if (warp == kPairMmaWarp) {
+        } else if (warp == kQuadWatchWarp) {
+            // barrier watcher of the pair's MMA issuer (see the pair kernel)
+            if (lane == 0 && leader) {
+                volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+                int done = 0;
+                Ring r;
+                for (int i = 0; i < n_iter; ++i) {
+                    const int buf = i & 1;
+                    const uint32_t ph = (i >> 1) & 1;
+                    if (!g_role) {
+                        mbar_wait(bar_sempty(buf), ph ^ 1);
+                        *ready = ++done;
+                        for (int k = 0; k < p.NKC; ++k) {
+                            if (i == 0) mbar_wait(bar_xfull(k), 0);
+                            mbar_wait(bar_full(r.stage), r.phase);
+                            *ready = ++done;
+                            r.advance(p.NS);
+                        }
+                    } else {
+                        mbar_wait(bar_pready(buf), ph);
+                        *ready = ++done;
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            mbar_wait(bar_full(r.stage), r.phase);
+                            *ready = ++done;
+                            r.advance(p.NS);
+                        }
+                    }
+                }
+            }
+        } else if (warp == kQuadMmaWarp) {
             if (lane == 0 && leader) {
                 constexpr int fmt = BF16 ? 1 : 0;
-                Ring r;
-                if (!g_role) {
-                    // ---- S pair: S(j) = X . Y_j^T into accumulator j & 1
-                    const uint32_t idescS = make_idesc(fmt, 0, 0, 256, NT);
-                    mbar_wait(bar_xfull, 0);
-                    for (int i = 0; i < n_iter; ++i) {
-                        const int buf = i & 1;
-                        mbar_wait(bar_sempty(buf), ((i >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                        trace_at(p, 1, i, 0);
-                        for (int k = 0; k < p.NKC; ++k) {
-                            mbar_wait(bar_full(r.stage), r.phase);
-                            tc_fence_after();
-                            const uint32_t a = sX + k * kChunkBytes;
-                            const uint32_t b = sRing + r.stage * STAGE;
-                            if (!(p.dbg & 1)) {
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma_f16_ss_pair(tmem_base + buf * NT, desc_kmajor(a, kk), desc_kmajor(b, kk), idescS,
-                                                     (k | kk) != 0);
+                const uint32_t idesc = make_idesc(fmt, 0, 0, 256, 256);
+                const uint32_t xlo = desc_lo(sX), rlo = desc_lo(sRing);
+                volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+                int need = 0, have = 0;
+                auto wait_event = [&]() {
+                    ++need;
+                    if (have < need) {
+                        uint32_t spins = 0;
+                        while ((have = *ready) < need) {
+                            if (++spins > (1u << 26)) {
+                                printf("ttx: quad MMA issuer timed out waiting for event %d (block %d,%d,%d rank %u)\n", need,
+                                       blockIdx.x, blockIdx.y, blockIdx.z, rank);
+                                __trap();
                             }
-                            umma_commit_mask(bar_empty(r.stage), pair_mask);
-                            r.advance(p.NS);
+                        }
+                    }
+                };
+                int stage = 0;
+                for (int i = 0; i < n_iter; ++i) {
+                    const int buf = i & 1;
+                    if (!g_role) {
+                        // ---- S pair: S(i) = X . Y_i^T into accumulator i & 1
+                        trace_at(p, 1, i, 0);
+                        wait_event();                           // group `buf` has read chunk i - 2 out of this accumulator
+                        tc_fence_after();
+                        for (int k = 0; k < p.NKC; ++k) {
+                            wait_event();
+                            tc_fence_after();
+                            const uint32_t a = xlo + k * 1024, b = rlo + stage * 1024;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_f16_ss_pair_lo(tmem_base + buf * 256, a + 2 * kk, b + 2 * kk, idesc, (k | kk) != 0);
+                            umma_commit_mask(bar_empty(stage), pair_mask);
+                            if (++stage == p.NS) stage = 0;
                         }
                         umma_commit_mask(bar_sfull(buf), pair_mask);
                         trace_at(p, 1, i, 1);
-                    }
-                } else {
-                    // ---- G pair: G(slab) += P'(j, sp) . Y^T chunk
-                    const uint32_t idescG = make_idesc(fmt, 0, 0, 256, HH);
-                    for (int i = 0; i < n_iter; ++i) {
-                        const int buf = i & 1;
-                        const uint32_t ph = (i >> 1) & 1;
-                        mbar_wait(bar_pfull(buf), ph);
-                        if (MODE == MODE_FG) mbar_wait(bar_gscaled(buf), ph);
+                    } else {
+                        // ---- G pair: G(slab) += P'(i, sp) . Y^T chunk, both slabs per P' sub-tile
+                        wait_event();                           // chunk buffer `buf` landed and patched in both CTAs
                         tc_fence_after();
                         for (int sp = 0; sp < 4; ++sp) {
-                            for (int sl = 0; sl < n_slabs; ++sl) {
-                                mbar_wait(bar_full(r.stage), r.phase);
+                            const uint32_t a = xlo + (buf * 4 + sp) * 1024;
+                            for (int sl = 0; sl < 2; ++sl) {
+                                wait_event();
                                 tc_fence_after();
-                                const uint32_t a = sX + buf * PCHUNK + sp * kChunkBytes;
-                                const uint32_t b = sRing + r.stage * STAGE;
-                                if (!(p.dbg & 2)) {
+                                const uint32_t b = rlo + stage * 1024;
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        umma_f16_ss_pair(tmem_base + sl * 256, desc_kmajor(a, kk), desc_kmajor(b, kk), idescG,
-                                                         (i | sp | kk) != 0);
-                                }
-                                umma_commit_mask(bar_empty(r.stage), pair_mask);
-                                r.advance(p.NS);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_f16_ss_pair_lo(tmem_base + sl * 256, a + 2 * kk, b + 2 * kk, idesc, (i | sp | kk) != 0);
+                                umma_commit_mask(bar_empty(stage), pair_mask);
+                                if (++stage == p.NS) stage = 0;
                             }
                         }
                         umma_commit_mask(bar_pempty(buf), 0xF);
                     }
-                    umma_commit_mask(bar_gfull, pair_mask);
                 }
+                if (g_role) umma_commit_mask(bar_gfull, pair_mask);
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPairEpiRegs));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kQuadEpiRegs));
         const int q = warp & 3;
-        const int ch = warp >> 2;
+        const int ch = (warp >> 2) & 1;
+        const int grp = warp >> 3;                    // S pair: epilogue group; G pair: only group 0 works
         const int row = q * 32 + lane;
-        const int et = threadIdx.x;                   // 0..255
+        const int et = threadIdx.x & 255;             // thread within its group
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float inv_ws = p.scal[1];
         const float pscale = BF16 ? 1.0f : kPScale;
         const float lg_scale = BF16 ? 0.0f : 12.0f;
+        const int n_valid_rows = n_tiles * kTile;
         if (!g_role) {
-            // =========================================================== S pair epilogue: thread = (row, column half ch)
+            // =========================================================== S pair epilogue: group grp <-> accumulator grp,
+            // chunks of parity grp, P' chunk buffer grp of the sibling G CTA.  thread = (row, column half ch)
             const float c1 = inv_ws * kLog2e;
-            float* kbuf = aux;
+            float* kbuf = reinterpret_cast<float*>(smem_gen + (sAux - smem_base)) + grp * 264;   // 256 offsets + 8 sign words
+            const uint32_t* sgn = reinterpret_cast<const uint32_t*>(kbuf + 256);
             const bool any_neg = p.scal[3] != 0.f;
-            const int n_valid_rows = n_tiles * kTile;
-            // addresses in the sibling G CTA (rank + 2): P' chunk buffers, aux block, barriers
-            const uint32_t rP = mapa_rank(sX, rank + 2);
-            const uint32_t rAux = mapa_rank(sAux, rank + 2);
-            const uint32_t r_pfull_lead[2] = {mapa_rank(bar_pfull(0), 2), mapa_rank(bar_pfull(1), 2)};
-            const uint32_t r_pfull_sib[2] = {mapa_rank(bar_pfull_l(0), rank + 2), mapa_rank(bar_pfull_l(1), rank + 2)};
-            auto sempty_arrive = [&](int buf) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(bar_sempty(buf), 0);
-            };
-            // this thread's 32 columns of sub-tile g of chunk buffer `buf`: four 16-byte chunks at swizzled positions
-            auto store_p = [&](const int buf, const uint32_t (&packed)[4][16]) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t r0 = rP + buf * PCHUNK + g * kChunkBytes + row * 128;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        st_cluster_v4(r0 + (((ch * 4 + cc) ^ (row & 7)) << 4),
-                                      make_uint4(packed[g][4 * cc + 0], packed[g][4 * cc + 1], packed[g][4 * cc + 2],
-                                                 packed[g][4 * cc + 3]));
-                }
-            };
-            // 16-bit element (row r, column col of the 256-column chunk) of chunk buffer `buf` in the sibling
-            auto p_addr = [&](const int buf, const int r, const int col) {
-                return rP + buf * PCHUNK + (col >> 6) * kChunkBytes + ptile_off(r, col & 63);
-            };
-            auto publish = [&](const int buf) {
-                fence_proxy_async_all();
-                fence_cluster();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_remote(r_pfull_lead[buf]);
-                    if (MODE == MODE_FG) mbar_arrive_remote(r_pfull_sib[buf]);
-                }
-            };
-            if (MODE == MODE_FG) {
-                const int grow = x_row0 + row;
-                const int label = valid_x ? p.row_label[grow] : -1;
-                float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;
-                float* xg = kbuf;                                      // [2 column halves][128] row maxima
-                for (int i = 0; i < n_iter; ++i) {
-                    const int buf = i & 1;
-                    const uint32_t ph = (i >> 1) & 1;
-                    const int t0 = (j0 + i) * NT;
-                    const float* bias_t = p.bias2 + t0 + ch * 32;
-                    float4 bpre[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
-                    mbar_wait(bar_sfull(buf), ph);
-                    if (et == 0) trace_at(p, 2, i, 0);
-                    tc_fence_after();
-                    uint32_t acc[4][32];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) tmem_ld32(tmem_base + lane_addr + buf * NT + g * 64 + ch * 32, acc[g]);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    sempty_arrive(buf);
-                    if (et == 0) trace_at(p, 2, i, 1);
-                    float lmax = -INFINITY;
-                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-                    float fsc = 1.f;
-                    bool rescaled = false;
-                    if (i == 0) {
-                        // First chunk: exact two-step (row maximum first, then the exponentials against the new reference).
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 bv = (g == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + g * 64) + e);
-                                const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x + lg_scale);
-                                const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y + lg_scale);
-                                const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z + lg_scale);
-                                const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w + lg_scale);
-                                lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                                acc[g][4 * e + 0] = __float_as_uint(y0); acc[g][4 * e + 1] = __float_as_uint(y1);
-                                acc[g][4 * e + 2] = __float_as_uint(y2); acc[g][4 * e + 3] = __float_as_uint(y3);
-                            }
-                        }
-                        xg[ch * kTile + row] = lmax;
-                        quarter_sync(q);
-                        const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                        mref = (rmax > -INFINITY) ? (rmax - lg_scale + 2.f) : 0.f;
-                        quarter_sync(q);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                const float e0 = ex2f(__uint_as_float(acc[g][e]) - mref), e1 = ex2f(__uint_as_float(acc[g][e + 1]) - mref);
-                                const float e2 = ex2f(__uint_as_float(acc[g][e + 2]) - mref), e3 = ex2f(__uint_as_float(acc[g][e + 3]) - mref);
-                                p0 += e0; p1 += e1; p2 += e2; p3 += e3;
-                                acc[g][e] = __float_as_uint(e0); acc[g][e + 1] = __float_as_uint(e1);
-                                acc[g][e + 2] = __float_as_uint(e2); acc[g][e + 3] = __float_as_uint(e3);
-                            }
-                        }
-                        ssum = (p0 + p1) + (p2 + p3);
-                    } else {
-                        // Later chunks, optimistic single pass against the CURRENT reference (see the pair kernel).
-                        const float krow = lg_scale - mref;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 bv = (g == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + g * 64) + e);
-                                const float y0 = fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, bv.x + krow);
-                                const float y1 = fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, bv.y + krow);
-                                const float y2 = fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, bv.z + krow);
-                                const float y3 = fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, bv.w + krow);
-                                lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                                const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
-                                p0 += e0; p1 += e1; p2 += e2; p3 += e3;
-                                acc[g][4 * e + 0] = __float_as_uint(e0); acc[g][4 * e + 1] = __float_as_uint(e1);
-                                acc[g][4 * e + 2] = __float_as_uint(e2); acc[g][4 * e + 3] = __float_as_uint(e3);
-                            }
-                        }
-                        float part = (p0 + p1) + (p2 + p3);
-                        if (quarter_any(q, lmax > lg_scale + 3.f)) {
-                            xg[ch * kTile + row] = lmax;
-                            quarter_sync(q);
-                            const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                            // new reference = row maximum + 2 (log2 units): values and sums scale by 2^-delta here, the
-                            // G pair scales the rows' accumulators before it consumes this chunk
-                            const float delta = (rmax > lg_scale + 3.f) ? (rmax - lg_scale + 2.f) : 0.f;
-                            fsc = ex2f(-delta);
-                            ssum *= fsc;
-                            part *= fsc;
-                            mref += delta;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) acc[g][e] = __float_as_uint(__uint_as_float(acc[g][e]) * fsc);
-                            rescaled = true;
-                            quarter_sync(q);
-                        }
-                        ssum += part;
-                    }
-                    {
-                        const int cbl = p.blank - t0, clb = label - t0;   // column inside this chunk, if any
-                        if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch) {
-                            float v = 0.f;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) v = (g * 64 + ch * 32 + e == cbl) ? __uint_as_float(acc[g][e]) : v;
-                            zb = lg2f(v) + mref - lg_scale;
-                        }
-                        if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch) {
-                            float v = 0.f;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) v = (g * 64 + ch * 32 + e == clb) ? __uint_as_float(acc[g][e]) : v;
-                            zl = lg2f(v) + mref - lg_scale;
-                        }
-                    }
-                    uint32_t packed[4][16];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            packed[g][e] = pack16<BF16>(__uint_as_float(acc[g][2 * e]), __uint_as_float(acc[g][2 * e + 1]));
-                    mbar_wait(bar_pempty(buf), ph ^ 1);           // the G pair has consumed chunk i - 2
-                    if (et == 0) trace_at(p, 2, i, 2);
-                    if (!(p.dbg & 16)) store_p(buf, packed);
-                    {
-                        const int cbl = p.blank - t0, clb = label - t0;
-                        if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch) st_cluster_u16(p_addr(buf, row, cbl), 0);
-                        if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch) st_cluster_u16(p_addr(buf, row, clb), 0);
-                    }
-                    if (rescaled) {
-                        if (ch == 0) st_cluster_f32(rAux + 4 * (kAuxScale + buf * kTile + row), fsc);
-                        if (ch == 0 && lane == 0) st_cluster_u32(rAux + 4 * (kAuxFlag + buf * 4 + q), 1u);
-                    }
-                    publish(buf);
-                    if (et == 0) trace_at(p, 2, i, 3);
-                }
-                // combine the two column halves of each row through the (now idle) X tile
-                float4* xch = reinterpret_cast<float4*>(smem_gen);
-                pair_epi_sync();
-                xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
-                pair_epi_sync();
-                const float4 o = xch[(ch ^ 1) * kTile + row];
-                const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
-                if (ch == 0) {
-                    if (valid_x) {
-                        zb = ((p.blank & 63) < 32) ? zb : o.y;        // which column half owns the blank / label column
-                        if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
-                        p.lse[grow] = lse2 * kLn2;
-                        p.lpb[grow] = (zb - lse2) * kLn2;
-                        p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
-                    }
-                    st_cluster_f32(rAux + 4 * (kAuxFinal + row), ex2f(mref - lg_scale - lse2) * inv_ws);
-                }
-                fence_cluster();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(mapa_rank(bar_fin, rank + 2));
+            const uint32_t rP = mapa_rank(sX, rank + 2) + grp * PCHUNK;
+            const uint32_t r_pland = mapa_rank(bar_pland(grp), rank + 2);
+            auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(kEpiBarrier + grp) : "memory"); };
+            float krow = 0.f, db_acc = 0.f;
+            int vrow = 0;
+            if (MODE == MODE_DA) {
+                const float lse = valid_x ? p.rowmeta[x_row0 + row].x : INFINITY;
+                krow = fmaf(lse, -kLog2e, lg_scale);
             } else {
-                float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-                int label = -1;
-                float krow = 0.f, db_acc = 0.f;
-                int vrow = 0;
-                if (MODE == MODE_DA) {
-                    if (valid_x) {
-                        rm = p.rowmeta[x_row0 + row];
-                        label = p.row_label[x_row0 + row];
-                    }
-                    krow = fmaf(rm.x, -kLog2e, lg_scale);
-                } else {
-                    vrow = x_row0 + row;
-                    krow = __ldg(p.bias2 + vrow);
-                }
-                for (int i = 0; i < n_iter; ++i) {
-                    const int buf = i & 1;
-                    const uint32_t ph = (i >> 1) & 1;
-                    const int t0 = (j0 + i) * NT;           // first vocab id (DA) / lattice row (DW) of this stream chunk
-                    float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-                    int clabel = -1;
-                    if (MODE == MODE_DW) {
-                        const int col = t0 + et;            // this thread owns column et of the 256-column chunk
-                        if (col < n_valid_rows) {
-                            cm = __ldg(p.rowmeta + col);
-                            clabel = __ldg(p.row_label + col);
-                        }
-                        kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
-                        kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
-                        pair_epi_sync();
-                    }
-                    mbar_wait(bar_sfull(buf), ph);
-                    if (et == 0) trace_at(p, 2, i, 0);
-                    tc_fence_after();
-                    uint32_t acc[4][32];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) tmem_ld32(tmem_base + lane_addr + buf * NT + g * 64 + ch * 32, acc[g]);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    sempty_arrive(buf);
-                    if (et == 0) trace_at(p, 2, i, 1);
-                    uint32_t packed[4][16];
-                    {
-                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int cb = g * 64 + ch * 32;
-                            const float4* k4 = (MODE == MODE_DA) ? reinterpret_cast<const float4*>(p.bias2 + t0 + cb)
-                                                                 : reinterpret_cast<const float4*>(kbuf + cb);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 kv = (MODE == MODE_DA) ? __ldg(k4 + e) : k4[e];
-                                float v0 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 0]), c1, kv.x + krow));
-                                float v1 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 1]), c1, kv.y + krow));
-                                float v2 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 2]), c1, kv.z + krow));
-                                float v3 = ex2f(fmaf(__uint_as_float(acc[g][4 * e + 3]), c1, kv.w + krow));
-                                if (MODE == MODE_DW) {
-                                    if (any_neg) {
-                                        const float4 sg = *reinterpret_cast<const float4*>(kbuf + NT + cb + 4 * e);
-                                        v0 *= sg.x; v1 *= sg.y; v2 *= sg.z; v3 *= sg.w;
-                                    }
-                                    d0 += v0; d1 += v1; d2 += v2; d3 += v3;
-                                }
-                                packed[g][2 * e] = pack16<BF16>(v0, v1);
-                                packed[g][2 * e + 1] = pack16<BF16>(v2, v3);
-                            }
-                        }
-                        if (MODE == MODE_DW) db_acc += (d0 + d1) + (d2 + d3);
-                    }
-                    mbar_wait(bar_pempty(buf), ph ^ 1);
-                    if (et == 0) trace_at(p, 2, i, 2);
-                    if (!(p.dbg & 16)) store_p(buf, packed);
-                    // sparse corrections: the blank and label entries are p - rb / p - rl, with p = exp(lp) from the
-                    // forward pass (rowmeta .y / .z), written exactly instead of being carried through the dense loop
-                    if (MODE == MODE_DA) {
-                        const int cbl = p.blank - t0, clb = label - t0;
-                        if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch)
-                            st_cluster_u16(p_addr(buf, row, cbl), to16<BF16>(rm.y * pscale));
-                        if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch)
-                            st_cluster_u16(p_addr(buf, row, clb), to16<BF16>(rm.z * pscale));
-                    } else {
-                        pair_epi_sync();                    // column owners patch rows written by other threads
-                        const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
-                        if (rbl >= 0 && rbl < kTile) st_cluster_u16(p_addr(buf, rbl, et), to16<BF16>(cm.y * cm.w * pscale));
-                        if (rlb >= 0 && rlb < kTile) st_cluster_u16(p_addr(buf, rlb, et), to16<BF16>(cm.z * cm.w * pscale));
-                    }
-                    publish(buf);
-                    if (et == 0) trace_at(p, 2, i, 3);
-                }
-                // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
-                if (MODE == MODE_DW && vrow < p.V) atomicAdd(p.db + vrow, db_acc * p.scal[2] / pscale);
+                vrow = x_row0 + row;
+                krow = __ldg(p.bias2 + vrow);
             }
-        } else {
-            // =========================================================== G pair epilogue warps
-            if (MODE == MODE_FG && ch == 0) {
-                // Reference changes (rare): before the pair consumes chunk i, scale the accumulator rows by the factors the
-                // S sibling left in this CTA's shared memory.  Warps 0..3 (one per TMEM lane quarter) serve every chunk.
-                volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(aux + kAuxFlag);
-                volatile float* gs = aux + kAuxScale;
-                for (int i = 0; i < n_iter; ++i) {
-                    const int buf = i & 1;
-                    const uint32_t ph = (i >> 1) & 1;
-                    mbar_wait(bar_pfull_l(buf), ph);
-                    fence_cluster();
-                    if (flags[buf * 4 + q] != 0) {
-                        // G sub-passes of chunk i - 1 and earlier are complete once its buffer has been released
-                        if (i > 0) mbar_wait(bar_pempty(buf ^ 1), ((i - 1) >> 1) & 1);
-                        tc_fence_after();
-                        const float fsc = gs[buf * kTile + row];
-                        uint32_t gacc[32];
-                        for (int cc = 0; cc < p.H / 32; ++cc) {
-                            const uint32_t ta = tmem_base + lane_addr + (cc >> 3) * 256 + (cc & 7) * 32;
-                            tmem_ld32(ta, gacc);
-                            tmem_ld_wait();
+            const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1);
+            uint64_t d01 = pk2(0.f, 0.f), d23 = d01;
+            int k_own = 0;
+            for (int i = grp; i < n_iter; i += 2, ++k_own) {
+                const int t0 = (j0 + i) * NT;           // first vocab id (DA) / lattice row (DW) of this stream chunk
+                if (MODE == MODE_DW) {
+                    // per-column constant k_m = -lse2_m + log2(|w_m| * scale): Q = +-2^(acc*c1 + bias2_v + k_m)
+                    group_sync();                       // every thread of the group is done with the previous constants
+                    const int col = t0 + et;
+                    float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+                    if (col < n_valid_rows) cm = __ldg(p.rowmeta + col);
+                    kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
+                    const uint32_t neg = __ballot_sync(0xffffffffu, cm.w < 0.f);
+                    if (lane == 0) reinterpret_cast<uint32_t*>(kbuf + 256)[et >> 5] = neg;
+                    group_sync();
+                }
+                mbar_wait(bar_sfull(grp), k_own & 1);
+                if (et == 0 && grp == 0) trace_at(p, 2, k_own, 0);
+                tc_fence_after();
+                mbar_wait(bar_pempty(grp), (k_own & 1) ^ 1);    // the G pair has consumed chunk i - 2 from this buffer
+                // One 64-column sub-tile at a time: read 32 accumulator columns, exponentials, asynchronous DSMEM stores.
+                // (Keeping all four sub-tiles' results in registers until the accumulator is released was tried: with
+                // 104 registers it spills and the exponentials slow down by more than the earlier release gains.)
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + lane_addr + grp * 256 + g * 64 + ch * 32, acc);
+                    const int cb = g * 64 + ch * 32;    // this thread's first column of sub-tile g inside the chunk
+                    const float4* k4 = (MODE == MODE_DA) ? reinterpret_cast<const float4*>(p.bias2 + t0 + cb)
+                                                         : reinterpret_cast<const float4*>(kbuf + cb);
+                    float4 kv[8];
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) gacc[e] = __float_as_uint(__uint_as_float(gacc[e]) * fsc);
-                            tmem_st32(ta, gacc);
-                        }
-                        tmem_st_wait();
+                    for (int e = 0; e < 8; ++e) kv[e] = (MODE == MODE_DA) ? __ldg(k4 + e) : k4[e];
+                    const uint32_t sbits = (MODE == MODE_DW && any_neg) ? sgn[cb >> 5] : 0u;
+                    tmem_ld_wait();
+                    if (g == 3) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) flags[buf * 4 + q] = 0;
+                        if (lane == 0) mbar_arrive_cluster(bar_sempty(grp), 0);
+                        if (et == 0 && grp == 0) trace_at(p, 2, k_own, 1);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(bar_gscaled(buf), 2);
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint64_t y01 = fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(kv[e].x, kv[e].y), krow2));
+                        const uint64_t y23 = fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(kv[e].z, kv[e].w), krow2));
+                        float y0, y1, y2, y3;
+                        unpk2(y01, y0, y1);
+                        unpk2(y23, y2, y3);
+                        float v0 = ex2f(y0), v1 = ex2f(y1), v2 = ex2f(y2), v3 = ex2f(y3);
+                        if (MODE == MODE_DW) {
+                            if (sbits) {
+                                v0 = ((sbits >> (4 * e + 0)) & 1) ? -v0 : v0;
+                                v1 = ((sbits >> (4 * e + 1)) & 1) ? -v1 : v1;
+                                v2 = ((sbits >> (4 * e + 2)) & 1) ? -v2 : v2;
+                                v3 = ((sbits >> (4 * e + 3)) & 1) ? -v3 : v3;
+                            }
+                            d01 = add2(d01, pk2(v0, v1));
+                            d23 = add2(d23, pk2(v2, v3));
+                        }
+                        packed[2 * e] = pack16<BF16>(v0, v1);
+                        packed[2 * e + 1] = pack16<BF16>(v2, v3);
+                    }
+                    const uint32_t r0 = rP + g * kChunkBytes + row * 128;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        st_async_v4(r0 + (((ch * 4 + cc) ^ (row & 7)) << 4), packed[4 * cc + 0], packed[4 * cc + 1],
+                                    packed[4 * cc + 2], packed[4 * cc + 3], r_pland);
                 }
+                if (et == 0 && grp == 0) trace_at(p, 2, k_own, 3);
             }
-            // ---- final: G (128 rows x H fp32 in TMEM) -> global; the two warps of a lane quarter split the columns
+            // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
+            if (MODE == MODE_DW && vrow < p.V) {
+                float d0, d1;
+                unpk2(add2(d01, d23), d0, d1);
+                db_acc = d0 + d1;
+                atomicAdd(p.db + vrow, db_acc * p.scal[2] / pscale);
+            }
+        } else if (grp == 0) {
+            // =========================================================== G pair epilogue warps 0..7: thread = (row, ch)
+            // Per chunk: arm the landing barrier, wait until the S sibling's 64 KiB have arrived, write the exact blank /
+            // label entries (p = exp(lp) from the forward pass, rowmeta .y / .z) over the dense ones, hand over to the MMA.
+            uint8_t* sP_gen = smem_gen;
+            float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+            int label = -1;
+            if (MODE == MODE_DA && valid_x) {
+                rm = p.rowmeta[x_row0 + row];
+                label = p.row_label[x_row0 + row];
+            }
+            for (int i = 0; i < n_iter; ++i) {
+                const int buf = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                const int t0 = (j0 + i) * NT;
+                float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
+                int clabel = -1;
+                if (MODE == MODE_DW) {
+                    const int col = t0 + et;            // this thread owns column et of the chunk
+                    if (col < n_valid_rows) {
+                        cm = __ldg(p.rowmeta + col);
+                        clabel = __ldg(p.row_label + col);
+                    }
+                }
+                if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_pland(buf), PCHUNK);
+                mbar_wait(bar_pland(buf), ph);
+                uint8_t* cbuf = sP_gen + buf * PCHUNK;
+                if (MODE == MODE_DA) {
+                    const int cbl = p.blank - t0, clb = label - t0;
+                    if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch)
+                        *reinterpret_cast<uint16_t*>(cbuf + (cbl >> 6) * kChunkBytes + ptile_off(row, cbl & 63)) = to16<BF16>(rm.y * pscale);
+                    if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch)
+                        *reinterpret_cast<uint16_t*>(cbuf + (clb >> 6) * kChunkBytes + ptile_off(row, clb & 63)) = to16<BF16>(rm.z * pscale);
+                } else {
+                    const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
+                    uint8_t* sub = cbuf + (et >> 6) * kChunkBytes;
+                    if (rbl >= 0 && rbl < kTile) *reinterpret_cast<uint16_t*>(sub + ptile_off(rbl, et & 63)) = to16<BF16>(cm.y * cm.w * pscale);
+                    if (rlb >= 0 && rlb < kTile) *reinterpret_cast<uint16_t*>(sub + ptile_off(rlb, et & 63)) = to16<BF16>(cm.z * cm.w * pscale);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(bar_pready(buf), 2);
+            }
+            // ---- final: G (128 rows x 512 fp32 in TMEM) -> global; the two warps of a lane quarter split the columns
             mbar_wait(bar_gfull, 0);
             tc_fence_after();
             const float gmax = p.scal[2];
-            const int ngrp = p.H / 32;                  // 32-column groups; H = 512: slab = group / 8
             uint32_t gacc[32];
             float f;
             float* dst;
             bool ok;
-            if (MODE == MODE_FG) {
-                mbar_wait(bar_fin, 0);
-                fence_cluster();
-                f = reinterpret_cast<volatile float*>(aux + kAuxFinal)[row];
-                dst = p.dA + (size_t)(x_row0 + row) * p.H;
-                ok = valid_x;
-            } else if (MODE == MODE_DA) {
-                const float4 rm = valid_x ? p.rowmeta[x_row0 + row] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == MODE_DA) {
                 f = rm.w * gmax * inv_ws / pscale;
                 dst = p.dA + (size_t)(x_row0 + row) * p.H;
                 ok = valid_x;
@@ -1851,23 +1676,21 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 ok = x_row0 + row < p.V;
                 dst = p.dW + (size_t)(x_row0 + row) * p.H;
             }
-            for (int cc = ch; cc < ngrp; cc += 2) {
-                const int col = (HH == 256) ? cc * 32 : cc * 32;     // slabs are contiguous in TMEM when HH = 256
-                const uint32_t ta = tmem_base + lane_addr + ((HH == 256) ? col : (col / HH) * 256 + (col % HH));
-                tmem_ld32(ta, gacc);
+            for (int cc = ch; cc < 16; cc += 2) {
+                tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
                 tmem_ld_wait();
                 if (ok) {
                     if (MODE == MODE_DW) {
 #pragma unroll
                         for (int e = 0; e < 32; e += 4)
-                            red_add_v4(dst + col + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                            red_add_v4(dst + cc * 32 + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
                                        __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; e += 4) {
                             float4 o4 = make_float4(__uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
                                                     __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
-                            *reinterpret_cast<float4*>(dst + col + e) = o4;
+                            *reinterpret_cast<float4*>(dst + cc * 32 + e) = o4;
                         }
                     }
                 }
@@ -1877,7 +1700,7 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == kPairMmaWarp) {
+    if (warp == kQuadMmaWarp) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 512);
     }
@@ -2122,9 +1945,11 @@ static bool v3_applicable(int H, const void* w16t, const void* a16t) {
 bool fwd_grad_supported_h(int H) { return H == 128 || H == 256 || H == 512; }
 
 // ---- quad kernel (cluster of 4: S pair + G pair)
-static bool quad_enabled() {
-    const char* e = getenv("TTX_QUAD");     // opt-in: see DESIGN.md (DSMEM hand-off bandwidth makes it slower today)
-    return e && e[0] == '1';
+// TTX_QUAD: 0 = pair kernel everywhere, 1 (default) = quad kernel for the weight gradient (measured 4.6 vs 5.0 ms at
+// cfg2), 2 = also for the activation gradient when it is a separate launch (no gain measured: 5.7 ms either way).
+static int quad_level() {
+    const char* e = getenv("TTX_QUAD");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 
 template <int MODE, bool BF16>
@@ -2179,8 +2004,8 @@ static void quad_params(MmaParams& p, size_t& smem, int H, int V) {
     p.H = H;
     p.NKC = H / 64;
     p.V = V;
-    p.n_halves = (H > 256) ? 2 : 1;
-    p.HH = H / p.n_halves;
+    p.n_halves = 2;
+    p.HH = 256;
     p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
     p.trace = trace_buffer();
     const size_t fixed = (size_t)kQuadRing0 + kQuadBars * 8 + 16 + kQuadAux;
@@ -2196,30 +2021,6 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
                           int V, int Vpad, bool bf16, const int* meta, const float* bias2, const float* scal,
                           const int* row_label, int blank, float* lse, float* lpb, float* lpl, float* ew,
                           cudaStream_t stream) {
-    if (quad_enabled()) {
-        MmaParams p{};
-        size_t smem;
-        quad_params(p, smem, H, V);
-        p.blank = blank;
-        p.splits = 1;
-        p.meta = meta;
-        p.bias2 = bias2;
-        p.scal = scal;
-        p.row_label = row_label;
-        p.lse = lse;
-        p.lpb = lpb;
-        p.lpl = lpl;
-        p.dA = ew;
-        CUtensorMap mx, my, myt;
-        if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
-        if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-        if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
-        dim3 grid(4 * ((n_tiles_ub + 1) / 2), 1, 1);
-        int rc = bf16 ? launch_quad<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
-                      : launch_quad<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
-        if (rc == 0) trace_dump("FG quad", stream);
-        return rc;
-    }
     MmaParams p{};
     p.H = H;
     p.NKC = H / 64;
@@ -2259,7 +2060,8 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
                      int n_tiles_ub, int H, int V, int Vpad, bool bf16, const int* meta, const float* bias2,
                      const float* scal, const int* row_label, int blank, const float4* rowmeta, float* dA, float* dW,
                      float* db, int splits, cudaStream_t stream) {
-    if (v3_applicable(H, w16t, a16t) && quad_enabled()) {
+    if (H == 512 && v3_applicable(H, w16t, a16t) && quad_level() > 0) {
+        const bool quad_da = quad_level() > 1;
         MmaParams p{};
         size_t smem;
         quad_params(p, smem, H, V);
@@ -2272,7 +2074,7 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         p.dA = dA;
         p.dW = dW;
         p.db = db;
-        if (dA) {
+        if (dA && quad_da) {
             CUtensorMap mx, my, myt;
             if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
             if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
@@ -2312,7 +2114,9 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             if (rc) return rc;
             trace_dump("DW quad", stream);
         }
-        return 0;
+        if (!dA || quad_da) return 0;
+        dW = nullptr;                                           // the pair kernel below does the activation gradient only
+        db = nullptr;
     }
     if (v3_applicable(H, w16t, a16t)) {
         MmaParams p{};
