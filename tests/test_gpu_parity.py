@@ -267,8 +267,9 @@ def test_unsupported_width_uses_dense_entry_and_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
-def test_bf16_input_variant_stated_tolerance():
-    case = _espnet_case(2, 40, 8, 500, 64, 256, [40, 31], [8, 5], seed=9)
+@pytest.mark.parametrize("H", [256, 512])        # 512: the quad kernel's bf16 instantiation does the weight gradient
+def test_bf16_input_variant_stated_tolerance(H):
+    case = _espnet_case(2, 40, 8, 500, 64, H, [40, 31], [8, 5], seed=9)
     errs, (_, _, got) = _run_pair(*case, dtype=torch.bfloat16)
     _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
 
@@ -281,10 +282,13 @@ def test_c_abi_rejects_unsupported_width_with_message():
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
-@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"}, {}])
+@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"}, {"TTX_QUAD": "0"},
+                                 {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"}, {}])
 def test_kernel_variants_agree_with_oracle(env, monkeypatch):
     """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
-    kernel (TTX_NO_FWD_GRAD=1) and the default kernels (fused forward+gradient, pair backward) all meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair)."""
+    kernel (TTX_NO_FWD_GRAD=1), the pair kernel for the weight gradient (TTX_QUAD=0), the quad kernel for both gradients
+    (TTX_QUAD=2) and the default kernels (fused forward+gradient pair kernel, quad kernel for the weight gradient) all
+    meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair / quad)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)

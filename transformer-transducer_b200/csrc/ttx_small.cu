@@ -476,9 +476,31 @@ __global__ void reduce_pred_kernel(const ActGradSrc a, const float* __restrict__
         float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // the label emitted from u is the same for every frame: fetch its W_out row once
+        float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool has_label = false;
+        if (EW) {
+            const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);
+            has_label = lab >= 0 && lab != a.blank;
+            if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+        }
+        const float gscale = EW ? a.scal[2] : 1.f;
         for (int t = t0; t < t1; ++t) {
             const float4 e = __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h));
-            const float4 g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
+            float4 g;
+            if (EW) {
+                const size_t grow = base + (size_t)t * U1b + u;
+                g = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
+                const float4 rm = __ldg(a.rowmeta + grow);
+                const float coef = rm.w * gscale;
+                g.x = fmaf(rm.y, wb.x, g.x); g.y = fmaf(rm.y, wb.y, g.y); g.z = fmaf(rm.y, wb.z, g.z); g.w = fmaf(rm.y, wb.w, g.w);
+                if (has_label) {
+                    g.x = fmaf(rm.z, wl.x, g.x); g.y = fmaf(rm.z, wl.y, g.y); g.z = fmaf(rm.z, wl.z, g.z); g.w = fmaf(rm.z, wl.w, g.w);
+                }
+                g.x *= coef; g.y *= coef; g.z *= coef; g.w *= coef;
+            } else {
+                g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
+            }
             acc.x += g.x * sech2(e.x + pp.x);
             acc.y += g.y * sech2(e.y + pp.y);
             acc.z += g.z * sech2(e.z + pp.z);
