@@ -396,7 +396,7 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
 __device__ __forceinline__ float sech2(float x) {
     const float e = __expf(-2.f * fabsf(x));
     const float d = 1.f + e;
-    return 4.f * e / (d * d);
+    return __fdividef(4.f * e, d * d);      // d in [1, 2]: the fast division is good to 2 ulp here
 }
 
 // Source of dL/dA for the two reductions below.  EW = false: `src` already holds dL/dA.  EW = true: `src` holds
