@@ -10,10 +10,77 @@ B*T + B*U rows instead of the reference's B*T*U).  Everything else -- 1-D decode
 (tt/model.py:77), CPU tensors, other activations, widths that are not a multiple of 64 -- is the reference's
 dense math.
 """
+import os
+
 import torch
 
 from . import functional as F
 from .lazy import LazyJointLogits
+
+
+class _tf32_matmul:
+    """cuBLAS TF32 (fp32 accumulate) for the GEMMs issued inside the block, whatever the process-wide setting."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+def _split_tf32(x):
+    """x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32."""
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, x - hi
+
+
+def _mm3(a, b_t, passes):
+    """a @ b_t^T on the tensor cores (cuBLAS TF32, fp32 accumulate).  passes = 3: error-compensated split
+    a_hi b_hi + a_lo b_hi + a_hi b_lo (the dropped a_lo b_lo term is 2^-22 relative), i.e. fp32-grade results at three
+    small tensor-core GEMMs; passes = 1: plain TF32 operands (2^-11 relative rounding)."""
+    with _tf32_matmul():
+        if passes == 1:
+            return torch.matmul(a, b_t.t())
+        a_hi, a_lo = _split_tf32(a)
+        b_hi, b_lo = _split_tf32(b_t)
+        a2 = a_hi.reshape(-1, a.shape[-1])
+        y = torch.mm(a2, b_hi.t())
+        y.addmm_(a_lo.reshape(-1, a.shape[-1]), b_hi.t())
+        y.addmm_(a2, b_lo.t())
+        return y.view(*a.shape[:-1], b_t.shape[0])
+
+
+class _ProjTC(torch.autograd.Function):
+    """y = x W^T (+ b) for the two small pre-projections of the joint, forward and backward on the tensor cores instead
+    of the fp32 SIMT GEMMs torch picks by default for float32.  `TTX_TF32_PROJ`: 0 (default) = torch.nn.functional.linear;
+    1 = single TF32 pass (cfg2 step 13.1 -> 12.6 ms, gradient error vs the oracle 1-3e-4 -> 3-6e-4, still inside the
+    1e-3 tolerance); 3 = error-compensated 3 x TF32 (fp32-grade results, but as separate library launches it is no
+    faster than the SIMT GEMMs -- a single fused kernel is the next step)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, passes):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias, ctx.passes = b is not None, passes
+        y = _mm3(x, w, passes)
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
+        dx = _mm3(dy, w.t(), ctx.passes) if ctx.needs_input_grad[0] else None
+        dw = _mm3(dy2.t(), x2.t(), ctx.passes) if ctx.needs_input_grad[1] else None
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+def _proj(x, w, b=None):
+    passes = int(os.environ.get("TTX_TF32_PROJ", "0"))
+    if x.dtype == torch.float32 and w.dtype == torch.float32 and passes in (1, 3):
+        return _ProjTC.apply(x, w, b, passes)
+    return torch.nn.functional.linear(x, w, b)
 
 
 def _fusable(x, width):
@@ -35,8 +102,8 @@ class JointNet(torch.nn.Module):
                 _fusable(enc_state, self.forward_layer.out_features)):
             de = enc_state.size(-1)
             w = self.forward_layer.weight
-            eproj = torch.nn.functional.linear(enc_state, w[:, :de], self.forward_layer.bias)
-            pproj = torch.nn.functional.linear(dec_state, w[:, de:])
+            eproj = _proj(enc_state, w[:, :de], self.forward_layer.bias)
+            pproj = _proj(dec_state, w[:, de:])
             return LazyJointLogits(eproj, pproj, self.project_layer.weight, self.project_layer.bias)
         if enc_state.dim() == 3 and dec_state.dim() == 3:  # tt/model.py:21-29
             t, u = enc_state.size(1), dec_state.size(1)
@@ -74,8 +141,8 @@ class JointNetwork(torch.nn.Module):
         if (self.fused and self.joint_activation_type == "tanh" and h_enc.dim() == 4 and h_dec.dim() == 4 and
                 h_enc.size(2) == 1 and h_dec.size(1) == 1 and h_enc.size(0) == h_dec.size(0) and
                 _fusable(h_enc, self.lin_enc.out_features)):
-            eproj = self.lin_enc(h_enc.squeeze(2))
-            pproj = self.lin_dec(h_dec.squeeze(1))
+            eproj = _proj(h_enc.squeeze(2), self.lin_enc.weight, self.lin_enc.bias)
+            pproj = _proj(h_dec.squeeze(1), self.lin_dec.weight)
             return LazyJointLogits(eproj, pproj, self.lin_out.weight, self.lin_out.bias)
         z = self.joint_activation(self.lin_enc(h_enc) + self.lin_dec(h_dec))  # joint_network.py:48-49
         return self.lin_out(z)
