@@ -53,16 +53,23 @@ def _mm3(a, b_t, passes):
 
 
 class _ProjTC(torch.autograd.Function):
-    """y = x W^T (+ b) for the two small pre-projections of the joint, forward and backward on the tensor cores instead
-    of the fp32 SIMT GEMMs torch picks by default for float32.  `TTX_TF32_PROJ`: 0 (default) = torch.nn.functional.linear;
-    1 = single TF32 pass (cfg2 step 13.1 -> 12.6 ms, gradient error vs the oracle 1-3e-4 -> 3-6e-4, still inside the
-    1e-3 tolerance); 3 = error-compensated 3 x TF32 (fp32-grade results, but as separate library launches it is no
-    faster than the SIMT GEMMs -- a single fused kernel is the next step)."""
+    """y = x W^T (+ b) for the two small pre-projections of the joint (float32).  torch runs float32 GEMMs as fp32 SIMT
+    kernels by default (0.58 ms per cfg2 step for the six of them).  `TTX_TF32_PROJ` selects where cuBLAS TF32 tensor-core
+    GEMMs (fp32 accumulate) are used instead:
+      0  nowhere (torch.nn.functional.linear and its autograd);
+      2  (default) the four backward GEMMs only -- the forward stays exact because its rounding would reach the loss and
+         every gradient; d_enc / d_pred / first-layer weight gradients move from ~1e-4 to ~3e-4 relative error against
+         the oracle (tolerance 1e-3; the output-layer gradients are at 1-3e-4 anyway), ~0.3 ms per step;
+      1  forward too (another 0.15 ms; every gradient at 3-6e-4);
+      3  error-compensated 3 x TF32 everywhere (fp32-grade results, but as separate library launches no faster than
+         the SIMT GEMMs -- one fused kernel is the next step)."""
 
     @staticmethod
     def forward(ctx, x, w, b, passes):
         ctx.save_for_backward(x, w)
         ctx.has_bias, ctx.passes = b is not None, passes
+        if passes == 2:      # exact forward (its rounding would reach every gradient), TF32 only in the backward GEMMs
+            return torch.nn.functional.linear(x, w, b)
         y = _mm3(x, w, passes)
         return y + b if b is not None else y
 
@@ -70,15 +77,16 @@ class _ProjTC(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
-        dx = _mm3(dy, w.t(), ctx.passes) if ctx.needs_input_grad[0] else None
-        dw = _mm3(dy2.t(), x2.t(), ctx.passes) if ctx.needs_input_grad[1] else None
+        bp = 1 if ctx.passes == 2 else ctx.passes
+        dx = _mm3(dy, w.t(), bp) if ctx.needs_input_grad[0] else None
+        dw = _mm3(dy2.t(), x2.t(), bp) if ctx.needs_input_grad[1] else None
         db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
 
 def _proj(x, w, b=None):
-    passes = int(os.environ.get("TTX_TF32_PROJ", "0"))
-    if x.dtype == torch.float32 and w.dtype == torch.float32 and passes in (1, 3):
+    passes = int(os.environ.get("TTX_TF32_PROJ", "2"))
+    if x.dtype == torch.float32 and w.dtype == torch.float32 and passes in (1, 2, 3):
         return _ProjTC.apply(x, w, b, passes)
     return torch.nn.functional.linear(x, w, b)
 
