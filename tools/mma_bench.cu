@@ -368,6 +368,120 @@ static void run_ring(int pat, int ns, long long* d_out) {
     printf("ring pat %d ns %d: %.1f cycles per MMA (4 per group, commit per group)\n", pat, ns, (double)h[37] / groups / 4);
 }
 
+
+// ---- TMA ingest: every CTA streams [128 rows x 64 cols] 16-bit boxes (16 KiB) of an L2-resident matrix into a ring of
+// shared-memory stages; nothing consumes the data except a thread that recycles the stage at once.
+//   mc = 0: unicast, each CTA fetches its own 16 KiB per stage
+//   mc = 1: clusters of 2: each CTA fetches 8 KiB (64 rows) and multicasts it to both CTAs (each still receives 16 KiB)
+//   mc = 2: clusters of 4, pairs (0,2) and (1,3) share: each CTA fetches 8 KiB and multicasts to its partner and itself
+__global__ void __launch_bounds__(128, 1) tma_bench(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map8,
+                                                    int mc, int ns, int stages_total, int rows_total, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t sBar = base + 12 * 16384;
+    auto full = [&](int i) { return sBar + 8 * i; };
+    auto empty = [&](int i) { return sBar + 8 * (16 + i); };
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ns; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), mc ? 2 : 1); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (mc) cluster_sync_all();
+    const int cta = blockIdx.x;
+    long long t0 = clock64();
+    if (threadIdx.x == 0) {
+        // producer
+        int st = 0; uint32_t ph = 0;
+        const uint32_t partner = (mc == 1) ? (rank ^ 1) : (rank ^ 2);
+        const uint16_t mask = (uint16_t)((1u << rank) | (1u << partner));
+        const int half = (mc == 1) ? (int)(rank & 1) : (int)((rank >> 1) & 1);
+        const int group = (mc == 0) ? cta : (mc == 1 ? cta / 2 : (cta / 4) * 2 + (int)(rank & 1));
+        for (int g = 0; g < stages_total; ++g) {
+            mbar_wait(empty(st), ph ^ 1);
+            mbar_arrive_expect_tx(full(st), 16384);
+            const int col = (g & 7) * 64;
+            const int row = ((group * 37 + (g >> 3)) * 128) % rows_total;
+            if (mc == 0) {
+                tma_load_2d(base + st * 16384, &map16, full(st), col, row);
+            } else {
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                    ::"r"(base + st * 16384 + half * 8192), "l"(reinterpret_cast<uint64_t>(&map8)), "r"(full(st)), "r"(col), "r"(row + half * 64), "h"(mask)
+                    : "memory");
+            }
+            if (++st == ns) { st = 0; ph ^= 1; }
+        }
+    } else if (threadIdx.x == 32) {
+        // consumer: release each stage as soon as it is full (to both producers that write into it)
+        int st = 0; uint32_t ph = 0;
+        const uint32_t partner = (mc == 1) ? (rank ^ 1) : (rank ^ 2);
+        for (int g = 0; g < stages_total; ++g) {
+            mbar_wait(full(st), ph);
+            if (mc) {
+                mbar_arrive(empty(st));
+                mbar_arrive_cluster(empty(st), partner);
+            } else {
+                mbar_arrive(empty(st));
+            }
+            if (++st == ns) { st = 0; ph ^= 1; }
+        }
+        out[cta] = clock64() - t0;
+    }
+    __syncthreads();
+    if (mc) cluster_sync_all();
+}
+
+static void run_tma(int mc, int ns, long long* d_out) {
+    typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static PFN enc = nullptr;
+    static void* buf = nullptr;
+    const int rows = 8192, cols = 512;      // 8 MiB of 16-bit values: stays in L2
+    if (!enc) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+        enc = (PFN)ptr;
+        cudaMalloc(&buf, (size_t)rows * cols * 2);
+        cudaMemset(buf, 0, (size_t)rows * cols * 2);
+    }
+    CUtensorMap m16, m8;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint32_t box16[2] = {64, 128}, box8[2] = {64, 64};
+    enc(&m16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, buf, dims, strides, box16, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    enc(&m8, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, buf, dims, strides, box8, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cudaFuncSetAttribute(tma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaLaunchConfig_t cfg{};
+    const int csz = mc == 0 ? 1 : (mc == 1 ? 2 : 4);
+    const int grid = mc == 2 ? 132 : 148;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 12 * 16384 + 512;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csz;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int stages_total = 2048;
+    cudaMemset(d_out, 0, 148 * sizeof(long long));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tma_bench, m16, m8, mc, ns, stages_total, rows, d_out);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e != cudaSuccess || e2 != cudaSuccess) { printf("tma mc %d FAILED: %s / %s\n", mc, cudaGetErrorString(e), cudaGetErrorString(e2)); return; }
+    std::vector<long long> h(grid);
+    cudaMemcpy(h.data(), d_out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    std::sort(h.begin(), h.end());
+    const double cyc = (double)h[grid / 2] / stages_total;
+    printf("tma ingest mc=%d ring=%2d stages: %.0f cycles per 16 KiB stage -> %.1f B/cycle/SM received (%d SMs)\n", mc, ns, cyc, 16384.0 / cyc, grid);
+}
+
 __global__ void __cluster_dims__(1, 1, 1) dummy_kernel(int* x) { if (x) *x = 1; }
 template <int CS>
 static void occupancy() {
@@ -393,6 +507,7 @@ static void occupancy() {
 int main() {
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_dsmem(0, d); run_dsmem(1, d); run_dsmem(2, d); cudaFree(d); }
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_ring(0, 4, d); run_ring(1, 4, d); run_ring(2, 4, d); run_ring(3, 4, d); run_ring(4, 4, d); cudaFree(d); }
+    { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); for (int mc = 0; mc < 3; ++mc) { run_tma(mc, 4, d); run_tma(mc, 8, d); run_tma(mc, 12, d); } cudaFree(d); }
     occupancy<2>();
     occupancy<4>();
     occupancy<8>();
