@@ -375,7 +375,7 @@ static void run_ring(int pat, int ns, long long* d_out) {
 //   mc = 1: clusters of 2: each CTA fetches 8 KiB (64 rows) and multicasts it to both CTAs (each still receives 16 KiB)
 //   mc = 2: clusters of 4, pairs (0,2) and (1,3) share: each CTA fetches 8 KiB and multicasts to its partner and itself
 __global__ void __launch_bounds__(128, 1) tma_bench(const __grid_constant__ CUtensorMap map16, const __grid_constant__ CUtensorMap map8,
-                                                    int mc, int ns, int stages_total, int rows_total, long long* out) {
+                                                    int mc, int ns, int stages_total, int rows_total, long long* out, uint8_t* scratch, int st_every) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     const uint32_t sBar = base + 12 * 16384;
@@ -418,6 +418,13 @@ __global__ void __launch_bounds__(128, 1) tma_bench(const __grid_constant__ CUte
         const uint32_t partner = (mc == 1) ? (rank ^ 1) : (rank ^ 2);
         for (int g = 0; g < stages_total; ++g) {
             mbar_wait(full(st), ph);
+            if (st_every && (g % st_every) == 0) {
+                // send the stage back out to an L2-resident scratch (bulk store), wait until the source may be reused
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(scratch + ((size_t)cta * 4 + (g & 3)) * 16384), "r"(base + st * 16384), "r"(16384) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             if (mc) {
                 mbar_arrive(empty(st));
                 mbar_arrive_cluster(empty(st), partner);
@@ -432,7 +439,8 @@ __global__ void __launch_bounds__(128, 1) tma_bench(const __grid_constant__ CUte
     if (mc) cluster_sync_all();
 }
 
-static void run_tma(int mc, int ns, long long* d_out) {
+static uint8_t* g_scratch = nullptr;
+static void run_tma(int mc, int ns, long long* d_out, int st_every = 0) {
     typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -446,6 +454,7 @@ static void run_tma(int mc, int ns, long long* d_out) {
         enc = (PFN)ptr;
         cudaMalloc(&buf, (size_t)rows * cols * 2);
         cudaMemset(buf, 0, (size_t)rows * cols * 2);
+        cudaMalloc(&g_scratch, (size_t)148 * 4 * 16384);
     }
     CUtensorMap m16, m8;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -472,14 +481,14 @@ static void run_tma(int mc, int ns, long long* d_out) {
     cfg.numAttrs = 1;
     const int stages_total = 2048;
     cudaMemset(d_out, 0, 148 * sizeof(long long));
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tma_bench, m16, m8, mc, ns, stages_total, rows, d_out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tma_bench, m16, m8, mc, ns, stages_total, rows, d_out, g_scratch, st_every);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess) { printf("tma mc %d FAILED: %s / %s\n", mc, cudaGetErrorString(e), cudaGetErrorString(e2)); return; }
     std::vector<long long> h(grid);
     cudaMemcpy(h.data(), d_out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
     std::sort(h.begin(), h.end());
     const double cyc = (double)h[grid / 2] / stages_total;
-    printf("tma ingest mc=%d ring=%2d stages: %.0f cycles per 16 KiB stage -> %.1f B/cycle/SM received (%d SMs)\n", mc, ns, cyc, 16384.0 / cyc, grid);
+    printf("tma ingest mc=%d ring=%2d stages, bulk store of every %d-th stage: %.0f cycles per 16 KiB stage -> %.1f B/cycle/SM received (%d SMs)\n", mc, ns, st_every, cyc, 16384.0 / cyc, grid);
 }
 
 __global__ void __cluster_dims__(1, 1, 1) dummy_kernel(int* x) { if (x) *x = 1; }
@@ -507,7 +516,7 @@ static void occupancy() {
 int main() {
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_dsmem(0, d); run_dsmem(1, d); run_dsmem(2, d); cudaFree(d); }
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_ring(0, 4, d); run_ring(1, 4, d); run_ring(2, 4, d); run_ring(3, 4, d); run_ring(4, 4, d); cudaFree(d); }
-    { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); for (int mc = 0; mc < 3; ++mc) { run_tma(mc, 4, d); run_tma(mc, 8, d); run_tma(mc, 12, d); } cudaFree(d); }
+    { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_tma(0, 8, d); run_tma(0, 8, d, 2); run_tma(0, 8, d, 1); run_tma(1, 8, d); cudaFree(d); }
     occupancy<2>();
     occupancy<4>();
     occupancy<8>();

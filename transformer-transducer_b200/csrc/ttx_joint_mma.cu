@@ -621,23 +621,29 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
+    // FG / DA: persistent -- the grid is one CTA pair per SM pair and each pair walks work items (tile pair, slab) one
+    // after the other, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
+    // behind the read-out of G, and TMEM / barriers are set up once.  DW: one item per CTA pair (grid x, y, z).
+    constexpr bool PERSIST = (MODE != MODE_DW);
     int j0, j1;
-    bool valid_x = true;
+    int n_items = 1, item0 = 0, item_step = 1;
     if (MODE == MODE_DW) {
         const int n_st = (n_tiles + 1) / 2;
         const int per = (n_st + p.splits - 1) / p.splits;
         j0 = blockIdx.z * per;
         j1 = min(n_st, j0 + per);
     } else {
-        if ((int)(blockIdx.x & ~1u) >= n_tiles) return;
-        valid_x = (int)blockIdx.x < n_tiles;
+        n_items = ((n_tiles + 1) >> 1) * p.n_halves;
+        item0 = blockIdx.x >> 1;
+        item_step = gridDim.x >> 1;
+        if (item0 >= n_items) return;
         j0 = 0;
         j1 = (p.V + NT - 1) / NT;
     }
     if (j0 >= j1) return;
-    const int x_row0 = blockIdx.x * kTile;
-    const int half = blockIdx.y;
     const int n_iter = j1 - j0;
+    auto item_tile = [&](int item) { return PERSIST ? (item / p.n_halves) * 2 + (int)rank : (int)blockIdx.x; };
+    auto item_half = [&](int item) { return PERSIST ? item % p.n_halves : (int)blockIdx.y; };
     const int hh2 = p.HH / 2;               // G columns (N rows of the K-major B operand) held by this CTA
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -662,6 +668,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t bar_sfull = sBar + 8 * 33;
     const uint32_t bar_sempty = sBar + 8 * 34;
     const uint32_t bar_gfull = sBar + 8 * 35;
+    const uint32_t bar_xempty = sBar;                               // the item's last S pass has read the X tile
+    const uint32_t bar_gempty = sBar + 8 * 40;                      // the epilogue has read the item's G out of TMEM
     auto bar_pfull = [&](int b) { return sBar + 8 * (36 + b); };     // one barrier pair per P' sub-tile buffer
     auto bar_pempty = [&](int b) { return sBar + 8 * (36 + kPB + b); };
 
@@ -686,6 +694,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             mbar_init(bar_pempty(b), 1);
         }
         mbar_init(bar_gfull, 1);
+        mbar_init(bar_xempty, 1);
+        mbar_init(bar_gempty, 2 * kPairEpiWarps);
         fence_barrier_init();
     }
     if (warp == kPairMmaWarp) tmem_alloc_pair(sTmemPtr, kTmemCols);
@@ -707,11 +717,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
       if (warp == kPairProducerWarp) {
         // =========================================================== TMA producer
         if (lane == 0) {
-            // the stationary tile arrives chunk by chunk (own barrier each), so the first S pass starts after 16 KiB
-            for (int c = 0; c < p.NKC; ++c) {
-                if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
-                tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
-            }
             Ring r;
             auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
                 mbar_wait(bar_empty(r.stage), r.phase ^ 1);
@@ -723,15 +728,25 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             auto load_S = [&](int j) {
                 for (int c = 0; c < p.NKC; ++c) load_stage(&mapY, c * kKC, j * NT + (int)rank * SR, STAGE);
             };
-            auto load_G = [&](int j) {                 // K-major B chunks: [hh2 joint columns x 64 stream rows]
+            auto load_G = [&](int j, int half) {       // K-major B chunks: [hh2 joint columns x 64 stream rows]
                 const int h0 = half * p.HH + (int)rank * hh2;
                 for (int c = 0; c < 4; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
             };
-            // same order as the MMA issuer: S(i+1), then the four G sub-passes of tile i
-            load_S(j0);
-            for (int i = 0; i < n_iter; ++i) {
-                if (i + 1 < n_iter) load_S(j0 + i + 1);
-                load_G(j0 + i);
+            int it = 0;
+            for (int item = item0; item < n_items; item += item_step, ++it) {
+                const int x_row0 = item_tile(item) * kTile, half = item_half(item);
+                // the stationary tile arrives chunk by chunk (own barrier each), so the first S pass starts after 16 KiB
+                if (it > 0) mbar_wait(bar_xempty, (it - 1) & 1);
+                for (int c = 0; c < p.NKC; ++c) {
+                    if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
+                    tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
+                }
+                // same order as the MMA issuer: S(i+1), then the four G sub-passes of tile i
+                load_S(j0);
+                for (int i = 0; i < n_iter; ++i) {
+                    if (i + 1 < n_iter) load_S(j0 + i + 1);
+                    load_G(j0 + i, half);
+                }
             }
         }
       } else if (warp == kPairWatchWarp) {
@@ -747,18 +762,21 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             Ring r;
             PRing pr;
             auto publish = [&]() { *ready = ++done; };
+            int it = 0, gs = 0;                                 // items done, S passes watched (all items)
             auto watch_S = [&](int idx) {
-                mbar_wait(bar_sempty, (idx & 1) ^ 1);
+                mbar_wait(bar_sempty, (gs & 1) ^ 1);
                 publish();
                 for (int c = 0; c < p.NKC; ++c) {
-                    if (idx == 0) mbar_wait(bar_xfull(c), 0);
+                    if (idx == 0) mbar_wait(bar_xfull(c), it & 1);
                     mbar_wait(bar_full(r.stage), r.phase);
                     publish();
                     r.advance(p.NS);
                 }
+                ++gs;
             };
-            auto watch_G = [&]() {
+            auto watch_G = [&](int i) {
                 for (int sp = 0; sp < 4; ++sp) {
+                    if (i == 0 && sp == 0 && it > 0) mbar_wait(bar_gempty, (it - 1) & 1);   // previous item's G was read out
                     mbar_wait(bar_pfull(pr.buf), pr.phase);
                     mbar_wait(bar_full(r.stage), r.phase);
                     publish();
@@ -766,10 +784,12 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     pr.advance();
                 }
             };
-            watch_S(0);
-            for (int i = 0; i < n_iter; ++i) {
-                if (i + 1 < n_iter) watch_S(i + 1);
-                watch_G();
+            for (int item = item0; item < n_items; item += item_step, ++it) {
+                watch_S(0);
+                for (int i = 0; i < n_iter; ++i) {
+                    if (i + 1 < n_iter) watch_S(i + 1);
+                    watch_G(i);
+                }
             }
         }
       } else if (warp == kPairMmaWarp) {
@@ -810,6 +830,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     umma_commit_pair(bar_empty(stage));
                     if (++stage == p.NS) stage = 0;
                 }
+                if (idx == n_iter - 1) umma_commit_pair(bar_xempty);    // the X tile may be replaced by the next item's
                 umma_commit_pair(bar_sfull);
             };
             int pb = 0;                                         // P' sub-tile ring: sub-pass n uses buffer n % kPB
@@ -826,15 +847,17 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     if (++pb == kPB) pb = 0;
                 }
             };
-            issue_S(0);
-            for (int i = 0; i < n_iter; ++i) {
-                trace_at(p, 1, i, 0);
-                if (i + 1 < n_iter) issue_S(i + 1);
-                trace_at(p, 1, i, 1);
-                issue_G(i);
-                trace_at(p, 1, i, 3);
+            for (int item = item0; item < n_items; item += item_step) {
+                issue_S(0);
+                for (int i = 0; i < n_iter; ++i) {
+                    trace_at(p, 1, i, 0);
+                    if (i + 1 < n_iter) issue_S(i + 1);
+                    trace_at(p, 1, i, 1);
+                    issue_G(i);
+                    trace_at(p, 1, i, 3);
+                }
+                umma_commit_pair(bar_gfull);
             }
-            umma_commit_pair(bar_gfull);
         }
       }
     } else {
@@ -902,6 +925,11 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             if (et == 0) trace_at(p, 2, i, 3);
             pr = r;
         };
+        int it = 0;
+        for (int item = item0; item < n_items; item += item_step, ++it) {
+        const int x_row0 = item_tile(item) * kTile, half = item_half(item);
+        const bool valid_x = !PERSIST || item_tile(item) < n_tiles;
+        const int gs0 = it * n_iter;                  // S passes of earlier items (accumulator barrier parity)
         if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
             // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
@@ -920,7 +948,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 float4 bpre[8];                               // bias of sub-tile 0, fetched while waiting for the S tile
 #pragma unroll
                 for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
-                mbar_wait(bar_sfull, i & 1);
+                mbar_wait(bar_sfull, (gs0 + i) & 1);
                 if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t acc[4][32];
@@ -1066,7 +1094,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
-            mbar_wait(bar_gfull, 0);
+            mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
             // combine the two column halves of each row through the (now idle) P' buffers
             float4* xch = reinterpret_cast<float4*>(sP_gen);
@@ -1074,6 +1102,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
             pair_epi_sync();
             const float4 o = xch[(ch ^ 1) * kTile + row];
+            pair_epi_sync();                              // (the next item's P' sub-tiles go into the same memory)
             const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
             if (ch == 0 && valid_x && half == 0) {
                 zb = ((p.blank & 63) < 32) ? zb : o.y;            // which column half owns the blank / label column
@@ -1126,7 +1155,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     kbuf[NT + et] = (cm.w < 0.f) ? -1.f : 1.f;
                     pair_epi_sync();
                 }
-                mbar_wait(bar_sfull, i & 1);
+                mbar_wait(bar_sfull, (gs0 + i) & 1);
                 if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 // Pull this thread's share of the S tile (4 sub-tiles x 32 columns) into registers and hand the single S
@@ -1203,7 +1232,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 }, i);
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global
-            mbar_wait(bar_gfull, 0);
+            mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
             const float gmax = p.scal[2];
             const int ngrp = p.HH / 32;
@@ -1241,6 +1270,11 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
                 if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
+        }
+        if (PERSIST) {                                // G has left TMEM: the next item may overwrite it
+            tc_fence_before();
+            epi_arrive(bar_gempty);
+        }
         }
     }
     tc_fence_before();
@@ -1944,6 +1978,18 @@ static bool v3_applicable(int H, const void* w16t, const void* a16t) {
 
 bool fwd_grad_supported_h(int H) { return H == 128 || H == 256 || H == 512; }
 
+// Persistent pair kernels (FG / DA): one CTA pair per SM pair, or fewer when there are fewer work items.
+static unsigned persistent_grid(int n_tiles_ub, int n_halves) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int items = ((n_tiles_ub + 1) / 2) * n_halves;
+    return 2u * (unsigned)max(1, min(items, sms / 2));
+}
+
 // ---- quad kernel (cluster of 4: S pair + G pair)
 // TTX_QUAD: 0 = pair kernel everywhere, 1 (default) = quad kernel for the weight gradient (measured 4.6 vs 5.0 ms at
 // cfg2), 2 = also for the activation gradient when it is a separate launch (no gain measured: 5.7 ms either way).
@@ -2049,7 +2095,7 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     const int hs = (p.dbg & 8) ? 2 : 1;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile / hs)) return rc;
     if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2 / hs)) return rc;
-    dim3 grid(n_tiles_ub, p.n_halves, 1);
+    dim3 grid(persistent_grid(n_tiles_ub, p.n_halves), 1, 1);
     int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
                   : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
     if (rc == 0) trace_dump("FG", stream);
@@ -2149,7 +2195,7 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
             if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
             p.splits = 1;
-            dim3 grid(n_tiles_ub, p.n_halves, 1);
+            dim3 grid(persistent_grid(n_tiles_ub, p.n_halves), 1, 1);
             int rc = bf16 ? launch_v3<MODE_DA, true>(mx, my, myt, p, grid, smem, stream)
                           : launch_v3<MODE_DA, false>(mx, my, myt, p, grid, smem, stream);
             if (rc) return rc;
