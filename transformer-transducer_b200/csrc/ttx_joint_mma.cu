@@ -669,7 +669,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t bar_sempty = sBar + 8 * 34;
     const uint32_t bar_gfull = sBar + 8 * 35;
     const uint32_t bar_xempty = sBar;                               // the item's last S pass has read the X tile
-    const uint32_t bar_gempty = sBar + 8 * 40;                      // the epilogue has read the item's G out of TMEM
+    const uint32_t bar_gempty = sBar + 8 * 43;                      // the epilogue has read the item's G out of TMEM
     auto bar_pfull = [&](int b) { return sBar + 8 * (36 + b); };     // one barrier pair per P' sub-tile buffer
     auto bar_pempty = [&](int b) { return sBar + 8 * (36 + kPB + b); };
 
@@ -847,7 +847,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     if (++pb == kPB) pb = 0;
                 }
             };
-            for (int item = item0; item < n_items; item += item_step) {
+            int itt = 0;
+            for (int item = item0; item < n_items; item += item_step, ++itt) {
+                trace_at(p, 0, itt, 2);
                 issue_S(0);
                 for (int i = 0; i < n_iter; ++i) {
                     trace_at(p, 1, i, 0);
@@ -857,6 +859,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     trace_at(p, 1, i, 3);
                 }
                 umma_commit_pair(bar_gfull);
+                trace_at(p, 0, itt, 3);
             }
         }
       }
@@ -930,6 +933,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         const int x_row0 = item_tile(item) * kTile, half = item_half(item);
         const bool valid_x = !PERSIST || item_tile(item) < n_tiles;
         const int gs0 = it * n_iter;                  // S passes of earlier items (accumulator barrier parity)
+        if (et == 0) trace_at(p, 0, it, 0);
         if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
             // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
@@ -1275,6 +1279,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             tc_fence_before();
             epi_arrive(bar_gempty);
         }
+        if (et == 0) trace_at(p, 0, it, 1);
         }
     }
     tc_fence_before();
@@ -1899,7 +1904,7 @@ static void trace_dump(const char* what, cudaStream_t stream) {
     cudaMemset(buf, 0, sizeof(h));
     long long t0 = h[(1 * kTraceIters + 0) * 4 + 0];
     fprintf(stderr, "TRACE %s (cycles since first MMA-loop entry)\n", what);
-    fprintf(stderr, " it | epi sub-pass 1: entry voted packed pempty_ok | mma: loop S_issued (epi sp1 arrived) G_issued | epi: sfull S_released pempty(sp0) pfull(sp3)\n");
+    fprintf(stderr, " it | item it: epi start, epi end, mma start, mma end | tile it (last item): mma loop, S_issued, -, G_issued | epi: sfull, S_released, round A stored, all stored\n");
     for (int i = 0; i < 12; ++i) {
         fprintf(stderr, "%3d |", i);
         for (int r = 0; r < 3; ++r) {
