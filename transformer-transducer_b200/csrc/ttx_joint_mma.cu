@@ -43,6 +43,7 @@ struct MmaParams {
     float* dA;             // DA out (rows x H)
     float* dW;             // DW out (V x H), accumulated with red.add
     float* db;             // DW out (V)
+    uint8_t* scratch;      // pair kernel, forward+gradient: per-pair flags + P' scratch matrix (replay), or null
 };
 
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
@@ -614,7 +615,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 template <int MODE, bool BF16>
 __global__ void __launch_bounds__(kPairThreads, 1)
 joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
-                      const __grid_constant__ CUtensorMap mapYT, const MmaParams p) {
+                      const __grid_constant__ CUtensorMap mapYT, const __grid_constant__ CUtensorMap mapScr,
+                      const MmaParams p) {
     constexpr int NT = 256;                 // stream rows per step (pair-wide) = S accumulator columns
     constexpr int SR = 128;                 // stream rows this CTA loads per S chunk
     constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
@@ -626,24 +628,37 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     // behind the read-out of G, and TMEM / barriers are set up once.  DW: one item per CTA pair (grid x, y, z).
     constexpr bool PERSIST = (MODE != MODE_DW);
     int j0, j1;
-    int n_items = 1, item0 = 0, item_step = 1;
+    int n_units = 1, unit0 = 0, unit_step = 1;        // persistent modes: a unit = one tile pair, all its slabs in turn
     if (MODE == MODE_DW) {
         const int n_st = (n_tiles + 1) / 2;
         const int per = (n_st + p.splits - 1) / p.splits;
         j0 = blockIdx.z * per;
         j1 = min(n_st, j0 + per);
     } else {
-        n_items = ((n_tiles + 1) >> 1) * p.n_halves;
-        item0 = blockIdx.x >> 1;
-        item_step = gridDim.x >> 1;
-        if (item0 >= n_items) return;
+        n_units = (n_tiles + 1) >> 1;
+        unit0 = blockIdx.x >> 1;
+        unit_step = gridDim.x >> 1;
+        if (unit0 >= n_units) return;
         j0 = 0;
         j1 = (p.V + NT - 1) / NT;
     }
     if (j0 >= j1) return;
     const int n_iter = j1 - j0;
-    auto item_tile = [&](int item) { return PERSIST ? (item / p.n_halves) * 2 + (int)rank : (int)blockIdx.x; };
-    auto item_half = [&](int item) { return PERSIST ? item % p.n_halves : (int)blockIdx.y; };
+    const int n_hl = PERSIST ? p.n_halves : 1;        // slabs per unit handled by this pair
+    auto unit_tile = [&](int unit) { return PERSIST ? unit * 2 + (int)rank : (int)blockIdx.x; };
+    auto slab_of = [&](int hh) { return PERSIST ? hh : (int)blockIdx.y; };
+    // Forward+gradient with a scratch area (REPLAY): the first slab of a unit also sends every P' sub-tile to a scratch
+    // matrix in global memory (TMA store from the shared-memory buffer the G sub-pass reads); the second slab then
+    // needs neither S passes nor exponentials -- it streams P' back as the A operand next to the W16^T chunks.  If the
+    // running reference moved after the unit's first tile (rare), the stored sub-tiles carry mixed scales: the unit is
+    // flagged and its second slab recomputes everything as without the scratch area.
+    const bool rp = (MODE == MODE_FG) && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 && p.NKC + kPB <= 12;
+    // The replay streams two operands and touches neither the X tile nor the P' buffers: their shared memory (contiguous,
+    // 10 x 16 KiB) is its ring, with its own barriers (slots kRB.. of the full / empty arrays) and its own position.
+    constexpr int kRB = 4;                            // first barrier slot of the replay ring (the S / G ring uses < 4)
+    const int nrs = p.NKC + kPB;                      // replay ring stages
+    volatile int* const dirty = rp ? reinterpret_cast<volatile int*>(p.scratch) + (blockIdx.x >> 1) : nullptr;
+    const int scr_row0 = (int)blockIdx.x * kTile;     // this CTA's 128 rows of the scratch matrix
     const int hh2 = p.HH / 2;               // G columns (N rows of the K-major B operand) held by this CTA
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -672,6 +687,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t bar_gempty = sBar + 8 * 43;                      // the epilogue has read the item's G out of TMEM
     auto bar_pfull = [&](int b) { return sBar + 8 * (36 + b); };     // one barrier pair per P' sub-tile buffer
     auto bar_pempty = [&](int b) { return sBar + 8 * (36 + kPB + b); };
+    static_assert(kPB == 2, "barrier slots 40..42 are used below");
+    auto bar_pwritten = [&](int b) { return sBar + 8 * (40 + b); };  // REPLAY: this CTA's epilogue warps wrote buffer b
+    const uint32_t bar_unit = sBar + 8 * 42;                         // REPLAY: first slab of the unit is complete
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -681,9 +699,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapYT);
+        tma_prefetch_desc(&mapScr);
         for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
         *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
-        for (int s = 0; s < p.NS; ++s) {
+        for (int s = 0; s < 16; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
         }
@@ -691,8 +710,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         mbar_init(bar_sempty, 2 * kPairEpiWarps);       // every epilogue warp of both CTAs
         for (int b = 0; b < kPB; ++b) {
             mbar_init(bar_pfull(b), 2 * kPairEpiWarps);  // every epilogue warp of both CTAs, once per sub-pass
-            mbar_init(bar_pempty(b), 1);
+            mbar_init(bar_pempty(b), rp ? 2 : 1);        // the G sub-pass (and the store to the scratch area) have read it
+            mbar_init(bar_pwritten(b), kPairEpiWarps);
         }
+        mbar_init(bar_unit, 2 * kPairEpiWarps + 1);      // every epilogue warp of both CTAs + this CTA's storer
         mbar_init(bar_gfull, 1);
         mbar_init(bar_xempty, 1);
         mbar_init(bar_gempty, 2 * kPairEpiWarps);
@@ -732,20 +753,85 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 const int h0 = half * p.HH + (int)rank * hh2;
                 for (int c = 0; c < 4; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
             };
-            int it = 0;
-            for (int item = item0; item < n_items; item += item_step, ++it) {
-                const int x_row0 = item_tile(item) * kTile, half = item_half(item);
-                // the stationary tile arrives chunk by chunk (own barrier each), so the first S pass starts after 16 KiB
-                if (it > 0) mbar_wait(bar_xempty, (it - 1) & 1);
-                for (int c = 0; c < p.NKC; ++c) {
-                    if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
-                    tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
+            int xt = 0, uidx = 0, it = 0;                       // X tiles loaded, units started, items started
+            Ring rr;                                            // replay ring position
+            bool replayed = false;                              // the previous item was a replay (its ring is our X tile)
+            for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                for (int hh = 0; hh < n_hl; ++hh, ++it) {
+                    const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
+                    if (rp && hh == 1) {
+                        mbar_wait(bar_unit, uidx & 1);
+                        if (*dirty != uidx + 1) {
+                            // replay: per sub-pass one stage of P' (A operand, from the scratch matrix) and one of W16^T;
+                            // the ring is the X tile + P' buffers, free once the first slab's last S pass / G sub-pass
+                            // have read them (xempty; the epilogue's unit arrival came after its last pempty wait)
+                            const int h0 = half * p.HH + (int)rank * hh2;
+                            mbar_wait(bar_xempty, (xt - 1) & 1);
+                            auto load_rstage = [&](const CUtensorMap* map, int col, int row, int bytes) {
+                                mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
+                                if (leader) mbar_arrive_expect_tx(bar_full(kRB + rr.stage), 2 * bytes);
+                                tma_load_2d_pair(sX + rr.stage * STAGE, map, bar_full(kRB + rr.stage), col, row);
+                                rr.advance(nrs);
+                            };
+                            for (int i = 0; i < n_iter; ++i)
+                                for (int c = 0; c < 4; ++c) {
+                                    load_rstage(&mapScr, (i * 4 + c) * kKC, scr_row0, STAGE);
+                                    load_rstage(&mapYT, (j0 + i) * NT + c * kKC, h0, hh2 * 128);
+                                }
+                            replayed = true;
+                            continue;
+                        }
+                    }
+                    // the stationary tile arrives chunk by chunk (own barrier each): the first S pass starts after 16 KiB
+                    if (xt > 0) mbar_wait(bar_xempty, (xt - 1) & 1);
+                    if (replayed) {                             // ... and the replay's MMAs have read the ring stages there
+                        mbar_wait(bar_gfull, (it - 1) & 1);
+                        replayed = false;
+                    }
+                    ++xt;
+                    for (int c = 0; c < p.NKC; ++c) {
+                        if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
+                        tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
+                    }
+                    // same order as the MMA issuer: S(i+1), then the four G sub-passes of tile i
+                    load_S(j0);
+                    for (int i = 0; i < n_iter; ++i) {
+                        if (i + 1 < n_iter) load_S(j0 + i + 1);
+                        load_G(j0 + i, half);
+                    }
                 }
-                // same order as the MMA issuer: S(i+1), then the four G sub-passes of tile i
-                load_S(j0);
-                for (int i = 0; i < n_iter; ++i) {
-                    if (i + 1 < n_iter) load_S(j0 + i + 1);
-                    load_G(j0 + i, half);
+            }
+        }
+      } else if (warp == kPairWatchWarp + 1) {
+        // =========================================================== REPLAY: storer (each CTA): P' sub-tile -> scratch
+        if (lane == 0 && rp) {
+            PRing sr;
+            int uidx = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                for (int hh = 0; hh < n_hl; ++hh) {
+                    if (hh == 1) {
+                        mbar_wait(bar_unit, uidx & 1);
+                        if (*dirty != uidx + 1) continue;
+                    }
+                    for (int i = 0; i < n_iter; ++i)
+                        for (int c = 0; c < 4; ++c) {
+                            mbar_wait(bar_pwritten(sr.buf), sr.phase);
+                            if (hh == 0) {
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                             ::"l"(reinterpret_cast<uint64_t>(&mapScr)), "r"(sP + sr.buf * kChunkBytes),
+                                               "r"((i * 4 + c) * kKC), "r"(scr_row0)
+                                             : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            }
+                            mbar_arrive(bar_pempty(sr.buf));
+                            sr.advance();
+                        }
+                    if (hh == 0) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores are complete: replay may load
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        mbar_arrive(bar_unit);
+                    }
                 }
             }
         }
@@ -762,12 +848,13 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             Ring r;
             PRing pr;
             auto publish = [&]() { *ready = ++done; };
-            int it = 0, gs = 0;                                 // items done, S passes watched (all items)
+            int it = 0, gs = 0, xt = 0;                         // items done, S passes watched, X tiles loaded
+            Ring rr;                                            // replay ring position
             auto watch_S = [&](int idx) {
                 mbar_wait(bar_sempty, (gs & 1) ^ 1);
                 publish();
                 for (int c = 0; c < p.NKC; ++c) {
-                    if (idx == 0) mbar_wait(bar_xfull(c), it & 1);
+                    if (idx == 0) mbar_wait(bar_xfull(c), xt & 1);
                     mbar_wait(bar_full(r.stage), r.phase);
                     publish();
                     r.advance(p.NS);
@@ -784,11 +871,30 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     pr.advance();
                 }
             };
-            for (int item = item0; item < n_items; item += item_step, ++it) {
-                watch_S(0);
-                for (int i = 0; i < n_iter; ++i) {
-                    if (i + 1 < n_iter) watch_S(i + 1);
-                    watch_G(i);
+            int uidx = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                for (int hh = 0; hh < n_hl; ++hh, ++it) {
+                    if (rp && hh == 1) {
+                        mbar_wait(bar_unit, uidx & 1);
+                        if (*dirty != uidx + 1) {
+                            for (int i = 0; i < n_iter; ++i)
+                                for (int c = 0; c < 4; ++c) {
+                                    if (i == 0 && c == 0) mbar_wait(bar_gempty, (it - 1) & 1);
+                                    mbar_wait(bar_full(kRB + rr.stage), rr.phase);
+                                    rr.advance(nrs);
+                                    mbar_wait(bar_full(kRB + rr.stage), rr.phase);
+                                    rr.advance(nrs);
+                                    publish();
+                                }
+                            continue;
+                        }
+                    }
+                    watch_S(0);
+                    for (int i = 0; i < n_iter; ++i) {
+                        if (i + 1 < n_iter) watch_S(i + 1);
+                        watch_G(i);
+                    }
+                    ++xt;
                 }
             }
         }
@@ -847,19 +953,43 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     if (++pb == kPB) pb = 0;
                 }
             };
-            int itt = 0;
-            for (int item = item0; item < n_items; item += item_step, ++itt) {
-                trace_at(p, 0, itt, 2);
-                issue_S(0);
-                for (int i = 0; i < n_iter; ++i) {
-                    trace_at(p, 1, i, 0);
-                    if (i + 1 < n_iter) issue_S(i + 1);
-                    trace_at(p, 1, i, 1);
-                    issue_G(i);
-                    trace_at(p, 1, i, 3);
+            int itt = 0, uidx = 0, rstage = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                for (int hh = 0; hh < n_hl; ++hh, ++itt) {
+                    trace_at(p, 0, itt, 2);
+                    bool replay = false;
+                    if (rp && hh == 1) {
+                        mbar_wait(bar_unit, uidx & 1);
+                        replay = (*dirty != uidx + 1);
+                    }
+                    if (replay) {
+                        // G(slab 1) += P'(i, c) . W16^T chunk, both operands from consecutive ring stages
+                        for (int i = 0; i < n_iter; ++i)
+                            for (int c = 0; c < 4; ++c) {
+                                wait_event();
+                                tc_fence_after();
+                                const int s2 = (rstage + 1 == nrs) ? 0 : rstage + 1;
+                                const uint32_t a = xlo + rstage * 1024, b = xlo + s2 * 1024;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ss_pair_lo(tmem_G, a + 2 * k, b + 2 * k, idescG, (i | c | k) != 0);
+                                umma_commit_pair(bar_empty(kRB + rstage));
+                                umma_commit_pair(bar_empty(kRB + s2));
+                                rstage = (s2 + 1 == nrs) ? 0 : s2 + 1;
+                            }
+                    } else {
+                        issue_S(0);
+                        for (int i = 0; i < n_iter; ++i) {
+                            trace_at(p, 1, i, 0);
+                            if (i + 1 < n_iter) issue_S(i + 1);
+                            trace_at(p, 1, i, 1);
+                            issue_G(i);
+                            trace_at(p, 1, i, 3);
+                        }
+                    }
+                    umma_commit_pair(bar_gfull);
+                    trace_at(p, 0, itt, 3);
                 }
-                umma_commit_pair(bar_gfull);
-                trace_at(p, 0, itt, 3);
             }
         }
       }
@@ -912,7 +1042,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             patch(0, kPB, dst);
             fence_proxy_async_smem();
 #pragma unroll
-            for (int g = 0; g < kPB; ++g) epi_arrive(bar_pfull(bufs[g]));
+            for (int g = 0; g < kPB; ++g) {
+                epi_arrive(bar_pfull(bufs[g]));
+                if (rp && lane == 0) mbar_arrive(bar_pwritten(bufs[g]));
+            }
             // later rounds: one sub-tile each, as this tile's own G sub-passes release the buffers
 #pragma unroll
             for (int g = kPB; g < 4; ++g) {
@@ -924,15 +1057,22 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 patch(g, g + 1, dst);
                 fence_proxy_async_smem();
                 epi_arrive(bar_pfull(bufs[g]));
+                if (rp && lane == 0) mbar_arrive(bar_pwritten(bufs[g]));
             }
             if (et == 0) trace_at(p, 2, i, 3);
             pr = r;
         };
-        int it = 0;
-        for (int item = item0; item < n_items; item += item_step, ++it) {
-        const int x_row0 = item_tile(item) * kTile, half = item_half(item);
-        const bool valid_x = !PERSIST || item_tile(item) < n_tiles;
-        const int gs0 = it * n_iter;                  // S passes of earlier items (accumulator barrier parity)
+        int it = 0, gs0 = 0, uidx = 0;                // items, S passes (accumulator barrier parity), units so far
+        float f_keep = 0.f;                           // REPLAY: the row's output scale, from the unit's first slab
+        for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+        for (int hh = 0; hh < n_hl; ++hh, ++it) {
+        const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
+        const bool valid_x = !PERSIST || unit_tile(unit) < n_tiles;
+        bool replay = false;
+        if (rp && hh == 1) {
+            mbar_wait(bar_unit, uidx & 1);
+            replay = (*dirty != uidx + 1);
+        }
         if (et == 0) trace_at(p, 0, it, 0);
         if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
@@ -946,7 +1086,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;     // mref: finite start, fixed by the first tile
             float* xg = kbuf;                                      // [2 column halves][128] row maxima (rare path)
             const int ngrp = p.HH / 32;
-            for (int i = 0; i < n_iter; ++i) {
+            for (int i = 0; i < (replay ? 0 : n_iter); ++i) {
                 const int t0 = (j0 + i) * NT;
                 const float* bias_t = p.bias2 + t0 + ch * 32;
                 float4 bpre[8];                               // bias of sub-tile 0, fetched while waiting for the S tile
@@ -1031,6 +1171,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                     float part = p0 + p1;
                     if (quarter_any(q, lmax > lg_scale + 3.f)) {
+                        if (rp && hh == 0) *dirty = uidx + 1;     // stored sub-tiles now carry mixed scales: no replay
                         xg[ch * kTile + row] = lmax;
                         quarter_sync(q);
                         const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
@@ -1098,24 +1239,28 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
+            if (!replay) gs0 += n_iter;
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
-            // combine the two column halves of each row through the (now idle) P' buffers
-            float4* xch = reinterpret_cast<float4*>(sP_gen);
-            pair_epi_sync();
-            xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
-            pair_epi_sync();
-            const float4 o = xch[(ch ^ 1) * kTile + row];
-            pair_epi_sync();                              // (the next item's P' sub-tiles go into the same memory)
-            const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
-            if (ch == 0 && valid_x && half == 0) {
-                zb = ((p.blank & 63) < 32) ? zb : o.y;            // which column half owns the blank / label column
-                if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
-                p.lse[grow] = lse2 * kLn2;
-                p.lpb[grow] = (zb - lse2) * kLn2;
-                p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+            if (!replay) {
+                // combine the two column halves of each row through the (now idle) P' buffers
+                float4* xch = reinterpret_cast<float4*>(sP_gen);
+                pair_epi_sync();
+                xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
+                pair_epi_sync();
+                const float4 o = xch[(ch ^ 1) * kTile + row];
+                pair_epi_sync();                          // (the next item's P' sub-tiles go into the same memory)
+                const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
+                if (ch == 0 && valid_x && half == 0) {
+                    zb = ((p.blank & 63) < 32) ? zb : o.y;        // which column half owns the blank / label column
+                    if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
+                    p.lse[grow] = lse2 * kLn2;
+                    p.lpb[grow] = (zb - lse2) * kLn2;
+                    p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+                }
+                f_keep = ex2f(mref - lg_scale - lse2) * inv_ws;
             }
-            const float f = ex2f(mref - lg_scale - lse2) * inv_ws;
+            const float f = f_keep;
             float* dst = p.dA + (size_t)grow * p.H + half * p.HH;
             uint32_t gacc[32];
             for (int cc = ch; cc < ngrp; cc += 2) {
@@ -1235,6 +1380,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
+            gs0 += n_iter;
             // ---- final: G (128 x HH fp32 in TMEM) -> global
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
@@ -1279,7 +1425,16 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             tc_fence_before();
             epi_arrive(bar_gempty);
         }
+        if (rp && hh == 0) {                          // first slab done in this warp (flag writes included)
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_unit);
+                mbar_arrive_cluster(bar_unit, rank ^ 1);
+            }
+        }
         if (et == 0) trace_at(p, 0, it, 1);
+        }
         }
     }
     tc_fence_before();
@@ -1952,7 +2107,7 @@ int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
 
 template <int MODE, bool BF16>
 static int launch_v3(const CUtensorMap& mx, const CUtensorMap& my, const CUtensorMap& myt, const MmaParams& p,
-                     dim3 grid, size_t smem, cudaStream_t stream) {
+                     dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap* mscr = nullptr) {
     auto kern = joint_bwd_pair_kernel<MODE, BF16>;
     TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     cudaLaunchConfig_t cfg{};
@@ -1968,7 +2123,7 @@ static int launch_v3(const CUtensorMap& mx, const CUtensorMap& my, const CUtenso
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, myt, p));
+    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, myt, mscr ? *mscr : mx, p));
     return 0;
 }
 
@@ -2101,8 +2256,39 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile / hs)) return rc;
     if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2 / hs)) return rc;
     dim3 grid(persistent_grid(n_tiles_ub, p.n_halves), 1, 1);
-    int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream)
-                  : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream);
+    // P' replay (H = 512): scratch = 64 KiB of per-pair flags + a 16-bit matrix of 128 rows per CTA x Vpad columns that
+    // holds the P' of the unit a CTA pair is working on (165 MB on a B200, whatever the problem size); stream-ordered
+    // allocation, nothing is kept between calls.  TTX_REPLAY=0 recomputes the second slab instead.
+    const char* re = getenv("TTX_REPLAY");
+    void* scratch = nullptr;
+    CUtensorMap mscr;
+    if (p.n_halves == 2 && !(re && re[0] == '0')) {
+        const int n_chunks = (V + 255) / 256;
+        const size_t bytes = 65536 + (size_t)grid.x * kTile * n_chunks * 256 * 2;
+        {
+            // keep freed blocks in the device's default pool between steps (the default returns them to the driver at every
+            // synchronisation, which makes a 165 MB stream-ordered allocation per step cost milliseconds)
+            static bool pool_tuned[64];
+            int dev = 0;
+            TTX_CUDA_OK(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
+                cudaMemPool_t pool;
+                uint64_t keep = ~0ull;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                pool_tuned[dev] = true;
+            }
+        }
+        TTX_CUDA_OK(cudaMallocAsync(&scratch, bytes, stream));
+        TTX_CUDA_OK(cudaMemsetAsync(scratch, 0, 65536, stream));
+        if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
+                                     (uint64_t)n_chunks * 256, bf16, kTile))
+            return rc;
+        p.scratch = static_cast<uint8_t*>(scratch);
+    }
+    int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr)
+                  : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr);
+    if (scratch) TTX_CUDA_OK(cudaFreeAsync(scratch, stream));
     if (rc == 0) trace_dump("FG", stream);
     return rc;
 }
