@@ -283,12 +283,12 @@ def test_c_abi_rejects_unsupported_width_with_message():
 
 
 @pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"}, {"TTX_QUAD": "0"},
-                                 {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"}, {}])
+                                 {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"}, {"TTX_REPLAY": "0"}, {}])
 def test_kernel_variants_agree_with_oracle(env, monkeypatch):
     """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
     kernel (TTX_NO_FWD_GRAD=1), the pair kernel for the weight gradient (TTX_QUAD=0), the quad kernel for both gradients
-    (TTX_QUAD=2) and the default kernels (fused forward+gradient pair kernel, quad kernel for the weight gradient) all
-    meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair / quad)."""
+    (TTX_QUAD=2), the forward+gradient kernel without its P' replay (TTX_REPLAY=0) and the default kernels (persistent
+    forward+gradient pair kernel with replay, quad kernel for the weight gradient) all meet the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last pair / quad)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)
