@@ -623,36 +623,41 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
-    // FG / DA: persistent -- the grid is one CTA pair per SM pair and each pair walks work items (tile pair, slab) one
-    // after the other, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
-    // behind the read-out of G, and TMEM / barriers are set up once.  DW: one item per CTA pair (grid x, y, z).
-    constexpr bool PERSIST = (MODE != MODE_DW);
-    int j0, j1;
-    int n_units = 1, unit0 = 0, unit_step = 1;        // persistent modes: a unit = one tile pair, all its slabs in turn
+    // Persistent: the grid is one CTA pair per SM pair and each pair walks work units one after the other, all slabs of
+    // a unit in turn, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
+    // behind the read-out of G, and TMEM / barriers are set up once.  FG / DA: unit = tile pair, streams the whole
+    // vocabulary.  DW: unit = (vocabulary tile pair, lattice-row split), consecutive units share the split.
+    constexpr bool PERSIST = true;
+    int j0 = 0, n_iter = 0;                           // the unit's stream chunks [j0, j0 + n_iter)
+    int n_units, n_vq = 1, per = 0, n_st = 0;
+    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
     if (MODE == MODE_DW) {
-        const int n_st = (n_tiles + 1) / 2;
-        const int per = (n_st + p.splits - 1) / p.splits;
-        j0 = blockIdx.z * per;
-        j1 = min(n_st, j0 + per);
+        n_st = (n_tiles + 1) / 2;
+        per = (n_st + p.splits - 1) / p.splits;
+        n_vq = ((p.V + kTile - 1) / kTile + 1) / 2;
+        n_units = n_vq * p.splits;
     } else {
         n_units = (n_tiles + 1) >> 1;
-        unit0 = blockIdx.x >> 1;
-        unit_step = gridDim.x >> 1;
-        if (unit0 >= n_units) return;
-        j0 = 0;
-        j1 = (p.V + NT - 1) / NT;
+        n_iter = (p.V + NT - 1) / NT;
     }
-    if (j0 >= j1) return;
-    const int n_iter = j1 - j0;
-    const int n_hl = PERSIST ? p.n_halves : 1;        // slabs per unit handled by this pair
-    auto unit_tile = [&](int unit) { return PERSIST ? unit * 2 + (int)rank : (int)blockIdx.x; };
-    auto slab_of = [&](int hh) { return PERSIST ? hh : (int)blockIdx.y; };
+    if (unit0 >= n_units) return;
+    // every role calls this at the top of its unit loop; false = no work left (empty trailing splits)
+    auto begin_unit = [&](int unit) {
+        if (MODE == MODE_DW) {
+            j0 = (unit / n_vq) * per;
+            n_iter = min(n_st, j0 + per) - j0;
+        }
+        return n_iter > 0;
+    };
+    const int n_hl = p.n_halves;                      // slabs per unit
+    auto unit_tile = [&](int unit) { return (MODE == MODE_DW ? (unit % n_vq) * 2 : unit * 2) + (int)rank; };
+    auto slab_of = [&](int hh) { return hh; };
     // Forward+gradient with a scratch area (REPLAY): the first slab of a unit also sends every P' sub-tile to a scratch
     // matrix in global memory (TMA store from the shared-memory buffer the G sub-pass reads); the second slab then
     // needs neither S passes nor exponentials -- it streams P' back as the A operand next to the W16^T chunks.  If the
     // running reference moved after the unit's first tile (rare), the stored sub-tiles carry mixed scales: the unit is
     // flagged and its second slab recomputes everything as without the scratch area.
-    const bool rp = (MODE == MODE_FG) && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 && p.NKC + kPB <= 12;
+    const bool rp = (MODE == MODE_FG || MODE == MODE_DW) && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 && p.NKC + kPB <= 12;
     // The replay streams two operands and touches neither the X tile nor the P' buffers: their shared memory (contiguous,
     // 10 x 16 KiB) is its ring, with its own barriers (slots kRB.. of the full / empty arrays) and its own position.
     constexpr int kRB = 4;                            // first barrier slot of the replay ring (the S / G ring uses < 4)
@@ -757,6 +762,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             Ring rr;                                            // replay ring position
             bool replayed = false;                              // the previous item was a replay (its ring is our X tile)
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
                     const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
                     if (rp && hh == 1) {
@@ -808,6 +814,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             PRing sr;
             int uidx = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh) {
                     if (hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
@@ -873,6 +880,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             };
             int uidx = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
                     if (rp && hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
@@ -955,6 +963,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             };
             int itt = 0, uidx = 0, rstage = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+                if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++itt) {
                     trace_at(p, 0, itt, 2);
                     bool replay = false;
@@ -1065,9 +1074,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         int it = 0, gs0 = 0, uidx = 0;                // items, S passes (accumulator barrier parity), units so far
         float f_keep = 0.f;                           // REPLAY: the row's output scale, from the unit's first slab
         for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
+        if (!begin_unit(unit)) break;
         for (int hh = 0; hh < n_hl; ++hh, ++it) {
         const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
-        const bool valid_x = !PERSIST || unit_tile(unit) < n_tiles;
+        const bool valid_x = MODE == MODE_DW || unit_tile(unit) < n_tiles;
         bool replay = false;
         if (rp && hh == 1) {
             mbar_wait(bar_unit, uidx & 1);
@@ -1290,7 +1300,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 vrow = x_row0 + row;
                 krow = __ldg(p.bias2 + vrow);
             }
-            for (int i = 0; i < n_iter; ++i) {
+            for (int i = 0; i < (replay ? 0 : n_iter); ++i) {
                 const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
                 float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
                 int clabel = -1;
@@ -1380,7 +1390,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
-            gs0 += n_iter;
+            if (!replay) gs0 += n_iter;
             // ---- final: G (128 x HH fp32 in TMEM) -> global
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
@@ -1418,7 +1428,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }
                 // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
-                if (ok && half == 0) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+                if (ok && half == 0 && !replay) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
         }
         if (PERSIST) {                                // G has left TMEM: the next item may overwrite it
@@ -2138,24 +2148,54 @@ static bool v3_applicable(int H, const void* w16t, const void* a16t) {
 
 bool fwd_grad_supported_h(int H) { return H == 128 || H == 256 || H == 512; }
 
-// Persistent pair kernels (FG / DA): one CTA pair per SM pair, or fewer when there are fewer work items.
-static unsigned persistent_grid(int n_tiles_ub, int n_halves) {
+static int sm_count() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
+    return sms;
+}
+
+// Persistent pair kernels: one CTA pair per SM pair, or fewer when there are fewer work items.
+static unsigned persistent_grid(int n_tiles_ub, int n_halves) {
     const int items = ((n_tiles_ub + 1) / 2) * n_halves;
-    return 2u * (unsigned)max(1, min(items, sms / 2));
+    return 2u * (unsigned)max(1, min(items, sm_count() / 2));
+}
+
+// P' replay scratch (pair kernel, H = 512): 64 KiB of per-pair flags (zeroed) + a 16-bit matrix of 128 rows per CTA.
+// Stream-ordered allocation, nothing is kept between calls.  TTX_REPLAY=0 recomputes the second slab instead.
+static bool replay_enabled() {
+    const char* re = getenv("TTX_REPLAY");
+    return !(re && re[0] == '0');
+}
+
+static int alloc_scratch(void** scratch, size_t bytes, cudaStream_t stream) {
+    // keep freed blocks in the device's default pool between steps (the default returns them to the driver at every
+    // synchronisation, which makes a 165 MB stream-ordered allocation per step cost milliseconds)
+    static bool pool_tuned[64];
+    int dev = 0;
+    TTX_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
+        cudaMemPool_t pool;
+        uint64_t keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_tuned[dev] = true;
+    }
+    TTX_CUDA_OK(cudaMallocAsync(scratch, bytes, stream));
+    TTX_CUDA_OK(cudaMemsetAsync(*scratch, 0, 65536, stream));
+    return 0;
 }
 
 // ---- quad kernel (cluster of 4: S pair + G pair)
-// TTX_QUAD: 0 = pair kernel everywhere, 1 (default) = quad kernel for the weight gradient (measured 4.6 vs 5.0 ms at
-// cfg2), 2 = also for the activation gradient when it is a separate launch (no gain measured: 5.7 ms either way).
+// TTX_QUAD: 0 (default) = pair kernel everywhere (weight gradient 3.9 ms at cfg2 since it is persistent and replays
+// P'), 1 = quad kernel for the weight gradient (5.0 ms), 2 = also for the activation gradient when it is a separate
+// launch (5.7 ms either way).  The quad kernel is kept as the measured alternative to the replay, see DESIGN.md.
 static int quad_level() {
     const char* e = getenv("TTX_QUAD");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
 }
 
 template <int MODE, bool BF16>
@@ -2256,31 +2296,14 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile / hs)) return rc;
     if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2 / hs)) return rc;
     dim3 grid(persistent_grid(n_tiles_ub, p.n_halves), 1, 1);
-    // P' replay (H = 512): scratch = 64 KiB of per-pair flags + a 16-bit matrix of 128 rows per CTA x Vpad columns that
-    // holds the P' of the unit a CTA pair is working on (165 MB on a B200, whatever the problem size); stream-ordered
-    // allocation, nothing is kept between calls.  TTX_REPLAY=0 recomputes the second slab instead.
-    const char* re = getenv("TTX_REPLAY");
+    // P' replay (H = 512): the scratch matrix holds the P' of the unit a CTA pair is working on: 128 rows per CTA x Vpad
+    // columns (165 MB on a B200, whatever the problem size).
     void* scratch = nullptr;
     CUtensorMap mscr;
-    if (p.n_halves == 2 && !(re && re[0] == '0')) {
+    if (p.n_halves == 2 && replay_enabled()) {
         const int n_chunks = (V + 255) / 256;
         const size_t bytes = 65536 + (size_t)grid.x * kTile * n_chunks * 256 * 2;
-        {
-            // keep freed blocks in the device's default pool between steps (the default returns them to the driver at every
-            // synchronisation, which makes a 165 MB stream-ordered allocation per step cost milliseconds)
-            static bool pool_tuned[64];
-            int dev = 0;
-            TTX_CUDA_OK(cudaGetDevice(&dev));
-            if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
-                cudaMemPool_t pool;
-                uint64_t keep = ~0ull;
-                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                pool_tuned[dev] = true;
-            }
-        }
-        TTX_CUDA_OK(cudaMallocAsync(&scratch, bytes, stream));
-        TTX_CUDA_OK(cudaMemsetAsync(scratch, 0, 65536, stream));
+        if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
         if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
                                      (uint64_t)n_chunks * 256, bf16, kTile))
             return rc;
@@ -2398,10 +2421,46 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             const int hs = (p.dbg & 8) ? 2 : 1;
             if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile / hs)) return rc;
             if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2 / hs)) return rc;
-            p.splits = splits;
-            dim3 grid(n_vtiles, p.n_halves, splits);
-            int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream)
-                          : launch_v3<MODE_DW, false>(mx, my, myt, p, grid, smem, stream);
+            // Persistent: units = vocabulary tile pairs x lattice-row splits.  The split count is chosen so that the units
+            // fill whole waves of the device's CTA pairs, with long units preferred (every item ends with a G read-out and
+            // a red.add of its tile: ~1.5 stream chunks' worth of time) up to `cap` stream chunks -- a unit's P' must fit
+            // its CTA's share of the scratch matrix (cap 160: 10 MiB per CTA, 1.5 GB on a B200).
+            const int n_st = (n_tiles_ub + 1) / 2;
+            const int n_vq = (n_vtiles + 1) / 2;
+            const int pairs = max(1, sm_count() / 2);
+            int cap = 160;
+            if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
+            const int sp0 = (n_st + cap - 1) / cap;
+            double best_score = -1.0;
+            p.splits = sp0;
+            for (int sp = sp0; sp <= min(n_st, sp0 + 96); ++sp) {
+                const int len = (n_st + sp - 1) / sp;
+                if ((n_st + len - 1) / len != sp) continue;         // trailing splits would be empty
+                const int units = n_vq * sp;
+                const int waves = (units + pairs - 1) / pairs;
+                const double score = (double)units / ((double)pairs * waves) * len / (len + 1.5);
+                if (score > best_score) {
+                    best_score = score;
+                    p.splits = sp;
+                }
+            }
+            const int per = (n_st + p.splits - 1) / p.splits;
+            (void)splits;
+            dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
+            void* scratch = nullptr;
+            CUtensorMap mscr;
+            if (p.n_halves == 2 && replay_enabled()) {
+                const size_t bytes = 65536 + (size_t)grid.x * kTile * per * 256 * 2;
+                if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
+                if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
+                                             (uint64_t)per * 256, bf16, kTile))
+                    return rc;
+                p.scratch = static_cast<uint8_t*>(scratch);
+            }
+            int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr)
+                          : launch_v3<MODE_DW, false>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr);
+            if (scratch) TTX_CUDA_OK(cudaFreeAsync(scratch, stream));
+            if (rc == 0) trace_dump("DW v3", stream);
             if (rc) return rc;
         }
         return 0;
