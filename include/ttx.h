@@ -124,6 +124,26 @@ int ttx_fwd_grad_supported_h(int H);
 int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
                        const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                        int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream);
+/* Same launch, but the softmax numerators P' it computes anyway (16 bit, blank / label entries zero) are KEPT in the
+ * caller's matrix pstore (rows_ub x Vpad, rows_ub = 128 * n_tiles_ub, Vpad = V rounded up to 256) instead of a bounded
+ * scratch area, with pfac (rows): softmax(row, v) = pstore[row, v] * pfac[row].  pflags: 16384 int32, zeroed by the
+ * caller; word 16383 != 0 afterwards means some row's running reference moved and the matrix must not be used.
+ * H = 512 only.  The weight gradient is then one product on the kept matrix (ttx_weight_grad_kept) -- no second
+ * projection pass, no exponentials.  Costs rows_ub * Vpad * 2 bytes between forward and backward. */
+int ttx_joint_fwd_grad_keep(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
+                            const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
+                            int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* pstore,
+                            int32_t* pflags, float* pfac, int device, void* stream);
+/* d_w_out += dL/dW_out, d_b_out += the dense part of dL/db_out (as ttx_joint_grad with d_act = NULL) from the kept
+ * matrix: scales A16^T by w * pfac into a16st ((H + 16) x rows_ub, 16 bit, scratch owned by the caller), adds the exact
+ * blank / label terms, then dW += P'^T . As on the tensor cores.  If pflags[16383] != 0 those launches are no-ops and
+ * the recomputing kernel of ttx_joint_grad runs instead (decided on the device, no host synchronisation). */
+int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float* pfac, const void* a16, const void* w16,
+                         const void* a16t, const void* w16t, void* a16st, const float* bias2, const float* scal,
+                         const int32_t* row_label, const int32_t* meta, const void* rowmeta, const float* lp_blank,
+                         const float* lp_label, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, float* d_w_out, float* d_b_out, int device,
+                         void* stream);
 int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
                            const float* scal, int blank, const float* eproj, const float* pproj,
                            const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,

@@ -35,7 +35,8 @@ __device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_
 }  // namespace ttx
 using namespace ttx;
 
-// mode: 0 = SS, 1 = TS (A from TMEM columns 256..), 2 = SS + 8 warps reading TMEM concurrently, 3 = TMEM read only
+// mode: 0 = SS, 1 = TS (A from TMEM columns 256..), 2 = SS + 8 warps reading TMEM concurrently, 3 = TMEM read only,
+// 4 = SS with an MN-major A operand, 5 = SS with an MN-major B operand, 6 = both MN-major, 7 = SS with A bf16 / B f16
 template <int CG>
 __global__ void __launch_bounds__(320, 1) bench(int M, int N, int mode, int n_mma, int ld_warps, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -67,16 +68,23 @@ __global__ void __launch_bounds__(320, 1) bench(int M, int N, int mode, int n_mm
     long long t0 = 0, t1 = 0;
     if (warp == 1) {
         if (lane == 0 && rank == 0 && mode != 3) {
-            const uint32_t idesc = make_idesc(0, 0, 0, M, N);
+            uint32_t idesc = make_idesc(0, mode == 4 || mode == 6, mode == 5 || mode == 6, M, N);
+            if (mode == 7) idesc |= 1u << 7;               // A format bf16, B stays f16
+            // descriptors = base + (chunk, k slice) steps of the start-address field (16-byte units), fixed per mode so
+            // that the issue loop stays within one MMA's time
+            const bool amn = (mode == 4 || mode == 6), bmn = (mode == 5 || mode == 6);
+            const uint64_t da0 = amn ? desc_mnmajor(sA, 0, 8192) : desc_kmajor(sA, 0);
+            const uint64_t db0 = bmn ? desc_mnmajor(sB, 0, 8192) : desc_kmajor(sB, 0);
+            const uint32_t aks = amn ? 128 : 2, bks = bmn ? 128 : 2;
             t0 = clock64();
             for (int i = 0; i < n_mma; ++i) {
                 const int c = (i >> 2) & 3, k = i & 3;
-                const uint64_t db = desc_kmajor(sB + c * 32768, k);
+                const uint64_t db = db0 + (uint64_t)(c * 2048 + k * bks);
                 if (mode == 1) {
                     if (CG == 2) umma_f16_ts_pair(tmem, tmem + 256 + (i & 7) * 8, db, idesc, i != 0);
                     else umma_f16_ts(tmem, tmem + 256 + (i & 7) * 8, db, idesc, i != 0);
                 } else {
-                    const uint64_t da = desc_kmajor(sA + c * 16384, k);
+                    const uint64_t da = da0 + (uint64_t)(c * 1024 + k * aks);
                     if (CG == 2) umma_f16_ss_pair(tmem, da, db, idesc, i != 0);
                     else umma_f16_ss(tmem, da, db, idesc, i != 0);
                 }
@@ -513,7 +521,22 @@ static void occupancy() {
     printf("cluster size %d: max active clusters %d (%d SMs) [%s]\n", CS, n, n * CS, cudaGetErrorString(e));
 }
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 'm') {            // operand-major / mixed-format variants only
+        long long* d_out;
+        cudaMalloc(&d_out, 148 * sizeof(long long));
+        const int n = 4096;
+        run<2>("cg2 SS K-major (warm-up)", 256, 256, 0, 4 * n, 0, d_out);
+        run<2>("cg2 SS K-major (reference)", 256, 256, 0, n, 0, d_out);
+        run<2>("cg2 SS A MN-major", 256, 256, 4, n, 0, d_out);
+        run<2>("cg2 SS B MN-major", 256, 256, 5, n, 0, d_out);
+        run<2>("cg2 SS A and B MN-major", 256, 256, 6, n, 0, d_out);
+        run<1>("cg1 SS A MN-major", 128, 256, 4, n, 0, d_out);
+        run<1>("cg1 SS B MN-major", 128, 256, 5, n, 0, d_out);
+        run<2>("cg2 SS K-major (reference)", 256, 256, 0, n, 0, d_out);
+        if (argv[1][1] == 'x') run<2>("cg2 SS A bf16, B f16", 256, 256, 7, n, 0, d_out);   // illegal instruction on sm_100a
+        return 0;
+    }
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_dsmem(0, d); run_dsmem(1, d); run_dsmem(2, d); cudaFree(d); }
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_ring(0, 4, d); run_ring(1, 4, d); run_ring(2, 4, d); run_ring(3, 4, d); run_ring(4, 4, d); cudaFree(d); }
     { long long* d; cudaMalloc(&d, 148 * sizeof(long long)); run_tma(0, 8, d); run_tma(0, 8, d, 2); run_tma(0, 8, d, 1); run_tma(1, 8, d); cudaFree(d); }

@@ -40,6 +40,9 @@ _PROTOS = {
     "ttx_fwd_grad_supported_h": [c_i32],
     "ttx_joint_fwd_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
                            c_i32, c_p],
+    "ttx_joint_fwd_grad_keep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
+                                c_p, c_p, c_p, c_i32, c_p],
+    "ttx_weight_grad_kept": [c_p] * 17 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_reduce_act_grad_ew": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
                                c_p, c_p, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],

@@ -22,6 +22,8 @@ constexpr float kPScale = 4096.0f;                  // power-of-two scale of the
 //   meta[kMetaHdr + b]            b in [0,B]   : first tile of utterance b (meta[kMetaHdr+B] == n_tiles)
 //   meta[kMetaHdr + B+1 + i]      i in [0,ub)  : utterance of tile i (-1 when unused)
 constexpr int kMetaHdr = 4;
+// Kept P' matrix (forward+gradient -> weight gradient): flag words, one per tile pair; this one = some pair is flagged.
+constexpr int kKeptAnyDirty = 16383;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -43,7 +43,11 @@ struct MmaParams {
     float* dA;             // DA out (rows x H)
     float* dW;             // DW out (V x H), accumulated with red.add
     float* db;             // DW out (V)
-    uint8_t* scratch;      // pair kernel, forward+gradient: per-pair flags + P' scratch matrix (replay), or null
+    uint8_t* scratch;      // pair kernel: flags (64 KiB) of the P' scratch matrix (replay), or null
+    int keep;              // the P' matrix covers every lattice row (rows_ub x Vpad) and is kept for the weight gradient
+    float* pfac;           // FG out (rows), optional: softmax(row, v) = P'(row, v) * pfac[row]
+    const int* run_if;     // DW, optional: the launch is a no-op unless (*run_if != 0) == (run_if_val != 0)
+    int run_if_val;
 };
 
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
@@ -150,6 +154,7 @@ template <int MODE, bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                  const MmaParams p) {
+    if (MODE == MODE_DW && p.run_if != nullptr && (*p.run_if != 0) != (p.run_if_val != 0)) return;   // whole grid alike
     constexpr bool BWD = (MODE != MODE_FWD);
     constexpr int NT = (CG == 2 && !BWD) ? 256 : 128;   // columns of one S accumulator = stream rows per step
     constexpr int SR = NT / CG;                          // stream rows this CTA loads per S chunk
@@ -620,9 +625,16 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     constexpr int NT = 256;                 // stream rows per step (pair-wide) = S accumulator columns
     constexpr int SR = 128;                 // stream rows this CTA loads per S chunk
     constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
+    if (MODE == MODE_DW && p.run_if != nullptr && (*p.run_if != 0) != (p.run_if_val != 0)) return;   // whole grid alike
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
+    // KEPT (weight gradient, p.keep): the forward+gradient launch left P' for every lattice row in global memory.  Every
+    // item is then a replay: A operand = P'^T (MN-major, straight from the row-major P' matrix: two [64 m x 64 v] boxes
+    // per stage), B operand = the scaled A16^T chunk; no S pass, no exponentials, no P' buffers.  mapScr = P' matrix,
+    // mapYT = scaled A16^T (H + 16 rows), mapY = its last 16 rows (8-row boxes): As = 1 * scale, whose product with P'
+    // (a 16-column accumulator next to G, first slab only) is the dense part of db.
+    const bool kept = (MODE == MODE_DW) && p.keep != 0;
     // Persistent: the grid is one CTA pair per SM pair and each pair walks work units one after the other, all slabs of
     // a unit in turn, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
     // behind the read-out of G, and TMEM / barriers are set up once.  FG / DA: unit = tile pair, streams the whole
@@ -657,13 +669,20 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     // needs neither S passes nor exponentials -- it streams P' back as the A operand next to the W16^T chunks.  If the
     // running reference moved after the unit's first tile (rare), the stored sub-tiles carry mixed scales: the unit is
     // flagged and its second slab recomputes everything as without the scratch area.
-    const bool rp = (MODE == MODE_FG || MODE == MODE_DW) && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 && p.NKC + kPB <= 12;
+    const bool rp = (MODE == MODE_FG || MODE == MODE_DW) && !kept && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 &&
+                    p.NKC + kPB <= 12;
     // The replay streams two operands and touches neither the X tile nor the P' buffers: their shared memory (contiguous,
     // 10 x 16 KiB) is its ring, with its own barriers (slots kRB.. of the full / empty arrays) and its own position.
     constexpr int kRB = 4;                            // first barrier slot of the replay ring (the S / G ring uses < 4)
     const int nrs = p.NKC + kPB;                      // replay ring stages
-    volatile int* const dirty = rp ? reinterpret_cast<volatile int*>(p.scratch) + (blockIdx.x >> 1) : nullptr;
-    const int scr_row0 = (int)blockIdx.x * kTile;     // this CTA's 128 rows of the scratch matrix
+    // Flags (first 64 KiB of the scratch area, zeroed by the host).  Bounded scratch: one word per CTA pair, stamped with
+    // the pair's unit counter + 1.  KEEP (p.keep: the matrix covers every lattice row and outlives the launch -- the
+    // weight-gradient launch reads it): one word per unit, plus word kKeptAnyDirty = some unit of the launch is flagged.
+    volatile int* const flags = reinterpret_cast<volatile int*>(p.scratch);
+    auto unit_clean = [&](int unit, int uidx) {
+        return p.keep ? flags[unit] == 0 : flags[blockIdx.x >> 1] != uidx + 1;
+    };
+    auto scr_row = [&](int x_row0) { return p.keep ? x_row0 : (int)blockIdx.x * kTile; };   // the CTA's rows of the matrix
     const int hh2 = p.HH / 2;               // G columns (N rows of the K-major B operand) held by this CTA
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -763,11 +782,31 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             bool replayed = false;                              // the previous item was a replay (its ring is our X tile)
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
+                if (kept) {
+                    const int v0 = unit_tile(unit) * kTile;     // this CTA's vocabulary rows = columns of the P' matrix
+                    for (int hh = 0; hh < n_hl; ++hh)
+                        for (int i = 0; i < n_iter; ++i)
+                            for (int c = 0; c < 4; ++c) {
+                                const int m0 = (j0 + i) * NT + c * kKC;
+                                mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
+                                if (leader) mbar_arrive_expect_tx(bar_full(kRB + rr.stage), 2 * STAGE);
+                                tma_load_2d_pair(sX + rr.stage * STAGE, &mapScr, bar_full(kRB + rr.stage), v0, m0);
+                                tma_load_2d_pair(sX + rr.stage * STAGE + STAGE / 2, &mapScr, bar_full(kRB + rr.stage), v0 + kKC, m0);
+                                rr.advance(nrs);
+                                mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
+                                if (leader) mbar_arrive_expect_tx(bar_full(kRB + rr.stage), 2 * (hh2 * 128 + (hh == 0 ? 1024 : 0)));
+                                tma_load_2d_pair(sX + rr.stage * STAGE, &mapYT, bar_full(kRB + rr.stage), m0, hh * p.HH + (int)rank * hh2);
+                                if (hh == 0)
+                                    tma_load_2d_pair(sRing + (rr.stage >> 1) * 1024, &mapY, bar_full(kRB + rr.stage), m0, p.H + (int)rank * 8);
+                                rr.advance(nrs);
+                            }
+                    continue;
+                }
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
                     const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
                     if (rp && hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
-                        if (*dirty != uidx + 1) {
+                        if (unit_clean(unit, uidx)) {
                             // replay: per sub-pass one stage of P' (A operand, from the scratch matrix) and one of W16^T;
                             // the ring is the X tile + P' buffers, free once the first slab's last S pass / G sub-pass
                             // have read them (xempty; the epilogue's unit arrival came after its last pempty wait)
@@ -781,7 +820,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             };
                             for (int i = 0; i < n_iter; ++i)
                                 for (int c = 0; c < 4; ++c) {
-                                    load_rstage(&mapScr, (i * 4 + c) * kKC, scr_row0, STAGE);
+                                    load_rstage(&mapScr, (i * 4 + c) * kKC, scr_row(x_row0), STAGE);
                                     load_rstage(&mapYT, (j0 + i) * NT + c * kKC, h0, hh2 * 128);
                                 }
                             replayed = true;
@@ -818,7 +857,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 for (int hh = 0; hh < n_hl; ++hh) {
                     if (hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
-                        if (*dirty != uidx + 1) continue;
+                        if (unit_clean(unit, uidx)) continue;
                     }
                     for (int i = 0; i < n_iter; ++i)
                         for (int c = 0; c < 4; ++c) {
@@ -826,7 +865,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             if (hh == 0) {
                                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                              ::"l"(reinterpret_cast<uint64_t>(&mapScr)), "r"(sP + sr.buf * kChunkBytes),
-                                               "r"((i * 4 + c) * kKC), "r"(scr_row0)
+                                               "r"((i * 4 + c) * kKC), "r"(scr_row(unit_tile(unit) * kTile))
                                              : "memory");
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -882,9 +921,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
-                    if (rp && hh == 1) {
-                        mbar_wait(bar_unit, uidx & 1);
-                        if (*dirty != uidx + 1) {
+                    if (kept || (rp && hh == 1)) {
+                        if (!kept) mbar_wait(bar_unit, uidx & 1);
+                        if (kept || unit_clean(unit, uidx)) {
                             for (int i = 0; i < n_iter; ++i)
                                 for (int c = 0; c < 4; ++c) {
                                     if (i == 0 && c == 0) mbar_wait(bar_gempty, (it - 1) & 1);
@@ -969,9 +1008,29 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     bool replay = false;
                     if (rp && hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
-                        replay = (*dirty != uidx + 1);
+                        replay = unit_clean(unit, uidx);
                     }
-                    if (replay) {
+                    if (kept) {
+                        // G(slab hh) += P'^T(stage) . As^T chunk(next stage); slab 0 also D2 += P'^T . scale rows
+                        const uint32_t idescGm = make_idesc(fmt, 1, 0, 256, p.HH), idescD = make_idesc(fmt, 1, 0, 256, 16);
+                        const uint32_t amn = (xlo & 0xFFFFu) | (512u << 16);     // MN-major: 64-wide blocks 8 KiB apart
+                        const uint32_t olo = desc_lo(sRing);
+                        for (int i = 0; i < n_iter; ++i)
+                            for (int c = 0; c < 4; ++c) {
+                                wait_event();
+                                tc_fence_after();
+                                const int s2 = rstage + 1;                        // stages come in (P', As^T) pairs
+                                const uint32_t a = amn + rstage * 1024, b = xlo + s2 * 1024, o = olo + (s2 >> 1) * 64;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_f16_ss_pair_lo(tmem_G, a + 128 * k, b + 2 * k, idescGm, (i | c | k) != 0);
+                                    if (hh == 0) umma_f16_ss_pair_lo(tmem_base, a + 128 * k, o + 2 * k, idescD, (i | c | k) != 0);
+                                }
+                                umma_commit_pair(bar_empty(kRB + rstage));
+                                umma_commit_pair(bar_empty(kRB + s2));
+                                rstage = (s2 + 1 == nrs) ? 0 : s2 + 1;
+                            }
+                    } else if (replay) {
                         // G(slab 1) += P'(i, c) . W16^T chunk, both operands from consecutive ring stages
                         for (int i = 0; i < n_iter; ++i)
                             for (int c = 0; c < 4; ++c) {
@@ -1081,7 +1140,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         bool replay = false;
         if (rp && hh == 1) {
             mbar_wait(bar_unit, uidx & 1);
-            replay = (*dirty != uidx + 1);
+            replay = unit_clean(unit, uidx);
         }
         if (et == 0) trace_at(p, 0, it, 0);
         if (MODE == MODE_FG) {
@@ -1181,7 +1240,14 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                     float part = p0 + p1;
                     if (quarter_any(q, lmax > lg_scale + 3.f)) {
-                        if (rp && hh == 0) *dirty = uidx + 1;     // stored sub-tiles now carry mixed scales: no replay
+                        if (rp && hh == 0) {                       // stored sub-tiles now carry mixed scales: no replay
+                            if (p.keep) {
+                                flags[unit] = 1;
+                                flags[kKeptAnyDirty] = 1;
+                            } else {
+                                flags[blockIdx.x >> 1] = uidx + 1;
+                            }
+                        }
                         xg[ch * kTile + row] = lmax;
                         quarter_sync(q);
                         const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
@@ -1268,7 +1334,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     p.lpb[grow] = (zb - lse2) * kLn2;
                     p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
                 }
-                f_keep = ex2f(mref - lg_scale - lse2) * inv_ws;
+                const float pf = ex2f(mref - lg_scale - lse2);    // softmax(row, v) = P'(row, v) * pf
+                if (p.pfac && ch == 0 && valid_x && half == 0) p.pfac[grow] = pf;
+                f_keep = pf * inv_ws;
             }
             const float f = f_keep;
             float* dst = p.dA + (size_t)grow * p.H + half * p.HH;
@@ -1298,9 +1366,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 krow = fmaf(rm.x, -kLog2e, lg_scale);
             } else {
                 vrow = x_row0 + row;
-                krow = __ldg(p.bias2 + vrow);
+                if (!kept) krow = __ldg(p.bias2 + vrow);
             }
-            for (int i = 0; i < (replay ? 0 : n_iter); ++i) {
+            for (int i = 0; i < ((replay || kept) ? 0 : n_iter); ++i) {
                 const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
                 float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
                 int clabel = -1;
@@ -1390,7 +1458,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
-            if (!replay) gs0 += n_iter;
+            if (!replay && !kept) gs0 += n_iter;
             // ---- final: G (128 x HH fp32 in TMEM) -> global
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
@@ -1414,9 +1482,16 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }
             } else {
-                const float f = gmax / pscale;
+                // kept: the As operand carries 2^24 (fp16) on top of w * pfac
+                const float f = kept ? gmax * (BF16 ? 1.0f : 5.9604644775390625e-8f) : gmax / pscale;
                 const bool ok = vrow < p.V;
                 float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
+                if (kept && half == 0) {                   // dense part of db: column 0 of the 16-column accumulator
+                    uint32_t d2[16];
+                    tmem_ld16(tmem_base + lane_addr, d2);
+                    tmem_ld_wait();
+                    if (ok && ch == 0) atomicAdd(p.db + vrow, __uint_as_float(d2[0]) * f);
+                }
                 for (int cc = ch; cc < ngrp; cc += 2) {
                     tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
                     tmem_ld_wait();
@@ -1428,7 +1503,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }
                 // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
-                if (ok && half == 0 && !replay) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+                if (ok && half == 0 && !replay && !kept) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
         }
         if (PERSIST) {                                // G has left TMEM: the next item may overwrite it
@@ -2137,6 +2212,27 @@ static int launch_v3(const CUtensorMap& mx, const CUtensorMap& my, const CUtenso
     return 0;
 }
 
+// Split count of the persistent weight-gradient launch: units = vocabulary tile pairs x lattice-row splits should fill
+// whole waves of the device's CTA pairs, with long units preferred (every item ends with a G read-out and a red.add
+// of its tile: ~1.5 stream chunks' worth of time) up to `cap` stream chunks per unit.
+static int dw_splits(int n_st, int n_vq, int pairs, int cap) {
+    const int sp0 = (n_st + cap - 1) / cap;
+    double best_score = -1.0;
+    int best = sp0;
+    for (int sp = sp0; sp <= min(n_st, sp0 + 96); ++sp) {
+        const int len = (n_st + sp - 1) / sp;
+        if ((n_st + len - 1) / len != sp) continue;         // trailing splits would be empty
+        const int units = n_vq * sp;
+        const int waves = (units + pairs - 1) / pairs;
+        const double score = (double)units / ((double)pairs * waves) * len / (len + 1.5);
+        if (score > best_score) {
+            best_score = score;
+            best = sp;
+        }
+    }
+    return best;
+}
+
 // v3 applies when both transposed copies exist and every CTA's share of a G slab is a whole number of 64-row
 // chunk rows that fits one 16 KiB stage: HH / 2 in {64, 128}.
 static bool v3_applicable(int H, const void* w16t, const void* a16t) {
@@ -2266,7 +2362,7 @@ static void quad_params(MmaParams& p, size_t& smem, int H, int V) {
 int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, uint64_t rows_ub, int n_tiles_ub, int H,
                           int V, int Vpad, bool bf16, const int* meta, const float* bias2, const float* scal,
                           const int* row_label, int blank, float* lse, float* lpb, float* lpl, float* ew,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, void* pstore, int* pflags, float* pfac) {
     MmaParams p{};
     p.H = H;
     p.NKC = H / 64;
@@ -2300,27 +2396,86 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     // columns (165 MB on a B200, whatever the problem size).
     void* scratch = nullptr;
     CUtensorMap mscr;
-    if (p.n_halves == 2 && replay_enabled()) {
-        const int n_chunks = (V + 255) / 256;
+    const int n_chunks = (V + 255) / 256;
+    bool have_map = false;
+    if (pstore) {
+        // KEEP: the caller's matrix covers every lattice row (rows_ub x Vpad, 16 bit) and goes on to the weight gradient
+        if (p.n_halves != 2 || !pflags || !pfac || (n_tiles_ub + 1) / 2 > 16383) {
+            set_error("ttx_joint_fwd_grad: the kept P' matrix needs H = 512, flags, pfac and at most 16383 tile pairs");
+            return 1;
+        }
+        if (int rc = make_matrix_map(&mscr, pstore, rows_ub, (uint64_t)n_chunks * 256, bf16, kTile)) return rc;
+        p.scratch = reinterpret_cast<uint8_t*>(pflags);
+        p.keep = 1;
+        p.pfac = pfac;
+        have_map = true;
+    } else if (p.n_halves == 2 && replay_enabled()) {
         const size_t bytes = 65536 + (size_t)grid.x * kTile * n_chunks * 256 * 2;
         if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
         if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
                                      (uint64_t)n_chunks * 256, bf16, kTile))
             return rc;
         p.scratch = static_cast<uint8_t*>(scratch);
+        have_map = true;
     }
-    int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr)
-                  : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr);
+    int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr)
+                  : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr);
     if (scratch) TTX_CUDA_OK(cudaFreeAsync(scratch, stream));
     if (rc == 0) trace_dump("FG", stream);
+    return rc;
+}
+
+// Weight gradient from the kept P' matrix (forward+gradient launch with pstore): dW += gmax 2^-shift P'^T . As, db likewise.
+// a16st = scaled A16^T with its 16 scale rows ((H + 16) x rows_ub, launch_kept_prepare).  No-op if the matrix is flagged.
+int launch_joint_dw_kept(const void* pstore, const int* pflags, const void* a16st, uint64_t rows_ub, int n_tiles_ub, int H,
+                         int V, int Vpad, bool bf16, const int* meta, const float* scal, float* dW, float* db,
+                         cudaStream_t stream) {
+    if (H != 512) {
+        set_error("ttx_weight_grad_kept: H = %d (the kept P' path is built for two 256-column slabs, H = 512)", H);
+        return 1;
+    }
+    MmaParams p{};
+    p.H = H;
+    p.NKC = H / 64;
+    p.V = V;
+    p.n_halves = 2;
+    p.HH = H / 2;
+    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
+    p.trace = trace_buffer();
+    const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+    int ns = 8;
+    while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
+    p.NS = ns;
+    const size_t smem = fixed + (size_t)ns * kChunkBytes;
+    p.meta = meta;
+    p.scal = scal;
+    p.dW = dW;
+    p.db = db;
+    p.keep = 1;
+    p.scratch = reinterpret_cast<uint8_t*>(const_cast<int*>(pflags));
+    p.run_if = pflags + kKeptAnyDirty;
+    p.run_if_val = 0;
+    const int n_vtiles = (V + kTile - 1) / kTile;
+    const int n_st = (n_tiles_ub + 1) / 2, n_vq = (n_vtiles + 1) / 2, pairs = max(1, sm_count() / 2);
+    int cap = 160;
+    if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
+    p.splits = dw_splits(n_st, n_vq, pairs, cap);
+    CUtensorMap mp, myt, mones;
+    if (int rc = make_matrix_map(&mp, pstore, rows_ub, (uint64_t)Vpad, bf16, 64)) return rc;
+    if (int rc = make_matrix_map(&myt, a16st, (uint64_t)H + 16, rows_ub, bf16, p.HH / 2)) return rc;
+    if (int rc = make_matrix_map(&mones, a16st, (uint64_t)H + 16, rows_ub, bf16, 8)) return rc;
+    dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
+    int rc = bf16 ? launch_v3<MODE_DW, true>(mp, mones, myt, p, grid, smem, stream, &mp)
+                  : launch_v3<MODE_DW, false>(mp, mones, myt, p, grid, smem, stream, &mp);
+    if (rc == 0) trace_dump("DW kept", stream);
     return rc;
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const void* w16t, uint64_t rows_ub,
                      int n_tiles_ub, int H, int V, int Vpad, bool bf16, const int* meta, const float* bias2,
                      const float* scal, const int* row_label, int blank, const float4* rowmeta, float* dA, float* dW,
-                     float* db, int splits, cudaStream_t stream) {
-    if (H == 512 && v3_applicable(H, w16t, a16t) && quad_level() > 0) {
+                     float* db, int splits, cudaStream_t stream, const int* run_if) {
+    if (H == 512 && v3_applicable(H, w16t, a16t) && quad_level() > 0 && !run_if) {
         const bool quad_da = quad_level() > 1;
         MmaParams p{};
         size_t smem;
@@ -2421,35 +2576,22 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             const int hs = (p.dbg & 8) ? 2 : 1;
             if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile / hs)) return rc;
             if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2 / hs)) return rc;
-            // Persistent: units = vocabulary tile pairs x lattice-row splits.  The split count is chosen so that the units
-            // fill whole waves of the device's CTA pairs, with long units preferred (every item ends with a G read-out and
-            // a red.add of its tile: ~1.5 stream chunks' worth of time) up to `cap` stream chunks -- a unit's P' must fit
-            // its CTA's share of the scratch matrix (cap 160: 10 MiB per CTA, 1.5 GB on a B200).
+            // Persistent: units = vocabulary tile pairs x lattice-row splits of at most `cap` stream chunks -- a unit's P' must
+            // fit its CTA's share of the scratch matrix (cap 160: 10 MiB per CTA, 1.5 GB on a B200).
             const int n_st = (n_tiles_ub + 1) / 2;
             const int n_vq = (n_vtiles + 1) / 2;
             const int pairs = max(1, sm_count() / 2);
             int cap = 160;
             if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
-            const int sp0 = (n_st + cap - 1) / cap;
-            double best_score = -1.0;
-            p.splits = sp0;
-            for (int sp = sp0; sp <= min(n_st, sp0 + 96); ++sp) {
-                const int len = (n_st + sp - 1) / sp;
-                if ((n_st + len - 1) / len != sp) continue;         // trailing splits would be empty
-                const int units = n_vq * sp;
-                const int waves = (units + pairs - 1) / pairs;
-                const double score = (double)units / ((double)pairs * waves) * len / (len + 1.5);
-                if (score > best_score) {
-                    best_score = score;
-                    p.splits = sp;
-                }
-            }
+            p.splits = dw_splits(n_st, n_vq, pairs, cap);
             const int per = (n_st + p.splits - 1) / p.splits;
             (void)splits;
             dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
             void* scratch = nullptr;
             CUtensorMap mscr;
-            if (p.n_halves == 2 && replay_enabled()) {
+            p.run_if = run_if;
+            p.run_if_val = 1;
+            if (p.n_halves == 2 && replay_enabled() && !run_if) {    // (the fallback of the kept-P' path runs without scratch)
                 const size_t bytes = 65536 + (size_t)grid.x * kTile * per * 256 * 2;
                 if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
                 if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
@@ -2467,6 +2609,8 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
     }
     Plan pl = plan(H, V, true);
     MmaParams& p = pl.p;
+    p.run_if = run_if;
+    p.run_if_val = 1;
     p.blank = blank;
     p.meta = meta;
     p.bias2 = bias2;

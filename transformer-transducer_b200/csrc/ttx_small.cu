@@ -772,6 +772,150 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------- weight gradient from kept P'
+// The forward+gradient launch can keep its softmax numerators P' (rows_ub x Vpad, 16 bit; softmax = P' * pfac[row]).
+// Then the dense part of the weight gradient is one product with no projection pass and no exponentials,
+//   dW[v, h] = gmax * 2^-shift * sum_m P'[m, v] * As[m, h],   As[m, h] = 2^shift * w_m * pfac_m * A16[m, h],
+// whose K-major B operand is the scaled transposed copy written here (the scale cannot ride on P': it is streamed
+// straight into the tensor core).  Sixteen extra rows h = H .. H+15 hold As = 2^shift * w_m * pfac_m (A = 1): their
+// product with P' is the dense part of db.  shift (24 for fp16, 0 for bf16) keeps As out of the subnormals.
+// Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.  No-op if the P' matrix is flagged.
+template <bool BF16>
+__device__ __forceinline__ void unpack16(uint32_t v, float& a, float& b) {
+    if (BF16) {
+        a = __uint_as_float(v << 16);
+        b = __uint_as_float(v & 0xffff0000u);
+    } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&v);
+        a = __low2float(h);
+        b = __high2float(h);
+    }
+}
+
+constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T) per block
+template <bool BF16>
+__global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float4* __restrict__ rowmeta,
+                                  const float* __restrict__ pfac, const int* __restrict__ meta,
+                                  const int* __restrict__ flags, int H, size_t rows_total, float up,
+                                  uint16_t* __restrict__ out) {
+    if (flags[kKeptAnyDirty] != 0) return;
+    const size_t m0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (m0 >= rows_total) return;
+    const size_t rows_used = (size_t)meta[0] * kTile;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float v = 0.f;
+        if (m0 + e < rows_used) {
+            const float w = __ldg(&rowmeta[m0 + e].w);
+            if (w != 0.f) v = w * __ldg(pfac + m0 + e) * up;
+        }
+        s[e] = v;
+    }
+    const int h0 = blockIdx.y * kScaleRowsPerBlock;
+    for (int h = h0; h < h0 + kScaleRowsPerBlock; ++h) {
+        uint4 o;
+        if (h < H) {
+            const uint4 in = __ldg(reinterpret_cast<const uint4*>(a16t + (size_t)h * rows_total + m0));
+            const uint32_t w4[4] = {in.x, in.y, in.z, in.w};
+            uint32_t r4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a, b;
+                unpack16<BF16>(w4[e], a, b);
+                r4[e] = pack16<BF16>(a * s[2 * e], b * s[2 * e + 1]);
+            }
+            o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+        } else {
+            o = make_uint4(pack16<BF16>(s[0], s[1]), pack16<BF16>(s[2], s[3]), pack16<BF16>(s[4], s[5]),
+                           pack16<BF16>(s[6], s[7]));
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)h * rows_total + m0) = o;
+    }
+}
+
+// The blank and label entries are absent from the kept P' (the forward+gradient launch zeroes them): their exact terms
+//   dW[blank] += gmax * sum_m w (p_b - rb) A[m],  dW[label_m] += gmax * w (p_l - rl) A[m]   (rowmeta .y / .z),
+//   db[blank] += gmax * sum_m w p_b,              db[label_m] += gmax * w p_l               (dense part they left out)
+// are added here.  grid = (U1, B, t-chunks) like reduce_pred_kernel: the label depends on (b, u) only.
+template <bool BF16>
+__global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4* __restrict__ rowmeta,
+                                 const int* __restrict__ row_label, const float* __restrict__ lpb,
+                                 const float* __restrict__ lpl, const float* __restrict__ scal,
+                                 const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                 const int* __restrict__ meta, const int* __restrict__ flags, int U1, int H, int blank,
+                                 int t_chunk, float* __restrict__ d_w, float* __restrict__ d_b) {
+    if (flags[kKeptAnyDirty] != 0 || meta[1] != 0) return;
+    const int u = blockIdx.x, b = blockIdx.y;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    if (u >= U1b) return;
+    const int t0 = blockIdx.z * t_chunk, t1 = min(Tb, t0 + t_chunk);
+    if (t0 >= t1) return;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    const int lab = __ldg(row_label + base + (size_t)t0 * U1b + u);
+    const bool has_label = lab >= 0 && lab != blank;
+    const float gmax = scal[2];
+    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
+        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), al = ab;
+        float dbb = 0.f, dbl = 0.f;
+        for (int t = t0; t < t1; ++t) {
+            const size_t m = base + (size_t)t * U1b + u;
+            const float4 rm = __ldg(rowmeta + m);
+            const uint2 av = __ldg(reinterpret_cast<const uint2*>(a16 + m * H + h));
+            float a0, a1, a2, a3;
+            unpack16<BF16>(av.x, a0, a1);
+            unpack16<BF16>(av.y, a2, a3);
+            const float cb = rm.w * rm.y, cl = rm.w * rm.z;
+            ab.x = fmaf(cb, a0, ab.x); ab.y = fmaf(cb, a1, ab.y); ab.z = fmaf(cb, a2, ab.z); ab.w = fmaf(cb, a3, ab.w);
+            if (has_label) {
+                al.x = fmaf(cl, a0, al.x); al.y = fmaf(cl, a1, al.y); al.z = fmaf(cl, a2, al.z); al.w = fmaf(cl, a3, al.w);
+            }
+            if (h == 0) {
+                dbb = fmaf(rm.w, __expf(__ldg(lpb + m)), dbb);
+                if (has_label) dbl = fmaf(rm.w, __expf(__ldg(lpl + m)), dbl);
+            }
+        }
+        float* db_ = d_w + (size_t)blank * H + h;
+        atomicAdd(db_ + 0, ab.x * gmax); atomicAdd(db_ + 1, ab.y * gmax);
+        atomicAdd(db_ + 2, ab.z * gmax); atomicAdd(db_ + 3, ab.w * gmax);
+        if (has_label) {
+            float* dl = d_w + (size_t)lab * H + h;
+            atomicAdd(dl + 0, al.x * gmax); atomicAdd(dl + 1, al.y * gmax);
+            atomicAdd(dl + 2, al.z * gmax); atomicAdd(dl + 3, al.w * gmax);
+        }
+        if (h == 0) {
+            atomicAdd(d_b + blank, dbb * gmax);
+            if (has_label) atomicAdd(d_b + lab, dbl * gmax);
+        }
+    }
+}
+
+int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta, const int* row_label,
+                        const float* lpb, const float* lpl, const float* pfac, const float* scal, const int* act_lens,
+                        const int* label_lens, const int* meta, const int* flags, int B, int T, int U1, int H, int blank,
+                        bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, cudaStream_t s) {
+    const float up = bf16 ? 1.f : 16777216.f;
+    const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
+    if (bf16)
+        scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, flags, H, rows_total, up,
+                                                   (uint16_t*)a16st);
+    else
+        scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, flags, H, rows_total, up,
+                                                    (uint16_t*)a16st);
+    const int t_chunk = 64;
+    const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
+    const int threads = min(256, max(32, H / 4));
+    if (bf16)
+        dw_sparse_kernel<true><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
+                                                      label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b);
+    else
+        dw_sparse_kernel<false><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
+                                                       label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_dense_lse(const float* acts, const int* labels, const int* act_lens, const int* label_lens,
                      const int* meta, int B, int T, int U1, int V, int label_stride, int blank, int n_tiles_ub,
                      float* lse, float* lpb, float* lpl, int* row_label, cudaStream_t s) {

@@ -24,7 +24,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_reduce_act_grad_ew": 2, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 4, "ttx_reduce_act_grad_ew": 2, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -102,6 +102,14 @@ def _dw_splits(sms, V, H, ntub):
     return best
 
 
+def _keep_fits(plan, H, Vpad, dev):
+    """The kept-P' weight gradient (H = 512) holds rows * Vpad 16-bit values from forward to backward: used when that
+    fits TTX_KEEP_GB (default 32; 0 disables)."""
+    budget = float(os.environ.get("TTX_KEEP_GB", "32")) * 2**30
+    need = plan.rows * Vpad * 2
+    return H == 512 and 0 < need <= budget and (plan.ntub + 1) // 2 <= 16383
+
+
 def supported_width(H):
     return bool(_lib.get().ttx_supported_h(int(H)))
 
@@ -148,13 +156,21 @@ class FusedJointRNNT(torch.autograd.Function):
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             # When the activations need gradients the forward also accumulates EW = sum_v p_v W_out[v] (minus the
             # blank / label columns) on the tensor cores, so the backward has no activation-gradient MMA pass.
-            ew = None
+            ew = kept = None
             if (with_t and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and lib.ttx_fwd_grad_supported_h(H)
                     and os.environ.get("TTX_NO_FWD_GRAD", "0") != "1"):
                 ew = plan.rowf(H)
-                _call("ttx_joint_fwd_grad", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label),
-                      _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(ew),
-                      plan.idx, st)
+                if (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]) and _keep_fits(plan, H, Vpad, dev):
+                    # keep the softmax numerators P' (16 bit) for the weight gradient: no second projection pass there
+                    kept = (torch.empty(plan.rows * Vpad, dtype=torch.int16, device=dev),
+                            torch.zeros(16384, dtype=torch.int32, device=dev), plan.rowf())
+                    _call("ttx_joint_fwd_grad_keep", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal),
+                          _p(row_label), _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
+                          _p(ew), _p(kept[0]), _p(kept[1]), _p(kept[2]), plan.idx, st, label="ttx_joint_fwd_grad")
+                else:
+                    _call("ttx_joint_fwd_grad", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label),
+                          _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(ew),
+                          plan.idx, st)
             else:
                 _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                       plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), plan.idx, st)
@@ -162,7 +178,7 @@ class FusedJointRNNT(torch.autograd.Function):
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
         ctx.transposed = (a16t, w16t)
-        ctx.ew, ctx.w32 = ew, (w if ew is not None else None)
+        ctx.ew, ctx.w32, ctx.kept = ew, (w if ew is not None else None), kept
         ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
         return costs
 
@@ -191,7 +207,15 @@ class FusedJointRNNT(torch.autograd.Function):
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
-                if need_w:
+                if need_w and ctx.kept is not None:
+                    pstore, pflags, pfac = ctx.kept
+                    a16st = torch.empty((H + 16) * plan.rows, dtype=torch.int16, device=dev)
+                    _call("ttx_weight_grad_kept", dev, _p(pstore), _p(pflags), _p(pfac), _p(a16), _p(w16), _p(a16t),
+                          _p(w16t), _p(a16st), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), _p(rowmeta), _p(lpb),
+                          _p(lpl), _p(plan.act_lens), _p(plan.label_lens), B, T, U1, plan.ntub, H, V, ctx.blank,
+                          ctx.bf16, _p(d_w), _p(d_b), plan.idx, st, label="ttx_joint_grad[dW]")
+                    ctx.kept = None
+                elif need_w:
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
                           st, n_kernels=1, label="ttx_joint_grad[dW]")
