@@ -135,7 +135,8 @@ int ttx_joint_fwd_grad_keep(const void* a16, const void* w16, const void* w16t, 
                             int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* pstore,
                             int32_t* pflags, float* pfac, int device, void* stream);
 /* d_w_out += dL/dW_out, d_b_out += the dense part of dL/db_out (as ttx_joint_grad with d_act = NULL) from the kept
- * matrix: scales A16^T by w * pfac into a16st ((H + 16) x rows_ub, 16 bit, scratch owned by the caller), adds the exact
+ * matrix: scales A16^T by w * pfac into a16st (scratch owned by the caller: (H + 16) x rows_ub 16-bit values followed by
+ * 64 x (H + 4) floats), adds the exact
  * blank / label terms, then dW += P'^T . As on the tensor cores.  If pflags[16383] != 0 those launches are no-ops and
  * the recomputing kernel of ttx_joint_grad runs instead (decided on the device, no host synchronisation). */
 int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float* pfac, const void* a16, const void* w16,

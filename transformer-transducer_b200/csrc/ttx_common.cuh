@@ -328,6 +328,19 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
     return r;
 }
 
+// First 16-bit value of a word as float (and the second one).
+template <bool BF16>
+__device__ __forceinline__ void unpk16(uint32_t v, float& a, float& b) {
+    if (BF16) {
+        a = __uint_as_float(v << 16);
+        b = __uint_as_float(v & 0xffff0000u);
+    } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&v);
+        a = __low2float(h);
+        b = __high2float(h);
+    }
+}
+
 }  // namespace ttx
 
 // ---------------------------------------------------------------- host-side error plumbing

@@ -629,12 +629,14 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
-    // KEPT (weight gradient, p.keep): the forward+gradient launch left P' for every lattice row in global memory.  Every
-    // item is then a replay: A operand = P'^T (MN-major, straight from the row-major P' matrix: two [64 m x 64 v] boxes
-    // per stage), B operand = the scaled A16^T chunk; no S pass, no exponentials, no P' buffers.  mapScr = P' matrix,
-    // mapYT = scaled A16^T (H + 16 rows), mapY = its last 16 rows (8-row boxes): As = 1 * scale, whose product with P'
-    // (a 16-column accumulator next to G, first slab only) is the dense part of db.
+    // KEPT (weight gradient, p.keep): the forward+gradient launch left P' for every lattice row in global memory.  A unit
+    // is then ONE item without S pass, exponentials or P' buffers: per 64 lattice rows the ring takes a group of three
+    // stages -- P'^T (the A operand, MN-major, straight from the row-major P' matrix: two [64 m x 64 v] boxes) and the
+    // scaled A16^T chunks of both slabs (B operands) -- and eight MMAs accumulate both G slabs (all 512 TMEM columns).
+    // mapScr = P' matrix, mapYT = scaled A16^T (H + 16 rows), mapY = its last 16 rows (8-row boxes) = the row scales
+    // themselves: the idle epilogue warps multiply them with the P' stage in shared memory for the dense part of db.
     const bool kept = (MODE == MODE_DW) && p.keep != 0;
+    constexpr int kKG = 3;                            // kept: ring stages per group, groups in flight (9 stages)
     // Persistent: the grid is one CTA pair per SM pair and each pair walks work units one after the other, all slabs of
     // a unit in turn, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
     // behind the read-out of G, and TMEM / barriers are set up once.  FG / DA: unit = tile pair, streams the whole
@@ -661,7 +663,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         return n_iter > 0;
     };
-    const int n_hl = p.n_halves;                      // slabs per unit
+    const int n_hl = kept ? 1 : p.n_halves;           // items per unit: one per slab (kept: both slabs in one item)
     auto unit_tile = [&](int unit) { return (MODE == MODE_DW ? (unit % n_vq) * 2 : unit * 2) + (int)rank; };
     auto slab_of = [&](int hh) { return hh; };
     // Forward+gradient with a scratch area (REPLAY): the first slab of a unit also sends every P' sub-tile to a scratch
@@ -714,6 +716,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     static_assert(kPB == 2, "barrier slots 40..42 are used below");
     auto bar_pwritten = [&](int b) { return sBar + 8 * (40 + b); };  // REPLAY: this CTA's epilogue warps wrote buffer b
     const uint32_t bar_unit = sBar + 8 * 42;                         // REPLAY: first slab of the unit is complete
+    auto bar_cons = [&](int g) { return bar_full(kRB + kKG * kKG + g); };   // KEPT: the MMAs have read group g's stages
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -728,7 +731,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
         for (int s = 0; s < 16; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
+            // kept: the P' and first As^T stage of a group are released by this CTA's epilogue warps (which read them
+            // after the MMAs, see bar_cons), the third stage by the MMAs' commit as everywhere else
+            const bool epi_released = kept && s >= kRB && s < kRB + kKG * kKG && (s - kRB) % kKG != kKG - 1;
+            mbar_init(bar_empty(s), epi_released ? kPairEpiWarps : 1);
         }
         mbar_init(bar_sfull, 1);
         mbar_init(bar_sempty, 2 * kPairEpiWarps);       // every epilogue warp of both CTAs
@@ -784,22 +790,24 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 if (!begin_unit(unit)) break;
                 if (kept) {
                     const int v0 = unit_tile(unit) * kTile;     // this CTA's vocabulary rows = columns of the P' matrix
-                    for (int hh = 0; hh < n_hl; ++hh)
-                        for (int i = 0; i < n_iter; ++i)
-                            for (int c = 0; c < 4; ++c) {
-                                const int m0 = (j0 + i) * NT + c * kKC;
+                    for (int i = 0; i < n_iter; ++i)
+                        for (int c = 0; c < 4; ++c) {
+                            const int m0 = (j0 + i) * NT + c * kKC;
+                            uint32_t full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
+                            mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
+                            if (leader) mbar_arrive_expect_tx(full, 2 * STAGE);
+                            tma_load_2d_pair(dst, &mapScr, full, v0, m0);
+                            tma_load_2d_pair(dst + STAGE / 2, &mapScr, full, v0 + kKC, m0);
+                            rr.advance(kKG * kKG);
+                            for (int hh = 0; hh < 2; ++hh) {
+                                full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
                                 mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
-                                if (leader) mbar_arrive_expect_tx(bar_full(kRB + rr.stage), 2 * STAGE);
-                                tma_load_2d_pair(sX + rr.stage * STAGE, &mapScr, bar_full(kRB + rr.stage), v0, m0);
-                                tma_load_2d_pair(sX + rr.stage * STAGE + STAGE / 2, &mapScr, bar_full(kRB + rr.stage), v0 + kKC, m0);
-                                rr.advance(nrs);
-                                mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
-                                if (leader) mbar_arrive_expect_tx(bar_full(kRB + rr.stage), 2 * (hh2 * 128 + (hh == 0 ? 1024 : 0)));
-                                tma_load_2d_pair(sX + rr.stage * STAGE, &mapYT, bar_full(kRB + rr.stage), m0, hh * p.HH + (int)rank * hh2);
-                                if (hh == 0)
-                                    tma_load_2d_pair(sRing + (rr.stage >> 1) * 1024, &mapY, bar_full(kRB + rr.stage), m0, p.H + (int)rank * 8);
-                                rr.advance(nrs);
+                                if (leader) mbar_arrive_expect_tx(full, 2 * (hh2 * 128 + (hh == 0 ? 1024 : 0)));
+                                tma_load_2d_pair(dst, &mapYT, full, m0, hh * p.HH + (int)rank * hh2);
+                                if (hh == 0) tma_load_2d_pair(sRing + (rr.stage / kKG) * 1024, &mapY, full, m0, p.H + (int)rank * 8);
+                                rr.advance(kKG * kKG);
                             }
+                        }
                     continue;
                 }
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
@@ -921,9 +929,21 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
-                    if (kept || (rp && hh == 1)) {
-                        if (!kept) mbar_wait(bar_unit, uidx & 1);
-                        if (kept || unit_clean(unit, uidx)) {
+                    if (kept) {
+                        for (int i = 0; i < n_iter; ++i)
+                            for (int c = 0; c < 4; ++c) {
+                                if (i == 0 && c == 0) mbar_wait(bar_gempty, (it - 1) & 1);
+                                for (int g = 0; g < kKG; ++g) {
+                                    mbar_wait(bar_full(kRB + rr.stage), rr.phase);
+                                    rr.advance(kKG * kKG);
+                                }
+                                publish();
+                            }
+                        continue;
+                    }
+                    if (rp && hh == 1) {
+                        mbar_wait(bar_unit, uidx & 1);
+                        if (unit_clean(unit, uidx)) {
                             for (int i = 0; i < n_iter; ++i)
                                 for (int c = 0; c < 4; ++c) {
                                     if (i == 0 && c == 0) mbar_wait(bar_gempty, (it - 1) & 1);
@@ -1011,24 +1031,22 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                         replay = unit_clean(unit, uidx);
                     }
                     if (kept) {
-                        // G(slab hh) += P'^T(stage) . As^T chunk(next stage); slab 0 also D2 += P'^T . scale rows
-                        const uint32_t idescGm = make_idesc(fmt, 1, 0, 256, p.HH), idescD = make_idesc(fmt, 1, 0, 256, 16);
+                        // G(slab 0 | slab 1) += P'^T(stage r) . As^T chunks (stages r + 1 | r + 2)
+                        const uint32_t idescGm = make_idesc(fmt, 1, 0, 256, p.HH);
                         const uint32_t amn = (xlo & 0xFFFFu) | (512u << 16);     // MN-major: 64-wide blocks 8 KiB apart
-                        const uint32_t olo = desc_lo(sRing);
                         for (int i = 0; i < n_iter; ++i)
                             for (int c = 0; c < 4; ++c) {
                                 wait_event();
                                 tc_fence_after();
-                                const int s2 = rstage + 1;                        // stages come in (P', As^T) pairs
-                                const uint32_t a = amn + rstage * 1024, b = xlo + s2 * 1024, o = olo + (s2 >> 1) * 64;
+                                const uint32_t a = amn + rstage * 1024, b0 = xlo + (rstage + 1) * 1024, b1 = b0 + 1024;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma_f16_ss_pair_lo(tmem_G, a + 128 * k, b + 2 * k, idescGm, (i | c | k) != 0);
-                                    if (hh == 0) umma_f16_ss_pair_lo(tmem_base, a + 128 * k, o + 2 * k, idescD, (i | c | k) != 0);
+                                    umma_f16_ss_pair_lo(tmem_base, a + 128 * k, b0 + 2 * k, idescGm, (i | c | k) != 0);
+                                    umma_f16_ss_pair_lo(tmem_G, a + 128 * k, b1 + 2 * k, idescGm, (i | c | k) != 0);
                                 }
-                                umma_commit_pair(bar_empty(kRB + rstage));
-                                umma_commit_pair(bar_empty(kRB + s2));
-                                rstage = (s2 + 1 == nrs) ? 0 : s2 + 1;
+                                umma_commit_pair(bar_cons(rstage / kKG));          // the epilogue warps release r and r + 1
+                                umma_commit_pair(bar_empty(kRB + rstage + 2));
+                                rstage = (rstage + kKG == kKG * kKG) ? 0 : rstage + kKG;
                             }
                     } else if (replay) {
                         // G(slab 1) += P'(i, c) . W16^T chunk, both operands from consecutive ring stages
@@ -1131,6 +1149,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             pr = r;
         };
         int it = 0, gs0 = 0, uidx = 0;                // items, S passes (accumulator barrier parity), units so far
+        Ring kr;                                      // KEPT: ring position (first stage of the current group)
         float f_keep = 0.f;                           // REPLAY: the row's output scale, from the unit's first slab
         for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
         if (!begin_unit(unit)) break;
@@ -1143,7 +1162,56 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             replay = unit_clean(unit, uidx);
         }
         if (et == 0) trace_at(p, 0, it, 0);
-        if (MODE == MODE_FG) {
+        if (kept) {
+            // ---- kept P': nothing to do per stream tile but the dense part of db[v] = sum_m s_m P'[m, v]: thread (v, mh)
+            // takes half of each stage's 64 lattice rows for vocabulary row v of this CTA, from the P' stage and the row
+            // scales (row 0 of the 8-row scale tile) once the MMAs have read the group, then the warp releases both stages
+            const int v = et & (kTile - 1), mh = et >> 7;
+            const uint8_t* sX_gen = smem_gen + (sX - smem_base);
+            const uint8_t* sS_gen = smem_gen + (sRing - smem_base);
+            float dacc = 0.f;
+            for (int i = 0; i < n_iter; ++i)
+                for (int c = 0; c < 4; ++c) {
+                    const int g = kr.stage / kKG;
+                    mbar_wait(bar_cons(g), kr.phase);
+                    const uint8_t* pst = sX_gen + kr.stage * STAGE + (v >> 6) * (STAGE / 2) + (v & 7) * 2;
+                    const uint16_t* sc = reinterpret_cast<const uint16_t*>(sS_gen + g * 1024);
+                    const int vc = (v & 63) >> 3;
+#pragma unroll 8
+                    for (int m = mh * 32; m < mh * 32 + 32; ++m) {
+                        const uint32_t pv = *reinterpret_cast<const uint16_t*>(pst + m * 128 + ((vc ^ (m & 7)) << 4));
+                        const uint32_t sv = sc[m];
+                        float pf_, sf_, d0, d1;
+                        unpk16<BF16>(pv, pf_, d0);
+                        unpk16<BF16>(sv, sf_, d1);
+                        dacc = fmaf(pf_, sf_, dacc);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar_empty(kRB + kr.stage));
+                        mbar_arrive(bar_empty(kRB + kr.stage + 1));
+                    }
+                    kr.advance(kKG * kKG, kKG);
+                }
+            const int vrow = x_row0 + row;
+            const float f = p.scal[2] * (BF16 ? 1.0f : 5.9604644775390625e-8f);   // the As operand carries 2^24 (fp16)
+            if (x_row0 + v < p.V) atomicAdd(p.db + x_row0 + v, dacc * f);
+            mbar_wait(bar_gfull, it & 1);
+            tc_fence_after();
+            const bool ok = vrow < p.V;
+            uint32_t gacc[32];
+            for (int cc = ch; cc < 2 * (p.HH / 32); cc += 2) {           // both slabs: TMEM column cc * 32 <-> joint column
+                tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
+                tmem_ld_wait();
+                if (ok) {
+                    float* dst = p.dW + (size_t)vrow * p.H + cc * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        red_add_v4(dst + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                   __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
+                }
+            }
+        } else if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
             // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
             // mref (log2 units).  The reference is fixed by the first tile and only moves when a later tile would
@@ -1366,9 +1434,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 krow = fmaf(rm.x, -kLog2e, lg_scale);
             } else {
                 vrow = x_row0 + row;
-                if (!kept) krow = __ldg(p.bias2 + vrow);
+                krow = __ldg(p.bias2 + vrow);
             }
-            for (int i = 0; i < ((replay || kept) ? 0 : n_iter); ++i) {
+            for (int i = 0; i < (replay ? 0 : n_iter); ++i) {
                 const int t0 = (j0 + i) * NT;               // first vocab id (DA) / lattice row (DW) of this stream tile
                 float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
                 int clabel = -1;
@@ -1458,7 +1526,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }, i);
             }
-            if (!replay && !kept) gs0 += n_iter;
+            if (!replay) gs0 += n_iter;
             // ---- final: G (128 x HH fp32 in TMEM) -> global
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
@@ -1482,16 +1550,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }
             } else {
-                // kept: the As operand carries 2^24 (fp16) on top of w * pfac
-                const float f = kept ? gmax * (BF16 ? 1.0f : 5.9604644775390625e-8f) : gmax / pscale;
+                const float f = gmax / pscale;
                 const bool ok = vrow < p.V;
                 float* dst = p.dW + (size_t)vrow * p.H + half * p.HH;
-                if (kept && half == 0) {                   // dense part of db: column 0 of the 16-column accumulator
-                    uint32_t d2[16];
-                    tmem_ld16(tmem_base + lane_addr, d2);
-                    tmem_ld_wait();
-                    if (ok && ch == 0) atomicAdd(p.db + vrow, __uint_as_float(d2[0]) * f);
-                }
                 for (int cc = ch; cc < ngrp; cc += 2) {
                     tmem_ld32(tmem_G + lane_addr + cc * 32, gacc);
                     tmem_ld_wait();
@@ -1503,7 +1564,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     }
                 }
                 // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
-                if (ok && half == 0 && !replay && !kept) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
+                if (ok && half == 0 && !replay) atomicAdd(p.db + vrow, db_acc * gmax / pscale);
             }
         }
         if (PERSIST) {                                // G has left TMEM: the next item may overwrite it

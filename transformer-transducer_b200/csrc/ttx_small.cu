@@ -781,19 +781,8 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
 // straight into the tensor core).  Sixteen extra rows h = H .. H+15 hold As = 2^shift * w_m * pfac_m (A = 1): their
 // product with P' is the dense part of db.  shift (24 for fp16, 0 for bf16) keeps As out of the subnormals.
 // Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.  No-op if the P' matrix is flagged.
-template <bool BF16>
-__device__ __forceinline__ void unpack16(uint32_t v, float& a, float& b) {
-    if (BF16) {
-        a = __uint_as_float(v << 16);
-        b = __uint_as_float(v & 0xffff0000u);
-    } else {
-        const __half2 h = *reinterpret_cast<const __half2*>(&v);
-        a = __low2float(h);
-        b = __high2float(h);
-    }
-}
-
 constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T) per block
+constexpr int kBlankSlots = 64;                 // partial rows for the blank row's accumulation
 template <bool BF16>
 __global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float4* __restrict__ rowmeta,
                                   const float* __restrict__ pfac, const int* __restrict__ meta,
@@ -823,7 +812,7 @@ __global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float a, b;
-                unpack16<BF16>(w4[e], a, b);
+                unpk16<BF16>(w4[e], a, b);
                 r4[e] = pack16<BF16>(a * s[2 * e], b * s[2 * e + 1]);
             }
             o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
@@ -845,7 +834,8 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
                                  const float* __restrict__ lpl, const float* __restrict__ scal,
                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,
                                  const int* __restrict__ meta, const int* __restrict__ flags, int U1, int H, int blank,
-                                 int t_chunk, float* __restrict__ d_w, float* __restrict__ d_b) {
+                                 int t_chunk, float* __restrict__ d_w, float* __restrict__ d_b,
+                                 float* __restrict__ blank_slots) {
     if (flags[kKeptAnyDirty] != 0 || meta[1] != 0) return;
     const int u = blockIdx.x, b = blockIdx.y;
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
@@ -859,24 +849,40 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
     for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
         float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), al = ab;
         float dbb = 0.f, dbl = 0.f;
-        for (int t = t0; t < t1; ++t) {
-            const size_t m = base + (size_t)t * U1b + u;
-            const float4 rm = __ldg(rowmeta + m);
-            const uint2 av = __ldg(reinterpret_cast<const uint2*>(a16 + m * H + h));
-            float a0, a1, a2, a3;
-            unpack16<BF16>(av.x, a0, a1);
-            unpack16<BF16>(av.y, a2, a3);
-            const float cb = rm.w * rm.y, cl = rm.w * rm.z;
-            ab.x = fmaf(cb, a0, ab.x); ab.y = fmaf(cb, a1, ab.y); ab.z = fmaf(cb, a2, ab.z); ab.w = fmaf(cb, a3, ab.w);
-            if (has_label) {
-                al.x = fmaf(cl, a0, al.x); al.y = fmaf(cl, a1, al.y); al.z = fmaf(cl, a2, al.z); al.w = fmaf(cl, a3, al.w);
+        for (int tb = t0; tb < t1; tb += 8) {
+            // eight frames per round: all loads of the round are issued before the first use
+            float4 rm[8];
+            uint2 av[8];
+            float eb[8], el[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const bool in = tb + e < t1;
+                const size_t m = base + (size_t)(in ? tb + e : t0) * U1b + u;
+                rm[e] = __ldg(rowmeta + m);
+                av[e] = __ldg(reinterpret_cast<const uint2*>(a16 + m * H + h));
+                if (!in) rm[e].w = 0.f;
+                eb[e] = (h == 0) ? __ldg(lpb + m) : 0.f;
+                el[e] = (h == 0 && has_label) ? __ldg(lpl + m) : 0.f;
             }
-            if (h == 0) {
-                dbb = fmaf(rm.w, __expf(__ldg(lpb + m)), dbb);
-                if (has_label) dbl = fmaf(rm.w, __expf(__ldg(lpl + m)), dbl);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float a0, a1, a2, a3;
+                unpk16<BF16>(av[e].x, a0, a1);
+                unpk16<BF16>(av[e].y, a2, a3);
+                const float cb = rm[e].w * rm[e].y, cl = rm[e].w * rm[e].z;
+                ab.x = fmaf(cb, a0, ab.x); ab.y = fmaf(cb, a1, ab.y); ab.z = fmaf(cb, a2, ab.z); ab.w = fmaf(cb, a3, ab.w);
+                if (has_label) {
+                    al.x = fmaf(cl, a0, al.x); al.y = fmaf(cl, a1, al.y); al.z = fmaf(cl, a2, al.z); al.w = fmaf(cl, a3, al.w);
+                }
+                if (h == 0) {
+                    dbb = fmaf(rm[e].w, __expf(eb[e]), dbb);
+                    if (has_label) dbl = fmaf(rm[e].w, __expf(el[e]), dbl);
+                }
             }
         }
-        float* db_ = d_w + (size_t)blank * H + h;
+        // every block adds to the blank row: spread over kBlankSlots partial rows (same-address atomics serialise in L2),
+        // folded into d_w[blank] / d_b[blank] by blank_fold_kernel
+        float* db_ = blank_slots + (size_t)((blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * 7) % kBlankSlots) * (H + 4) + h;
         atomicAdd(db_ + 0, ab.x * gmax); atomicAdd(db_ + 1, ab.y * gmax);
         atomicAdd(db_ + 2, ab.z * gmax); atomicAdd(db_ + 3, ab.w * gmax);
         if (has_label) {
@@ -885,10 +891,21 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
             atomicAdd(dl + 2, al.z * gmax); atomicAdd(dl + 3, al.w * gmax);
         }
         if (h == 0) {
-            atomicAdd(d_b + blank, dbb * gmax);
+            atomicAdd(db_ + H, dbb * gmax);
             if (has_label) atomicAdd(d_b + lab, dbl * gmax);
         }
     }
+}
+
+__global__ void blank_fold_kernel(const float* __restrict__ blank_slots, const int* __restrict__ flags, int H, int blank,
+                                  float* __restrict__ d_w, float* __restrict__ d_b) {
+    if (flags[kKeptAnyDirty] != 0) return;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > H) return;
+    float acc = 0.f;
+    for (int k = 0; k < kBlankSlots; ++k) acc += blank_slots[(size_t)k * (H + 4) + h];
+    if (h < H) atomicAdd(d_w + (size_t)blank * H + h, acc);
+    else atomicAdd(d_b + blank, acc);
 }
 
 int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta, const int* row_label,
@@ -906,12 +923,17 @@ int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta
     const int t_chunk = 64;
     const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
     const int threads = min(256, max(32, H / 4));
+    // the partial rows live behind the (H + 16) x rows_total matrix in the caller's a16st buffer
+    float* slots = reinterpret_cast<float*>(static_cast<uint8_t*>(a16st) + (size_t)(H + 16) * rows_total * 2);
+    const size_t slot_bytes = (size_t)kBlankSlots * (H + 4) * sizeof(float);
+    TTX_CUDA_OK(cudaMemsetAsync(slots, 0, slot_bytes, s));
     if (bf16)
         dw_sparse_kernel<true><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                      label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b);
+                                                      label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b, slots);
     else
         dw_sparse_kernel<false><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                       label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b);
+                                                       label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b, slots);
+    blank_fold_kernel<<<(H + 1 + 127) / 128, 128, 0, s>>>(slots, flags, H, blank, d_w, d_b);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

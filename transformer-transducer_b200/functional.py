@@ -24,7 +24,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 4, "ttx_reduce_act_grad_ew": 2, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew": 2, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -209,7 +209,7 @@ class FusedJointRNNT(torch.autograd.Function):
                           n_kernels=1, label="ttx_joint_grad[dA]")
                 if need_w and ctx.kept is not None:
                     pstore, pflags, pfac = ctx.kept
-                    a16st = torch.empty((H + 16) * plan.rows, dtype=torch.int16, device=dev)
+                    a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
                     _call("ttx_weight_grad_kept", dev, _p(pstore), _p(pflags), _p(pfac), _p(a16), _p(w16), _p(a16t),
                           _p(w16t), _p(a16st), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), _p(rowmeta), _p(lpb),
                           _p(lpl), _p(plan.act_lens), _p(plan.label_lens), B, T, U1, plan.ntub, H, V, ctx.blank,
