@@ -267,8 +267,9 @@ def test_unsupported_width_uses_dense_entry_and_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
-@pytest.mark.parametrize("H", [256, 512])        # 512: two slabs (P' replay) in the bf16 instantiation
-def test_bf16_input_variant_stated_tolerance(H):
+@pytest.mark.parametrize("H,keep", [(256, "32"), (512, "32"), (512, "0")])   # 512: two slabs; kept P' / recompute
+def test_bf16_input_variant_stated_tolerance(H, keep, monkeypatch):
+    monkeypatch.setenv("TTX_KEEP_GB", keep)
     case = _espnet_case(2, 40, 8, 500, 64, H, [40, 31], [8, 5], seed=9)
     errs, (_, _, got) = _run_pair(*case, dtype=torch.bfloat16)
     _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
@@ -282,16 +283,19 @@ def test_c_abi_rejects_unsupported_width_with_message():
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
-@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"}, {"TTX_QUAD": "1"},
-                                 {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"}, {"TTX_REPLAY": "0"}, {"TTX_DW_CHUNKS": "2"},
-                                 {"TTX_DW_CHUNKS": "2", "TTX_REPLAY": "0"}, {}])
+@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"},
+                                 {"TTX_QUAD": "1", "TTX_KEEP_GB": "0"}, {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"},
+                                 {"TTX_REPLAY": "0"}, {"TTX_DW_CHUNKS": "2"}, {"TTX_KEEP_GB": "0"},
+                                 {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2"},
+                                 {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2", "TTX_REPLAY": "0"}, {}])
 def test_kernel_variants_agree_with_oracle(env, monkeypatch):
     """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
     kernel (TTX_NO_FWD_GRAD=1), the quad kernel for the weight gradient (TTX_QUAD=1) and for both gradients
-    (TTX_QUAD=2), the pair kernels without their P' replay (TTX_REPLAY=0), the weight gradient cut into several
-    lattice-row splits with a short last one (TTX_DW_CHUNKS=2: 2 + 2 + 1 stream chunks), and the default kernels
-    (persistent pair kernels with replay) all meet the tolerance on a batch with an odd number of lattice tiles (the pad
-    tile of the last pair / quad)."""
+    (TTX_QUAD=2), the forward+gradient kernel without its P' replay (TTX_REPLAY=0), the weight gradient cut into several
+    lattice-row splits with a short last one (TTX_DW_CHUNKS=2: 2 + 2 + 1 stream chunks), the recomputing weight gradient
+    (TTX_KEEP_GB=0: nothing kept between forward and backward; with and without replay) and the default kernels
+    (forward+gradient launch that keeps P', weight gradient as one product on it) all meet the tolerance on a batch
+    with an odd number of lattice tiles (the pad tile of the last pair / quad)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)
