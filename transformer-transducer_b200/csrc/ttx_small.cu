@@ -119,13 +119,21 @@ __global__ void cast_w_kernel(const float* __restrict__ w, const float* __restri
 // ------------------------------------------------------------------------------------------- A16 = tanh(E + P)
 // The joint's broadcast-add + tanh (/root/reference/tt/model.py:22-36 after splitting forward_layer,
 // espnet joint_network.py:48) written once per lattice cell as the 16-bit tensor-core operand.
+// tanh from one exponential and one reciprocal: (1 - e) / (1 + e), e = exp(-2|x|).  Absolute error ~1e-7 (the result
+// is rounded to 16 bits, 2.4e-4 relative, right after); tanhf() costs three times the instructions and this kernel
+// is issue-bound.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
 template <bool BF16>
 __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* __restrict__ pproj,
                                  const int* __restrict__ labels, const int* __restrict__ act_lens,
                                  const int* __restrict__ label_lens, const int* __restrict__ meta, int B, int T,
                                  int U1, int H, int label_stride, uint16_t* __restrict__ a16,
                                  int* __restrict__ row_label, uint16_t* __restrict__ a16t, size_t rows_total) {
-    __shared__ uint16_t tr[64][kTile + 2];       // one 64-column slab of the tile, for the transposed copy
+    __shared__ uint32_t tr[kTile][33];           // one 64-column slab of the tile (row-major, 33-word rows), for the transposed copy
     const int tile = blockIdx.x;
     if (tile >= meta[0]) {
         // CTA pairs work on tile pairs: with an odd tile count the partner of the last tile must read zeros
@@ -158,28 +166,25 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
                 const float4* e4 = reinterpret_cast<const float4*>(eb + (size_t)t * H + vc * 8);
                 const float4* p4 = reinterpret_cast<const float4*>(pb + (size_t)u * H + vc * 8);
                 const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
-                out.x = pack16<BF16>(tanhf(e0.x + p0.x), tanhf(e0.y + p0.y));
-                out.y = pack16<BF16>(tanhf(e0.z + p0.z), tanhf(e0.w + p0.w));
-                out.z = pack16<BF16>(tanhf(e1.x + p1.x), tanhf(e1.y + p1.y));
-                out.w = pack16<BF16>(tanhf(e1.z + p1.z), tanhf(e1.w + p1.w));
+                out.x = pack16<BF16>(tanh_fast(e0.x + p0.x), tanh_fast(e0.y + p0.y));
+                out.y = pack16<BF16>(tanh_fast(e0.z + p0.z), tanh_fast(e0.w + p0.w));
+                out.z = pack16<BF16>(tanh_fast(e1.x + p1.x), tanh_fast(e1.y + p1.y));
+                out.w = pack16<BF16>(tanh_fast(e1.z + p1.z), tanh_fast(e1.w + p1.w));
             }
             *reinterpret_cast<uint4*>(a16 + ((size_t)tile * kTile + lr) * H + vc * 8) = out;
             if (a16t) {
-                const int c = (idx & 7) * 8;
-                const uint32_t w4[4] = {out.x, out.y, out.z, out.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    tr[c + 2 * e][lr] = (uint16_t)(w4[e] & 0xffff);
-                    tr[c + 2 * e + 1][lr] = (uint16_t)(w4[e] >> 16);
-                }
+                // word stores, conflict-free: bank = (row + 4 * (idx & 7) + j) mod 32 over a warp's 4 rows x 8 vectors
+                uint32_t* dst = &tr[lr][(idx & 7) * 4];
+                dst[0] = out.x; dst[1] = out.y; dst[2] = out.z; dst[3] = out.w;
             }
         }
         if (a16t) {
             __syncthreads();
             for (int idx = threadIdx.x; idx < 64 * (kTile / 2); idx += blockDim.x) {
                 const int c = idx / (kTile / 2), r2 = idx % (kTile / 2);
-                const uint32_t v = (uint32_t)tr[c][2 * r2] | ((uint32_t)tr[c][2 * r2 + 1] << 16);
-                *reinterpret_cast<uint32_t*>(a16t + (size_t)(h0 + c) * rows_total + (size_t)tile * kTile + 2 * r2) = v;
+                const int sh = (c & 1) * 16;
+                const uint32_t lo = (tr[2 * r2][c >> 1] >> sh) & 0xffffu, hi = (tr[2 * r2 + 1][c >> 1] >> sh) & 0xffffu;
+                *reinterpret_cast<uint32_t*>(a16t + (size_t)(h0 + c) * rows_total + (size_t)tile * kTile + 2 * r2) = lo | (hi << 16);
             }
             __syncthreads();
         }
