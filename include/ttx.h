@@ -125,7 +125,8 @@ int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const
                        const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                        int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream);
 /* Same launch, but the softmax numerators P' it computes anyway (16 bit, blank / label entries zero) are KEPT in the
- * caller's matrix pstore (rows_ub x Vpad, rows_ub = 128 * n_tiles_ub, Vpad = V rounded up to 256) instead of a bounded
+ * caller's matrix pstore (rows_ub x Vpad 16-bit values, rows_ub = 128 * n_tiles_ub, Vpad = V rounded up to 256; stored
+ * in 64-column blocks, [Vpad / 64][rows_ub][64], so that every tile the kernels move is contiguous) instead of a bounded
  * scratch area, with pfac (rows): softmax(row, v) = pstore[row, v] * pfac[row].  pflags: 16384 int32, zeroed by the
  * caller; word 16383 != 0 afterwards means some row's running reference moved and the matrix must not be used.
  * H = 512 only.  The weight gradient is then one product on the kept matrix (ttx_weight_grad_kept) -- no second

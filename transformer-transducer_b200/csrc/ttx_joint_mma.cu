@@ -45,6 +45,7 @@ struct MmaParams {
     float* db;             // DW out (V)
     uint8_t* scratch;      // pair kernel: flags (64 KiB) of the P' scratch matrix (replay), or null
     int keep;              // the P' matrix covers every lattice row (rows_ub x Vpad) and is kept for the weight gradient
+    int scr_rows;          // rows R of the P' matrix; it is stored in 64-column blocks, [cols / 64][R][64]
     float* pfac;           // FG out (rows), optional: softmax(row, v) = P'(row, v) * pfac[row]
     const int* run_if;     // DW, optional: the launch is a no-op unless (*run_if != 0) == (run_if_val != 0)
     int run_if_val;
@@ -796,8 +797,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             uint32_t full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
                             mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
                             if (leader) mbar_arrive_expect_tx(full, 2 * STAGE);
-                            tma_load_2d_pair(dst, &mapScr, full, v0, m0);
-                            tma_load_2d_pair(dst + STAGE / 2, &mapScr, full, v0 + kKC, m0);
+                            tma_load_2d_pair(dst, &mapScr, full, 0, (v0 / kKC) * p.scr_rows + m0);
+                            tma_load_2d_pair(dst + STAGE / 2, &mapScr, full, 0, (v0 / kKC + 1) * p.scr_rows + m0);
                             rr.advance(kKG * kKG);
                             for (int hh = 0; hh < 2; ++hh) {
                                 full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
@@ -828,7 +829,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             };
                             for (int i = 0; i < n_iter; ++i)
                                 for (int c = 0; c < 4; ++c) {
-                                    load_rstage(&mapScr, (i * 4 + c) * kKC, scr_row(x_row0), STAGE);
+                                    load_rstage(&mapScr, 0, (i * 4 + c) * p.scr_rows + scr_row(x_row0), STAGE);
                                     load_rstage(&mapYT, (j0 + i) * NT + c * kKC, h0, hh2 * 128);
                                 }
                             replayed = true;
@@ -873,7 +874,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             if (hh == 0) {
                                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                              ::"l"(reinterpret_cast<uint64_t>(&mapScr)), "r"(sP + sr.buf * kChunkBytes),
-                                               "r"((i * 4 + c) * kKC), "r"(scr_row(unit_tile(unit) * kTile))
+                                               "r"(0), "r"((i * 4 + c) * p.scr_rows + scr_row(unit_tile(unit) * kTile))
                                              : "memory");
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -2465,7 +2466,8 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
             set_error("ttx_joint_fwd_grad: the kept P' matrix needs H = 512, flags, pfac and at most 16383 tile pairs");
             return 1;
         }
-        if (int rc = make_matrix_map(&mscr, pstore, rows_ub, (uint64_t)n_chunks * 256, bf16, kTile)) return rc;
+        if (int rc = make_matrix_map(&mscr, pstore, rows_ub * (uint64_t)(n_chunks * 4), kKC, bf16, kTile)) return rc;
+        p.scr_rows = (int)rows_ub;
         p.scratch = reinterpret_cast<uint8_t*>(pflags);
         p.keep = 1;
         p.pfac = pfac;
@@ -2473,9 +2475,10 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     } else if (p.n_halves == 2 && replay_enabled()) {
         const size_t bytes = 65536 + (size_t)grid.x * kTile * n_chunks * 256 * 2;
         if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
-        if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
-                                     (uint64_t)n_chunks * 256, bf16, kTile))
+        if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536,
+                                     (uint64_t)grid.x * kTile * (uint64_t)(n_chunks * 4), kKC, bf16, kTile))
             return rc;
+        p.scr_rows = (int)(grid.x * kTile);
         p.scratch = static_cast<uint8_t*>(scratch);
         have_map = true;
     }
@@ -2522,7 +2525,8 @@ int launch_joint_dw_kept(const void* pstore, const int* pflags, const void* a16s
     if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
     p.splits = dw_splits(n_st, n_vq, pairs, cap);
     CUtensorMap mp, myt, mones;
-    if (int rc = make_matrix_map(&mp, pstore, rows_ub, (uint64_t)Vpad, bf16, 64)) return rc;
+    if (int rc = make_matrix_map(&mp, pstore, rows_ub * (uint64_t)(Vpad / kKC), kKC, bf16, 64)) return rc;
+    p.scr_rows = (int)rows_ub;
     if (int rc = make_matrix_map(&myt, a16st, (uint64_t)H + 16, rows_ub, bf16, p.HH / 2)) return rc;
     if (int rc = make_matrix_map(&mones, a16st, (uint64_t)H + 16, rows_ub, bf16, 8)) return rc;
     dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
@@ -2655,9 +2659,10 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             if (p.n_halves == 2 && replay_enabled() && !run_if) {    // (the fallback of the kept-P' path runs without scratch)
                 const size_t bytes = 65536 + (size_t)grid.x * kTile * per * 256 * 2;
                 if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
-                if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536, (uint64_t)grid.x * kTile,
-                                             (uint64_t)per * 256, bf16, kTile))
+                if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536,
+                                             (uint64_t)grid.x * kTile * (uint64_t)(per * 4), kKC, bf16, kTile))
                     return rc;
+                p.scr_rows = (int)(grid.x * kTile);
                 p.scratch = static_cast<uint8_t*>(scratch);
             }
             int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr)
