@@ -804,8 +804,10 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                                 full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
                                 mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
                                 if (leader) mbar_arrive_expect_tx(full, 2 * (hh2 * 128 + (hh == 0 ? 1024 : 0)));
-                                tma_load_2d_pair(dst, &mapYT, full, m0, hh * p.HH + (int)rank * hh2);
-                                if (hh == 0) tma_load_2d_pair(sRing + (rr.stage / kKG) * 1024, &mapY, full, m0, p.H + (int)rank * 8);
+                                // the scaled A16^T is stored in 64-row blocks of lattice rows, [rows / 64][H + 16][64]
+                                const int hb = (m0 / kKC) * (p.H + 16);
+                                tma_load_2d_pair(dst, &mapYT, full, 0, hb + hh * p.HH + (int)rank * hh2);
+                                if (hh == 0) tma_load_2d_pair(sRing + (rr.stage / kKG) * 1024, &mapY, full, 0, hb + p.H + (int)rank * 8);
                                 rr.advance(kKG * kKG);
                             }
                         }
@@ -2490,7 +2492,7 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
 }
 
 // Weight gradient from the kept P' matrix (forward+gradient launch with pstore): dW += gmax 2^-shift P'^T . As, db likewise.
-// a16st = scaled A16^T with its 16 scale rows ((H + 16) x rows_ub, launch_kept_prepare).  No-op if the matrix is flagged.
+// a16st = scaled A16^T with its 16 scale rows, in 64-column blocks [rows_ub / 64][H + 16][64] (launch_kept_prepare).  No-op if the matrix is flagged.
 int launch_joint_dw_kept(const void* pstore, const int* pflags, const void* a16st, uint64_t rows_ub, int n_tiles_ub, int H,
                          int V, int Vpad, bool bf16, const int* meta, const float* scal, float* dW, float* db,
                          cudaStream_t stream) {
@@ -2527,8 +2529,8 @@ int launch_joint_dw_kept(const void* pstore, const int* pflags, const void* a16s
     CUtensorMap mp, myt, mones;
     if (int rc = make_matrix_map(&mp, pstore, rows_ub * (uint64_t)(Vpad / kKC), kKC, bf16, 64)) return rc;
     p.scr_rows = (int)rows_ub;
-    if (int rc = make_matrix_map(&myt, a16st, (uint64_t)H + 16, rows_ub, bf16, p.HH / 2)) return rc;
-    if (int rc = make_matrix_map(&mones, a16st, (uint64_t)H + 16, rows_ub, bf16, 8)) return rc;
+    if (int rc = make_matrix_map(&myt, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, p.HH / 2)) return rc;
+    if (int rc = make_matrix_map(&mones, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, 8)) return rc;
     dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
     int rc = bf16 ? launch_v3<MODE_DW, true>(mp, mones, myt, p, grid, smem, stream, &mp)
                   : launch_v3<MODE_DW, false>(mp, mones, myt, p, grid, smem, stream, &mp);

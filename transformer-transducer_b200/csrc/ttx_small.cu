@@ -784,7 +784,8 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
 // Then the dense part of the weight gradient is one product with no projection pass and no exponentials,
 //   dW[v, h] = gmax * 2^-shift * sum_m P'[m, v] * As[m, h],   As[m, h] = 2^shift * w_m * pfac_m * A16[m, h],
 // whose K-major B operand is the scaled transposed copy written here (the scale cannot ride on P': it is streamed
-// straight into the tensor core).  Sixteen extra rows h = H .. H+15 hold As = 2^shift * w_m * pfac_m (A = 1): their
+// straight into the tensor core; stored in blocks of 64 lattice rows).  Sixteen extra rows h = H .. H+15 hold
+// As = 2^shift * w_m * pfac_m (A = 1): their
 // product with P' is the dense part of db.  shift (24 for fp16, 0 for bf16) keeps As out of the subnormals.
 // Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.  No-op if the P' matrix is flagged.
 constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T) per block
@@ -826,7 +827,9 @@ __global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float
             o = make_uint4(pack16<BF16>(s[0], s[1]), pack16<BF16>(s[2], s[3]), pack16<BF16>(s[4], s[5]),
                            pack16<BF16>(s[6], s[7]));
         }
-        *reinterpret_cast<uint4*>(out + (size_t)h * rows_total + m0) = o;
+        // out is stored in 64-column blocks, [rows_total / 64][H + 16][64]: every box the weight-gradient kernel streams
+        // ([128 joint columns x 64 lattice rows]) is 16 KiB of contiguous memory
+        *reinterpret_cast<uint4*>(out + ((m0 >> 6) * (size_t)(H + 16) + h) * 64 + (m0 & 63)) = o;
     }
 }
 
