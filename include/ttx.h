@@ -59,7 +59,7 @@ int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
                   int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label,
-                  void* a16t /* NULL or (H, rows): transposed copy for the gradient pass */, int device, void* stream);
+                  void* a16t /* NULL or the transposed copy for the gradient pass, H x rows values stored in blocks of 64 rows: [rows / 64][H][64] */, int device, void* stream);
 
 /* tcgen05 projection A16 . W16^T + b_out fused with log-softmax statistics: per row lse, log p(blank),
  * log p(label).  The (B,T,U1,V) logits are never written. */
@@ -100,7 +100,8 @@ int ttx_rows_grad(const float* z, const void* rowmeta, const int32_t* row_label,
 
 /* out (cols, rows) = transpose of the row-major 16-bit matrix in (rows, cols); rows, cols multiples of 64.
  * meta != NULL: `in` is the A16 operand and row blocks beyond the tiles in use (meta[0]) are skipped.  Produces the
- * K-major operand copies W16^T (H, Vpad) and A16^T (H, rows) streamed by the backward pair kernel. */
+ * K-major operand copies W16^T (H, Vpad) and A16^T (with meta: blocks of 64 lattice rows, [rows / 64][H][64], the layout
+ * ttx_joint_act writes) streamed by the backward pair kernel. */
 int ttx_transpose16(const void* in, void* out, int rows, int cols, const int32_t* meta, int device, void* stream);
 
 int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const void* w16t, const float* bias2,

@@ -782,7 +782,12 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             };
             auto load_G = [&](int j, int half) {       // K-major B chunks: [hh2 joint columns x 64 stream rows]
                 const int h0 = half * p.HH + (int)rank * hh2;
-                for (int c = 0; c < 4; ++c) load_stage(&mapYT, j * NT + c * kKC, h0, hh2 * 128);
+                for (int c = 0; c < 4; ++c) {
+                    const int k0 = j * NT + c * kKC;
+                    // W16^T (FG / DA) is row-major [H][Vpad]; A16^T (DW) is stored in blocks of 64 lattice rows, [rows / 64][H][64]
+                    if (MODE == MODE_DW) load_stage(&mapYT, 0, (k0 / kKC) * p.H + h0, hh2 * 128);
+                    else load_stage(&mapYT, k0, h0, hh2 * 128);
+                }
             };
             int xt = 0, uidx = 0, it = 0;                       // X tiles loaded, units started, items started
             Ring rr;                                            // replay ring position
@@ -832,7 +837,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             for (int i = 0; i < n_iter; ++i)
                                 for (int c = 0; c < 4; ++c) {
                                     load_rstage(&mapScr, 0, (i * 4 + c) * p.scr_rows + scr_row(x_row0), STAGE);
-                                    load_rstage(&mapYT, (j0 + i) * NT + c * kKC, h0, hh2 * 128);
+                                    if (MODE == MODE_DW) load_rstage(&mapYT, 0, (((j0 + i) * NT + c * kKC) / kKC) * p.H + h0, hh2 * 128);
+                                    else load_rstage(&mapYT, (j0 + i) * NT + c * kKC, h0, hh2 * 128);
                                 }
                             replayed = true;
                             continue;
@@ -1755,7 +1761,10 @@ joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     for (int i = 0; i < n_iter; ++i)
                         for (int sp = 0; sp < 4; ++sp)
                             for (int sl = 0; sl < 2; ++sl)
-                                load_stage(&mapYT, (j0 + i) * NT + sp * kKC, sl * 256 + (int)c * kTile);
+                                if (MODE == MODE_DW)      // A16^T in blocks of 64 lattice rows, [rows / 64][H][64]
+                                    load_stage(&mapYT, 0, (((j0 + i) * NT + sp * kKC) / kKC) * p.H + sl * 256 + (int)c * kTile);
+                                else
+                                    load_stage(&mapYT, (j0 + i) * NT + sp * kKC, sl * 256 + (int)c * kTile);
                 }
             }
         } else if (warp == kQuadWatchWarp) {
@@ -2588,7 +2597,7 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             CUtensorMap mx, my, myt;
             if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
             if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile)) return rc;
-            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2)) return rc;
+            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H * (rows_ub / kKC), kKC, bf16, p.HH / 2)) return rc;
             p.splits = best;
             dim3 grid(4 * n_vq, 1, best);
             int rc = bf16 ? launch_quad<MODE_DW, true>(mx, my, myt, p, grid, smem, stream)
@@ -2642,7 +2651,7 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
             const int hs = (p.dbg & 8) ? 2 : 1;
             if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile / hs)) return rc;
-            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H, rows_ub, bf16, p.HH / 2 / hs)) return rc;
+            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H * (rows_ub / kKC), kKC, bf16, p.HH / 2 / hs)) return rc;
             // Persistent: units = vocabulary tile pairs x lattice-row splits of at most `cap` stream chunks -- a unit's P' must
             // fit its CTA's share of the scratch matrix (cap 160: 10 MiB per CTA, 1.5 GB on a B200).
             const int n_st = (n_tiles_ub + 1) / 2;

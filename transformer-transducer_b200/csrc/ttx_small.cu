@@ -141,10 +141,10 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
             uint4* dst = reinterpret_cast<uint4*>(a16 + (size_t)tile * kTile * H);
             for (int idx = threadIdx.x; idx < kTile * H / 8; idx += blockDim.x) dst[idx] = make_uint4(0, 0, 0, 0);
             for (int lr = threadIdx.x; lr < kTile; lr += blockDim.x) row_label[(size_t)tile * kTile + lr] = -1;
-            if (a16t)
-                for (int idx = threadIdx.x; idx < H * (kTile / 8); idx += blockDim.x)
-                    *reinterpret_cast<uint4*>(a16t + (size_t)(idx / (kTile / 8)) * rows_total + (size_t)tile * kTile +
-                                              (idx % (kTile / 8)) * 8) = make_uint4(0, 0, 0, 0);
+            if (a16t) {      // blocked layout [rows / 64][H][64]: the tile's two blocks are one contiguous range
+                uint4* dt = reinterpret_cast<uint4*>(a16t + (size_t)tile * kTile * H);
+                for (int idx = threadIdx.x; idx < kTile * H / 8; idx += blockDim.x) dt[idx] = make_uint4(0, 0, 0, 0);
+            }
         }
         return;
     }
@@ -184,7 +184,8 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
                 const int c = idx / (kTile / 2), r2 = idx % (kTile / 2);
                 const int sh = (c & 1) * 16;
                 const uint32_t lo = (tr[2 * r2][c >> 1] >> sh) & 0xffffu, hi = (tr[2 * r2 + 1][c >> 1] >> sh) & 0xffffu;
-                *reinterpret_cast<uint32_t*>(a16t + (size_t)(h0 + c) * rows_total + (size_t)tile * kTile + 2 * r2) = lo | (hi << 16);
+                // A16^T is stored in blocks of 64 lattice rows, [rows / 64][H][64]: a tile writes two contiguous 64 KiB ranges
+                *reinterpret_cast<uint32_t*>(a16t + (((size_t)tile * 2 + (r2 >> 5)) * H + h0 + c) * 64 + ((2 * r2) & 63)) = lo | (hi << 16);
             }
             __syncthreads();
         }
@@ -217,7 +218,10 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __
     for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
         const int c = i / 32, r2 = i % 32;
         const uint32_t v = (uint32_t)tile[2 * r2][c] | ((uint32_t)tile[2 * r2 + 1][c] << 16);
-        *reinterpret_cast<uint32_t*>(out + (size_t)(c0 + c) * R + r0 + 2 * r2) = v;
+        if (meta_rows)   // A16^T: blocks of 64 lattice rows, [R / 64][C][64] (r0 is a multiple of 64)
+            *reinterpret_cast<uint32_t*>(out + ((size_t)(r0 >> 6) * C + c0 + c) * 64 + 2 * r2) = v;
+        else
+            *reinterpret_cast<uint32_t*>(out + (size_t)(c0 + c) * R + r0 + 2 * r2) = v;
     }
 }
 
@@ -813,7 +817,7 @@ __global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float
     for (int h = h0; h < h0 + kScaleRowsPerBlock; ++h) {
         uint4 o;
         if (h < H) {
-            const uint4 in = __ldg(reinterpret_cast<const uint4*>(a16t + (size_t)h * rows_total + m0));
+            const uint4 in = __ldg(reinterpret_cast<const uint4*>(a16t + ((m0 >> 6) * (size_t)H + h) * 64 + (m0 & 63)));
             const uint32_t w4[4] = {in.x, in.y, in.z, in.w};
             uint32_t r4[4];
 #pragma unroll
