@@ -328,6 +328,10 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
     return r;
 }
 
+// one 16-byte reduction into global memory (no return value); dst 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // First 16-bit value of a word as float (and the second one).
 template <bool BF16>
 __device__ __forceinline__ void unpk16(uint32_t v, float& a, float& b) {

@@ -131,11 +131,6 @@ __device__ __forceinline__ uint16_t to16(float x) {
     return __half_as_ushort(__float2half_rn(x));
 }
 
-// one 16-byte reduction into global memory (no return value)
-__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 constexpr int kTraceIters = 40;
 __device__ __forceinline__ void trace_at(const MmaParams& p, int role, int iter, int ev) {
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && iter < kTraceIters)

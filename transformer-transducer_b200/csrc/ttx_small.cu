@@ -524,6 +524,69 @@ __global__ void reduce_pred_kernel(const ActGradSrc a, const float* __restrict__
     }
 }
 
+
+// Both reductions in ONE pass over EW (the two kernels above are issue-bound: each of them recomputes tanh' and the
+// bracket for every element).  grid = (ceil(T / TT), B); thread = one float4 of h; the block keeps TT frames of Eproj
+// and their dEproj accumulators in registers, walks u, and for every u adds the TT products to both sums:
+// dEproj[b, t, :] is written once at the end, dPproj[b, u, :] gets one 16-byte reduction per (block, u).
+template <int TT>
+__global__ void __launch_bounds__(128) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
+                                                          const float* __restrict__ pproj, const int* __restrict__ act_lens,
+                                                          const int* __restrict__ label_lens, const int* __restrict__ meta,
+                                                          int T, int U1, int H, float* __restrict__ d_eproj,
+                                                          float* __restrict__ d_pproj) {
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    if (meta[1] != 0) return;
+    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    const float gscale = a.scal[2];
+    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
+        float4 e[TT], acc[TT];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            e[i] = (t0 + i < Tb) ? __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t0 + i) * H + h)) : acc[i];
+        }
+        if (t0 < Tb) {
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
+            for (int u = 0; u < U1b; ++u) {
+                const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
+                const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);     // depends on (b, u) only
+                const bool has_label = lab >= 0 && lab != a.blank;
+                float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+                float4 g[TT], rm[TT];
+#pragma unroll
+                for (int i = 0; i < TT; ++i) {                 // all loads of the round first
+                    const size_t grow = base + (size_t)min(t0 + i, Tb - 1) * U1b + u;
+                    g[i] = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
+                    rm[i] = __ldg(a.rowmeta + grow);
+                }
+                float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < TT; ++i) {
+                    const float coef = (t0 + i < Tb) ? rm[i].w * gscale : 0.f;
+                    float4 v = g[i];
+                    v.x = fmaf(rm[i].y, wb.x, v.x); v.y = fmaf(rm[i].y, wb.y, v.y); v.z = fmaf(rm[i].y, wb.z, v.z); v.w = fmaf(rm[i].y, wb.w, v.w);
+                    if (has_label) {
+                        v.x = fmaf(rm[i].z, wl.x, v.x); v.y = fmaf(rm[i].z, wl.y, v.y); v.z = fmaf(rm[i].z, wl.z, v.z); v.w = fmaf(rm[i].z, wl.w, v.w);
+                    }
+                    v.x *= coef * sech2(e[i].x + pp.x);
+                    v.y *= coef * sech2(e[i].y + pp.y);
+                    v.z *= coef * sech2(e[i].z + pp.z);
+                    v.w *= coef * sech2(e[i].w + pp.w);
+                    acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+                    ap.x += v.x; ap.y += v.y; ap.z += v.z; ap.w += v.w;
+                }
+                red_add_v4(d_pproj + ((size_t)b * U1 + u) * H + h, ap.x, ap.y, ap.z, ap.w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TT; ++i)
+            if (t0 + i < T) *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t0 + i) * H + h) = acc[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------- dense-logits entry
 // rnnt_loss called on a materialised (B,T,U1,V) fp32 logits tensor (someone else's joint): one warp per
 // lattice cell streams the row once (online log-sum-exp) and drops the 3 floats into the compact row space.
@@ -772,6 +835,20 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
     const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
     const bool ew = rowmeta != nullptr;
     TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
+    const char* fe = getenv("TTX_REDUCE_FUSED");
+    if (ew && !(fe && fe[0] == '0')) {               // one pass over EW for both sums
+        int tt = 8;                                   // frames per block (TTX_REDUCE_TT: 4 / 8 / 16 for A/B runs)
+        if (const char* e = getenv("TTX_REDUCE_TT")) tt = atoi(e);
+        const int nt = min(128, threads);
+        if (tt == 4)
+            reduce_both_kernel<4><<<dim3((T + 3) / 4, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+        else if (tt == 16)
+            reduce_both_kernel<16><<<dim3((T + 15) / 16, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+        else
+            reduce_both_kernel<8><<<dim3((T + 7) / 8, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+        TTX_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (ew) reduce_enc_kernel<true><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
     else reduce_enc_kernel<false><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
     const int t_chunk = 64;
