@@ -145,8 +145,18 @@ int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float*
                          const void* a16t, const void* w16t, void* a16st, const float* bias2, const float* scal,
                          const int32_t* row_label, const int32_t* meta, const void* rowmeta, const float* lp_blank,
                          const float* lp_label, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, float* d_w_out, float* d_b_out, int device,
-                         void* stream);
+                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, int sparse_terms, float* d_w_out,
+                         float* d_b_out, int device, void* stream);
+/* ttx_reduce_act_grad_ew that also adds the exact blank / label terms of the kept-P' weight gradient (the rows of
+ * d_w_out / entries of d_b_out that the kept matrix leaves out) in the same pass over the lattice cells: call
+ * ttx_weight_grad_kept with sparse_terms = 0 first (it fills a16st), then this.  With sparse_terms = 1
+ * ttx_weight_grad_kept adds them itself (a separate kernel; for steps without activation gradients). */
+int ttx_reduce_act_grad_ew_kept(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
+                                const float* scal, int blank, const float* eproj, const float* pproj,
+                                const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T,
+                                int U1, int H, float* d_eproj, float* d_pproj, const int32_t* pflags,
+                                const float* lp_blank, const float* lp_label, void* a16st, int64_t n_tiles_ub,
+                                float* d_w_out, float* d_b_out, int device, void* stream);
 int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
                            const float* scal, int blank, const float* eproj, const float* pproj,
                            const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,

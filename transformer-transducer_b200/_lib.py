@@ -42,7 +42,10 @@ _PROTOS = {
                            c_i32, c_p],
     "ttx_joint_fwd_grad_keep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
                                 c_p, c_p, c_p, c_i32, c_p],
-    "ttx_weight_grad_kept": [c_p] * 17 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
+    "ttx_weight_grad_kept": [c_p] * 17 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32,
+                             c_p],
+    "ttx_reduce_act_grad_ew_kept": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
+                                    c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_p],
     "ttx_reduce_act_grad_ew": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
                                c_p, c_p, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],

@@ -34,7 +34,10 @@ int launch_joint_fwd_grad(const void*, const void*, const void*, uint64_t, int, 
                           void*, int*, float*);
 int launch_kept_prepare(const void*, const void*, const float4*, const int*, const float*, const float*, const float*,
                         const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, bool,
-                        size_t, void*, float*, float*, cudaStream_t);
+                        size_t, void*, float*, float*, bool, cudaStream_t);
+int launch_reduce_sparse(const float*, const float4*, const int*, const float*, const float*, int, const float*,
+                         const float*, const int*, const int*, const int*, int, int, int, int, float*, float*, const int*,
+                         const float*, const float*, void*, size_t, float*, float*, cudaStream_t);
 int launch_joint_dw_kept(const void*, const int*, const void*, uint64_t, int, int, int, int, bool, const int*,
                          const float*, float*, float*, cudaStream_t);
 int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
@@ -247,8 +250,8 @@ int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float*
                          const void* a16t, const void* w16t, void* a16st, const float* bias2, const float* scal,
                          const int32_t* row_label, const int32_t* meta, const void* rowmeta, const float* lp_blank,
                          const float* lp_label, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, float* d_w_out, float* d_b_out, int device,
-                         void* stream) {
+                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, int sparse_terms, float* d_w_out,
+                         float* d_b_out, int device, void* stream) {
     TTX_REQUIRE(pstore && pflags && pfac && a16 && w16 && a16t && w16t && a16st && bias2 && scal && row_label && meta &&
                     rowmeta && lp_blank && lp_label && act_lens && label_lens && d_w_out && d_b_out,
                 "ttx_weight_grad_kept: null pointer");
@@ -261,7 +264,7 @@ int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float*
     cudaStream_t s = (cudaStream_t)stream;
     if (int rc = launch_kept_prepare(a16, a16t, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal,
                                      act_lens, label_lens, meta, pflags, B, T, U1, H, blank, bf16 != 0, rows, a16st,
-                                     d_w_out, d_b_out, s))
+                                     d_w_out, d_b_out, sparse_terms != 0, s))
         return rc;
     if (int rc = launch_joint_dw_kept(pstore, pflags, a16st, rows, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta, scal,
                                       d_w_out, d_b_out, s))
@@ -282,6 +285,22 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
     TTX_ENTER(device);
     return launch_reduce(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens, label_lens,
                          meta, B, T, U1, H, d_eproj, d_pproj, (cudaStream_t)stream);
+}
+
+int ttx_reduce_act_grad_ew_kept(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
+                                const float* scal, int blank, const float* eproj, const float* pproj,
+                                const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T,
+                                int U1, int H, float* d_eproj, float* d_pproj, const int32_t* pflags,
+                                const float* lp_blank, const float* lp_label, void* a16st, int64_t n_tiles_ub,
+                                float* d_w_out, float* d_b_out, int device, void* stream) {
+    TTX_REQUIRE(ew && rowmeta && row_label && w_out && scal && eproj && pproj && act_lens && label_lens && meta &&
+                    d_eproj && d_pproj && pflags && lp_blank && lp_label && a16st && d_w_out && d_b_out,
+                "ttx_reduce_act_grad_ew_kept: null pointer");
+    TTX_REQUIRE(H % 4 == 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_reduce_act_grad_ew_kept: bad shape");
+    TTX_ENTER(device);
+    return launch_reduce_sparse(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens,
+                                label_lens, meta, B, T, U1, H, d_eproj, d_pproj, pflags, lp_blank, lp_label, a16st,
+                                (size_t)n_tiles_ub * kTile, d_w_out, d_b_out, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

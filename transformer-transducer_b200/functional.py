@@ -24,7 +24,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew_kept": 2, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -207,13 +207,19 @@ class FusedJointRNNT(torch.autograd.Function):
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
+                kept_sparse = None
                 if need_w and ctx.kept is not None:
                     pstore, pflags, pfac = ctx.kept
                     a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
+                    # the exact blank / label terms ride on the activation-gradient reduction when there is one
+                    fuse = need_act and ew is not None and os.environ.get("TTX_SPARSE_FUSED", "0") == "1"
                     _call("ttx_weight_grad_kept", dev, _p(pstore), _p(pflags), _p(pfac), _p(a16), _p(w16), _p(a16t),
                           _p(w16t), _p(a16st), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), _p(rowmeta), _p(lpb),
                           _p(lpl), _p(plan.act_lens), _p(plan.label_lens), B, T, U1, plan.ntub, H, V, ctx.blank,
-                          ctx.bf16, _p(d_w), _p(d_b), plan.idx, st, label="ttx_joint_grad[dW]")
+                          ctx.bf16, int(not fuse), _p(d_w), _p(d_b), plan.idx, st, n_kernels=3 if fuse else 5,
+                          label="ttx_joint_grad[dW]")
+                    if fuse:
+                        kept_sparse = (pflags, a16st)
                     ctx.kept = None
                 elif need_w:
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
@@ -222,7 +228,12 @@ class FusedJointRNNT(torch.autograd.Function):
             if need_act:
                 d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
                 d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
-                if ew is not None:
+                if ew is not None and kept_sparse is not None:
+                    _call("ttx_reduce_act_grad_ew_kept", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
+                          ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
+                          _p(d_ep), _p(d_pp), _p(kept_sparse[0]), _p(lpb), _p(lpl), _p(kept_sparse[1]), plan.ntub,
+                          _p(d_w), _p(d_b), plan.idx, st, label="ttx_reduce_act_grad_ew")
+                elif ew is not None:
                     _call("ttx_reduce_act_grad_ew", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
                           ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
                           _p(d_ep), _p(d_pp), plan.idx, st)
