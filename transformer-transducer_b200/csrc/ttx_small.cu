@@ -991,49 +991,57 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
     const int lab = __ldg(row_label + base + (size_t)t0 * U1b + u);
     const bool has_label = lab >= 0 && lab != blank;
     const float gmax = scal[2];
-    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
-        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), al = ab;
+    // thread = 8 joint columns (one 16-byte load per row); the block's two 64-thread groups take alternate rounds of
+    // eight frames, all loads of a round issued before the first use (128 bytes in flight per thread)
+    const int grp = threadIdx.x >> 6, ngrp = blockDim.x >> 6;
+    for (int h = (threadIdx.x & 63) * 8; h < H; h += 64 * 8) {
+        float ab[8], al[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ab[k] = al[k] = 0.f;
         float dbb = 0.f, dbl = 0.f;
-        for (int tb = t0; tb < t1; tb += 8) {
-            // eight frames per round: all loads of the round are issued before the first use
-            float4 rm[8];
-            uint2 av[8];
+        for (int tb = t0 + grp * 8; tb < t1; tb += ngrp * 8) {
+            float ry[8], rz[8];
+            uint4 av[8];
             float eb[8], el[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const bool in = tb + e < t1;
                 const size_t m = base + (size_t)(in ? tb + e : t0) * U1b + u;
-                rm[e] = __ldg(rowmeta + m);
-                av[e] = __ldg(reinterpret_cast<const uint2*>(a16 + m * H + h));
-                if (!in) rm[e].w = 0.f;
-                eb[e] = (h == 0) ? __ldg(lpb + m) : 0.f;
-                el[e] = (h == 0 && has_label) ? __ldg(lpl + m) : 0.f;
+                const float4 rm = __ldg(rowmeta + m);
+                const float w = in ? rm.w : 0.f;
+                ry[e] = w * rm.y;
+                rz[e] = w * rm.z;
+                av[e] = __ldg(reinterpret_cast<const uint4*>(a16 + m * H + h));
+                eb[e] = (h == 0) ? w * __expf(__ldg(lpb + m)) : 0.f;
+                el[e] = (h == 0 && has_label) ? w * __expf(__ldg(lpl + m)) : 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float a0, a1, a2, a3;
-                unpk16<BF16>(av[e].x, a0, a1);
-                unpk16<BF16>(av[e].y, a2, a3);
-                const float cb = rm[e].w * rm[e].y, cl = rm[e].w * rm[e].z;
-                ab.x = fmaf(cb, a0, ab.x); ab.y = fmaf(cb, a1, ab.y); ab.z = fmaf(cb, a2, ab.z); ab.w = fmaf(cb, a3, ab.w);
-                if (has_label) {
-                    al.x = fmaf(cl, a0, al.x); al.y = fmaf(cl, a1, al.y); al.z = fmaf(cl, a2, al.z); al.w = fmaf(cl, a3, al.w);
+                const uint32_t w4[4] = {av[e].x, av[e].y, av[e].z, av[e].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a0, a1;
+                    unpk16<BF16>(w4[k], a0, a1);
+                    ab[2 * k] = fmaf(ry[e], a0, ab[2 * k]);
+                    ab[2 * k + 1] = fmaf(ry[e], a1, ab[2 * k + 1]);
+                    if (has_label) {
+                        al[2 * k] = fmaf(rz[e], a0, al[2 * k]);
+                        al[2 * k + 1] = fmaf(rz[e], a1, al[2 * k + 1]);
+                    }
                 }
-                if (h == 0) {
-                    dbb = fmaf(rm[e].w, __expf(eb[e]), dbb);
-                    if (has_label) dbl = fmaf(rm[e].w, __expf(el[e]), dbl);
-                }
+                dbb += eb[e];
+                dbl += el[e];
             }
         }
         // every block adds to the blank row: spread over kBlankSlots partial rows (same-address atomics serialise in L2),
         // folded into d_w[blank] / d_b[blank] by blank_fold_kernel
         float* db_ = blank_slots + (size_t)((blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * 7) % kBlankSlots) * (H + 4) + h;
-        atomicAdd(db_ + 0, ab.x * gmax); atomicAdd(db_ + 1, ab.y * gmax);
-        atomicAdd(db_ + 2, ab.z * gmax); atomicAdd(db_ + 3, ab.w * gmax);
+        red_add_v4(db_, ab[0] * gmax, ab[1] * gmax, ab[2] * gmax, ab[3] * gmax);
+        red_add_v4(db_ + 4, ab[4] * gmax, ab[5] * gmax, ab[6] * gmax, ab[7] * gmax);
         if (has_label) {
             float* dl = d_w + (size_t)lab * H + h;
-            atomicAdd(dl + 0, al.x * gmax); atomicAdd(dl + 1, al.y * gmax);
-            atomicAdd(dl + 2, al.z * gmax); atomicAdd(dl + 3, al.w * gmax);
+            red_add_v4(dl, al[0] * gmax, al[1] * gmax, al[2] * gmax, al[3] * gmax);
+            red_add_v4(dl + 4, al[4] * gmax, al[5] * gmax, al[6] * gmax, al[7] * gmax);
         }
         if (h == 0) {
             atomicAdd(db_ + H, dbb * gmax);
@@ -1072,7 +1080,7 @@ int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta
     }
     const int t_chunk = 64;                      // (longer chunks = fewer atomics were slower: 0.31 -> 0.35 ms at 512)
     const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
-    const int threads = min(256, max(32, H / 4));
+    const int threads = 128;                     // two groups of 64 threads x 8 joint columns
     // the partial rows live behind the (H + 16) x rows_total matrix in the caller's a16st buffer
     float* slots = reinterpret_cast<float*>(static_cast<uint8_t*>(a16st) + (size_t)(H + 16) * rows_total * 2);
     const size_t slot_bytes = (size_t)kBlankSlots * (H + 4) * sizeof(float);
