@@ -43,6 +43,28 @@ def test_c_abi_argument_errors_without_gpu():
     assert rc == 1
 
 
+def test_kept_matrix_budget_and_new_entry_points_reject_bad_arguments(monkeypatch):
+    """Host logic of the kept-P' weight gradient: the 16-bit softmax-numerator matrix is kept only for H = 512, within
+    TTX_KEEP_GB and 16383 tile pairs (the flag words); the two C entry points check their arguments before any launch."""
+    from types import SimpleNamespace
+    from transformer_transducer_b200 import functional as F
+    plan = SimpleNamespace(rows=524800, ntub=4100)                    # cfg2: 4.57 GB
+    assert F._keep_fits(plan, 512, 4352, None)
+    assert not F._keep_fits(plan, 256, 4352, None)
+    monkeypatch.setenv("TTX_KEEP_GB", "4")
+    assert not F._keep_fits(plan, 512, 4352, None)
+    monkeypatch.setenv("TTX_KEEP_GB", "0")
+    assert not F._keep_fits(plan, 512, 4352, None)
+    monkeypatch.delenv("TTX_KEEP_GB")
+    assert not F._keep_fits(SimpleNamespace(rows=128 * 40000, ntub=40000), 512, 256, None)   # too many tile pairs
+    lib = _lib.get()
+    null = ctypes.c_void_p(0)
+    rc = lib.ttx_joint_fwd_grad_keep(*([null] * 7), 1, 512, 10, 0, 0, *([null] * 7), 0, null)
+    assert rc == 1 and b"null pointer" in lib.ttx_last_error()
+    rc = lib.ttx_weight_grad_kept(*([null] * 17), 1, 1, 1, 1, 512, 10, 0, 0, 1, null, null, 0, null)
+    assert rc == 1 and b"null pointer" in lib.ttx_last_error()
+
+
 def test_warprnnt_pytorch_surface():
     assert warprnnt_pytorch.RNNTLoss is ttb.RNNTLoss and warprnnt_pytorch.rnnt_loss is ttb.rnnt_loss
     crit = warprnnt_pytorch.RNNTLoss()
