@@ -156,15 +156,25 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
     const float* pb = pproj + (size_t)b * U1 * H;
     // 64-column slabs: 8 vectors of 8 columns per row; the slab is also staged in shared memory and written out
     // transposed (A16^T[h][row], 256 contiguous bytes per joint column) for the gradient pass's K-major operand.
+    // 256 threads: thread (row group tid >> 3, vector tid & 7) handles the same four rows lr = (tid >> 3) + 32 k in every
+    // slab, so their (t, u) -- an integer division each -- are worked out once (the kernel is issue-bound)
+    int eoff[4], poff[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + (threadIdx.x >> 3) + 32 * k;
+        const int t = r / U1b, u = r - t * U1b;
+        eoff[k] = (r < nrows) ? t * H : -1;
+        poff[k] = u * H;
+    }
     for (int h0 = 0; h0 < H; h0 += 64) {
-        for (int idx = threadIdx.x; idx < kTile * 8; idx += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = threadIdx.x + 256 * k;
             const int lr = idx >> 3, vc = (h0 >> 3) + (idx & 7);
-            const int r = r0 + lr;
             uint4 out = make_uint4(0, 0, 0, 0);
-            if (r < nrows) {
-                const int t = r / U1b, u = r - t * U1b;
-                const float4* e4 = reinterpret_cast<const float4*>(eb + (size_t)t * H + vc * 8);
-                const float4* p4 = reinterpret_cast<const float4*>(pb + (size_t)u * H + vc * 8);
+            if (eoff[k] >= 0) {
+                const float4* e4 = reinterpret_cast<const float4*>(eb + eoff[k] + vc * 8);
+                const float4* p4 = reinterpret_cast<const float4*>(pb + poff[k] + vc * 8);
                 const float4 e0 = __ldg(e4), e1 = __ldg(e4 + 1), p0 = __ldg(p4), p1 = __ldg(p4 + 1);
                 out.x = pack16<BF16>(tanh_fast(e0.x + p0.x), tanh_fast(e0.y + p0.y));
                 out.y = pack16<BF16>(tanh_fast(e0.z + p0.z), tanh_fast(e0.w + p0.w));
@@ -182,10 +192,10 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
             __syncthreads();
             for (int idx = threadIdx.x; idx < 64 * (kTile / 2); idx += blockDim.x) {
                 const int c = idx / (kTile / 2), r2 = idx % (kTile / 2);
-                const int sh = (c & 1) * 16;
-                const uint32_t lo = (tr[2 * r2][c >> 1] >> sh) & 0xffffu, hi = (tr[2 * r2 + 1][c >> 1] >> sh) & 0xffffu;
+                // column c of rows 2 r2 and 2 r2 + 1: the low or the high halves of two words, one byte permute
+                const uint32_t v = __byte_perm(tr[2 * r2][c >> 1], tr[2 * r2 + 1][c >> 1], (c & 1) ? 0x7632 : 0x5410);
                 // A16^T is stored in blocks of 64 lattice rows, [rows / 64][H][64]: a tile writes two contiguous 64 KiB ranges
-                *reinterpret_cast<uint32_t*>(a16t + (((size_t)tile * 2 + (r2 >> 5)) * H + h0 + c) * 64 + ((2 * r2) & 63)) = lo | (hi << 16);
+                *reinterpret_cast<uint32_t*>(a16t + (((size_t)tile * 2 + (r2 >> 5)) * H + h0 + c) * 64 + ((2 * r2) & 63)) = v;
             }
             __syncthreads();
         }
