@@ -1,7 +1,8 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-Imports the UNMODIFIED reference modules from /root/reference (build container only; the GPU box
-has no copy -- callers must check ``available()``).  The reference's module-top imports of packages
+Imports the UNMODIFIED reference modules from /root/reference (build container) or from the git-ignored
+copy ``baseline/_ref/`` that ``stage()`` makes of the reference's Python / YAML files (it travels to the
+GPU box with the repository snapshot, like built .so files) -- callers must check ``available()``.  The reference's module-top imports of packages
 that are not installed and not used on the joint/loss path (tt/utils.py:5-8, train.py:12,
 augment/speed_augment.py:8) are satisfied with empty stub modules.
 """
@@ -9,11 +10,43 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("TT_REFERENCE_ROOT"), "/root/reference", STAGED):
+        if cand and os.path.exists(os.path.join(cand, "tt", "model.py")):
+            return cand
+    return os.environ.get("TT_REFERENCE_ROOT", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available():
     return os.path.exists(os.path.join(REF_ROOT, "tt", "model.py"))
+
+
+def stage(src="/root/reference"):
+    """Copy the reference's own Python sources and YAML configs (unmodified) into baseline/_ref/ so that the
+    GPU box, which has no /root/reference, can run the reference's callers and its CPU joint.  The directory is
+    git-ignored: reference sources never enter this repository's history."""
+    import shutil
+    if not os.path.exists(os.path.join(src, "tt", "model.py")):
+        return None
+    keep = ("tt", "tt_espnet", "espnet", "espnet2", "config", "augment")
+    for top in keep:
+        for dirpath, _, files in os.walk(os.path.join(src, top)):
+            for f in files:
+                if f.endswith((".py", ".yaml", ".txt")):      # espnet/version.txt is read at import
+                    rel = os.path.relpath(os.path.join(dirpath, f), src)
+                    dst = os.path.join(STAGED, rel)
+                    os.makedirs(os.path.dirname(dst), exist_ok=True)
+                    shutil.copyfile(os.path.join(dirpath, f), dst)
+    for f in ("train.py", "train_esptt.py"):
+        shutil.copyfile(os.path.join(src, f), os.path.join(STAGED, f))
+    return STAGED
 
 
 def _stub(name, **attrs):

@@ -1,0 +1,225 @@
+"""GPU gate (-m gpu): the reference's OWN callers drive the product on CUDA.
+
+  * tt path     -- unmodified `train.train()` (train.py:22-91) steps an unmodified `tt.model.Transducer`
+                   (tt/model.py:42-68) whose joint is our drop-in (`install()`), with `warprnnt_pytorch.RNNTLoss`
+                   (this repository's package, train.py:13) as the criterion, on cuda:0.
+  * espnet path -- unmodified `tt_espnet.model.TransformerTransducer.forward` (tt_espnet/model.py:35-81) with the
+                   reference's own `TransLoss` wrapper (transducer/loss.py:43-77: fp32 up-cast of the joint output,
+                   loss cast back) around our joint + loss, fp32 and bf16.
+
+The arbiter is the SAME reference model with the reference's own joint, run on the CPU with the oracle loss
+(fp32), or -- bf16, where CPU and GPU encoders round differently -- run on the GPU with the reference's dense
+joint and the dense-logits entry of the product loss (itself pinned to the oracle in test_gpu_parity.py).
+
+The reference sources come from baseline/_ref/ (staged by __graft_entry__.build(), git-ignored, travels with the
+snapshot).  Nothing here reads /root/reference on the GPU box.
+"""
+import copy
+import logging
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import transformer_transducer_b200 as ttb
+from oracle import ref_import, rnnt_oracle
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_import.available(), reason="baseline/_ref (staged reference) is missing")]
+DEV = "cuda:0"
+LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _seed(s):
+    torch.manual_seed(s)
+    np.random.seed(s)
+    random.seed(s)
+
+
+def _tt_config(inner, vocab):
+    import yaml
+    from tt.utils import AttrDict
+    cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "aishell.yaml"))))
+    cfg.model.enc.n_layer = 1
+    cfg.model.dec.n_layer = 1
+    cfg.model.vocab_size = vocab
+    cfg.model.joint.inner_size = inner
+    cfg.model.dropout = 0.0                      # CPU and CUDA dropout streams differ
+    cfg.training.show_interval = 1
+    return cfg
+
+
+def _capture_logger(name):
+    log = logging.getLogger(name)
+    records = []
+    handler = logging.Handler()
+    handler.emit = lambda r: records.append(r.getMessage())
+    log.handlers = [handler]
+    log.setLevel(logging.INFO)
+    return log, records
+
+
+def _losses(records):
+    return [float(m.split(", Loss:")[1].split(",")[0]) for m in records if "Global Step" in m]
+
+
+@pytest.mark.parametrize("inner", [512, 1024])          # fused tcgen05 width / aishell.yaml's own joint width
+def test_unmodified_train_loop_drives_product_on_cuda(inner):
+    """train.py:22-91 unchanged, model on cuda:0 with our JointNet + our RNNTLoss, vs the reference joint + oracle
+    loss on the CPU: same per-step losses (SGD steps in between, so later losses also check the gradients) and the
+    same parameters after three optimizer steps; a separate single step compares every parameter gradient."""
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    import train as ref_train
+    from tt.optim import Optimizer
+    assert ref_train.RNNTLoss is ttb.RNNTLoss          # `from warprnnt_pytorch import RNNTLoss` resolved to the product
+    V = 211
+    cfg = _tt_config(inner, V)
+    _seed(0)
+    data = [(torch.randn(3, 36, 512), torch.tensor([36, 30, 17]), torch.randint(1, V, (3, 7)), torch.tensor([7, 5, 2]))
+            for _ in range(3)]
+    orig = tt_model.JointNet
+    try:
+        _seed(1)
+        ref_model = tt_model.Transducer(cfg.model)       # reference joint (dense logits)
+        ttb.install(patch_espnet=False)
+        model = tt_model.Transducer(cfg.model)           # same assembly, our joint inside
+        assert isinstance(model.joint, ttb.JointNet) and not isinstance(ref_model.joint, ttb.JointNet)
+        model.load_state_dict(ref_model.state_dict())    # state-dict keys are the reference's
+        model = model.to(DEV)
+
+        # (1) one step by hand: every parameter gradient
+        inputs, ilen, targets, tlen = data[0]
+        ref_model.train()
+        model.train()
+        want = rnnt_oracle.RNNTLoss()(ref_model(inputs, targets), targets.int(), ilen.int(), tlen.int())
+        want.backward()
+        logits = model(inputs.to(DEV), targets.to(DEV))
+        assert isinstance(logits, ttb.LazyJointLogits)
+        got = ref_train.RNNTLoss()(logits, targets.int().to(DEV), ilen.int().to(DEV), tlen.int().to(DEV))
+        got.backward()
+        assert abs(float(got) - float(want)) / abs(float(want)) < LOSS_TOL
+        for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+            assert b.grad is not None and a.grad is not None, n
+            assert rel(a.grad, b.grad) < GRAD_TOL, (n, rel(a.grad, b.grad))
+        ref_model.zero_grad()
+        model.zero_grad()
+
+        # (2) the unmodified loop
+        cfg.training.num_gpu = 0
+        log_r, rec_r = _capture_logger("tt-ref")
+        _seed(2)                                          # time / frequency masks draw from numpy + random
+        ref_train.train(0, cfg, ref_model, copy.deepcopy(data), Optimizer(ref_model.parameters(), cfg.optim),
+                        rnnt_oracle.RNNTLoss(), log_r)
+        cfg.training.num_gpu = 1
+        log_g, rec_g = _capture_logger("tt-gpu")
+        _seed(2)
+        ref_train.train(0, cfg, model, copy.deepcopy(data), Optimizer(model.parameters(), cfg.optim),
+                        ref_train.RNNTLoss(), log_g)
+        lr_, lg_ = _losses(rec_r), _losses(rec_g)
+        assert len(lr_) == 3 and len(lg_) == 3
+        assert abs(lg_[0] - lr_[0]) / abs(lr_[0]) < LOSS_TOL, (lg_, lr_)
+        for a, b in zip(lg_[1:], lr_[1:]):                   # after SGD steps taken with the compared gradients
+            assert abs(a - b) / abs(b) < 1e-3, (lg_, lr_)
+        for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+            assert rel(a, b) < 1e-5, n
+    finally:
+        tt_model.JointNet = orig
+
+
+def _espnet_config(vocab):
+    import yaml
+    from tt.utils import AttrDict
+    cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "espnet_aishell.yaml"))))
+    m = cfg.model
+    for part in (m.enc, m.dec):
+        part.dropout_rate = 0.0
+        part.positional_dropout_rate = 0.0
+        part.attention_dropout_rate = 0.0
+    m.dec.input_size = vocab
+    m.joint.vocab_size = vocab
+    return m
+
+
+def _espnet_models(vocab):
+    ref_import.prepare(stub_train_deps=True)
+    jn = ref_import.espnet_joint_module()
+    import tt_espnet.model as tem
+    orig = (jn.JointNetwork, tem.JointNetwork)
+    cfg = _espnet_config(vocab)
+    _seed(3)
+    ref_model = tem.TransformerTransducer(cfg)           # reference JointNetwork inside
+    ttb.install(patch_tt=False)
+    try:
+        model = tem.TransformerTransducer(cfg)
+    finally:
+        jn.JointNetwork, tem.JointNetwork = orig
+    assert isinstance(model.joint, ttb.JointNetwork) and not isinstance(ref_model.joint, ttb.JointNetwork)
+    model.load_state_dict(ref_model.state_dict())
+    return ref_model, model
+
+
+def _espnet_batch(vocab):
+    _seed(4)
+    speech = torch.randn(3, 40, 512)
+    slen = torch.tensor([40, 33, 12])
+    text = torch.randint(1, vocab - 1, (3, 8))
+    tlen = torch.tensor([8, 6, 1])
+    for i, n in enumerate(tlen):
+        text[i, int(n):] = -1                             # tt/dataset.py:46-48 pads with ignore_id = -1
+    return speech, slen, text, tlen
+
+
+def test_espnet_transformer_transducer_forward_backward_fp32():
+    """tt_espnet/model.py:35-81 + transducer/loss.py:43-77 unchanged around our joint and loss (fp32), vs the same
+    model with the reference joint and the oracle loss on the CPU."""
+    V = 333
+    ref_model, model = _espnet_models(V)
+    speech, slen, text, tlen = _espnet_batch(V)
+    ref_model.loss.trans_loss = rnnt_oracle.RNNTLoss(blank=0)      # the CPU arbiter behind the reference's wrapper
+    ref_model.train()
+    want = ref_model(speech, slen, text, tlen)
+    want.backward()
+    model = model.to(DEV).train()
+    assert isinstance(model.loss.trans_loss, ttb.RNNTLoss)         # TransLoss found `warprnnt_pytorch` = the product
+    got = model(speech.to(DEV), slen.to(DEV), text.to(DEV), tlen.to(DEV))
+    assert got.dtype == torch.float32 and got.shape == (1,)
+    got.backward()
+    assert abs(float(got) - float(want)) / abs(float(want)) < LOSS_TOL
+    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        if b.grad is None:
+            assert a.grad is None or float(a.grad.abs().max()) == 0, n
+            continue
+        assert rel(a.grad, b.grad) < GRAD_TOL, (n, rel(a.grad, b.grad))
+
+
+def test_espnet_transformer_transducer_forward_backward_bf16():
+    """bf16 model (the fp32 up-cast / loss cast-back of TransLoss crosses the lazy handle): fused path vs the SAME
+    model on the GPU with the reference's dense joint + the dense-logits entry of the product loss.  Tolerances are the
+    bf16-variant ones (the reference rounds its logits to bf16, the fused path does not): loss 1e-2, joint / encoder /
+    decoder gradients 5e-2 relative L2."""
+    V = 333
+    ref_model, model = _espnet_models(V)
+    speech, slen, text, tlen = _espnet_batch(V)
+    ref_model = ref_model.to(DEV).bfloat16().train()
+    model = model.to(DEV).bfloat16().train()
+    args = (speech.to(DEV).bfloat16(), slen.to(DEV), text.to(DEV), tlen.to(DEV))
+    want = ref_model(*args)
+    want.backward()
+    got = model(*args)
+    assert got.dtype == torch.bfloat16 and got.shape == (1,)       # transducer/loss.py:75 casts the loss back
+    got.backward()
+    assert abs(float(got) - float(want)) / abs(float(want)) < 1e-2
+    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        if b.grad is None:
+            continue
+        assert a.grad is not None and a.grad.dtype == torch.bfloat16, n
+        assert rel(a.grad, b.grad) < 5e-2, (n, rel(a.grad, b.grad))

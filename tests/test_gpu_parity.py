@@ -124,6 +124,9 @@ def _run_pair(ref, mine, enc, pred, labels, al, ll, weights=None, dtype=torch.fl
             "d_enc": rel(e1.grad, e0.grad), "d_pred": rel(p1.grad, p0.grad)}
     for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
         errs["d_" + n] = rel(a.grad, b.grad)
+    for b in range(len(al)):                    # per utterance too: a large grad_output must not hide a small one
+        errs["d_enc[%d]" % b] = rel(e1.grad[b], e0.grad[b])
+        errs["d_pred[%d]" % b] = rel(p1.grad[b], p0.grad[b])
     return errs, (e1, p1, got)
 
 
@@ -212,7 +215,7 @@ def test_fused_tt_jointnet_split_first_layer_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
-@pytest.mark.parametrize("H,V", [(1024, 4232), (2048, 700)])
+@pytest.mark.parametrize("H,V", [(1024, 4232), (2048, 700), (2048, 6485)])
 def test_wide_joint_chunked_path_matches_oracle(H, V, monkeypatch):
     """aishell.yaml (H=1024) / joint_streaming.yaml (H=2048) joint widths: lazy handle + chunked path (library GEMM on
     the 16-bit operands + our row kernels), several chunks, ragged lengths."""
@@ -303,6 +306,88 @@ def test_kernel_variants_agree_with_oracle(env, monkeypatch):
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)
     errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))                 # a negative grad_output too
+    _check(errs)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs at their real dims
+@pytest.mark.parametrize("keep", ["32", "0"])           # kept softmax numerators / bounded scratch + recompute
+def test_cfg2_full_lattice_vs_oracle(keep, monkeypatch):
+    """configs[1] with its full lattice (T=400, U=40, V=4232, D=H=512), B=2 so the CPU oracle finishes in seconds:
+    129 + 99 = 228 lattice tiles = 114 tile pairs, more than the 74 CTA pairs of a B200, so the persistent kernels'
+    multi-unit loop (next unit's operands behind the previous read-out, barrier parities across units) is checked
+    against the oracle, with and without the kept P' matrix."""
+    monkeypatch.setenv("TTX_KEEP_GB", keep)
+    case = _espnet_case(2, 400, 40, 4232, 512, 512, [400, 371], [40, 33], seed=11)
+    errs, (e1, p1, _) = _run_pair(*case, weights=torch.tensor([1.0, 0.5]))
+    _check(errs)
+    assert e1.grad[1, 371:].abs().max() == 0 and p1.grad[1, 34:].abs().max() == 0
+
+
+def test_cfg4_long_utterance_real_dims_vs_float64_oracle():
+    """configs[3] dims with the real joint (H=512, V=4232) on a T=1000, U=100 lattice (101 000 cells, 790 tiles), B=1
+    (the float64 arbiter needs ~14 GB of host memory for it).  See test_fused_long_utterance_lattice for why the
+    arbiter is the float64 oracle at this lattice size."""
+    case = _espnet_case(1, 1000, 100, 4232, 512, 512, [1000], [100], seed=12)
+    errs, _ = _run_pair(*case, arbiter64=True)
+    _check(errs)
+
+
+def test_cfg5_ragged_bf16_real_lengths_vs_oracle():
+    """configs[4]: ragged batch with lengths from the config's ranges (T in [50,1000], U in [5,200]), bf16 joint inputs and
+    parameters, V=4233, -1 label padding.  The oracle (fed the same bf16-rounded inputs, fp32 arithmetic) runs one
+    utterance at a time on that utterance's own (T_b, U_b) crop -- the padded dense logits would be 13.6 GB."""
+    T_l, U_l = [1000, 430, 50, 640], [200, 77, 5, 120]
+    ref, mine, enc, pred, labels, al, ll = _espnet_case(4, 1000, 200, 4233, 512, 512, T_l, U_l, seed=13)
+    wts = torch.tensor([1.0, 2.0, 0.5, 1.0])
+    mine = mine.to(DEV).bfloat16()
+    ref.load_state_dict({k: v.float().cpu() for k, v in mine.state_dict().items()})
+    enc, pred = enc.bfloat16().float(), pred.bfloat16().float()
+    want = []
+    g_enc, g_pred = torch.zeros_like(enc), torch.zeros_like(pred)
+    for b, (t, u) in enumerate(zip(T_l, U_l)):
+        e0 = enc[b:b + 1, :t].clone().requires_grad_()
+        p0 = pred[b:b + 1, :u + 1].clone().requires_grad_()
+        c = rnnt_oracle.rnnt_loss(ref(e0[:, :, None], p0[:, None]), labels[b:b + 1, :u].contiguous(), _i32([t]), _i32([u]),
+                                  0, "none")
+        (c * wts[b]).sum().backward()
+        want.append(float(c))
+        g_enc[b, :t], g_pred[b, :u + 1] = e0.grad[0], p0.grad[0]
+    e1 = enc.to(DEV).bfloat16().requires_grad_()
+    p1 = pred.to(DEV).bfloat16().requires_grad_()
+    z = mine(e1[:, :, None], p1[:, None])
+    assert isinstance(z, ttb.LazyJointLogits) and z.dtype == torch.bfloat16
+    got = ttb.rnnt_loss(z.to(dtype=torch.float32), labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")   # loss.py:57-60
+    (got.float() * wts.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    want = torch.tensor(want, dtype=torch.float64)
+    errs = {"loss": float(((got.double().cpu() - want) / want).abs().max()),
+            "d_enc": rel(e1.grad, g_enc), "d_pred": rel(p1.grad, g_pred)}
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        errs["d_" + n] = rel(a.grad, b.grad)
+    _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
+    assert e1.grad[2, 50:].abs().max() == 0 and p1.grad[2, 6:].abs().max() == 0
+
+
+@pytest.mark.parametrize("keep", ["32", "0"])
+def test_trained_like_distribution(keep, monkeypatch):
+    """Beyond random initialisation: heavy-tailed output weights (a few |w| far above the median), posteriors peaked
+    in EVERY vocabulary tile (the row maximum sits in a late tile for most rows, so the forward's running reference
+    moves after its first tile), label logits boosted like a trained model's, and grad_output spanning six orders of
+    magnitude between utterances (the gmax normalisation of the 16-bit gradient operand)."""
+    monkeypatch.setenv("TTX_KEEP_GB", keep)
+    ref, mine, enc, pred, labels, al, ll = _espnet_case(3, 48, 9, 2100, 64, 512, [48, 40, 21], [9, 7, 3], seed=14)
+    g = torch.Generator().manual_seed(15)
+    with torch.no_grad():
+        w = ref.lin_out.weight
+        w.mul_(3.0)                                               # logits with a standard deviation of several nats
+        tail = torch.rand(w.shape, generator=g) < 2e-3
+        w[tail] *= 12.0                                           # weight outliers
+        for t0 in range(0, 2100, 256):                            # one strongly preferred unit per 256-wide tile
+            ref.lin_out.bias[t0 + int(torch.randint(0, 200, (1,), generator=g))] += 6.0
+        ref.lin_out.bias[0] += 4.0                                # blank
+        ref.lin_out.bias[labels[labels > 0].long().unique()] += 5.0
+    mine.load_state_dict(ref.state_dict())
+    errs, _ = _run_pair(ref, mine, enc, pred, labels, al, ll, weights=torch.tensor([1e-3, 1.0, 1e3]))
     _check(errs)
 
 

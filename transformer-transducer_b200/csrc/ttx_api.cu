@@ -100,8 +100,10 @@ int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T
                 int32_t* meta, int device, void* stream) {
     TTX_REQUIRE(act_lens && label_lens && meta, "ttx_prepare: null pointer");
     TTX_REQUIRE(B > 0 && T > 0 && U1 > 0, "ttx_prepare: bad shape B=%d T=%d U1=%d", B, T, U1);
-    TTX_REQUIRE(n_tiles_ub >= ttx_tiles_upper_bound(B, T, U1) && n_tiles_ub < (1 << 24),
-                "ttx_prepare: tile bound %lld out of range", (long long)n_tiles_ub);
+    // any bound is accepted (callers that know the batch's real tile count size their buffers by it); a bound smaller
+    // than the count found on the device is flagged in meta[1] like bad lengths and no kernel does any work
+    TTX_REQUIRE(n_tiles_ub >= 1 && n_tiles_ub < (1 << 24), "ttx_prepare: tile bound %lld out of range",
+                (long long)n_tiles_ub);
     TTX_ENTER(device);
     return launch_prep(act_lens, label_lens, B, T, U1, (int)n_tiles_ub, meta, (cudaStream_t)stream);
 }

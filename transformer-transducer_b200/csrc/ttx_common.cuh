@@ -24,6 +24,9 @@ constexpr float kPScale = 4096.0f;                  // power-of-two scale of the
 constexpr int kMetaHdr = 4;
 // Kept P' matrix (forward+gradient -> weight gradient): flag words, one per tile pair; this one = some pair is flagged.
 constexpr int kKeptAnyDirty = 16383;
+// fp16 scale of the kept-P' weight gradient's B operand As = kKeptUp * w * pfac * A16 (w, |A16| <= 1 and
+// pfac <= 2^-2 by the forward's range plan, so |As| <= 2^14; the factor keeps small lattice weights out of the subnormals)
+constexpr float kKeptUp = 65536.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

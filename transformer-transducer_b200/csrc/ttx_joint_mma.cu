@@ -1198,7 +1198,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     kr.advance(kKG * kKG, kKG);
                 }
             const int vrow = x_row0 + row;
-            const float f = p.scal[2] * (BF16 ? 1.0f : 5.9604644775390625e-8f);   // the As operand carries 2^24 (fp16)
+            const float f = p.scal[2] * (BF16 ? 1.0f : 1.0f / kKeptUp);           // the As operand carries 2^16 (fp16)
             if (x_row0 + v < p.V) atomicAdd(p.db + x_row0 + v, dacc * f);
             mbar_wait(bar_gfull, it & 1);
             tc_fence_after();
@@ -1225,6 +1225,13 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             const int grow = x_row0 + row;
             const int label = valid_x ? p.row_label[grow] : -1;
             float mref = 0.f, ssum = 0.f, zb = 0.f, zl = 0.f;     // mref: finite start, fixed by the first tile
+            // Range plan of the 16-bit operand P' = 2^(y - mref) (y = logit in log2 units + lg_scale).  fp16: the first
+            // tile's row maximum sits at 2^2, later tiles may reach 2^15 before the reference has to move -- 13 binades
+            // (9 nats) of headroom for logits above anything in the first 256 columns (a trained model's label logit
+            // against a first tile that holds the blank), 16 normal + 10 subnormal binades below.  bf16 has the fp32
+            // exponent range: the reference practically never moves.
+            const float ref_exp = BF16 ? -2.f : 2.f;
+            const float ref_limit = BF16 ? 100.f : 15.f;
             float* xg = kbuf;                                      // [2 column halves][128] row maxima (rare path)
             const int ngrp = p.HH / 32;
             for (int i = 0; i < (replay ? 0 : n_iter); ++i) {
@@ -1264,8 +1271,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     xg[ch * kTile + row] = lmax;
                     quarter_sync(q);
                     const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                    // reference = row maximum of the first tile + 2 (log2 units); -inf only on all-padding columns
-                    mref = (rmax > -INFINITY) ? (rmax - lg_scale + 2.f) : 0.f;
+                    // reference: the first tile's row maximum becomes 2^kRefExp in the 16-bit operand (-inf only on
+                    // all-padding columns)
+                    mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
                     quarter_sync(q);                              // xg may be rewritten
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -1311,7 +1319,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                         unpk2(st, p0, p1);
                     }
                     float part = p0 + p1;
-                    if (quarter_any(q, lmax > lg_scale + 3.f)) {
+                    if (quarter_any(q, lmax > ref_limit)) {
                         if (rp && hh == 0) {                       // stored sub-tiles now carry mixed scales: no replay
                             if (p.keep) {
                                 flags[unit] = 1;
@@ -1323,8 +1331,8 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                         xg[ch * kTile + row] = lmax;
                         quarter_sync(q);
                         const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                        // new reference = row maximum + 2 (log2 units): values, sums and accumulators scale by 2^-delta
-                        const float delta = (rmax > lg_scale + 3.f) ? (rmax - lg_scale + 2.f) : 0.f;
+                        // new reference: the row maximum becomes 2^kRefExp again; values, sums and accumulators scale by 2^-delta
+                        const float delta = (rmax > ref_limit) ? (rmax - ref_exp) : 0.f;
                         const float fsc = ex2f(-delta);
                         ssum *= fsc;
                         part *= fsc;

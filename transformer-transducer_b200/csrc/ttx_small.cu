@@ -46,18 +46,20 @@ __global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restr
     int tile = part[tid] - local;  // exclusive prefix
     int* tile0 = meta + kMetaHdr;
     int* tile_b = meta + kMetaHdr + B + 1;
+    const int total = part[blockDim.x - 1];
+    const bool fits = total <= n_tiles_ub;       // the caller's buffers hold n_tiles_ub tiles
     for (int b = b_lo; b < b_hi; ++b) {
         const int t = act_lens[b], u1 = label_lens[b] + 1;
         const bool ok = !(t < 1 || t > T || u1 < 1 || u1 > U1);
         const int nt = ok ? (t * u1 + kTile - 1) / kTile : 0;
         tile0[b] = tile;
-        for (int i = 0; i < nt; ++i) tile_b[tile + i] = b;
+        if (fits)
+            for (int i = 0; i < nt; ++i) tile_b[tile + i] = b;
         tile += nt;
     }
-    const int total = part[blockDim.x - 1];
-    for (int i = total + tid; i < n_tiles_ub; i += blockDim.x) tile_b[i] = -1;
+    for (int i = (fits ? total : 0) + tid; i < n_tiles_ub; i += blockDim.x) tile_b[i] = -1;
     if (tid == 0) {
-        const int first_bad = (bad == 0x7fffffff) ? 0 : bad;
+        const int first_bad = (bad == 0x7fffffff) ? (fits ? 0 : B + 1) : bad;
         tile0[B] = total;
         meta[0] = first_bad ? 0 : total;
         meta[1] = first_bad;
@@ -933,7 +935,7 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
 // whose K-major B operand is the scaled transposed copy written here (the scale cannot ride on P': it is streamed
 // straight into the tensor core; stored in blocks of 64 lattice rows).  Sixteen extra rows h = H .. H+15 hold
 // As = 2^shift * w_m * pfac_m (A = 1): their
-// product with P' is the dense part of db.  shift (24 for fp16, 0 for bf16) keeps As out of the subnormals.
+// product with P' is the dense part of db.  shift (16 for fp16, 0 for bf16) keeps As out of the subnormals.
 // Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.  No-op if the P' matrix is flagged.
 constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T) per block
 template <bool BF16>
@@ -1076,7 +1078,7 @@ int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta
                         const int* label_lens, const int* meta, const int* flags, int B, int T, int U1, int H, int blank,
                         bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, bool sparse_terms,
                         cudaStream_t s) {
-    const float up = bf16 ? 1.f : 16777216.f;
+    const float up = bf16 ? 1.f : kKeptUp;
     const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
     if (bf16)
         scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, flags, H, rows_total, up,

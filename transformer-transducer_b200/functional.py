@@ -53,11 +53,15 @@ def _i32_cuda(t, dev, name):
 class _Plan:
     """Shape bookkeeping + the buffers shared by both entry paths."""
 
-    def __init__(self, B, T, U1, dev, act_lens, label_lens):
+    def __init__(self, B, T, U1, dev, act_lens, label_lens, n_tiles=None):
         lib = _lib.get()
         self.lib, self.dev, self.B, self.T, self.U1 = lib, dev, B, T, U1
         self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        self.ntub = int(lib.ttx_tiles_upper_bound(B, T, U1))
+        # Every per-row buffer is sized by `ntub` tiles.  With the exact tile count from the host-side length check
+        # (loss.certify_inputs; ragged batches: ~1/4 of the dense bound at configs[4]) rounded up to a whole tile pair,
+        # otherwise by the dense upper bound B * ceil(T * U1 / 128).  ttx_prepare flags a count that is too small.
+        ub = int(lib.ttx_tiles_upper_bound(B, T, U1))
+        self.ntub = ub if n_tiles is None else max(2, min(ub + 1, (int(n_tiles) + 1) & ~1))
         self.rows = self.ntub * 128
         self.meta = torch.empty(int(lib.ttx_meta_ints(B, self.ntub)), dtype=torch.int32, device=dev)
         self.act_lens, self.label_lens = act_lens, label_lens
@@ -70,7 +74,7 @@ class _Plan:
     def lattice(self, lse, lpb, lpl):
         alpha = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
         beta = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
-        costs = torch.empty(self.B, dtype=torch.float32, device=self.dev)
+        costs = torch.full((self.B,), float("nan"), dtype=torch.float32, device=self.dev)   # stays NaN on bad lengths
         ll_beta = torch.empty(self.B, dtype=torch.float64, device=self.dev)
         _call("ttx_lattice_fwd_bwd", self.dev, _p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
                                                _p(self.meta), self.B, self.U1, _p(alpha), _p(beta), _p(costs),
@@ -116,7 +120,7 @@ def supported_width(H):
 
 class FusedJointRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16):
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, n_tiles=None):
         need_grad = any(ctx.needs_input_grad[:4])      # (grad mode is off inside Function.forward)
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
@@ -135,7 +139,7 @@ class FusedJointRNNT(torch.autograd.Function):
         b = b_out.detach().float().contiguous()
         labels = labels.contiguous()
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -161,9 +165,14 @@ class FusedJointRNNT(torch.autograd.Function):
                     and os.environ.get("TTX_NO_FWD_GRAD", "0") != "1"):
                 ew = plan.rowf(H)
                 if (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]) and _keep_fits(plan, H, Vpad, dev):
-                    # keep the softmax numerators P' (16 bit) for the weight gradient: no second projection pass there
-                    kept = (torch.empty(plan.rows * Vpad, dtype=torch.int16, device=dev),
-                            torch.zeros(16384, dtype=torch.int32, device=dev), plan.rowf())
+                    # keep the softmax numerators P' (16 bit) for the weight gradient: no second projection pass there.
+                    # If the device cannot hold the matrix next to the rest of the model, the recomputing path can.
+                    try:
+                        kept = (torch.empty(plan.rows * Vpad, dtype=torch.int16, device=dev),
+                                torch.zeros(16384, dtype=torch.int32, device=dev), plan.rowf())
+                    except torch.cuda.OutOfMemoryError:
+                        kept = None
+                if kept is not None:
                     _call("ttx_joint_fwd_grad_keep", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal),
                           _p(row_label), _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
                           _p(ew), _p(kept[0]), _p(kept[1]), _p(kept[2]), plan.idx, st, label="ttx_joint_fwd_grad")
@@ -226,8 +235,8 @@ class FusedJointRNNT(torch.autograd.Function):
                           _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
                           st, n_kernels=1, label="ttx_joint_grad[dW]")
             if need_act:
-                d_ep = torch.empty(B, T, H, dtype=torch.float32, device=dev)
-                d_pp = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
+                d_ep = torch.zeros(B, T, H, dtype=torch.float32, device=dev)   # (stay zero if the lengths were flagged bad)
+                d_pp = torch.zeros(B, U1, H, dtype=torch.float32, device=dev)
                 if ew is not None and kept_sparse is not None:
                     _call("ttx_reduce_act_grad_ew_kept", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
                           ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
@@ -244,7 +253,7 @@ class FusedJointRNNT(torch.autograd.Function):
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
                 cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class ChunkedJointRNNT(torch.autograd.Function):
@@ -261,7 +270,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         return [(t0, min(plan.ntub, t0 + tiles)) for t0 in range(0, plan.ntub, tiles)]
 
     @staticmethod
-    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16):
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, n_tiles=None):
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
         dev = eproj.device
@@ -275,7 +284,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         labels = labels.contiguous()
         dt16 = torch.bfloat16 if bf16 else torch.float16
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -353,10 +362,10 @@ class ChunkedJointRNNT(torch.autograd.Function):
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
                 cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
-def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False):
+def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, n_tiles=None):
     """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out.
 
     Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
@@ -364,12 +373,12 @@ def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, b
     fused = supported_width(eproj.shape[-1]) and os.environ.get("TTX_FORCE_CHUNKED", "0") != "1"
     fn = FusedJointRNNT if fused else ChunkedJointRNNT
     return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
-                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16)
+                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16, n_tiles)
 
 
 class DenseRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, acts, labels, act_lens, label_lens, blank):
+    def forward(ctx, acts, labels, act_lens, label_lens, blank, n_tiles=None):
         if not acts.is_cuda:
             raise RuntimeError("rnnt_loss needs CUDA tensors (there is no CPU fallback)")
         dev = acts.device
@@ -378,7 +387,7 @@ class DenseRNNT(torch.autograd.Function):
         labels = labels.contiguous()
         lib = _lib.get()
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
@@ -402,10 +411,10 @@ class DenseRNNT(torch.autograd.Function):
             _call("ttx_dense_grad", plan.dev, _p(a), _p(rowmeta), _p(row_label), _p(scal), _p(plan.act_lens),
                                                _p(plan.label_lens), _p(plan.meta), B, T, U1, V, ctx.blank, _p(grads),
                                                plan.idx, _stream(plan.dev))
-        return grads.to(ctx.in_dtype), None, None, None, None
+        return grads.to(ctx.in_dtype), None, None, None, None, None
 
 
-def dense_rnnt(acts, labels, act_lens, label_lens, blank=0):
+def dense_rnnt(acts, labels, act_lens, label_lens, blank=0, n_tiles=None):
     dev = acts.device
     return DenseRNNT.apply(acts, _i32_cuda(labels, dev, "labels"), _i32_cuda(act_lens, dev, "act_lens"),
-                           _i32_cuda(label_lens, dev, "label_lens"), blank)
+                           _i32_cuda(label_lens, dev, "label_lens"), blank, n_tiles)

@@ -12,6 +12,11 @@ import os
 import torch
 
 _ALLOWED_NOOP = ("aten.detach.default", "aten.alias.default")
+# torch-function names that only look at / re-type the handle: they keep it lazy (everything else materialises)
+_META = ("__get__", "size", "dim", "ndimension", "is_contiguous", "contiguous", "to", "float", "type", "__repr__",
+         "__str__", "__format__", "numel", "nelement", "is_floating_point", "get_device", "stride", "__len__",
+         "__bool__", "__dir__", "__hash__", "requires_grad_", "data_ptr", "__reduce_ex__", "element_size",
+         "storage_offset", "is_complex", "is_pinned")
 
 
 def _limit_bytes():
@@ -44,6 +49,25 @@ class LazyJointLogits(torch.Tensor):
                                "override); pass the handle to RNNTLoss instead" % (nbytes / (1 << 30)))
         h = torch.tanh(self.eproj.unsqueeze(2) + self.pproj.unsqueeze(1))
         return torch.nn.functional.linear(h, self.w_out, self.b_out).to(self.dtype)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """Anything but the loss and the metadata calls above gets the dense logits -- materialised WITH autograd, so
+        slicing the handle, a log_softmax for another loss, or mixing it into an auxiliary loss keeps gradients to the
+        joint's inputs and parameters (guarded by the size limit)."""
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        if name in _META:
+            return super().__torch_function__(func, types, args, kwargs)
+        if name == "detach":
+            src = args[0]
+            return LazyJointLogits(*[t.detach() for t in src.parts], dtype=src.dtype)
+
+        def unwrap(x):
+            return x.materialize() if isinstance(x, LazyJointLogits) else x
+
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*torch.utils._pytree.tree_map(unwrap, args), **torch.utils._pytree.tree_map(unwrap, kwargs))
 
     @classmethod
     def __torch_dispatch__(cls, func, types, args=(), kwargs=None):

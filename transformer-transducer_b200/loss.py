@@ -15,6 +15,9 @@ from .lazy import LazyJointLogits
 
 
 def certify_inputs(acts, labels, act_lens, label_lens):
+    """Upstream's argument checks.  Returns the number of 128-row lattice tiles the batch really has
+    (sum_b ceil(T_b (U_b + 1) / 128)), taken from the same single host synchronisation as the length checks, or None
+    when TTX_SKIP_LENGTH_CHECKS=1 skips that synchronisation (buffers are then sized by the dense upper bound)."""
     for name, t in (("labels", labels), ("act_lens", act_lens), ("label_lens", label_lens)):
         if t.dtype != torch.int32:
             raise TypeError("%s must be int32" % name)
@@ -30,8 +33,17 @@ def certify_inputs(acts, labels, act_lens, label_lens):
     if act_lens.shape[0] != B or label_lens.shape[0] != B or labels.shape[0] != B:
         raise ValueError("must have a length per example.")
     if os.environ.get("TTX_SKIP_LENGTH_CHECKS", "0") == "1":
-        return
-    mx = torch.stack((act_lens.max(), label_lens.max(), act_lens.min(), label_lens.min())).tolist()  # one sync
+        return None
+    al, ll = act_lens.long(), label_lens.long().to(act_lens.device)
+    tiles = ((al * (ll + 1) + 127) // 128).sum()
+    # labels inside the valid region must index the vocabulary (the kernels gather W_out rows / scatter into them)
+    if labels.shape[1] > 0:
+        lab = labels.to(act_lens.device)
+        valid = torch.arange(labels.shape[1], device=lab.device)[None, :] < ll[:, None]
+        bad = (valid & ((lab < 0) | (lab >= acts.shape[3]))).any().long()
+    else:
+        bad = tiles.new_zeros(())
+    mx = torch.stack((al.max(), ll.max(), al.min(), ll.min(), tiles, bad)).tolist()  # one sync
     if mx[0] != acts.shape[1]:
         raise ValueError("Input length mismatch")
     if mx[1] + 1 != acts.shape[2]:
@@ -40,6 +52,9 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         raise ValueError("lengths must be positive")
     if labels.shape[1] < mx[1]:
         raise ValueError("labels is shorter than max(label_lens)")
+    if mx[5]:
+        raise ValueError("labels must lie in [0, %d) inside each utterance's label_lens" % acts.shape[3])
+    return int(mx[4])
 
 
 def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fastemit_lambda=0.0):
@@ -50,13 +65,13 @@ def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fas
         raise NotImplementedError("fastemit_lambda is not part of the reference's call and is not supported")
     if not acts.is_cuda:
         raise RuntimeError("warprnnt_pytorch (B200): acts must be a CUDA tensor -- there is no CPU fallback")
-    certify_inputs(acts, labels, act_lens, label_lens)
+    n_tiles = certify_inputs(acts, labels, act_lens, label_lens)
     if isinstance(acts, LazyJointLogits):
         ep, pp, w, b = acts.parts
         bf16 = ep.dtype == torch.bfloat16
-        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16)
+        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16, n_tiles=n_tiles)
     else:
-        costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank)
+        costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank, n_tiles=n_tiles)
     if reduction in ("sum", "mean"):
         costs = costs.sum().unsqueeze(-1)
         if reduction == "mean":
