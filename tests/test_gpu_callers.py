@@ -95,6 +95,7 @@ def test_unmodified_train_loop_drives_product_on_cuda(inner):
         assert isinstance(model.joint, ttb.JointNet) and not isinstance(ref_model.joint, ttb.JointNet)
         model.load_state_dict(ref_model.state_dict())    # state-dict keys are the reference's
         model = model.to(DEV)
+        init = {n: p_.detach().clone() for n, p_ in ref_model.named_parameters()}
 
         # (1) one step by hand: every parameter gradient
         inputs, ilen, targets, tlen = data[0]
@@ -130,7 +131,8 @@ def test_unmodified_train_loop_drives_product_on_cuda(inner):
         for a, b in zip(lg_[1:], lr_[1:]):                   # after SGD steps taken with the compared gradients
             assert abs(a - b) / abs(b) < 1e-3, (lg_, lr_)
         for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
-            assert rel(a, b) < 1e-5, n
+            # the three (momentum) SGD updates themselves, not the parameters they are small against
+            assert rel(a.detach().cpu() - init[n], b.detach() - init[n]) < 2 * GRAD_TOL, n
     finally:
         tt_model.JointNet = orig
 
