@@ -67,13 +67,24 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, cons
                       const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
                       int bf16, float* lse, float* lp_blank, float* lp_label, int device, void* stream);
 
-/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried in float64
- * (alpha / beta: one double per row).  costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
-int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
-                        const int32_t* label_lens, const int32_t* meta, int B, int U1, double* alpha, double* beta,
-                        float* costs, double* ll_beta, int device, void* stream);
+/* Elements of the diagonal-major lattice arrays (upper bound for a (B, T, U1) batch; the exact figure is
+ * sum_b (T_b + U_b) * pitch(U_b + 1), pitch(n) = n rounded up to a multiple of 4). */
+int64_t ttx_lattice_elems_upper_bound(int B, int T, int U1);
 
-/* Per-row gradient coefficients rowmeta[row] = {lse, p_blank - rb, p_label - rl, gamma * grad_costs[b] / gmax}
+/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried in float64.  One warp per
+ * (utterance, direction), warp-shuffle hand-off between columns, operand diagonals staged in shared memory by
+ * 16-byte asynchronous copies.  alpha / beta (lat_elems doubles each) are DIAGONAL-MAJOR: cell (t, u) of utterance b
+ * is element meta[4 + B+1 + n_tiles_ub + b] + (t + u) * pitch(U_b + 1) + u.  lat_ws: 2 * lat_elems floats of scratch
+ * (the two log-probs per cell re-ordered the same way).  lat_elems must cover the batch (ttx_prepare computes the
+ * offsets; use the upper bound or the exact sum).
+ * costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
+int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, int64_t n_tiles_ub,
+                        int64_t lat_elems, float* lat_ws, double* alpha, double* beta, float* costs, double* ll_beta,
+                        int device, void* stream);
+
+/* (alpha / beta: the diagonal-major arrays of ttx_lattice_fwd_bwd.)
+ * Per-row gradient coefficients rowmeta[row] = {lse, p_blank - rb, p_label - rl, gamma * grad_costs[b] / gmax}
  * (float4; rb / rl = posteriors of the blank / label arc out of the cell), gmax = max_b |grad_costs[b]| -> scal[2].
  * If d_b_out != NULL the sparse (blank / label) part of dL/db_out is accumulated into it. */
 int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,

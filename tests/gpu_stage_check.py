@@ -153,12 +153,25 @@ def run(stage, B, T, U, V, H):
     lpl_want = torch.where(valid_lab, mm["lpl"], torch.full_like(mm["lpl"], float("nan")))
     fail |= report("lp_label", lpl, compact(mh, lpl_want, al, ll, rows), tol)
 
-    alpha = torch.empty(rows, dtype=torch.float64, device=dev)
-    beta = torch.empty(rows, dtype=torch.float64, device=dev)
+    lat = int(lib.ttx_lattice_elems_upper_bound(B, T, U1))
+    alpha_d = torch.full((lat,), float("nan"), dtype=torch.float64, device=dev)
+    beta_d = torch.full((lat,), float("nan"), dtype=torch.float64, device=dev)
+    lat_ws = f32(2 * lat)
     costs, llb = f32(B), torch.empty(B, dtype=torch.float64, device=dev)
-    _lib.check(lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(ald), _p(lld), _p(meta), B, U1, _p(alpha), _p(beta),
-                                       _p(costs), _p(llb), 0, st), "lattice")
+    _lib.check(lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(ald), _p(lld), _p(meta), B, U1, ntub, lat, _p(lat_ws),
+                                       _p(alpha_d), _p(beta_d), _p(costs), _p(llb), 0, st), "lattice")
     torch.cuda.synchronize()
+
+    def from_diag(x):          # diagonal-major lattice array -> the compact row space the other stages use
+        out = torch.full((rows,), float("nan"), dtype=torch.float64)
+        mh2, xc = meta.cpu(), x.cpu()
+        for i in range(B):
+            Tb, U1b = int(al[i]), int(ll[i]) + 1
+            P, o, base = (U1b + 3) // 4 * 4, int(mh2[4 + B + 1 + ntub + i]), int(mh2[4 + i]) * 128
+            t, u = torch.arange(Tb).view(-1, 1), torch.arange(U1b).view(1, -1)
+            out[base: base + Tb * U1b] = xc[(o + (t + u) * P + u).reshape(-1)]
+        return out
+    alpha, beta = from_diag(alpha_d), from_diag(beta_d)
     inf2nan = lambda x: torch.where(torch.isinf(x), torch.full_like(x, float("nan")), x)  # noqa: E731
     fail |= report("alpha", alpha, compact(mh, inf2nan(mm["alpha"]), al, ll, rows), 1e-5)
     fail |= report("beta", beta, compact(mh, inf2nan(mm["beta"]), al, ll, rows), 1e-5)
@@ -170,7 +183,7 @@ def run(stage, B, T, U, V, H):
     db = torch.zeros(V, dtype=torch.float32, device=dev)
     which = os.environ.get("TTX_BWD", "both")
     rlab = rl2 if stage == "small" else row_label
-    _lib.check(lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha), _p(beta), _p(llb), _p(gcd), _p(scal), _p(rlab),
+    _lib.check(lib.ttx_grad_coeffs(_p(lse), _p(lpb), _p(lpl), _p(alpha_d), _p(beta_d), _p(llb), _p(gcd), _p(scal), _p(rlab),
                                    _p(ald), _p(lld), _p(meta), B, 0, ntub, _p(rowmeta),
                                    _p(db) if (stage == "bwd" and which in ("both", "dw")) else None, 0, st), "coeffs")
     torch.cuda.synchronize()

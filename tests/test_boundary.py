@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.ttx_version() == 1
     assert [h for h in range(32, 1100, 32) if lib.ttx_supported_h(h)] == [64, 128, 192, 256, 384, 512]
     assert lib.ttx_tiles_upper_bound(32, 400, 41) == 32 * 129
-    assert lib.ttx_meta_ints(32, 32 * 129) == 4 + 33 + 32 * 129
+    assert lib.ttx_meta_ints(32, 32 * 129) == 4 + 2 * 33 + 32 * 129
+    assert lib.ttx_lattice_elems_upper_bound(32, 400, 41) == 32 * 440 * 44
 
 
 def test_c_abi_argument_errors_without_gpu():

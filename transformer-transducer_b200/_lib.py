@@ -33,7 +33,8 @@ _PROTOS = {
     "ttx_joint_act": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_joint_lse_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
-    "ttx_lattice_fwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_lattice_elems_upper_bound": [c_i32, c_i32, c_i32],
+    "ttx_lattice_fwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_i32, c_p],
     "ttx_grad_coeffs": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_p, c_p,
                         c_i32, c_p],
     "ttx_transpose16": [c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
@@ -57,7 +58,8 @@ _PROTOS = {
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
 }
-_RESTYPES = {"ttx_last_error": ctypes.c_char_p, "ttx_tiles_upper_bound": c_i64, "ttx_meta_ints": c_i64}
+_RESTYPES = {"ttx_last_error": ctypes.c_char_p, "ttx_tiles_upper_bound": c_i64, "ttx_meta_ints": c_i64,
+             "ttx_lattice_elems_upper_bound": c_i64}
 EXPORTS = tuple(_PROTOS)
 
 

@@ -21,8 +21,8 @@ int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
 int launch_cast_w(const float*, const float*, int, int, int, bool, float*, void*, float*, void*, cudaStream_t);
 int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
                      int, int, bool, void*, int*, void*, cudaStream_t);
-int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, double*, double*, float*,
-                   double*, cudaStream_t);
+int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, int, size_t, float*, double*,
+                   double*, float*, double*, cudaStream_t);
 int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
                      const float*, float*, const int*, const int*, const int*, const int*, int, int, int, float4*,
                      float*, cudaStream_t);
@@ -94,7 +94,12 @@ int64_t ttx_tiles_upper_bound(int B, int T, int U1) {
     return (int64_t)B * (((int64_t)T * U1 + kTile - 1) / kTile);
 }
 
-int64_t ttx_meta_ints(int B, int64_t n_tiles_ub) { return kMetaHdr + (int64_t)B + 1 + n_tiles_ub; }
+int64_t ttx_meta_ints(int B, int64_t n_tiles_ub) { return kMetaHdr + 2 * ((int64_t)B + 1) + n_tiles_ub; }
+
+int64_t ttx_lattice_elems_upper_bound(int B, int T, int U1) {
+    if (B <= 0 || T <= 0 || U1 <= 0) return 0;
+    return (int64_t)B * lat_elems(T, U1);
+}
 
 int ttx_prepare(const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int64_t n_tiles_ub,
                 int32_t* meta, int device, void* stream) {
@@ -142,13 +147,17 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, cons
 }
 
 int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,
-                        const int32_t* label_lens, const int32_t* meta, int B, int U1, double* alpha, double* beta,
-                        float* costs, double* ll_beta, int device, void* stream) {
-    TTX_REQUIRE(lp_blank && lp_label && act_lens && label_lens && meta && alpha && beta && costs && ll_beta,
+                        const int32_t* label_lens, const int32_t* meta, int B, int U1, int64_t n_tiles_ub,
+                        int64_t lat_elems, float* lat_ws, double* alpha, double* beta, float* costs, double* ll_beta,
+                        int device, void* stream) {
+    TTX_REQUIRE(lp_blank && lp_label && act_lens && label_lens && meta && lat_ws && alpha && beta && costs && ll_beta,
                 "ttx_lattice_fwd_bwd: null pointer");
+    TTX_REQUIRE(B > 0 && U1 > 0 && n_tiles_ub >= 1 && lat_elems >= 4 && lat_elems % 4 == 0 && lat_elems < (1ll << 31),
+                "ttx_lattice_fwd_bwd: bad shape B=%d U1=%d tiles=%lld lattice elements=%lld", B, U1,
+                (long long)n_tiles_ub, (long long)lat_elems);
     TTX_ENTER(device);
-    return launch_lattice(lp_blank, lp_label, act_lens, label_lens, meta, B, U1, alpha, beta, costs, ll_beta,
-                          (cudaStream_t)stream);
+    return launch_lattice(lp_blank, lp_label, act_lens, label_lens, meta, B, U1, (int)n_tiles_ub, (size_t)lat_elems,
+                          lat_ws, alpha, beta, costs, ll_beta, (cudaStream_t)stream);
 }
 
 int ttx_grad_coeffs(const float* lse, const float* lp_blank, const float* lp_label, const double* alpha,

@@ -21,7 +21,12 @@ constexpr float kPScale = 4096.0f;                  // power-of-two scale of the
 //   meta[2] = total valid lattice cells, meta[3] = n_tiles upper bound
 //   meta[kMetaHdr + b]            b in [0,B]   : first tile of utterance b (meta[kMetaHdr+B] == n_tiles)
 //   meta[kMetaHdr + B+1 + i]      i in [0,ub)  : utterance of tile i (-1 when unused)
+//   meta[kMetaHdr + B+1 + ub + b] b in [0,B]   : first element of utterance b in the diagonal-major lattice arrays
 constexpr int kMetaHdr = 4;
+// Diagonal-major lattice arrays (lattice kernels, ttx_small.cu): cell (t, u) of an utterance with T frames and U1 = U + 1
+// columns lives at lat0 + (t + u) * lat_pitch(U1) + u; an utterance takes lat_elems(T, U1) elements.
+__host__ __device__ __forceinline__ int lat_pitch(int U1) { return (U1 + 3) & ~3; }
+__host__ __device__ __forceinline__ int lat_elems(int T, int U1) { return (T + U1 - 1) * lat_pitch(U1); }
 // Kept P' matrix (forward+gradient -> weight gradient): flag words, one per tile pair; this one = some pair is flagged.
 constexpr int kKeptAnyDirty = 16383;
 // fp16 scale of the kept-P' weight gradient's B operand As = kKeptUp * w * pfac * A16 (w, |A16| <= 1 and

@@ -12,6 +12,7 @@ namespace ttx {
 __global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restrict__ label_lens, int B, int T,
                             int U1, int n_tiles_ub, int* __restrict__ meta) {
     __shared__ int part[1024];
+    __shared__ int lpart[1024];
     __shared__ int bad;
     __shared__ long long cells_sh;
     const int tid = threadIdx.x;
@@ -22,7 +23,7 @@ __global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restr
         cells_sh = 0;
     }
     __syncthreads();
-    int local = 0;
+    int local = 0, llocal = 0;
     long long cells = 0;
     for (int b = b_lo; b < b_hi; ++b) {
         const int t = act_lens[b], u1 = label_lens[b] + 1;
@@ -31,21 +32,27 @@ __global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restr
             continue;
         }
         local += (t * u1 + kTile - 1) / kTile;
+        llocal += lat_elems(t, u1);
         cells += (long long)t * u1;
     }
     part[tid] = local;
+    lpart[tid] = llocal;
     atomicAdd(reinterpret_cast<unsigned long long*>(&cells_sh), (unsigned long long)cells);
     __syncthreads();
-    // inclusive Hillis-Steele scan over the per-thread partial tile counts
+    // inclusive Hillis-Steele scans over the per-thread partial tile counts / lattice sizes
     for (int off = 1; off < (int)blockDim.x; off <<= 1) {
-        int v = (tid >= off) ? part[tid - off] : 0;
+        const int v = (tid >= off) ? part[tid - off] : 0;
+        const int lv = (tid >= off) ? lpart[tid - off] : 0;
         __syncthreads();
         part[tid] += v;
+        lpart[tid] += lv;
         __syncthreads();
     }
     int tile = part[tid] - local;  // exclusive prefix
+    int lat = lpart[tid] - llocal;
     int* tile0 = meta + kMetaHdr;
     int* tile_b = meta + kMetaHdr + B + 1;
+    int* lat0 = meta + kMetaHdr + B + 1 + n_tiles_ub;
     const int total = part[blockDim.x - 1];
     const bool fits = total <= n_tiles_ub;       // the caller's buffers hold n_tiles_ub tiles
     for (int b = b_lo; b < b_hi; ++b) {
@@ -53,14 +60,17 @@ __global__ void prep_kernel(const int* __restrict__ act_lens, const int* __restr
         const bool ok = !(t < 1 || t > T || u1 < 1 || u1 > U1);
         const int nt = ok ? (t * u1 + kTile - 1) / kTile : 0;
         tile0[b] = tile;
+        lat0[b] = lat;
         if (fits)
             for (int i = 0; i < nt; ++i) tile_b[tile + i] = b;
         tile += nt;
+        lat += ok ? lat_elems(t, u1) : 0;
     }
     for (int i = (fits ? total : 0) + tid; i < n_tiles_ub; i += blockDim.x) tile_b[i] = -1;
     if (tid == 0) {
         const int first_bad = (bad == 0x7fffffff) ? (fits ? 0 : B + 1) : bad;
         tile0[B] = total;
+        lat0[B] = lpart[blockDim.x - 1];
         meta[0] = first_bad ? 0 : total;
         meta[1] = first_bad;
         meta[2] = (int)min(cells_sh, (long long)0x7fffffff);
@@ -244,97 +254,161 @@ int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_
 }
 
 // ------------------------------------------------------------------------------------------- lattice
-// The recursion runs in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
-// ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).
-// The carrier stays float64; the increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 (absolute
-// error ~6e-8 per cell, a random walk of ~2e-6 over a 1200-step lattice).
+// alpha / beta wavefront of the transducer loss (warp-transducer semantics; called
+// train.py:53).  Everything the wavefront touches is stored DIAGONAL-MAJOR: cell (t, u) of utterance b lives at
+// lat0[b] + (t + u) * P_b + u with P_b = U1_b rounded up to a multiple of 4 (ttx_common.cuh: lat_pitch / lat_elems), so
+// one anti-diagonal is one contiguous, 16-byte aligned run of memory:
+//   * lattice_skew_kernel moves the two log-probs per cell that the projection kernels wrote in row order
+//     (lp_blank, lp_label -- nothing else of the V-wide distribution is ever read) into that layout;
+//   * lattice_wave_kernel: ONE WARP per (utterance, direction); lane l owns K adjacent columns u = K l .. K l + K - 1
+//     and carries their alpha (beta) in registers; the neighbour column's value crosses lanes with a warp shuffle.
+//     The operand diagonals are staged PD steps ahead in a shared-memory ring by 16-byte cp.async copies (whole
+//     diagonals, coalesced), alpha / beta are written back as contiguous runs of doubles.
+// The recursion is carried in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
+// ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).  The
+// increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 with ex2 / lg2 (absolute error ~1e-7 per
+// cell, a random walk of ~3e-6 over a 1200-step lattice).
 __device__ __forceinline__ double log_add(double a, double b) {
     const double mx = fmax(a, b), mn = fmin(a, b);
     if (mx == -INFINITY) return -INFINITY;
-    return mx + (double)log1pf(expf((float)(mn - mx)));
+    const float e = ex2f((float)(mn - mx) * kLog2e);          // ex2(-inf) = 0
+    return mx + (double)(lg2f(1.f + e) * kLn2);
 }
 
-// grid = 2B: block b computes alpha of utterance b, block B + b computes beta.  Thread u owns column u and
-// walks the anti-diagonals; its left / right neighbour's previous value travels through shared memory.
-// (warp-transducer semantics; called train.py:53.)
-__global__ void lattice_kernel(const float* __restrict__ lpb, const float* __restrict__ lpl,
-                               const int* __restrict__ act_lens, const int* __restrict__ label_lens,
-                               const int* __restrict__ meta, int B, double* __restrict__ alpha,
-                               double* __restrict__ beta, float* __restrict__ costs, double* __restrict__ ll_beta) {
-    extern __shared__ double xch[];  // 2 x blockDim.x
+__global__ void lattice_skew_kernel(const float* __restrict__ lpb, const float* __restrict__ lpl,
+                                    const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                    const int* __restrict__ meta, int B, float* __restrict__ lpb_d,
+                                    float* __restrict__ lpl_d) {
+    const int tile = blockIdx.x;
+    if (tile >= meta[0]) return;
+    const int b = meta[kMetaHdr + B + 1 + tile];
+    const int r = (tile - meta[kMetaHdr + b]) * kTile + threadIdx.x;
+    const int T = act_lens[b], U1 = label_lens[b] + 1;
+    if (r >= T * U1) return;
+    const int t = r / U1, u = r - t * U1;
+    const size_t o = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b] + (size_t)(t + u) * lat_pitch(U1) + u;
+    const size_t g = (size_t)tile * kTile + threadIdx.x;
+    lpb_d[o] = lpb[g];
+    lpl_d[o] = lpl[g];
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ double shfl_up_f64(double v, bool take) {
+    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), 1);
+    return take ? __hiloint2double(hi, lo) : -INFINITY;
+}
+__device__ __forceinline__ double shfl_down_f64(double v, bool take) {
+    const int lo = __shfl_down_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_down_sync(0xffffffffu, __double2hiint(v), 1);
+    return take ? __hiloint2double(hi, lo) : -INFINITY;
+}
+
+// grid = 2B: block b computes alpha of utterance b, block B + b its beta.  W warps of 32 K columns each (W = 1 whenever
+// U1 <= 32 K, i.e. up to 256 columns; wider lattices hand the boundary column over through shared memory with one
+// block barrier per diagonal).
+template <int K, int PD, int W>
+__global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
+        const float* __restrict__ lpb_d, const float* __restrict__ lpl_d, const int* __restrict__ act_lens,
+        const int* __restrict__ label_lens, const int* __restrict__ meta, int B, double* __restrict__ alpha_d,
+        double* __restrict__ beta_d, float* __restrict__ costs, double* __restrict__ ll_beta) {
+    static_assert(PD >= 2, "ring of at least two diagonals");
+    constexpr int PMAX = 32 * K * W;                       // floats per staged diagonal
+    __shared__ __align__(16) float stage[PD][2][PMAX];
+    __shared__ double bnd[2][W + 1];
     if (meta[1] != 0) return;
     const bool is_beta = blockIdx.x >= (unsigned)B;
     const int b = is_beta ? blockIdx.x - B : blockIdx.x;
     const int T = act_lens[b], U1 = label_lens[b] + 1;
-    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
-    const int u = threadIdx.x;
+    const int P = lat_pitch(U1);
+    const size_t base = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u0 = (warp * 32 + lane) * K;                 // first column of this lane
     const int nd = T + U1 - 1;
-    const bool active = u < U1;
-    double self = -INFINITY;  // my column's value on the previous diagonal
-    constexpr int PD = 4;    // prefetch distance in diagonals
-    float pf_b[PD], pf_l[PD];
-    // operand of diagonal d for column u:  alpha: t = d - u;  beta: t = T-1 - (d - (U1-1-u))
-    auto fetch = [&](int d, float& xb, float& xl) {
-        xb = 0.f;
-        xl = 0.f;
-        if (!active) return;
-        if (!is_beta) {
-            const int t = d - u;
-            if (t < 0 || t >= T) return;
-            if (t > 0) xb = __ldg(lpb + base + (size_t)(t - 1) * U1 + u);
-            if (u > 0) xl = __ldg(lpl + base + (size_t)t * U1 + (u - 1));
-        } else {
-            const int t = T - 1 - (d - (U1 - 1 - u));
-            if (t < 0 || t >= T) return;
-            xb = __ldg(lpb + base + (size_t)t * U1 + u);
-            if (u < U1 - 1) xl = __ldg(lpl + base + (size_t)t * U1 + u);
+    const int nchunk = P >> 2;                             // 16-byte chunks per diagonal
+    // operand diagonal of step s: alpha step s works on diagonal s with operands from diagonal s - 1,
+    // beta step s works on diagonal nd - 1 - s with operands from the same diagonal
+    auto stage_step = [&](int s) {
+        const int od = is_beta ? nd - 1 - s : s - 1;
+        if (s < nd && od >= 0) {
+            const size_t g = base + (size_t)od * P;
+            float* dst = &stage[s % PD][0][0];
+            for (int c = threadIdx.x; c < nchunk; c += 32 * W) {
+                cp_async16(smem_u32(dst + 4 * c), lpb_d + g + 4 * c);
+                cp_async16(smem_u32(dst + PMAX + 4 * c), lpl_d + g + 4 * c);
+            }
         }
+        cp_async_commit();
     };
 #pragma unroll
-    for (int i = 0; i < PD; ++i) fetch(i, pf_b[i], pf_l[i]);
-    for (int d0 = 0; d0 < nd; d0 += PD) {
+    for (int s = 0; s < PD - 1; ++s) stage_step(s);
+    double v[K];
 #pragma unroll
-        for (int i = 0; i < PD; ++i) {
-            const int d = d0 + i;
-            if (d >= nd) break;
-            const float xb = pf_b[i], xl = pf_l[i];
-            fetch(d + PD, pf_b[i], pf_l[i]);
-            double* cur = xch + (d & 1) * blockDim.x;
-            const double* prev = xch + ((d & 1) ^ 1) * blockDim.x;
+    for (int j = 0; j < K; ++j) v[j] = -INFINITY;
+    double* out = (is_beta ? beta_d : alpha_d) + base;
+    for (int s = 0; s < nd; ++s) {
+        if (W > 1) {                                        // boundary column of the previous step, for the next warp
+            if (!is_beta && lane == 31) bnd[s & 1][warp + 1] = v[K - 1];
+            if (is_beta && lane == 0) bnd[s & 1][warp] = v[0];
+        }
+        cp_async_wait<PD - 2>();                            // this step's diagonal has landed (own copies) ...
+        if (W > 1) __syncthreads();                         // ... everybody's, and slot (s - 1) % PD has been read
+        else __syncwarp();
+        stage_step(s + PD - 1);
+        const float* sb = &stage[s % PD][0][0];
+        const float* sl = sb + PMAX;
+        const int d = is_beta ? nd - 1 - s : s;
+        // neighbour column's value of the previous step: lane - 1's last column (alpha) / lane + 1's first (beta)
+        double nb;
+        if (!is_beta) {
+            nb = shfl_up_f64(v[K - 1], lane > 0);
+            if (W > 1 && lane == 0 && warp > 0) nb = bnd[s & 1][warp];
+        } else {
+            nb = shfl_down_f64(v[0], lane < 31);
+            if (W > 1 && lane == 31 && warp < W - 1) nb = bnd[s & 1][warp + 1];
+        }
+        double nv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int u = u0 + j, t = d - u;
+            const bool on = u < U1 && t >= 0 && t < T;
             double val = -INFINITY;
-            bool on = false;
-            int t = 0;
-            if (active) {
-                t = is_beta ? T - 1 - (d - (U1 - 1 - u)) : d - u;
-                on = (t >= 0 && t < T);
-            }
             if (on) {
                 if (!is_beta) {
-                    if (t == 0 && u == 0) val = 0.0;
-                    else {
-                        const double from_t = (t > 0) ? self + (double)xb : -INFINITY;
-                        const double from_u = (u > 0) ? prev[u - 1] + (double)xl : -INFINITY;
-                        val = log_add(from_t, from_u);
-                    }
-                    alpha[base + (size_t)t * U1 + u] = val;
+                    const double left = (j > 0) ? v[j > 0 ? j - 1 : 0] : nb;
+                    const double from_t = (t > 0) ? v[j] + (double)sb[u] : -INFINITY;
+                    const double from_u = (u > 0) ? left + (double)sl[u > 0 ? u - 1 : 0] : -INFINITY;
+                    val = (d == 0) ? 0.0 : log_add(from_t, from_u);
                 } else {
-                    if (t == T - 1 && u == U1 - 1) val = (double)xb;
-                    else {
-                        const double from_t = (t < T - 1) ? self + (double)xb : -INFINITY;
-                        const double from_u = (u < U1 - 1) ? prev[u + 1] + (double)xl : -INFINITY;
-                        val = log_add(from_t, from_u);
-                    }
-                    beta[base + (size_t)t * U1 + u] = val;
+                    const double right = (j < K - 1) ? v[j < K - 1 ? j + 1 : j] : nb;
+                    const double from_t = (t < T - 1) ? v[j] + (double)sb[u] : -INFINITY;
+                    const double from_u = (u < U1 - 1) ? right + (double)sl[u] : -INFINITY;
+                    val = (d == nd - 1) ? (double)sb[u] : log_add(from_t, from_u);
                 }
-                self = val;
+                out[(size_t)d * P + u] = val;
             }
-            cur[u] = val;
-            __syncthreads();
-            if (d == nd - 1 && on) {
-                if (!is_beta) costs[b] = (float)-(val + (double)__ldg(lpb + base + (size_t)(T - 1) * U1 + (U1 - 1)));
-                else ll_beta[b] = val;
-            }
+            nv[j] = val;
         }
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = nv[j];
+    }
+    cp_async_wait<0>();
+    // alpha ends in cell (T-1, U1-1) on diagonal nd - 1, beta in cell (0, 0) on diagonal 0
+    if (!is_beta) {
+        const int u = U1 - 1;
+        if (u >= u0 && u < u0 + K) {
+            double a = v[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) a = (u - u0 == j) ? v[j] : a;
+            costs[b] = (float)-(a + (double)__ldg(lpb_d + base + (size_t)(nd - 1) * P + u));
+        }
+    } else if (threadIdx.x == 0) {
+        ll_beta[b] = v[0];
     }
 }
 
@@ -384,12 +458,15 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
     if (r < T * U1) {
         const int t = r / U1, u = r - t * U1;
         const double ll = ll_beta[b];
-        const double be = beta[base + r];
-        const float gam = expf((float)(alpha[base + r] + be - ll));
+        // alpha / beta are diagonal-major (see the lattice kernels): (t+1, u) and (t, u+1) sit on the next diagonal
+        const int P = lat_pitch(U1);
+        const size_t li = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b] + (size_t)(t + u) * P + u;
+        const double be = beta[li];
+        const float gam = expf((float)(alpha[li] + be - ll));
         float rb, rl = 0.f;
-        if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[base + r + U1] - be));
+        if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[li + P] - be));
         else rb = (u == U1 - 1) ? 1.f : 0.f;
-        if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[base + r + 1] - be));
+        if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[li + P + 1] - be));
         const int lab = row_label[base + r];
         const float w = gam * grad_costs[b] / scal[2];
         float fb = expf(lpb[base + r]) - rb;
@@ -870,15 +947,33 @@ int launch_joint_act(const float* eproj, const float* pproj, const int* labels, 
     return 0;
 }
 
+template <int K, int PD, int W>
+static void lattice_launch(int B, cudaStream_t s, const float* lpb_d, const float* lpl_d, const int* act_lens,
+                           const int* label_lens, const int* meta, double* alpha, double* beta, float* costs,
+                           double* ll_beta) {
+    lattice_wave_kernel<K, PD, W><<<2 * B, 32 * W, 0, s>>>(lpb_d, lpl_d, act_lens, label_lens, meta, B, alpha, beta, costs,
+                                                          ll_beta);
+}
+
+// lat_ws: 2 * lat_elems floats (the skewed copies of lp_blank / lp_label); alpha / beta: lat_elems doubles each
 int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, const int* label_lens, const int* meta,
-                   int B, int U1, double* alpha, double* beta, float* costs, double* ll_beta, cudaStream_t s) {
-    const int threads = ((U1 + 31) / 32) * 32;
-    if (threads > 1024) {
+                   int B, int U1, int n_tiles_ub, size_t lat_elems, float* lat_ws, double* alpha, double* beta,
+                   float* costs, double* ll_beta, cudaStream_t s) {
+    if (U1 > 1024) {
         set_error("lattice kernel supports at most 1023 labels per utterance (got U+1 = %d)", U1);
         return 1;
     }
-    lattice_kernel<<<2 * B, threads, 2 * threads * sizeof(double), s>>>(lpb, lpl, act_lens, label_lens, meta, B, alpha,
-                                                                     beta, costs, ll_beta);
+    float* lpb_d = lat_ws;
+    float* lpl_d = lat_ws + lat_elems;
+    lattice_skew_kernel<<<n_tiles_ub, kTile, 0, s>>>(lpb, lpl, act_lens, label_lens, meta, B, lpb_d, lpl_d);
+#define TTX_LAT(K, PD, W) lattice_launch<K, PD, W>(B, s, lpb_d, lpl_d, act_lens, label_lens, meta, alpha, beta, costs, ll_beta)
+    if (U1 <= 32) TTX_LAT(1, 8, 1);
+    else if (U1 <= 64) TTX_LAT(2, 8, 1);
+    else if (U1 <= 128) TTX_LAT(4, 8, 1);
+    else if (U1 <= 256) TTX_LAT(8, 8, 1);
+    else if (U1 <= 512) TTX_LAT(8, 4, 2);
+    else TTX_LAT(8, 4, 4);
+#undef TTX_LAT
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -25,7 +25,7 @@ def _stream(dev):
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
 KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew_kept": 2, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
-                    "ttx_lattice_fwd_bwd": 1, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
+                    "ttx_lattice_fwd_bwd": 2, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
 
@@ -53,7 +53,8 @@ def _i32_cuda(t, dev, name):
 class _Plan:
     """Shape bookkeeping + the buffers shared by both entry paths."""
 
-    def __init__(self, B, T, U1, dev, act_lens, label_lens, n_tiles=None):
+    def __init__(self, B, T, U1, dev, act_lens, label_lens, sizes=None):
+        n_tiles, n_lat = sizes if sizes is not None else (None, None)
         lib = _lib.get()
         self.lib, self.dev, self.B, self.T, self.U1 = lib, dev, B, T, U1
         self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -63,6 +64,8 @@ class _Plan:
         ub = int(lib.ttx_tiles_upper_bound(B, T, U1))
         self.ntub = ub if n_tiles is None else max(2, min(ub + 1, (int(n_tiles) + 1) & ~1))
         self.rows = self.ntub * 128
+        lat_ub = int(lib.ttx_lattice_elems_upper_bound(B, T, U1))
+        self.lat = lat_ub if n_lat is None else max(4, min(lat_ub, int(n_lat)))     # diagonal-major lattice elements
         self.meta = torch.empty(int(lib.ttx_meta_ints(B, self.ntub)), dtype=torch.int32, device=dev)
         self.act_lens, self.label_lens = act_lens, label_lens
         _call("ttx_prepare", dev, _p(act_lens), _p(label_lens), B, T, U1, self.ntub, _p(self.meta), self.idx,
@@ -72,13 +75,15 @@ class _Plan:
         return torch.empty(self.rows * n, dtype=torch.float32, device=self.dev)
 
     def lattice(self, lse, lpb, lpl):
-        alpha = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
-        beta = torch.empty(self.rows, dtype=torch.float64, device=self.dev)
+        alpha = torch.empty(self.lat, dtype=torch.float64, device=self.dev)
+        beta = torch.empty(self.lat, dtype=torch.float64, device=self.dev)
+        lat_ws = torch.empty(2 * self.lat, dtype=torch.float32, device=self.dev)
         costs = torch.full((self.B,), float("nan"), dtype=torch.float32, device=self.dev)   # stays NaN on bad lengths
         ll_beta = torch.empty(self.B, dtype=torch.float64, device=self.dev)
         _call("ttx_lattice_fwd_bwd", self.dev, _p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
-                                               _p(self.meta), self.B, self.U1, _p(alpha), _p(beta), _p(costs),
-                                               _p(ll_beta), self.idx, _stream(self.dev))
+                                               _p(self.meta), self.B, self.U1, self.ntub, self.lat, _p(lat_ws),
+                                               _p(alpha), _p(beta), _p(costs), _p(ll_beta), self.idx,
+                                               _stream(self.dev))
         return alpha, beta, costs, ll_beta
 
     def grad_coeffs(self, lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, blank, d_b=None):
@@ -120,7 +125,7 @@ def supported_width(H):
 
 class FusedJointRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, n_tiles=None):
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
         need_grad = any(ctx.needs_input_grad[:4])      # (grad mode is off inside Function.forward)
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
@@ -139,7 +144,7 @@ class FusedJointRNNT(torch.autograd.Function):
         b = b_out.detach().float().contiguous()
         labels = labels.contiguous()
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -270,7 +275,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         return [(t0, min(plan.ntub, t0 + tiles)) for t0 in range(0, plan.ntub, tiles)]
 
     @staticmethod
-    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, n_tiles=None):
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
         dev = eproj.device
@@ -284,7 +289,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         labels = labels.contiguous()
         dt16 = torch.bfloat16 if bf16 else torch.float16
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
             scal = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -365,7 +370,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
-def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, n_tiles=None):
+def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, sizes=None):
     """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out.
 
     Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
@@ -373,12 +378,12 @@ def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, b
     fused = supported_width(eproj.shape[-1]) and os.environ.get("TTX_FORCE_CHUNKED", "0") != "1"
     fn = FusedJointRNNT if fused else ChunkedJointRNNT
     return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
-                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16, n_tiles)
+                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16, sizes)
 
 
 class DenseRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, acts, labels, act_lens, label_lens, blank, n_tiles=None):
+    def forward(ctx, acts, labels, act_lens, label_lens, blank, sizes=None):
         if not acts.is_cuda:
             raise RuntimeError("rnnt_loss needs CUDA tensors (there is no CPU fallback)")
         dev = acts.device
@@ -387,7 +392,7 @@ class DenseRNNT(torch.autograd.Function):
         labels = labels.contiguous()
         lib = _lib.get()
         with torch.cuda.device(dev):
-            plan = _Plan(B, T, U1, dev, act_lens, label_lens, n_tiles)
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
@@ -414,7 +419,7 @@ class DenseRNNT(torch.autograd.Function):
         return grads.to(ctx.in_dtype), None, None, None, None, None
 
 
-def dense_rnnt(acts, labels, act_lens, label_lens, blank=0, n_tiles=None):
+def dense_rnnt(acts, labels, act_lens, label_lens, blank=0, sizes=None):
     dev = acts.device
     return DenseRNNT.apply(acts, _i32_cuda(labels, dev, "labels"), _i32_cuda(act_lens, dev, "act_lens"),
-                           _i32_cuda(label_lens, dev, "label_lens"), blank, n_tiles)
+                           _i32_cuda(label_lens, dev, "label_lens"), blank, sizes)

@@ -15,9 +15,10 @@ from .lazy import LazyJointLogits
 
 
 def certify_inputs(acts, labels, act_lens, label_lens):
-    """Upstream's argument checks.  Returns the number of 128-row lattice tiles the batch really has
-    (sum_b ceil(T_b (U_b + 1) / 128)), taken from the same single host synchronisation as the length checks, or None
-    when TTX_SKIP_LENGTH_CHECKS=1 skips that synchronisation (buffers are then sized by the dense upper bound)."""
+    """Upstream's argument checks.  Returns the batch's real sizes (128-row lattice tiles sum_b ceil(T_b (U_b + 1) / 128),
+    elements of the diagonal-major lattice arrays), taken from the same single host synchronisation as the length
+    checks, or None when TTX_SKIP_LENGTH_CHECKS=1 skips that synchronisation (buffers are then sized by the dense
+    upper bounds)."""
     for name, t in (("labels", labels), ("act_lens", act_lens), ("label_lens", label_lens)):
         if t.dtype != torch.int32:
             raise TypeError("%s must be int32" % name)
@@ -36,6 +37,7 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         return None
     al, ll = act_lens.long(), label_lens.long().to(act_lens.device)
     tiles = ((al * (ll + 1) + 127) // 128).sum()
+    lat = ((al + ll) * ((ll + 4) // 4 * 4)).sum()            # (T + U1 - 1) * pitch(U1), pitch = U1 rounded up to 4
     # labels inside the valid region must index the vocabulary (the kernels gather W_out rows / scatter into them)
     if labels.shape[1] > 0:
         lab = labels.to(act_lens.device)
@@ -43,7 +45,7 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         bad = (valid & ((lab < 0) | (lab >= acts.shape[3]))).any().long()
     else:
         bad = tiles.new_zeros(())
-    mx = torch.stack((al.max(), ll.max(), al.min(), ll.min(), tiles, bad)).tolist()  # one sync
+    mx = torch.stack((al.max(), ll.max(), al.min(), ll.min(), tiles, bad, lat)).tolist()  # one sync
     if mx[0] != acts.shape[1]:
         raise ValueError("Input length mismatch")
     if mx[1] + 1 != acts.shape[2]:
@@ -54,7 +56,7 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         raise ValueError("labels is shorter than max(label_lens)")
     if mx[5]:
         raise ValueError("labels must lie in [0, %d) inside each utterance's label_lens" % acts.shape[3])
-    return int(mx[4])
+    return int(mx[4]), int(mx[6])
 
 
 def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fastemit_lambda=0.0):
@@ -65,13 +67,13 @@ def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fas
         raise NotImplementedError("fastemit_lambda is not part of the reference's call and is not supported")
     if not acts.is_cuda:
         raise RuntimeError("warprnnt_pytorch (B200): acts must be a CUDA tensor -- there is no CPU fallback")
-    n_tiles = certify_inputs(acts, labels, act_lens, label_lens)
+    sizes = certify_inputs(acts, labels, act_lens, label_lens)
     if isinstance(acts, LazyJointLogits):
         ep, pp, w, b = acts.parts
         bf16 = ep.dtype == torch.bfloat16
-        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16, n_tiles=n_tiles)
+        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16, sizes=sizes)
     else:
-        costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank, n_tiles=n_tiles)
+        costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank, sizes=sizes)
     if reduction in ("sum", "mean"):
         costs = costs.sum().unsqueeze(-1)
         if reduction == "mean":
