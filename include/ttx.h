@@ -74,8 +74,9 @@ int64_t ttx_lattice_elems_upper_bound(int B, int T, int U1);
 /* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried in float64.  One warp per
  * (utterance, direction), warp-shuffle hand-off between columns, operand diagonals staged in shared memory by
  * 16-byte asynchronous copies.  alpha / beta (lat_elems doubles each) are DIAGONAL-MAJOR: cell (t, u) of utterance b
- * is element meta[4 + B+1 + n_tiles_ub + b] + (t + u) * pitch(U_b + 1) + u.  lat_ws: 2 * lat_elems floats of scratch
- * (the two log-probs per cell re-ordered the same way).  lat_elems must cover the batch (ttx_prepare computes the
+ * is element meta[4 + B+1 + n_tiles_ub + b] + (t + u) * pitch(U_b + 1) + u of alpha; beta lives on the mirrored
+ * lattice, beta(t, u) at the position of cell (T_b-1-t, U_b-u).  lat_ws: 4 * lat_elems floats of scratch (the two
+ * log-probs per cell re-ordered the same way, as arriving arcs of the lattice and of its mirror image).  lat_elems must cover the batch (ttx_prepare computes the
  * offsets; use the upper bound or the exact sum).
  * costs[b] = -(alpha(T_b-1,U_b) + lp_blank(T_b-1,U_b)); ll_beta[b] = beta(0,0). */
 int ttx_lattice_fwd_bwd(const float* lp_blank, const float* lp_label, const int32_t* act_lens,

@@ -156,22 +156,24 @@ def run(stage, B, T, U, V, H):
     lat = int(lib.ttx_lattice_elems_upper_bound(B, T, U1))
     alpha_d = torch.full((lat,), float("nan"), dtype=torch.float64, device=dev)
     beta_d = torch.full((lat,), float("nan"), dtype=torch.float64, device=dev)
-    lat_ws = f32(2 * lat)
+    lat_ws = f32(4 * lat)
     costs, llb = f32(B), torch.empty(B, dtype=torch.float64, device=dev)
     _lib.check(lib.ttx_lattice_fwd_bwd(_p(lpb), _p(lpl), _p(ald), _p(lld), _p(meta), B, U1, ntub, lat, _p(lat_ws),
                                        _p(alpha_d), _p(beta_d), _p(costs), _p(llb), 0, st), "lattice")
     torch.cuda.synchronize()
 
-    def from_diag(x):          # diagonal-major lattice array -> the compact row space the other stages use
+    def from_diag(x, mirrored):          # diagonal-major lattice array -> the compact row space the other stages use
         out = torch.full((rows,), float("nan"), dtype=torch.float64)
         mh2, xc = meta.cpu(), x.cpu()
         for i in range(B):
             Tb, U1b = int(al[i]), int(ll[i]) + 1
             P, o, base = (U1b + 3) // 4 * 4, int(mh2[4 + B + 1 + ntub + i]), int(mh2[4 + i]) * 128
             t, u = torch.arange(Tb).view(-1, 1), torch.arange(U1b).view(1, -1)
+            if mirrored:
+                t, u = Tb - 1 - t, U1b - 1 - u
             out[base: base + Tb * U1b] = xc[(o + (t + u) * P + u).reshape(-1)]
         return out
-    alpha, beta = from_diag(alpha_d), from_diag(beta_d)
+    alpha, beta = from_diag(alpha_d, False), from_diag(beta_d, True)
     inf2nan = lambda x: torch.where(torch.isinf(x), torch.full_like(x, float("nan")), x)  # noqa: E731
     fail |= report("alpha", alpha, compact(mh, inf2nan(mm["alpha"]), al, ll, rows), 1e-5)
     fail |= report("beta", beta, compact(mh, inf2nan(mm["beta"]), al, ll, rows), 1e-5)

@@ -118,7 +118,7 @@ def test_lattice_wavefront_matches_float64_oracle(T, U):
     lat = int(lib.ttx_lattice_elems_upper_bound(B, T, U1))
     alpha = torch.full((lat,), float("nan"), dtype=torch.float64, device=DEV)
     beta = torch.full((lat,), float("nan"), dtype=torch.float64, device=DEV)
-    ws = torch.empty(2 * lat, dtype=torch.float32, device=DEV)
+    ws = torch.empty(4 * lat, dtype=torch.float32, device=DEV)
     costs = torch.empty(B, dtype=torch.float32, device=DEV)
     llb = torch.empty(B, dtype=torch.float64, device=DEV)
     lpb_g, lpl_g = lpb_r.to(DEV), lpl_r.to(DEV)
@@ -131,8 +131,9 @@ def test_lattice_wavefront_matches_float64_oracle(T, U):
         P, o = (U1b + 3) // 4 * 4, int(mh[4 + B + 1 + ntub + b])
         t, u = torch.arange(Tb).view(-1, 1), torch.arange(U1b).view(1, -1)
         idx = (o + (t + u) * P + u).reshape(-1)
+        idx_m = (o + (Tb - 1 - t + U1b - 1 - u) * P + (U1b - 1 - u)).reshape(-1)      # beta: mirrored lattice
         assert (alpha[idx] - alpha_w[b, :Tb, :U1b].reshape(-1)).abs().max() < 2e-5
-        assert (beta[idx] - beta_w[b, :Tb, :U1b].reshape(-1)).abs().max() < 2e-5
+        assert (beta[idx_m] - beta_w[b, :Tb, :U1b].reshape(-1)).abs().max() < 2e-5
     assert ((costs.double().cpu() - costs_w) / costs_w).abs().max() < 1e-6
     assert ((-llb.cpu() - costs_w) / costs_w).abs().max() < 1e-6
 

@@ -257,28 +257,33 @@ int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_
 // alpha / beta wavefront of the transducer loss (warp-transducer semantics; called
 // train.py:53).  Everything the wavefront touches is stored DIAGONAL-MAJOR: cell (t, u) of utterance b lives at
 // lat0[b] + (t + u) * P_b + u with P_b = U1_b rounded up to a multiple of 4 (ttx_common.cuh: lat_pitch / lat_elems), so
-// one anti-diagonal is one contiguous, 16-byte aligned run of memory:
-//   * lattice_skew_kernel moves the two log-probs per cell that the projection kernels wrote in row order
-//     (lp_blank, lp_label -- nothing else of the V-wide distribution is ever read) into that layout;
-//   * lattice_wave_kernel: ONE WARP per (utterance, direction); lane l owns K adjacent columns u = K l .. K l + K - 1
-//     and carries their alpha (beta) in registers; the neighbour column's value crosses lanes with a warp shuffle.
-//     The operand diagonals are staged PD steps ahead in a shared-memory ring by 16-byte cp.async copies (whole
-//     diagonals, coalesced), alpha / beta are written back as contiguous runs of doubles.
+// one anti-diagonal is one contiguous, 16-byte aligned run of memory.  beta is computed on the MIRRORED lattice
+// (t', u') = (T-1-t, U1-1-u), on which it is the same recursion as alpha,
+//     x(t, u) = logaddexp(x(t-1, u) + inB(t, u), x(t, u-1) + inL(t, u)),   x(0, 0) = init,
+// with inB / inL the log-probabilities of the blank / label arc ARRIVING in the cell -- so one code path serves both:
+//   * lattice_skew_kernel re-orders the two log-probs per cell that the projection kernels wrote in row order
+//     (lp_blank, lp_label -- nothing else of the V-wide distribution is ever read) into the four arc arrays;
+//   * lattice_wave_kernel: one CTA per (utterance, direction), lane l owns K <= 2 adjacent columns and carries them in
+//     registers; the neighbour column's value crosses lanes with a warp shuffle (and warps, for lattices wider than
+//     64 columns, through shared memory behind the one block barrier per diagonal).  The operand diagonals are staged
+//     PD - 1 steps ahead in a shared-memory ring by 16-byte cp.async copies (whole diagonals, coalesced), read back as
+//     one vector per lane, and alpha / beta leave as contiguous runs of doubles.
 // The recursion is carried in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
 // ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).  The
 // increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 with ex2 / lg2 (absolute error ~1e-7 per
-// cell, a random walk of ~3e-6 over a 1200-step lattice).
+// cell, a random walk of ~3e-6 over a 1200-step lattice).  "log 0" is the finite sentinel kLatNeg: no special cases.
+constexpr double kLatNeg = -1.0e30;
 __device__ __forceinline__ double log_add(double a, double b) {
     const double mx = fmax(a, b), mn = fmin(a, b);
-    if (mx == -INFINITY) return -INFINITY;
-    const float e = ex2f((float)(mn - mx) * kLog2e);          // ex2(-inf) = 0
+    const float e = ex2f((float)(mn - mx) * kLog2e);          // both "log 0": e = 1, the sum stays at the sentinel
     return mx + (double)(lg2f(1.f + e) * kLn2);
 }
 
+// lat_ws = four arrays of lat_elems floats: [0] inB, [1] inL of the alpha lattice, [2] inB, [3] inL of the mirrored
+// (beta) lattice.  Entries that no arc arrives in (first row / first column) stay unwritten and are never used.
 __global__ void lattice_skew_kernel(const float* __restrict__ lpb, const float* __restrict__ lpl,
                                     const int* __restrict__ act_lens, const int* __restrict__ label_lens,
-                                    const int* __restrict__ meta, int B, float* __restrict__ lpb_d,
-                                    float* __restrict__ lpl_d) {
+                                    const int* __restrict__ meta, int B, size_t lat_elems, float* __restrict__ ws) {
     const int tile = blockIdx.x;
     if (tile >= meta[0]) return;
     const int b = meta[kMetaHdr + B + 1 + tile];
@@ -286,10 +291,17 @@ __global__ void lattice_skew_kernel(const float* __restrict__ lpb, const float* 
     const int T = act_lens[b], U1 = label_lens[b] + 1;
     if (r >= T * U1) return;
     const int t = r / U1, u = r - t * U1;
-    const size_t o = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b] + (size_t)(t + u) * lat_pitch(U1) + u;
+    const int P = lat_pitch(U1);
+    const size_t base = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b];
     const size_t g = (size_t)tile * kTile + threadIdx.x;
-    lpb_d[o] = lpb[g];
-    lpl_d[o] = lpl[g];
+    const float vb = lpb[g], vl = lpl[g];
+    const size_t nxt = base + (size_t)(t + u + 1) * P + u;      // next diagonal, same column: cell (t+1, u)
+    if (t + 1 < T) ws[nxt] = vb;                               // blank arc (t, u) -> (t+1, u)
+    if (u + 1 < U1) ws[lat_elems + nxt + 1] = vl;              // label arc (t, u) -> (t, u+1)
+    const int tm = T - 1 - t, um = U1 - 1 - u;                 // mirrored lattice: both arcs of (t, u) arrive in (tm, um)
+    const size_t m = base + (size_t)(tm + um) * P + um;
+    ws[2 * lat_elems + m] = vb;
+    ws[3 * lat_elems + m] = vl;
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -300,24 +312,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ double shfl_up_f64(double v, bool take) {
-    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), 1);
-    return take ? __hiloint2double(hi, lo) : -INFINITY;
-}
-__device__ __forceinline__ double shfl_down_f64(double v, bool take) {
-    const int lo = __shfl_down_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_down_sync(0xffffffffu, __double2hiint(v), 1);
-    return take ? __hiloint2double(hi, lo) : -INFINITY;
-}
 
-// grid = 2B: block b computes alpha of utterance b, block B + b its beta.  W warps of 32 K columns each (W = 1 whenever
-// U1 <= 32 K, i.e. up to 256 columns; wider lattices hand the boundary column over through shared memory with one
-// block barrier per diagonal).
+// grid = 2B: block b computes alpha of utterance b, block B + b its beta (on the mirrored lattice, stored mirrored:
+// beta(t, u) is element (T-1-t + U1-1-u) * P + U1-1-u of the utterance's run).  W warps x 32 lanes x K columns.
 template <int K, int PD, int W>
 __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
-        const float* __restrict__ lpb_d, const float* __restrict__ lpl_d, const int* __restrict__ act_lens,
+        const float* __restrict__ ws, size_t lat_elems, const int* __restrict__ act_lens,
         const int* __restrict__ label_lens, const int* __restrict__ meta, int B, double* __restrict__ alpha_d,
         double* __restrict__ beta_d, float* __restrict__ costs, double* __restrict__ ll_beta) {
-    static_assert(PD >= 2, "ring of at least two diagonals");
+    static_assert(PD >= 2 && (K == 1 || K == 2), "ring of at least two diagonals, one or two columns per lane");
     constexpr int PMAX = 32 * K * W;                       // floats per staged diagonal
     __shared__ __align__(16) float stage[PD][2][PMAX];
     __shared__ double bnd[2][W + 1];
@@ -327,88 +330,77 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
     const int T = act_lens[b], U1 = label_lens[b] + 1;
     const int P = lat_pitch(U1);
     const size_t base = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b];
+    const float* inB = ws + (is_beta ? 2 * lat_elems : 0) + base;
+    const float* inL = inB + lat_elems;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u0 = (warp * 32 + lane) * K;                 // first column of this lane
+    const int u0 = threadIdx.x * K;                        // first column of this lane
     const int nd = T + U1 - 1;
     const int nchunk = P >> 2;                             // 16-byte chunks per diagonal
-    // operand diagonal of step s: alpha step s works on diagonal s with operands from diagonal s - 1,
-    // beta step s works on diagonal nd - 1 - s with operands from the same diagonal
-    auto stage_step = [&](int s) {
-        const int od = is_beta ? nd - 1 - s : s - 1;
-        if (s < nd && od >= 0) {
-            const size_t g = base + (size_t)od * P;
-            float* dst = &stage[s % PD][0][0];
+    auto stage_step = [&](int s, int slot) {               // operands of diagonal s into ring slot `slot`
+        if (s < nd) {
+            const float* gb = inB + (size_t)s * P;
+            const float* gl = inL + (size_t)s * P;
             for (int c = threadIdx.x; c < nchunk; c += 32 * W) {
-                cp_async16(smem_u32(dst + 4 * c), lpb_d + g + 4 * c);
-                cp_async16(smem_u32(dst + PMAX + 4 * c), lpl_d + g + 4 * c);
+                cp_async16(smem_u32(&stage[slot][0][4 * c]), gb + 4 * c);
+                cp_async16(smem_u32(&stage[slot][1][4 * c]), gl + 4 * c);
             }
         }
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < PD - 1; ++s) stage_step(s);
+    for (int s = 0; s < PD - 1; ++s) stage_step(s, s);
     double v[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) v[j] = -INFINITY;
-    double* out = (is_beta ? beta_d : alpha_d) + base;
-    for (int s = 0; s < nd; ++s) {
-        if (W > 1) {                                        // boundary column of the previous step, for the next warp
-            if (!is_beta && lane == 31) bnd[s & 1][warp + 1] = v[K - 1];
-            if (is_beta && lane == 0) bnd[s & 1][warp] = v[0];
-        }
-        cp_async_wait<PD - 2>();                            // this step's diagonal has landed (own copies) ...
-        if (W > 1) __syncthreads();                         // ... everybody's, and slot (s - 1) % PD has been read
-        else __syncwarp();
-        stage_step(s + PD - 1);
-        const float* sb = &stage[s % PD][0][0];
-        const float* sl = sb + PMAX;
-        const int d = is_beta ? nd - 1 - s : s;
-        // neighbour column's value of the previous step: lane - 1's last column (alpha) / lane + 1's first (beta)
-        double nb;
-        if (!is_beta) {
-            nb = shfl_up_f64(v[K - 1], lane > 0);
-            if (W > 1 && lane == 0 && warp > 0) nb = bnd[s & 1][warp];
-        } else {
-            nb = shfl_down_f64(v[0], lane < 31);
-            if (W > 1 && lane == 31 && warp < W - 1) nb = bnd[s & 1][warp + 1];
-        }
-        double nv[K];
+    for (int j = 0; j < K; ++j) v[j] = kLatNeg;
+    double* out = (is_beta ? beta_d : alpha_d) + base + u0;
+    for (int s0 = 0; s0 < nd; s0 += PD) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int u = u0 + j, t = d - u;
-            const bool on = u < U1 && t >= 0 && t < T;
-            double val = -INFINITY;
-            if (on) {
-                if (!is_beta) {
-                    const double left = (j > 0) ? v[j > 0 ? j - 1 : 0] : nb;
-                    const double from_t = (t > 0) ? v[j] + (double)sb[u] : -INFINITY;
-                    const double from_u = (u > 0) ? left + (double)sl[u > 0 ? u - 1 : 0] : -INFINITY;
-                    val = (d == 0) ? 0.0 : log_add(from_t, from_u);
-                } else {
-                    const double right = (j < K - 1) ? v[j < K - 1 ? j + 1 : j] : nb;
-                    const double from_t = (t < T - 1) ? v[j] + (double)sb[u] : -INFINITY;
-                    const double from_u = (u < U1 - 1) ? right + (double)sl[u] : -INFINITY;
-                    val = (d == nd - 1) ? (double)sb[u] : log_add(from_t, from_u);
-                }
-                out[(size_t)d * P + u] = val;
+        for (int i = 0; i < PD; ++i) {
+            const int s = s0 + i;                          // diagonal of this step; ring slot i
+            if (s >= nd) break;
+            if (W > 1 && lane == 31) bnd[i & 1][warp + 1] = v[K - 1];   // boundary column of the previous step
+            cp_async_wait<PD - 2>();                        // this step's diagonal has landed (own copies) ...
+            if (W > 1) __syncthreads();                     // ... everybody's, and the slot refilled below has been read
+            else __syncwarp();
+            stage_step(s + PD - 1, (i + PD - 1) % PD);
+            float sb[K], sl[K];
+            if (K == 2) {
+                const float2 b2 = *reinterpret_cast<const float2*>(&stage[i][0][u0]);
+                const float2 l2 = *reinterpret_cast<const float2*>(&stage[i][1][u0]);
+                sb[0] = b2.x; sb[K - 1] = b2.y; sl[0] = l2.x; sl[K - 1] = l2.y;
+            } else {
+                sb[0] = stage[i][0][u0];
+                sl[0] = stage[i][1][u0];
             }
-            nv[j] = val;
-        }
+            // left neighbour column's value of the previous step
+            const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v[K - 1]), 1);
+            const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v[K - 1]), 1);
+            double left = (lane > 0) ? __hiloint2double(hi, lo) : kLatNeg;
+            if (W > 1 && lane == 0 && warp > 0) left = bnd[i & 1][warp];
+            double nv[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) v[j] = nv[j];
+            for (int j = 0; j < K; ++j) {
+                const int u = u0 + j, t = s - u;
+                const bool on = u < U1 && t >= 0 && t < T;
+                const double from_t = v[j] + (double)(t > 0 ? sb[j] : 0.f);          // v = sentinel when there is no cell above
+                const double from_u = (j > 0 ? v[j > 0 ? j - 1 : 0] : left) + (double)(u > 0 ? sl[j] : 0.f);
+                double val = log_add(from_t, from_u);
+                if (s == 0) val = is_beta ? (double)sb[j] : 0.0;                      // x(0,0): beta starts from lp_blank(T-1,U)
+                val = on ? val : kLatNeg;
+                if (on) out[(size_t)s * P + j] = val;
+                nv[j] = val;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = nv[j];
+        }
     }
     cp_async_wait<0>();
-    // alpha ends in cell (T-1, U1-1) on diagonal nd - 1, beta in cell (0, 0) on diagonal 0
-    if (!is_beta) {
-        const int u = U1 - 1;
-        if (u >= u0 && u < u0 + K) {
-            double a = v[0];
-#pragma unroll
-            for (int j = 1; j < K; ++j) a = (u - u0 == j) ? v[j] : a;
-            costs[b] = (float)-(a + (double)__ldg(lpb_d + base + (size_t)(nd - 1) * P + u));
-        }
-    } else if (threadIdx.x == 0) {
-        ll_beta[b] = v[0];
+    // both lattices end in their last cell (T-1, U1-1), alone on diagonal nd - 1
+    const int j_last = U1 - 1 - u0;
+    if (j_last >= 0 && j_last < K) {
+        const double x = (K == 2 && j_last == 1) ? v[K - 1] : v[0];
+        if (is_beta) ll_beta[b] = x;                                                   // beta(0, 0)
+        else costs[b] = (float)-(x + (double)__ldg(ws + 2 * lat_elems + base));       // + lp_blank(T-1, U1-1)
     }
 }
 
@@ -459,14 +451,16 @@ __global__ void grad_prep_kernel(const float* __restrict__ lse, const float* __r
         const int t = r / U1, u = r - t * U1;
         const double ll = ll_beta[b];
         // alpha / beta are diagonal-major (see the lattice kernels): (t+1, u) and (t, u+1) sit on the next diagonal
+        // beta is stored on the mirrored lattice: (t+1, u) and (t, u+1) sit on its previous diagonal
         const int P = lat_pitch(U1);
-        const size_t li = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b] + (size_t)(t + u) * P + u;
-        const double be = beta[li];
-        const float gam = expf((float)(alpha[li] + be - ll));
+        const size_t l0 = (size_t)meta[kMetaHdr + B + 1 + meta[3] + b];
+        const size_t lb = l0 + (size_t)(T - 1 - t + U1 - 1 - u) * P + (U1 - 1 - u);
+        const double be = beta[lb];
+        const float gam = expf((float)(alpha[l0 + (size_t)(t + u) * P + u] + be - ll));
         float rb, rl = 0.f;
-        if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[li + P] - be));
+        if (t < T - 1) rb = expf((float)((double)lpb[base + r] + beta[lb - P] - be));
         else rb = (u == U1 - 1) ? 1.f : 0.f;
-        if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[li + P + 1] - be));
+        if (u < U1 - 1) rl = expf((float)((double)lpl[base + r] + beta[lb - P - 1] - be));
         const int lab = row_label[base + r];
         const float w = gam * grad_costs[b] / scal[2];
         float fb = expf(lpb[base + r]) - rb;
@@ -948,14 +942,14 @@ int launch_joint_act(const float* eproj, const float* pproj, const int* labels, 
 }
 
 template <int K, int PD, int W>
-static void lattice_launch(int B, cudaStream_t s, const float* lpb_d, const float* lpl_d, const int* act_lens,
+static void lattice_launch(int B, cudaStream_t s, const float* ws, size_t lat_elems, const int* act_lens,
                            const int* label_lens, const int* meta, double* alpha, double* beta, float* costs,
                            double* ll_beta) {
-    lattice_wave_kernel<K, PD, W><<<2 * B, 32 * W, 0, s>>>(lpb_d, lpl_d, act_lens, label_lens, meta, B, alpha, beta, costs,
+    lattice_wave_kernel<K, PD, W><<<2 * B, 32 * W, 0, s>>>(ws, lat_elems, act_lens, label_lens, meta, B, alpha, beta, costs,
                                                           ll_beta);
 }
 
-// lat_ws: 2 * lat_elems floats (the skewed copies of lp_blank / lp_label); alpha / beta: lat_elems doubles each
+// lat_ws: 4 * lat_elems floats (the arc log-probs in diagonal-major order); alpha / beta: lat_elems doubles each
 int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, const int* label_lens, const int* meta,
                    int B, int U1, int n_tiles_ub, size_t lat_elems, float* lat_ws, double* alpha, double* beta,
                    float* costs, double* ll_beta, cudaStream_t s) {
@@ -963,16 +957,14 @@ int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, cons
         set_error("lattice kernel supports at most 1023 labels per utterance (got U+1 = %d)", U1);
         return 1;
     }
-    float* lpb_d = lat_ws;
-    float* lpl_d = lat_ws + lat_elems;
-    lattice_skew_kernel<<<n_tiles_ub, kTile, 0, s>>>(lpb, lpl, act_lens, label_lens, meta, B, lpb_d, lpl_d);
-#define TTX_LAT(K, PD, W) lattice_launch<K, PD, W>(B, s, lpb_d, lpl_d, act_lens, label_lens, meta, alpha, beta, costs, ll_beta)
+    lattice_skew_kernel<<<n_tiles_ub, kTile, 0, s>>>(lpb, lpl, act_lens, label_lens, meta, B, lat_elems, lat_ws);
+#define TTX_LAT(K, PD, W) lattice_launch<K, PD, W>(B, s, lat_ws, lat_elems, act_lens, label_lens, meta, alpha, beta, costs, ll_beta)
     if (U1 <= 32) TTX_LAT(1, 8, 1);
     else if (U1 <= 64) TTX_LAT(2, 8, 1);
-    else if (U1 <= 128) TTX_LAT(4, 8, 1);
-    else if (U1 <= 256) TTX_LAT(8, 8, 1);
-    else if (U1 <= 512) TTX_LAT(8, 4, 2);
-    else TTX_LAT(8, 4, 4);
+    else if (U1 <= 128) TTX_LAT(2, 8, 2);
+    else if (U1 <= 256) TTX_LAT(2, 8, 4);
+    else if (U1 <= 512) TTX_LAT(2, 8, 8);
+    else TTX_LAT(2, 4, 16);
 #undef TTX_LAT
     TTX_CUDA_OK(cudaGetLastError());
     return 0;

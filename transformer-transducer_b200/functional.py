@@ -77,7 +77,7 @@ class _Plan:
     def lattice(self, lse, lpb, lpl):
         alpha = torch.empty(self.lat, dtype=torch.float64, device=self.dev)
         beta = torch.empty(self.lat, dtype=torch.float64, device=self.dev)
-        lat_ws = torch.empty(2 * self.lat, dtype=torch.float32, device=self.dev)
+        lat_ws = torch.empty(4 * self.lat, dtype=torch.float32, device=self.dev)
         costs = torch.full((self.B,), float("nan"), dtype=torch.float32, device=self.dev)   # stays NaN on bad lengths
         ll_beta = torch.empty(self.B, dtype=torch.float64, device=self.dev)
         _call("ttx_lattice_fwd_bwd", self.dev, _p(lpb), _p(lpl), _p(self.act_lens), _p(self.label_lens),
