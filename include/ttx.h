@@ -174,6 +174,37 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
                            const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
                            int H, float* d_eproj, float* d_pproj, int device, void* stream);
 
+/* ---- Wide joints (H a multiple of 512 up to 4096: aishell.yaml's 1024, joint_streaming.yaml's 2048; tt/model.py:35-37).
+ * The same three contractions as three streamed tcgen05 products around the 16-bit softmax numerators P' (layout as
+ * pstore above: [Vpad / 64][store_rows][64]).  Every call works on lattice tiles [tile_lo, tile_lo + tile_cnt) (tile_lo
+ * even; clipped on the device to the tiles in use) and addresses the P' matrix relative to tile_lo: a caller that can
+ * hold P' for the whole batch passes (0, n_tiles_ub) and keeps it for the backward; otherwise it walks the batch in
+ * chunks with one chunk-sized matrix and calls ttx_wide_sp again in the backward.
+ *   ttx_wide_sp   S = A16 . W16^T with both operands streamed; lse / log p(blank) / log p(label) per row, P', pfac
+ *                 (softmax = P' * pfac) and mref (the row's reference, scratch).  flags: one int32 per tile pair of the
+ *                 batch, zeroed by the caller; rows whose reference had to move are recomputed by a second launch, so
+ *                 P' is always consistent on return.
+ *   ttx_wide_pw   ew (rows, H) fp32 = P' . W16 * pfac / w_scale  (as ttx_joint_fwd_grad's ew)
+ *   ttx_wide_dw   d_w_out += P'^T . As, d_b_out += dense part, As = a16st from ttx_kept_prepare.
+ *   ttx_kept_prepare  a16st = scaled A16^T ((H + 16) x rows_ub 16-bit values + 64 x (H + 4) floats), and the exact
+ *                 blank / label terms of d_w_out / d_b_out (pflags: 16384 zero words). */
+int ttx_wide_supported_h(int H);
+int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
+                const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
+                float* lse, float* lp_blank, float* lp_label, float* pfac, float* mref, void* pstore, int64_t store_rows,
+                int32_t* flags, int device, void* stream);
+int ttx_wide_pw(const void* pstore, int64_t store_rows, const void* w16t, const float* pfac, const float* scal,
+                const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* ew,
+                int device, void* stream);
+int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const float* scal, const int32_t* meta,
+                int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* d_w_out, float* d_b_out,
+                int device, void* stream);
+int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
+                     const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
+                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, const int32_t* pflags, int B,
+                     int T, int U1, int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out,
+                     float* d_b_out, int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

@@ -265,14 +265,8 @@ def test_fused_tt_jointnet_split_first_layer_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
-@pytest.mark.parametrize("H,V", [(1024, 4232), (2048, 700), (2048, 6485)])
-def test_wide_joint_chunked_path_matches_oracle(H, V, monkeypatch):
-    """aishell.yaml (H=1024) / joint_streaming.yaml (H=2048) joint widths: lazy handle + chunked path (library GEMM on
-    the 16-bit operands + our row kernels), several chunks, ragged lengths."""
-    from transformer_transducer_b200 import functional as Fn
-    monkeypatch.setattr(Fn.ChunkedJointRNNT, "CHUNK_BYTES", 3 * 128 * ((V + 255) // 256 * 256) * 4)   # 3 tiles / chunk
+def _tt_wide_case(H, V, B=3, T=40, U=9, D=64):
     torch.manual_seed(H)
-    B, T, U, D = 3, 40, 9, 64
     ref = joint_ref.TTJointNet(2 * D, H, V)
     mine = ttb.JointNet(2 * D, H, V)
     mine.load_state_dict(ref.state_dict())
@@ -282,19 +276,52 @@ def test_wide_joint_chunked_path_matches_oracle(H, V, monkeypatch):
     al, ll = _i32([T, T - 9, 7]), _i32([U, U - 4, 0])
     labels[1, U - 4:] = -1
     labels[2, :] = -1
+    wts = torch.tensor([1.0, 2.0, 0.5])
     e0, d0 = enc.clone().requires_grad_(), dec.clone().requires_grad_()
     want = rnnt_oracle.rnnt_loss(ref(e0, d0), labels, al, ll, 0, "none")
-    (want * torch.tensor([1.0, 2.0, 0.5])).sum().backward()
+    (want * wts).sum().backward()
     e1, d1 = enc.to(DEV).requires_grad_(), dec.to(DEV).requires_grad_()
     z = mine(e1, d1)
     assert isinstance(z, ttb.LazyJointLogits)
     got = ttb.rnnt_loss(z, labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")
-    (got * torch.tensor([1.0, 2.0, 0.5], device=DEV)).sum().backward()
+    (got * wts.to(DEV)).sum().backward()
     assert float(((got.cpu() - want.detach()) / want.detach()).abs().max()) < LOSS_TOL
     assert rel(e1.grad, e0.grad) < GRAD_TOL and rel(d1.grad, d0.grad) < GRAD_TOL
     for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
-        assert rel(a.grad, b.grad) < GRAD_TOL, n
+        assert rel(a.grad, b.grad) < GRAD_TOL, (n, rel(a.grad, b.grad))
     assert e1.grad[2, 7:].abs().max() == 0 and d1.grad[2, 1:].abs().max() == 0
+
+
+@pytest.mark.parametrize("H,V,keep", [(1024, 4232, "32"), (2048, 700, "32"), (2048, 6485, "32"), (1024, 4232, "1e-9"),
+                                      (2048, 6485, "1e-9"), (1536, 900, "32")])
+def test_wide_joint_tcgen05_path_matches_oracle(H, V, keep, monkeypatch):
+    """aishell.yaml (H=1024, V=4232) / joint_streaming.yaml (H=2048, V=6485) joint widths through the tt JointNet: lazy
+    handle + the three streamed tcgen05 products of csrc/ttx_wide.cu, ragged lengths.  keep = "32": P' for the whole
+    batch, kept for the backward; keep = "1e-9": a budget of one tile pair -- several chunks, and the backward recomputes
+    each chunk's P'."""
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setenv("TTX_KEEP_GB", keep)
+    calls = []
+    orig = Fn.WideJointRNNT.apply
+    monkeypatch.setattr(Fn.WideJointRNNT, "apply", lambda *a: (calls.append(1), orig(*a))[1])
+    _tt_wide_case(H, V)
+    assert calls, "the wide tcgen05 path did not run"
+
+
+def test_wide_path_at_h512_matches_oracle(monkeypatch):
+    """The streamed products are a second implementation of H = 512 (TTX_WIDE=1): same tolerance as the fused kernel."""
+    monkeypatch.setenv("TTX_WIDE", "1")
+    case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)
+    errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))
+    _check(errs)
+
+
+def test_odd_wide_width_takes_library_gemm_fallback_and_matches_oracle(monkeypatch):
+    """A multiple of 64 that is neither a fused width nor a multiple of 512 (768): the chunked fallback (library GEMM on
+    the 16-bit operands + our row kernels), several chunks."""
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setattr(Fn.ChunkedJointRNNT, "CHUNK_BYTES", 3 * 128 * 1024 * 4)   # 3 tiles / chunk
+    _tt_wide_case(768, 900)
 
 
 def test_unsupported_width_uses_dense_entry_and_matches_oracle():

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libttx.so")
-SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu"]
+SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -49,6 +49,12 @@ _PROTOS = {
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_p],
     "ttx_reduce_act_grad_ew": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
                                c_p, c_p, c_i32, c_p],
+    "ttx_wide_supported_h": [c_i32],
+    "ttx_wide_sp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p,
+                    c_p, c_i64, c_p, c_i32, c_p],
+    "ttx_wide_pw": [c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
+    "ttx_wide_dw": [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
+    "ttx_kept_prepare": [c_p] * 12 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_grad": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p,

@@ -56,6 +56,14 @@ int launch_joint_bwd(const void*, const void*, const void*, const void*, uint64_
                      const int*, const float*, const float*, const int*, int, const float4*, float*, float*, float*,
                      int, cudaStream_t, const int*);
 
+bool wide_supported_h(int H);
+int launch_wide_sp(const void*, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*, const float*,
+                   const int*, int, float*, float*, float*, float*, float*, void*, uint64_t, int*, cudaStream_t);
+int launch_wide_pw(const void*, uint64_t, const void*, int, int, int, int, int, bool, const int*, const float*, const float*,
+                   float*, cudaStream_t);
+int launch_wide_dw(const void*, uint64_t, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*,
+                   float*, float*, cudaStream_t);
+
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -284,6 +292,75 @@ int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float*
     return launch_joint_bwd(a16, w16, a16t, w16t, rows, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta, bias2, scal,
                             row_label, blank, (const float4*)rowmeta, nullptr, d_w_out, d_b_out, 1, s,
                             pflags + kKeptAnyDirty);
+}
+
+int ttx_wide_supported_h(int H) { return wide_supported_h(H) ? 1 : 0; }
+
+static int wide_range_ok(const char* who, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int64_t store_rows) {
+    if (tile_lo < 0 || (tile_lo & 1) || tile_cnt < 1 || tile_lo + (int64_t)tile_cnt > n_tiles_ub + 1 ||
+        store_rows < (int64_t)kTile * ((tile_cnt + 1) & ~1) || store_rows % kTile != 0) {
+        set_error("%s: bad tile range [%d, +%d) of %lld tiles / P' matrix of %lld rows (tile_lo must be even, the matrix "
+                  "must hold the range rounded up to a tile pair)", who, tile_lo, tile_cnt, (long long)n_tiles_ub,
+                  (long long)store_rows);
+        return 1;
+    }
+    return 0;
+}
+
+int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
+                const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
+                float* lse, float* lp_blank, float* lp_label, float* pfac, float* mref, void* pstore, int64_t store_rows,
+                int32_t* flags, int device, void* stream) {
+    TTX_REQUIRE(a16 && w16 && bias2 && scal && row_label && meta && lse && lp_blank && lp_label && pfac && mref && pstore &&
+                    flags, "ttx_wide_sp: null pointer");
+    TTX_REQUIRE(wide_supported_h(H), "ttx_wide_sp: joint width H=%d is not supported (multiples of 512 up to 4096)", H);
+    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_wide_sp: bad V=%d / blank=%d", V, blank);
+    if (int rc = wide_range_ok("ttx_wide_sp", n_tiles_ub, tile_lo, tile_cnt, store_rows)) return rc;
+    TTX_ENTER(device);
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
+    return launch_wide_sp(a16, w16, (uint64_t)n_tiles_ub * kTile, tile_lo, tile_cnt, H, V, Vpad, bf16 != 0, meta, bias2, scal,
+                          row_label, blank, lse, lp_blank, lp_label, pfac, mref, pstore, (uint64_t)store_rows, flags,
+                          (cudaStream_t)stream);
+}
+
+int ttx_wide_pw(const void* pstore, int64_t store_rows, const void* w16t, const float* pfac, const float* scal,
+                const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* ew,
+                int device, void* stream) {
+    TTX_REQUIRE(pstore && w16t && pfac && scal && meta && ew, "ttx_wide_pw: null pointer");
+    TTX_REQUIRE(wide_supported_h(H), "ttx_wide_pw: joint width H=%d is not supported (multiples of 512 up to 4096)", H);
+    TTX_REQUIRE(V > 0, "ttx_wide_pw: bad V=%d", V);
+    if (int rc = wide_range_ok("ttx_wide_pw", n_tiles_ub, tile_lo, tile_cnt, store_rows)) return rc;
+    TTX_ENTER(device);
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
+    return launch_wide_pw(pstore, (uint64_t)store_rows, w16t, tile_lo, tile_cnt, H, V, Vpad, bf16 != 0, meta, scal, pfac, ew,
+                          (cudaStream_t)stream);
+}
+
+int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const float* scal, const int32_t* meta,
+                int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* d_w_out, float* d_b_out,
+                int device, void* stream) {
+    TTX_REQUIRE(pstore && a16st && scal && meta && d_w_out && d_b_out, "ttx_wide_dw: null pointer");
+    TTX_REQUIRE(wide_supported_h(H), "ttx_wide_dw: joint width H=%d is not supported (multiples of 512 up to 4096)", H);
+    TTX_REQUIRE(V > 0, "ttx_wide_dw: bad V=%d", V);
+    if (int rc = wide_range_ok("ttx_wide_dw", n_tiles_ub, tile_lo, tile_cnt, store_rows)) return rc;
+    TTX_ENTER(device);
+    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
+    return launch_wide_dw(pstore, (uint64_t)store_rows, a16st, (uint64_t)n_tiles_ub * kTile, tile_lo, tile_cnt, H, V, Vpad,
+                          bf16 != 0, meta, scal, d_w_out, d_b_out, (cudaStream_t)stream);
+}
+
+int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
+                     const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
+                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, const int32_t* pflags, int B,
+                     int T, int U1, int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out,
+                     float* d_b_out, int device, void* stream) {
+    TTX_REQUIRE(a16 && a16t && rowmeta && row_label && lp_blank && lp_label && pfac && scal && act_lens && label_lens &&
+                    meta && pflags && a16st && d_w_out && d_b_out, "ttx_kept_prepare: null pointer");
+    TTX_REQUIRE(H > 0 && H % 64 == 0 && B > 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_kept_prepare: bad shape");
+    TTX_ENTER(device);
+    return launch_kept_prepare(a16, a16t, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal, act_lens,
+                               label_lens, meta, pflags, B, T, U1, H, blank, bf16 != 0, (size_t)n_tiles_ub * kTile, a16st,
+                               d_w_out, d_b_out, true, (cudaStream_t)stream);
 }
 
 int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,

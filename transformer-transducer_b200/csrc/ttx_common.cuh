@@ -116,6 +116,19 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Position in a ring of `ns` pipeline stages; `phase` = parity of the ring's wrap count (mbarrier phase bit).
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int ns, int n = 1) {
+        stage += n;
+        if (stage >= ns) {
+            stage -= ns;
+            phase ^= 1;
+        }
+    }
+};
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -59,18 +59,6 @@ constexpr int kPB = 2;                             // pair kernel: P' sub-tile b
 constexpr int kEpiBarrier = 1;                     // named barrier id for the epilogue warps
 constexpr int kMaxStages = 16;
 
-struct Ring {
-    int stage = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance(int ns, int n = 1) {
-        stage += n;
-        if (stage >= ns) {
-            stage -= ns;
-            phase ^= 1;
-        }
-    }
-};
-
 // Position in the pair kernel's ring of P' sub-tile buffers: sub-pass n uses buffer n % kPB; `phase` = parity of its
 // use count n / kPB.  The MMA issuer and every epilogue thread step through the sub-passes in the same order.
 struct PRing {

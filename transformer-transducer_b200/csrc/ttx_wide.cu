@@ -1,0 +1,782 @@
+// Joint widths beyond one shared-memory tile (aishell.yaml's inner_size 1024, joint_streaming.yaml's 2048;
+// /root/reference/tt/model.py:35-37 with config/aishell.yaml:42-45, config/joint_streaming.yaml:42-45): the same three
+// contractions as ttx_joint_mma.cu, on tcgen05 tensor cores, organised as three plain streamed products around the
+// 16-bit softmax numerators P' = 2^(y - mref) (y = logit in log2 units):
+//
+//   sp_kernel      S = A16 . W16^T, BOTH operands streamed in 64-column K chunks (no stationary tile: 128 rows x H no longer
+//                  fit shared memory), two 256-column S accumulators in TMEM so that the exponential epilogue of chunk j
+//                  overlaps the MMAs of chunk j + 1.  Epilogue: online log-sum-exp statistics (lse, log p(blank), log p(label))
+//                  + P' written straight from registers to the blocked P' matrix, [Vpad / 64][rows][64].
+//   kp_kernel<PW>  EW = P' . W16 for a 512-column block of H (two 256-column slabs = all of TMEM), K = vocabulary.
+//   kp_kernel<DW>  dW_out += P'^T . As for a 512-column block of H, K = lattice rows; As = scaled A16^T (ttx_small.cu).
+//
+// P' rows are stored against a per-row reference mref fixed by the first vocabulary chunk; a row whose later logits
+// would overflow the 16-bit range moves its reference (rare, see the range plan in ttx_joint_mma.cu) and flags its tile
+// pair, and a second launch of sp_kernel (redo mode, same grid, skips every unflagged pair on the device) recomputes
+// the flagged pairs against the FINAL reference -- so the matrix the two products read is always consistent and there is
+// no whole-batch fallback.
+#include "ttx_common.cuh"
+
+namespace ttx {
+
+int make_tile_map(CUtensorMap* map, const void* base, uint64_t rows, int H, bool bf16, int box_rows);
+int make_matrix_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, bool bf16, int box_rows);
+
+struct WideParams {
+    int H, NKC;              // joint width, H / 64
+    int V, n_vchunks;        // vocabulary size, 256-column chunks of it
+    int n_k64;               // Vpad / 64
+    int blank;
+    int NS;                  // sp: ring stages (32 KiB each)
+    int tile_lo, tile_cnt;   // lattice tiles [tile_lo, tile_lo + tile_cnt) (clipped to the tiles in use); tile_lo even
+    int store_rows;          // rows of the P' matrix; its row 0 is lattice row tile_lo * 128
+    int redo;                // sp: only tile pairs whose flag is set, against the stored final reference
+    int n_hb;                // kp: 512-column blocks of H
+    int splits;              // kp<DW>: lattice-row splits
+    const int* meta;
+    const float* bias2;
+    const float* scal;
+    const int* row_label;
+    float* lse;
+    float* lpb;
+    float* lpl;
+    float* pfac;             // softmax(row, v) = P'(row, v) * pfac[row]
+    float* mref;             // the row's final reference (log2 units)
+    uint16_t* pstore;
+    int* flags;              // one word per tile pair of the whole batch
+    float* ew;               // kp<PW> out (rows x H)
+    float* dW;               // kp<DW> out (V x H), red.add
+    float* db;               // kp<DW> out (V)
+};
+
+constexpr int kWEpiWarps = 8;
+constexpr int kWEpiThreads = kWEpiWarps * 32;
+constexpr int kWThreads = kWEpiThreads + 128;          // + control warpgroup: producer, MMA issuer, watcher, idle
+constexpr int kWProducerWarp = kWEpiWarps, kWMmaWarp = kWEpiWarps + 1, kWWatchWarp = kWEpiWarps + 2;
+constexpr int kWCtrlRegs = 72, kWEpiRegs = 216;        // 12 warps x 168 = 4 x 72 + 8 x 216
+constexpr int kSpStage = 2 * kChunkBytes;              // A chunk + W chunk
+constexpr int kSpMaxStages = 6;
+
+__device__ __forceinline__ void w_epi_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kWEpiThreads) : "memory");
+}
+__device__ __forceinline__ void w_quarter_sync(int q) {
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(kWEpiThreads / 4) : "memory");
+}
+__device__ __forceinline__ bool w_quarter_any(int q, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred pin, pout;\n\t"
+        "setp.ne.b32 pin, %2, 0;\n\t"
+        "bar.red.or.pred pout, %1, %3, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t}"
+        : "=r"(r)
+        : "r"(2 + q), "r"((uint32_t)pred), "n"(kWEpiThreads / 4)
+        : "memory");
+    return r != 0;
+}
+
+// The issuing thread's view of the barrier watcher's event counter (see ttx_joint_mma.cu: an mbarrier try_wait costs
+// ~90 cycles, a tcgen05.mma must be issued every ~128).
+struct EventWait {
+    volatile int* ready;
+    int need = 0, have = 0;
+    __device__ __forceinline__ void wait() {
+        ++need;
+        if (have < need) {
+            uint32_t spins = 0;
+            while ((have = *ready) < need) {
+                if (++spins > (1u << 26)) {
+                    printf("ttx: MMA issuer timed out waiting for event %d (block %d)\n", need, blockIdx.x);
+                    __trap();
+                }
+            }
+        }
+    }
+};
+
+// =========================================================================================================== S pass
+template <bool BF16>
+__global__ void __launch_bounds__(kWThreads, 1)
+sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, const WideParams p) {
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int n_tiles = p.meta[0];
+    const int n_range = min(n_tiles, p.tile_lo + p.tile_cnt) - p.tile_lo;
+    const int n_units = (n_range + 1) >> 1;
+    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+    if (unit0 >= n_units) return;
+    auto skip_unit = [&](int unit) { return p.redo && p.flags[(p.tile_lo >> 1) + unit] == 0; };
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) {
+        if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
+        __trap();
+    }
+    const uint32_t sRing = smem_base;
+    const uint32_t sBar = sRing + p.NS * kSpStage;
+    const uint32_t sTmemPtr = sBar + 32 * 8;
+    const uint32_t sWatch = sTmemPtr + 8;
+    const uint32_t sXg = sTmemPtr + 16;                    // [2][128] floats: row maxima of the two column halves
+    const uint32_t sXch = sXg + 2 * kTile * 4;             // [2][128] float4: per-row statistics of the two halves
+    uint8_t* smem_gen = smem_raw;
+    auto bar_full = [&](int s) { return sBar + 8 * s; };
+    auto bar_empty = [&](int s) { return sBar + 8 * (8 + s); };
+    auto bar_sfull = [&](int b) { return sBar + 8 * (16 + b); };
+    auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == kWProducerWarp && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapY);
+        for (int s = 0; s < p.NS; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_sfull(b), 1);
+            mbar_init(bar_sempty(b), 2 * kWEpiWarps);      // every epilogue warp of both CTAs
+        }
+        *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
+        fence_barrier_init();
+    }
+    if (warp == kWMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
+
+    if (warp >= kWEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWCtrlRegs));
+        if (warp == kWProducerWarp && lane == 0) {
+            // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
+            Ring r;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (skip_unit(unit)) continue;
+                const int x_row0 = (p.tile_lo + unit * 2 + (int)rank) * kTile;
+                for (int j = 0; j < p.n_vchunks; ++j)
+                    for (int c = 0; c < p.NKC; ++c) {
+                        mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                        if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * kSpStage);
+                        const uint32_t dst = sRing + r.stage * kSpStage;
+                        tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
+                        tma_load_2d_pair(dst + kChunkBytes, &mapY, bar_full(r.stage), c * kKC, j * 256 + (int)rank * kTile);
+                        r.advance(p.NS);
+                    }
+            }
+        } else if (warp == kWWatchWarp && lane == 0 && leader) {
+            // =================================================== barrier watcher: the issuer's barriers, in its order
+            volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+            int done = 0, g = 0;
+            Ring r;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (skip_unit(unit)) continue;
+                for (int j = 0; j < p.n_vchunks; ++j, ++g) {
+                    mbar_wait(bar_sempty(g & 1), ((g >> 1) & 1) ^ 1);
+                    *ready = ++done;
+                    for (int c = 0; c < p.NKC; ++c) {
+                        mbar_wait(bar_full(r.stage), r.phase);
+                        *ready = ++done;
+                        r.advance(p.NS);
+                    }
+                }
+            }
+        } else if (warp == kWMmaWarp && lane == 0 && leader) {
+            // =================================================== MMA issuer
+            const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
+            const uint32_t rlo = desc_lo(sRing);
+            EventWait ev{reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base))};
+            int stage = 0, g = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (skip_unit(unit)) continue;
+                for (int j = 0; j < p.n_vchunks; ++j, ++g) {
+                    ev.wait();                              // the epilogue has read this accumulator's previous tile
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (g & 1) * 256;
+                    for (int c = 0; c < p.NKC; ++c) {
+                        ev.wait();                          // ring stage has landed
+                        tc_fence_after();
+                        const uint32_t a = rlo + stage * (kSpStage >> 4), b = a + (kChunkBytes >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
+                        umma_commit_pair(bar_empty(stage));
+                        if (++stage == p.NS) stage = 0;
+                    }
+                    umma_commit_pair(bar_sfull(g & 1));
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWEpiRegs));
+        // ======================================================= epilogue: thread = (row, column half ch of the S tile)
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const float inv_ws = p.scal[1];
+        const float c1 = inv_ws * kLog2e;
+        const float lg_scale = BF16 ? 0.0f : 12.0f;
+        const float ref_exp = BF16 ? -2.f : 2.f;           // range plan of P': see ttx_joint_mma.cu (MODE_FG)
+        const float ref_limit = BF16 ? 100.f : 15.f;
+        float* xg = reinterpret_cast<float*>(smem_gen + (sXg - smem_base));
+        float4* xch = reinterpret_cast<float4*>(smem_gen + (sXch - smem_base));
+        auto epi_arrive = [&](uint32_t bar) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar, 0);
+        };
+        int g = 0;
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+            if (skip_unit(unit)) continue;
+            const int tile = p.tile_lo + unit * 2 + (int)rank;
+            const bool valid_x = tile < n_tiles;
+            const int grow = tile * kTile + row;
+            const size_t srow = (size_t)(grow - p.tile_lo * kTile);
+            const int label = valid_x ? p.row_label[grow] : -1;
+            float mref = (p.redo && valid_x) ? p.mref[grow] : 0.f;
+            float ssum = 0.f, zb = 0.f, zl = 0.f;
+            for (int j = 0; j < p.n_vchunks; ++j, ++g) {
+                const int t0 = j * 256 + ch * 128;          // first vocabulary id of this thread's 128 columns
+                const float* bias_t = p.bias2 + t0;
+                mbar_wait(bar_sfull(g & 1), (g >> 1) & 1);
+                tc_fence_after();
+                uint32_t acc[4][32];
+#pragma unroll
+                for (int gg = 0; gg < 4; ++gg) tmem_ld32(tmem_base + lane_addr + (g & 1) * 256 + ch * 128 + gg * 32, acc[gg]);
+                tmem_ld_wait();
+                tc_fence_before();
+                epi_arrive(bar_sempty(g & 1));
+                float lmax = -INFINITY, part = 0.f;
+                // logits of this thread's columns in log2 units (+ lg_scale); blank / label logits picked on the way
+#pragma unroll
+                for (int gg = 0; gg < 4; ++gg) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + gg * 32) + e);
+                        const float y0 = fmaf(__uint_as_float(acc[gg][4 * e + 0]), c1, bv.x + lg_scale);
+                        const float y1 = fmaf(__uint_as_float(acc[gg][4 * e + 1]), c1, bv.y + lg_scale);
+                        const float y2 = fmaf(__uint_as_float(acc[gg][4 * e + 2]), c1, bv.z + lg_scale);
+                        const float y3 = fmaf(__uint_as_float(acc[gg][4 * e + 3]), c1, bv.w + lg_scale);
+                        lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                        acc[gg][4 * e + 0] = __float_as_uint(y0); acc[gg][4 * e + 1] = __float_as_uint(y1);
+                        acc[gg][4 * e + 2] = __float_as_uint(y2); acc[gg][4 * e + 3] = __float_as_uint(y3);
+                    }
+                    const int cbl = p.blank - (t0 + gg * 32), clb = label - (t0 + gg * 32);
+                    if (cbl >= 0 && cbl < 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zb = (e == cbl) ? __uint_as_float(acc[gg][e]) - lg_scale : zb;
+                    }
+                    if (clb >= 0 && clb < 32) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) zl = (e == clb) ? __uint_as_float(acc[gg][e]) - lg_scale : zl;
+                    }
+                }
+                // reference: fixed by the row maximum of the first chunk (both halves); later chunks vote and only move
+                // it when a value would leave the 16-bit range (then the tile pair is flagged for the redo launch)
+                bool move = false;
+                if (j == 0 && !p.redo) {
+                    move = true;
+                } else {
+                    move = w_quarter_any(q, lmax - mref > ref_limit);
+                    if (move && !p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;
+                }
+                if (move) {
+                    xg[ch * kTile + row] = lmax;
+                    w_quarter_sync(q);
+                    const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                    w_quarter_sync(q);                       // xg may be rewritten
+                    if (j == 0) {
+                        mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
+                    } else if (rmax - mref > ref_limit) {
+                        const float nref = rmax - ref_exp;
+                        ssum *= ex2f(mref - nref);
+                        mref = nref;
+                    }
+                }
+                uint32_t packed[4][16];
+                {
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float e0 = ex2f(__uint_as_float(acc[gg][e]) - mref), e1 = ex2f(__uint_as_float(acc[gg][e + 1]) - mref);
+                            const float e2 = ex2f(__uint_as_float(acc[gg][e + 2]) - mref), e3 = ex2f(__uint_as_float(acc[gg][e + 3]) - mref);
+                            p0 += e0; p1 += e1; p2 += e2; p3 += e3;
+                            packed[gg][e >> 1] = pack16<BF16>(e0, e1);
+                            packed[gg][(e >> 1) + 1] = pack16<BF16>(e2, e3);
+                        }
+                    }
+                    part = (p0 + p1) + (p2 + p3);
+                }
+                ssum += part;
+                // P' -> the blocked matrix [Vpad / 64][store_rows][64]: this thread's 128 columns = two 128-byte runs
+                {
+                    uint16_t* dst0 = p.pstore + ((size_t)(j * 4 + ch * 2) * p.store_rows + srow) * 64;
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst0 + (size_t)(gg >> 1) * p.store_rows * 64 + (gg & 1) * 32);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            d4[c] = make_uint4(packed[gg][4 * c], packed[gg][4 * c + 1], packed[gg][4 * c + 2], packed[gg][4 * c + 3]);
+                    }
+                    // the blank and label columns are left out of P' (their exact terms are added in fp32 later)
+                    const int cbl = p.blank - t0, clb = label - t0;
+                    if (cbl >= 0 && cbl < 128) dst0[(size_t)(cbl >> 6) * p.store_rows * 64 + (cbl & 63)] = 0;
+                    if (clb >= 0 && clb < 128) dst0[(size_t)(clb >> 6) * p.store_rows * 64 + (clb & 63)] = 0;
+                }
+            }
+            // combine the two column halves of each row
+            w_epi_sync();
+            xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
+            w_epi_sync();
+            const float4 o = xch[(ch ^ 1) * kTile + row];
+            w_epi_sync();
+            if (ch == 0 && valid_x) {
+                const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
+                zb = ((p.blank & 255) < 128) ? zb : o.y;     // which column half owns the blank / label column
+                if (label >= 0) zl = ((label & 255) < 128) ? zl : o.z;
+                p.lse[grow] = lse2 * kLn2;
+                p.lpb[grow] = (zb - lse2) * kLn2;
+                p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
+                p.pfac[grow] = ex2f(mref - lg_scale - lse2);
+                p.mref[grow] = mref;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kWMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =========================================================================================================== kept products
+// One product with all 512 TMEM columns as accumulator (two 256-column slabs of the H block), no S pass, no exponentials.
+// Per 64 elements of K the ring takes a GROUP of three 16 KiB stages: the A operand and the two slabs' B operands; eight
+// MMAs (four k slices x two slabs) per group.
+//   PW: rows = lattice rows (pair: two 128-row tiles), K = vocabulary.  A = P' box [128 rows x 64 v] (K-major),
+//       B = W16^T boxes [128 h x 64 v].  Out: EW = G * pfac / w_scale.
+//   DW: rows = vocabulary (pair: two 128-row vocabulary tiles), K = lattice rows.  A = P'^T, read MN-major straight from
+//       the row-major P' blocks (two [64 m x 64 v] boxes), B = scaled A16^T boxes [128 h x 64 m]; + the 16 scale rows
+//       appended to every 64-row block of As^T (H block 0 only), from which the idle epilogue warps form the dense part
+//       of db out of the P' stage in shared memory.  Out: red.add into dW.
+enum { KP_PW = 0, KP_DW = 1 };
+constexpr int kKG = 3;                                  // stages per group = groups in flight
+
+template <int MODE, bool BF16>
+__global__ void __launch_bounds__(kWThreads, 1)
+kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapB,
+          const __grid_constant__ CUtensorMap mapS, const WideParams p) {
+    constexpr int STAGE = kChunkBytes;
+    constexpr int NRING = kKG * kKG;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int n_tiles = p.meta[0];
+    const int n_range = min(n_tiles, p.tile_lo + p.tile_cnt) - p.tile_lo;
+    const int n_tp = (n_range + 1) >> 1;                 // lattice tile pairs in range
+    const int n_vq = ((p.V + kTile - 1) / kTile + 1) / 2;
+    const int per = (MODE == KP_DW) ? (n_tp + p.splits - 1) / p.splits : 0;
+    const int n_units = (MODE == KP_DW) ? n_vq * p.n_hb * p.splits : n_tp * p.n_hb;
+    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+    if (unit0 >= n_units || n_range <= 0) return;
+    // unit -> (row tile pair of the output, H block, K range in 64-element groups)
+    int hb = 0, rt = 0, k_lo = 0, k_n = 0;
+    auto begin_unit = [&](int unit) {
+        hb = unit % p.n_hb;
+        const int rest = unit / p.n_hb;
+        if (MODE == KP_DW) {
+            rt = rest % n_vq;
+            const int j0 = (rest / n_vq) * per;
+            k_lo = j0 * 4;                               // 64-row groups: four per tile pair
+            k_n = (min(n_tp, j0 + per) - j0) * 4;
+        } else {
+            rt = rest;
+            k_lo = 0;
+            k_n = p.n_k64;
+        }
+        return k_n > 0;
+    };
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) {
+        if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
+        __trap();
+    }
+    const uint32_t sX = smem_base;                                   // NRING stages
+    const uint32_t sScale = sX + NRING * STAGE;                      // DW: kKG x [8 x 64] 16-bit scale rows
+    const uint32_t sBar = sScale + kKG * 1024;
+    const uint32_t sTmemPtr = sBar + 32 * 8;
+    const uint32_t sWatch = sTmemPtr + 8;
+    uint8_t* smem_gen = smem_raw;
+    auto bar_full = [&](int s) { return sBar + 8 * s; };
+    auto bar_empty = [&](int s) { return sBar + 8 * (NRING + s); };
+    auto bar_cons = [&](int g) { return sBar + 8 * (2 * NRING + g); };
+    const uint32_t bar_gfull = sBar + 8 * (2 * NRING + kKG);
+    const uint32_t bar_gempty = bar_gfull + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == kWProducerWarp && lane == 0) {
+        tma_prefetch_desc(&mapP);
+        tma_prefetch_desc(&mapB);
+        tma_prefetch_desc(&mapS);
+        for (int s = 0; s < NRING; ++s) {
+            mbar_init(bar_full(s), 1);
+            // DW: the P' stage and the first As^T stage of a group are released by this CTA's epilogue warps (which read
+            // them after the MMAs, see bar_cons); everything else by the MMAs' commit
+            const bool epi_released = MODE == KP_DW && s % kKG != kKG - 1;
+            mbar_init(bar_empty(s), epi_released ? kWEpiWarps : 1);
+        }
+        for (int g = 0; g < kKG; ++g) mbar_init(bar_cons(g), 1);
+        mbar_init(bar_gfull, 1);
+        mbar_init(bar_gempty, 2 * kWEpiWarps);
+        *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
+        fence_barrier_init();
+    }
+    if (warp == kWMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
+    const int row_off = p.tile_lo * kTile;                           // lattice row of the P' matrix's row 0
+
+    if (warp >= kWEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWCtrlRegs));
+        if (warp == kWProducerWarp && lane == 0) {
+            // =================================================== TMA producer
+            Ring r;
+            auto stage_in = [&](uint32_t& full, uint32_t& dst, uint32_t bytes) {
+                mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                full = bar_full(r.stage);
+                dst = sX + r.stage * STAGE;
+                if (leader) mbar_arrive_expect_tx(full, 2 * bytes);
+            };
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (!begin_unit(unit)) continue;
+                for (int i = 0; i < k_n; ++i) {
+                    uint32_t full, dst;
+                    if (MODE == KP_PW) {
+                        const int srow0 = (p.tile_lo + rt * 2 + (int)rank) * kTile - row_off;
+                        stage_in(full, dst, STAGE);
+                        tma_load_2d_pair(dst, &mapP, full, 0, (k_lo + i) * p.store_rows + srow0);
+                        r.advance(NRING);
+                        for (int s = 0; s < 2; ++s) {
+                            stage_in(full, dst, STAGE);
+                            tma_load_2d_pair(dst, &mapB, full, (k_lo + i) * kKC, hb * 512 + s * 256 + (int)rank * kTile);
+                            r.advance(NRING);
+                        }
+                    } else {
+                        const int v0 = (rt * 2 + (int)rank) * kTile;            // this CTA's vocabulary rows = P' columns
+                        const int m0 = (k_lo + i) * kKC;                        // first lattice row (of the range) of the group
+                        stage_in(full, dst, STAGE);
+                        tma_load_2d_pair(dst, &mapP, full, 0, (v0 / kKC) * p.store_rows + m0);
+                        tma_load_2d_pair(dst + STAGE / 2, &mapP, full, 0, (v0 / kKC + 1) * p.store_rows + m0);
+                        const int grp = r.stage / kKG;
+                        r.advance(NRING);
+                        // As^T: 64-row blocks of lattice rows, [rows / 64][H + 16][64]
+                        const int hrow = ((row_off + m0) / kKC) * (p.H + 16);
+                        for (int s = 0; s < 2; ++s) {
+                            const bool with_scale = (s == 0 && hb == 0);
+                            stage_in(full, dst, STAGE + (with_scale ? 1024 : 0));
+                            tma_load_2d_pair(dst, &mapB, full, 0, hrow + hb * 512 + s * 256 + (int)rank * kTile);
+                            if (with_scale) tma_load_2d_pair(sScale + grp * 1024, &mapS, full, 0, hrow + p.H + (int)rank * 8);
+                            r.advance(NRING);
+                        }
+                    }
+                }
+            }
+        } else if (warp == kWWatchWarp && lane == 0 && leader) {
+            // =================================================== barrier watcher
+            volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
+            int done = 0, it = 0;
+            Ring r;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (!begin_unit(unit)) continue;
+                for (int i = 0; i < k_n; ++i) {
+                    if (i == 0 && it > 0) mbar_wait(bar_gempty, (it - 1) & 1);      // previous unit's G has left TMEM
+                    for (int s = 0; s < kKG; ++s) {
+                        mbar_wait(bar_full(r.stage), r.phase);
+                        r.advance(NRING);
+                    }
+                    *ready = ++done;
+                }
+                ++it;
+            }
+        } else if (warp == kWMmaWarp && lane == 0 && leader) {
+            // =================================================== MMA issuer
+            constexpr int fmt = BF16 ? 1 : 0;
+            const uint32_t idesc = make_idesc(fmt, MODE == KP_DW ? 1 : 0, 0, 256, 256);
+            const uint32_t xlo = desc_lo(sX);
+            // MN-major A (DW): 64-wide blocks 8 KiB apart (LBO), a 16-row k slice = +2 KiB
+            const uint32_t amn = (xlo & 0xFFFFu) | (512u << 16);
+            EventWait ev{reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base))};
+            int rstage = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (!begin_unit(unit)) continue;
+                for (int i = 0; i < k_n; ++i) {
+                    ev.wait();
+                    tc_fence_after();
+                    const uint32_t b0 = xlo + (rstage + 1) * 1024, b1 = b0 + 1024;
+                    if (MODE == KP_DW) {
+                        const uint32_t a = amn + rstage * 1024;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ss_pair_lo(tmem_base, a + 128 * k, b0 + 2 * k, idesc, (i | k) != 0);
+                            umma_f16_ss_pair_lo(tmem_base + 256, a + 128 * k, b1 + 2 * k, idesc, (i | k) != 0);
+                        }
+                        umma_commit_pair(bar_cons(rstage / kKG));       // the epilogue warps release stages r and r + 1
+                        umma_commit_pair(bar_empty(rstage + 2));
+                    } else {
+                        const uint32_t a = xlo + rstage * 1024;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ss_pair_lo(tmem_base, a + 2 * k, b0 + 2 * k, idesc, (i | k) != 0);
+                            umma_f16_ss_pair_lo(tmem_base + 256, a + 2 * k, b1 + 2 * k, idesc, (i | k) != 0);
+                        }
+                        umma_commit_pair(bar_empty(rstage));
+                        umma_commit_pair(bar_empty(rstage + 1));
+                        umma_commit_pair(bar_empty(rstage + 2));
+                    }
+                    rstage = (rstage + kKG == NRING) ? 0 : rstage + kKG;
+                }
+                umma_commit_pair(bar_gfull);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWEpiRegs));
+        // ======================================================= epilogue warps
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        auto epi_arrive = [&](uint32_t bar) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar, 0);
+        };
+        Ring kr;
+        int it = 0;
+        for (int unit = unit0; unit < n_units; unit += unit_step) {
+            if (!begin_unit(unit)) continue;
+            uint32_t gacc[32];
+            if (MODE == KP_DW) {
+                // dense part of db[v] = sum_m s_m P'[m, v]: thread (v, mh) takes half of each stage's 64 lattice rows for
+                // vocabulary row v of this CTA, from the P' stage and the row scales (row 0 of the 8-row scale tile), once
+                // the MMAs have read the group; then the warp releases both stages.  (H block 0 only.)
+                const int v = et & (kTile - 1), mh = et >> 7;
+                const int x_row0 = (rt * 2 + (int)rank) * kTile;
+                const uint8_t* sX_gen = smem_gen + (sX - smem_base);
+                const uint8_t* sS_gen = smem_gen + (sScale - smem_base);
+                float dacc = 0.f;
+                for (int i = 0; i < k_n; ++i) {
+                    const int g = kr.stage / kKG;
+                    mbar_wait(bar_cons(g), kr.phase);
+                    if (hb == 0) {
+                        const uint8_t* pst = sX_gen + kr.stage * STAGE + (v >> 6) * (STAGE / 2) + (v & 7) * 2;
+                        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sS_gen + g * 1024);
+                        const int vc = (v & 63) >> 3;
+#pragma unroll 8
+                        for (int m = mh * 32; m < mh * 32 + 32; ++m) {
+                            const uint32_t pv = *reinterpret_cast<const uint16_t*>(pst + m * 128 + ((vc ^ (m & 7)) << 4));
+                            const uint32_t sv = sc[m];
+                            float pf_, sf_, d0, d1;
+                            unpk16<BF16>(pv, pf_, d0);
+                            unpk16<BF16>(sv, sf_, d1);
+                            dacc = fmaf(pf_, sf_, dacc);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar_empty(kr.stage));
+                        mbar_arrive(bar_empty(kr.stage + 1));
+                    }
+                    kr.advance(NRING, kKG);
+                }
+                const float f = p.scal[2] * (BF16 ? 1.0f : 1.0f / kKeptUp);
+                if (hb == 0 && x_row0 + v < p.V) atomicAdd(p.db + x_row0 + v, dacc * f);
+                mbar_wait(bar_gfull, it & 1);
+                tc_fence_after();
+                const int vrow = x_row0 + row;
+                const bool ok = vrow < p.V;
+                for (int cc = ch; cc < 16; cc += 2) {               // TMEM column cc * 32 <-> joint column hb * 512 + cc * 32
+                    tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
+                    tmem_ld_wait();
+                    if (ok) {
+                        float* dst = p.dW + (size_t)vrow * p.H + hb * 512 + cc * 32;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            red_add_v4(dst + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                       __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
+                    }
+                }
+            } else {
+                const int tile = p.tile_lo + rt * 2 + (int)rank;
+                const bool valid_x = tile < n_tiles;
+                const int grow = tile * kTile + row;
+                const float f = valid_x ? p.pfac[grow] * p.scal[1] : 0.f;
+                mbar_wait(bar_gfull, it & 1);
+                tc_fence_after();
+                float* dst = p.ew + (size_t)grow * p.H + hb * 512;
+                for (int cc = ch; cc < 16; cc += 2) {
+                    tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
+                    tmem_ld_wait();
+                    if (valid_x) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dst + cc * 32 + e) =
+                                make_float4(__uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
+                                            __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
+                    }
+                }
+            }
+            tc_fence_before();
+            epi_arrive(bar_gempty);
+            ++it;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kWMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+bool wide_supported_h(int H) { return H >= 512 && H <= 4096 && H % 512 == 0; }
+
+static int wide_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <typename K, typename... Args>
+static int launch_pair(K kern, unsigned grid_x, size_t smem, cudaStream_t stream, Args... args) {
+    TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((grid_x + 1) & ~1u, 1, 1);
+    cfg.blockDim = dim3(kWThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
+static WideParams wide_params(int H, int V, int Vpad, int tile_lo, int tile_cnt, uint64_t store_rows, const int* meta,
+                              const float* scal) {
+    WideParams p{};
+    p.H = H;
+    p.NKC = H / kKC;
+    p.V = V;
+    p.n_vchunks = Vpad / 256;
+    p.n_k64 = Vpad / kKC;
+    p.tile_lo = tile_lo;
+    p.tile_cnt = tile_cnt;
+    p.store_rows = (int)store_rows;
+    p.n_hb = H / 512;
+    p.meta = meta;
+    p.scal = scal;
+    return p;
+}
+
+// S pass over lattice tiles [tile_lo, tile_lo + tile_cnt): statistics + P' (pass over every tile pair, then the redo
+// pass over the flagged ones).  store_rows >= 128 * (tile_cnt rounded up to even).
+int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_lo, int tile_cnt, int H, int V, int Vpad,
+                   bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label, int blank,
+                   float* lse, float* lpb, float* lpl, float* pfac, float* mref, void* pstore, uint64_t store_rows,
+                   int* flags, cudaStream_t stream) {
+    WideParams p = wide_params(H, V, Vpad, tile_lo, tile_cnt, store_rows, meta, scal);
+    p.blank = blank;
+    p.bias2 = bias2;
+    p.row_label = row_label;
+    p.lse = lse;
+    p.lpb = lpb;
+    p.lpl = lpl;
+    p.pfac = pfac;
+    p.mref = mref;
+    p.pstore = static_cast<uint16_t*>(pstore);
+    p.flags = flags;
+    const size_t fixed = 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
+    p.NS = kSpMaxStages;
+    const size_t smem = (size_t)p.NS * kSpStage + fixed;
+    CUtensorMap mx, my;
+    if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+    const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
+    for (int redo = 0; redo < 2; ++redo) {
+        p.redo = redo;
+        int rc = bf16 ? launch_pair(sp_kernel<true>, grid, smem, stream, mx, my, p)
+                      : launch_pair(sp_kernel<false>, grid, smem, stream, mx, my, p);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// EW rows of tiles [tile_lo, tile_lo + tile_cnt) = P' . W16 * pfac / w_scale
+int launch_wide_pw(const void* pstore, uint64_t store_rows, const void* w16t, int tile_lo, int tile_cnt, int H, int V,
+                   int Vpad, bool bf16, const int* meta, const float* scal, const float* pfac, float* ew,
+                   cudaStream_t stream) {
+    WideParams p = wide_params(H, V, Vpad, tile_lo, tile_cnt, store_rows, meta, scal);
+    p.pfac = const_cast<float*>(pfac);
+    p.ew = ew;
+    const size_t smem = (size_t)kKG * kKG * kChunkBytes + kKG * 1024 + 32 * 8 + 16;
+    CUtensorMap mp, mb;
+    if (int rc = make_matrix_map(&mp, pstore, store_rows * (uint64_t)(Vpad / kKC), kKC, bf16, kTile)) return rc;
+    if (int rc = make_matrix_map(&mb, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, kTile)) return rc;
+    const int units = ((tile_cnt + 1) / 2) * p.n_hb;
+    const unsigned grid = 2u * (unsigned)max(1, min(units, wide_sm_count() / 2));
+    return bf16 ? launch_pair(kp_kernel<KP_PW, true>, grid, smem, stream, mp, mb, mb, p)
+                : launch_pair(kp_kernel<KP_PW, false>, grid, smem, stream, mp, mb, mb, p);
+}
+
+// dW += gmax / kKeptUp * P'^T . As over the lattice rows of tiles [tile_lo, tile_lo + tile_cnt), db likewise (dense part)
+int launch_wide_dw(const void* pstore, uint64_t store_rows, const void* a16st, uint64_t rows_ub, int tile_lo, int tile_cnt,
+                   int H, int V, int Vpad, bool bf16, const int* meta, const float* scal, float* dW, float* db,
+                   cudaStream_t stream) {
+    WideParams p = wide_params(H, V, Vpad, tile_lo, tile_cnt, store_rows, meta, scal);
+    p.dW = dW;
+    p.db = db;
+    const size_t smem = (size_t)kKG * kKG * kChunkBytes + kKG * 1024 + 32 * 8 + 16;
+    const int n_tp = (tile_cnt + 1) / 2, n_vq = ((V + kTile - 1) / kTile + 1) / 2, pairs = max(1, wide_sm_count() / 2);
+    // lattice-row splits: units = vocabulary tile pairs x H blocks x splits should fill whole waves of the CTA pairs,
+    // long units preferred (every unit ends with a read-out + red.add of its 256 x 512 tile: ~1.5 tile pairs' worth)
+    int best = 1;
+    double best_score = -1.0;
+    for (int sp = 1; sp <= min(n_tp, 128); ++sp) {
+        const int len = (n_tp + sp - 1) / sp;
+        if ((n_tp + len - 1) / len != sp) continue;
+        const int units = n_vq * p.n_hb * sp;
+        const int waves = (units + pairs - 1) / pairs;
+        const double score = (double)units / ((double)pairs * waves) * len / (len + 1.5);
+        if (score > best_score) {
+            best_score = score;
+            best = sp;
+        }
+    }
+    p.splits = best;
+    CUtensorMap mp, mb, ms;
+    if (int rc = make_matrix_map(&mp, pstore, store_rows * (uint64_t)(Vpad / kKC), kKC, bf16, 64)) return rc;
+    if (int rc = make_matrix_map(&mb, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, kTile)) return rc;
+    if (int rc = make_matrix_map(&ms, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, 8)) return rc;
+    const unsigned grid = 2u * (unsigned)max(1, min(n_vq * p.n_hb * p.splits, pairs));
+    return bf16 ? launch_pair(kp_kernel<KP_DW, true>, grid, smem, stream, mp, mb, ms, p)
+                : launch_pair(kp_kernel<KP_DW, false>, grid, smem, stream, mp, mb, ms, p);
+}
+
+}  // namespace ttx

@@ -24,7 +24,7 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew_kept": 2, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew_kept": 2, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_wide_sp": 2, "ttx_wide_pw": 1, "ttx_wide_dw": 1, "ttx_kept_prepare": 4, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 2, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
@@ -261,6 +261,134 @@ class FusedJointRNNT(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+def wide_width(H):
+    return bool(_lib.get().ttx_wide_supported_h(int(H)))
+
+
+def _wide_chunks(plan, Vpad):
+    """Tile ranges (tile_lo even) whose 16-bit P' matrix fits the budget (TTX_KEEP_GB, default 32; at least one tile
+    pair).  One range = the whole batch: P' is kept from forward to backward; several: one chunk-sized matrix, and the
+    backward recomputes each chunk's P'."""
+    budget = max(float(os.environ.get("TTX_KEEP_GB", "32")), 0.0) * 2**30
+    tiles = max(2, int(budget // (128 * Vpad * 2)) & ~1)
+    return [(t0, min(tiles, plan.ntub - t0)) for t0 in range(0, plan.ntub, tiles)]
+
+
+class WideJointRNNT(torch.autograd.Function):
+    """Same contract as FusedJointRNNT for joint widths that are multiples of 512 (aishell.yaml's 1024,
+    joint_streaming.yaml's 2048; /root/reference/tt/model.py:35-37): three streamed tcgen05 products around the 16-bit
+    softmax numerators P' (csrc/ttx_wide.cu) -- S pass with both operands streamed, EW = P' . W16, dW = P'^T . As --
+    with everything else (operand casts, lattice, coefficients, reductions) shared with the fused path.  No library GEMM."""
+
+    @staticmethod
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        if not eproj.is_cuda:
+            raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
+        dev = eproj.device
+        B, T, H = eproj.shape
+        U1 = pproj.shape[1]
+        V = w_out.shape[0]
+        if pproj.shape[0] != B or pproj.shape[2] != H or w_out.shape[1] != H or b_out.shape[0] != V:
+            raise ValueError("inconsistent joint shapes")
+        ep, pp = eproj.detach().float().contiguous(), pproj.detach().float().contiguous()
+        w, b = w_out.detach().float().contiguous(), b_out.detach().float().contiguous()
+        labels = labels.contiguous()
+        with torch.cuda.device(dev):
+            plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
+            st = _stream(dev)
+            Vpad = (V + 255) // 256 * 256
+            scal = torch.zeros(8, dtype=torch.float32, device=dev)
+            w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
+            bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
+            w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if need_act else None
+            a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev) if need_w else None
+            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
+                  plan.idx, st)
+            a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
+            row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
+            lstride = labels.shape[1] if labels.dim() == 2 else 0
+            _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
+                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
+                  _p(a16t), plan.idx, st)
+            lse, lpb, lpl, pfac, mref = (plan.rowf() for _ in range(5))
+            ew = plan.rowf(H) if need_act else None
+            chunks = _wide_chunks(plan, Vpad)
+            store_rows = 128 * ((max(c[1] for c in chunks) + 1) & ~1)
+            pstore = torch.empty(store_rows * Vpad, dtype=torch.int16, device=dev)
+            flags = torch.zeros((plan.ntub + 1) // 2 + 1, dtype=torch.int32, device=dev)
+            for t0, cnt in chunks:
+                WideJointRNNT._sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, blank, bf16, lse, lpb, lpl,
+                                  pfac, mref, pstore, store_rows, flags)
+                if need_act:
+                    _call("ttx_wide_pw", dev, _p(pstore), store_rows, _p(w16t), _p(pfac), _p(scal), _p(plan.meta), plan.ntub,
+                          t0, cnt, H, V, int(bf16), _p(ew), plan.idx, st)
+            alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
+        ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
+        ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
+        ctx.chunks, ctx.store_rows = chunks, store_rows
+        ctx.ew, ctx.w32, ctx.a16t = ew, (w if need_act else None), a16t
+        ctx.pstore = pstore if (need_w and len(chunks) == 1) else None      # kept from forward to backward
+        ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta, pfac, mref)
+        return costs
+
+    @staticmethod
+    def _sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, blank, bf16, lse, lpb, lpl, pfac, mref, pstore,
+            store_rows, flags):
+        _call("ttx_wide_sp", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), plan.ntub, t0, cnt,
+              H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(pfac), _p(mref), _p(pstore), store_rows,
+              _p(flags), plan.idx, st)
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        (ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta, pfac,
+         mref) = ctx.saved_tensors
+        plan, (B, T, U1, H, V) = ctx.plan, ctx.dims
+        dev = plan.dev
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        d_ep = d_pp = d_w = d_b = None
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            scal = scal.clone()
+            Vpad = w16.numel() // H
+            if need_w:
+                d_w = torch.zeros(V, H, dtype=torch.float32, device=dev)
+                d_b = torch.zeros(V, dtype=torch.float32, device=dev)
+            rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
+            if need_w:
+                a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
+                zflags = torch.zeros(16384, dtype=torch.int32, device=dev)
+                _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl), _p(pfac),
+                      _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), _p(zflags), B, T, U1, plan.ntub, H,
+                      ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st)
+                pstore = ctx.pstore
+                recompute = pstore is None
+                if recompute:
+                    pstore = torch.empty(ctx.store_rows * Vpad, dtype=torch.int16, device=dev)
+                    flags = torch.zeros((plan.ntub + 1) // 2 + 1, dtype=torch.int32, device=dev)
+                    sink = [plan.rowf() for _ in range(5)]          # the statistics come out again; only P' is wanted
+                for t0, cnt in ctx.chunks:
+                    if recompute:
+                        WideJointRNNT._sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, ctx.blank, ctx.bf16,
+                                          sink[0], sink[1], sink[2], sink[3], sink[4], pstore, ctx.store_rows, flags)
+                    _call("ttx_wide_dw", dev, _p(pstore), ctx.store_rows, _p(a16st), _p(scal), _p(plan.meta), plan.ntub, t0,
+                          cnt, H, V, ctx.bf16, _p(d_w), _p(d_b), plan.idx, st)
+                ctx.pstore = None
+            if need_act:
+                d_ep = torch.zeros(B, T, H, dtype=torch.float32, device=dev)
+                d_pp = torch.zeros(B, U1, H, dtype=torch.float32, device=dev)
+                _call("ttx_reduce_act_grad_ew", dev, _p(ctx.ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
+                      ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
+                      _p(d_ep), _p(d_pp), plan.idx, st)
+        dt = ctx.in_dtypes
+        cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
+        return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
+                cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
+                None, None, None, None, None, None)
+
+
 class ChunkedJointRNNT(torch.autograd.Function):
     """Same contract as FusedJointRNNT for joint widths the fused tensor-core kernels do not cover (any multiple of
     64, e.g. aishell.yaml's 1024 and joint_streaming.yaml's 2048): lattice rows are processed in chunks, the
@@ -375,8 +503,13 @@ def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, b
 
     Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
     dev = eproj.device
-    fused = supported_width(eproj.shape[-1]) and os.environ.get("TTX_FORCE_CHUNKED", "0") != "1"
-    fn = FusedJointRNNT if fused else ChunkedJointRNNT
+    H = eproj.shape[-1]
+    if os.environ.get("TTX_FORCE_CHUNKED", "0") == "1":
+        fn = ChunkedJointRNNT
+    elif wide_width(H) and (H > 512 or os.environ.get("TTX_WIDE", "0") == "1"):
+        fn = WideJointRNNT
+    else:
+        fn = FusedJointRNNT if supported_width(H) else ChunkedJointRNNT
     return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
                     _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16, sizes)
 
