@@ -45,12 +45,15 @@ WORKLOADS = {
 
 
 def peaks():
+    """Roofline denominators: the sustained cuBLAS figure is the one for a kernel timed inside a long step (the roofline
+    'frac'); the burst figure is reported next to it ('frac_burst') -- the timed region here is short."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), hbm=float(p["hbm_gbs"]),
-                    source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)")
-    return dict(tflops=1400.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), burst=float(p["bf16_tflops"]),
+                    hbm=float(p["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (frac: bf16_tflops_sustained, frac_burst: bf16_tflops)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
 
 
 def synth(w, seed, device=None, pin=False):
@@ -120,15 +123,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(clocks), "power_w_max": max(power) if power else None}
 
 
+def _cpu_joint(w):
+    """The reference's own joint module (unmodified, from the staged copy baseline/_ref/ -- /root/reference does not exist
+    on the GPU box) or, without it, the oracle's restatement."""
+    from oracle import joint_ref, ref_import
+    tt = w.get("joint") == "tt"
+    if ref_import.available():
+        try:
+            if tt:
+                return ref_import.tt_model().JointNet(2 * w["D"], w["H"], w["V"]), "tt.model.JointNet (unmodified reference)"
+            jn = ref_import.espnet_joint_module().JointNetwork
+            return (jn(w["V"], w["D"], w["D"], w["H"], "tanh"),
+                    "espnet...joint_network.JointNetwork (unmodified reference)")
+        except Exception:                          # a stale or partial copy: the restatement is pinned to it by the tests
+            pass
+    if tt:
+        return joint_ref.TTJointNet(2 * w["D"], w["H"], w["V"]), "oracle/joint_ref.TTJointNet"
+    return joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh"), "oracle/joint_ref.EspnetJointNetwork"
+
+
 def cpu_port_step(w, B_s, seed=1234):
-    """One step of the reference's CPU path (oracle port) on B_s utterances of workload w; returns seconds."""
-    from oracle import joint_ref, rnnt_oracle
-    ws = dict(w, B=B_s)
+    """One step of the reference's CPU path on B_s utterances of workload w (reference joint + the oracle's port of the
+    un-vendored warprnnt_pytorch loss); returns seconds."""
+    from oracle import rnnt_oracle
+    ws = dict(w, B=B_s, bf16=False)
     enc, pred, labels, act_lens, label_lens = synth(ws, seed)
     torch.manual_seed(seed)
     tt = w.get("joint") == "tt"
-    joint = (joint_ref.TTJointNet(2 * w["D"], w["H"], w["V"]) if tt else
-             joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh"))
+    joint, cpu_port_step.joint_name = _cpu_joint(w)
     crit = rnnt_oracle.RNNTLoss(blank=0)
     enc.requires_grad_()
     pred.requires_grad_()
@@ -149,9 +171,9 @@ def cpu_baseline(w, budget_s=12.0):
     ts = [cpu_port_step(w, B_s) for _ in range(2)]
     t = min(ts)
     return {"value": B_s / t, "unit": "utt/s", "cores": cores, "kind": "port",
-            "sample": "%d utterances of the workload per step (T=%d U=%d V=%d H=%d), best of 2 steps, "
-                      "oracle/joint_ref.EspnetJointNetwork + oracle/rnnt_cpu.c (OpenMP)" %
-                      (B_s, w["T"], w["U"], w["V"], w["H"])}
+            "sample": "%d utterances of the workload per step (T=%d U=%d V=%d H=%d), best of 2 steps, %s + "
+                      "oracle/rnnt_cpu.c (OpenMP port of warprnnt_pytorch)" %
+                      (B_s, w["T"], w["U"], w["V"], w["H"], cpu_port_step.joint_name)}
 
 
 def run_reference(args, w):
@@ -173,12 +195,13 @@ def run_reference(args, w):
         cpu_port_step(w, B_s)
     dt = time.perf_counter() - t0
     val = B_s * args.steps / dt
-    sample = "%d utterances per step of %s" % (B_s, w["desc"])
+    sample = "%d utterances per step of %s; %s + oracle/rnnt_cpu.c (OpenMP port of warprnnt_pytorch)" % (
+        B_s, w["desc"], cpu_port_step.joint_name)
     print(json.dumps({
         "impl": "reference", "metric": "joint+RNN-T loss fwd+bwd utterances/s", "value": val, "unit": "utt/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "sample": sample},
+        "config": {"workload": w["desc"]},
         "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -192,6 +215,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the workload's batch; strong: the workload's batch is sharded over the GPUs")
+    ap.add_argument("--logits", default="init", choices=["init", "peaked"],
+                    help="peaked: trained-like output layer (larger weights, boosted blank / label biases)")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel table to stderr")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -214,10 +241,22 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.scaling == "strong":
+        if w["B"] % world:
+            raise SystemExit("--scaling strong: the workload's batch %d is not divisible by %d GPUs" % (w["B"], world))
+        w = dict(w, B=w["B"] // world, desc=w["desc"] + " (global batch, sharded)")
     torch.manual_seed(1234)
     tt = w.get("joint") == "tt"
     joint = (ttb.JointNet(2 * w["D"], w["H"], w["V"]) if tt else
              ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh")).to(dev)
+    if args.logits == "peaked":
+        # a trained model's output layer rather than nn.Linear's initialisation: logits several nats wide, the blank and a
+        # few hundred frequent units boosted -- exercises the moving softmax reference of the forward kernels
+        out_layer = joint.project_layer if tt else joint.lin_out
+        with torch.no_grad():
+            out_layer.weight.mul_(3.0)
+            out_layer.bias[0] += 4.0
+            out_layer.bias[torch.randperm(w["V"])[: w["V"] // 16].to(dev)] += 6.0
     if w.get("bf16"):
         joint = joint.bfloat16()
 
@@ -300,12 +339,13 @@ def main():
     M = int((act_lens.long() * (label_lens.long() + 1)).sum())      # lattice cells actually present
     unit_flops = 2.0 * M * w["H"] * w["V"]           # one M x H x V contraction (F = 3 of these)
     pk = peaks()
-    dom = max((k for k in table if k.startswith("ttx_joint_") or k.startswith("ttx_rows_")),
+    dom = max((k for k in table if k.startswith("ttx_joint_") or k.startswith("ttx_rows_") or k.startswith("ttx_wide_")),
               key=lambda k: table[k]["avg_ms"] * table[k]["calls"])
     dom_ms = table[dom]["avg_ms"]
     # algorithmic contractions (2*M*H*V each) one launch of the kernel accounts for: the fused forward+gradient
     # launch does the forward projection AND the dL/dA contraction; the chunked path's row kernels do none themselves
-    alg_units = {"ttx_joint_fwd_grad": 2.0, "ttx_rows_lse": 0.0, "ttx_rows_grad": 0.0}.get(dom, 1.0)
+    alg_units = {"ttx_joint_fwd_grad": 2.0, "ttx_rows_lse": 0.0, "ttx_rows_grad": 0.0, "ttx_wide_sp": 1.0, "ttx_wide_pw": 1.0,
+                 "ttx_wide_dw": 1.0}.get(dom, 1.0)
     unit_flops_dom = unit_flops * alg_units
     achieved = unit_flops_dom / (dom_ms * 1e-3) / 1e12
     traffic = None
@@ -317,10 +357,12 @@ def main():
         "metric": "joint+RNN-T loss fwd+bwd utterances/s",
         "value": world * w["B"] * args.steps / (ms * 1e-3), "unit": "utt/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 tensor-core operands, f32 accumulate/softmax/lattice (fp32 variant)",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": ("bf16 tensor-core operands" if w.get("bf16") else "f16 tensor-core operands") +
+                 ", f32 accumulate/softmax, f64 lattice (%s variant)" % ("bf16-input" if w.get("bf16") else "fp32"),
         "data": "synthetic",
         "config": {"workload": w["desc"], "global_batch": world * w["B"], "parallelism": "dp%d" % world,
+                   "logits": args.logits,
                    "l2": "per-step working set (A16 %.2f GB + dA %.2f GB) exceeds the 126 MB L2; no explicit flush" %
                          (M * w["H"] * 2 / 1e9, M * w["H"] * 4 / 1e9)},
         "e2e": {"value": world * w["B"] * args.steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d,
@@ -328,10 +370,12 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops"], "traffic": traffic, "kernel_ms": dom_ms,
+                     "frac": achieved / pk["tflops"], "frac_burst": achieved / pk["burst"], "peak_burst": pk["burst"],
+                     "traffic": traffic, "kernel_ms": dom_ms,
                      "algorithmic_flops_per_launch": unit_flops_dom, "peak_source": pk["source"]},
         "roofline_step": {"algorithmic_flops": 3 * unit_flops, "achieved": 3 * unit_flops / (step_ms * 1e-3) / 1e12,
-                          "frac": 3 * unit_flops / (step_ms * 1e-3) / 1e12 / pk["tflops"]},
+                          "frac": 3 * unit_flops / (step_ms * 1e-3) / 1e12 / pk["tflops"],
+                          "frac_burst": 3 * unit_flops / (step_ms * 1e-3) / 1e12 / pk["burst"]},
         "kernels": table,
     }
     if "ttx_lattice_fwd_bwd" in table:

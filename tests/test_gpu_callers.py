@@ -131,8 +131,10 @@ def test_unmodified_train_loop_drives_product_on_cuda(inner):
         for a, b in zip(lg_[1:], lr_[1:]):                   # after SGD steps taken with the compared gradients
             assert abs(a - b) / abs(b) < 1e-3, (lg_, lr_)
         for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
-            # the three (momentum) SGD updates themselves, not the parameters they are small against
-            assert rel(a.detach().cpu() - init[n], b.detach() - init[n]) < 2 * GRAD_TOL, n
+            # the three (momentum, norm-clipped) SGD updates themselves, not the parameters they are small against; a
+            # clipped update is a few float32 ulps of an O(1) parameter, so this is a coarse check -- the gradients were
+            # compared to 1e-3 above and the loss trajectory to 1e-3 here
+            assert rel(a.detach().cpu() - init[n], b.detach() - init[n]) < 5e-2, n
     finally:
         tt_model.JointNet = orig
 
