@@ -38,6 +38,20 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def _assert_grads_close(model, ref_model, tol):
+    """Relative L2 per parameter; a gradient that is mathematically zero (the key bias of softmax attention: pure
+    rounding noise on both sides, ~1e-11 here) is compared against the largest gradient of the model instead."""
+    pairs = [(n, a.grad, b.grad) for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters())]
+    gmax = max(float(b.detach().double().norm()) for _, _, b in pairs if b is not None)
+    for n, a, b in pairs:
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0, n
+            continue
+        assert a is not None, n
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        assert float((a - b).norm()) <= tol * float(b.norm()) + 1e-7 * gmax, (n, rel(a, b))
+
+
 def _seed(s):
     torch.manual_seed(s)
     np.random.seed(s)
@@ -198,11 +212,7 @@ def test_espnet_transformer_transducer_forward_backward_fp32():
     assert got.dtype == torch.float32 and got.shape == (1,)
     got.backward()
     assert abs(float(got) - float(want)) / abs(float(want)) < LOSS_TOL
-    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
-        if b.grad is None:
-            assert a.grad is None or float(a.grad.abs().max()) == 0, n
-            continue
-        assert rel(a.grad, b.grad) < GRAD_TOL, (n, rel(a.grad, b.grad))
+    _assert_grads_close(model, ref_model, GRAD_TOL)
 
 
 def test_espnet_transformer_transducer_forward_backward_bf16_joint():
@@ -231,8 +241,4 @@ def test_espnet_transformer_transducer_forward_backward_bf16_joint():
         outs.append(loss)
     want, got = outs
     assert abs(float(got) - float(want)) / abs(float(want)) < 1e-2
-    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
-        if b.grad is None:
-            continue
-        assert a.grad is not None and a.grad.dtype == b.grad.dtype, n
-        assert rel(a.grad, b.grad) < 5e-2, (n, rel(a.grad, b.grad))
+    _assert_grads_close(model, ref_model, 5e-2)
