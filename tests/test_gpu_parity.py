@@ -364,21 +364,19 @@ def test_c_abi_rejects_unsupported_width_with_message():
 
 
 @pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"},
-                                 {"TTX_QUAD": "1", "TTX_KEEP_GB": "0"}, {"TTX_QUAD": "2", "TTX_NO_FWD_GRAD": "1"},
                                  {"TTX_REPLAY": "0"}, {"TTX_DW_CHUNKS": "2"}, {"TTX_KEEP_GB": "0"},
                                  {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2"},
                                  {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2", "TTX_REPLAY": "0"},
                                  {"TTX_SPARSE_FUSED": "1"}, {"TTX_REDUCE_FUSED": "0"}, {}])
 def test_kernel_variants_agree_with_oracle(env, monkeypatch):
     """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
-    kernel (TTX_NO_FWD_GRAD=1), the quad kernel for the weight gradient (TTX_QUAD=1) and for both gradients
-    (TTX_QUAD=2), the forward+gradient kernel without its P' replay (TTX_REPLAY=0), the weight gradient cut into several
+    kernel (TTX_NO_FWD_GRAD=1), the forward+gradient kernel without its P' replay (TTX_REPLAY=0), the weight gradient cut into several
     lattice-row splits with a short last one (TTX_DW_CHUNKS=2: 2 + 2 + 1 stream chunks), the recomputing weight gradient
     (TTX_KEEP_GB=0: nothing kept between forward and backward; with and without replay), the exact blank / label terms
     of the kept-P' weight gradient folded into the activation-gradient reduction (TTX_SPARSE_FUSED=1), the two-kernel activation-gradient
     reductions (TTX_REDUCE_FUSED=0) and the default kernels
     (forward+gradient launch that keeps P', weight gradient as one product on it) all meet the tolerance on a batch
-    with an odd number of lattice tiles (the pad tile of the last pair / quad)."""
+    with an odd number of lattice tiles (the pad tile of the last pair)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)

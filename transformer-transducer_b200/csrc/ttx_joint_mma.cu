@@ -1592,463 +1592,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     }
 }
 
-// ===========================================================================================================
-// Quad kernel (H = 512, modes DA and DW): the pair kernel's work split over a cluster of FOUR CTAs = two CTA pairs
-// with different roles, so that the softmax operand is computed ONCE per (stationary row, stream row) instead of once
-// per 256-column slab of H:
-//
-//   S pair (cluster ranks 0, 1)   X tile stationary in shared memory, streams Y, S = X . Y^T into a DOUBLE-buffered
-//                                  TMEM accumulator (the pair holds no G, so TMEM has room).  Sixteen epilogue warps in
-//                                  two groups -- group g owns accumulator g and the chunks of parity g -- turn S into
-//                                  the 16-bit operand P' sub-tile by sub-tile and push it with asynchronous DSMEM
-//                                  stores (st.async, completion counted in bytes on a barrier of the receiver)
-//                                  straight into the G pair's shared memory.
-//   G pair (cluster ranks 2, 3)   no X tile: its shared memory holds two 256-column P' chunks (64 KiB each per CTA)
-//                                  and a ring for the K-major transposed stream; its epilogue warps write the exact
-//                                  blank / label entries into a landed chunk, then G = P' . Y^T-chunks accumulates
-//                                  for ALL of H (2 x 256 TMEM columns), read out once at the end.
-//
-// CTA c of the S pair and CTA c of the G pair own the same 128 rows.  Per 256 x 256 block the quad executes the S
-// contraction and the exponentials once (the pair kernel: once per slab) and streams each operand chunk from L2 once.
-// Measured inputs to this design (tools/mma_bench.cu): tcgen05 issue floor, DSMEM 16-18 B/cycle whatever the
-// instruction, 33 clusters of four per B200.
-constexpr int kQuadEpiWarps = 16;
-constexpr int kQuadThreads = (kQuadEpiWarps + 4) * 32;
-constexpr int kQuadProducerWarp = kQuadEpiWarps;
-constexpr int kQuadMmaWarp = kQuadEpiWarps + 1;
-constexpr int kQuadWatchWarp = kQuadEpiWarps + 2;
-constexpr int kQuadCtrlRegs = 56;                  // 20 warps x 96 = 4 x 56 + 16 x 104 (setmaxnreg needs multiples of 8)
-constexpr int kQuadEpiRegs = 104;
-constexpr int kQuadRing0 = 8 * kChunkBytes;        // [0, 128 KiB): X tile (S pair) / two P' chunks (G pair); ring behind
-constexpr int kQuadMaxStages = 6;
-constexpr int kQuadBars = 40;
-constexpr int kQuadAux = 2560;                     // S pair: per group 256 exponent offsets + 8 words of sign bits
-
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-// asynchronous 16-byte store into another CTA's shared memory; the receiver's barrier counts the bytes
-__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar) : "memory");
-}
-// commit of the calling pair's MMAs, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"(mask)
-        : "memory");
-}
-
-template <int MODE, bool BF16>
-__global__ void __launch_bounds__(kQuadThreads, 1)
-joint_quad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
-                  const __grid_constant__ CUtensorMap mapYT, const MmaParams p) {
-    static_assert(MODE == MODE_DA || MODE == MODE_DW, "the quad kernel has no forward+gradient mode");
-    constexpr int NT = 256;                 // stream rows per chunk = S accumulator columns
-    constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
-    constexpr int PCHUNK = 4 * kChunkBytes; // one 256-column P' chunk of this CTA's 128 rows
-    const uint32_t rank = cluster_ctarank();
-    const bool g_role = rank >= 2;          // G pair
-    const uint32_t c = rank & 1;            // row half inside the pair
-    const bool leader = (c == 0);
-    const uint16_t pair_mask = g_role ? 0xC : 0x3;
-    const int n_tiles = p.meta[0];
-    const int quad = blockIdx.x >> 2;
-    int j0, j1;
-    bool valid_x = true;
-    if (MODE == MODE_DW) {
-        const int n_st = (n_tiles + 1) / 2;
-        const int per = (n_st + p.splits - 1) / p.splits;
-        j0 = blockIdx.z * per;
-        j1 = min(n_st, j0 + per);
-    } else {
-        if (quad * 2 >= n_tiles) return;
-        valid_x = quad * 2 + (int)c < n_tiles;
-        j0 = 0;
-        j1 = (p.V + NT - 1) / NT;
-    }
-    if (j0 >= j1) return;
-    const int x_row0 = (quad * 2 + (int)c) * kTile;
-    const int n_iter = j1 - j0;
-
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t smem_base = smem_u32(smem_raw);
-    if (smem_base & 1023u) {
-        if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
-        __trap();
-    }
-    const uint32_t sX = smem_base;                     // S pair: X tile; G pair: P' chunk buffers 0 / 1
-    const uint32_t sRing = smem_base + kQuadRing0;
-    const uint32_t sBar = sRing + p.NS * STAGE;
-    const uint32_t sTmemPtr = sBar + kQuadBars * 8;
-    const uint32_t sWatch = sTmemPtr + 8;
-    const uint32_t sAux = sTmemPtr + 16;
-    uint8_t* smem_gen = smem_raw;
-    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
-
-    auto bar_xfull = [&](int k) { return sBar + 8 * k; };            // 0..7
-    auto bar_full = [&](int s) { return sBar + 8 * (8 + s); };       // 8..13
-    auto bar_empty = [&](int s) { return sBar + 8 * (14 + s); };     // 14..19
-    auto bar_sfull = [&](int b) { return sBar + 8 * (20 + b); };     // S pair
-    auto bar_sempty = [&](int b) { return sBar + 8 * (22 + b); };    // S leader: the 16 warps of group b (both CTAs)
-    auto bar_pland = [&](int b) { return sBar + 8 * (24 + b); };     // each G CTA: bytes of chunk buffer b have landed
-    auto bar_pready = [&](int b) { return sBar + 8 * (26 + b); };    // G leader: both G CTAs patched chunk buffer b
-    auto bar_pempty = [&](int b) { return sBar + 8 * (28 + b); };    // every CTA: the G pair has consumed chunk buffer b
-    const uint32_t bar_gfull = sBar + 8 * 30;
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == kQuadProducerWarp && lane == 0) {
-        tma_prefetch_desc(&mapX);
-        tma_prefetch_desc(&mapY);
-        tma_prefetch_desc(&mapYT);
-        for (int k = 0; k < 8; ++k) mbar_init(bar_xfull(k), 1);
-        for (int s = 0; s < p.NS; ++s) {
-            mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_sfull(b), 1);
-            mbar_init(bar_sempty(b), 16);
-            mbar_init(bar_pland(b), 1);
-            mbar_init(bar_pready(b), 16);
-            mbar_init(bar_pempty(b), 1);
-        }
-        mbar_init(bar_gfull, 1);
-        *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
-        fence_barrier_init();
-    }
-    if (warp == kQuadMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_gen;
-
-    if (warp >= kQuadEpiWarps) {
-        // =========================================================== control warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kQuadCtrlRegs));
-        if (warp == kQuadProducerWarp) {
-            if (lane == 0) {
-                Ring r;
-                auto load_stage = [&](const CUtensorMap* map, int col, int row) {
-                    mbar_wait(bar_empty(r.stage), r.phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STAGE);
-                    tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
-                    r.advance(p.NS);
-                };
-                if (!g_role) {
-                    for (int k = 0; k < p.NKC; ++k) {
-                        if (leader) mbar_arrive_expect_tx(bar_xfull(k), 2 * kChunkBytes);
-                        tma_load_2d_pair(sX + k * kChunkBytes, &mapX, bar_xfull(k), k * kKC, x_row0);
-                    }
-                    for (int i = 0; i < n_iter; ++i)
-                        for (int k = 0; k < p.NKC; ++k) load_stage(&mapY, k * kKC, (j0 + i) * NT + (int)c * kTile);
-                } else {
-                    for (int i = 0; i < n_iter; ++i)
-                        for (int sp = 0; sp < 4; ++sp)
-                            for (int sl = 0; sl < 2; ++sl)
-                                if (MODE == MODE_DW)      // A16^T in blocks of 64 lattice rows, [rows / 64][H][64]
-                                    load_stage(&mapYT, 0, (((j0 + i) * NT + sp * kKC) / kKC) * p.H + sl * 256 + (int)c * kTile);
-                                else
-                                    load_stage(&mapYT, (j0 + i) * NT + sp * kKC, sl * 256 + (int)c * kTile);
-                }
-            }
-        } else if (warp == kQuadWatchWarp) {
-            // barrier watcher of the pair's MMA issuer (see the pair kernel)
-            if (lane == 0 && leader) {
-                volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
-                int done = 0;
-                Ring r;
-                for (int i = 0; i < n_iter; ++i) {
-                    const int buf = i & 1;
-                    const uint32_t ph = (i >> 1) & 1;
-                    if (!g_role) {
-                        mbar_wait(bar_sempty(buf), ph ^ 1);
-                        *ready = ++done;
-                        for (int k = 0; k < p.NKC; ++k) {
-                            if (i == 0) mbar_wait(bar_xfull(k), 0);
-                            mbar_wait(bar_full(r.stage), r.phase);
-                            *ready = ++done;
-                            r.advance(p.NS);
-                        }
-                    } else {
-                        mbar_wait(bar_pready(buf), ph);
-                        *ready = ++done;
-                        for (int s8 = 0; s8 < 8; ++s8) {
-                            mbar_wait(bar_full(r.stage), r.phase);
-                            *ready = ++done;
-                            r.advance(p.NS);
-                        }
-                    }
-                }
-            }
-        } else if (warp == kQuadMmaWarp) {
-            if (lane == 0 && leader) {
-                constexpr int fmt = BF16 ? 1 : 0;
-                const uint32_t idesc = make_idesc(fmt, 0, 0, 256, 256);
-                const uint32_t xlo = desc_lo(sX), rlo = desc_lo(sRing);
-                volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
-                int need = 0, have = 0;
-                auto wait_event = [&]() {
-                    ++need;
-                    if (have < need) {
-                        uint32_t spins = 0;
-                        while ((have = *ready) < need) {
-                            if (++spins > (1u << 26)) {
-                                printf("ttx: quad MMA issuer timed out waiting for event %d (block %d,%d,%d rank %u)\n", need,
-                                       blockIdx.x, blockIdx.y, blockIdx.z, rank);
-                                __trap();
-                            }
-                        }
-                    }
-                };
-                int stage = 0;
-                for (int i = 0; i < n_iter; ++i) {
-                    const int buf = i & 1;
-                    if (!g_role) {
-                        // ---- S pair: S(i) = X . Y_i^T into accumulator i & 1
-                        trace_at(p, 1, i, 0);
-                        wait_event();                           // group `buf` has read chunk i - 2 out of this accumulator
-                        tc_fence_after();
-                        for (int k = 0; k < p.NKC; ++k) {
-                            wait_event();
-                            tc_fence_after();
-                            const uint32_t a = xlo + k * 1024, b = rlo + stage * 1024;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_f16_ss_pair_lo(tmem_base + buf * 256, a + 2 * kk, b + 2 * kk, idesc, (k | kk) != 0);
-                            umma_commit_mask(bar_empty(stage), pair_mask);
-                            if (++stage == p.NS) stage = 0;
-                        }
-                        umma_commit_mask(bar_sfull(buf), pair_mask);
-                        trace_at(p, 1, i, 1);
-                    } else {
-                        // ---- G pair: G(slab) += P'(i, sp) . Y^T chunk, both slabs per P' sub-tile
-                        wait_event();                           // chunk buffer `buf` landed and patched in both CTAs
-                        tc_fence_after();
-                        for (int sp = 0; sp < 4; ++sp) {
-                            const uint32_t a = xlo + (buf * 4 + sp) * 1024;
-                            for (int sl = 0; sl < 2; ++sl) {
-                                wait_event();
-                                tc_fence_after();
-                                const uint32_t b = rlo + stage * 1024;
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma_f16_ss_pair_lo(tmem_base + sl * 256, a + 2 * kk, b + 2 * kk, idesc, (i | sp | kk) != 0);
-                                umma_commit_mask(bar_empty(stage), pair_mask);
-                                if (++stage == p.NS) stage = 0;
-                            }
-                        }
-                        umma_commit_mask(bar_pempty(buf), 0xF);
-                    }
-                }
-                if (g_role) umma_commit_mask(bar_gfull, pair_mask);
-            }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kQuadEpiRegs));
-        const int q = warp & 3;
-        const int ch = (warp >> 2) & 1;
-        const int grp = warp >> 3;                    // S pair: epilogue group; G pair: only group 0 works
-        const int row = q * 32 + lane;
-        const int et = threadIdx.x & 255;             // thread within its group
-        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const float inv_ws = p.scal[1];
-        const float pscale = BF16 ? 1.0f : kPScale;
-        const float lg_scale = BF16 ? 0.0f : 12.0f;
-        const int n_valid_rows = n_tiles * kTile;
-        if (!g_role) {
-            // =========================================================== S pair epilogue: group grp <-> accumulator grp,
-            // chunks of parity grp, P' chunk buffer grp of the sibling G CTA.  thread = (row, column half ch)
-            const float c1 = inv_ws * kLog2e;
-            float* kbuf = reinterpret_cast<float*>(smem_gen + (sAux - smem_base)) + grp * 264;   // 256 offsets + 8 sign words
-            const uint32_t* sgn = reinterpret_cast<const uint32_t*>(kbuf + 256);
-            const bool any_neg = p.scal[3] != 0.f;
-            const uint32_t rP = mapa_rank(sX, rank + 2) + grp * PCHUNK;
-            const uint32_t r_pland = mapa_rank(bar_pland(grp), rank + 2);
-            auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(kEpiBarrier + grp) : "memory"); };
-            float krow = 0.f, db_acc = 0.f;
-            int vrow = 0;
-            if (MODE == MODE_DA) {
-                const float lse = valid_x ? p.rowmeta[x_row0 + row].x : INFINITY;
-                krow = fmaf(lse, -kLog2e, lg_scale);
-            } else {
-                vrow = x_row0 + row;
-                krow = __ldg(p.bias2 + vrow);
-            }
-            const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1);
-            uint64_t d01 = pk2(0.f, 0.f), d23 = d01;
-            int k_own = 0;
-            for (int i = grp; i < n_iter; i += 2, ++k_own) {
-                const int t0 = (j0 + i) * NT;           // first vocab id (DA) / lattice row (DW) of this stream chunk
-                if (MODE == MODE_DW) {
-                    // per-column constant k_m = -lse2_m + log2(|w_m| * scale): Q = +-2^(acc*c1 + bias2_v + k_m)
-                    group_sync();                       // every thread of the group is done with the previous constants
-                    const int col = t0 + et;
-                    float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-                    if (col < n_valid_rows) cm = __ldg(p.rowmeta + col);
-                    kbuf[et] = fmaf(cm.x, -kLog2e, lg2f(fabsf(cm.w)) + lg_scale);
-                    const uint32_t neg = __ballot_sync(0xffffffffu, cm.w < 0.f);
-                    if (lane == 0) reinterpret_cast<uint32_t*>(kbuf + 256)[et >> 5] = neg;
-                    group_sync();
-                }
-                mbar_wait(bar_sfull(grp), k_own & 1);
-                if (et == 0 && grp == 0) trace_at(p, 2, k_own, 0);
-                tc_fence_after();
-                mbar_wait(bar_pempty(grp), (k_own & 1) ^ 1);    // the G pair has consumed chunk i - 2 from this buffer
-                // One 64-column sub-tile at a time: read 32 accumulator columns, exponentials, asynchronous DSMEM stores.
-                // (Keeping all four sub-tiles' results in registers until the accumulator is released was tried: with
-                // 104 registers it spills and the exponentials slow down by more than the earlier release gains.)
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem_base + lane_addr + grp * 256 + g * 64 + ch * 32, acc);
-                    const int cb = g * 64 + ch * 32;    // this thread's first column of sub-tile g inside the chunk
-                    const float4* k4 = (MODE == MODE_DA) ? reinterpret_cast<const float4*>(p.bias2 + t0 + cb)
-                                                         : reinterpret_cast<const float4*>(kbuf + cb);
-                    float4 kv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) kv[e] = (MODE == MODE_DA) ? __ldg(k4 + e) : k4[e];
-                    const uint32_t sbits = (MODE == MODE_DW && any_neg) ? sgn[cb >> 5] : 0u;
-                    tmem_ld_wait();
-                    if (g == 3) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(bar_sempty(grp), 0);
-                        if (et == 0 && grp == 0) trace_at(p, 2, k_own, 1);
-                    }
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint64_t y01 = fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(kv[e].x, kv[e].y), krow2));
-                        const uint64_t y23 = fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(kv[e].z, kv[e].w), krow2));
-                        float y0, y1, y2, y3;
-                        unpk2(y01, y0, y1);
-                        unpk2(y23, y2, y3);
-                        float v0 = ex2f(y0), v1 = ex2f(y1), v2 = ex2f(y2), v3 = ex2f(y3);
-                        if (MODE == MODE_DW) {
-                            if (sbits) {
-                                v0 = ((sbits >> (4 * e + 0)) & 1) ? -v0 : v0;
-                                v1 = ((sbits >> (4 * e + 1)) & 1) ? -v1 : v1;
-                                v2 = ((sbits >> (4 * e + 2)) & 1) ? -v2 : v2;
-                                v3 = ((sbits >> (4 * e + 3)) & 1) ? -v3 : v3;
-                            }
-                            d01 = add2(d01, pk2(v0, v1));
-                            d23 = add2(d23, pk2(v2, v3));
-                        }
-                        packed[2 * e] = pack16<BF16>(v0, v1);
-                        packed[2 * e + 1] = pack16<BF16>(v2, v3);
-                    }
-                    const uint32_t r0 = rP + g * kChunkBytes + row * 128;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        st_async_v4(r0 + (((ch * 4 + cc) ^ (row & 7)) << 4), packed[4 * cc + 0], packed[4 * cc + 1],
-                                    packed[4 * cc + 2], packed[4 * cc + 3], r_pland);
-                }
-                if (et == 0 && grp == 0) trace_at(p, 2, k_own, 3);
-            }
-            // dense part of db: sum_m w_m * softmax(m, v); the sparse -rb / -rl terms are added by grad_prep_kernel
-            if (MODE == MODE_DW && vrow < p.V) {
-                float d0, d1;
-                unpk2(add2(d01, d23), d0, d1);
-                db_acc = d0 + d1;
-                atomicAdd(p.db + vrow, db_acc * p.scal[2] / pscale);
-            }
-        } else if (grp == 0) {
-            // =========================================================== G pair epilogue warps 0..7: thread = (row, ch)
-            // Per chunk: arm the landing barrier, wait until the S sibling's 64 KiB have arrived, write the exact blank /
-            // label entries (p = exp(lp) from the forward pass, rowmeta .y / .z) over the dense ones, hand over to the MMA.
-            uint8_t* sP_gen = smem_gen;
-            float4 rm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-            int label = -1;
-            if (MODE == MODE_DA && valid_x) {
-                rm = p.rowmeta[x_row0 + row];
-                label = p.row_label[x_row0 + row];
-            }
-            for (int i = 0; i < n_iter; ++i) {
-                const int buf = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                const int t0 = (j0 + i) * NT;
-                float4 cm = make_float4(INFINITY, 0.f, 0.f, 0.f);
-                int clabel = -1;
-                if (MODE == MODE_DW) {
-                    const int col = t0 + et;            // this thread owns column et of the chunk
-                    if (col < n_valid_rows) {
-                        cm = __ldg(p.rowmeta + col);
-                        clabel = __ldg(p.row_label + col);
-                    }
-                }
-                if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_pland(buf), PCHUNK);
-                mbar_wait(bar_pland(buf), ph);
-                uint8_t* cbuf = sP_gen + buf * PCHUNK;
-                if (MODE == MODE_DA) {
-                    const int cbl = p.blank - t0, clb = label - t0;
-                    if (cbl >= 0 && cbl < NT && ((cbl >> 5) & 1) == ch)
-                        *reinterpret_cast<uint16_t*>(cbuf + (cbl >> 6) * kChunkBytes + ptile_off(row, cbl & 63)) = to16<BF16>(rm.y * pscale);
-                    if (clb >= 0 && clb < NT && ((clb >> 5) & 1) == ch)
-                        *reinterpret_cast<uint16_t*>(cbuf + (clb >> 6) * kChunkBytes + ptile_off(row, clb & 63)) = to16<BF16>(rm.z * pscale);
-                } else {
-                    const int rbl = p.blank - x_row0, rlb = clabel - x_row0;
-                    uint8_t* sub = cbuf + (et >> 6) * kChunkBytes;
-                    if (rbl >= 0 && rbl < kTile) *reinterpret_cast<uint16_t*>(sub + ptile_off(rbl, et & 63)) = to16<BF16>(cm.y * cm.w * pscale);
-                    if (rlb >= 0 && rlb < kTile) *reinterpret_cast<uint16_t*>(sub + ptile_off(rlb, et & 63)) = to16<BF16>(cm.z * cm.w * pscale);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(bar_pready(buf), 2);
-            }
-            // ---- final: G (128 rows x 512 fp32 in TMEM) -> global; the two warps of a lane quarter split the columns
-            mbar_wait(bar_gfull, 0);
-            tc_fence_after();
-            const float gmax = p.scal[2];
-            uint32_t gacc[32];
-            float f;
-            float* dst;
-            bool ok;
-            if (MODE == MODE_DA) {
-                f = rm.w * gmax * inv_ws / pscale;
-                dst = p.dA + (size_t)(x_row0 + row) * p.H;
-                ok = valid_x;
-            } else {
-                f = gmax / pscale;
-                ok = x_row0 + row < p.V;
-                dst = p.dW + (size_t)(x_row0 + row) * p.H;
-            }
-            for (int cc = ch; cc < 16; cc += 2) {
-                tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
-                tmem_ld_wait();
-                if (ok) {
-                    if (MODE == MODE_DW) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4)
-                            red_add_v4(dst + cc * 32 + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
-                                       __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            float4 o4 = make_float4(__uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
-                                                    __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
-                            *reinterpret_cast<float4*>(dst + cc * 32 + e) = o4;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == kQuadMmaWarp) {
-        tc_fence_after();
-        tmem_dealloc_pair(tmem_base, 512);
-    }
-}
-
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -2349,79 +1892,6 @@ static int alloc_scratch(void** scratch, size_t bytes, cudaStream_t stream) {
     return 0;
 }
 
-// ---- quad kernel (cluster of 4: S pair + G pair)
-// TTX_QUAD: 0 (default) = pair kernel everywhere (weight gradient 3.9 ms at cfg2 since it is persistent and replays
-// P'), 1 = quad kernel for the weight gradient (5.0 ms), 2 = also for the activation gradient when it is a separate
-// launch (5.7 ms either way).  The quad kernel is kept as the measured alternative to the replay, see DESIGN.md.
-static int quad_level() {
-    const char* e = getenv("TTX_QUAD");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
-}
-
-template <int MODE, bool BF16>
-static int launch_quad(const CUtensorMap& mx, const CUtensorMap& my, const CUtensorMap& myt, const MmaParams& p, dim3 grid,
-                       size_t smem, cudaStream_t stream) {
-    auto kern = joint_quad_kernel<MODE, BF16>;
-    TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kQuadThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TTX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, myt, p));
-    return 0;
-}
-
-// Clusters of four that the device runs at once (B200: 33 -- each GPC strands the SMs that do not fill a cluster).
-static int quad_slots(size_t smem) {
-    static int slots = 0;
-    if (!slots) {
-        auto kern = joint_quad_kernel<MODE_DW, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(4 * 256);
-        cfg.blockDim = dim3(kQuadThreads);
-        cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 4;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = 33;
-        }
-        slots = n;
-    }
-    return slots;
-}
-
-static void quad_params(MmaParams& p, size_t& smem, int H, int V) {
-    p.H = H;
-    p.NKC = H / 64;
-    p.V = V;
-    p.n_halves = 2;
-    p.HH = 256;
-    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-    p.trace = trace_buffer();
-    const size_t fixed = (size_t)kQuadRing0 + kQuadBars * 8 + 16 + kQuadAux;
-    int ns = kQuadMaxStages;
-    if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kQuadMaxStages, atoi(e)));
-    while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
-    p.NS = ns;
-    smem = fixed + (size_t)ns * kChunkBytes;
-}
-
 // Forward statistics + EW = sum_v p_v W_v (blank / label columns excluded) in one pass (MODE_FG of the pair kernel).
 int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, uint64_t rows_ub, int n_tiles_ub, int H,
                           int V, int Vpad, bool bf16, const int* meta, const float* bias2, const float* scal,
@@ -2542,64 +2012,6 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
                      int n_tiles_ub, int H, int V, int Vpad, bool bf16, const int* meta, const float* bias2,
                      const float* scal, const int* row_label, int blank, const float4* rowmeta, float* dA, float* dW,
                      float* db, int splits, cudaStream_t stream, const int* run_if) {
-    if (H == 512 && v3_applicable(H, w16t, a16t) && quad_level() > 0 && !run_if) {
-        const bool quad_da = quad_level() > 1;
-        MmaParams p{};
-        size_t smem;
-        quad_params(p, smem, H, V);
-        p.blank = blank;
-        p.meta = meta;
-        p.bias2 = bias2;
-        p.scal = scal;
-        p.row_label = row_label;
-        p.rowmeta = rowmeta;
-        p.dA = dA;
-        p.dW = dW;
-        p.db = db;
-        if (dA && quad_da) {
-            CUtensorMap mx, my, myt;
-            if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
-            if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-            if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
-            p.splits = 1;
-            dim3 grid(4 * ((n_tiles_ub + 1) / 2), 1, 1);
-            int rc = bf16 ? launch_quad<MODE_DA, true>(mx, my, myt, p, grid, smem, stream)
-                          : launch_quad<MODE_DA, false>(mx, my, myt, p, grid, smem, stream);
-            if (rc) return rc;
-            trace_dump("DA quad", stream);
-        }
-        if (dW) {
-            // Lattice-row splits chosen here (the caller's `splits` targets the pair kernel): quads = vocabulary tile
-            // pairs x splits should fill whole waves of the device's cluster slots, >= 16 stream chunks per quad.
-            const int n_vq = (V + 2 * kTile - 1) / (2 * kTile);
-            const int n_st = (n_tiles_ub + 1) / 2;
-            const int slots = quad_slots(smem);
-            int best = 1;
-            double best_eff = 0.0;
-            for (int sp = 1; sp <= 128; ++sp) {
-                if (sp > 1 && n_st < 16 * sp) break;
-                const int quads = n_vq * sp;
-                const double eff = (double)quads / ((double)slots * ((quads + slots - 1) / slots));
-                if (eff > best_eff + 0.02) {
-                    best = sp;
-                    best_eff = eff;
-                }
-            }
-            CUtensorMap mx, my, myt;
-            if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-            if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile)) return rc;
-            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H * (rows_ub / kKC), kKC, bf16, p.HH / 2)) return rc;
-            p.splits = best;
-            dim3 grid(4 * n_vq, 1, best);
-            int rc = bf16 ? launch_quad<MODE_DW, true>(mx, my, myt, p, grid, smem, stream)
-                          : launch_quad<MODE_DW, false>(mx, my, myt, p, grid, smem, stream);
-            if (rc) return rc;
-            trace_dump("DW quad", stream);
-        }
-        if (!dA || quad_da) return 0;
-        dW = nullptr;                                           // the pair kernel below does the activation gradient only
-        db = nullptr;
-    }
     if (v3_applicable(H, w16t, a16t)) {
         MmaParams p{};
         p.H = H;

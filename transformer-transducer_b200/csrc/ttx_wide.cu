@@ -76,6 +76,11 @@ __device__ __forceinline__ bool w_quarter_any(int q, bool pred) {
     return r != 0;
 }
 
+// byte offset of 16-bit element (row, col < 64) inside a staged [128 x 64] sub-tile (128-byte rows, 128B swizzle)
+__device__ __forceinline__ uint32_t stile_off(int row, int col) {
+    return row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;
+}
+
 // The issuing thread's view of the barrier watcher's event counter (see ttx_joint_mma.cu: an mbarrier try_wait costs
 // ~90 cycles, a tcgen05.mma must be issued every ~128).
 struct EventWait {
@@ -98,7 +103,8 @@ struct EventWait {
 // =========================================================================================================== S pass
 template <bool BF16>
 __global__ void __launch_bounds__(kWThreads, 1)
-sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, const WideParams p) {
+sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+          const __grid_constant__ CUtensorMap mapP, const WideParams p) {
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
@@ -115,7 +121,8 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         __trap();
     }
     const uint32_t sRing = smem_base;
-    const uint32_t sBar = sRing + p.NS * kSpStage;
+    const uint32_t sStage = sRing + p.NS * kSpStage;       // four [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
+    const uint32_t sBar = sStage + 4 * kChunkBytes;
     const uint32_t sTmemPtr = sBar + 32 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sXg = sTmemPtr + 16;                    // [2][128] floats: row maxima of the two column halves
@@ -125,11 +132,16 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     auto bar_empty = [&](int s) { return sBar + 8 * (8 + s); };
     auto bar_sfull = [&](int b) { return sBar + 8 * (16 + b); };
     auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
+    const uint32_t bar_pwritten = sBar + 8 * 20;           // this CTA's epilogue warps have staged a tile's P'
+    const uint32_t bar_pfree = sBar + 8 * 21;              // ... and the TMA store has read it out of shared memory
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kWProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapP);
+        mbar_init(bar_pwritten, kWEpiWarps);
+        mbar_init(bar_pfree, 1);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
@@ -183,6 +195,25 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     }
                 }
             }
+        } else if (warp == kWWatchWarp + 1 && lane == 0) {
+            // =================================================== storer (each CTA): staged P' tile -> the blocked matrix
+            int n = 0;
+            for (int unit = unit0; unit < n_units; unit += unit_step) {
+                if (skip_unit(unit)) continue;
+                const int srow0 = (unit * 2 + (int)rank) * kTile;          // row of the P' matrix (relative to tile_lo)
+                for (int j = 0; j < p.n_vchunks; ++j, ++n) {
+                    mbar_wait(bar_pwritten, n & 1);
+                    for (int gg = 0; gg < 4; ++gg)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + gg * kChunkBytes), "r"(0),
+                                       "r"((j * 4 + gg) * p.store_rows + srow0)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(bar_pfree);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else if (warp == kWMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
@@ -210,7 +241,11 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWEpiRegs));
-        // ======================================================= epilogue: thread = (row, column half ch of the S tile)
+        // ======================================================= epilogue: thread = (row, column half ch)
+        // Thread (row, ch) owns columns ch*32 .. ch*32+31 of each of the tile's four 64-column sub-tiles (the layout of
+        // the staged P' sub-tiles: one 128-byte swizzled row per lattice row).  A 256-column S tile is processed in
+        // registers in one pass: read-out (the accumulator is handed back at once), exponentials, reference vote,
+        // staging, and the storer thread's TMA store moves the 64 KiB to the P' matrix.
         const int q = warp & 3, ch = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -221,6 +256,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         const float ref_limit = BF16 ? 100.f : 15.f;
         float* xg = reinterpret_cast<float*>(smem_gen + (sXg - smem_base));
         float4* xch = reinterpret_cast<float4*>(smem_gen + (sXch - smem_base));
+        uint8_t* stage_gen = smem_gen + (sStage - smem_base);
         auto epi_arrive = [&](uint32_t bar) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar, 0);
@@ -231,71 +267,46 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             const int tile = p.tile_lo + unit * 2 + (int)rank;
             const bool valid_x = tile < n_tiles;
             const int grow = tile * kTile + row;
-            const size_t srow = (size_t)(grow - p.tile_lo * kTile);
             const int label = valid_x ? p.row_label[grow] : -1;
             float mref = (p.redo && valid_x) ? p.mref[grow] : 0.f;
             float ssum = 0.f, zb = 0.f, zl = 0.f;
             for (int j = 0; j < p.n_vchunks; ++j, ++g) {
-                const int t0 = j * 256 + ch * 128;          // first vocabulary id of this thread's 128 columns
-                const float* bias_t = p.bias2 + t0;
+                const int t0 = j * 256;
+                const float* bias_t = p.bias2 + t0 + ch * 32;
+                float4 bpre[8];                               // bias of sub-tile 0, fetched while waiting for the S tile
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
                 mbar_wait(bar_sfull(g & 1), (g >> 1) & 1);
                 tc_fence_after();
                 uint32_t acc[4][32];
 #pragma unroll
-                for (int gg = 0; gg < 4; ++gg) tmem_ld32(tmem_base + lane_addr + (g & 1) * 256 + ch * 128 + gg * 32, acc[gg]);
+                for (int gg = 0; gg < 4; ++gg) tmem_ld32(tmem_base + lane_addr + (g & 1) * 256 + gg * 64 + ch * 32, acc[gg]);
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty(g & 1));
-                float lmax = -INFINITY, part = 0.f;
-                // logits of this thread's columns in log2 units (+ lg_scale); blank / label logits picked on the way
-#pragma unroll
-                for (int gg = 0; gg < 4; ++gg) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + gg * 32) + e);
-                        const float y0 = fmaf(__uint_as_float(acc[gg][4 * e + 0]), c1, bv.x + lg_scale);
-                        const float y1 = fmaf(__uint_as_float(acc[gg][4 * e + 1]), c1, bv.y + lg_scale);
-                        const float y2 = fmaf(__uint_as_float(acc[gg][4 * e + 2]), c1, bv.z + lg_scale);
-                        const float y3 = fmaf(__uint_as_float(acc[gg][4 * e + 3]), c1, bv.w + lg_scale);
-                        lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                        acc[gg][4 * e + 0] = __float_as_uint(y0); acc[gg][4 * e + 1] = __float_as_uint(y1);
-                        acc[gg][4 * e + 2] = __float_as_uint(y2); acc[gg][4 * e + 3] = __float_as_uint(y3);
-                    }
-                    const int cbl = p.blank - (t0 + gg * 32), clb = label - (t0 + gg * 32);
-                    if (cbl >= 0 && cbl < 32) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) zb = (e == cbl) ? __uint_as_float(acc[gg][e]) - lg_scale : zb;
-                    }
-                    if (clb >= 0 && clb < 32) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) zl = (e == clb) ? __uint_as_float(acc[gg][e]) - lg_scale : zl;
-                    }
-                }
-                // reference: fixed by the row maximum of the first chunk (both halves); later chunks vote and only move
-                // it when a value would leave the 16-bit range (then the tile pair is flagged for the redo launch)
-                bool move = false;
+                float lmax = -INFINITY;
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
                 if (j == 0 && !p.redo) {
-                    move = true;
-                } else {
-                    move = w_quarter_any(q, lmax - mref > ref_limit);
-                    if (move && !p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;
-                }
-                if (move) {
+                    // First chunk: exact two-step (row maximum first, then the exponentials against the new reference).
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = (gg == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + gg * 64) + e);
+                            const float y0 = fmaf(__uint_as_float(acc[gg][4 * e + 0]), c1, bv.x + lg_scale);
+                            const float y1 = fmaf(__uint_as_float(acc[gg][4 * e + 1]), c1, bv.y + lg_scale);
+                            const float y2 = fmaf(__uint_as_float(acc[gg][4 * e + 2]), c1, bv.z + lg_scale);
+                            const float y3 = fmaf(__uint_as_float(acc[gg][4 * e + 3]), c1, bv.w + lg_scale);
+                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                            acc[gg][4 * e + 0] = __float_as_uint(y0); acc[gg][4 * e + 1] = __float_as_uint(y1);
+                            acc[gg][4 * e + 2] = __float_as_uint(y2); acc[gg][4 * e + 3] = __float_as_uint(y3);
+                        }
+                    }
                     xg[ch * kTile + row] = lmax;
                     w_quarter_sync(q);
                     const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                    w_quarter_sync(q);                       // xg may be rewritten
-                    if (j == 0) {
-                        mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
-                    } else if (rmax - mref > ref_limit) {
-                        const float nref = rmax - ref_exp;
-                        ssum *= ex2f(mref - nref);
-                        mref = nref;
-                    }
-                }
-                uint32_t packed[4][16];
-                {
-                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                    mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
+                    w_quarter_sync(q);                            // xg may be rewritten
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
 #pragma unroll
@@ -303,28 +314,103 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                             const float e0 = ex2f(__uint_as_float(acc[gg][e]) - mref), e1 = ex2f(__uint_as_float(acc[gg][e + 1]) - mref);
                             const float e2 = ex2f(__uint_as_float(acc[gg][e + 2]) - mref), e3 = ex2f(__uint_as_float(acc[gg][e + 3]) - mref);
                             p0 += e0; p1 += e1; p2 += e2; p3 += e3;
-                            packed[gg][e >> 1] = pack16<BF16>(e0, e1);
-                            packed[gg][(e >> 1) + 1] = pack16<BF16>(e2, e3);
+                            acc[gg][e] = __float_as_uint(e0); acc[gg][e + 1] = __float_as_uint(e1);
+                            acc[gg][e + 2] = __float_as_uint(e2); acc[gg][e + 3] = __float_as_uint(e3);
                         }
                     }
-                    part = (p0 + p1) + (p2 + p3);
-                }
-                ssum += part;
-                // P' -> the blocked matrix [Vpad / 64][store_rows][64]: this thread's 128 columns = two 128-byte runs
-                {
-                    uint16_t* dst0 = p.pstore + ((size_t)(j * 4 + ch * 2) * p.store_rows + srow) * 64;
+                    ssum = (p0 + p1) + (p2 + p3);
+                } else {
+                    // Later chunks (and every chunk of the redo launch), optimistic single pass: exponentials against the
+                    // CURRENT reference fused with the logits; the partner warps then vote and only if a value left the
+                    // 16-bit range the reference moves (and the tile pair is flagged for the redo launch).
+                    const float krow = lg_scale - mref;
+                    const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1);
+                    uint64_t s01 = pk2(0.f, 0.f), s23 = s01;
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
-                        uint4* d4 = reinterpret_cast<uint4*>(dst0 + (size_t)(gg >> 1) * p.store_rows * 64 + (gg & 1) * 32);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = (gg == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + gg * 64) + e);
+                            const uint64_t y01 = fma2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2));
+                            const uint64_t y23 = fma2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2));
+                            float y0, y1, y2, y3;
+                            unpk2(y01, y0, y1);
+                            unpk2(y23, y2, y3);
+                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
+                            const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
+                            s01 = add2(s01, pk2(e0, e1));
+                            s23 = add2(s23, pk2(e2, e3));
+                            acc[gg][4 * e + 0] = __float_as_uint(e0); acc[gg][4 * e + 1] = __float_as_uint(e1);
+                            acc[gg][4 * e + 2] = __float_as_uint(e2); acc[gg][4 * e + 3] = __float_as_uint(e3);
+                        }
+                    }
+                    {
+                        const uint64_t st = add2(s01, s23);
+                        unpk2(st, p0, p1);
+                    }
+                    float part = p0 + p1;
+                    if (w_quarter_any(q, lmax > ref_limit)) {
+                        if (!p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;     // stored chunks now carry mixed scales
+                        xg[ch * kTile + row] = lmax;
+                        w_quarter_sync(q);
+                        const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                        const float delta = (rmax > ref_limit) ? (rmax - ref_exp) : 0.f;
+                        const float fsc = ex2f(-delta);
+                        ssum *= fsc;
+                        part *= fsc;
+                        mref += delta;
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) acc[gg][e] = __float_as_uint(__uint_as_float(acc[gg][e]) * fsc);
+                        w_quarter_sync(q);                        // xg may be rewritten
+                    }
+                    ssum += part;
+                }
+                {
+                    // blank / label logits (log2 units) of this row, recovered from the exponentials: once per row
+                    const int cbl = p.blank - t0, clb = label - t0;   // column inside this chunk, if any
+                    if (cbl >= 0 && cbl < 256 && ((cbl >> 5) & 1) == ch) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v = (gg * 64 + ch * 32 + e == cbl) ? __uint_as_float(acc[gg][e]) : v;
+                        zb = lg2f(v) + mref - lg_scale;
+                    }
+                    if (clb >= 0 && clb < 256 && ((clb >> 5) & 1) == ch) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v = (gg * 64 + ch * 32 + e == clb) ? __uint_as_float(acc[gg][e]) : v;
+                        zl = lg2f(v) + mref - lg_scale;
+                    }
+                }
+                // stage the tile's P' (previous tile's store has read the buffers), blank / label entries zeroed: they are
+                // left out of P' (their exact terms are added in fp32 later)
+                mbar_wait(bar_pfree, (g & 1) ^ 1);
+                {
+                    const int cbl = p.blank - t0, clb = label - t0;
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        uint8_t* dstP = stage_gen + gg * kChunkBytes;
+                        uint8_t* r0 = dstP + row * 128;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            d4[c] = make_uint4(packed[gg][4 * c], packed[gg][4 * c + 1], packed[gg][4 * c + 2], packed[gg][4 * c + 3]);
+                            *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
+                                make_uint4(pack16<BF16>(__uint_as_float(acc[gg][8 * c + 0]), __uint_as_float(acc[gg][8 * c + 1])),
+                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 2]), __uint_as_float(acc[gg][8 * c + 3])),
+                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 4]), __uint_as_float(acc[gg][8 * c + 5])),
+                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 6]), __uint_as_float(acc[gg][8 * c + 7])));
+                        const int lo = gg * 64 + ch * 32;
+                        if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, cbl - gg * 64)) = 0;
+                        if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, clb - gg * 64)) = 0;
                     }
-                    // the blank and label columns are left out of P' (their exact terms are added in fp32 later)
-                    const int cbl = p.blank - t0, clb = label - t0;
-                    if (cbl >= 0 && cbl < 128) dst0[(size_t)(cbl >> 6) * p.store_rows * 64 + (cbl & 63)] = 0;
-                    if (clb >= 0 && clb < 128) dst0[(size_t)(clb >> 6) * p.store_rows * 64 + (clb & 63)] = 0;
                 }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pwritten);
             }
             // combine the two column halves of each row
             w_epi_sync();
@@ -334,8 +420,8 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             w_epi_sync();
             if (ch == 0 && valid_x) {
                 const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
-                zb = ((p.blank & 255) < 128) ? zb : o.y;     // which column half owns the blank / label column
-                if (label >= 0) zl = ((label & 255) < 128) ? zl : o.z;
+                zb = ((p.blank & 63) < 32) ? zb : o.y;        // which column half owns the blank / label column
+                if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
                 p.lse[grow] = lse2 * kLn2;
                 p.lpb[grow] = (zb - lse2) * kLn2;
                 p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
@@ -712,17 +798,19 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.mref = mref;
     p.pstore = static_cast<uint16_t*>(pstore);
     p.flags = flags;
-    const size_t fixed = 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
+    const size_t fixed = 4 * kChunkBytes + 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
     p.NS = kSpMaxStages;
+    while (p.NS > 2 && (size_t)p.NS * kSpStage + fixed > 232448) --p.NS;
     const size_t smem = (size_t)p.NS * kSpStage + fixed;
-    CUtensorMap mx, my;
+    CUtensorMap mx, my, mp;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+    if (int rc = make_matrix_map(&mp, pstore, store_rows * (uint64_t)(Vpad / kKC), kKC, bf16, kTile)) return rc;
     const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
     for (int redo = 0; redo < 2; ++redo) {
         p.redo = redo;
-        int rc = bf16 ? launch_pair(sp_kernel<true>, grid, smem, stream, mx, my, p)
-                      : launch_pair(sp_kernel<false>, grid, smem, stream, mx, my, p);
+        int rc = bf16 ? launch_pair(sp_kernel<true>, grid, smem, stream, mx, my, mp, p)
+                      : launch_pair(sp_kernel<false>, grid, smem, stream, mx, my, mp, p);
         if (rc) return rc;
     }
     return 0;
