@@ -16,6 +16,7 @@
 // the flagged pairs against the FINAL reference -- so the matrix the two products read is always consistent and there is
 // no whole-batch fallback.
 #include "ttx_common.cuh"
+#include <stdlib.h>
 
 namespace ttx {
 
@@ -101,10 +102,15 @@ struct EventWait {
 };
 
 // =========================================================================================================== S pass
-template <bool BF16>
+// XS (H <= 512): the pair's A16 tiles stay in shared memory for the whole unit (loaded chunk by chunk behind their own
+// barriers) and only W16 streams: half the bytes per MMA, which takes the kernel from the L2-to-SM bandwidth bound of
+// the fully streamed form to its epilogue bound.
+template <bool BF16, bool XS>
 __global__ void __launch_bounds__(kWThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
           const __grid_constant__ CUtensorMap mapP, const WideParams p) {
+    constexpr int STG = XS ? kChunkBytes : kSpStage;       // bytes of one ring stage (W chunk [+ A chunk])
+    constexpr int NSB = 2;                                 // staged P' sub-tiles per store round (two rounds per tile)
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
@@ -120,9 +126,10 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
         __trap();
     }
-    const uint32_t sRing = smem_base;
-    const uint32_t sStage = sRing + p.NS * kSpStage;       // four [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
-    const uint32_t sBar = sStage + 4 * kChunkBytes;
+    const uint32_t sX = smem_base;                         // XS: the stationary A16 tile, NKC chunks
+    const uint32_t sRing = sX + (XS ? p.NKC * kChunkBytes : 0);
+    const uint32_t sStage = sRing + p.NS * STG;            // NSB [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
+    const uint32_t sBar = sStage + NSB * kChunkBytes;
     const uint32_t sTmemPtr = sBar + 32 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sXg = sTmemPtr + 16;                    // [2][128] floats: row maxima of the two column halves
@@ -134,6 +141,8 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
     const uint32_t bar_pwritten = sBar + 8 * 20;           // this CTA's epilogue warps have staged a tile's P'
     const uint32_t bar_pfree = sBar + 8 * 21;              // ... and the TMA store has read it out of shared memory
+    auto bar_xfull = [&](int c) { return sBar + 8 * (22 + c); };   // XS: chunk c of the stationary tile has landed
+    const uint32_t bar_xempty = sBar + 8 * 30;             // XS: the unit's last S pass has read the stationary tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kWProducerWarp && lane == 0) {
@@ -142,6 +151,8 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         tma_prefetch_desc(&mapP);
         mbar_init(bar_pwritten, kWEpiWarps);
         mbar_init(bar_pfree, 1);
+        for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
+        mbar_init(bar_xempty, 1);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
@@ -165,23 +176,33 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         if (warp == kWProducerWarp && lane == 0) {
             // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
             Ring r;
+            int xt = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
                 const int x_row0 = (p.tile_lo + unit * 2 + (int)rank) * kTile;
+                if (XS) {
+                    if (xt > 0) mbar_wait(bar_xempty, (xt - 1) & 1);
+                    ++xt;
+                    for (int c = 0; c < p.NKC; ++c) {
+                        if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
+                        tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
+                    }
+                }
                 for (int j = 0; j < p.n_vchunks; ++j)
                     for (int c = 0; c < p.NKC; ++c) {
                         mbar_wait(bar_empty(r.stage), r.phase ^ 1);
-                        if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * kSpStage);
-                        const uint32_t dst = sRing + r.stage * kSpStage;
-                        tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
-                        tma_load_2d_pair(dst + kChunkBytes, &mapY, bar_full(r.stage), c * kKC, j * 256 + (int)rank * kTile);
+                        if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STG);
+                        const uint32_t dst = sRing + r.stage * STG;
+                        if (!XS) tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
+                        tma_load_2d_pair(dst + (XS ? 0 : kChunkBytes), &mapY, bar_full(r.stage), c * kKC,
+                                         j * 256 + (int)rank * kTile);
                         r.advance(p.NS);
                     }
             }
         } else if (warp == kWWatchWarp && lane == 0 && leader) {
             // =================================================== barrier watcher: the issuer's barriers, in its order
             volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
-            int done = 0, g = 0;
+            int done = 0, g = 0, xt = 0;
             Ring r;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
@@ -189,11 +210,13 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     mbar_wait(bar_sempty(g & 1), ((g >> 1) & 1) ^ 1);
                     *ready = ++done;
                     for (int c = 0; c < p.NKC; ++c) {
+                        if (XS && j == 0) mbar_wait(bar_xfull(c), xt & 1);
                         mbar_wait(bar_full(r.stage), r.phase);
                         *ready = ++done;
                         r.advance(p.NS);
                     }
                 }
+                ++xt;
             }
         } else if (warp == kWWatchWarp + 1 && lane == 0) {
             // =================================================== storer (each CTA): staged P' tile -> the blocked matrix
@@ -201,23 +224,24 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
                 const int srow0 = (unit * 2 + (int)rank) * kTile;          // row of the P' matrix (relative to tile_lo)
-                for (int j = 0; j < p.n_vchunks; ++j, ++n) {
-                    mbar_wait(bar_pwritten, n & 1);
-                    for (int gg = 0; gg < 4; ++gg)
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + gg * kChunkBytes), "r"(0),
-                                       "r"((j * 4 + gg) * p.store_rows + srow0)
-                                     : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    mbar_arrive(bar_pfree);
-                }
+                for (int j = 0; j < p.n_vchunks; ++j)
+                    for (int rd = 0; rd < 4 / NSB; ++rd, ++n) {
+                        mbar_wait(bar_pwritten, n & 1);
+                        for (int sb = 0; sb < NSB; ++sb)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + sb * kChunkBytes), "r"(0),
+                                           "r"((j * 4 + rd * NSB + sb) * p.store_rows + srow0)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(bar_pfree);
+                    }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else if (warp == kWMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
-            const uint32_t rlo = desc_lo(sRing);
+            const uint32_t rlo = desc_lo(sRing), xlo = desc_lo(sX);
             EventWait ev{reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base))};
             int stage = 0, g = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -229,12 +253,14 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     for (int c = 0; c < p.NKC; ++c) {
                         ev.wait();                          // ring stage has landed
                         tc_fence_after();
-                        const uint32_t a = rlo + stage * (kSpStage >> 4), b = a + (kChunkBytes >> 4);
+                        const uint32_t a = XS ? xlo + c * (kChunkBytes >> 4) : rlo + stage * (STG >> 4);
+                        const uint32_t b = XS ? rlo + stage * (STG >> 4) : a + (kChunkBytes >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
                         umma_commit_pair(bar_empty(stage));
                         if (++stage == p.NS) stage = 0;
                     }
+                    if (XS && j == p.n_vchunks - 1) umma_commit_pair(bar_xempty);   // the next unit's tile may replace this one
                     umma_commit_pair(bar_sfull(g & 1));
                 }
             }
@@ -261,7 +287,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar, 0);
         };
-        int g = 0;
+        int g = 0, n = 0;                                 // S tiles, store rounds so far
         for (int unit = unit0; unit < n_units; unit += unit_step) {
             if (skip_unit(unit)) continue;
             const int tile = p.tile_lo + unit * 2 + (int)rank;
@@ -389,28 +415,32 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 }
                 // stage the tile's P' (previous tile's store has read the buffers), blank / label entries zeroed: they are
                 // left out of P' (their exact terms are added in fp32 later)
-                mbar_wait(bar_pfree, (g & 1) ^ 1);
-                {
+                uint32_t packed[4][16];
+#pragma unroll
+                for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        packed[gg][e] = pack16<BF16>(__uint_as_float(acc[gg][2 * e]), __uint_as_float(acc[gg][2 * e + 1]));
+#pragma unroll
+                for (int rd = 0; rd < 4 / NSB; ++rd, ++n) {
+                    mbar_wait(bar_pfree, (n & 1) ^ 1);
                     const int cbl = p.blank - t0, clb = label - t0;
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) {
-                        uint8_t* dstP = stage_gen + gg * kChunkBytes;
+                    for (int gg = rd * NSB; gg < rd * NSB + NSB; ++gg) {
+                        uint8_t* dstP = stage_gen + (gg - rd * NSB) * kChunkBytes;
                         uint8_t* r0 = dstP + row * 128;
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
-                                make_uint4(pack16<BF16>(__uint_as_float(acc[gg][8 * c + 0]), __uint_as_float(acc[gg][8 * c + 1])),
-                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 2]), __uint_as_float(acc[gg][8 * c + 3])),
-                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 4]), __uint_as_float(acc[gg][8 * c + 5])),
-                                           pack16<BF16>(__uint_as_float(acc[gg][8 * c + 6]), __uint_as_float(acc[gg][8 * c + 7])));
+                                make_uint4(packed[gg][4 * c], packed[gg][4 * c + 1], packed[gg][4 * c + 2], packed[gg][4 * c + 3]);
                         const int lo = gg * 64 + ch * 32;
                         if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, cbl - gg * 64)) = 0;
                         if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, clb - gg * 64)) = 0;
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_pwritten);
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pwritten);
             }
             // combine the two column halves of each row
             w_epi_sync();
@@ -798,10 +828,12 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.mref = mref;
     p.pstore = static_cast<uint16_t*>(pstore);
     p.flags = flags;
-    const size_t fixed = 4 * kChunkBytes + 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
-    p.NS = kSpMaxStages;
-    while (p.NS > 2 && (size_t)p.NS * kSpStage + fixed > 232448) --p.NS;
-    const size_t smem = (size_t)p.NS * kSpStage + fixed;
+    const bool xs = H <= 512 && !getenv("TTX_SP_STREAM_X");        // (the switch: A/B measurement of the stationary tile)
+    const size_t stg = xs ? kChunkBytes : kSpStage;
+    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
+    p.NS = 8;
+    while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
+    const size_t smem = (size_t)p.NS * stg + fixed;
     CUtensorMap mx, my, mp;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
@@ -809,8 +841,10 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
     for (int redo = 0; redo < 2; ++redo) {
         p.redo = redo;
-        int rc = bf16 ? launch_pair(sp_kernel<true>, grid, smem, stream, mx, my, mp, p)
-                      : launch_pair(sp_kernel<false>, grid, smem, stream, mx, my, mp, p);
+        int rc = xs ? (bf16 ? launch_pair(sp_kernel<true, true>, grid, smem, stream, mx, my, mp, p)
+                            : launch_pair(sp_kernel<false, true>, grid, smem, stream, mx, my, mp, p))
+                    : (bf16 ? launch_pair(sp_kernel<true, false>, grid, smem, stream, mx, my, mp, p)
+                            : launch_pair(sp_kernel<false, false>, grid, smem, stream, mx, my, mp, p));
         if (rc) return rc;
     }
     return 0;
