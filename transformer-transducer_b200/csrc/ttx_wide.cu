@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
           const __grid_constant__ CUtensorMap mapP, const WideParams p) {
     constexpr int STG = XS ? kChunkBytes : kSpStage;       // bytes of one ring stage (W chunk [+ A chunk])
-    constexpr int NSB = 2;                                 // staged P' sub-tiles per store round (two rounds per tile)
+    constexpr int NSB = 2;                                 // staging buffers: one 64-column P' sub-tile each, used in turn
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
@@ -130,7 +130,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     const uint32_t sRing = sX + (XS ? p.NKC * kChunkBytes : 0);
     const uint32_t sStage = sRing + p.NS * STG;            // NSB [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
     const uint32_t sBar = sStage + NSB * kChunkBytes;
-    const uint32_t sTmemPtr = sBar + 32 * 8;
+    const uint32_t sTmemPtr = sBar + 40 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sXg = sTmemPtr + 16;                    // [2][128] floats: row maxima of the two column halves
     const uint32_t sXch = sXg + 2 * kTile * 4;             // [2][128] float4: per-row statistics of the two halves
@@ -139,18 +139,20 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     auto bar_empty = [&](int s) { return sBar + 8 * (8 + s); };
     auto bar_sfull = [&](int b) { return sBar + 8 * (16 + b); };
     auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
-    const uint32_t bar_pwritten = sBar + 8 * 20;           // this CTA's epilogue warps have staged a tile's P'
-    const uint32_t bar_pfree = sBar + 8 * 21;              // ... and the TMA store has read it out of shared memory
-    auto bar_xfull = [&](int c) { return sBar + 8 * (22 + c); };   // XS: chunk c of the stationary tile has landed
-    const uint32_t bar_xempty = sBar + 8 * 30;             // XS: the unit's last S pass has read the stationary tile
+    auto bar_pwritten = [&](int b) { return sBar + 8 * (20 + b); };   // this CTA's epilogue warps have staged a sub-tile in buffer b
+    auto bar_pfree = [&](int b) { return sBar + 8 * (22 + b); };      // ... and the TMA store has read it out of shared memory
+    auto bar_xfull = [&](int c) { return sBar + 8 * (24 + c); };   // XS: chunk c of the stationary tile has landed
+    const uint32_t bar_xempty = sBar + 8 * 32;             // XS: the unit's last S pass has read the stationary tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kWProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapP);
-        mbar_init(bar_pwritten, kWEpiWarps);
-        mbar_init(bar_pfree, 1);
+        for (int b = 0; b < NSB; ++b) {
+            mbar_init(bar_pwritten(b), kWEpiWarps);
+            mbar_init(bar_pfree(b), 1);
+        }
         for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
         mbar_init(bar_xempty, 1);
         for (int s = 0; s < p.NS; ++s) {
@@ -225,19 +227,20 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 if (skip_unit(unit)) continue;
                 const int srow0 = (unit * 2 + (int)rank) * kTile;          // row of the P' matrix (relative to tile_lo)
                 for (int j = 0; j < p.n_vchunks; ++j)
-                    for (int rd = 0; rd < 4 / NSB; ++rd, ++n) {
-                        mbar_wait(bar_pwritten, n & 1);
-                        for (int sb = 0; sb < NSB; ++sb)
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                         ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + sb * kChunkBytes), "r"(0),
-                                           "r"((j * 4 + rd * NSB + sb) * p.store_rows + srow0)
-                                         : "memory");
+                    for (int gg = 0; gg < 4; ++gg, ++n) {           // sub-tile n goes through buffer n % NSB
+                        const int b = n % NSB;
+                        mbar_wait(bar_pwritten(b), (n / NSB) & 1);
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + b * kChunkBytes), "r"(0),
+                                       "r"((j * 4 + gg) * p.store_rows + srow0)
+                                     : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        mbar_arrive(bar_pfree);
+                        // the PREVIOUS sub-tile's store has read its buffer by now (one store stays in flight)
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (n > 0) mbar_arrive(bar_pfree((n - 1) % NSB));
                     }
             }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (the last buffer is never waited for again)
         } else if (warp == kWMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
@@ -287,14 +290,15 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar, 0);
         };
-        int g = 0, n = 0;                                 // S tiles, store rounds so far
+        int g = 0, n = 0;                                 // S tiles, staged sub-tiles so far
         for (int unit = unit0; unit < n_units; unit += unit_step) {
             if (skip_unit(unit)) continue;
             const int tile = p.tile_lo + unit * 2 + (int)rank;
             const bool valid_x = tile < n_tiles;
             const int grow = tile * kTile + row;
             const int label = valid_x ? p.row_label[grow] : -1;
-            float mref = (p.redo && valid_x) ? p.mref[grow] : 0.f;
+            // (redo: rows of a pad tile have no stored reference -- an unreachable one makes their P' exact zeros)
+            float mref = p.redo ? (valid_x ? p.mref[grow] : 1.0e4f) : 0.f;
             float ssum = 0.f, zb = 0.f, zl = 0.f;
             for (int j = 0; j < p.n_vchunks; ++j, ++g) {
                 const int t0 = j * 256;
@@ -311,9 +315,10 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 tc_fence_before();
                 epi_arrive(bar_sempty(g & 1));
                 float lmax = -INFINITY;
-                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-                if (j == 0 && !p.redo) {
-                    // First chunk: exact two-step (row maximum first, then the exponentials against the new reference).
+                const bool first = (j == 0 && !p.redo);
+                if (first) {
+                    // First chunk: exact two-step -- row maximum first (acc <- logits), then the exponentials below run
+                    // against the reference it fixes.
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
 #pragma unroll
@@ -333,69 +338,63 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
                     mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
                     w_quarter_sync(q);                            // xg may be rewritten
+                    lmax = -INFINITY;
+                }
+                // Exponentials sub-tile by sub-tile, each one staged for the TMA store as soon as it is packed (the wait for
+                // its buffer hides behind the next sub-tile's math).  Later chunks are OPTIMISTIC: values go out against the
+                // current reference and the partner warps vote afterwards; if one left the 16-bit range the reference moves
+                // and the tile pair is flagged -- the redo launch rewrites all of its P' against the final reference.
+                const float krow = lg_scale - mref;
+                const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1), nref2 = pk2(-mref, -mref);
+                uint64_t s01 = pk2(0.f, 0.f), s23 = s01;
+                const int cbl = p.blank - t0, clb = label - t0;   // blank / label column inside this chunk, if any
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) {
+                for (int gg = 0; gg < 4; ++gg, ++n) {
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            const float e0 = ex2f(__uint_as_float(acc[gg][e]) - mref), e1 = ex2f(__uint_as_float(acc[gg][e + 1]) - mref);
-                            const float e2 = ex2f(__uint_as_float(acc[gg][e + 2]) - mref), e3 = ex2f(__uint_as_float(acc[gg][e + 3]) - mref);
-                            p0 += e0; p1 += e1; p2 += e2; p3 += e3;
-                            acc[gg][e] = __float_as_uint(e0); acc[gg][e + 1] = __float_as_uint(e1);
-                            acc[gg][e + 2] = __float_as_uint(e2); acc[gg][e + 3] = __float_as_uint(e3);
-                        }
-                    }
-                    ssum = (p0 + p1) + (p2 + p3);
-                } else {
-                    // Later chunks (and every chunk of the redo launch), optimistic single pass: exponentials against the
-                    // CURRENT reference fused with the logits; the partner warps then vote and only if a value left the
-                    // 16-bit range the reference moves (and the tile pair is flagged for the redo launch).
-                    const float krow = lg_scale - mref;
-                    const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1);
-                    uint64_t s01 = pk2(0.f, 0.f), s23 = s01;
-#pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
+                    for (int e = 0; e < 8; ++e) {
+                        float y0, y1, y2, y3;
+                        if (first) {
+                            unpk2(add2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), nref2), y0, y1);
+                            unpk2(add2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), nref2), y2, y3);
+                        } else {
                             const float4 bv = (gg == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + gg * 64) + e);
-                            const uint64_t y01 = fma2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2));
-                            const uint64_t y23 = fma2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2));
-                            float y0, y1, y2, y3;
-                            unpk2(y01, y0, y1);
-                            unpk2(y23, y2, y3);
+                            unpk2(fma2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2)), y0, y1);
+                            unpk2(fma2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2)), y2, y3);
                             lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                            const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
-                            s01 = add2(s01, pk2(e0, e1));
-                            s23 = add2(s23, pk2(e2, e3));
-                            acc[gg][4 * e + 0] = __float_as_uint(e0); acc[gg][4 * e + 1] = __float_as_uint(e1);
-                            acc[gg][4 * e + 2] = __float_as_uint(e2); acc[gg][4 * e + 3] = __float_as_uint(e3);
                         }
+                        const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
+                        s01 = add2(s01, pk2(e0, e1));
+                        s23 = add2(s23, pk2(e2, e3));
+                        acc[gg][4 * e + 0] = __float_as_uint(e0); acc[gg][4 * e + 1] = __float_as_uint(e1);
+                        acc[gg][4 * e + 2] = __float_as_uint(e2); acc[gg][4 * e + 3] = __float_as_uint(e3);
+                        pk[2 * e] = pack16<BF16>(e0, e1);
+                        pk[2 * e + 1] = pack16<BF16>(e2, e3);
                     }
-                    {
-                        const uint64_t st = add2(s01, s23);
-                        unpk2(st, p0, p1);
-                    }
-                    float part = p0 + p1;
-                    if (w_quarter_any(q, lmax > ref_limit)) {
-                        if (!p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;     // stored chunks now carry mixed scales
-                        xg[ch * kTile + row] = lmax;
-                        w_quarter_sync(q);
-                        const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                        const float delta = (rmax > ref_limit) ? (rmax - ref_exp) : 0.f;
-                        const float fsc = ex2f(-delta);
-                        ssum *= fsc;
-                        part *= fsc;
-                        mref += delta;
+                    const int sbuf = n % NSB;
+                    mbar_wait(bar_pfree(sbuf), ((n / NSB) & 1) ^ 1);       // the store of sub-tile n - NSB has read the buffer
+                    uint8_t* dstP = stage_gen + sbuf * kChunkBytes;
+                    uint8_t* r0 = dstP + row * 128;
 #pragma unroll
-                        for (int gg = 0; gg < 4; ++gg)
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) acc[gg][e] = __float_as_uint(__uint_as_float(acc[gg][e]) * fsc);
-                        w_quarter_sync(q);                        // xg may be rewritten
-                    }
-                    ssum += part;
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    // the blank and label columns are left out of P' (their exact terms are added in fp32 later)
+                    const int lo = gg * 64 + ch * 32;
+                    if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, cbl - gg * 64)) = 0;
+                    if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, clb - gg * 64)) = 0;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_pwritten(sbuf));
+                }
+                float part;
+                {
+                    float p0, p1;
+                    unpk2(add2(s01, s23), p0, p1);
+                    part = p0 + p1;
                 }
                 {
                     // blank / label logits (log2 units) of this row, recovered from the exponentials: once per row
-                    const int cbl = p.blank - t0, clb = label - t0;   // column inside this chunk, if any
                     if (cbl >= 0 && cbl < 256 && ((cbl >> 5) & 1) == ch) {
                         float v = 0.f;
 #pragma unroll
@@ -413,34 +412,19 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         zl = lg2f(v) + mref - lg_scale;
                     }
                 }
-                // stage the tile's P' (previous tile's store has read the buffers), blank / label entries zeroed: they are
-                // left out of P' (their exact terms are added in fp32 later)
-                uint32_t packed[4][16];
-#pragma unroll
-                for (int gg = 0; gg < 4; ++gg)
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        packed[gg][e] = pack16<BF16>(__uint_as_float(acc[gg][2 * e]), __uint_as_float(acc[gg][2 * e + 1]));
-#pragma unroll
-                for (int rd = 0; rd < 4 / NSB; ++rd, ++n) {
-                    mbar_wait(bar_pfree, (n & 1) ^ 1);
-                    const int cbl = p.blank - t0, clb = label - t0;
-#pragma unroll
-                    for (int gg = rd * NSB; gg < rd * NSB + NSB; ++gg) {
-                        uint8_t* dstP = stage_gen + (gg - rd * NSB) * kChunkBytes;
-                        uint8_t* r0 = dstP + row * 128;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
-                                make_uint4(packed[gg][4 * c], packed[gg][4 * c + 1], packed[gg][4 * c + 2], packed[gg][4 * c + 3]);
-                        const int lo = gg * 64 + ch * 32;
-                        if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, cbl - gg * 64)) = 0;
-                        if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, clb - gg * 64)) = 0;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_pwritten);
+                if (!first && w_quarter_any(q, lmax > ref_limit)) {
+                    if (!p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;         // this pair's P' now carries mixed scales
+                    xg[ch * kTile + row] = lmax;
+                    w_quarter_sync(q);
+                    const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                    const float delta = (rmax > ref_limit) ? (rmax - ref_exp) : 0.f;
+                    const float fsc = ex2f(-delta);
+                    ssum *= fsc;
+                    part *= fsc;
+                    mref += delta;
+                    w_quarter_sync(q);                            // xg may be rewritten
                 }
+                ssum += part;
             }
             // combine the two column halves of each row
             w_epi_sync();
@@ -830,7 +814,7 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.flags = flags;
     const bool xs = H <= 512 && !getenv("TTX_SP_STREAM_X");        // (the switch: A/B measurement of the stationary tile)
     const size_t stg = xs ? kChunkBytes : kSpStage;
-    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 32 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
+    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
     p.NS = 8;
     while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
     const size_t smem = (size_t)p.NS * stg + fixed;
