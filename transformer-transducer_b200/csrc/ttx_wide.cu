@@ -57,9 +57,34 @@ constexpr int kWProducerWarp = kWEpiWarps, kWMmaWarp = kWEpiWarps + 1, kWWatchWa
 constexpr int kWCtrlRegs = 72, kWEpiRegs = 216;        // 12 warps x 168 = 4 x 72 + 8 x 216
 constexpr int kSpStage = 2 * kChunkBytes;              // A chunk + W chunk
 constexpr int kSpMaxStages = 6;
+// The S pass runs SIXTEEN epilogue warps (four per TMEM lane quarter): its epilogue -- one exponential per logit -- is
+// latency-bound with two warps per scheduler (ncu: the schedulers issue 30 % of the cycles, profiles/r2_sp_epilogue.md).
+constexpr int kSpEpiWarps = 16;
+constexpr int kSpEpiThreads = kSpEpiWarps * 32;
+constexpr int kSpThreads = kSpEpiThreads + 128;
+constexpr int kSpProducerWarp = kSpEpiWarps, kSpMmaWarp = kSpEpiWarps + 1, kSpWatchWarp = kSpEpiWarps + 2;
+constexpr int kSpCtrlRegs = 40, kSpEpiRegs = 112;      // 20 warps x 96 = 4 x 40 + 16 x 110
 
 __device__ __forceinline__ void w_epi_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kWEpiThreads) : "memory");
+}
+__device__ __forceinline__ void sp_epi_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kSpEpiThreads) : "memory");
+}
+__device__ __forceinline__ void sp_quarter_sync(int q) {
+    asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(kSpEpiThreads / 4) : "memory");
+}
+__device__ __forceinline__ bool sp_quarter_any(int q, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred pin, pout;\n\t"
+        "setp.ne.b32 pin, %2, 0;\n\t"
+        "bar.red.or.pred pout, %1, %3, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t}"
+        : "=r"(r)
+        : "r"(2 + q), "r"((uint32_t)pred), "n"(kSpEpiThreads / 4)
+        : "memory");
+    return r != 0;
 }
 __device__ __forceinline__ void w_quarter_sync(int q) {
     asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(kWEpiThreads / 4) : "memory");
@@ -106,7 +131,7 @@ struct EventWait {
 // barriers) and only W16 streams: half the bytes per MMA, which takes the kernel from the L2-to-SM bandwidth bound of
 // the fully streamed form to its epilogue bound.
 template <bool BF16, bool XS>
-__global__ void __launch_bounds__(kWThreads, 1)
+__global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
           const __grid_constant__ CUtensorMap mapP, const WideParams p) {
     constexpr int STG = XS ? kChunkBytes : kSpStage;       // bytes of one ring stage (W chunk [+ A chunk])
@@ -132,8 +157,8 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     const uint32_t sBar = sStage + NSB * kChunkBytes;
     const uint32_t sTmemPtr = sBar + 40 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
-    const uint32_t sXg = sTmemPtr + 16;                    // [2][128] floats: row maxima of the two column halves
-    const uint32_t sXch = sXg + 2 * kTile * 4;             // [2][128] float4: per-row statistics of the two halves
+    const uint32_t sXg = sTmemPtr + 16;                    // [4][128] floats: row maxima of the four column groups
+    const uint32_t sXch = sXg + 4 * kTile * 4;             // [4][128] float4: per-row statistics of the four column groups
     uint8_t* smem_gen = smem_raw;
     auto bar_full = [&](int s) { return sBar + 8 * s; };
     auto bar_empty = [&](int s) { return sBar + 8 * (8 + s); };
@@ -145,12 +170,12 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     const uint32_t bar_xempty = sBar + 8 * 32;             // XS: the unit's last S pass has read the stationary tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == kWProducerWarp && lane == 0) {
+    if (warp == kSpProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapP);
         for (int b = 0; b < NSB; ++b) {
-            mbar_init(bar_pwritten(b), kWEpiWarps);
+            mbar_init(bar_pwritten(b), kSpEpiWarps / 2);     // the eight warps that stage into buffer b
             mbar_init(bar_pfree(b), 1);
         }
         for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
@@ -161,21 +186,21 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_sfull(b), 1);
-            mbar_init(bar_sempty(b), 2 * kWEpiWarps);      // every epilogue warp of both CTAs
+            mbar_init(bar_sempty(b), 2 * kSpEpiWarps);     // every epilogue warp of both CTAs
         }
         *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
         fence_barrier_init();
     }
-    if (warp == kWMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
+    if (warp == kSpMmaWarp) tmem_alloc_pair(sTmemPtr, 512);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
-    if (warp >= kWEpiWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWCtrlRegs));
-        if (warp == kWProducerWarp && lane == 0) {
+    if (warp >= kSpEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSpCtrlRegs));
+        if (warp == kSpProducerWarp && lane == 0) {
             // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
             Ring r;
             int xt = 0;
@@ -201,7 +226,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         r.advance(p.NS);
                     }
             }
-        } else if (warp == kWWatchWarp && lane == 0 && leader) {
+        } else if (warp == kSpWatchWarp && lane == 0 && leader) {
             // =================================================== barrier watcher: the issuer's barriers, in its order
             volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
             int done = 0, g = 0, xt = 0;
@@ -220,7 +245,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 }
                 ++xt;
             }
-        } else if (warp == kWWatchWarp + 1 && lane == 0) {
+        } else if (warp == kSpWatchWarp + 1 && lane == 0) {
             // =================================================== storer (each CTA): staged P' tile -> the blocked matrix
             int n = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -241,7 +266,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (the last buffer is never waited for again)
-        } else if (warp == kWMmaWarp && lane == 0 && leader) {
+        } else if (warp == kSpMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
             const uint32_t rlo = desc_lo(sRing), xlo = desc_lo(sX);
@@ -269,13 +294,16 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWEpiRegs));
-        // ======================================================= epilogue: thread = (row, column half ch)
-        // Thread (row, ch) owns columns ch*32 .. ch*32+31 of each of the tile's four 64-column sub-tiles (the layout of
-        // the staged P' sub-tiles: one 128-byte swizzled row per lattice row).  A 256-column S tile is processed in
-        // registers in one pass: read-out (the accumulator is handed back at once), exponentials, reference vote,
-        // staging, and the storer thread's TMA store moves the 64 KiB to the P' matrix.
-        const int q = warp & 3, ch = warp >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSpEpiRegs));
+        // ======================================================= epilogue: thread = (row, column group cq)
+        // Sixteen warps, four per TMEM lane quarter.  A 256-column S tile is done in two ROUNDS of two 64-column
+        // sub-tiles; in a round thread (row, cq) owns 32 columns: sub-tile rd * 2 + (cq >> 1), half cq & 1 -- read-out,
+        // exponentials, pack, and the sub-tile is staged (128-byte swizzled rows) for the storer thread's TMA store,
+        // buffer = cq >> 1.  Later chunks are OPTIMISTIC: values go out against the current reference and the row's four
+        // threads vote afterwards; if one left the 16-bit range the reference moves and the tile pair is flagged -- the
+        // redo launch rewrites all of its P' against the final reference.
+        const int q = warp & 3, cq = warp >> 2;
+        const int sub = cq >> 1, hf = cq & 1;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const float inv_ws = p.scal[1];
@@ -285,12 +313,20 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         const float ref_limit = BF16 ? 100.f : 15.f;
         float* xg = reinterpret_cast<float*>(smem_gen + (sXg - smem_base));
         float4* xch = reinterpret_cast<float4*>(smem_gen + (sXch - smem_base));
-        uint8_t* stage_gen = smem_gen + (sStage - smem_base);
+        uint8_t* dstP = smem_gen + (sStage - smem_base) + sub * kChunkBytes;
+        uint8_t* r0 = dstP + row * 128;
         auto epi_arrive = [&](uint32_t bar) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar, 0);
         };
-        int g = 0, n = 0;                                 // S tiles, staged sub-tiles so far
+        auto row_max4 = [&](float v) {                       // maximum over the row's four threads (-> all four)
+            xg[cq * kTile + row] = v;
+            sp_quarter_sync(q);
+            const float m = fmaxf(fmaxf(xg[row], xg[kTile + row]), fmaxf(xg[2 * kTile + row], xg[3 * kTile + row]));
+            sp_quarter_sync(q);                              // xg may be rewritten
+            return m;
+        };
+        int g = 0;                                         // S tiles so far (accumulator + staging parities)
         for (int unit = unit0; unit < n_units; unit += unit_step) {
             if (skip_unit(unit)) continue;
             const int tile = p.tile_lo + unit * 2 + (int)rank;
@@ -302,90 +338,87 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             float ssum = 0.f, zb = 0.f, zl = 0.f;
             for (int j = 0; j < p.n_vchunks; ++j, ++g) {
                 const int t0 = j * 256;
-                const float* bias_t = p.bias2 + t0 + ch * 32;
-                float4 bpre[8];                               // bias of sub-tile 0, fetched while waiting for the S tile
-#pragma unroll
-                for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
+                const uint32_t tcol = tmem_base + lane_addr + (g & 1) * 256 + sub * 64 + hf * 32;
+                const float* bias_t = p.bias2 + t0 + sub * 64 + hf * 32;
+                const bool first = (j == 0 && !p.redo);
                 mbar_wait(bar_sfull(g & 1), (g >> 1) & 1);
                 tc_fence_after();
-                uint32_t acc[4][32];
-#pragma unroll
-                for (int gg = 0; gg < 4; ++gg) tmem_ld32(tmem_base + lane_addr + (g & 1) * 256 + gg * 64 + ch * 32, acc[gg]);
-                tmem_ld_wait();
-                tc_fence_before();
-                epi_arrive(bar_sempty(g & 1));
-                float lmax = -INFINITY;
-                const bool first = (j == 0 && !p.redo);
+                uint32_t acc[32];
                 if (first) {
-                    // First chunk: exact two-step -- row maximum first (acc <- logits), then the exponentials below run
-                    // against the reference it fixes.
+                    // First chunk: exact two-step -- the row maximum fixes the reference, then the rounds below re-read
+                    // the accumulator and take their exponentials against it.
+                    float lm = -INFINITY;
 #pragma unroll
-                    for (int gg = 0; gg < 4; ++gg) {
+                    for (int rd = 0; rd < 2; ++rd) {
+                        tmem_ld32(tcol + rd * 128, acc);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float4 bv = (gg == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + gg * 64) + e);
-                            const float y0 = fmaf(__uint_as_float(acc[gg][4 * e + 0]), c1, bv.x + lg_scale);
-                            const float y1 = fmaf(__uint_as_float(acc[gg][4 * e + 1]), c1, bv.y + lg_scale);
-                            const float y2 = fmaf(__uint_as_float(acc[gg][4 * e + 2]), c1, bv.z + lg_scale);
-                            const float y3 = fmaf(__uint_as_float(acc[gg][4 * e + 3]), c1, bv.w + lg_scale);
-                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                            acc[gg][4 * e + 0] = __float_as_uint(y0); acc[gg][4 * e + 1] = __float_as_uint(y1);
-                            acc[gg][4 * e + 2] = __float_as_uint(y2); acc[gg][4 * e + 3] = __float_as_uint(y3);
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
+                            lm = fmaxf(lm, fmaxf(fmaxf(fmaf(__uint_as_float(acc[4 * e + 0]), c1, bv.x), fmaf(__uint_as_float(acc[4 * e + 1]), c1, bv.y)),
+                                                 fmaxf(fmaf(__uint_as_float(acc[4 * e + 2]), c1, bv.z), fmaf(__uint_as_float(acc[4 * e + 3]), c1, bv.w))));
                         }
                     }
-                    xg[ch * kTile + row] = lmax;
-                    w_quarter_sync(q);
-                    const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
-                    mref = (rmax > -INFINITY) ? (rmax - ref_exp) : 0.f;
-                    w_quarter_sync(q);                            // xg may be rewritten
-                    lmax = -INFINITY;
+                    const float rmax = row_max4(lm);
+                    mref = (rmax > -INFINITY) ? (rmax + lg_scale - ref_exp) : 0.f;
                 }
-                // Exponentials sub-tile by sub-tile, each one staged for the TMA store as soon as it is packed (the wait for
-                // its buffer hides behind the next sub-tile's math).  Later chunks are OPTIMISTIC: values go out against the
-                // current reference and the partner warps vote afterwards; if one left the 16-bit range the reference moves
-                // and the tile pair is flagged -- the redo launch rewrites all of its P' against the final reference.
                 const float krow = lg_scale - mref;
-                const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1), nref2 = pk2(-mref, -mref);
+                const uint64_t krow2 = pk2(krow, krow), c2 = pk2(c1, c1);
                 uint64_t s01 = pk2(0.f, 0.f), s23 = s01;
-                const int cbl = p.blank - t0, clb = label - t0;   // blank / label column inside this chunk, if any
+                float lmax = -INFINITY;
 #pragma unroll
-                for (int gg = 0; gg < 4; ++gg, ++n) {
+                for (int rd = 0; rd < 2; ++rd) {
+                    float4 bv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) bv[e] = __ldg(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
+                    tmem_ld32(tcol + rd * 128, acc);
+                    tmem_ld_wait();
+                    if (rd == 1) {                            // the accumulator is free again as soon as it sits in registers
+                        tc_fence_before();
+                        epi_arrive(bar_sempty(g & 1));
+                    }
                     uint32_t pk[16];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float y0, y1, y2, y3;
-                        if (first) {
-                            unpk2(add2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), nref2), y0, y1);
-                            unpk2(add2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), nref2), y2, y3);
-                        } else {
-                            const float4 bv = (gg == 0) ? bpre[e] : __ldg(reinterpret_cast<const float4*>(bias_t + gg * 64) + e);
-                            unpk2(fma2(pk2u(acc[gg][4 * e + 0], acc[gg][4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2)), y0, y1);
-                            unpk2(fma2(pk2u(acc[gg][4 * e + 2], acc[gg][4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2)), y2, y3);
-                            lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                        }
+                        unpk2(fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(bv[e].x, bv[e].y), krow2)), y0, y1);
+                        unpk2(fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(bv[e].z, bv[e].w), krow2)), y2, y3);
+                        lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
                         const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
                         s01 = add2(s01, pk2(e0, e1));
                         s23 = add2(s23, pk2(e2, e3));
-                        acc[gg][4 * e + 0] = __float_as_uint(e0); acc[gg][4 * e + 1] = __float_as_uint(e1);
-                        acc[gg][4 * e + 2] = __float_as_uint(e2); acc[gg][4 * e + 3] = __float_as_uint(e3);
+                        acc[4 * e + 0] = __float_as_uint(y0); acc[4 * e + 1] = __float_as_uint(y1);
+                        acc[4 * e + 2] = __float_as_uint(y2); acc[4 * e + 3] = __float_as_uint(y3);
                         pk[2 * e] = pack16<BF16>(e0, e1);
                         pk[2 * e + 1] = pack16<BF16>(e2, e3);
                     }
-                    const int sbuf = n % NSB;
-                    mbar_wait(bar_pfree(sbuf), ((n / NSB) & 1) ^ 1);       // the store of sub-tile n - NSB has read the buffer
-                    uint8_t* dstP = stage_gen + sbuf * kChunkBytes;
-                    uint8_t* r0 = dstP + row * 128;
+                    // blank / label logits of this row (log2 units): acc holds the exponents y = logit + lg_scale - mref
+                    const int c0 = t0 + rd * 128 + sub * 64 + hf * 32;      // first vocabulary id of this round's 32 columns
+                    const int cbl = p.blank - c0, clb = label - c0;
+                    if (cbl >= 0 && cbl < 32) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v = (e == cbl) ? __uint_as_float(acc[e]) : v;
+                        zb = v - krow;
+                    }
+                    if (clb >= 0 && clb < 32) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v = (e == clb) ? __uint_as_float(acc[e]) : v;
+                        zl = v - krow;
+                    }
+                    // stage this round's sub-tile (the store of the previous round's has read the buffer); the blank and
+                    // label columns are left out of P' (their exact terms are added in fp32 later)
+                    mbar_wait(bar_pfree(sub), (rd & 1) ^ 1);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(r0 + (((ch * 4 + c) ^ (row & 7)) << 4)) =
+                        *reinterpret_cast<uint4*>(r0 + (((hf * 4 + c) ^ (row & 7)) << 4)) =
                             make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    // the blank and label columns are left out of P' (their exact terms are added in fp32 later)
-                    const int lo = gg * 64 + ch * 32;
-                    if (cbl >= lo && cbl < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, cbl - gg * 64)) = 0;
-                    if (clb >= lo && clb < lo + 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, clb - gg * 64)) = 0;
+                    if (cbl >= 0 && cbl < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + cbl)) = 0;
+                    if (clb >= 0 && clb < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + clb)) = 0;
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_pwritten(sbuf));
+                    if (lane == 0) mbar_arrive(bar_pwritten(sub));
                 }
                 float part;
                 {
@@ -393,61 +426,44 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     unpk2(add2(s01, s23), p0, p1);
                     part = p0 + p1;
                 }
-                {
-                    // blank / label logits (log2 units) of this row, recovered from the exponentials: once per row
-                    if (cbl >= 0 && cbl < 256 && ((cbl >> 5) & 1) == ch) {
-                        float v = 0.f;
-#pragma unroll
-                        for (int gg = 0; gg < 4; ++gg)
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) v = (gg * 64 + ch * 32 + e == cbl) ? __uint_as_float(acc[gg][e]) : v;
-                        zb = lg2f(v) + mref - lg_scale;
-                    }
-                    if (clb >= 0 && clb < 256 && ((clb >> 5) & 1) == ch) {
-                        float v = 0.f;
-#pragma unroll
-                        for (int gg = 0; gg < 4; ++gg)
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) v = (gg * 64 + ch * 32 + e == clb) ? __uint_as_float(acc[gg][e]) : v;
-                        zl = lg2f(v) + mref - lg_scale;
-                    }
-                }
-                if (!first && w_quarter_any(q, lmax > ref_limit)) {
+                if (!first && sp_quarter_any(q, lmax > ref_limit)) {
                     if (!p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;         // this pair's P' now carries mixed scales
-                    xg[ch * kTile + row] = lmax;
-                    w_quarter_sync(q);
-                    const float rmax = fmaxf(lmax, xg[(ch ^ 1) * kTile + row]);
+                    const float rmax = row_max4(lmax);
                     const float delta = (rmax > ref_limit) ? (rmax - ref_exp) : 0.f;
                     const float fsc = ex2f(-delta);
                     ssum *= fsc;
                     part *= fsc;
                     mref += delta;
-                    w_quarter_sync(q);                            // xg may be rewritten
                 }
                 ssum += part;
             }
-            // combine the two column halves of each row
-            w_epi_sync();
-            xch[ch * kTile + row] = make_float4(ssum, zb, zl, 0.f);
-            w_epi_sync();
-            const float4 o = xch[(ch ^ 1) * kTile + row];
-            w_epi_sync();
-            if (ch == 0 && valid_x) {
-                const float lse2 = mref - lg_scale + lg2f(ssum + o.x);
-                zb = ((p.blank & 63) < 32) ? zb : o.y;        // which column half owns the blank / label column
-                if (label >= 0) zl = ((label & 63) < 32) ? zl : o.z;
+            // combine the row's four column groups
+            sp_epi_sync();
+            xch[cq * kTile + row] = make_float4(ssum, zb, zl, 0.f);
+            sp_epi_sync();
+            if (cq == 0 && valid_x) {
+                const float4 o1 = xch[kTile + row], o2 = xch[2 * kTile + row], o3 = xch[3 * kTile + row];
+                const float lse2 = mref - lg_scale + lg2f((ssum + o1.x) + (o2.x + o3.x));
+                // which group owns the blank / label column: sub-tile parity (bit 6) and half (bit 5) of the column
+                const int ob = ((p.blank >> 6) & 1) * 2 + ((p.blank >> 5) & 1);
+                zb = ob == 0 ? zb : ob == 1 ? o1.y : ob == 2 ? o2.y : o3.y;
+                if (label >= 0) {
+                    const int ol = ((label >> 6) & 1) * 2 + ((label >> 5) & 1);
+                    zl = ol == 0 ? zl : ol == 1 ? o1.z : ol == 2 ? o2.z : o3.z;
+                }
                 p.lse[grow] = lse2 * kLn2;
                 p.lpb[grow] = (zb - lse2) * kLn2;
                 p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
                 p.pfac[grow] = ex2f(mref - lg_scale - lse2);
                 p.mref[grow] = mref;
             }
+            sp_epi_sync();                                   // (the next unit rewrites xch)
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == kWMmaWarp) {
+    if (warp == kSpMmaWarp) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 512);
     }
@@ -760,11 +776,11 @@ static int wide_sm_count() {
 }
 
 template <typename K, typename... Args>
-static int launch_pair(K kern, unsigned grid_x, size_t smem, cudaStream_t stream, Args... args) {
+static int launch_pair(K kern, int threads, unsigned grid_x, size_t smem, cudaStream_t stream, Args... args) {
     TTX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((grid_x + 1) & ~1u, 1, 1);
-    cfg.blockDim = dim3(kWThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -814,7 +830,7 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.flags = flags;
     const bool xs = H <= 512 && !getenv("TTX_SP_STREAM_X");        // (the switch: A/B measurement of the stationary tile)
     const size_t stg = xs ? kChunkBytes : kSpStage;
-    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 2 * kTile * 4 + 2 * kTile * 16;
+    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16;
     p.NS = 8;
     while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
     const size_t smem = (size_t)p.NS * stg + fixed;
@@ -825,10 +841,10 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
     for (int redo = 0; redo < 2; ++redo) {
         p.redo = redo;
-        int rc = xs ? (bf16 ? launch_pair(sp_kernel<true, true>, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, true>, grid, smem, stream, mx, my, mp, p))
-                    : (bf16 ? launch_pair(sp_kernel<true, false>, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, false>, grid, smem, stream, mx, my, mp, p));
+        int rc = xs ? (bf16 ? launch_pair(sp_kernel<true, true>, kSpThreads, grid, smem, stream, mx, my, mp, p)
+                            : launch_pair(sp_kernel<false, true>, kSpThreads, grid, smem, stream, mx, my, mp, p))
+                    : (bf16 ? launch_pair(sp_kernel<true, false>, kSpThreads, grid, smem, stream, mx, my, mp, p)
+                            : launch_pair(sp_kernel<false, false>, kSpThreads, grid, smem, stream, mx, my, mp, p));
         if (rc) return rc;
     }
     return 0;
@@ -847,8 +863,8 @@ int launch_wide_pw(const void* pstore, uint64_t store_rows, const void* w16t, in
     if (int rc = make_matrix_map(&mb, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, kTile)) return rc;
     const int units = ((tile_cnt + 1) / 2) * p.n_hb;
     const unsigned grid = 2u * (unsigned)max(1, min(units, wide_sm_count() / 2));
-    return bf16 ? launch_pair(kp_kernel<KP_PW, true>, grid, smem, stream, mp, mb, mb, p)
-                : launch_pair(kp_kernel<KP_PW, false>, grid, smem, stream, mp, mb, mb, p);
+    return bf16 ? launch_pair(kp_kernel<KP_PW, true>, kWThreads, grid, smem, stream, mp, mb, mb, p)
+                : launch_pair(kp_kernel<KP_PW, false>, kWThreads, grid, smem, stream, mp, mb, mb, p);
 }
 
 // dW += gmax / kKeptUp * P'^T . As over the lattice rows of tiles [tile_lo, tile_lo + tile_cnt), db likewise (dense part)
@@ -881,8 +897,8 @@ int launch_wide_dw(const void* pstore, uint64_t store_rows, const void* a16st, u
     if (int rc = make_matrix_map(&mb, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, kTile)) return rc;
     if (int rc = make_matrix_map(&ms, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, 8)) return rc;
     const unsigned grid = 2u * (unsigned)max(1, min(n_vq * p.n_hb * p.splits, pairs));
-    return bf16 ? launch_pair(kp_kernel<KP_DW, true>, grid, smem, stream, mp, mb, ms, p)
-                : launch_pair(kp_kernel<KP_DW, false>, grid, smem, stream, mp, mb, ms, p);
+    return bf16 ? launch_pair(kp_kernel<KP_DW, true>, kWThreads, grid, smem, stream, mp, mb, ms, p)
+                : launch_pair(kp_kernel<KP_DW, false>, kWThreads, grid, smem, stream, mp, mb, ms, p);
 }
 
 }  // namespace ttx
