@@ -33,6 +33,7 @@ struct WideParams {
     int store_rows;          // rows of the P' matrix; its row 0 is lattice row tile_lo * 128
     int redo;                // sp: only tile pairs whose flag is set, against the stored final reference
     int n_hb;                // kp: 512-column blocks of H
+    int dbg;                 // timing experiments (TTX_WIDE_DBG): 1 = no S-pass MMAs, 2 = no epilogue math / staging
     int splits;              // kp<DW>: lattice-row splits
     const int* meta;
     const float* bias2;
@@ -63,7 +64,7 @@ constexpr int kSpEpiWarps = 16;
 constexpr int kSpEpiThreads = kSpEpiWarps * 32;
 constexpr int kSpThreads = kSpEpiThreads + 128;
 constexpr int kSpProducerWarp = kSpEpiWarps, kSpMmaWarp = kSpEpiWarps + 1, kSpWatchWarp = kSpEpiWarps + 2;
-constexpr int kSpCtrlRegs = 40, kSpEpiRegs = 112;      // 20 warps x 96 = 4 x 40 + 16 x 110
+// (640 threads: the compiler's budget is 96 registers per thread for every role, so there is nothing for setmaxnreg to move)
 
 __device__ __forceinline__ void w_epi_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kWEpiThreads) : "memory");
@@ -159,6 +160,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sXg = sTmemPtr + 16;                    // [4][128] floats: row maxima of the four column groups
     const uint32_t sXch = sXg + 4 * kTile * 4;             // [4][128] float4: per-row statistics of the four column groups
+    const uint32_t sBias = sXch + 4 * kTile * 16;          // [4 lane quarters][2][256] floats: bias2 of this / the next chunk
     uint8_t* smem_gen = smem_raw;
     auto bar_full = [&](int s) { return sBar + 8 * s; };
     auto bar_empty = [&](int s) { return sBar + 8 * (8 + s); };
@@ -199,7 +201,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (sTmemPtr - smem_base));
 
     if (warp >= kSpEpiWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSpCtrlRegs));
         if (warp == kSpProducerWarp && lane == 0) {
             // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
             Ring r;
@@ -254,7 +255,9 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 for (int j = 0; j < p.n_vchunks; ++j)
                     for (int gg = 0; gg < 4; ++gg, ++n) {           // sub-tile n goes through buffer n % NSB
                         const int b = n % NSB;
+                        if (p.dbg & 2) continue;
                         mbar_wait(bar_pwritten(b), (n / NSB) & 1);
+                        if (!(p.dbg & 4))
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + b * kChunkBytes), "r"(0),
                                        "r"((j * 4 + gg) * p.store_rows + srow0)
@@ -283,8 +286,10 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         tc_fence_after();
                         const uint32_t a = XS ? xlo + c * (kChunkBytes >> 4) : rlo + stage * (STG >> 4);
                         const uint32_t b = XS ? rlo + stage * (STG >> 4) : a + (kChunkBytes >> 4);
+                        if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
+                            for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
+                        }
                         umma_commit_pair(bar_empty(stage));
                         if (++stage == p.NS) stage = 0;
                     }
@@ -294,7 +299,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSpEpiRegs));
         // ======================================================= epilogue: thread = (row, column group cq)
         // Sixteen warps, four per TMEM lane quarter.  A 256-column S tile is done in two ROUNDS of two 64-column
         // sub-tiles; in a round thread (row, cq) owns 32 columns: sub-tile rd * 2 + (cq >> 1), half cq & 1 -- read-out,
@@ -326,7 +330,16 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             sp_quarter_sync(q);                              // xg may be rewritten
             return m;
         };
-        int g = 0;                                         // S tiles so far (accumulator + staging parities)
+        // bias2 of a chunk comes from shared memory: with 227 KB of it configured there is no L1 left, and a global load
+        // per use costs an L2 round trip each time (ncu: the largest stall of the epilogue).  Each lane quarter keeps its
+        // own double-buffered copy, filled one chunk ahead by its 128 threads (two floats each) and published by the
+        // quarter barrier that ends every tile.
+        float* qbias = reinterpret_cast<float*>(smem_gen + (sBias - smem_base)) + q * 512;
+        const int bt = cq * 32 + lane;                     // this thread's two floats of a chunk: bt, bt + 128
+        qbias[bt] = __ldg(p.bias2 + bt);
+        qbias[bt + 128] = __ldg(p.bias2 + bt + 128);
+        sp_quarter_sync(q);
+        int g = 0;                                         // S tiles so far (accumulator + staging + bias parities)
         for (int unit = unit0; unit < n_units; unit += unit_step) {
             if (skip_unit(unit)) continue;
             const int tile = p.tile_lo + unit * 2 + (int)rank;
@@ -339,8 +352,11 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             for (int j = 0; j < p.n_vchunks; ++j, ++g) {
                 const int t0 = j * 256;
                 const uint32_t tcol = tmem_base + lane_addr + (g & 1) * 256 + sub * 64 + hf * 32;
-                const float* bias_t = p.bias2 + t0 + sub * 64 + hf * 32;
+                const float* bias_t = qbias + (g & 1) * 256 + sub * 64 + hf * 32;
                 const bool first = (j == 0 && !p.redo);
+                // next tile's chunk (the next unit starts at chunk 0 again): fetched now, stored at the end of this tile
+                const int jn = (j + 1 == p.n_vchunks) ? 0 : j + 1;
+                const float nb0 = __ldg(p.bias2 + jn * 256 + bt), nb1 = __ldg(p.bias2 + jn * 256 + bt + 128);
                 mbar_wait(bar_sfull(g & 1), (g >> 1) & 1);
                 tc_fence_after();
                 uint32_t acc[32];
@@ -354,7 +370,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
+                            const float4 bv = *(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
                             lm = fmaxf(lm, fmaxf(fmaxf(fmaf(__uint_as_float(acc[4 * e + 0]), c1, bv.x), fmaf(__uint_as_float(acc[4 * e + 1]), c1, bv.y)),
                                                  fmaxf(fmaf(__uint_as_float(acc[4 * e + 2]), c1, bv.z), fmaf(__uint_as_float(acc[4 * e + 3]), c1, bv.w))));
                         }
@@ -368,9 +384,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 float lmax = -INFINITY;
 #pragma unroll
                 for (int rd = 0; rd < 2; ++rd) {
-                    float4 bv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) bv[e] = __ldg(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
                     tmem_ld32(tcol + rd * 128, acc);
                     tmem_ld_wait();
                     if (rd == 1) {                            // the accumulator is free again as soon as it sits in registers
@@ -378,13 +391,16 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         epi_arrive(bar_sempty(g & 1));
                     }
                     uint32_t pk[16];
+                    if (p.dbg & 2) continue;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float y0, y1, y2, y3;
-                        unpk2(fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(bv[e].x, bv[e].y), krow2)), y0, y1);
-                        unpk2(fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(bv[e].z, bv[e].w), krow2)), y2, y3);
+                        const float4 bv = *(reinterpret_cast<const float4*>(bias_t + rd * 128) + e);
+                        unpk2(fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2)), y0, y1);
+                        unpk2(fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2)), y2, y3);
                         lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                        const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
+                        const bool nomufu = p.dbg & 8;
+                        const float e0 = nomufu ? y0 : ex2f(y0), e1 = nomufu ? y1 : ex2f(y1), e2 = nomufu ? y2 : ex2f(y2), e3 = nomufu ? y3 : ex2f(y3);
                         s01 = add2(s01, pk2(e0, e1));
                         s23 = add2(s23, pk2(e2, e3));
                         acc[4 * e + 0] = __float_as_uint(y0); acc[4 * e + 1] = __float_as_uint(y1);
@@ -426,6 +442,9 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     unpk2(add2(s01, s23), p0, p1);
                     part = p0 + p1;
                 }
+                qbias[((g + 1) & 1) * 256 + bt] = nb0;
+                qbias[((g + 1) & 1) * 256 + bt + 128] = nb1;
+                if (first) sp_quarter_sync(q);              // (publishes the next chunk's bias; later chunks: the vote below)
                 if (!first && sp_quarter_any(q, lmax > ref_limit)) {
                     if (!p.redo) p.flags[(p.tile_lo >> 1) + unit] = 1;         // this pair's P' now carries mixed scales
                     const float rmax = row_max4(lmax);
@@ -828,9 +847,10 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.mref = mref;
     p.pstore = static_cast<uint16_t*>(pstore);
     p.flags = flags;
+    p.dbg = getenv("TTX_WIDE_DBG") ? atoi(getenv("TTX_WIDE_DBG")) : 0;
     const bool xs = H <= 512 && !getenv("TTX_SP_STREAM_X");        // (the switch: A/B measurement of the stationary tile)
     const size_t stg = xs ? kChunkBytes : kSpStage;
-    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16;
+    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16 + 4 * 512 * 4;
     p.NS = 8;
     while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
     const size_t smem = (size_t)p.NS * stg + fixed;
