@@ -28,10 +28,10 @@ WORKLOADS = {
                      desc="B=32 T=400 U=40 V=4232 D=512 H=256 fp32 (experiment)"),
     # BASELINE.json configs[0]: aishell.yaml joint (tt JointNet 1024 -> 1024 -> V), the reference's CPU-runnable case
     "cfg1": dict(B=4, T=200, U=30, V=4232, D=512, H=1024, joint="tt", ragged=False,
-                 desc="aishell.yaml joint B=4 T=200 U=30 V=4232 D=512 H=1024 fp32 (chunked wide-joint path)"),
+                 desc="aishell.yaml joint B=4 T=200 U=30 V=4232 D=512 H=1024 fp32"),
     # BASELINE.json configs[2]: joint_streaming.yaml joint dims (H=2048, V=6485) at the global batch of 64
     "cfg3": dict(B=64, T=410, U=42, V=6485, D=512, H=2048, joint="tt", ragged=False,
-                 desc="joint_streaming.yaml joint B=64 T=410 U=42 V=6485 D=512 H=2048 fp32 (chunked wide-joint path)"),
+                 desc="joint_streaming.yaml joint B=64 T=410 U=42 V=6485 D=512 H=2048 fp32"),
     # BASELINE.json configs[0] shapes but with a fused-path joint width (parity-sized smoke workload)
     "small": dict(B=4, T=200, U=30, V=4232, D=512, H=512, joint="espnet", ragged=False,
                   desc="B=4 T=200 U=30 V=4232 D=512 H=512 fp32"),
@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--logits", default="init", choices=["init", "peaked"],
                     help="peaked: trained-like output layer (larger weights, boosted blank / label biases)")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel table to stderr")
+    ap.add_argument("--route", default="default", choices=["default", "fused", "chunked"],
+                    help="A/B runs: fused = the recomputing kernels at H = 512 (nothing V-wide in HBM), chunked = library GEMMs")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -228,6 +230,8 @@ def main():
 
     import transformer_transducer_b200 as ttb
     from transformer_transducer_b200 import functional as F
+    if args.route != "default":
+        F.ROUTE = args.route
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -362,7 +366,7 @@ def main():
                  ", f32 accumulate/softmax, f64 lattice (%s variant)" % ("bf16-input" if w.get("bf16") else "fp32"),
         "data": "synthetic",
         "config": {"workload": w["desc"], "global_batch": world * w["B"], "parallelism": "dp%d" % world,
-                   "logits": args.logits,
+                   "logits": args.logits, "route": args.route,
                    "l2": "per-step working set (A16 %.2f GB + dA %.2f GB) exceeds the 126 MB L2; no explicit flush" %
                          (M * w["H"] * 2 / 1e9, M * w["H"] * 4 / 1e9)},
         "e2e": {"value": world * w["B"] * args.steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d,

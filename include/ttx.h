@@ -119,8 +119,9 @@ int ttx_transpose16(const void* in, void* out, int rows, int cols, const int32_t
 int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const void* w16t, const float* bias2,
                    const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
-                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
-                   void* stream);
+                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits,
+                   void* workspace /* NULL or ttx_joint_workspace_bytes(1, ...) bytes, see ttx_joint_fwd_grad */,
+                   int64_t workspace_bytes, int device, void* stream);
 
 /* d_eproj[b,t,:] = sum_u d_act * (1 - tanh^2), d_pproj[b,u,:] = sum_t d_act * (1 - tanh^2); both fully
  * overwritten (zeros outside the ragged region). */
@@ -134,49 +135,24 @@ int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* ppr
  * dL/dA = gmax * w * (ew + (p_b - rb) W_out[blank] + (p_l - rl) W_out[label]) from the lattice coefficients
  * (rowmeta of ttx_grad_coeffs) on the fly.  H in {128, 256, 512} (ttx_fwd_grad_supported_h); needs w16t. */
 int ttx_fwd_grad_supported_h(int H);
+/* workspace: NULL, or ttx_joint_workspace_bytes(0, ...) bytes of caller-owned scratch (H = 512: the launch stores the
+ * 16-bit softmax numerators of the tile pair a CTA pair is working on there and replays them for the second half of the
+ * joint columns instead of recomputing the projection; bounded by the device's CTA count, independent of B, T, U). */
 int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
                        const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
-                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream);
-/* Same launch, but the softmax numerators P' it computes anyway (16 bit, blank / label entries zero) are KEPT in the
- * caller's matrix pstore (rows_ub x Vpad 16-bit values, rows_ub = 128 * n_tiles_ub, Vpad = V rounded up to 256; stored
- * in 64-column blocks, [Vpad / 64][rows_ub][64], so that every tile the kernels move is contiguous) instead of a bounded
- * scratch area, with pfac (rows): softmax(row, v) = pstore[row, v] * pfac[row].  pflags: 16384 int32, zeroed by the
- * caller; word 16383 != 0 afterwards means some row's running reference moved and the matrix must not be used.
- * H = 512 only.  The weight gradient is then one product on the kept matrix (ttx_weight_grad_kept) -- no second
- * projection pass, no exponentials.  Costs rows_ub * Vpad * 2 bytes between forward and backward. */
-int ttx_joint_fwd_grad_keep(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
-                            const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
-                            int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* pstore,
-                            int32_t* pflags, float* pfac, int device, void* stream);
-/* d_w_out += dL/dW_out, d_b_out += the dense part of dL/db_out (as ttx_joint_grad with d_act = NULL) from the kept
- * matrix: scales A16^T by w * pfac into a16st (scratch owned by the caller: (H + 16) x rows_ub 16-bit values followed by
- * 64 x (H + 4) floats), adds the exact
- * blank / label terms, then dW += P'^T . As on the tensor cores.  If pflags[16383] != 0 those launches are no-ops and
- * the recomputing kernel of ttx_joint_grad runs instead (decided on the device, no host synchronisation). */
-int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float* pfac, const void* a16, const void* w16,
-                         const void* a16t, const void* w16t, void* a16st, const float* bias2, const float* scal,
-                         const int32_t* row_label, const int32_t* meta, const void* rowmeta, const float* lp_blank,
-                         const float* lp_label, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, int sparse_terms, float* d_w_out,
-                         float* d_b_out, int device, void* stream);
-/* ttx_reduce_act_grad_ew that also adds the exact blank / label terms of the kept-P' weight gradient (the rows of
- * d_w_out / entries of d_b_out that the kept matrix leaves out) in the same pass over the lattice cells: call
- * ttx_weight_grad_kept with sparse_terms = 0 first (it fills a16st), then this.  With sparse_terms = 1
- * ttx_weight_grad_kept adds them itself (a separate kernel; for steps without activation gradients). */
-int ttx_reduce_act_grad_ew_kept(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
-                                const float* scal, int blank, const float* eproj, const float* pproj,
-                                const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T,
-                                int U1, int H, float* d_eproj, float* d_pproj, const int32_t* pflags,
-                                const float* lp_blank, const float* lp_label, void* a16st, int64_t n_tiles_ub,
-                                float* d_w_out, float* d_b_out, int device, void* stream);
+                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* workspace,
+                       int64_t workspace_bytes, int device, void* stream);
+/* Scratch the fused launches can use: which = 0 ttx_joint_fwd_grad, 1 = ttx_joint_grad with d_w_out.  0 = none. */
+int64_t ttx_joint_workspace_bytes(int which, int64_t n_tiles_ub, int H, int V, int device);
 int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
                            const float* scal, int blank, const float* eproj, const float* pproj,
                            const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
                            int H, float* d_eproj, float* d_pproj, int device, void* stream);
 
 /* ---- Wide joints (H a multiple of 512 up to 4096: aishell.yaml's 1024, joint_streaming.yaml's 2048; tt/model.py:35-37).
- * The same three contractions as three streamed tcgen05 products around the 16-bit softmax numerators P' (layout as
- * pstore above: [Vpad / 64][store_rows][64]).  Every call works on lattice tiles [tile_lo, tile_lo + tile_cnt) (tile_lo
+ * The same three contractions as three streamed tcgen05 products around the 16-bit softmax numerators P' (store_rows x
+ * Vpad values, Vpad = V rounded up to 256, in 64-column blocks [Vpad / 64][store_rows][64] so that every tile the kernels
+ * move is contiguous; blank / label entries zero).  Every call works on lattice tiles [tile_lo, tile_lo + tile_cnt) (tile_lo
  * even; clipped on the device to the tiles in use) and addresses the P' matrix relative to tile_lo: a caller that can
  * hold P' for the whole batch passes (0, n_tiles_ub) and keeps it for the backward; otherwise it walks the batch in
  * chunks with one chunk-sized matrix and calls ttx_wide_sp again in the backward.
@@ -187,7 +163,7 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
  *   ttx_wide_pw   ew (rows, H) fp32 = P' . W16 * pfac / w_scale  (as ttx_joint_fwd_grad's ew)
  *   ttx_wide_dw   d_w_out += P'^T . As, d_b_out += dense part, As = a16st from ttx_kept_prepare.
  *   ttx_kept_prepare  a16st = scaled A16^T ((H + 16) x rows_ub 16-bit values + 64 x (H + 4) floats), and the exact
- *                 blank / label terms of d_w_out / d_b_out (pflags: 16384 zero words). */
+ *                 blank / label terms of d_w_out / d_b_out. */
 int ttx_wide_supported_h(int H);
 int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
                 const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
@@ -201,9 +177,9 @@ int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const
                 int device, void* stream);
 int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
                      const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
-                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, const int32_t* pflags, int B,
-                     int T, int U1, int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out,
-                     float* d_b_out, int device, void* stream);
+                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                     int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,
+                     int device, void* stream);
 
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

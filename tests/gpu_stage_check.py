@@ -113,8 +113,11 @@ def run(stage, B, T, U, V, H):
         tol = 2e-5
     elif stage == "fg":
         ew = f32(rows * H)
+        ws_n = int(lib.ttx_joint_workspace_bytes(0, ntub, H, V, 0))
+        ws = torch.empty(max(ws_n, 1), dtype=torch.uint8, device=dev)
         _lib.check(lib.ttx_joint_fwd_grad(_p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(meta), ntub,
-                                          H, V, 0, 0, _p(lse), _p(lpb), _p(lpl), _p(ew), 0, st), "fwd_grad")
+                                          H, V, 0, 0, _p(lse), _p(lpb), _p(lpl), _p(ew), _p(ws) if ws_n else None, ws_n, 0,
+                                          st), "fwd_grad")
         torch.cuda.synchronize()
         mm = m
         tol = 2e-5
@@ -230,7 +233,7 @@ def run(stage, B, T, U, V, H):
     _lib.check(lib.ttx_joint_grad(_p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(meta), _p(rowmeta), ntub, H, V,
                                   0, 0, _p(d_act) if which in ("both", "da") else None,
                                   _p(dW) if which in ("both", "dw") else None,
-                                  _p(db) if which in ("both", "dw") else None, splits, 0, st), "joint_grad")
+                                  _p(db) if which in ("both", "dw") else None, splits, None, 0, 0, st), "joint_grad")
     torch.cuda.synchronize()
     if which in ("both", "da"):
         dA_model = torch.full((rows, H), float("nan"), dtype=torch.float64)

@@ -44,26 +44,28 @@ def test_c_abi_argument_errors_without_gpu():
     assert rc == 1
 
 
-def test_kept_matrix_budget_and_new_entry_points_reject_bad_arguments(monkeypatch):
-    """Host logic of the kept-P' weight gradient: the 16-bit softmax-numerator matrix is kept only for H = 512, within
-    TTX_KEEP_GB and 16383 tile pairs (the flag words); the two C entry points check their arguments before any launch."""
-    from types import SimpleNamespace
+def test_kept_matrix_chunking_and_entry_points_reject_bad_arguments():
+    """Host logic of the streamed products: the 16-bit softmax-numerator matrix covers the batch when it fits the budget
+    (one range, kept for the backward), otherwise even-aligned tile ranges of at least one tile pair; the C entry points
+    check their arguments before any launch."""
     from transformer_transducer_b200 import functional as F
-    plan = SimpleNamespace(rows=524800, ntub=4100)                    # cfg2: 4.57 GB
-    assert F._keep_fits(plan, 512, 4352, None)
-    assert not F._keep_fits(plan, 256, 4352, None)
-    monkeypatch.setenv("TTX_KEEP_GB", "4")
-    assert not F._keep_fits(plan, 512, 4352, None)
-    monkeypatch.setenv("TTX_KEEP_GB", "0")
-    assert not F._keep_fits(plan, 512, 4352, None)
-    monkeypatch.delenv("TTX_KEEP_GB")
-    assert not F._keep_fits(SimpleNamespace(rows=128 * 40000, ntub=40000), 512, 256, None)   # too many tile pairs
+    assert F._chunk_ranges(4100, 4352, 32 * 2**30) == [(0, 4100)]                   # cfg2: 4.57 GB
+    r = F._chunk_ranges(4100, 4352, 1 * 2**30)
+    assert r[0] == (0, 962) and all(t0 % 2 == 0 for t0, _ in r) and sum(n for _, n in r) == 4100
+    assert F._chunk_ranges(5, 4352, 0.0) == [(0, 2), (2, 2), (4, 1)]
     lib = _lib.get()
     null = ctypes.c_void_p(0)
-    rc = lib.ttx_joint_fwd_grad_keep(*([null] * 7), 1, 512, 10, 0, 0, *([null] * 7), 0, null)
+    rc = lib.ttx_joint_fwd_grad(*([null] * 7), 1, 512, 10, 0, 0, *([null] * 5), 0, 0, null)
     assert rc == 1 and b"null pointer" in lib.ttx_last_error()
-    rc = lib.ttx_weight_grad_kept(*([null] * 17), 1, 1, 1, 1, 512, 10, 0, 0, 1, null, null, 0, null)
+    rc = lib.ttx_wide_sp(*([null] * 6), 4, 0, 4, 512, 10, 0, 0, *([null] * 6), 512, null, 0, null)
     assert rc == 1 and b"null pointer" in lib.ttx_last_error()
+    x = ctypes.c_void_p(256)                                                          # never dereferenced: checks come first
+    rc = lib.ttx_wide_pw(x, 512, x, x, x, x, 4, 1, 4, 512, 10, 0, x, 0, null)           # odd tile_lo
+    assert rc == 1 and b"tile_lo must be even" in lib.ttx_last_error()
+    rc = lib.ttx_wide_dw(x, 256, x, x, x, 4, 0, 4, 512, 10, 0, x, x, 0, null)           # matrix smaller than the range
+    assert rc == 1 and b"bad tile range" in lib.ttx_last_error()
+    rc = lib.ttx_wide_dw(x, 512, x, x, x, 4, 0, 4, 768, 10, 0, x, x, 0, null)
+    assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
 def test_warprnnt_pytorch_surface():

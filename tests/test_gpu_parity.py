@@ -308,12 +308,17 @@ def test_wide_joint_tcgen05_path_matches_oracle(H, V, keep, monkeypatch):
     assert calls, "the wide tcgen05 path did not run"
 
 
-def test_wide_path_at_h512_matches_oracle(monkeypatch):
-    """The streamed products are a second implementation of H = 512 (TTX_WIDE=1): same tolerance as the fused kernel."""
-    monkeypatch.setenv("TTX_WIDE", "1")
+def test_wide_path_is_the_default_at_h512_and_matches_oracle(monkeypatch):
+    """H = 512 takes the streamed products around the kept P' by default (the fused recomputing kernels are the
+    memory-bounded alternative, see test_kernel_variants_agree_with_oracle)."""
+    from transformer_transducer_b200 import functional as Fn
+    calls = []
+    orig = Fn.WideJointRNNT.apply
+    monkeypatch.setattr(Fn.WideJointRNNT, "apply", lambda *a: (calls.append(1), orig(*a))[1])
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)
     errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))
     _check(errs)
+    assert calls, "the wide tcgen05 path did not run"
 
 
 def test_odd_wide_width_takes_library_gemm_fallback_and_matches_oracle(monkeypatch):
@@ -347,9 +352,10 @@ def test_unsupported_width_uses_dense_entry_and_matches_oracle():
         assert rel(a.grad, b.grad) < GRAD_TOL, n
 
 
-@pytest.mark.parametrize("H,keep", [(256, "32"), (512, "32"), (512, "0")])   # 512: two slabs; kept P' / recompute
-def test_bf16_input_variant_stated_tolerance(H, keep, monkeypatch):
-    monkeypatch.setenv("TTX_KEEP_GB", keep)
+@pytest.mark.parametrize("H,route", [(256, None), (512, None), (512, "fused")])   # fused kernels / kept P' / fused at 512
+def test_bf16_input_variant_stated_tolerance(H, route, monkeypatch):
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setattr(Fn, "ROUTE", route)
     case = _espnet_case(2, 40, 8, 500, 64, H, [40, 31], [8, 5], seed=9)
     errs, (_, _, got) = _run_pair(*case, dtype=torch.bfloat16)
     _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
@@ -363,35 +369,41 @@ def test_c_abi_rejects_unsupported_width_with_message():
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
-@pytest.mark.parametrize("env", [{"TTX_CG": "1"}, {"TTX_BWD_V3": "0"}, {"TTX_NO_FWD_GRAD": "1"},
-                                 {"TTX_REPLAY": "0"}, {"TTX_DW_CHUNKS": "2"}, {"TTX_KEEP_GB": "0"},
-                                 {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2"},
-                                 {"TTX_KEEP_GB": "0", "TTX_DW_CHUNKS": "2", "TTX_REPLAY": "0"},
-                                 {"TTX_SPARSE_FUSED": "1"}, {"TTX_REDUCE_FUSED": "0"}, {}])
-def test_kernel_variants_agree_with_oracle(env, monkeypatch):
-    """The single-CTA kernels (TTX_CG=1), the generic pair backward (TTX_BWD_V3=0), the separate activation-gradient
-    kernel (TTX_NO_FWD_GRAD=1), the forward+gradient kernel without its P' replay (TTX_REPLAY=0), the weight gradient cut into several
-    lattice-row splits with a short last one (TTX_DW_CHUNKS=2: 2 + 2 + 1 stream chunks), the recomputing weight gradient
-    (TTX_KEEP_GB=0: nothing kept between forward and backward; with and without replay), the exact blank / label terms
-    of the kept-P' weight gradient folded into the activation-gradient reduction (TTX_SPARSE_FUSED=1), the two-kernel activation-gradient
-    reductions (TTX_REDUCE_FUSED=0) and the default kernels
-    (forward+gradient launch that keeps P', weight gradient as one product on it) all meet the tolerance on a batch
-    with an odd number of lattice tiles (the pad tile of the last pair)."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+@pytest.mark.parametrize("variant", ["wide", "wide-chunked", "fused", "fused-no-replay", "fused-separate-dA", "generic",
+                                     "chunked"])
+def test_kernel_variants_agree_with_oracle(variant, monkeypatch):
+    """Every route of H = 512 meets the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last
+    pair) and a negative grad_output: the default (streamed products around the kept P'); the same with a budget of one
+    tile pair (several chunks, P' recomputed in the backward); the fused recomputing kernels with their bounded P' replay
+    workspace, without it, and with the separate activation-gradient launch; the generic single-CTA backward kernels
+    (no transposed operand copies: what H = 64 / 192 / 384 run); the library-GEMM chunked fallback."""
+    from transformer_transducer_b200 import functional as Fn
+    if variant == "wide-chunked":
+        monkeypatch.setenv("TTX_KEEP_GB", "1e-9")
+    elif variant == "chunked":
+        monkeypatch.setattr(Fn, "ROUTE", "chunked")
+    elif variant != "wide":
+        monkeypatch.setattr(Fn, "ROUTE", "fused")
+        if variant == "fused-no-replay":
+            monkeypatch.setattr(Fn.FusedJointRNNT, "REPLAY", False)
+        if variant in ("fused-separate-dA", "generic"):
+            monkeypatch.setattr(Fn.FusedJointRNNT, "SEPARATE_ACT_GRAD", True)
+        if variant == "generic":
+            monkeypatch.setattr(Fn.FusedJointRNNT, "PAIR_WIDTHS", ())
     case = _espnet_case(3, 47, 10, 1100, 64, 512, [47, 31, 6], [10, 8, 1], seed=21)     # 5 + 3 + 1 = 9 tiles (odd)
-    errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))                 # a negative grad_output too
+    errs, _ = _run_pair(*case, weights=torch.tensor([1.0, -0.5, 2.0]))
     _check(errs)
 
 
 # ----------------------------------------------------------------------------- BASELINE.json configs at their real dims
-@pytest.mark.parametrize("keep", ["32", "0"])           # kept softmax numerators / bounded scratch + recompute
-def test_cfg2_full_lattice_vs_oracle(keep, monkeypatch):
+@pytest.mark.parametrize("route", [None, "fused"])      # kept softmax numerators / bounded scratch + recompute
+def test_cfg2_full_lattice_vs_oracle(route, monkeypatch):
     """configs[1] with its full lattice (T=400, U=40, V=4232, D=H=512), B=2 so the CPU oracle finishes in seconds:
     129 + 99 = 228 lattice tiles = 114 tile pairs, more than the 74 CTA pairs of a B200, so the persistent kernels'
     multi-unit loop (next unit's operands behind the previous read-out, barrier parities across units) is checked
     against the oracle, with and without the kept P' matrix."""
-    monkeypatch.setenv("TTX_KEEP_GB", keep)
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setattr(Fn, "ROUTE", route)
     case = _espnet_case(2, 400, 40, 4232, 512, 512, [400, 371], [40, 33], seed=11)
     errs, (e1, p1, _) = _run_pair(*case, weights=torch.tensor([1.0, 0.5]))
     _check(errs)
@@ -443,13 +455,14 @@ def test_cfg5_ragged_bf16_real_lengths_vs_oracle():
     assert e1.grad[2, 50:].abs().max() == 0 and p1.grad[2, 6:].abs().max() == 0
 
 
-@pytest.mark.parametrize("keep", ["32", "0"])
-def test_trained_like_distribution(keep, monkeypatch):
+@pytest.mark.parametrize("route", [None, "fused"])
+def test_trained_like_distribution(route, monkeypatch):
     """Beyond random initialisation: heavy-tailed output weights (a few |w| far above the median), posteriors peaked
     in EVERY vocabulary tile (the row maximum sits in a late tile for most rows, so the forward's running reference
     moves after its first tile), label logits boosted like a trained model's, and grad_output spanning six orders of
     magnitude between utterances (the gmax normalisation of the 16-bit gradient operand)."""
-    monkeypatch.setenv("TTX_KEEP_GB", keep)
+    from transformer_transducer_b200 import functional as Fn
+    monkeypatch.setattr(Fn, "ROUTE", route)
     ref, mine, enc, pred, labels, al, ll = _espnet_case(3, 48, 9, 2100, 64, 512, [48, 40, 21], [9, 7, 3], seed=14)
     g = torch.Generator().manual_seed(15)
     with torch.no_grad():

@@ -30,7 +30,7 @@ for s in $STAGES; do
       TTX_BWD=both run bwd 2 40 6 300 256
       TTX_BWD=both run bwd 2 40 6 300 384
       TTX_BWD=both TTX_SPLITS=3 run bwd 3 50 9 1000 512
-      TTX_CG=1 TTX_BWD=both TTX_SPLITS=3 run bwd 3 50 9 1000 512 ;;
+      TTX_BWD=both TTX_SPLITS=3 run bwd 3 50 9 1000 384 ;;
   esac
 done
 grep -E "^===|STAGE|FAIL|Error|error|timed out" $LOG | tail -60

@@ -13,8 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libttx.so")
 SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 _lock = threading.Lock()
 _lib = None
@@ -40,13 +39,8 @@ _PROTOS = {
     "ttx_transpose16": [c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_fwd_grad_supported_h": [c_i32],
     "ttx_joint_fwd_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
-                           c_i32, c_p],
-    "ttx_joint_fwd_grad_keep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
-                                c_p, c_p, c_p, c_i32, c_p],
-    "ttx_weight_grad_kept": [c_p] * 17 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32,
-                             c_p],
-    "ttx_reduce_act_grad_ew_kept": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
-                                    c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_p],
+                           c_p, c_i64, c_i32, c_p],
+    "ttx_joint_workspace_bytes": [c_i32, c_i64, c_i32, c_i32, c_i32],
     "ttx_reduce_act_grad_ew": [c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32,
                                c_p, c_p, c_i32, c_p],
     "ttx_wide_supported_h": [c_i32],
@@ -54,18 +48,18 @@ _PROTOS = {
                     c_p, c_i64, c_p, c_i32, c_p],
     "ttx_wide_pw": [c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_wide_dw": [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
-    "ttx_kept_prepare": [c_p] * 12 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_kept_prepare": [c_p] * 11 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_grad": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p,
-                       c_i32, c_i32, c_p],
+                       c_i32, c_p, c_i64, c_i32, c_p],
     "ttx_reduce_act_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
 }
 _RESTYPES = {"ttx_last_error": ctypes.c_char_p, "ttx_tiles_upper_bound": c_i64, "ttx_meta_ints": c_i64,
-             "ttx_lattice_elems_upper_bound": c_i64}
+             "ttx_lattice_elems_upper_bound": c_i64, "ttx_joint_workspace_bytes": c_i64}
 EXPORTS = tuple(_PROTOS)
 
 
@@ -81,8 +75,15 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
-    subprocess.check_call(cmd, cwd=CSRC)
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    objs = [os.path.join(LIB_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    procs = [subprocess.Popen(["nvcc"] + flags + ["-c", "-o", o, s], cwd=CSRC) for s, o in zip(srcs, objs)]   # in parallel
+    failed = [s for s, p in zip(srcs, procs) if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, "nvcc -c " + " ".join(failed))
+    subprocess.check_call(["nvcc"] + flags + ["-shared", "-o", tmp] + objs, cwd=CSRC)
+    for o in objs:
+        os.remove(o)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -30,16 +30,12 @@ int launch_reduce(const float*, const float4*, const int*, const float*, const f
                   const int*, const int*, const int*, int, int, int, int, float*, float*, cudaStream_t);
 bool fwd_grad_supported_h(int H);
 int launch_joint_fwd_grad(const void*, const void*, const void*, uint64_t, int, int, int, int, bool, const int*,
-                          const float*, const float*, const int*, int, float*, float*, float*, float*, cudaStream_t,
-                          void*, int*, float*);
+                          const float*, const float*, const int*, int, float*, float*, float*, float*, void*, size_t,
+                          cudaStream_t);
+size_t joint_workspace_bytes(int which, int n_tiles_ub, int H, int V);
 int launch_kept_prepare(const void*, const void*, const float4*, const int*, const float*, const float*, const float*,
-                        const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, bool,
-                        size_t, void*, float*, float*, bool, cudaStream_t);
-int launch_reduce_sparse(const float*, const float4*, const int*, const float*, const float*, int, const float*,
-                         const float*, const int*, const int*, const int*, int, int, int, int, float*, float*, const int*,
-                         const float*, const float*, void*, size_t, float*, float*, cudaStream_t);
-int launch_joint_dw_kept(const void*, const int*, const void*, uint64_t, int, int, int, int, bool, const int*,
-                         const float*, float*, float*, cudaStream_t);
+                        const float*, const int*, const int*, const int*, int, int, int, int, int, bool, size_t, void*,
+                        float*, float*, cudaStream_t);
 int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
                      float*, float*, float*, int*, cudaStream_t);
 int launch_dense_grad(const float*, const float4*, const int*, const float*, const int*, const int*, const int*, int,
@@ -54,7 +50,7 @@ int launch_joint_fwd(const void*, const void*, uint64_t, int, int, int, int, boo
                      const float*, const int*, int, float*, float*, float*, cudaStream_t);
 int launch_joint_bwd(const void*, const void*, const void*, const void*, uint64_t, int, int, int, int, bool,
                      const int*, const float*, const float*, const int*, int, const float4*, float*, float*, float*,
-                     int, cudaStream_t, const int*);
+                     int, void*, size_t, cudaStream_t);
 
 bool wide_supported_h(int H);
 int launch_wide_sp(const void*, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*, const float*,
@@ -209,8 +205,8 @@ int ttx_transpose16(const void* in, void* out, int rows, int cols, const int32_t
 int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const void* w16t, const float* bias2,
                    const float* scal,
                    const int32_t* row_label, const int32_t* meta, const void* rowmeta, int64_t n_tiles_ub, int H,
-                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits, int device,
-                   void* stream) {
+                   int V, int blank, int bf16, float* d_act, float* d_w_out, float* d_b_out, int splits,
+                   void* workspace, int64_t workspace_bytes, int device, void* stream) {
     TTX_REQUIRE(a16 && w16 && bias2 && scal && row_label && meta && rowmeta, "ttx_joint_grad: null pointer");
     TTX_REQUIRE((d_w_out == nullptr) == (d_b_out == nullptr), "ttx_joint_grad: d_w_out and d_b_out go together");
     TTX_REQUIRE(mma_supported_h(H), "ttx_joint_grad: joint width H=%d is not supported by the tensor-core path", H);
@@ -220,7 +216,7 @@ int ttx_joint_grad(const void* a16, const void* w16, const void* a16t, const voi
     const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_joint_bwd(a16, w16, a16t, w16t, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta,
                             bias2, scal, row_label, blank, (const float4*)rowmeta, d_act, d_w_out, d_b_out, splits,
-                            (cudaStream_t)stream, nullptr);
+                            workspace, workspace ? (size_t)workspace_bytes : 0, (cudaStream_t)stream);
 }
 
 int ttx_reduce_act_grad(const float* d_act, const float* eproj, const float* pproj, const int32_t* act_lens,
@@ -238,7 +234,8 @@ int ttx_fwd_grad_supported_h(int H) { return fwd_grad_supported_h(H) ? 1 : 0; }
 
 int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
                        const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
-                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, int device, void* stream) {
+                       int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* workspace,
+                       int64_t workspace_bytes, int device, void* stream) {
     TTX_REQUIRE(a16 && w16 && w16t && bias2 && scal && row_label && meta && lse && lp_blank && lp_label && ew,
                 "ttx_joint_fwd_grad: null pointer");
     TTX_REQUIRE(fwd_grad_supported_h(H), "ttx_joint_fwd_grad: joint width H=%d is not supported (128, 256, 512)", H);
@@ -246,52 +243,13 @@ int ttx_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, const
     TTX_ENTER(device);
     const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_joint_fwd_grad(a16, w16, w16t, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0,
-                                 meta, bias2, scal, row_label, blank, lse, lp_blank, lp_label, ew, (cudaStream_t)stream,
-                                 nullptr, nullptr, nullptr);
+                                 meta, bias2, scal, row_label, blank, lse, lp_blank, lp_label, ew, workspace,
+                                 workspace ? (size_t)workspace_bytes : 0, (cudaStream_t)stream);
 }
 
-int ttx_joint_fwd_grad_keep(const void* a16, const void* w16, const void* w16t, const float* bias2, const float* scal,
-                            const int32_t* row_label, const int32_t* meta, int64_t n_tiles_ub, int H, int V, int blank,
-                            int bf16, float* lse, float* lp_blank, float* lp_label, float* ew, void* pstore,
-                            int32_t* pflags, float* pfac, int device, void* stream) {
-    TTX_REQUIRE(a16 && w16 && w16t && bias2 && scal && row_label && meta && lse && lp_blank && lp_label && ew && pstore &&
-                    pflags && pfac, "ttx_joint_fwd_grad_keep: null pointer");
-    TTX_REQUIRE(H == 512, "ttx_joint_fwd_grad_keep: joint width H=%d is not supported (512)", H);
-    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_joint_fwd_grad_keep: bad V=%d / blank=%d", V, blank);
-    TTX_ENTER(device);
-    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
-    return launch_joint_fwd_grad(a16, w16, w16t, (uint64_t)n_tiles_ub * kTile, (int)n_tiles_ub, H, V, Vpad, bf16 != 0,
-                                 meta, bias2, scal, row_label, blank, lse, lp_blank, lp_label, ew, (cudaStream_t)stream,
-                                 pstore, pflags, pfac);
-}
-
-int ttx_weight_grad_kept(const void* pstore, const int32_t* pflags, const float* pfac, const void* a16, const void* w16,
-                         const void* a16t, const void* w16t, void* a16st, const float* bias2, const float* scal,
-                         const int32_t* row_label, const int32_t* meta, const void* rowmeta, const float* lp_blank,
-                         const float* lp_label, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                         int64_t n_tiles_ub, int H, int V, int blank, int bf16, int sparse_terms, float* d_w_out,
-                         float* d_b_out, int device, void* stream) {
-    TTX_REQUIRE(pstore && pflags && pfac && a16 && w16 && a16t && w16t && a16st && bias2 && scal && row_label && meta &&
-                    rowmeta && lp_blank && lp_label && act_lens && label_lens && d_w_out && d_b_out,
-                "ttx_weight_grad_kept: null pointer");
-    TTX_REQUIRE(H == 512, "ttx_weight_grad_kept: joint width H=%d is not supported (512)", H);
-    TTX_REQUIRE(V > 0 && blank >= 0 && blank < V, "ttx_weight_grad_kept: bad V=%d / blank=%d", V, blank);
-    TTX_REQUIRE(B > 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_weight_grad_kept: bad shape");
-    TTX_ENTER(device);
-    const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
-    const uint64_t rows = (uint64_t)n_tiles_ub * kTile;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = launch_kept_prepare(a16, a16t, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal,
-                                     act_lens, label_lens, meta, pflags, B, T, U1, H, blank, bf16 != 0, rows, a16st,
-                                     d_w_out, d_b_out, sparse_terms != 0, s))
-        return rc;
-    if (int rc = launch_joint_dw_kept(pstore, pflags, a16st, rows, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta, scal,
-                                      d_w_out, d_b_out, s))
-        return rc;
-    // flagged matrix (a row's running reference moved during the forward: mixed scales): the recomputing kernel runs instead
-    return launch_joint_bwd(a16, w16, a16t, w16t, rows, (int)n_tiles_ub, H, V, Vpad, bf16 != 0, meta, bias2, scal,
-                            row_label, blank, (const float4*)rowmeta, nullptr, d_w_out, d_b_out, 1, s,
-                            pflags + kKeptAnyDirty);
+int64_t ttx_joint_workspace_bytes(int which, int64_t n_tiles_ub, int H, int V, int device) {
+    if (which < 0 || which > 1 || n_tiles_ub < 1 || n_tiles_ub >= (1 << 24) || V <= 0 || enter(device)) return 0;
+    return (int64_t)joint_workspace_bytes(which, (int)n_tiles_ub, H, V);
 }
 
 int ttx_wide_supported_h(int H) { return wide_supported_h(H) ? 1 : 0; }
@@ -351,16 +309,16 @@ int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const
 
 int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
                      const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
-                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, const int32_t* pflags, int B,
-                     int T, int U1, int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out,
-                     float* d_b_out, int device, void* stream) {
+                     const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
+                     int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,
+                     int device, void* stream) {
     TTX_REQUIRE(a16 && a16t && rowmeta && row_label && lp_blank && lp_label && pfac && scal && act_lens && label_lens &&
-                    meta && pflags && a16st && d_w_out && d_b_out, "ttx_kept_prepare: null pointer");
+                    meta && a16st && d_w_out && d_b_out, "ttx_kept_prepare: null pointer");
     TTX_REQUIRE(H > 0 && H % 64 == 0 && B > 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_kept_prepare: bad shape");
     TTX_ENTER(device);
     return launch_kept_prepare(a16, a16t, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal, act_lens,
-                               label_lens, meta, pflags, B, T, U1, H, blank, bf16 != 0, (size_t)n_tiles_ub * kTile, a16st,
-                               d_w_out, d_b_out, true, (cudaStream_t)stream);
+                               label_lens, meta, B, T, U1, H, blank, bf16 != 0, (size_t)n_tiles_ub * kTile, a16st, d_w_out,
+                               d_b_out, (cudaStream_t)stream);
 }
 
 int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
@@ -373,22 +331,6 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
     TTX_ENTER(device);
     return launch_reduce(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens, label_lens,
                          meta, B, T, U1, H, d_eproj, d_pproj, (cudaStream_t)stream);
-}
-
-int ttx_reduce_act_grad_ew_kept(const float* ew, const void* rowmeta, const int32_t* row_label, const float* w_out,
-                                const float* scal, int blank, const float* eproj, const float* pproj,
-                                const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T,
-                                int U1, int H, float* d_eproj, float* d_pproj, const int32_t* pflags,
-                                const float* lp_blank, const float* lp_label, void* a16st, int64_t n_tiles_ub,
-                                float* d_w_out, float* d_b_out, int device, void* stream) {
-    TTX_REQUIRE(ew && rowmeta && row_label && w_out && scal && eproj && pproj && act_lens && label_lens && meta &&
-                    d_eproj && d_pproj && pflags && lp_blank && lp_label && a16st && d_w_out && d_b_out,
-                "ttx_reduce_act_grad_ew_kept: null pointer");
-    TTX_REQUIRE(H % 4 == 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_reduce_act_grad_ew_kept: bad shape");
-    TTX_ENTER(device);
-    return launch_reduce_sparse(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens,
-                                label_lens, meta, B, T, U1, H, d_eproj, d_pproj, pflags, lp_blank, lp_label, a16st,
-                                (size_t)n_tiles_ub * kTile, d_w_out, d_b_out, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

@@ -30,8 +30,6 @@ struct MmaParams {
     int NS;                // ring stages
     int blank;
     int splits;            // DW: lattice-row splits
-    long long* trace;      // timing experiments only (TTX_TRACE): clock64 stamps of CTA (0,0,0), [role][iter][4]
-    int dbg;               // timing experiments only (TTX_DBG): 1 = skip S-pass MMAs, 2 = skip G-pass MMAs, 4 = skip epilogue math
     const int* meta;       // tile table
     const float* bias2;    // (Vpad) b_out * log2(e), -inf for v >= V
     const float* scal;     // [0] w_scale, [1] 1 / w_scale, [2] gmax, [3] != 0 if some grad_costs[b] < 0
@@ -44,11 +42,7 @@ struct MmaParams {
     float* dW;             // DW out (V x H), accumulated with red.add
     float* db;             // DW out (V)
     uint8_t* scratch;      // pair kernel: flags (64 KiB) of the P' scratch matrix (replay), or null
-    int keep;              // the P' matrix covers every lattice row (rows_ub x Vpad) and is kept for the weight gradient
     int scr_rows;          // rows R of the P' matrix; it is stored in 64-column blocks, [cols / 64][R][64]
-    float* pfac;           // FG out (rows), optional: softmax(row, v) = P'(row, v) * pfac[row]
-    const int* run_if;     // DW, optional: the launch is a no-op unless (*run_if != 0) == (run_if_val != 0)
-    int run_if_val;
 };
 
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter
@@ -119,12 +113,6 @@ __device__ __forceinline__ uint16_t to16(float x) {
     return __half_as_ushort(__float2half_rn(x));
 }
 
-constexpr int kTraceIters = 40;
-__device__ __forceinline__ void trace_at(const MmaParams& p, int role, int iter, int ev) {
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && iter < kTraceIters)
-        p.trace[(role * kTraceIters + iter) * 4 + ev] = clock64();
-}
-
 template <int CG>
 __device__ __forceinline__ void bwait(uint32_t bar, uint32_t parity) {
     mbar_wait(bar, parity);
@@ -138,7 +126,6 @@ template <int MODE, bool BF16, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                  const MmaParams p) {
-    if (MODE == MODE_DW && p.run_if != nullptr && (*p.run_if != 0) != (p.run_if_val != 0)) return;   // whole grid alike
     constexpr bool BWD = (MODE != MODE_FWD);
     constexpr int NT = (CG == 2 && !BWD) ? 256 : 128;   // columns of one S accumulator = stream rows per step
     constexpr int SR = NT / CG;                          // stream rows this CTA loads per S chunk
@@ -271,11 +258,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             } else {
                 load_S(j0);
                 for (int i = 0; i < n_iter; ++i) {
-                    trace_at(p, 0, i, 0);
                     if (i + 1 < n_iter) load_S(j0 + i + 1);
-                    trace_at(p, 0, i, 1);
                     load_G(j0 + i);
-                    trace_at(p, 0, i, 2);
                 }
             }
         }
@@ -306,11 +290,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     tc_fence_after();
                     const uint32_t a = sX + c * kChunkBytes;
                     const uint32_t b = sRing + r.stage * STAGE;
-                    if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
-                    }
+                    for (int k = 0; k < 4; ++k) mma(d, desc_kmajor(a, k), desc_kmajor(b, k), idescS, (c | k) != 0);
                     commit(bar_empty(r.stage));
                     r.advance(p.NS);
                 }
@@ -318,19 +299,16 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             };
             auto issue_G = [&](int idx) {
                 bwait<CG>(bar_pfull, idx & 1);
-                trace_at(p, 1, idx, 2);
                 tc_fence_after();
                 for (int g = 0; g < p.NGCL; g += p.GCH) {
                     for (int s = 0; s < gstages; ++s) bwait<CG>(bar_full(r.stage + s), r.phase);
                     tc_fence_after();
                     const uint32_t d = tmem_G + g * 64;
                     const uint32_t b = sRing + r.stage * STAGE;
-                    if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            mma(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3), desc_mnmajor(b, k, kChunkBytes),
-                                idescG, (idx | k) != 0);
-                    }
+                    for (int k = 0; k < 8; ++k)
+                        mma(d, desc_kmajor(sP + (k >> 2) * kChunkBytes, k & 3), desc_mnmajor(b, k, kChunkBytes), idescG,
+                            (idx | k) != 0);
                     for (int s = 0; s < gstages; ++s) commit(bar_empty(r.stage + s));
                     r.advance(p.NS, gstages);
                 }
@@ -341,11 +319,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             } else {
                 issue_S(0);
                 for (int i = 0; i < n_iter; ++i) {
-                    trace_at(p, 1, i, 0);
                     if (i + 1 < n_iter) issue_S(i + 1);
-                    trace_at(p, 1, i, 1);
                     issue_G(i);
-                    trace_at(p, 1, i, 3);
                 }
                 commit(bar_gfull);
             }
@@ -465,16 +440,10 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     epi_sync();
                 }
                 bwait<CG>(bar_sfull(buf), (i >> 1) & 1);
-                if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t packed[32];
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    if (p.dbg & 4) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) packed[g * 16 + e] = 0;
-                        continue;
-                    }
                     const int cb = ch * 64 + g * 32;           // first accumulator column of this group
                     tmem_ld32(tmem_base + lane_addr + buf * 128 + cb, acc);
                     float kc[32];
@@ -513,10 +482,8 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 // S buffer is free again as soon as it sits in registers
                 tc_fence_before();
                 epi_arrive(bar_sempty(buf));
-                if (et == 0) trace_at(p, 2, i, 1);
                 // wait until the previous G pass has finished reading the P tile, then overwrite it
                 bwait<CG>(bar_pempty, (i & 1) ^ 1);
-                if (et == 0) trace_at(p, 2, i, 2);
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {       // 8 chunks of 8 values (16 B) = this thread's 64 columns
                     uint4 v4 = make_uint4(packed[cc * 4 + 0], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
@@ -542,7 +509,6 @@ joint_mma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
                 fence_proxy_async_smem();
                 epi_arrive(bar_pfull);
-                if (et == 0) trace_at(p, 2, i, 3);
             }
             // ---- final: G (128 x HH fp32 in TMEM) -> global; the two column halves split the HH columns
             bwait<CG>(bar_gfull, 0);
@@ -609,18 +575,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     constexpr int NT = 256;                 // stream rows per step (pair-wide) = S accumulator columns
     constexpr int SR = 128;                 // stream rows this CTA loads per S chunk
     constexpr int STAGE = kChunkBytes;      // 16 KiB ring stages
-    if (MODE == MODE_DW && p.run_if != nullptr && (*p.run_if != 0) != (p.run_if_val != 0)) return;   // whole grid alike
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
     const int n_tiles = p.meta[0];
-    // KEPT (weight gradient, p.keep): the forward+gradient launch left P' for every lattice row in global memory.  A unit
-    // is then ONE item without S pass, exponentials or P' buffers: per 64 lattice rows the ring takes a group of three
-    // stages -- P'^T (the A operand, MN-major, straight from the row-major P' matrix: two [64 m x 64 v] boxes) and the
-    // scaled A16^T chunks of both slabs (B operands) -- and eight MMAs accumulate both G slabs (all 512 TMEM columns).
-    // mapScr = P' matrix, mapYT = scaled A16^T (H + 16 rows), mapY = its last 16 rows (8-row boxes) = the row scales
-    // themselves: the idle epilogue warps multiply them with the P' stage in shared memory for the dense part of db.
-    const bool kept = (MODE == MODE_DW) && p.keep != 0;
-    constexpr int kKG = 3;                            // kept: ring stages per group, groups in flight (9 stages)
     // Persistent: the grid is one CTA pair per SM pair and each pair walks work units one after the other, all slabs of
     // a unit in turn, so the next item's stationary tile loads behind the last G sub-passes, its first S passes run
     // behind the read-out of G, and TMEM / barriers are set up once.  FG / DA: unit = tile pair, streams the whole
@@ -647,7 +604,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         }
         return n_iter > 0;
     };
-    const int n_hl = kept ? 1 : p.n_halves;           // items per unit: one per slab (kept: both slabs in one item)
+    const int n_hl = p.n_halves;                      // items per unit: one per slab
     auto unit_tile = [&](int unit) { return (MODE == MODE_DW ? (unit % n_vq) * 2 : unit * 2) + (int)rank; };
     auto slab_of = [&](int hh) { return hh; };
     // Forward+gradient with a scratch area (REPLAY): the first slab of a unit also sends every P' sub-tile to a scratch
@@ -655,20 +612,17 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     // needs neither S passes nor exponentials -- it streams P' back as the A operand next to the W16^T chunks.  If the
     // running reference moved after the unit's first tile (rare), the stored sub-tiles carry mixed scales: the unit is
     // flagged and its second slab recomputes everything as without the scratch area.
-    const bool rp = (MODE == MODE_FG || MODE == MODE_DW) && !kept && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 &&
+    const bool rp = (MODE == MODE_FG || MODE == MODE_DW) && p.scratch != nullptr && p.n_halves == 2 && p.NS <= 4 &&
                     p.NKC + kPB <= 12;
     // The replay streams two operands and touches neither the X tile nor the P' buffers: their shared memory (contiguous,
     // 10 x 16 KiB) is its ring, with its own barriers (slots kRB.. of the full / empty arrays) and its own position.
     constexpr int kRB = 4;                            // first barrier slot of the replay ring (the S / G ring uses < 4)
     const int nrs = p.NKC + kPB;                      // replay ring stages
-    // Flags (first 64 KiB of the scratch area, zeroed by the host).  Bounded scratch: one word per CTA pair, stamped with
-    // the pair's unit counter + 1.  KEEP (p.keep: the matrix covers every lattice row and outlives the launch -- the
-    // weight-gradient launch reads it): one word per unit, plus word kKeptAnyDirty = some unit of the launch is flagged.
+    // Flags (first 64 KiB of the scratch area, zeroed by the launcher): one word per CTA pair, stamped with the pair's
+    // unit counter + 1 when the unit's stored sub-tiles carry mixed scales.
     volatile int* const flags = reinterpret_cast<volatile int*>(p.scratch);
-    auto unit_clean = [&](int unit, int uidx) {
-        return p.keep ? flags[unit] == 0 : flags[blockIdx.x >> 1] != uidx + 1;
-    };
-    auto scr_row = [&](int x_row0) { return p.keep ? x_row0 : (int)blockIdx.x * kTile; };   // the CTA's rows of the matrix
+    auto unit_clean = [&](int unit, int uidx) { return flags[blockIdx.x >> 1] != uidx + 1; };
+    auto scr_row = [&](int x_row0) { return (int)blockIdx.x * kTile; };   // the CTA's rows of the scratch matrix
     const int hh2 = p.HH / 2;               // G columns (N rows of the K-major B operand) held by this CTA
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -700,7 +654,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     static_assert(kPB == 2, "barrier slots 40..42 are used below");
     auto bar_pwritten = [&](int b) { return sBar + 8 * (40 + b); };  // REPLAY: this CTA's epilogue warps wrote buffer b
     const uint32_t bar_unit = sBar + 8 * 42;                         // REPLAY: first slab of the unit is complete
-    auto bar_cons = [&](int g) { return bar_full(kRB + kKG * kKG + g); };   // KEPT: the MMAs have read group g's stages
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -715,10 +668,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         *reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base)) = 0;
         for (int s = 0; s < 16; ++s) {
             mbar_init(bar_full(s), 1);
-            // kept: the P' and first As^T stage of a group are released by this CTA's epilogue warps (which read them
-            // after the MMAs, see bar_cons), the third stage by the MMAs' commit as everywhere else
-            const bool epi_released = kept && s >= kRB && s < kRB + kKG * kKG && (s - kRB) % kKG != kKG - 1;
-            mbar_init(bar_empty(s), epi_released ? kPairEpiWarps : 1);
+            mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_sfull, 1);
         mbar_init(bar_sempty, 2 * kPairEpiWarps);       // every epilogue warp of both CTAs
@@ -755,7 +705,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             Ring r;
             auto load_stage = [&](const CUtensorMap* map, int col, int row, int bytes) {
                 mbar_wait(bar_empty(r.stage), r.phase ^ 1);
-                if (p.dbg & 8) bytes >>= 1;        // timing experiment: the tensor maps' boxes are half as tall
                 if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * bytes);
                 tma_load_2d_pair(sRing + r.stage * STAGE, map, bar_full(r.stage), col, row);
                 r.advance(p.NS);
@@ -777,30 +726,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             bool replayed = false;                              // the previous item was a replay (its ring is our X tile)
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
-                if (kept) {
-                    const int v0 = unit_tile(unit) * kTile;     // this CTA's vocabulary rows = columns of the P' matrix
-                    for (int i = 0; i < n_iter; ++i)
-                        for (int c = 0; c < 4; ++c) {
-                            const int m0 = (j0 + i) * NT + c * kKC;
-                            uint32_t full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
-                            mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
-                            if (leader) mbar_arrive_expect_tx(full, 2 * STAGE);
-                            tma_load_2d_pair(dst, &mapScr, full, 0, (v0 / kKC) * p.scr_rows + m0);
-                            tma_load_2d_pair(dst + STAGE / 2, &mapScr, full, 0, (v0 / kKC + 1) * p.scr_rows + m0);
-                            rr.advance(kKG * kKG);
-                            for (int hh = 0; hh < 2; ++hh) {
-                                full = bar_full(kRB + rr.stage), dst = sX + rr.stage * STAGE;
-                                mbar_wait(bar_empty(kRB + rr.stage), rr.phase ^ 1);
-                                if (leader) mbar_arrive_expect_tx(full, 2 * (hh2 * 128 + (hh == 0 ? 1024 : 0)));
-                                // the scaled A16^T is stored in 64-row blocks of lattice rows, [rows / 64][H + 16][64]
-                                const int hb = (m0 / kKC) * (p.H + 16);
-                                tma_load_2d_pair(dst, &mapYT, full, 0, hb + hh * p.HH + (int)rank * hh2);
-                                if (hh == 0) tma_load_2d_pair(sRing + (rr.stage / kKG) * 1024, &mapY, full, 0, hb + p.H + (int)rank * 8);
-                                rr.advance(kKG * kKG);
-                            }
-                        }
-                    continue;
-                }
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
                     const int x_row0 = unit_tile(unit) * kTile, half = slab_of(hh);
                     if (rp && hh == 1) {
@@ -921,18 +846,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++it) {
-                    if (kept) {
-                        for (int i = 0; i < n_iter; ++i)
-                            for (int c = 0; c < 4; ++c) {
-                                if (i == 0 && c == 0) mbar_wait(bar_gempty, (it - 1) & 1);
-                                for (int g = 0; g < kKG; ++g) {
-                                    mbar_wait(bar_full(kRB + rr.stage), rr.phase);
-                                    rr.advance(kKG * kKG);
-                                }
-                                publish();
-                            }
-                        continue;
-                    }
                     if (rp && hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
                         if (unit_clean(unit, uidx)) {
@@ -1016,31 +929,12 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
                 if (!begin_unit(unit)) break;
                 for (int hh = 0; hh < n_hl; ++hh, ++itt) {
-                    trace_at(p, 0, itt, 2);
                     bool replay = false;
                     if (rp && hh == 1) {
                         mbar_wait(bar_unit, uidx & 1);
                         replay = unit_clean(unit, uidx);
                     }
-                    if (kept) {
-                        // G(slab 0 | slab 1) += P'^T(stage r) . As^T chunks (stages r + 1 | r + 2)
-                        const uint32_t idescGm = make_idesc(fmt, 1, 0, 256, p.HH);
-                        const uint32_t amn = (xlo & 0xFFFFu) | (512u << 16);     // MN-major: 64-wide blocks 8 KiB apart
-                        for (int i = 0; i < n_iter; ++i)
-                            for (int c = 0; c < 4; ++c) {
-                                wait_event();
-                                tc_fence_after();
-                                const uint32_t a = amn + rstage * 1024, b0 = xlo + (rstage + 1) * 1024, b1 = b0 + 1024;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    umma_f16_ss_pair_lo(tmem_base, a + 128 * k, b0 + 2 * k, idescGm, (i | c | k) != 0);
-                                    umma_f16_ss_pair_lo(tmem_G, a + 128 * k, b1 + 2 * k, idescGm, (i | c | k) != 0);
-                                }
-                                umma_commit_pair(bar_cons(rstage / kKG));          // the epilogue warps release r and r + 1
-                                umma_commit_pair(bar_empty(kRB + rstage + 2));
-                                rstage = (rstage + kKG == kKG * kKG) ? 0 : rstage + kKG;
-                            }
-                    } else if (replay) {
+                    if (replay) {
                         // G(slab 1) += P'(i, c) . W16^T chunk, both operands from consecutive ring stages
                         for (int i = 0; i < n_iter; ++i)
                             for (int c = 0; c < 4; ++c) {
@@ -1058,15 +952,11 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     } else {
                         issue_S(0);
                         for (int i = 0; i < n_iter; ++i) {
-                            trace_at(p, 1, i, 0);
                             if (i + 1 < n_iter) issue_S(i + 1);
-                            trace_at(p, 1, i, 1);
                             issue_G(i);
-                            trace_at(p, 1, i, 3);
                         }
                     }
                     umma_commit_pair(bar_gfull);
-                    trace_at(p, 0, itt, 3);
                 }
             }
         }
@@ -1116,7 +1006,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 store_p(dst[g], packed[g]);
                 r.advance();
             }
-            if (et == 0) trace_at(p, 2, i, 2);
             patch(0, kPB, dst);
             fence_proxy_async_smem();
 #pragma unroll
@@ -1137,11 +1026,9 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 epi_arrive(bar_pfull(bufs[g]));
                 if (rp && lane == 0) mbar_arrive(bar_pwritten(bufs[g]));
             }
-            if (et == 0) trace_at(p, 2, i, 3);
             pr = r;
         };
         int it = 0, gs0 = 0, uidx = 0;                // items, S passes (accumulator barrier parity), units so far
-        Ring kr;                                      // KEPT: ring position (first stage of the current group)
         float f_keep = 0.f;                           // REPLAY: the row's output scale, from the unit's first slab
         for (int unit = unit0; unit < n_units; unit += unit_step, ++uidx) {
         if (!begin_unit(unit)) break;
@@ -1153,57 +1040,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             mbar_wait(bar_unit, uidx & 1);
             replay = unit_clean(unit, uidx);
         }
-        if (et == 0) trace_at(p, 0, it, 0);
-        if (kept) {
-            // ---- kept P': nothing to do per stream tile but the dense part of db[v] = sum_m s_m P'[m, v]: thread (v, mh)
-            // takes half of each stage's 64 lattice rows for vocabulary row v of this CTA, from the P' stage and the row
-            // scales (row 0 of the 8-row scale tile) once the MMAs have read the group, then the warp releases both stages
-            const int v = et & (kTile - 1), mh = et >> 7;
-            const uint8_t* sX_gen = smem_gen + (sX - smem_base);
-            const uint8_t* sS_gen = smem_gen + (sRing - smem_base);
-            float dacc = 0.f;
-            for (int i = 0; i < n_iter; ++i)
-                for (int c = 0; c < 4; ++c) {
-                    const int g = kr.stage / kKG;
-                    mbar_wait(bar_cons(g), kr.phase);
-                    const uint8_t* pst = sX_gen + kr.stage * STAGE + (v >> 6) * (STAGE / 2) + (v & 7) * 2;
-                    const uint16_t* sc = reinterpret_cast<const uint16_t*>(sS_gen + g * 1024);
-                    const int vc = (v & 63) >> 3;
-#pragma unroll 8
-                    for (int m = mh * 32; m < mh * 32 + 32; ++m) {
-                        const uint32_t pv = *reinterpret_cast<const uint16_t*>(pst + m * 128 + ((vc ^ (m & 7)) << 4));
-                        const uint32_t sv = sc[m];
-                        float pf_, sf_, d0, d1;
-                        unpk16<BF16>(pv, pf_, d0);
-                        unpk16<BF16>(sv, sf_, d1);
-                        dacc = fmaf(pf_, sf_, dacc);
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(bar_empty(kRB + kr.stage));
-                        mbar_arrive(bar_empty(kRB + kr.stage + 1));
-                    }
-                    kr.advance(kKG * kKG, kKG);
-                }
-            const int vrow = x_row0 + row;
-            const float f = p.scal[2] * (BF16 ? 1.0f : 1.0f / kKeptUp);           // the As operand carries 2^16 (fp16)
-            if (x_row0 + v < p.V) atomicAdd(p.db + x_row0 + v, dacc * f);
-            mbar_wait(bar_gfull, it & 1);
-            tc_fence_after();
-            const bool ok = vrow < p.V;
-            uint32_t gacc[32];
-            for (int cc = ch; cc < 2 * (p.HH / 32); cc += 2) {           // both slabs: TMEM column cc * 32 <-> joint column
-                tmem_ld32(tmem_base + lane_addr + cc * 32, gacc);
-                tmem_ld_wait();
-                if (ok) {
-                    float* dst = p.dW + (size_t)vrow * p.H + cc * 32;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        red_add_v4(dst + e, __uint_as_float(gacc[e]) * f, __uint_as_float(gacc[e + 1]) * f,
-                                   __uint_as_float(gacc[e + 2]) * f, __uint_as_float(gacc[e + 3]) * f);
-                }
-            }
-        } else if (MODE == MODE_FG) {
+        if (MODE == MODE_FG) {
             // ---- forward + expected-output-row mode (flash-attention style): besides the log-softmax statistics the
             // pair accumulates G = sum_v 2^(y_v - mref) * W16[v, slab] in TMEM against a per-row running reference
             // mref (log2 units).  The reference is fixed by the first tile and only moves when a later tile would
@@ -1229,7 +1066,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
 #pragma unroll
                 for (int e = 0; e < 8; ++e) bpre[e] = __ldg(reinterpret_cast<const float4*>(bias_t) + e);
                 mbar_wait(bar_sfull, (gs0 + i) & 1);
-                if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 uint32_t acc[4][32];
 #pragma unroll
@@ -1237,7 +1073,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
-                if (et == 0) trace_at(p, 2, i, 1);
                 float lmax = -INFINITY;
                 float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
                 if (i == 0) {
@@ -1309,12 +1144,7 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     float part = p0 + p1;
                     if (quarter_any(q, lmax > ref_limit)) {
                         if (rp && hh == 0) {                       // stored sub-tiles now carry mixed scales: no replay
-                            if (p.keep) {
-                                flags[unit] = 1;
-                                flags[kKeptAnyDirty] = 1;
-                            } else {
-                                flags[blockIdx.x >> 1] = uidx + 1;
-                            }
+                            flags[blockIdx.x >> 1] = uidx + 1;
                         }
                         xg[ch * kTile + row] = lmax;
                         quarter_sync(q);
@@ -1403,7 +1233,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     p.lpl[grow] = (label >= 0) ? (zl - lse2) * kLn2 : 0.f;
                 }
                 const float pf = ex2f(mref - lg_scale - lse2);    // softmax(row, v) = P'(row, v) * pf
-                if (p.pfac && ch == 0 && valid_x && half == 0) p.pfac[grow] = pf;
                 f_keep = pf * inv_ws;
             }
             const float f = f_keep;
@@ -1451,7 +1280,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                     pair_epi_sync();
                 }
                 mbar_wait(bar_sfull, (gs0 + i) & 1);
-                if (et == 0) trace_at(p, 2, i, 0);
                 tc_fence_after();
                 // Pull this thread's share of the S tile (4 sub-tiles x 32 columns) into registers and hand the single S
                 // accumulator back at once: the next tile's S pass then overlaps the exponentials below.
@@ -1461,7 +1289,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 tmem_ld_wait();
                 tc_fence_before();
                 epi_arrive(bar_sempty);
-                if (et == 0) trace_at(p, 2, i, 1);
                 uint32_t packed[4][16];
                 {
                     uint64_t d01 = pk2(0.f, 0.f), d23 = d01;
@@ -1480,7 +1307,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                             unpk2(y01, y0, y1);
                             unpk2(y23, y2, y3);
                             float v0 = ex2f(y0), v1 = ex2f(y1), v2 = ex2f(y2), v3 = ex2f(y3);
-                            if (p.dbg & 4) v0 = v1 = v2 = v3 = 0.f;
                             if (MODE == MODE_DW) {
                                 if (any_neg) {
                                     const float4 sg = *reinterpret_cast<const float4*>(kbuf + NT + cb + 4 * e);
@@ -1579,7 +1405,6 @@ joint_bwd_pair_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 mbar_arrive_cluster(bar_unit, rank ^ 1);
             }
         }
-        if (et == 0) trace_at(p, 0, it, 1);
         }
         }
     }
@@ -1659,32 +1484,22 @@ bool mma_supported_h(int H) {
     return H > 0 && H <= 512 && H % 64 == 0 && (H <= 256 || H == 384 || H == 512);
 }
 
-static int forced_cg() {
-    const char* e = getenv("TTX_CG");
-    return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
-}
-
-static long long* trace_buffer();
-
 struct Plan {
     MmaParams p;
     int cg, stage_bytes;
     size_t smem;
 };
 
-// Shape-derived launch plan.  CTA pairs need every CTA's share of a G slab to be whole 64-column chunks.
+// Shape-derived launch plan of joint_mma_kernel: forward = CTA pairs, generic backward = single CTAs.
 static Plan plan(int H, int V, bool bwd) {
     Plan pl{};
     MmaParams& p = pl.p;
     p.H = H;
-    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-    p.trace = trace_buffer();
     p.NKC = H / 64;
     p.V = V;
     p.n_halves = (bwd && H > 256) ? 2 : 1;
     p.HH = H / p.n_halves;
-    int cg = (!bwd || (p.HH / 2) % 64 == 0) ? 2 : 1;
-    if (forced_cg() == 1) cg = 1;
+    const int cg = bwd ? 1 : 2;          // (the pair kernels below cover the backward of H = 128, 256, 512)
     pl.cg = cg;
     pl.stage_bytes = (bwd && cg == 2) ? kChunkBytes / 2 : kChunkBytes;
     const int gst = kChunkBytes / pl.stage_bytes;
@@ -1692,7 +1507,6 @@ static Plan plan(int H, int V, bool bwd) {
     const size_t fixed = (size_t)(p.NKC + (bwd ? 2 : 0)) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     const size_t limit = 232448;
     int ns = kMaxStages;
-    if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kMaxStages, atoi(e)));
     while (ns > 2 && fixed + (size_t)ns * pl.stage_bytes > limit) --ns;
     p.GCH = 1;
     if (bwd) {
@@ -1732,51 +1546,6 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& my, const MmaParams&
     return 0;
 }
 
-static long long* trace_buffer() {
-    static long long* buf = nullptr;
-    if (!buf && getenv("TTX_TRACE")) {
-        cudaMalloc(&buf, sizeof(long long) * 3 * kTraceIters * 4);
-    }
-    return buf;
-}
-
-static void trace_dump(const char* what, cudaStream_t stream) {
-    long long* buf = trace_buffer();
-    if (!buf) return;
-    static int dumps = 0;
-    cudaStreamSynchronize(stream);
-    if (++dumps > 12 || dumps <= 9) { cudaMemset(buf, 0, sizeof(long long) * 3 * kTraceIters * 4); return; }
-    static long long h[3 * kTraceIters * 4];
-    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
-    cudaMemset(buf, 0, sizeof(h));
-    long long t0 = h[(1 * kTraceIters + 0) * 4 + 0];
-    fprintf(stderr, "TRACE %s (cycles since first MMA-loop entry)\n", what);
-    fprintf(stderr, " it | item it: epi start, epi end, mma start, mma end | tile it (last item): mma loop, S_issued, -, G_issued | epi: sfull, S_released, round A stored, all stored\n");
-    for (int i = 0; i < 12; ++i) {
-        fprintf(stderr, "%3d |", i);
-        for (int r = 0; r < 3; ++r) {
-            for (int e = 0; e < 4; ++e) {
-                long long v = h[(r * kTraceIters + i) * 4 + e];
-                fprintf(stderr, " %7lld", v ? v - t0 : -1);
-            }
-            fprintf(stderr, " |");
-        }
-        fprintf(stderr, "\n");
-    }
-}
-
-template <int MODE>
-static int dispatch(bool bf16, int cg, const CUtensorMap& mx, const CUtensorMap& my, const MmaParams& p, dim3 grid,
-                    size_t smem, cudaStream_t stream) {
-    if (cg == 2) {
-        grid.x = (grid.x + 1) & ~1u;
-        return bf16 ? launch<MODE, true, 2>(mx, my, p, grid, smem, stream)
-                    : launch<MODE, false, 2>(mx, my, p, grid, smem, stream);
-    }
-    return bf16 ? launch<MODE, true, 1>(mx, my, p, grid, smem, stream)
-                : launch<MODE, false, 1>(mx, my, p, grid, smem, stream);
-}
-
 int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_tiles_ub, int H, int V, int Vpad,
                      bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label,
                      int blank, float* lse, float* lpb, float* lpl, cudaStream_t stream) {
@@ -1794,7 +1563,9 @@ int launch_joint_fwd(const void* a16, const void* w16, uint64_t rows_ub, int n_t
     CUtensorMap mx, my;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, pl.stage_bytes / 128)) return rc;
-    return dispatch<MODE_FWD>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, 1, 1), pl.smem, stream);
+    const dim3 grid((n_tiles_ub + 1) & ~1u, 1, 1);
+    return bf16 ? launch<MODE_FWD, true, 2>(mx, my, p, grid, pl.smem, stream)
+                : launch<MODE_FWD, false, 2>(mx, my, p, grid, pl.smem, stream);
 }
 
 template <int MODE, bool BF16>
@@ -1840,13 +1611,10 @@ static int dw_splits(int n_st, int n_vq, int pairs, int cap) {
     return best;
 }
 
-// v3 applies when both transposed copies exist and every CTA's share of a G slab is a whole number of 64-row
-// chunk rows that fits one 16 KiB stage: HH / 2 in {64, 128}.
+// The pair kernels apply when both transposed copies exist and every CTA's share of a G slab is a whole number of
+// 64-row chunk rows that fits one 16 KiB stage: HH / 2 in {64, 128}.
 static bool v3_applicable(int H, const void* w16t, const void* a16t) {
-    const char* e = getenv("TTX_BWD_V3");
-    if (e && e[0] == '0') return false;
-    if (!w16t || !a16t || forced_cg() == 1) return false;
-    return H == 128 || H == 256 || H == 512;
+    return w16t && a16t && (H == 128 || H == 256 || H == 512);
 }
 
 bool fwd_grad_supported_h(int H) { return H == 128 || H == 256 || H == 512; }
@@ -1867,44 +1635,49 @@ static unsigned persistent_grid(int n_tiles_ub, int n_halves) {
     return 2u * (unsigned)max(1, min(items, sm_count() / 2));
 }
 
-// P' replay scratch (pair kernel, H = 512): 64 KiB of per-pair flags (zeroed) + a 16-bit matrix of 128 rows per CTA.
-// Stream-ordered allocation, nothing is kept between calls.  TTX_REPLAY=0 recomputes the second slab instead.
-static bool replay_enabled() {
-    const char* re = getenv("TTX_REPLAY");
-    return !(re && re[0] == '0');
+// P' replay scratch (pair kernels, H = 512): 64 KiB of per-pair flags + a 16-bit matrix of 128 rows per CTA, in the
+// caller's workspace (ttx_joint_workspace_bytes).  Without a workspace the second slab of a unit recomputes its S pass.
+static size_t fg_scratch_bytes(int n_tiles_ub, int V) {
+    const unsigned grid = persistent_grid(n_tiles_ub, 2);
+    return 65536 + (size_t)grid * kTile * ((V + 255) / 256) * 256 * 2;
 }
 
-static int alloc_scratch(void** scratch, size_t bytes, cudaStream_t stream) {
-    // keep freed blocks in the device's default pool between steps (the default returns them to the driver at every
-    // synchronisation, which makes a 165 MB stream-ordered allocation per step cost milliseconds)
-    static bool pool_tuned[64];
-    int dev = 0;
-    TTX_CUDA_OK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !pool_tuned[dev]) {
-        cudaMemPool_t pool;
-        uint64_t keep = ~0ull;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        pool_tuned[dev] = true;
-    }
-    TTX_CUDA_OK(cudaMallocAsync(scratch, bytes, stream));
-    TTX_CUDA_OK(cudaMemsetAsync(*scratch, 0, 65536, stream));
-    return 0;
+struct DwShape {
+    int splits, per;
+    unsigned grid;
+};
+static DwShape dw_shape(int n_tiles_ub, int V) {
+    // Persistent: units = vocabulary tile pairs x lattice-row splits of at most 160 stream chunks -- a unit's P' must fit
+    // its CTA's share of the scratch matrix (10 MiB per CTA, 1.5 GB on a B200).
+    const int n_vtiles = (V + kTile - 1) / kTile;
+    const int n_st = (n_tiles_ub + 1) / 2, n_vq = (n_vtiles + 1) / 2, pairs = max(1, sm_count() / 2);
+    DwShape d;
+    d.splits = dw_splits(n_st, n_vq, pairs, 160);
+    d.per = (n_st + d.splits - 1) / d.splits;
+    d.grid = 2u * (unsigned)max(1, min(n_vq * d.splits, pairs));
+    return d;
+}
+static size_t dw_scratch_bytes(int n_tiles_ub, int V) {
+    const DwShape d = dw_shape(n_tiles_ub, V);
+    return 65536 + (size_t)d.grid * kTile * d.per * 256 * 2;
+}
+
+size_t joint_workspace_bytes(int which, int n_tiles_ub, int H, int V) {
+    if (H != 512) return 0;
+    return which == 0 ? fg_scratch_bytes(n_tiles_ub, V) : dw_scratch_bytes(n_tiles_ub, V);
 }
 
 // Forward statistics + EW = sum_v p_v W_v (blank / label columns excluded) in one pass (MODE_FG of the pair kernel).
 int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, uint64_t rows_ub, int n_tiles_ub, int H,
                           int V, int Vpad, bool bf16, const int* meta, const float* bias2, const float* scal,
                           const int* row_label, int blank, float* lse, float* lpb, float* lpl, float* ew,
-                          cudaStream_t stream, void* pstore, int* pflags, float* pfac) {
+                          void* ws, size_t ws_bytes, cudaStream_t stream) {
     MmaParams p{};
     p.H = H;
     p.NKC = H / 64;
     p.V = V;
     p.n_halves = (H > 256) ? 2 : 1;
     p.HH = H / p.n_halves;
-    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-    p.trace = trace_buffer();
     const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
     int ns = 8;
     while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
@@ -1922,96 +1695,37 @@ int launch_joint_fwd_grad(const void* a16, const void* w16, const void* w16t, ui
     p.dA = ew;
     CUtensorMap mx, my, myt;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
-    const int hs = (p.dbg & 8) ? 2 : 1;
-    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile / hs)) return rc;
-    if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2 / hs)) return rc;
+    if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
+    if (int rc = make_matrix_map(&myt, w16t, (uint64_t)H, (uint64_t)Vpad, bf16, p.HH / 2)) return rc;
     dim3 grid(persistent_grid(n_tiles_ub, p.n_halves), 1, 1);
     // P' replay (H = 512): the scratch matrix holds the P' of the unit a CTA pair is working on: 128 rows per CTA x Vpad
     // columns (165 MB on a B200, whatever the problem size).
-    void* scratch = nullptr;
     CUtensorMap mscr;
     const int n_chunks = (V + 255) / 256;
     bool have_map = false;
-    if (pstore) {
-        // KEEP: the caller's matrix covers every lattice row (rows_ub x Vpad, 16 bit) and goes on to the weight gradient
-        if (p.n_halves != 2 || !pflags || !pfac || (n_tiles_ub + 1) / 2 > 16383) {
-            set_error("ttx_joint_fwd_grad: the kept P' matrix needs H = 512, flags, pfac and at most 16383 tile pairs");
+    if (p.n_halves == 2 && ws != nullptr) {
+        if (ws_bytes < fg_scratch_bytes(n_tiles_ub, V)) {
+            set_error("ttx_joint_fwd_grad: workspace of %zu bytes, ttx_joint_workspace_bytes asks for %zu", ws_bytes,
+                      fg_scratch_bytes(n_tiles_ub, V));
             return 1;
         }
-        if (int rc = make_matrix_map(&mscr, pstore, rows_ub * (uint64_t)(n_chunks * 4), kKC, bf16, kTile)) return rc;
-        p.scr_rows = (int)rows_ub;
-        p.scratch = reinterpret_cast<uint8_t*>(pflags);
-        p.keep = 1;
-        p.pfac = pfac;
-        have_map = true;
-    } else if (p.n_halves == 2 && replay_enabled()) {
-        const size_t bytes = 65536 + (size_t)grid.x * kTile * n_chunks * 256 * 2;
-        if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
-        if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536,
+        TTX_CUDA_OK(cudaMemsetAsync(ws, 0, 65536, stream));
+        if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(ws) + 65536,
                                      (uint64_t)grid.x * kTile * (uint64_t)(n_chunks * 4), kKC, bf16, kTile))
             return rc;
         p.scr_rows = (int)(grid.x * kTile);
-        p.scratch = static_cast<uint8_t*>(scratch);
+        p.scratch = static_cast<uint8_t*>(ws);
         have_map = true;
     }
     int rc = bf16 ? launch_v3<MODE_FG, true>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr)
                   : launch_v3<MODE_FG, false>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr);
-    if (scratch) TTX_CUDA_OK(cudaFreeAsync(scratch, stream));
-    if (rc == 0) trace_dump("FG", stream);
-    return rc;
-}
-
-// Weight gradient from the kept P' matrix (forward+gradient launch with pstore): dW += gmax 2^-shift P'^T . As, db likewise.
-// a16st = scaled A16^T with its 16 scale rows, in 64-column blocks [rows_ub / 64][H + 16][64] (launch_kept_prepare).  No-op if the matrix is flagged.
-int launch_joint_dw_kept(const void* pstore, const int* pflags, const void* a16st, uint64_t rows_ub, int n_tiles_ub, int H,
-                         int V, int Vpad, bool bf16, const int* meta, const float* scal, float* dW, float* db,
-                         cudaStream_t stream) {
-    if (H != 512) {
-        set_error("ttx_weight_grad_kept: H = %d (the kept P' path is built for two 256-column slabs, H = 512)", H);
-        return 1;
-    }
-    MmaParams p{};
-    p.H = H;
-    p.NKC = H / 64;
-    p.V = V;
-    p.n_halves = 2;
-    p.HH = H / 2;
-    p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-    p.trace = trace_buffer();
-    const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
-    int ns = 8;
-    while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
-    p.NS = ns;
-    const size_t smem = fixed + (size_t)ns * kChunkBytes;
-    p.meta = meta;
-    p.scal = scal;
-    p.dW = dW;
-    p.db = db;
-    p.keep = 1;
-    p.scratch = reinterpret_cast<uint8_t*>(const_cast<int*>(pflags));
-    p.run_if = pflags + kKeptAnyDirty;
-    p.run_if_val = 0;
-    const int n_vtiles = (V + kTile - 1) / kTile;
-    const int n_st = (n_tiles_ub + 1) / 2, n_vq = (n_vtiles + 1) / 2, pairs = max(1, sm_count() / 2);
-    int cap = 160;
-    if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
-    p.splits = dw_splits(n_st, n_vq, pairs, cap);
-    CUtensorMap mp, myt, mones;
-    if (int rc = make_matrix_map(&mp, pstore, rows_ub * (uint64_t)(Vpad / kKC), kKC, bf16, 64)) return rc;
-    p.scr_rows = (int)rows_ub;
-    if (int rc = make_matrix_map(&myt, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, p.HH / 2)) return rc;
-    if (int rc = make_matrix_map(&mones, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, 8)) return rc;
-    dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
-    int rc = bf16 ? launch_v3<MODE_DW, true>(mp, mones, myt, p, grid, smem, stream, &mp)
-                  : launch_v3<MODE_DW, false>(mp, mones, myt, p, grid, smem, stream, &mp);
-    if (rc == 0) trace_dump("DW kept", stream);
     return rc;
 }
 
 int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const void* w16t, uint64_t rows_ub,
                      int n_tiles_ub, int H, int V, int Vpad, bool bf16, const int* meta, const float* bias2,
                      const float* scal, const int* row_label, int blank, const float4* rowmeta, float* dA, float* dW,
-                     float* db, int splits, cudaStream_t stream, const int* run_if) {
+                     float* db, int splits, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (v3_applicable(H, w16t, a16t)) {
         MmaParams p{};
         p.H = H;
@@ -2019,12 +1733,9 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         p.V = V;
         p.n_halves = (H > 256) ? 2 : 1;
         p.HH = H / p.n_halves;
-        p.dbg = getenv("TTX_DBG") ? atoi(getenv("TTX_DBG")) : 0;
-        p.trace = trace_buffer();
-        const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
+                const size_t fixed = (size_t)(p.NKC + kPB) * kChunkBytes + kNumBars * 8 + 16 + 4 * kTile * sizeof(float);
         int ns = 8;
-        if (const char* e = getenv("TTX_MAX_STAGES")) ns = max(2, min(kMaxStages, atoi(e)));
-        while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
+            while (ns > 2 && fixed + (size_t)ns * kChunkBytes > 232448) --ns;
         p.NS = ns;
         const size_t smem = fixed + (size_t)ns * kChunkBytes;
         p.blank = blank;
@@ -2036,7 +1747,6 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         p.dA = dA;
         p.dW = dW;
         p.db = db;
-        const int n_vtiles = (V + kTile - 1) / kTile;
         if (dA) {
             CUtensorMap mx, my, myt;
             if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
@@ -2047,50 +1757,40 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
             int rc = bf16 ? launch_v3<MODE_DA, true>(mx, my, myt, p, grid, smem, stream)
                           : launch_v3<MODE_DA, false>(mx, my, myt, p, grid, smem, stream);
             if (rc) return rc;
-            trace_dump("DA v3", stream);
         }
         if (dW) {
             CUtensorMap mx, my, myt;
             if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
-            const int hs = (p.dbg & 8) ? 2 : 1;
-            if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile / hs)) return rc;
-            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H * (rows_ub / kKC), kKC, bf16, p.HH / 2 / hs)) return rc;
-            // Persistent: units = vocabulary tile pairs x lattice-row splits of at most `cap` stream chunks -- a unit's P' must
-            // fit its CTA's share of the scratch matrix (cap 160: 10 MiB per CTA, 1.5 GB on a B200).
-            const int n_st = (n_tiles_ub + 1) / 2;
-            const int n_vq = (n_vtiles + 1) / 2;
-            const int pairs = max(1, sm_count() / 2);
-            int cap = 160;
-            if (const char* e = getenv("TTX_DW_CHUNKS")) cap = max(1, atoi(e));
-            p.splits = dw_splits(n_st, n_vq, pairs, cap);
-            const int per = (n_st + p.splits - 1) / p.splits;
+                    if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, kTile)) return rc;
+            if (int rc = make_matrix_map(&myt, a16t, (uint64_t)H * (rows_ub / kKC), kKC, bf16, p.HH / 2)) return rc;
+            const DwShape d = dw_shape(n_tiles_ub, V);
+            p.splits = d.splits;
             (void)splits;
-            dim3 grid(2u * (unsigned)max(1, min(n_vq * p.splits, pairs)), 1, 1);
-            void* scratch = nullptr;
+            dim3 grid(d.grid, 1, 1);
             CUtensorMap mscr;
-            p.run_if = run_if;
-            p.run_if_val = 1;
-            if (p.n_halves == 2 && replay_enabled() && !run_if) {    // (the fallback of the kept-P' path runs without scratch)
-                const size_t bytes = 65536 + (size_t)grid.x * kTile * per * 256 * 2;
-                if (int rc = alloc_scratch(&scratch, bytes, stream)) return rc;
-                if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(scratch) + 65536,
-                                             (uint64_t)grid.x * kTile * (uint64_t)(per * 4), kKC, bf16, kTile))
+            bool have_map = false;
+            if (p.n_halves == 2 && ws != nullptr) {
+                if (ws_bytes < dw_scratch_bytes(n_tiles_ub, V)) {
+                    set_error("ttx_joint_grad: workspace of %zu bytes, ttx_joint_workspace_bytes asks for %zu", ws_bytes,
+                              dw_scratch_bytes(n_tiles_ub, V));
+                    return 1;
+                }
+                TTX_CUDA_OK(cudaMemsetAsync(ws, 0, 65536, stream));
+                if (int rc = make_matrix_map(&mscr, static_cast<uint8_t*>(ws) + 65536,
+                                             (uint64_t)grid.x * kTile * (uint64_t)(d.per * 4), kKC, bf16, kTile))
                     return rc;
                 p.scr_rows = (int)(grid.x * kTile);
-                p.scratch = static_cast<uint8_t*>(scratch);
+                p.scratch = static_cast<uint8_t*>(ws);
+                have_map = true;
             }
-            int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr)
-                          : launch_v3<MODE_DW, false>(mx, my, myt, p, grid, smem, stream, scratch ? &mscr : nullptr);
-            if (scratch) TTX_CUDA_OK(cudaFreeAsync(scratch, stream));
-            if (rc == 0) trace_dump("DW v3", stream);
+            int rc = bf16 ? launch_v3<MODE_DW, true>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr)
+                          : launch_v3<MODE_DW, false>(mx, my, myt, p, grid, smem, stream, have_map ? &mscr : nullptr);
             if (rc) return rc;
         }
         return 0;
     }
     Plan pl = plan(H, V, true);
     MmaParams& p = pl.p;
-    p.run_if = run_if;
-    p.run_if_val = 1;
     p.blank = blank;
     p.meta = meta;
     p.bias2 = bias2;
@@ -2107,16 +1807,19 @@ int launch_joint_bwd(const void* a16, const void* w16, const void* a16t, const v
         if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
         if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, box)) return rc;
         p.splits = 1;
-        if (int rc = dispatch<MODE_DA>(bf16, pl.cg, mx, my, p, dim3(n_tiles_ub, p.n_halves, 1), pl.smem, stream))
+        const dim3 grid(n_tiles_ub, p.n_halves, 1);
+        if (int rc = bf16 ? launch<MODE_DA, true, 1>(mx, my, p, grid, pl.smem, stream)
+                          : launch<MODE_DA, false, 1>(mx, my, p, grid, pl.smem, stream))
             return rc;
-        trace_dump("DA", stream);
     }
     if (dW) {
         CUtensorMap mx, my;
         if (int rc = make_tile_map(&mx, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
         if (int rc = make_tile_map(&my, a16, rows_ub, H, bf16, box)) return rc;
         p.splits = splits;
-        if (int rc = dispatch<MODE_DW>(bf16, pl.cg, mx, my, p, dim3(n_vtiles, p.n_halves, splits), pl.smem, stream))
+        const dim3 grid(n_vtiles, p.n_halves, splits);
+        if (int rc = bf16 ? launch<MODE_DW, true, 1>(mx, my, p, grid, pl.smem, stream)
+                          : launch<MODE_DW, false, 1>(mx, my, p, grid, pl.smem, stream))
             return rc;
     }
     return 0;

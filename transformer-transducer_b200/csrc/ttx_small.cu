@@ -505,146 +505,22 @@ struct ActGradSrc {
     int blank;
 };
 
+// Both reductions in ONE pass over the source.  grid = (ceil(T / TT), B); thread = one float4 of h; the block keeps TT
+// frames of Eproj and their dEproj accumulators in registers, walks u, and for every u adds the TT products to both
+// sums: dEproj[b, t, :] is written once at the end, dPproj[b, u, :] gets one 16-byte reduction per (block, u).
+constexpr int kReduceFrames = 8;
 template <bool EW>
-__device__ __forceinline__ float4 act_grad_at(const ActGradSrc& a, size_t grow, int H, int h, const float4& wb) {
-    float4 g = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
-    if (EW) {
-        const float4 rm = __ldg(a.rowmeta + grow);
-        const int lab = __ldg(a.row_label + grow);
-        const float coef = rm.w * a.scal[2];
-        g.x = fmaf(rm.y, wb.x, g.x); g.y = fmaf(rm.y, wb.y, g.y); g.z = fmaf(rm.y, wb.z, g.z); g.w = fmaf(rm.y, wb.w, g.w);
-        if (lab >= 0 && lab != a.blank) {
-            const float4 wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
-            g.x = fmaf(rm.z, wl.x, g.x); g.y = fmaf(rm.z, wl.y, g.y); g.z = fmaf(rm.z, wl.z, g.z); g.w = fmaf(rm.z, wl.w, g.w);
-        }
-        g.x *= coef; g.y *= coef; g.z *= coef; g.w *= coef;
-    }
-    return g;
-}
-
-// dEproj[b,t,:] = sum_u dA[b,t,u,:] * (1 - tanh^2(E[b,t,:] + P[b,u,:]));  grid = (T, B), one float4 of h per thread
-template <bool EW>
-__global__ void reduce_enc_kernel(const ActGradSrc a, const float* __restrict__ eproj,
-                                  const float* __restrict__ pproj, const int* __restrict__ act_lens,
-                                  const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
-                                  int H, float* __restrict__ d_eproj) {
-    const int t = blockIdx.x, b = blockIdx.y;
-    if (meta[1] != 0) return;
-    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
-    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
-    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < Tb) {
-            const float4 e = *reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h);
-            float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
-            for (int u = 0; u < U1b; ++u) {
-                const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
-                const float4 g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
-                acc.x += g.x * sech2(e.x + pp.x);
-                acc.y += g.y * sech2(e.y + pp.y);
-                acc.z += g.z * sech2(e.z + pp.z);
-                acc.w += g.w * sech2(e.w + pp.w);
-            }
-        }
-        *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t) * H + h) = acc;
-    }
-}
-
-// dPproj[b,u,:] += sum over a chunk of t;  grid = (U1, B, t-chunks); d_pproj zero-initialised by the caller
-template <bool EW>
-__global__ void reduce_pred_kernel(const ActGradSrc a, const float* __restrict__ eproj,
-                                   const float* __restrict__ pproj, const int* __restrict__ act_lens,
-                                   const int* __restrict__ label_lens, const int* __restrict__ meta, int T, int U1,
-                                   int H, int t_chunk, float* __restrict__ d_pproj) {
-    const int u = blockIdx.x, b = blockIdx.y;
-    if (meta[1] != 0) return;
-    const int Tb = act_lens[b], U1b = label_lens[b] + 1;
-    if (u >= U1b) return;
-    const int t0 = blockIdx.z * t_chunk, t1 = min(Tb, t0 + t_chunk);
-    if (t0 >= t1) return;
-    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
-    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
-        const float4 pp = *reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h);
-        float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // the label emitted from u is the same for every frame: fetch its W_out row once
-        float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool has_label = false;
-        if (EW) {
-            const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);
-            has_label = lab >= 0 && lab != a.blank;
-            if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
-        }
-        const float gscale = EW ? a.scal[2] : 1.f;
-        for (int t = t0; t < t1; ++t) {
-            const float4 e = __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t) * H + h));
-            float4 g;
-            if (EW) {
-                const size_t grow = base + (size_t)t * U1b + u;
-                g = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
-                const float4 rm = __ldg(a.rowmeta + grow);
-                const float coef = rm.w * gscale;
-                g.x = fmaf(rm.y, wb.x, g.x); g.y = fmaf(rm.y, wb.y, g.y); g.z = fmaf(rm.y, wb.z, g.z); g.w = fmaf(rm.y, wb.w, g.w);
-                if (has_label) {
-                    g.x = fmaf(rm.z, wl.x, g.x); g.y = fmaf(rm.z, wl.y, g.y); g.z = fmaf(rm.z, wl.z, g.z); g.w = fmaf(rm.z, wl.w, g.w);
-                }
-                g.x *= coef; g.y *= coef; g.z *= coef; g.w *= coef;
-            } else {
-                g = act_grad_at<EW>(a, base + (size_t)t * U1b + u, H, h, wb);
-            }
-            acc.x += g.x * sech2(e.x + pp.x);
-            acc.y += g.y * sech2(e.y + pp.y);
-            acc.z += g.z * sech2(e.z + pp.z);
-            acc.w += g.w * sech2(e.w + pp.w);
-        }
-        float* dst = d_pproj + ((size_t)b * U1 + u) * H + h;
-        atomicAdd(dst + 0, acc.x);
-        atomicAdd(dst + 1, acc.y);
-        atomicAdd(dst + 2, acc.z);
-        atomicAdd(dst + 3, acc.w);
-    }
-}
-
-
-// sech^2(x) and tanh(x) from one exponential.
-__device__ __forceinline__ float sech2_tanh(float x, float& th) {
-    const float e = __expf(-2.f * fabsf(x));
-    const float r = __fdividef(1.f, 1.f + e);
-    th = copysignf((1.f - e) * r, x);
-    return 4.f * e * r * r;
-}
-
-// SPARSE (kept-P' weight gradient): the pass below also forms the exact blank / label terms of dL/dW_out and dL/db_out
-// that the kept P' leaves out (see dw_sparse_kernel, which does it alone when no activation gradient is wanted) -- the
-// activation is recomputed from the projections, the lattice coefficients are already in registers.
-constexpr int kBlankSlots = 64;                 // partial rows for the blank row's accumulation
-struct SparseDst {
-    const float* lpb;
-    const float* lpl;
-    const int* flags;
-    float* d_w;
-    float* d_b;
-    float* blank_slots;
-};
-
-// Both reductions in ONE pass over EW (the two kernels above are issue-bound: each of them recomputes tanh' and the
-// bracket for every element).  grid = (ceil(T / TT), B); thread = one float4 of h; the block keeps TT frames of Eproj
-// and their dEproj accumulators in registers, walks u, and for every u adds the TT products to both sums:
-// dEproj[b, t, :] is written once at the end, dPproj[b, u, :] gets one 16-byte reduction per (block, u).
-template <int TT, bool SPARSE>
 __global__ void __launch_bounds__(128) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
                                                           const float* __restrict__ pproj, const int* __restrict__ act_lens,
                                                           const int* __restrict__ label_lens, const int* __restrict__ meta,
                                                           int T, int U1, int H, float* __restrict__ d_eproj,
-                                                          float* __restrict__ d_pproj, const SparseDst sd) {
+                                                          float* __restrict__ d_pproj) {
+    constexpr int TT = kReduceFrames;
     const int b = blockIdx.y, t0 = blockIdx.x * TT;
     if (meta[1] != 0) return;
-    const bool sparse = SPARSE && sd.flags[kKeptAnyDirty] == 0;     // flagged matrix: the recomputing kernel adds the terms
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
     const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
-    const float gscale = a.scal[2];
+    const float gscale = EW ? a.scal[2] : 1.f;
     for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
         float4 e[TT], acc[TT];
 #pragma unroll
@@ -653,70 +529,44 @@ __global__ void __launch_bounds__(128) reduce_both_kernel(const ActGradSrc a, co
             e[i] = (t0 + i < Tb) ? __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t0 + i) * H + h)) : acc[i];
         }
         if (t0 < Tb) {
-            const float4 wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
-            float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);      // SPARSE: blank row of dL/dW_out, over the block's cells
-            float dbb = 0.f;
+            float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
             for (int u = 0; u < U1b; ++u) {
                 const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
-                const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);     // depends on (b, u) only
-                const bool has_label = lab >= 0 && lab != a.blank;
+                bool has_label = false;
                 float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+                if (EW) {
+                    const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);     // depends on (b, u) only
+                    has_label = lab >= 0 && lab != a.blank;
+                    if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+                }
                 float4 g[TT], rm[TT];
-                float lb[TT], ll[TT];                          // SPARSE, thread h == 0: log p(blank), log p(label)
 #pragma unroll
                 for (int i = 0; i < TT; ++i) {                 // all loads of the round first
                     const size_t grow = base + (size_t)min(t0 + i, Tb - 1) * U1b + u;
                     g[i] = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
-                    rm[i] = __ldg(a.rowmeta + grow);
-                    if (SPARSE) {
-                        lb[i] = (h == 0 && sparse) ? __ldg(sd.lpb + grow) : 0.f;
-                        ll[i] = (h == 0 && sparse && has_label) ? __ldg(sd.lpl + grow) : 0.f;
-                    }
+                    if (EW) rm[i] = __ldg(a.rowmeta + grow);
                 }
                 float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 sl = make_float4(0.f, 0.f, 0.f, 0.f);  // SPARSE: row `lab` of dL/dW_out
-                float dbl = 0.f;
 #pragma unroll
                 for (int i = 0; i < TT; ++i) {
-                    const float coef = (t0 + i < Tb) ? rm[i].w * gscale : 0.f;
+                    float coef = (t0 + i < Tb) ? gscale : 0.f;
                     float4 v = g[i];
-                    v.x = fmaf(rm[i].y, wb.x, v.x); v.y = fmaf(rm[i].y, wb.y, v.y); v.z = fmaf(rm[i].y, wb.z, v.z); v.w = fmaf(rm[i].y, wb.w, v.w);
-                    if (has_label) {
-                        v.x = fmaf(rm[i].z, wl.x, v.x); v.y = fmaf(rm[i].z, wl.y, v.y); v.z = fmaf(rm[i].z, wl.z, v.z); v.w = fmaf(rm[i].z, wl.w, v.w);
-                    }
-                    if (SPARSE) {
-                        float4 th;
-                        v.x *= coef * sech2_tanh(e[i].x + pp.x, th.x);
-                        v.y *= coef * sech2_tanh(e[i].y + pp.y, th.y);
-                        v.z *= coef * sech2_tanh(e[i].z + pp.z, th.z);
-                        v.w *= coef * sech2_tanh(e[i].w + pp.w, th.w);
-                        const float cb = coef * rm[i].y, cl = coef * rm[i].z;
-                        sb.x = fmaf(cb, th.x, sb.x); sb.y = fmaf(cb, th.y, sb.y); sb.z = fmaf(cb, th.z, sb.z); sb.w = fmaf(cb, th.w, sb.w);
-                        sl.x = fmaf(cl, th.x, sl.x); sl.y = fmaf(cl, th.y, sl.y); sl.z = fmaf(cl, th.z, sl.z); sl.w = fmaf(cl, th.w, sl.w);
-                        if (h == 0) {                              // (coef = 0 beyond the utterance's last frame)
-                            dbb = fmaf(coef, __expf(lb[i]), dbb);
-                            dbl = fmaf(coef, __expf(ll[i]), dbl);
+                    if (EW) {
+                        coef *= rm[i].w;
+                        v.x = fmaf(rm[i].y, wb.x, v.x); v.y = fmaf(rm[i].y, wb.y, v.y); v.z = fmaf(rm[i].y, wb.z, v.z); v.w = fmaf(rm[i].y, wb.w, v.w);
+                        if (has_label) {
+                            v.x = fmaf(rm[i].z, wl.x, v.x); v.y = fmaf(rm[i].z, wl.y, v.y); v.z = fmaf(rm[i].z, wl.z, v.z); v.w = fmaf(rm[i].z, wl.w, v.w);
                         }
-                    } else {
-                        v.x *= coef * sech2(e[i].x + pp.x);
-                        v.y *= coef * sech2(e[i].y + pp.y);
-                        v.z *= coef * sech2(e[i].z + pp.z);
-                        v.w *= coef * sech2(e[i].w + pp.w);
                     }
+                    v.x *= coef * sech2(e[i].x + pp.x);
+                    v.y *= coef * sech2(e[i].y + pp.y);
+                    v.z *= coef * sech2(e[i].z + pp.z);
+                    v.w *= coef * sech2(e[i].w + pp.w);
                     acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
                     ap.x += v.x; ap.y += v.y; ap.z += v.z; ap.w += v.w;
                 }
                 red_add_v4(d_pproj + ((size_t)b * U1 + u) * H + h, ap.x, ap.y, ap.z, ap.w);
-                if (SPARSE && sparse && has_label) {
-                    red_add_v4(sd.d_w + (size_t)lab * H + h, sl.x, sl.y, sl.z, sl.w);
-                    if (h == 0) atomicAdd(sd.d_b + lab, dbl);
-                }
-            }
-            if (SPARSE && sparse) {      // blank row: through kBlankSlots partial rows (same-address atomics serialise in L2)
-                float* db_ = sd.blank_slots + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % kBlankSlots) * (H + 4) + h;
-                red_add_v4(db_, sb.x, sb.y, sb.z, sb.w);
-                if (h == 0) atomicAdd(db_ + H, dbb);
             }
         }
 #pragma unroll
@@ -724,6 +574,8 @@ __global__ void __launch_bounds__(128) reduce_both_kernel(const ActGradSrc a, co
             if (t0 + i < T) *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t0 + i) * H + h) = acc[i];
     }
 }
+
+constexpr int kBlankSlots = 64;                 // partial rows for the blank row's accumulation (dw_sparse_kernel)
 
 // ------------------------------------------------------------------------------------------- dense-logits entry
 // rnnt_loss called on a materialised (B,T,U1,V) fp32 logits tensor (someone else's joint): one warp per
@@ -986,31 +838,14 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
                   const float* scal, int blank, const float* eproj, const float* pproj, const int* act_lens,
                   const int* label_lens, const int* meta, int B, int T, int U1, int H, float* d_eproj,
                   float* d_pproj, cudaStream_t s) {
-    const int threads = min(256, max(32, H / 4));
+    const int threads = min(128, max(32, H / 4));
     const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
-    const bool ew = rowmeta != nullptr;
     TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
-    const char* fe = getenv("TTX_REDUCE_FUSED");
-    if (ew && !(fe && fe[0] == '0')) {               // one pass over EW for both sums
-        int tt = 8;                                   // frames per block (TTX_REDUCE_TT: 4 / 8 / 16 for A/B runs)
-        if (const char* e = getenv("TTX_REDUCE_TT")) tt = atoi(e);
-        const int nt = min(128, threads);
-        const SparseDst none{};
-        if (tt == 4)
-            reduce_both_kernel<4, false><<<dim3((T + 3) / 4, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj, none);
-        else if (tt == 16)
-            reduce_both_kernel<16, false><<<dim3((T + 15) / 16, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj, none);
-        else
-            reduce_both_kernel<8, false><<<dim3((T + 7) / 8, B), nt, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj, none);
-        TTX_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
-    if (ew) reduce_enc_kernel<true><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
-    else reduce_enc_kernel<false><<<dim3(T, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj);
-    const int t_chunk = 64;
-    const dim3 grid(U1, B, (T + t_chunk - 1) / t_chunk);
-    if (ew) reduce_pred_kernel<true><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, t_chunk, d_pproj);
-    else reduce_pred_kernel<false><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, t_chunk, d_pproj);
+    const dim3 grid((T + kReduceFrames - 1) / kReduceFrames, B);
+    if (rowmeta != nullptr)
+        reduce_both_kernel<true><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+    else
+        reduce_both_kernel<false><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1029,9 +864,8 @@ constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T)
 template <bool BF16>
 __global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float4* __restrict__ rowmeta,
                                   const float* __restrict__ pfac, const int* __restrict__ meta,
-                                  const int* __restrict__ flags, int H, size_t rows_total, float up,
+                                  int H, size_t rows_total, float up,
                                   uint16_t* __restrict__ out) {
-    if (flags[kKeptAnyDirty] != 0) return;
     const size_t m0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (m0 >= rows_total) return;
     const size_t rows_used = (size_t)meta[0] * kTile;
@@ -1078,10 +912,10 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
                                  const int* __restrict__ row_label, const float* __restrict__ lpb,
                                  const float* __restrict__ lpl, const float* __restrict__ scal,
                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,
-                                 const int* __restrict__ meta, const int* __restrict__ flags, int U1, int H, int blank,
+                                 const int* __restrict__ meta, int U1, int H, int blank,
                                  int t_chunk, float* __restrict__ d_w, float* __restrict__ d_b,
                                  float* __restrict__ blank_slots) {
-    if (flags[kKeptAnyDirty] != 0 || meta[1] != 0) return;
+    if (meta[1] != 0) return;
     const int u = blockIdx.x, b = blockIdx.y;
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
     if (u >= U1b) return;
@@ -1150,9 +984,8 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
     }
 }
 
-__global__ void blank_fold_kernel(const float* __restrict__ blank_slots, const int* __restrict__ flags, int H, int blank,
+__global__ void blank_fold_kernel(const float* __restrict__ blank_slots, int H, int blank,
                                   float* __restrict__ d_w, float* __restrict__ d_b) {
-    if (flags[kKeptAnyDirty] != 0) return;
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h > H) return;
     float acc = 0.f;
@@ -1163,21 +996,16 @@ __global__ void blank_fold_kernel(const float* __restrict__ blank_slots, const i
 
 int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta, const int* row_label,
                         const float* lpb, const float* lpl, const float* pfac, const float* scal, const int* act_lens,
-                        const int* label_lens, const int* meta, const int* flags, int B, int T, int U1, int H, int blank,
-                        bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, bool sparse_terms,
-                        cudaStream_t s) {
+                        const int* label_lens, const int* meta, int B, int T, int U1, int H, int blank,
+                        bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, cudaStream_t s) {
     const float up = bf16 ? 1.f : kKeptUp;
     const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
     if (bf16)
-        scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, flags, H, rows_total, up,
+        scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
                                                    (uint16_t*)a16st);
     else
-        scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, flags, H, rows_total, up,
+        scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
                                                     (uint16_t*)a16st);
-    if (!sparse_terms) {                         // the activation-gradient reduction adds them (launch_reduce_sparse)
-        TTX_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
     const int t_chunk = 64;                      // (longer chunks = fewer atomics were slower: 0.31 -> 0.35 ms at 512)
     const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
     const int threads = 128;                     // two groups of 64 threads x 8 joint columns
@@ -1187,11 +1015,11 @@ int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta
     TTX_CUDA_OK(cudaMemsetAsync(slots, 0, slot_bytes, s));
     if (bf16)
         dw_sparse_kernel<true><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                      label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b, slots);
+                                                      label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots);
     else
         dw_sparse_kernel<false><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                       label_lens, meta, flags, U1, H, blank, t_chunk, d_w, d_b, slots);
-    blank_fold_kernel<<<(H + 1 + 127) / 128, 128, 0, s>>>(slots, flags, H, blank, d_w, d_b);
+                                                       label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots);
+    blank_fold_kernel<<<(H + 1 + 127) / 128, 128, 0, s>>>(slots, H, blank, d_w, d_b);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1213,25 +1041,6 @@ int launch_dense_grad(const float* acts, const float4* rowmeta, const int* row_l
     dense_grad_kernel<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(acts, rowmeta, row_label, scal,
                                                                               act_lens, label_lens, meta, B, T, U1, V,
                                                                               blank, grads);
-    TTX_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-// launch_reduce for EW sources + the exact blank / label terms of the kept-P' weight gradient in the same pass.
-int launch_reduce_sparse(const float* src, const float4* rowmeta, const int* row_label, const float* w_out,
-                         const float* scal, int blank, const float* eproj, const float* pproj, const int* act_lens,
-                         const int* label_lens, const int* meta, int B, int T, int U1, int H, float* d_eproj,
-                         float* d_pproj, const int* flags, const float* lpb, const float* lpl, void* a16st,
-                         size_t rows_total, float* d_w, float* d_b, cudaStream_t s) {
-    const int threads = min(128, max(32, H / 4));
-    const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
-    float* slots = reinterpret_cast<float*>(static_cast<uint8_t*>(a16st) + (size_t)(H + 16) * rows_total * 2);
-    TTX_CUDA_OK(cudaMemsetAsync(slots, 0, (size_t)kBlankSlots * (H + 4) * sizeof(float), s));
-    TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
-    const SparseDst sd{lpb, lpl, flags, d_w, d_b, slots};
-    reduce_both_kernel<8, true><<<dim3((T + 7) / 8, B), threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1,
-                                                                        H, d_eproj, d_pproj, sd);
-    blank_fold_kernel<<<(H + 1 + 127) / 128, 128, 0, s>>>(slots, flags, H, blank, d_w, d_b);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

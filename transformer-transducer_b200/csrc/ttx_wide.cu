@@ -6,7 +6,7 @@
 //   sp_kernel      S = A16 . W16^T, BOTH operands streamed in 64-column K chunks (no stationary tile: 128 rows x H no longer
 //                  fit shared memory), two 256-column S accumulators in TMEM so that the exponential epilogue of chunk j
 //                  overlaps the MMAs of chunk j + 1.  Epilogue: online log-sum-exp statistics (lse, log p(blank), log p(label))
-//                  + P' written straight from registers to the blocked P' matrix, [Vpad / 64][rows][64].
+//                  + P' staged in shared memory and moved by TMA stores to the blocked P' matrix, [Vpad / 64][rows][64].
 //   kp_kernel<PW>  EW = P' . W16 for a 512-column block of H (two 256-column slabs = all of TMEM), K = vocabulary.
 //   kp_kernel<DW>  dW_out += P'^T . As for a 512-column block of H, K = lattice rows; As = scaled A16^T (ttx_small.cu).
 //
@@ -16,7 +16,6 @@
 // the flagged pairs against the FINAL reference -- so the matrix the two products read is always consistent and there is
 // no whole-batch fallback.
 #include "ttx_common.cuh"
-#include <stdlib.h>
 
 namespace ttx {
 
@@ -33,7 +32,6 @@ struct WideParams {
     int store_rows;          // rows of the P' matrix; its row 0 is lattice row tile_lo * 128
     int redo;                // sp: only tile pairs whose flag is set, against the stored final reference
     int n_hb;                // kp: 512-column blocks of H
-    int dbg;                 // timing experiments (TTX_WIDE_DBG): 1 = no S-pass MMAs, 2 = no epilogue math / staging
     int splits;              // kp<DW>: lattice-row splits
     const int* meta;
     const float* bias2;
@@ -128,14 +126,14 @@ struct EventWait {
 };
 
 // =========================================================================================================== S pass
-// XS (H <= 512): the pair's A16 tiles stay in shared memory for the whole unit (loaded chunk by chunk behind their own
-// barriers) and only W16 streams: half the bytes per MMA, which takes the kernel from the L2-to-SM bandwidth bound of
-// the fully streamed form to its epilogue bound.
-template <bool BF16, bool XS>
+// (A variant that kept the pair's A16 tiles stationary in shared memory for H <= 512 and streamed only W16 -- half the
+// bytes per MMA -- measured 2.23 ms against 2.02 ms at configs[1]: the stationary tile leaves room for three ring stages
+// only, and the kernel is bound by its epilogue and the pipeline's latency, not by the L2-to-SM bandwidth.)
+template <bool BF16>
 __global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
           const __grid_constant__ CUtensorMap mapP, const WideParams p) {
-    constexpr int STG = XS ? kChunkBytes : kSpStage;       // bytes of one ring stage (W chunk [+ A chunk])
+    constexpr int STG = kSpStage;                          // bytes of one ring stage (A chunk + W chunk)
     constexpr int NSB = 2;                                 // staging buffers: one 64-column P' sub-tile each, used in turn
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
@@ -152,8 +150,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         if (threadIdx.x == 0) printf("ttx: dynamic shared memory is not 1024-byte aligned (0x%x)\n", smem_base);
         __trap();
     }
-    const uint32_t sX = smem_base;                         // XS: the stationary A16 tile, NKC chunks
-    const uint32_t sRing = sX + (XS ? p.NKC * kChunkBytes : 0);
+    const uint32_t sRing = smem_base;
     const uint32_t sStage = sRing + p.NS * STG;            // NSB [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
     const uint32_t sBar = sStage + NSB * kChunkBytes;
     const uint32_t sTmemPtr = sBar + 40 * 8;
@@ -168,8 +165,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
     auto bar_pwritten = [&](int b) { return sBar + 8 * (20 + b); };   // this CTA's epilogue warps have staged a sub-tile in buffer b
     auto bar_pfree = [&](int b) { return sBar + 8 * (22 + b); };      // ... and the TMA store has read it out of shared memory
-    auto bar_xfull = [&](int c) { return sBar + 8 * (24 + c); };   // XS: chunk c of the stationary tile has landed
-    const uint32_t bar_xempty = sBar + 8 * 32;             // XS: the unit's last S pass has read the stationary tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kSpProducerWarp && lane == 0) {
@@ -180,8 +175,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             mbar_init(bar_pwritten(b), kSpEpiWarps / 2);     // the eight warps that stage into buffer b
             mbar_init(bar_pfree(b), 1);
         }
-        for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
-        mbar_init(bar_xempty, 1);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
@@ -204,33 +197,23 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         if (warp == kSpProducerWarp && lane == 0) {
             // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
             Ring r;
-            int xt = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
                 const int x_row0 = (p.tile_lo + unit * 2 + (int)rank) * kTile;
-                if (XS) {
-                    if (xt > 0) mbar_wait(bar_xempty, (xt - 1) & 1);
-                    ++xt;
-                    for (int c = 0; c < p.NKC; ++c) {
-                        if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
-                        tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
-                    }
-                }
                 for (int j = 0; j < p.n_vchunks; ++j)
                     for (int c = 0; c < p.NKC; ++c) {
                         mbar_wait(bar_empty(r.stage), r.phase ^ 1);
                         if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STG);
                         const uint32_t dst = sRing + r.stage * STG;
-                        if (!XS) tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
-                        tma_load_2d_pair(dst + (XS ? 0 : kChunkBytes), &mapY, bar_full(r.stage), c * kKC,
-                                         j * 256 + (int)rank * kTile);
+                        tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
+                        tma_load_2d_pair(dst + kChunkBytes, &mapY, bar_full(r.stage), c * kKC, j * 256 + (int)rank * kTile);
                         r.advance(p.NS);
                     }
             }
         } else if (warp == kSpWatchWarp && lane == 0 && leader) {
             // =================================================== barrier watcher: the issuer's barriers, in its order
             volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
-            int done = 0, g = 0, xt = 0;
+            int done = 0, g = 0;
             Ring r;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
@@ -238,13 +221,11 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     mbar_wait(bar_sempty(g & 1), ((g >> 1) & 1) ^ 1);
                     *ready = ++done;
                     for (int c = 0; c < p.NKC; ++c) {
-                        if (XS && j == 0) mbar_wait(bar_xfull(c), xt & 1);
                         mbar_wait(bar_full(r.stage), r.phase);
                         *ready = ++done;
                         r.advance(p.NS);
                     }
                 }
-                ++xt;
             }
         } else if (warp == kSpWatchWarp + 1 && lane == 0) {
             // =================================================== storer (each CTA): staged P' tile -> the blocked matrix
@@ -255,9 +236,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                 for (int j = 0; j < p.n_vchunks; ++j)
                     for (int gg = 0; gg < 4; ++gg, ++n) {           // sub-tile n goes through buffer n % NSB
                         const int b = n % NSB;
-                        if (p.dbg & 2) continue;
-                        mbar_wait(bar_pwritten(b), (n / NSB) & 1);
-                        if (!(p.dbg & 4))
+                            mbar_wait(bar_pwritten(b), (n / NSB) & 1);
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(reinterpret_cast<uint64_t>(&mapP)), "r"(sStage + b * kChunkBytes), "r"(0),
                                        "r"((j * 4 + gg) * p.store_rows + srow0)
@@ -272,7 +251,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         } else if (warp == kSpMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
-            const uint32_t rlo = desc_lo(sRing), xlo = desc_lo(sX);
+            const uint32_t rlo = desc_lo(sRing);
             EventWait ev{reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base))};
             int stage = 0, g = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -284,16 +263,12 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     for (int c = 0; c < p.NKC; ++c) {
                         ev.wait();                          // ring stage has landed
                         tc_fence_after();
-                        const uint32_t a = XS ? xlo + c * (kChunkBytes >> 4) : rlo + stage * (STG >> 4);
-                        const uint32_t b = XS ? rlo + stage * (STG >> 4) : a + (kChunkBytes >> 4);
-                        if (!(p.dbg & 1)) {
+                        const uint32_t a = rlo + stage * (STG >> 4), b = a + (kChunkBytes >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
-                        }
+                        for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
                         umma_commit_pair(bar_empty(stage));
                         if (++stage == p.NS) stage = 0;
                     }
-                    if (XS && j == p.n_vchunks - 1) umma_commit_pair(bar_xempty);   // the next unit's tile may replace this one
                     umma_commit_pair(bar_sfull(g & 1));
                 }
             }
@@ -391,7 +366,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         epi_arrive(bar_sempty(g & 1));
                     }
                     uint32_t pk[16];
-                    if (p.dbg & 2) continue;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float y0, y1, y2, y3;
@@ -399,8 +373,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         unpk2(fma2(pk2u(acc[4 * e + 0], acc[4 * e + 1]), c2, add2(pk2(bv.x, bv.y), krow2)), y0, y1);
                         unpk2(fma2(pk2u(acc[4 * e + 2], acc[4 * e + 3]), c2, add2(pk2(bv.z, bv.w), krow2)), y2, y3);
                         lmax = fmaxf(lmax, fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
-                        const bool nomufu = p.dbg & 8;
-                        const float e0 = nomufu ? y0 : ex2f(y0), e1 = nomufu ? y1 : ex2f(y1), e2 = nomufu ? y2 : ex2f(y2), e3 = nomufu ? y3 : ex2f(y3);
+                        const float e0 = ex2f(y0), e1 = ex2f(y1), e2 = ex2f(y2), e3 = ex2f(y3);
                         s01 = add2(s01, pk2(e0, e1));
                         s23 = add2(s23, pk2(e2, e3));
                         acc[4 * e + 0] = __float_as_uint(y0); acc[4 * e + 1] = __float_as_uint(y1);
@@ -847,13 +820,10 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.mref = mref;
     p.pstore = static_cast<uint16_t*>(pstore);
     p.flags = flags;
-    p.dbg = getenv("TTX_WIDE_DBG") ? atoi(getenv("TTX_WIDE_DBG")) : 0;
-    const bool xs = H <= 512 && !getenv("TTX_SP_STREAM_X");        // (the switch: A/B measurement of the stationary tile)
-    const size_t stg = xs ? kChunkBytes : kSpStage;
-    const size_t fixed = (xs ? (size_t)(p.NKC + 2) : 2) * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16 + 4 * 512 * 4;
+    const size_t fixed = 2 * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16 + 4 * 512 * 4;
     p.NS = 8;
-    while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
-    const size_t smem = (size_t)p.NS * stg + fixed;
+    while (p.NS > 2 && (size_t)p.NS * kSpStage + fixed > 232448) --p.NS;
+    const size_t smem = (size_t)p.NS * kSpStage + fixed;
     CUtensorMap mx, my, mp;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
@@ -861,10 +831,8 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
     for (int redo = 0; redo < 2; ++redo) {
         p.redo = redo;
-        int rc = xs ? (bf16 ? launch_pair(sp_kernel<true, true>, kSpThreads, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, true>, kSpThreads, grid, smem, stream, mx, my, mp, p))
-                    : (bf16 ? launch_pair(sp_kernel<true, false>, kSpThreads, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, false>, kSpThreads, grid, smem, stream, mx, my, mp, p));
+        int rc = bf16 ? launch_pair(sp_kernel<true>, kSpThreads, grid, smem, stream, mx, my, mp, p)
+                      : launch_pair(sp_kernel<false>, kSpThreads, grid, smem, stream, mx, my, mp, p);
         if (rc) return rc;
     }
     return 0;

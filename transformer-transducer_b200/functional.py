@@ -24,8 +24,10 @@ def _stream(dev):
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
-KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_joint_fwd_grad_keep": 1, "ttx_weight_grad_kept": 5, "ttx_reduce_act_grad_ew_kept": 2, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1, "ttx_wide_sp": 2, "ttx_wide_pw": 1, "ttx_wide_dw": 1, "ttx_kept_prepare": 4, "ttx_transpose16": 1, "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
-                    "ttx_lattice_fwd_bwd": 2, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 2,
+KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_reduce_act_grad_ew": 1, "ttx_rows_lse": 1, "ttx_rows_grad": 1,
+                    "ttx_wide_sp": 2, "ttx_wide_pw": 1, "ttx_wide_dw": 1, "ttx_kept_prepare": 3, "ttx_transpose16": 1,
+                    "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
+                    "ttx_lattice_fwd_bwd": 2, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 1,
                     "ttx_dense_lse": 1, "ttx_dense_grad": 1}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
 
@@ -111,12 +113,10 @@ def _dw_splits(sms, V, H, ntub):
     return best
 
 
-def _keep_fits(plan, H, Vpad, dev):
-    """The kept-P' weight gradient (H = 512) holds rows * Vpad 16-bit values from forward to backward: used when that
-    fits TTX_KEEP_GB (default 32; 0 disables)."""
-    budget = float(os.environ.get("TTX_KEEP_GB", "32")) * 2**30
-    need = plan.rows * Vpad * 2
-    return H == 512 and 0 < need <= budget and (plan.ntub + 1) // 2 <= 16383
+def _workspace(lib, which, plan, H, V, dev):
+    """Scratch of the fused launches' P' replay (H = 512; bounded by the CTA count, ~165 MB / <= 1.5 GB on a B200)."""
+    n = int(lib.ttx_joint_workspace_bytes(which, plan.ntub, H, V, plan.idx))
+    return (torch.empty(n, dtype=torch.uint8, device=dev), n) if n > 0 else (None, 0)
 
 
 def supported_width(H):
@@ -124,6 +124,14 @@ def supported_width(H):
 
 
 class FusedJointRNNT(torch.autograd.Function):
+    """Joint widths up to 512 without any V-wide tensor in HBM: forward statistics + EW in one tensor-core launch, weight
+    gradient by a second launch that recomputes the projection.  The default for H < 512, the memory-bounded alternative
+    at 512 (WideJointRNNT keeps the 16-bit softmax numerators instead and is faster when they fit)."""
+
+    SEPARATE_ACT_GRAD = False   # True: plain forward + a separate activation-gradient launch (tests A/B the two routes)
+    REPLAY = True               # False: no workspace -- the second half of the joint columns recomputes its projection
+    PAIR_WIDTHS = (128, 256, 512)   # widths whose backward runs the CTA-pair kernels (they need transposed operand copies)
+
     @staticmethod
     def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
         need_grad = any(ctx.needs_input_grad[:4])      # (grad mode is off inside Function.forward)
@@ -151,7 +159,7 @@ class FusedJointRNNT(torch.autograd.Function):
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
             bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
             # K-major (transposed) copies of both operands feed the gradient pass of the backward pair kernel
-            with_t = need_grad and H in (128, 256, 512)
+            with_t = need_grad and H in FusedJointRNNT.PAIR_WIDTHS
             w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if with_t else None
             a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev) if with_t else None
             _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
@@ -165,26 +173,14 @@ class FusedJointRNNT(torch.autograd.Function):
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             # When the activations need gradients the forward also accumulates EW = sum_v p_v W_out[v] (minus the
             # blank / label columns) on the tensor cores, so the backward has no activation-gradient MMA pass.
-            ew = kept = None
+            ew = None
             if (with_t and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and lib.ttx_fwd_grad_supported_h(H)
-                    and os.environ.get("TTX_NO_FWD_GRAD", "0") != "1"):
+                    and not FusedJointRNNT.SEPARATE_ACT_GRAD):
                 ew = plan.rowf(H)
-                if (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]) and _keep_fits(plan, H, Vpad, dev):
-                    # keep the softmax numerators P' (16 bit) for the weight gradient: no second projection pass there.
-                    # If the device cannot hold the matrix next to the rest of the model, the recomputing path can.
-                    try:
-                        kept = (torch.empty(plan.rows * Vpad, dtype=torch.int16, device=dev),
-                                torch.zeros(16384, dtype=torch.int32, device=dev), plan.rowf())
-                    except torch.cuda.OutOfMemoryError:
-                        kept = None
-                if kept is not None:
-                    _call("ttx_joint_fwd_grad_keep", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal),
-                          _p(row_label), _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl),
-                          _p(ew), _p(kept[0]), _p(kept[1]), _p(kept[2]), plan.idx, st, label="ttx_joint_fwd_grad")
-                else:
-                    _call("ttx_joint_fwd_grad", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label),
-                          _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(ew),
-                          plan.idx, st)
+                ws, ws_n = _workspace(lib, 0, plan, H, V, dev) if FusedJointRNNT.REPLAY else (None, 0)
+                _call("ttx_joint_fwd_grad", dev, _p(a16), _p(w16), _p(w16t), _p(bias2), _p(scal), _p(row_label),
+                      _p(plan.meta), plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(ew), _p(ws),
+                      ws_n, plan.idx, st)
             else:
                 _call("ttx_joint_lse_fwd", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
                       plan.ntub, H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), plan.idx, st)
@@ -192,7 +188,7 @@ class FusedJointRNNT(torch.autograd.Function):
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
         ctx.transposed = (a16t, w16t)
-        ctx.ew, ctx.w32, ctx.kept = ew, (w if ew is not None else None), kept
+        ctx.ew, ctx.w32 = ew, (w if ew is not None else None)
         ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta)
         return costs
 
@@ -219,35 +215,17 @@ class FusedJointRNNT(torch.autograd.Function):
                 # two launches (activation gradient, weight gradient) so each shows up separately in profiles
                 if need_act and ew is None:
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
-                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, plan.idx, st,
+                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, _p(d_act), None, None, 1, None, 0, plan.idx, st,
                           n_kernels=1, label="ttx_joint_grad[dA]")
-                kept_sparse = None
-                if need_w and ctx.kept is not None:
-                    pstore, pflags, pfac = ctx.kept
-                    a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
-                    # the exact blank / label terms ride on the activation-gradient reduction when there is one
-                    fuse = need_act and ew is not None and os.environ.get("TTX_SPARSE_FUSED", "0") == "1"
-                    _call("ttx_weight_grad_kept", dev, _p(pstore), _p(pflags), _p(pfac), _p(a16), _p(w16), _p(a16t),
-                          _p(w16t), _p(a16st), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), _p(rowmeta), _p(lpb),
-                          _p(lpl), _p(plan.act_lens), _p(plan.label_lens), B, T, U1, plan.ntub, H, V, ctx.blank,
-                          ctx.bf16, int(not fuse), _p(d_w), _p(d_b), plan.idx, st, n_kernels=3 if fuse else 5,
-                          label="ttx_joint_grad[dW]")
-                    if fuse:
-                        kept_sparse = (pflags, a16st)
-                    ctx.kept = None
-                elif need_w:
+                if need_w:
+                    ws, ws_n = _workspace(lib, 1, plan, H, V, dev) if (FusedJointRNNT.REPLAY and a16t is not None) else (None, 0)
                     _call("ttx_joint_grad", dev, _p(a16), _p(w16), _p(a16t), _p(w16t), _p(bias2), _p(scal), _p(row_label), _p(plan.meta),
-                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, plan.idx,
-                          st, n_kernels=1, label="ttx_joint_grad[dW]")
+                          _p(rowmeta), plan.ntub, H, V, ctx.blank, ctx.bf16, None, _p(d_w), _p(d_b), splits, _p(ws), ws_n,
+                          plan.idx, st, n_kernels=1, label="ttx_joint_grad[dW]")
             if need_act:
                 d_ep = torch.zeros(B, T, H, dtype=torch.float32, device=dev)   # (stay zero if the lengths were flagged bad)
                 d_pp = torch.zeros(B, U1, H, dtype=torch.float32, device=dev)
-                if ew is not None and kept_sparse is not None:
-                    _call("ttx_reduce_act_grad_ew_kept", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
-                          ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
-                          _p(d_ep), _p(d_pp), _p(kept_sparse[0]), _p(lpb), _p(lpl), _p(kept_sparse[1]), plan.ntub,
-                          _p(d_w), _p(d_b), plan.idx, st, label="ttx_reduce_act_grad_ew")
-                elif ew is not None:
+                if ew is not None:
                     _call("ttx_reduce_act_grad_ew", dev, _p(ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
                           ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
                           _p(d_ep), _p(d_pp), plan.idx, st)
@@ -265,13 +243,21 @@ def wide_width(H):
     return bool(_lib.get().ttx_wide_supported_h(int(H)))
 
 
+def _chunk_ranges(ntub, Vpad, budget_bytes):
+    """Tile ranges (tile_lo even) whose 16-bit P' matrix (128 * tiles rows x Vpad) fits the budget; at least one tile
+    pair per range."""
+    tiles = max(2, int(budget_bytes // (128 * Vpad * 2)) & ~1)
+    return [(t0, min(tiles, ntub - t0)) for t0 in range(0, ntub, tiles)]
+
+
 def _wide_chunks(plan, Vpad):
-    """Tile ranges (tile_lo even) whose 16-bit P' matrix fits the budget (TTX_KEEP_GB, default 32; at least one tile
-    pair).  One range = the whole batch: P' is kept from forward to backward; several: one chunk-sized matrix, and the
-    backward recomputes each chunk's P'."""
+    """One range = the whole batch: P' is kept from forward to backward; several: one chunk-sized matrix, and the backward
+    recomputes each chunk's P'.  Budget: TTX_KEEP_GB (default 32), and at most half of what the device can still give
+    (driver-free memory + the caching allocator's own free blocks)."""
     budget = max(float(os.environ.get("TTX_KEEP_GB", "32")), 0.0) * 2**30
-    tiles = max(2, int(budget // (128 * Vpad * 2)) & ~1)
-    return [(t0, min(tiles, plan.ntub - t0)) for t0 in range(0, plan.ntub, tiles)]
+    free_dev, _ = torch.cuda.mem_get_info(plan.dev)
+    cached = torch.cuda.memory_reserved(plan.dev) - torch.cuda.memory_allocated(plan.dev)
+    return _chunk_ranges(plan.ntub, Vpad, min(budget, 0.5 * (free_dev + cached)))
 
 
 class WideJointRNNT(torch.autograd.Function):
@@ -359,10 +345,9 @@ class WideJointRNNT(torch.autograd.Function):
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
             if need_w:
                 a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
-                zflags = torch.zeros(16384, dtype=torch.int32, device=dev)
                 _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl), _p(pfac),
-                      _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), _p(zflags), B, T, U1, plan.ntub, H,
-                      ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st)
+                      _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, plan.ntub, H, ctx.blank,
+                      ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st)
                 pstore = ctx.pstore
                 recompute = pstore is None
                 if recompute:
@@ -498,15 +483,22 @@ class ChunkedJointRNNT(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+# None: the default routing below.  "fused": the recomputing kernels also at H = 512 (nothing V-wide in HBM).  "chunked":
+# the library-GEMM fallback for every width.  (Tests and bench.py A/B the routes through this.)
+ROUTE = None
+
+
 def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, sizes=None):
     """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out.
 
-    Joint widths covered by the fused tcgen05 kernels run there; other multiples of 64 take the chunked path."""
+    H a multiple of 512: three streamed tcgen05 products around the kept 16-bit softmax numerators (WideJointRNNT);
+    smaller multiples of 64 (<= 256, 384): the fused recomputing kernels (FusedJointRNNT); other multiples of 64: the
+    chunked library-GEMM fallback."""
     dev = eproj.device
     H = eproj.shape[-1]
-    if os.environ.get("TTX_FORCE_CHUNKED", "0") == "1":
+    if ROUTE == "chunked":
         fn = ChunkedJointRNNT
-    elif wide_width(H) and (H > 512 or os.environ.get("TTX_WIDE", "0") == "1"):
+    elif wide_width(H) and ROUTE != "fused":                            # 512, 1024, 1536, ...
         fn = WideJointRNNT
     else:
         fn = FusedJointRNNT if supported_width(H) else ChunkedJointRNNT
