@@ -181,6 +181,21 @@ int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, con
                      int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,
                      int device, void* stream);
 
+/* ---- Pre-projections of the joint (tt/model.py:35 forward_layer, split into its encoder / decoder halves;
+ * joint_network.py:28-31,48 lin_enc / lin_dec), fp32 row-major with leading dimensions in floats.  tcgen05 kind::tf32 with
+ * on-chip error compensation (x = hi + lo; hi.hi + lo.hi + hi.lo accumulated in fp32): fp32-grade results like the
+ * reference's SGEMM.  N, K and the leading dimensions must be multiples of 4, pointers 16-byte aligned.
+ *   ttx_proj_fwd     y (M,N)  = x (M,K) . w (N,K)^T + bias (N, or NULL)
+ *   ttx_proj_bwd_x   dx (M,K) = dy (M,N) . w (N,K)
+ *   ttx_proj_bwd_w   dw (N,K) += dy (M,N)^T . x (M,K);  db (N) += column sums of dy (db may be NULL).  dw and db must be
+ *                    zero-filled (or hold a running sum): the contraction is split over CTAs that reduce into them. */
+int ttx_proj_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K, float* y, int ldy,
+                 int device, void* stream);
+int ttx_proj_bwd_x(const float* dy, int lddy, const float* w, int ldw, int M, int N, int K, float* dx, int lddx, int device,
+                   void* stream);
+int ttx_proj_bwd_w(const float* dy, int lddy, const float* x, int ldx, int M, int N, int K, float* dw, int lddw, float* db,
+                   int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

@@ -138,6 +138,39 @@ def test_lattice_wavefront_matches_float64_oracle(T, U):
     assert ((-llb.cpu() - costs_w) / costs_w).abs().max() < 1e-6
 
 
+# ----------------------------------------------------------------------------- pre-projection kernels through the C ABI
+@pytest.mark.parametrize("M,N,K,ldw", [(12800, 512, 512, 512), (1312, 512, 512, 1024), (37, 128, 100, 100), (300, 1024, 320, 640),
+                                       (129, 260, 36, 36)])
+def test_projection_kernels_are_fp32_grade(M, N, K, ldw):
+    """ttx_proj_fwd / _bwd_x / _bwd_w (tcgen05 TF32 products with on-chip hi/lo error compensation) against float64, on
+    shapes with row / column / contraction tails and a weight that is a column slice of a wider matrix.  Tolerance 2e-5
+    relative L2: the compensated product itself is good to 2^-22, what remains is the tensor core's truncating fp32
+    accumulation (measured 3e-6 .. 8e-6); a plain TF32 product sits at 3e-4, the reference's SGEMM (tt/model.py:35,
+    joint_network.py:28-31) at 3e-7, and the path's gradient tolerance is 1e-3."""
+    import ctypes
+    lib = _lib.get()
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    wfull = torch.randn(N, ldw, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    w = wfull[:, ldw - K:]
+    xd, wd, bd, dyd = x.to(DEV), wfull.to(DEV)[:, ldw - K:], b.to(DEV), dy.to(DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    y = torch.full((M, N), float("nan"), device=DEV)
+    dx = torch.full((M, K), float("nan"), device=DEV)
+    dw, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    _lib.check(lib.ttx_proj_fwd(p(xd), K, p(wd), ldw, p(bd), M, N, K, p(y), N, 0, None), "proj_fwd")
+    _lib.check(lib.ttx_proj_bwd_x(p(dyd), N, p(wd), ldw, M, N, K, p(dx), K, 0, None), "proj_bwd_x")
+    _lib.check(lib.ttx_proj_bwd_w(p(dyd), N, p(xd), K, M, N, K, p(dw), K, p(db), 0, None), "proj_bwd_w")
+    torch.cuda.synchronize()
+    x64, w64, dy64 = x.double(), w.double(), dy.double()
+    for got, want, ref32 in ((y, x64 @ w64.T + b.double(), x @ w.T + b), (dx, dy64 @ w64, dy @ w),
+                             (dw, dy64.T @ x64, dy.T @ x), (db, dy64.sum(0), dy.sum(0))):
+        err, err32 = rel(got, want), rel(ref32, want)
+        assert err < max(2e-5, 3 * err32), (err, err32)
+
+
 # ----------------------------------------------------------------------------- fused path vs oracle
 def _espnet_case(B, T, U, V, D, H, act_lens, label_lens, seed=0, dtype=torch.float32):
     torch.manual_seed(seed)

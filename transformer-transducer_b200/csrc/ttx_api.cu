@@ -60,6 +60,10 @@ int launch_wide_pw(const void*, uint64_t, const void*, int, int, int, int, int, 
 int launch_wide_dw(const void*, uint64_t, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*,
                    float*, float*, cudaStream_t);
 
+int launch_proj_fwd(const float*, int, const float*, int, const float*, int, int, int, float*, int, cudaStream_t);
+int launch_proj_bwd_x(const float*, int, const float*, int, int, int, int, float*, int, cudaStream_t);
+int launch_proj_bwd_w(const float*, int, const float*, int, int, int, int, float*, int, float*, cudaStream_t);
+
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -331,6 +335,44 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
     TTX_ENTER(device);
     return launch_reduce(ew, (const float4*)rowmeta, row_label, w_out, scal, blank, eproj, pproj, act_lens, label_lens,
                          meta, B, T, U1, H, d_eproj, d_pproj, (cudaStream_t)stream);
+}
+
+static int proj_args_ok(const char* who, const void* a, const void* b, const void* c, int M, int N, int K, int lda, int ldb,
+                        int ldc, int mina, int minb, int minc) {
+    if (!a || !b || !c) {
+        set_error("%s: null pointer", who);
+        return 1;
+    }
+    if (M <= 0 || N <= 0 || K <= 0 || (N & 3) || (K & 3) || lda < mina || ldb < minb || ldc < minc || ((lda | ldb | ldc) & 3) ||
+        (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) {
+        set_error("%s: M=%d N=%d K=%d with leading dimensions %d, %d, %d -- N, K and the leading dimensions must be multiples "
+                  "of 4 floats, the pointers 16-byte aligned", who, M, N, K, lda, ldb, ldc);
+        return 1;
+    }
+    return 0;
+}
+
+int ttx_proj_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, int M, int N, int K, float* y, int ldy,
+                 int device, void* stream) {
+    if (int rc = proj_args_ok("ttx_proj_fwd", x, w, y, M, N, K, ldx, ldw, ldy, K, K, N)) return rc;
+    TTX_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "ttx_proj_fwd: bias must be 16-byte aligned");
+    TTX_ENTER(device);
+    return launch_proj_fwd(x, ldx, w, ldw, bias, M, N, K, y, ldy, (cudaStream_t)stream);
+}
+
+int ttx_proj_bwd_x(const float* dy, int lddy, const float* w, int ldw, int M, int N, int K, float* dx, int lddx, int device,
+                   void* stream) {
+    if (int rc = proj_args_ok("ttx_proj_bwd_x", dy, w, dx, M, N, K, lddy, ldw, lddx, N, K, K)) return rc;
+    TTX_ENTER(device);
+    return launch_proj_bwd_x(dy, lddy, w, ldw, M, N, K, dx, lddx, (cudaStream_t)stream);
+}
+
+int ttx_proj_bwd_w(const float* dy, int lddy, const float* x, int ldx, int M, int N, int K, float* dw, int lddw, float* db,
+                   int device, void* stream) {
+    if (int rc = proj_args_ok("ttx_proj_bwd_w", dy, x, dw, M, N, K, lddy, ldx, lddw, N, K, K)) return rc;
+    TTX_REQUIRE(!db || ((uintptr_t)db & 15) == 0, "ttx_proj_bwd_w: db must be 16-byte aligned");
+    TTX_ENTER(device);
+    return launch_proj_bwd_w(dy, lddy, x, ldx, M, N, K, dw, lddw, db, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

@@ -1422,7 +1422,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled get_encode() {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void* ptr = nullptr;

@@ -28,7 +28,7 @@ KERNELS_PER_CALL = {"ttx_joint_fwd_grad": 1, "ttx_reduce_act_grad_ew": 1, "ttx_r
                     "ttx_wide_sp": 2, "ttx_wide_pw": 1, "ttx_wide_dw": 1, "ttx_kept_prepare": 3, "ttx_transpose16": 1,
                     "ttx_prepare": 1, "ttx_cast_weight": 2, "ttx_joint_act": 1, "ttx_joint_lse_fwd": 1,
                     "ttx_lattice_fwd_bwd": 2, "ttx_grad_coeffs": 2, "ttx_joint_grad": 2, "ttx_reduce_act_grad": 1,
-                    "ttx_dense_lse": 1, "ttx_dense_grad": 1}
+                    "ttx_dense_lse": 1, "ttx_dense_grad": 1, "ttx_proj_fwd": 1, "ttx_proj_bwd_x": 1, "ttx_proj_bwd_w": 2}
 PROFILE = None  # set to a list by bench.py: receives (name, start_event, end_event, n_kernels)
 
 
@@ -250,14 +250,21 @@ def _chunk_ranges(ntub, Vpad, budget_bytes):
     return [(t0, min(tiles, ntub - t0)) for t0 in range(0, ntub, tiles)]
 
 
-def _wide_chunks(plan, Vpad):
-    """One range = the whole batch: P' is kept from forward to backward; several: one chunk-sized matrix, and the backward
-    recomputes each chunk's P'.  Budget: TTX_KEEP_GB (default 32), and at most half of what the device can still give
-    (driver-free memory + the caching allocator's own free blocks)."""
+def _wide_pstore(plan, Vpad, dev):
+    """The P' matrix and the tile ranges it is used for.  One range = the whole batch: P' is kept from forward to
+    backward; several: one chunk-sized matrix, and the backward recomputes each chunk's P'.  Budget: TTX_KEEP_GB (default
+    32); if the device cannot give that much next to the rest of the model, halve until it can (an allocation attempt is
+    the only cheap probe: cudaMemGetInfo costs milliseconds while kernels are running)."""
     budget = max(float(os.environ.get("TTX_KEEP_GB", "32")), 0.0) * 2**30
-    free_dev, _ = torch.cuda.mem_get_info(plan.dev)
-    cached = torch.cuda.memory_reserved(plan.dev) - torch.cuda.memory_allocated(plan.dev)
-    return _chunk_ranges(plan.ntub, Vpad, min(budget, 0.5 * (free_dev + cached)))
+    while True:
+        chunks = _chunk_ranges(plan.ntub, Vpad, budget)
+        store_rows = 128 * ((max(c[1] for c in chunks) + 1) & ~1)
+        try:
+            return chunks, store_rows, torch.empty(store_rows * Vpad, dtype=torch.int16, device=dev)
+        except torch.cuda.OutOfMemoryError:
+            if store_rows <= 256:
+                raise
+            budget = store_rows * Vpad * 2 / 2
 
 
 class WideJointRNNT(torch.autograd.Function):
@@ -300,9 +307,7 @@ class WideJointRNNT(torch.autograd.Function):
                   _p(a16t), plan.idx, st)
             lse, lpb, lpl, pfac, mref = (plan.rowf() for _ in range(5))
             ew = plan.rowf(H) if need_act else None
-            chunks = _wide_chunks(plan, Vpad)
-            store_rows = 128 * ((max(c[1] for c in chunks) + 1) & ~1)
-            pstore = torch.empty(store_rows * Vpad, dtype=torch.int16, device=dev)
+            chunks, store_rows, pstore = _wide_pstore(plan, Vpad, dev)
             flags = torch.zeros((plan.ntub + 1) // 2 + 1, dtype=torch.int32, device=dev)
             for t0, cnt in chunks:
                 WideJointRNNT._sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, blank, bf16, lse, lpb, lpl,

@@ -10,84 +10,71 @@ B*T + B*U rows instead of the reference's B*T*U).  Everything else -- 1-D decode
 (tt/model.py:77), CPU tensors, other activations, widths that are not a multiple of 64 -- is the reference's
 dense math.
 """
-import os
+import ctypes
 
 import torch
 
+from . import _lib
 from . import functional as F
 from .lazy import LazyJointLogits
 
 
-class _tf32_matmul:
-    """cuBLAS TF32 (fp32 accumulate) for the GEMMs issued inside the block, whatever the process-wide setting."""
-
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
-        return False
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _split_tf32(x):
-    """x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32."""
-    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    return hi, x - hi
-
-
-def _mm3(a, b_t, passes):
-    """a @ b_t^T on the tensor cores (cuBLAS TF32, fp32 accumulate).  passes = 3: error-compensated split
-    a_hi b_hi + a_lo b_hi + a_hi b_lo (the dropped a_lo b_lo term is 2^-22 relative), i.e. fp32-grade results at three
-    small tensor-core GEMMs; passes = 1: plain TF32 operands (2^-11 relative rounding)."""
-    with _tf32_matmul():
-        if passes == 1:
-            return torch.matmul(a, b_t.t())
-        a_hi, a_lo = _split_tf32(a)
-        b_hi, b_lo = _split_tf32(b_t)
-        a2 = a_hi.reshape(-1, a.shape[-1])
-        y = torch.mm(a2, b_hi.t())
-        y.addmm_(a_lo.reshape(-1, a.shape[-1]), b_hi.t())
-        y.addmm_(a2, b_lo.t())
-        return y.view(*a.shape[:-1], b_t.shape[0])
-
-
-class _ProjTC(torch.autograd.Function):
-    """y = x W^T (+ b) for the two small pre-projections of the joint (float32).  torch runs float32 GEMMs as fp32 SIMT
-    kernels by default (0.58 ms per cfg2 step for the six of them).  `TTX_TF32_PROJ` selects where cuBLAS TF32 tensor-core
-    GEMMs (fp32 accumulate) are used instead:
-      0  nowhere (torch.nn.functional.linear and its autograd);
-      2  (default) the four backward GEMMs only -- the forward stays exact because its rounding would reach the loss and
-         every gradient; d_enc / d_pred / first-layer weight gradients move from ~1e-4 to ~3e-4 relative error against
-         the oracle (tolerance 1e-3; the output-layer gradients are at 1-3e-4 anyway), ~0.3 ms per step;
-      1  forward too (another 0.15 ms; every gradient at 3-6e-4);
-      3  error-compensated 3 x TF32 everywhere (fp32-grade results, but as separate library launches no faster than
-         the SIMT GEMMs -- one fused kernel is the next step)."""
+class _Proj(torch.autograd.Function):
+    """y = x W^T (+ b) for the two small pre-projections of the joint (tt/model.py:35, joint_network.py:28-31,48), float32,
+    forward and backward on our tcgen05 kernels (csrc/ttx_proj.cu: TF32 tensor-core products with on-chip error
+    compensation, fp32-grade like the reference's SGEMM).  W may be a column slice of a wider matrix (the split
+    forward_layer): only its row stride is used."""
 
     @staticmethod
-    def forward(ctx, x, w, b, passes):
-        ctx.save_for_backward(x, w)
-        ctx.has_bias, ctx.passes = b is not None, passes
-        if passes == 2:      # exact forward (its rounding would reach every gradient), TF32 only in the backward GEMMs
-            return torch.nn.functional.linear(x, w, b)
-        y = _mm3(x, w, passes)
-        return y + b if b is not None else y
+    def forward(ctx, x, w, b):
+        lib = _lib.get()
+        dev = x.device
+        N, K = w.shape
+        x2 = x.detach().reshape(-1, K).contiguous()
+        M = x2.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            bb = b.detach().contiguous() if b is not None else None
+            F._call("ttx_proj_fwd", dev, _p(x2), K, _p(w), w.stride(0), _p(bb), M, N, K, _p(y), N, idx, st)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias, ctx.x_shape = b is not None, x.shape
+        return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
-        bp = 1 if ctx.passes == 2 else ctx.passes
-        dx = _mm3(dy, w.t(), bp) if ctx.needs_input_grad[0] else None
-        dw = _mm3(dy2.t(), x2.t(), bp) if ctx.needs_input_grad[1] else None
-        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dx, dw, db, None
+        x2, w = ctx.saved_tensors
+        dev = x2.device
+        N, K = w.shape
+        M = x2.shape[0]
+        dy2 = dy.reshape(M, N).contiguous()
+        dx = dw = db = None
+        with torch.cuda.device(dev):
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+                F._call("ttx_proj_bwd_x", dev, _p(dy2), N, _p(w), w.stride(0), M, N, K, _p(dx), K, idx, st)
+                dx = dx.view(ctx.x_shape)
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw = torch.zeros(N, K, dtype=torch.float32, device=dev)
+                db = torch.zeros(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                F._call("ttx_proj_bwd_w", dev, _p(dy2), N, _p(x2), K, M, N, K, _p(dw), K, _p(db), idx, st,
+                        n_kernels=2 if db is not None else 1)
+        return dx, dw, db
 
 
 def _proj(x, w, b=None):
-    passes = int(os.environ.get("TTX_TF32_PROJ", "2"))
-    if x.dtype == torch.float32 and w.dtype == torch.float32 and passes in (1, 2, 3):
-        return _ProjTC.apply(x, w, b, passes)
+    """The projection on our kernels when the operands allow it (float32 CUDA, 16-byte aligned rows), else torch's."""
+    if (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and w.stride(1) == 1 and
+            w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0 and w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0 and
+            (b is None or b.dtype == torch.float32) and x.numel() > 0):
+        return _Proj.apply(x, w, b)
     return torch.nn.functional.linear(x, w, b)
 
 
