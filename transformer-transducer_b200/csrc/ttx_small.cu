@@ -505,73 +505,188 @@ struct ActGradSrc {
     int blank;
 };
 
-// Both reductions in ONE pass over the source.  grid = (ceil(T / TT), B); thread = one float4 of h; the block keeps TT
-// frames of Eproj and their dEproj accumulators in registers, walks u, and for every u adds the TT products to both
-// sums: dEproj[b, t, :] is written once at the end, dPproj[b, u, :] gets one 16-byte reduction per (block, u).
+// Both reductions in ONE pass over the source.  grid = (ceil(T / 8), B, ceil(H / 512)); a block owns 8 frames of one
+// utterance and a 512-column slab of h, keeps the frames' Eproj values and dEproj accumulators in registers, walks u, and
+// for every u adds the 8 products to both sums: dEproj[b, t, :] is written once at the end, dPproj[b, u, :] gets one
+// 16-byte reduction per (block, u).  The source rows (2 KiB each, 8 per u) do not go through registers on their way in:
+// a producer warp streams them into a four-stage shared-memory ring with bulk asynchronous copies
+// (cp.async.bulk, completion counted on an mbarrier), so ~48 KiB per block are in flight whatever the consumers are
+// doing -- with plain loads the kernel ran at the latency of two outstanding loads per thread (2.1 TB/s).
 constexpr int kReduceFrames = 8;
+constexpr int kReduceStages = 4;
+constexpr int kReduceSlab = 512;
+constexpr int kReduceThreads = 128 + 32;            // four consumer warps + the producer warp
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 template <bool EW>
-__global__ void __launch_bounds__(128) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
-                                                          const float* __restrict__ pproj, const int* __restrict__ act_lens,
-                                                          const int* __restrict__ label_lens, const int* __restrict__ meta,
-                                                          int T, int U1, int H, float* __restrict__ d_eproj,
-                                                          float* __restrict__ d_pproj) {
+__global__ void __launch_bounds__(kReduceThreads) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
+                                                                     const float* __restrict__ pproj,
+                                                                     const int* __restrict__ act_lens,
+                                                                     const int* __restrict__ label_lens,
+                                                                     const int* __restrict__ meta, int T, int U1, int H,
+                                                                     float* __restrict__ d_eproj, float* __restrict__ d_pproj) {
     constexpr int TT = kReduceFrames;
-    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, h0 = blockIdx.z * kReduceSlab;
     if (meta[1] != 0) return;
+    const int slab = min(kReduceSlab, H - h0);
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
-    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
-    const float gscale = EW ? a.scal[2] : 1.f;
-    for (int h = threadIdx.x * 4; h < H; h += blockDim.x * 4) {
-        float4 e[TT], acc[TT];
-#pragma unroll
-        for (int i = 0; i < TT; ++i) {
-            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            e[i] = (t0 + i < Tb) ? __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t0 + i) * H + h)) : acc[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hl = threadIdx.x * 4;                                 // consumer thread's first column inside the slab
+    const bool active = warp < 4 && hl < slab;
+    const int h = h0 + hl;
+    const int nv = min(TT, Tb - t0);                                // frames of the block inside the utterance
+    if (nv <= 0) {                                                  // beyond the utterance: exact zeros
+        if (active)
+            for (int i = 0; i < TT && t0 + i < T; ++i)
+                *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t0 + i) * H + h) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    extern __shared__ __align__(128) uint8_t rsm[];
+    const uint32_t row_bytes = slab * 4;
+    float* sSrc = reinterpret_cast<float*>(rsm);                                                    // [stage][frame][slab]
+    float4* sRm = reinterpret_cast<float4*>(rsm + kReduceStages * TT * kReduceSlab * 4);             // [stage][frame]
+    const uint32_t sBar = smem_u32(rsm) + kReduceStages * TT * (kReduceSlab * 4 + 16);
+    auto bar_full = [&](int s) { return sBar + 8 * s; };
+    auto bar_empty = [&](int s) { return sBar + 8 * (kReduceStages + s); };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kReduceStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 4);
         }
-        if (t0 < Tb) {
-            float4 wb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EW) wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
-            for (int u = 0; u < U1b; ++u) {
-                const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
-                bool has_label = false;
-                float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EW) {
-                    const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);     // depends on (b, u) only
-                    has_label = lab >= 0 && lab != a.blank;
-                    if (has_label) wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
-                }
-                float4 g[TT], rm[TT];
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const size_t base = (size_t)meta[kMetaHdr + b] * kTile;
+    if (warp == 4) {
+        // ----------------------------------------------------------- producer: 8 source rows (+ their coefficients) per u,
+        // lane i issues frame i's copies (a single thread issuing all sixteen took as long as the consumers' arithmetic)
+        Ring r;
+        const char* src_row = reinterpret_cast<const char*>(a.src + (base + (size_t)(t0 + lane) * U1b) * H + h0);
+        const float4* rm_row = EW ? a.rowmeta + base + (size_t)(t0 + lane) * U1b : nullptr;
+        const size_t src_step = (size_t)H * 4;
+        for (int u = 0; u < U1b; ++u) {
+            if (lane == 0) {
+                mbar_wait(bar_empty(r.stage), r.phase ^ 1);
+                mbar_arrive_expect_tx(bar_full(r.stage), nv * (row_bytes + (EW ? 16u : 0u)));
+            }
+            __syncwarp();
+            if (lane < nv) {
+                bulk_copy_g2s(smem_u32(sSrc + (r.stage * TT + lane) * kReduceSlab), src_row + u * src_step, row_bytes,
+                              bar_full(r.stage));
+                if (EW) bulk_copy_g2s(smem_u32(sRm + r.stage * TT + lane), rm_row + u, 16, bar_full(r.stage));
+            }
+            r.advance(kReduceStages);
+        }
+        return;
+    }
+    // --------------------------------------------------------------- consumers: thread = one float4 of h
+    // The arithmetic is packed (fma / add / mul .f32x2, two lanes per issue slot): with the loads out of the way the kernel
+    // is issue-bound, and what remains per element is the two MUFU operations of sech^2 = 4 e / (1 + e)^2, e = exp(-2|x|).
+    const float gscale4 = 4.f * (EW ? a.scal[2] : 1.f);              // (the 4 of sech^2 rides on the row coefficient)
+    const float kNeg2Log2e = -2.f * kLog2e;
+    uint64_t e01[TT], e23[TT], a01[TT], a23[TT];
+    const uint64_t zero2 = pk2(0.f, 0.f), one2 = pk2(1.f, 1.f);
 #pragma unroll
-                for (int i = 0; i < TT; ++i) {                 // all loads of the round first
-                    const size_t grow = base + (size_t)min(t0 + i, Tb - 1) * U1b + u;
-                    g[i] = __ldg(reinterpret_cast<const float4*>(a.src + grow * H + h));
-                    if (EW) rm[i] = __ldg(a.rowmeta + grow);
+    for (int i = 0; i < TT; ++i) {
+        a01[i] = a23[i] = zero2;
+        float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && i < nv) ev = __ldg(reinterpret_cast<const float4*>(eproj + ((size_t)b * T + t0 + i) * H + h));
+        e01[i] = pk2(ev.x, ev.y);
+        e23[i] = pk2(ev.z, ev.w);
+    }
+    uint64_t wb01 = zero2, wb23 = zero2;
+    if (EW && active) {
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)a.blank * H + h));
+        wb01 = pk2(wb.x, wb.y);
+        wb23 = pk2(wb.z, wb.w);
+    }
+    Ring r;
+    for (int u = 0; u < U1b; ++u) {
+        uint64_t pp01 = zero2, pp23 = zero2, wl01 = zero2, wl23 = zero2;      // (no label: its term multiplies zeros)
+        if (active) {
+            const float4 pp = __ldg(reinterpret_cast<const float4*>(pproj + ((size_t)b * U1 + u) * H + h));
+            pp01 = pk2(pp.x, pp.y);
+            pp23 = pk2(pp.z, pp.w);
+            if (EW) {
+                const int lab = __ldg(a.row_label + base + (size_t)t0 * U1b + u);       // depends on (b, u) only
+                if (lab >= 0 && lab != a.blank) {
+                    const float4 wl = __ldg(reinterpret_cast<const float4*>(a.w_out + (size_t)lab * H + h));
+                    wl01 = pk2(wl.x, wl.y);
+                    wl23 = pk2(wl.z, wl.w);
                 }
-                float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < TT; ++i) {
-                    float coef = (t0 + i < Tb) ? gscale : 0.f;
-                    float4 v = g[i];
-                    if (EW) {
-                        coef *= rm[i].w;
-                        v.x = fmaf(rm[i].y, wb.x, v.x); v.y = fmaf(rm[i].y, wb.y, v.y); v.z = fmaf(rm[i].y, wb.z, v.z); v.w = fmaf(rm[i].y, wb.w, v.w);
-                        if (has_label) {
-                            v.x = fmaf(rm[i].z, wl.x, v.x); v.y = fmaf(rm[i].z, wl.y, v.y); v.z = fmaf(rm[i].z, wl.z, v.z); v.w = fmaf(rm[i].z, wl.w, v.w);
-                        }
-                    }
-                    v.x *= coef * sech2(e[i].x + pp.x);
-                    v.y *= coef * sech2(e[i].y + pp.y);
-                    v.z *= coef * sech2(e[i].z + pp.z);
-                    v.w *= coef * sech2(e[i].w + pp.w);
-                    acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-                    ap.x += v.x; ap.y += v.y; ap.z += v.z; ap.w += v.w;
-                }
-                red_add_v4(d_pproj + ((size_t)b * U1 + u) * H + h, ap.x, ap.y, ap.z, ap.w);
             }
         }
+        mbar_wait(bar_full(r.stage), r.phase);
+        uint64_t ap01 = zero2, ap23 = zero2;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < TT; ++i) {
+                if (i < nv) {
+                    const uint4 g = *reinterpret_cast<const uint4*>(sSrc + (r.stage * TT + i) * kReduceSlab + hl);
+                    uint64_t v01 = pk2u(g.x, g.y), v23 = pk2u(g.z, g.w);
+                    float coef = gscale4;
+                    if (EW) {
+                        const float4 rm = sRm[r.stage * TT + i];
+                        coef *= rm.w;
+                        const uint64_t y2 = pk2(rm.y, rm.y), z2 = pk2(rm.z, rm.z);
+                        v01 = fma2(y2, wb01, v01);
+                        v23 = fma2(y2, wb23, v23);
+                        v01 = fma2(z2, wl01, v01);
+                        v23 = fma2(z2, wl23, v23);
+                    }
+                    float x0, x1, x2, x3;
+                    unpk2(add2(e01[i], pp01), x0, x1);
+                    unpk2(add2(e23[i], pp23), x2, x3);
+                    const float q0 = ex2f(fabsf(x0) * kNeg2Log2e), q1 = ex2f(fabsf(x1) * kNeg2Log2e);
+                    const float q2 = ex2f(fabsf(x2) * kNeg2Log2e), q3 = ex2f(fabsf(x3) * kNeg2Log2e);
+                    const uint64_t q01 = pk2(q0, q1), q23 = pk2(q2, q3);
+                    float d0, d1, d2, d3;
+                    unpk2(add2(q01, one2), d0, d1);
+                    unpk2(add2(q23, one2), d2, d3);
+                    const uint64_t r01 = pk2(rcp_approx(d0), rcp_approx(d1));       // d in [1, 2]
+                    const uint64_t r23 = pk2(rcp_approx(d2), rcp_approx(d3));
+                    const uint64_t c2 = pk2(coef, coef);
+                    const uint64_t s01 = mul2(mul2(q01, r01), mul2(r01, c2));      // coef * 4 e / (1 + e)^2
+                    const uint64_t s23 = mul2(mul2(q23, r23), mul2(r23, c2));
+                    v01 = mul2(v01, s01);
+                    v23 = mul2(v23, s23);
+                    a01[i] = add2(a01[i], v01);
+                    a23[i] = add2(a23[i], v23);
+                    ap01 = add2(ap01, v01);
+                    ap23 = add2(ap23, v23);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(r.stage));              // the stage may be refilled
+        if (active) {
+            float p0, p1, p2, p3;
+            unpk2(ap01, p0, p1);
+            unpk2(ap23, p2, p3);
+            red_add_v4(d_pproj + ((size_t)b * U1 + u) * H + h, p0, p1, p2, p3);
+        }
+        r.advance(kReduceStages);
+    }
+    if (active) {
 #pragma unroll
         for (int i = 0; i < TT; ++i)
-            if (t0 + i < T) *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t0 + i) * H + h) = acc[i];
+            if (t0 + i < T) {
+                float4 o;
+                unpk2(a01[i], o.x, o.y);
+                unpk2(a23[i], o.z, o.w);
+                *reinterpret_cast<float4*>(d_eproj + ((size_t)b * T + t0 + i) * H + h) = o;
+            }
     }
 }
 
@@ -838,14 +953,17 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
                   const float* scal, int blank, const float* eproj, const float* pproj, const int* act_lens,
                   const int* label_lens, const int* meta, int B, int T, int U1, int H, float* d_eproj,
                   float* d_pproj, cudaStream_t s) {
-    const int threads = min(128, max(32, H / 4));
     const ActGradSrc a{src, rowmeta, row_label, w_out, scal, blank};
     TTX_CUDA_OK(cudaMemsetAsync(d_pproj, 0, (size_t)B * U1 * H * sizeof(float), s));
-    const dim3 grid((T + kReduceFrames - 1) / kReduceFrames, B);
-    if (rowmeta != nullptr)
-        reduce_both_kernel<true><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
-    else
-        reduce_both_kernel<false><<<grid, threads, 0, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+    const dim3 grid((T + kReduceFrames - 1) / kReduceFrames, B, (H + kReduceSlab - 1) / kReduceSlab);
+    const size_t smem = (size_t)kReduceStages * kReduceFrames * (kReduceSlab * 4 + 16) + 2 * kReduceStages * 8;
+    if (rowmeta != nullptr) {
+        TTX_CUDA_OK(cudaFuncSetAttribute(reduce_both_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_both_kernel<true><<<grid, kReduceThreads, smem, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+    } else {
+        TTX_CUDA_OK(cudaFuncSetAttribute(reduce_both_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_both_kernel<false><<<grid, kReduceThreads, smem, s>>>(a, eproj, pproj, act_lens, label_lens, meta, T, U1, H, d_eproj, d_pproj);
+    }
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

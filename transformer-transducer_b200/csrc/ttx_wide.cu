@@ -55,7 +55,6 @@ constexpr int kWThreads = kWEpiThreads + 128;          // + control warpgroup: p
 constexpr int kWProducerWarp = kWEpiWarps, kWMmaWarp = kWEpiWarps + 1, kWWatchWarp = kWEpiWarps + 2;
 constexpr int kWCtrlRegs = 72, kWEpiRegs = 216;        // 12 warps x 168 = 4 x 72 + 8 x 216
 constexpr int kSpStage = 2 * kChunkBytes;              // A chunk + W chunk
-constexpr int kSpMaxStages = 6;
 // The S pass runs SIXTEEN epilogue warps (four per TMEM lane quarter): its epilogue -- one exponential per logit -- is
 // latency-bound with two warps per scheduler (ncu: the schedulers issue 30 % of the cycles, profiles/r2_sp_epilogue.md).
 constexpr int kSpEpiWarps = 16;
@@ -519,6 +518,7 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
     const uint32_t sBar = sScale + kKG * 1024;
     const uint32_t sTmemPtr = sBar + 32 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
+    const uint32_t sPart = sTmemPtr + 16;                            // DW: [16][128] floats, partial sums of db
     uint8_t* smem_gen = smem_raw;
     auto bar_full = [&](int s) { return sBar + 8 * s; };
     auto bar_empty = [&](int s) { return sBar + 8 * (NRING + s); };
@@ -671,29 +671,39 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
             if (!begin_unit(unit)) continue;
             uint32_t gacc[32];
             if (MODE == KP_DW) {
-                // dense part of db[v] = sum_m s_m P'[m, v]: thread (v, mh) takes half of each stage's 64 lattice rows for
-                // vocabulary row v of this CTA, from the P' stage and the row scales (row 0 of the 8-row scale tile), once
-                // the MMAs have read the group; then the warp releases both stages.  (H block 0 only.)
-                const int v = et & (kTile - 1), mh = et >> 7;
+                // dense part of db[v] = sum_m s_m P'[m, v] from the P' stage and the row scales (row 0 of the 8-row scale
+                // tile) once the MMAs have read the group; then the warp releases both stages.  (H block 0 only.)  Thread =
+                // (box, 16-byte chunk of 8 v, group of 4 lattice rows): four 16-byte loads per stage -- scalar 2-byte loads
+                // cost the shared-memory port a whole wavefront each, and the port is what bounds this kernel (TMA writes,
+                // MMA reads and these reads together).  The 16 row groups' partial sums meet in shared memory per unit.
+                const int vc = et & 7, bx = (et >> 3) & 1, mg = et >> 4;
                 const int x_row0 = (rt * 2 + (int)rank) * kTile;
                 const uint8_t* sX_gen = smem_gen + (sX - smem_base);
                 const uint8_t* sS_gen = smem_gen + (sScale - smem_base);
-                float dacc = 0.f;
+                float dacc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dacc[e] = 0.f;
                 for (int i = 0; i < k_n; ++i) {
                     const int g = kr.stage / kKG;
                     mbar_wait(bar_cons(g), kr.phase);
                     if (hb == 0) {
-                        const uint8_t* pst = sX_gen + kr.stage * STAGE + (v >> 6) * (STAGE / 2) + (v & 7) * 2;
-                        const uint16_t* sc = reinterpret_cast<const uint16_t*>(sS_gen + g * 1024);
-                        const int vc = (v & 63) >> 3;
-#pragma unroll 8
-                        for (int m = mh * 32; m < mh * 32 + 32; ++m) {
-                            const uint32_t pv = *reinterpret_cast<const uint16_t*>(pst + m * 128 + ((vc ^ (m & 7)) << 4));
-                            const uint32_t sv = sc[m];
-                            float pf_, sf_, d0, d1;
-                            unpk16<BF16>(pv, pf_, d0);
-                            unpk16<BF16>(sv, sf_, d1);
-                            dacc = fmaf(pf_, sf_, dacc);
+                        const uint8_t* pst = sX_gen + kr.stage * STAGE + bx * (STAGE / 2);
+                        const uint2 s4 = *reinterpret_cast<const uint2*>(sS_gen + g * 1024 + mg * 8);   // scales of 4 rows
+                        float sf[4];
+                        unpk16<BF16>(s4.x, sf[0], sf[1]);
+                        unpk16<BF16>(s4.y, sf[2], sf[3]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int m = mg * 4 + j;
+                            const uint4 pv = *reinterpret_cast<const uint4*>(pst + m * 128 + ((vc ^ (m & 7)) << 4));
+                            const uint32_t w4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float p0, p1;
+                                unpk16<BF16>(w4[e], p0, p1);
+                                dacc[2 * e] = fmaf(p0, sf[j], dacc[2 * e]);
+                                dacc[2 * e + 1] = fmaf(p1, sf[j], dacc[2 * e + 1]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -704,7 +714,19 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
                     kr.advance(NRING, kKG);
                 }
                 const float f = p.scal[2] * (BF16 ? 1.0f : 1.0f / kKeptUp);
-                if (hb == 0 && x_row0 + v < p.V) atomicAdd(p.db + x_row0 + v, dacc * f);
+                if (hb == 0) {
+                    float* part = reinterpret_cast<float*>(smem_gen + (sPart - smem_base));      // [16 row groups][128 v]
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) part[mg * kTile + bx * 64 + vc * 8 + e] = dacc[e];
+                    w_epi_sync();
+                    if (et < kTile) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int gq = 0; gq < 16; ++gq) sum += part[gq * kTile + et];
+                        if (x_row0 + et < p.V) atomicAdd(p.db + x_row0 + et, sum * f);
+                    }
+                    w_epi_sync();
+                }
                 mbar_wait(bar_gfull, it & 1);
                 tc_fence_after();
                 const int vrow = x_row0 + row;
@@ -862,7 +884,7 @@ int launch_wide_dw(const void* pstore, uint64_t store_rows, const void* a16st, u
     WideParams p = wide_params(H, V, Vpad, tile_lo, tile_cnt, store_rows, meta, scal);
     p.dW = dW;
     p.db = db;
-    const size_t smem = (size_t)kKG * kKG * kChunkBytes + kKG * 1024 + 32 * 8 + 16;
+    const size_t smem = (size_t)kKG * kKG * kChunkBytes + kKG * 1024 + 32 * 8 + 16 + 16 * kTile * 4;
     const int n_tp = (tile_cnt + 1) / 2, n_vq = ((V + kTile - 1) / kTile + 1) / 2, pairs = max(1, wide_sm_count() / 2);
     // lattice-row splits: units = vocabulary tile pairs x H blocks x splits should fill whole waves of the CTA pairs,
     // long units preferred (every unit ends with a read-out + red.add of its 256 x 512 tile: ~1.5 tile pairs' worth)
