@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--logits", default="init", choices=["init", "peaked"],
                     help="peaked: trained-like output layer (larger weights, boosted blank / label biases)")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel table to stderr")
+    ap.add_argument("--no-overlap", action="store_true", help="A/B runs: every kernel on the launching stream")
     ap.add_argument("--route", default="default", choices=["default", "fused", "chunked"],
                     help="A/B runs: fused = the recomputing kernels at H = 512 (nothing V-wide in HBM), chunked = library GEMMs")
     args = ap.parse_args()
@@ -232,6 +233,8 @@ def main():
     from transformer_transducer_b200 import functional as F
     if args.route != "default":
         F.ROUTE = args.route
+    if args.no_overlap:
+        F.WideJointRNNT.OVERLAP = False
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

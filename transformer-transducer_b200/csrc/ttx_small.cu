@@ -530,7 +530,7 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 }
 
 template <bool EW>
-__global__ void __launch_bounds__(kReduceThreads) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
+__global__ void __launch_bounds__(kReduceThreads, 4) reduce_both_kernel(const ActGradSrc a, const float* __restrict__ eproj,
                                                                      const float* __restrict__ pproj,
                                                                      const int* __restrict__ act_lens,
                                                                      const int* __restrict__ label_lens,

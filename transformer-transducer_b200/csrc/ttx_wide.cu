@@ -53,7 +53,10 @@ constexpr int kWEpiWarps = 8;
 constexpr int kWEpiThreads = kWEpiWarps * 32;
 constexpr int kWThreads = kWEpiThreads + 128;          // + control warpgroup: producer, MMA issuer, watcher, idle
 constexpr int kWProducerWarp = kWEpiWarps, kWMmaWarp = kWEpiWarps + 1, kWWatchWarp = kWEpiWarps + 2;
-constexpr int kWCtrlRegs = 72, kWEpiRegs = 216;        // 12 warps x 168 = 4 x 72 + 8 x 216
+// 128 registers per thread: three quarters of the register file, so that a block of a bandwidth-bound kernel launched on
+// another stream (the activation-gradient reduction, the lattice) fits next to it -- these products leave the SM's issue
+// slots and load/store path idle.
+constexpr int kWRegs = 128;
 constexpr int kSpStage = 2 * kChunkBytes;              // A chunk + W chunk
 // The S pass runs SIXTEEN epilogue warps (four per TMEM lane quarter): its epilogue -- one exponential per logit -- is
 // latency-bound with two warps per scheduler (ncu: the schedulers issue 30 % of the cycles, profiles/r2_sp_epilogue.md).
@@ -474,7 +477,7 @@ enum { KP_PW = 0, KP_DW = 1 };
 constexpr int kKG = 3;                                  // stages per group = groups in flight
 
 template <int MODE, bool BF16>
-__global__ void __launch_bounds__(kWThreads, 1)
+__global__ void __maxnreg__(kWRegs)
 kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapB,
           const __grid_constant__ CUtensorMap mapS, const WideParams p) {
     constexpr int STAGE = kChunkBytes;
@@ -553,7 +556,6 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
     const int row_off = p.tile_lo * kTile;                           // lattice row of the P' matrix's row 0
 
     if (warp >= kWEpiWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWCtrlRegs));
         if (warp == kWProducerWarp && lane == 0) {
             // =================================================== TMA producer
             Ring r;
@@ -655,7 +657,6 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWEpiRegs));
         // ======================================================= epilogue warps
         const int q = warp & 3, ch = warp >> 2;
         const int row = q * 32 + lane;

@@ -267,11 +267,29 @@ def _wide_pstore(plan, Vpad, dev):
             budget = store_rows * Vpad * 2 / 2
 
 
+_HI_STREAMS = {}
+
+
+def _hi_stream(dev):
+    """A high-priority stream per device for the streamed products: they are bound by the SM's TMA ingest and leave its
+    issue slots and load/store path idle (and a quarter of its registers and shared memory free), so the bandwidth-bound
+    kernel that is independent of them -- the lattice next to EW = P' . W, the activation-gradient reduction next to
+    dW = P'^T . As -- runs on the launching stream at the same time, its blocks filling the space the product's CTAs
+    leave.  The priority makes the block scheduler place the product's CTAs first."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _HI_STREAMS.get(key)
+    if s is None:
+        s = _HI_STREAMS[key] = torch.cuda.Stream(dev, priority=-1)
+    return s
+
+
 class WideJointRNNT(torch.autograd.Function):
     """Same contract as FusedJointRNNT for joint widths that are multiples of 512 (aishell.yaml's 1024,
     joint_streaming.yaml's 2048; /root/reference/tt/model.py:35-37): three streamed tcgen05 products around the 16-bit
     softmax numerators P' (csrc/ttx_wide.cu) -- S pass with both operands streamed, EW = P' . W16, dW = P'^T . As --
     with everything else (operand casts, lattice, coefficients, reductions) shared with the fused path.  No library GEMM."""
+
+    OVERLAP = True      # False: everything on the launching stream (A/B runs)
 
     @staticmethod
     def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
@@ -309,13 +327,24 @@ class WideJointRNNT(torch.autograd.Function):
             ew = plan.rowf(H) if need_act else None
             chunks, store_rows, pstore = _wide_pstore(plan, Vpad, dev)
             flags = torch.zeros((plan.ntub + 1) // 2 + 1, dtype=torch.int32, device=dev)
+            # one chunk (the usual case): EW = P' . W runs on the high-priority stream while the lattice runs here
+            main, hi = torch.cuda.current_stream(dev), None
+            if need_act and len(chunks) == 1 and WideJointRNNT.OVERLAP:
+                hi = _hi_stream(dev)
             for t0, cnt in chunks:
                 WideJointRNNT._sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, blank, bf16, lse, lpb, lpl,
                                   pfac, mref, pstore, store_rows, flags)
-                if need_act:
+                if need_act and hi is None:
                     _call("ttx_wide_pw", dev, _p(pstore), store_rows, _p(w16t), _p(pfac), _p(scal), _p(plan.meta), plan.ntub,
                           t0, cnt, H, V, int(bf16), _p(ew), plan.idx, st)
+            if hi is not None:
+                hi.wait_stream(main)
+                with torch.cuda.stream(hi):
+                    _call("ttx_wide_pw", dev, _p(pstore), store_rows, _p(w16t), _p(pfac), _p(scal), _p(plan.meta), plan.ntub,
+                          0, plan.ntub, H, V, int(bf16), _p(ew), plan.idx, _stream(dev))
             alpha, beta, costs, ll_beta = plan.lattice(lse, lpb, lpl)
+            if hi is not None:
+                main.wait_stream(hi)
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
         ctx.chunks, ctx.store_rows = chunks, store_rows
@@ -350,28 +379,40 @@ class WideJointRNNT(torch.autograd.Function):
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank, d_b)
             if need_w:
                 a16st = torch.empty((H + 16) * plan.rows + 64 * (H + 4) * 2, dtype=torch.int16, device=dev)
-                _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl), _p(pfac),
-                      _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, plan.ntub, H, ctx.blank,
-                      ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st)
                 pstore = ctx.pstore
                 recompute = pstore is None
                 if recompute:
                     pstore = torch.empty(ctx.store_rows * Vpad, dtype=torch.int16, device=dev)
                     flags = torch.zeros((plan.ntub + 1) // 2 + 1, dtype=torch.int32, device=dev)
                     sink = [plan.rowf() for _ in range(5)]          # the statistics come out again; only P' is wanted
-                for t0, cnt in ctx.chunks:
-                    if recompute:
-                        WideJointRNNT._sp(dev, plan, st, a16, w16, bias2, scal, row_label, t0, cnt, H, V, ctx.blank, ctx.bf16,
-                                          sink[0], sink[1], sink[2], sink[3], sink[4], pstore, ctx.store_rows, flags)
-                    _call("ttx_wide_dw", dev, _p(pstore), ctx.store_rows, _p(a16st), _p(scal), _p(plan.meta), plan.ntub, t0,
-                          cnt, H, V, ctx.bf16, _p(d_w), _p(d_b), plan.idx, st)
-                ctx.pstore = None
+                # the weight-gradient chain (scaled operand copy, exact blank / label terms, dW = P'^T . As) on the
+                # high-priority stream while the activation-gradient reduction runs here
+                main, hi = torch.cuda.current_stream(dev), None
+                if need_act and WideJointRNNT.OVERLAP:
+                    hi = _hi_stream(dev)
+                    hi.wait_stream(main)
+                with torch.cuda.stream(hi if hi is not None else main):
+                    st_w = _stream(dev)
+                    _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl),
+                          _p(pfac), _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, plan.ntub, H,
+                          ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st_w)
+                    for t0, cnt in ctx.chunks:
+                        if recompute:
+                            WideJointRNNT._sp(dev, plan, st_w, a16, w16, bias2, scal, row_label, t0, cnt, H, V, ctx.blank,
+                                              ctx.bf16, sink[0], sink[1], sink[2], sink[3], sink[4], pstore, ctx.store_rows,
+                                              flags)
+                        _call("ttx_wide_dw", dev, _p(pstore), ctx.store_rows, _p(a16st), _p(scal), _p(plan.meta), plan.ntub,
+                              t0, cnt, H, V, ctx.bf16, _p(d_w), _p(d_b), plan.idx, st_w)
             if need_act:
                 d_ep = torch.zeros(B, T, H, dtype=torch.float32, device=dev)
                 d_pp = torch.zeros(B, U1, H, dtype=torch.float32, device=dev)
                 _call("ttx_reduce_act_grad_ew", dev, _p(ctx.ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
                       ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
                       _p(d_ep), _p(d_pp), plan.idx, st)
+            if need_w:
+                if hi is not None:
+                    main.wait_stream(hi)
+                ctx.pstore = None
         dt = ctx.in_dtypes
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
