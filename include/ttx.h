@@ -196,6 +196,15 @@ int ttx_proj_bwd_x(const float* dy, int lddy, const float* w, int ldw, int M, in
 int ttx_proj_bwd_w(const float* dy, int lddy, const float* x, int ldx, int M, int N, int K, float* dw, int lddw, float* db,
                    int device, void* stream);
 
+/* ---- Decode-time joint (greedy search, tt/model.py:70-90, tt_espnet/model.py:83-106).  Scores n <= 64 consecutive frames
+ * against ONE decoder state: z[f] = tanh(eproj[f] + pvec) . w_out^T + b_out in fp32, per-frame argmax (lowest index on
+ * ties).  eproj: rows of the pre-projected encoder states (leading dimension ld_e floats), pvec (H): pre-projected decoder
+ * state, w_out (V,H), b_out (V).  scratch: 64 x 8 bytes.  out (2 + n int32): out[0] = first frame whose argmax is not
+ * `blank` (n if none), out[1] = that label, out[2 + f] = argmax of frame f.  Replaces the per-frame
+ * joint -> softmax -> argmax -> .item() loop by one launch group and one host read per emitted label. */
+int ttx_decode_scan(const float* eproj, int ld_e, const float* pvec, const float* w_out, const float* b_out, int n, int H, int V,
+                    int blank, void* scratch, int32_t* out, int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

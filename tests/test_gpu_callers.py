@@ -242,3 +242,86 @@ def test_espnet_transformer_transducer_forward_backward_bf16_joint():
     want, got = outs
     assert abs(float(got) - float(want)) / abs(float(want)) < 1e-2
     _assert_grads_close(model, ref_model, 5e-2)
+
+
+# ----------------------------------------------------------------------------- greedy search (decode-time joint)
+def test_decode_scan_kernel_matches_torch_argmax():
+    """ttx_decode_scan through the C ABI: per-frame argmax of tanh(eproj + pvec) . W^T + b, first non-blank frame and
+    its label, against float64 torch (frames whose two best logits are closer than 1e-4 are not compared: fp32
+    summation order decides those, in the reference too)."""
+    import ctypes
+    from transformer_transducer_b200 import _lib
+    lib = _lib.get()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    for seed, (n, H, V, blank_boost) in enumerate([(64, 512, 4232, 6.0), (17, 1024, 211, 3.0), (1, 200, 70, 0.0),
+                                                   (64, 2048, 6485, 50.0)]):
+        g = torch.Generator().manual_seed(seed)
+        eproj, pvec = torch.randn(n, H, generator=g), torch.randn(H, generator=g)
+        w, b = torch.randn(V, H, generator=g) / H ** 0.5, torch.randn(V, generator=g)
+        b[0] += blank_boost
+        z = torch.tanh(eproj.double() + pvec.double()) @ w.double().T + b.double()
+        top = z.topk(2, dim=1)
+        want = top.indices[:, 0]
+        clear = (top.values[:, 0] - top.values[:, 1]) > 1e-4
+        out = torch.full((2 + 64,), -7, dtype=torch.int32, device=DEV)
+        scratch = torch.empty(64, dtype=torch.int64, device=DEV)
+        args = [t.to(DEV) for t in (eproj, pvec, w, b)]
+        _lib.check(lib.ttx_decode_scan(p(args[0]), H, p(args[1]), p(args[2]), p(args[3]), n, H, V, 0, p(scratch), p(out), 0,
+                                       None), "decode_scan")
+        got = out.cpu()
+        assert torch.equal(got[2:2 + n][clear].long(), want[clear])
+        if bool(clear.all()):
+            nz = (want != 0).nonzero()
+            first = int(nz[0]) if len(nz) else n
+            assert int(got[0]) == first and int(got[1]) == (int(want[first]) if first < n else 0)
+
+
+def _boost_blank(out_layer, amount):
+    with torch.no_grad():
+        out_layer.bias[0] += amount
+
+
+@pytest.mark.parametrize("inner", [512, 1024])
+def test_tt_greedy_decode_equals_reference_decode(inner):
+    """tt/model.py:70-90: the reference's per-frame loop (joint -> softmax -> argmax -> .item()) on cuda:0 vs the
+    rebound `Transducer.decode` (install()): identical label sequences, integer-exact, through `recognize()`."""
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    V = 211
+    cfg = _tt_config(inner, V)
+    _seed(21)
+    model = tt_model.Transducer(cfg.model).to(DEV).eval()
+    _boost_blank(model.joint.project_layer, 0.7)          # most frames predict the blank, like a trained model
+    inputs = torch.randn(3, 90, 512, device=DEV)
+    lengths = [90, 71, 33]
+    with torch.no_grad():
+        want = model.recognize(inputs, lengths)
+        try:
+            done = ttb.install(patch_espnet=False)
+            assert "tt.model.Transducer.decode" in done
+            got = model.recognize(inputs, lengths)        # tt/model.py:92-108 unchanged, decode rebound
+        finally:
+            ttb.uninstall()
+    assert got == want
+    assert all(0 < len(w) < n for w, n in zip(want, lengths))    # labels were emitted, and blanks in between
+
+
+def test_espnet_greedy_decode_equals_reference_decode():
+    """tt_espnet/model.py:83-121: same check for TransformerTransducer.decode / recognize."""
+    V = 333
+    ref_model, _ = _espnet_models(V)
+    import tt_espnet.model as tem
+    model = ref_model.to(DEV).eval()
+    _boost_blank(model.joint.lin_out, 1.5)
+    _seed(5)
+    speech = torch.randn(2, 60, 512, device=DEV)
+    slen = torch.tensor([60, 41], device=DEV)
+    want = model.recognize(speech, slen)
+    try:
+        ttb.install(patch_tt=False)
+        assert tem.TransformerTransducer.decode is not tem.TransformerTransducer._ttb_reference_decode
+        got = model.recognize(speech, slen)
+    finally:
+        ttb.uninstall()
+    assert got == want
+    assert all(len(w) > 0 for w in want)

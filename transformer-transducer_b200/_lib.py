@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libttx.so")
-SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu", "ttx_proj.cu"]
+SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu", "ttx_proj.cu", "ttx_decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 _lock = threading.Lock()
@@ -57,6 +57,7 @@ _PROTOS = {
     "ttx_proj_fwd": [c_p, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_p],
     "ttx_proj_bwd_x": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_p],
     "ttx_proj_bwd_w": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_p],
+    "ttx_decode_scan": [c_p, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],

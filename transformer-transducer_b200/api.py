@@ -1,7 +1,8 @@
 """Public surface of the package."""
 from . import _lib
+from .decode import greedy_search
 from .functional import dense_rnnt, fused_joint_rnnt, supported_width
-from .install import install
+from .install import install, uninstall
 from .joint import JointNet, JointNetwork
 from .lazy import LazyJointLogits
 from .loss import RNNTLoss, certify_inputs, rnnt_loss
@@ -10,4 +11,4 @@ build = _lib.build
 TTXError = _lib.TTXError
 
 __all__ = ["JointNet", "JointNetwork", "LazyJointLogits", "RNNTLoss", "rnnt_loss", "certify_inputs",
-           "fused_joint_rnnt", "dense_rnnt", "supported_width", "install", "build", "TTXError"]
+           "fused_joint_rnnt", "dense_rnnt", "supported_width", "greedy_search", "install", "uninstall", "build", "TTXError"]

@@ -64,6 +64,9 @@ int launch_proj_fwd(const float*, int, const float*, int, const float*, int, int
 int launch_proj_bwd_x(const float*, int, const float*, int, int, int, int, float*, int, cudaStream_t);
 int launch_proj_bwd_w(const float*, int, const float*, int, int, int, int, float*, int, float*, cudaStream_t);
 
+int launch_decode_scan(const float*, int, const float*, const float*, const float*, int, int, int, int, unsigned long long*,
+                       int*, cudaStream_t);
+
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -373,6 +376,16 @@ int ttx_proj_bwd_w(const float* dy, int lddy, const float* x, int ldx, int M, in
     TTX_REQUIRE(!db || ((uintptr_t)db & 15) == 0, "ttx_proj_bwd_w: db must be 16-byte aligned");
     TTX_ENTER(device);
     return launch_proj_bwd_w(dy, lddy, x, ldx, M, N, K, dw, lddw, db, (cudaStream_t)stream);
+}
+
+int ttx_decode_scan(const float* eproj, int ld_e, const float* pvec, const float* w_out, const float* b_out, int n, int H, int V,
+                    int blank, void* scratch, int32_t* out, int device, void* stream) {
+    TTX_REQUIRE(eproj && pvec && w_out && b_out && scratch && out, "ttx_decode_scan: null pointer");
+    TTX_REQUIRE(n >= 1 && n <= 64 && H > 0 && V > 0 && ld_e >= H && blank >= 0 && blank < V,
+                "ttx_decode_scan: bad shape n=%d (1..64) H=%d V=%d ld=%d blank=%d", n, H, V, ld_e, blank);
+    TTX_ENTER(device);
+    return launch_decode_scan(eproj, ld_e, pvec, w_out, b_out, n, H, V, blank, (unsigned long long*)scratch, out,
+                              (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

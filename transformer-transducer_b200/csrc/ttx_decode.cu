@@ -1,0 +1,114 @@
+// Decode-time joint: the reference's greedy search evaluates the joint on ONE frame at a time,
+//   logits = project_layer(tanh(forward_layer(cat(enc[t], dec))));  pred = argmax(softmax(logits)).item()
+// (/root/reference/tt/model.py:70-90, tt_espnet/model.py:83-106), i.e. ~10 kernel launches and a host synchronisation per
+// frame.  Between two emitted labels the decoder state -- hence the predictor half of the first layer -- does not change,
+// so the frames up to the next non-blank prediction can all be scored against it at once:
+//   scan_kernel   for n <= 64 consecutive frames: A[f] = tanh(eproj[f] + pvec), z[f] = A[f] . W_out^T + b_out in plain fp32
+//                 FMAs (decoding compares logits, so no 16-bit operands here), per-frame argmax merged across the
+//                 vocabulary tiles with one 64-bit atomicMax (value bits, then the LOWEST index on ties, like torch.argmax)
+//   pick_kernel   first frame whose argmax is not the blank + that label -> 2 ints the host reads with ONE synchronisation
+// A register-tiled SGEMM: block = 64 vocabulary rows x 64 frames, 256 threads x (4 frames x 4 rows), K chunks of 32.
+#include "ttx_common.cuh"
+
+namespace ttx {
+
+constexpr int kDF = 64;          // frames per call
+constexpr int kDV = 64;          // vocabulary rows per block
+constexpr int kDK = 32;          // K chunk
+
+// monotone map float -> uint32 (larger float <-> larger key; NaN excluded by the caller's finite inputs)
+__device__ __forceinline__ uint32_t float_key(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256)
+scan_kernel(const float* __restrict__ eproj, int ld_e, const float* __restrict__ pvec, const float* __restrict__ w_out,
+            const float* __restrict__ b_out, int n, int H, int V, unsigned long long* __restrict__ best) {
+    __shared__ float As[kDK][kDF + 4];          // As[k][frame]
+    __shared__ float Ws[kDK][kDV + 4];          // Ws[k][vocabulary row]
+    const int v0 = blockIdx.x * kDV;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 4 vocabulary rows tx * 4 .., 4 frames ty * 4 ..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < H; k0 += kDK) {
+        // stage the chunk: 64 x 32 activations (tanh on the fly) and 64 x 32 weights, 8 of each per thread
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = it * 256 + threadIdx.x;
+            const int r = idx >> 5, k = idx & 31;                 // row (frame / vocabulary row), k inside the chunk
+            float a = 0.f, w = 0.f;
+            if (k0 + k < H) {
+                if (r < n) a = tanhf(eproj[(size_t)r * ld_e + k0 + k] + pvec[k0 + k]);
+                if (v0 + r < V) w = w_out[(size_t)(v0 + r) * H + k0 + k];
+            }
+            As[k][r] = a;
+            Ws[k][r] = w;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < kDK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // per frame: best (logit, lowest index) over this thread's 4 rows, then over the 16 threads of the frame group
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int f = ty * 4 + i;
+        unsigned long long key = 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = v0 + tx * 4 + j;
+            if (v < V) {
+                const float z = acc[i][j] + b_out[v];
+                const unsigned long long kk = ((unsigned long long)float_key(z) << 32) | (0xFFFFFFFFu - (uint32_t)v);
+                key = kk > key ? kk : key;
+            }
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (tx == 0 && f < n) atomicMax(best + f, key);
+    }
+}
+
+__global__ void pick_kernel(const unsigned long long* __restrict__ best, int n, int blank, int* __restrict__ out) {
+    // out[0] = first frame (0 .. n-1) whose argmax is not the blank, or n; out[1] = that label (or the blank);
+    // out[2 + f] = argmax of frame f
+    __shared__ int first;
+    if (threadIdx.x == 0) first = n;
+    __syncthreads();
+    for (int f = threadIdx.x; f < n; f += blockDim.x) {
+        const int v = (int)(0xFFFFFFFFu - (uint32_t)(best[f] & 0xFFFFFFFFull));
+        out[2 + f] = v;
+        if (v != blank) atomicMin(&first, f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[0] = first;
+        out[1] = first < n ? out[2 + first] : blank;
+    }
+}
+
+int launch_decode_scan(const float* eproj, int ld_e, const float* pvec, const float* w_out, const float* b_out, int n, int H,
+                       int V, int blank, unsigned long long* scratch, int* out, cudaStream_t s) {
+    TTX_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * kDF, s));
+    scan_kernel<<<(V + kDV - 1) / kDV, 256, 0, s>>>(eproj, ld_e, pvec, w_out, b_out, n, H, V, scratch);
+    pick_kernel<<<1, 64, 0, s>>>(scratch, n, blank, out);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ttx

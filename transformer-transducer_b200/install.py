@@ -4,31 +4,63 @@
 and ``tt_espnet/model.py:14`` copies ``JointNetwork`` at import, so patching the defining modules (and
 ``tt_espnet.model`` if it is already imported) before the model is constructed is enough.  The loss
 needs no patch: ``from warprnnt_pytorch import RNNTLoss`` (train.py:13) finds the ``warprnnt_pytorch``
-package of this repository once the repository root is on ``sys.path``.
+package of this repository once the repository root is on ``sys.path``.  The greedy-search methods
+(``Transducer.decode``, ``TransformerTransducer.decode``) are rebound to decode.py's versions.
 """
 import importlib
 import sys
 
+from . import decode as _decode
 from .joint import JointNet, JointNetwork
 
 
-def install(patch_tt=True, patch_espnet=True):
+_ORIGINALS = []          # (object, attribute, original value) in patch order, for uninstall()
+
+
+def _set(obj, attr, value):
+    _ORIGINALS.append((obj, attr, getattr(obj, attr)))
+    setattr(obj, attr, value)
+
+
+def uninstall():
+    """Undo every rebinding install() made (tests; A/B runs against the reference's own classes)."""
+    while _ORIGINALS:
+        obj, attr, value = _ORIGINALS.pop()
+        setattr(obj, attr, value)
+
+
+def _patch_decode(cls, fn, name, done):
+    """Greedy search (decode): same signature, the per-frame joint loop replaced by the GPU scan (decode.py); the
+    reference's method stays reachable (CPU tensors fall back to it)."""
+    if cls.decode is fn:
+        return
+    cls._ttb_reference_decode = cls.decode
+    _set(cls, "decode", fn)
+    done.append(name)
+
+
+def install(patch_tt=True, patch_espnet=True, patch_decode=True):
     done = []
     if patch_tt:
         try:
             m = importlib.import_module("tt.model")
-            m.JointNet = JointNet
+            _set(m, "JointNet", JointNet)
             done.append("tt.model.JointNet")
+            if patch_decode:
+                _patch_decode(m.Transducer, _decode.tt_decode, "tt.model.Transducer.decode", done)
         except ImportError:
             pass
     if patch_espnet:
         try:
             m = importlib.import_module("espnet.nets.pytorch_backend.transducer.joint_network")
-            m.JointNetwork = JointNetwork
+            _set(m, "JointNetwork", JointNetwork)
             done.append("espnet...joint_network.JointNetwork")
         except ImportError:
             pass
         if "tt_espnet.model" in sys.modules:
-            sys.modules["tt_espnet.model"].JointNetwork = JointNetwork
+            _set(sys.modules["tt_espnet.model"], "JointNetwork", JointNetwork)
             done.append("tt_espnet.model.JointNetwork")
+            if patch_decode:
+                _patch_decode(sys.modules["tt_espnet.model"].TransformerTransducer, _decode.espnet_decode,
+                              "tt_espnet.model.TransformerTransducer.decode", done)
     return done
