@@ -271,7 +271,10 @@ def main():
         return model(e, p_) if tt else model(e[:, :, None], p_[:, None])
     model = joint
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(joint, device_ids=[local], gradient_as_bucket_view=True)
+        # lin_out.weight (V x H fp32, 8.7 MB at configs[1]) is final first: its own bucket, so that its all-reduce runs
+        # under the pre-projections' backward instead of after it
+        model = torch.nn.parallel.DistributedDataParallel(joint, device_ids=[local], gradient_as_bucket_view=True,
+                                                          bucket_cap_mb=8)
     crit = ttb.RNNTLoss(blank=0, reduction="mean")
     enc, pred, labels, act_lens, label_lens = synth(w, 1234 + rank, device=dev)
     enc.requires_grad_()

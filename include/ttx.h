@@ -179,6 +179,8 @@ int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, con
                      const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
                      const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
                      int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,
+                     int parts /* 1: the operand copy, 2: the blank / label terms, 3: both -- the two are independent and may
+                                  run on different streams (the terms use the 64 x (H + 4) floats at the end of a16st) */,
                      int device, void* stream);
 
 /* ---- Pre-projections of the joint (tt/model.py:35 forward_layer, split into its encoder / decoder halves;

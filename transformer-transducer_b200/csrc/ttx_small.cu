@@ -1115,15 +1115,21 @@ __global__ void blank_fold_kernel(const float* __restrict__ blank_slots, int H, 
 int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta, const int* row_label,
                         const float* lpb, const float* lpl, const float* pfac, const float* scal, const int* act_lens,
                         const int* label_lens, const int* meta, int B, int T, int U1, int H, int blank,
-                        bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, cudaStream_t s) {
-    const float up = bf16 ? 1.f : kKeptUp;
-    const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
-    if (bf16)
-        scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
-                                                   (uint16_t*)a16st);
-    else
-        scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
-                                                    (uint16_t*)a16st);
+                        bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, int parts, cudaStream_t s) {
+    if (parts & 1) {                             // the scaled operand copy
+        const float up = bf16 ? 1.f : kKeptUp;
+        const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
+        if (bf16)
+            scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
+                                                       (uint16_t*)a16st);
+        else
+            scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
+                                                        (uint16_t*)a16st);
+    }
+    if (!(parts & 2)) {
+        TTX_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const int t_chunk = 64;                      // (longer chunks = fewer atomics were slower: 0.31 -> 0.35 ms at 512)
     const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
     const int threads = 128;                     // two groups of 64 threads x 8 joint columns

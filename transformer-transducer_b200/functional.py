@@ -391,11 +391,19 @@ class WideJointRNNT(torch.autograd.Function):
                 if need_act and WideJointRNNT.OVERLAP:
                     hi = _hi_stream(dev)
                     hi.wait_stream(main)
-                with torch.cuda.stream(hi if hi is not None else main):
-                    st_w = _stream(dev)
+
+                def prepare(parts, stream_ptr):
                     _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl),
                           _p(pfac), _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, plan.ntub, H,
-                          ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), plan.idx, st_w)
+                          ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), parts, plan.idx, stream_ptr,
+                          n_kernels=1 if parts == 1 else 2 if parts == 2 else 3,
+                          label="ttx_kept_prepare" + {1: "[As]", 2: "[blank/label]", 3: ""}[parts])
+
+                # (measured: with the blank / label terms on the launching stream next to the reduction that chain becomes
+                # the longer one -- a co-resident block per SM is all the reduction gets while dW runs: 7.89 vs 7.77 ms)
+                with torch.cuda.stream(hi if hi is not None else main):
+                    st_w = _stream(dev)
+                    prepare(3, st_w)
                     for t0, cnt in ctx.chunks:
                         if recompute:
                             WideJointRNNT._sp(dev, plan, st_w, a16, w16, bias2, scal, row_label, t0, cnt, H, V, ctx.blank,
