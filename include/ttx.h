@@ -207,6 +207,13 @@ int ttx_proj_bwd_w(const float* dy, int lddy, const float* x, int ldx, int M, in
 int ttx_decode_scan(const float* eproj, int ld_e, const float* pvec, const float* w_out, const float* b_out, int n, int H, int V,
                     int blank, void* scratch, int32_t* out, int device, void* stream);
 
+/* ---- Input pipeline: the reference's time / frequency mask augmentation (tt/utils.py:297-329, train.py:41-44: twenty
+ * slice assignments over the batch) as one in-place launch.  x (B,T,F) fp32 on the device with element strides stride_b,
+ * stride_t (frequency contiguous); masks_host: HOST array of n_masks x {axis (1 = time, 2 = frequency), start, width},
+ * at most 64 -- the positions are drawn by the caller with the reference's own random-number calls. */
+int ttx_spec_mask(float* x, int B, int T, int F, int64_t stride_b, int64_t stride_t, const int32_t* masks_host, int n_masks,
+                  int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

@@ -240,3 +240,74 @@ def test_unmodified_train_loop_runs_with_the_drop_ins():
         assert len(losses) == 3 and losses[-1] < losses[0]
     finally:
         tt_model.JointNet = orig
+
+
+def test_length_bucket_sampler_covers_every_index_once_and_balances_ranks():
+    rng = np.random.RandomState(0)
+    T = rng.randint(50, 1000, size=1003)
+    U = np.clip(T // 5 + rng.randint(-8, 9, size=1003), 5, 200)          # label count follows duration, as in speech
+    cells = T * (U + 1)
+    world, bs = 4, 8
+    per_rank = []
+    for rank in range(world):
+        s = ttb.LengthBucketSampler(cells, bs, world=world, rank=rank, bucket=4, seed=3)
+        s.set_epoch(2)
+        batches = list(s)
+        assert len(batches) == len(s) == -(-1003 // (world * bs)) and all(len(b) == bs for b in batches)
+        per_rank.append(batches)
+    seen = np.concatenate([np.asarray(b) for r in per_rank for b in r])
+    assert set(seen.tolist()) == set(range(1003)) and len(seen) == len(per_rank[0]) * world * bs      # + 21 repeats of the shortest
+    # the ranks of one step work on lattices of similar size: the padded size B * max T * max (U + 1) of the slowest rank,
+    # summed over the steps, against random batching of the same corpus
+    def padded(idx):
+        return len(idx) * T[idx].max() * (U[idx].max() + 1)
+    bucketed = sum(max(padded(np.asarray(per_rank[r][i])) for r in range(world)) for i in range(len(per_rank[0])))
+    perm = rng.permutation(1003)[: len(per_rank[0]) * world * bs - 21]
+    perm = np.concatenate([perm, perm[:21]]).reshape(len(per_rank[0]), world, bs)
+    random_batches = sum(max(padded(perm[i, r]) for r in range(world)) for i in range(len(per_rank[0])))
+    assert bucketed < 0.6 * random_batches
+    # another epoch, another order; drop_last drops the tail instead of padding it
+    s0 = ttb.LengthBucketSampler(cells, bs, world=world, rank=0, bucket=4, seed=3)
+    assert list(s0) != per_rank[0]
+    sd = ttb.LengthBucketSampler(cells, bs, world=world, rank=1, drop_last=True)
+    assert len(list(sd)) == len(sd) == 1003 // (world * bs)
+
+
+def test_mask_augment_draws_like_the_reference_and_crop_matches_train_loop():
+    """Same random-number consumption and the same masked bins as tt/utils.py:297-329 (CPU tensors take the slice
+    assignments; the CUDA launch is compared in tests/test_gpu_callers.py); crop_to_max = train.py:32-35."""
+    import random
+    x = torch.randn(3, 50, 40)
+
+    def ref_time(inputs, max_mask_time=5, mask_num=10):          # restated from tt/utils.py:297-312 for the CPU-only check
+        for _ in range(mask_num):
+            t = int(np.random.uniform(low=0.0, high=max_mask_time))
+            t0 = random.randint(0, inputs.shape[1] - t)
+            inputs[:, t0:t0 + t, :] = 0
+        return inputs
+
+    def ref_freq(inputs, max_mask_frequency=5, mask_num=10):
+        for _ in range(mask_num):
+            f = int(np.random.uniform(low=0.0, high=max_mask_frequency))
+            f0 = random.randint(0, inputs.shape[2] - f)
+            inputs[:, :, f0:f0 + f] = 0
+        return inputs
+
+    np.random.seed(5); random.seed(6)
+    want = ref_time(ref_freq(x.clone(), 5, 10), 5, 10)
+    state = (np.random.get_state()[1][:4].tolist(), random.random())
+    np.random.seed(5); random.seed(6)
+    got = ttb.time_mask_augment(ttb.frequency_mask_augment(x.clone(), max_mask_frequency=5, mask_num=10), max_mask_time=5,
+                                mask_num=10)
+    assert torch.equal(got, want) and (np.random.get_state()[1][:4].tolist(), random.random()) == state
+    np.random.seed(5); random.seed(6)
+    assert torch.equal(ttb.mask_augment(x.clone()), want)
+    assert 0 < int((want == 0).sum()) < want.numel()
+    inputs, il = torch.randn(2, 30, 8), torch.tensor([22, 17])
+    targets, tl = torch.randint(1, 9, (2, 12)), torch.tensor([5, 9])
+    a, _, b, _ = ttb.crop_to_max(inputs, il, targets, tl)
+    assert a.shape == (2, 22, 8) and b.shape == (2, 9)
+    lib = _lib.get()
+    bad = (ctypes.c_int32 * 3)(1, 48, 5)                                       # time mask running past T = 50
+    rc = lib.ttx_spec_mask(ctypes.c_void_p(256), 3, 50, 40, 2000, 40, bad, 1, 0, None)
+    assert rc == 1 and b"outside" in lib.ttx_last_error()

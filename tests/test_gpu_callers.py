@@ -325,3 +325,30 @@ def test_espnet_greedy_decode_equals_reference_decode():
         ttb.uninstall()
     assert got == want
     assert all(len(w) > 0 for w in want)
+
+
+# ----------------------------------------------------------------------------- input pipeline
+def test_mask_augment_launch_is_bit_identical_to_reference_slices():
+    """tt/utils.py:297-329 (the reference's own functions, on a CUDA tensor) vs the rebound single-launch versions under the
+    same seeds, contiguous and cropped (strided) batches."""
+    ref_import.prepare(stub_train_deps=True)
+    import tt.utils as tu
+    ref_time, ref_freq = tu.time_mask_augment, tu.frequency_mask_augment
+    for seed, crop in ((1, 410), (2, 333), (3, 57)):
+        _seed(seed)
+        full = torch.randn(5, 410, 512, device=DEV)
+        _seed(100 + seed)
+        want = ref_time(ref_freq(full.clone()[:, :crop, :], max_mask_frequency=5, mask_num=10), max_mask_time=5, mask_num=10)
+        try:
+            done = ttb.install(patch_tt=False, patch_espnet=False)
+            assert any("mask_augment" in d for d in done) and tu.time_mask_augment is ttb.time_mask_augment
+            _seed(100 + seed)
+            got = tu.time_mask_augment(tu.frequency_mask_augment(full.clone()[:, :crop, :], max_mask_frequency=5, mask_num=10),
+                                       max_mask_time=5, mask_num=10)
+            _seed(100 + seed)
+            fused = ttb.mask_augment(full.clone()[:, :crop, :])
+        finally:
+            ttb.uninstall()
+        assert tu.time_mask_augment is ref_time
+        assert torch.equal(got, want) and torch.equal(fused, want)
+        assert 0 < int((want == 0).sum()) < want.numel()

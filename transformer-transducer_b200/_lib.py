@@ -58,6 +58,7 @@ _PROTOS = {
     "ttx_proj_bwd_x": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_p],
     "ttx_proj_bwd_w": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_p],
     "ttx_decode_scan": [c_p, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
+    "ttx_spec_mask": [c_p, c_i32, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],

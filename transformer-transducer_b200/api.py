@@ -1,5 +1,6 @@
 """Public surface of the package."""
 from . import _lib
+from .data import LengthBucketSampler, crop_to_max, frequency_mask_augment, mask_augment, time_mask_augment
 from .decode import greedy_search
 from .functional import dense_rnnt, fused_joint_rnnt, supported_width
 from .install import install, uninstall
@@ -11,4 +12,5 @@ build = _lib.build
 TTXError = _lib.TTXError
 
 __all__ = ["JointNet", "JointNetwork", "LazyJointLogits", "RNNTLoss", "rnnt_loss", "certify_inputs",
-           "fused_joint_rnnt", "dense_rnnt", "supported_width", "greedy_search", "install", "uninstall", "build", "TTXError"]
+           "fused_joint_rnnt", "dense_rnnt", "supported_width", "greedy_search", "install", "uninstall", "LengthBucketSampler", "crop_to_max", "mask_augment",
+           "time_mask_augment", "frequency_mask_augment", "build", "TTXError"]

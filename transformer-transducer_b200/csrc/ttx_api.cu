@@ -67,6 +67,8 @@ int launch_proj_bwd_w(const float*, int, const float*, int, int, int, int, float
 int launch_decode_scan(const float*, int, const float*, const float*, const float*, int, int, int, int, unsigned long long*,
                        int*, cudaStream_t);
 
+int launch_spec_mask(float*, int, int, int, long long, long long, const int*, int, cudaStream_t);
+
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -387,6 +389,22 @@ int ttx_decode_scan(const float* eproj, int ld_e, const float* pvec, const float
     TTX_ENTER(device);
     return launch_decode_scan(eproj, ld_e, pvec, w_out, b_out, n, H, V, blank, (unsigned long long*)scratch, out,
                               (cudaStream_t)stream);
+}
+
+int ttx_spec_mask(float* x, int B, int T, int F, int64_t stride_b, int64_t stride_t, const int32_t* masks_host, int n_masks,
+                  int device, void* stream) {
+    TTX_REQUIRE(x && (masks_host || n_masks == 0), "ttx_spec_mask: null pointer");
+    TTX_REQUIRE(B > 0 && B <= 65535 && T > 0 && F > 0 && n_masks >= 0 && n_masks <= 64,
+                "ttx_spec_mask: bad shape B=%d T=%d F=%d masks=%d (at most 64)", B, T, F, n_masks);
+    for (int i = 0; i < n_masks; ++i) {
+        const int axis = masks_host[3 * i], start = masks_host[3 * i + 1], width = masks_host[3 * i + 2];
+        TTX_REQUIRE((axis == 1 || axis == 2) && start >= 0 && width >= 0 && start + width <= (axis == 1 ? T : F),
+                    "ttx_spec_mask: mask %d = {axis %d, start %d, width %d} outside the (%d, %d) frame", i, axis, start,
+                    width, T, F);
+    }
+    if (n_masks == 0) return 0;
+    TTX_ENTER(device);
+    return launch_spec_mask(x, B, T, F, stride_b, stride_t, masks_host, n_masks, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

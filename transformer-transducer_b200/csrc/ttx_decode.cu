@@ -112,3 +112,49 @@ int launch_decode_scan(const float* eproj, int ld_e, const float* pvec, const fl
 }
 
 }  // namespace ttx
+
+// ------------------------------------------------------------------------------------------- input pipeline
+// SpecAugment-style masking of a (B, T, F) feature batch, in place: the reference applies ten frequency masks and ten time
+// masks as twenty slice assignments `inputs[:, :, f0:f0+f] = 0` / `inputs[:, t0:t0+t, :] = 0`
+// (/root/reference/tt/utils.py:297-329, called train.py:41-44), twenty launches over the whole batch.  Here one launch
+// zeroes exactly the union of those slices; the mask positions come from the caller (drawn on the host with the
+// reference's own random-number calls, so the result is bit-identical).  masks: int32 [n_masks][3] = {axis (1 = time,
+// 2 = frequency), start, width}.
+namespace ttx {
+
+constexpr int kMaxMasks = 64;
+struct MaskList {
+    int n;
+    int axis[kMaxMasks], start[kMaxMasks], width[kMaxMasks];
+};
+
+__global__ void spec_mask_kernel(float* __restrict__ x, int B, int T, int F, long long ld_b, long long ld_t, const MaskList m) {
+    // grid = (T, B); a frame that a time mask covers is zeroed whole, otherwise only its masked frequency bins
+    const int t = blockIdx.x, b = blockIdx.y;
+    float* row = x + b * ld_b + t * ld_t;
+    bool whole = false;
+    for (int i = 0; i < m.n; ++i) whole |= (m.axis[i] == 1 && t >= m.start[i] && t < m.start[i] + m.width[i]);
+    if (whole) {
+        for (int f = threadIdx.x; f < F; f += blockDim.x) row[f] = 0.f;
+        return;
+    }
+    for (int i = 0; i < m.n; ++i)
+        if (m.axis[i] == 2)
+            for (int f = m.start[i] + threadIdx.x; f < min(F, m.start[i] + m.width[i]); f += blockDim.x) row[f] = 0.f;
+}
+
+int launch_spec_mask(float* x, int B, int T, int F, long long ld_b, long long ld_t, const int* masks_host, int n_masks,
+                     cudaStream_t s) {
+    MaskList m{};
+    m.n = n_masks;
+    for (int i = 0; i < n_masks; ++i) {
+        m.axis[i] = masks_host[3 * i];
+        m.start[i] = masks_host[3 * i + 1];
+        m.width[i] = masks_host[3 * i + 2];
+    }
+    spec_mask_kernel<<<dim3(T, B), 128, 0, s>>>(x, B, T, F, ld_b, ld_t, m);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ttx

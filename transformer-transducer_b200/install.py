@@ -5,11 +5,13 @@ and ``tt_espnet/model.py:14`` copies ``JointNetwork`` at import, so patching the
 ``tt_espnet.model`` if it is already imported) before the model is constructed is enough.  The loss
 needs no patch: ``from warprnnt_pytorch import RNNTLoss`` (train.py:13) finds the ``warprnnt_pytorch``
 package of this repository once the repository root is on ``sys.path``.  The greedy-search methods
-(``Transducer.decode``, ``TransformerTransducer.decode``) are rebound to decode.py's versions.
+(``Transducer.decode``, ``TransformerTransducer.decode``) are rebound to decode.py's versions, the mask augmentation
+(``tt.utils.time_mask_augment`` / ``frequency_mask_augment``) to data.py's single-launch versions.
 """
 import importlib
 import sys
 
+from . import data as _data
 from . import decode as _decode
 from .joint import JointNet, JointNetwork
 
@@ -39,8 +41,21 @@ def _patch_decode(cls, fn, name, done):
     done.append(name)
 
 
-def install(patch_tt=True, patch_espnet=True, patch_decode=True):
+def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True):
     done = []
+    if patch_data:
+        # tt/utils.py:297-329; train.py:18 copies the names at import (`from tt.utils import ...`)
+        for modname in ("tt.utils", "train"):
+            m = sys.modules.get(modname)
+            if m is None and modname == "tt.utils":
+                try:
+                    m = importlib.import_module(modname)
+                except ImportError:
+                    m = None
+            if m is not None and hasattr(m, "time_mask_augment"):
+                _set(m, "time_mask_augment", _data.time_mask_augment)
+                _set(m, "frequency_mask_augment", _data.frequency_mask_augment)
+                done.append(modname + ".{time,frequency}_mask_augment")
     if patch_tt:
         try:
             m = importlib.import_module("tt.model")
