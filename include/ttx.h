@@ -162,8 +162,11 @@ int ttx_reduce_act_grad_ew(const float* ew, const void* rowmeta, const int32_t* 
  *                 P' is always consistent on return.
  *   ttx_wide_pw   ew (rows, H) fp32 = P' . W16 * pfac / w_scale  (as ttx_joint_fwd_grad's ew)
  *   ttx_wide_dw   d_w_out += P'^T . As, d_b_out += dense part, As = a16st from ttx_kept_prepare.
- *   ttx_kept_prepare  a16st = scaled A16^T ((H + 16) x rows_ub 16-bit values + 64 x (H + 4) floats), and the exact
- *                 blank / label terms of d_w_out / d_b_out. */
+ *   ttx_kept_prepare  a16st (caller scratch of (H + 16) x rows_ub 16-bit values + 64 x (H + 4) floats) = As, the copy of
+ *                 A16 with every lattice row scaled by its gradient weight (rows_ub x H, row-major like A16 -- the
+ *                 product reads it MN-major, there is no transposed copy), then the rows_ub scales themselves, then
+ *                 (at byte (H + 16) * rows_ub * 2) the partial rows of the blank term; and the exact blank / label terms
+ *                 of d_w_out / d_b_out. */
 int ttx_wide_supported_h(int H);
 int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
                 const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
@@ -175,7 +178,7 @@ int ttx_wide_pw(const void* pstore, int64_t store_rows, const void* w16t, const 
 int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const float* scal, const int32_t* meta,
                 int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* d_w_out, float* d_b_out,
                 int device, void* stream);
-int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
+int ttx_kept_prepare(const void* a16, const void* rowmeta, const int32_t* row_label,
                      const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
                      const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
                      int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,

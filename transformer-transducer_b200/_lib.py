@@ -48,7 +48,7 @@ _PROTOS = {
                     c_p, c_i64, c_p, c_i32, c_p],
     "ttx_wide_pw": [c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_wide_dw": [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
-    "ttx_kept_prepare": [c_p] * 11 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_p],
+    "ttx_kept_prepare": [c_p] * 10 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_p],
     "ttx_rows_lse": [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_rows_grad": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_joint_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p,

@@ -33,7 +33,7 @@ int launch_joint_fwd_grad(const void*, const void*, const void*, uint64_t, int, 
                           const float*, const float*, const int*, int, float*, float*, float*, float*, void*, size_t,
                           cudaStream_t);
 size_t joint_workspace_bytes(int which, int n_tiles_ub, int H, int V);
-int launch_kept_prepare(const void*, const void*, const float4*, const int*, const float*, const float*, const float*,
+int launch_kept_prepare(const void*, const float4*, const int*, const float*, const float*, const float*,
                         const float*, const int*, const int*, const int*, int, int, int, int, int, bool, size_t, void*,
                         float*, float*, int, cudaStream_t);
 int launch_dense_lse(const float*, const int*, const int*, const int*, const int*, int, int, int, int, int, int, int,
@@ -316,17 +316,17 @@ int ttx_wide_dw(const void* pstore, int64_t store_rows, const void* a16st, const
                           bf16 != 0, meta, scal, d_w_out, d_b_out, (cudaStream_t)stream);
 }
 
-int ttx_kept_prepare(const void* a16, const void* a16t, const void* rowmeta, const int32_t* row_label,
+int ttx_kept_prepare(const void* a16, const void* rowmeta, const int32_t* row_label,
                      const float* lp_blank, const float* lp_label, const float* pfac, const float* scal,
                      const int32_t* act_lens, const int32_t* label_lens, const int32_t* meta, int B, int T, int U1,
                      int64_t n_tiles_ub, int H, int blank, int bf16, void* a16st, float* d_w_out, float* d_b_out,
                      int parts, int device, void* stream) {
-    TTX_REQUIRE(a16 && a16t && rowmeta && row_label && lp_blank && lp_label && pfac && scal && act_lens && label_lens &&
+    TTX_REQUIRE(a16 && rowmeta && row_label && lp_blank && lp_label && pfac && scal && act_lens && label_lens &&
                     meta && a16st && d_w_out && d_b_out, "ttx_kept_prepare: null pointer");
     TTX_REQUIRE(H > 0 && H % 64 == 0 && B > 0 && B <= 65535 && T > 0 && U1 > 0, "ttx_kept_prepare: bad shape");
     TTX_REQUIRE(parts >= 1 && parts <= 3, "ttx_kept_prepare: parts = %d (1 operand copy, 2 blank / label terms, 3 both)", parts);
     TTX_ENTER(device);
-    return launch_kept_prepare(a16, a16t, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal, act_lens,
+    return launch_kept_prepare(a16, (const float4*)rowmeta, row_label, lp_blank, lp_label, pfac, scal, act_lens,
                                label_lens, meta, B, T, U1, H, blank, bf16 != 0, (size_t)n_tiles_ub * kTile, a16st, d_w_out,
                                d_b_out, parts, (cudaStream_t)stream);
 }

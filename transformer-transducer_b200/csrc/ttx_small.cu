@@ -970,55 +970,44 @@ int launch_reduce(const float* src, const float4* rowmeta, const int* row_label,
 
 
 // ------------------------------------------------------------------------------------------- weight gradient from kept P'
-// The forward+gradient launch can keep its softmax numerators P' (rows_ub x Vpad, 16 bit; softmax = P' * pfac[row]).
-// Then the dense part of the weight gradient is one product with no projection pass and no exponentials,
-//   dW[v, h] = gmax * 2^-shift * sum_m P'[m, v] * As[m, h],   As[m, h] = 2^shift * w_m * pfac_m * A16[m, h],
-// whose K-major B operand is the scaled transposed copy written here (the scale cannot ride on P': it is streamed
-// straight into the tensor core; stored in blocks of 64 lattice rows).  Sixteen extra rows h = H .. H+15 hold
-// As = 2^shift * w_m * pfac_m (A = 1): their
-// product with P' is the dense part of db.  shift (16 for fp16, 0 for bf16) keeps As out of the subnormals.
-// Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.  No-op if the P' matrix is flagged.
-constexpr int kScaleRowsPerBlock = 16;          // joint columns (rows of A16^T) per block
+// The S pass keeps its softmax numerators P' (rows x Vpad, 16 bit; softmax = P' * pfac[row]).  The dense part of the weight
+// gradient is then one product with no projection pass and no exponentials,
+//   dW[v, h] = gmax * 2^-shift * sum_m P'[m, v] * As[m, h],   As[m, h] = 2^shift * w_m * pfac_m * A16[m, h].
+// The scale is per lattice row -- the contraction index -- so it cannot ride on the product's epilogue, and P' is
+// streamed straight into the tensor core: As is a scaled copy of A16, written here, ROW-MAJOR like A16 (the product reads
+// it MN-major, so no transposed copy of the activations exists anywhere on this route).  svec[m] = 2^shift * w_m * pfac_m
+// goes out next to it: its product with P' is the dense part of db.  shift (16 for fp16, 0 for bf16) keeps As out of the
+// subnormals.  Rows beyond the tiles in use, and padding rows (w = 0), give exact zeros.
 template <bool BF16>
-__global__ void scale_a16t_kernel(const uint16_t* __restrict__ a16t, const float4* __restrict__ rowmeta,
-                                  const float* __restrict__ pfac, const int* __restrict__ meta,
-                                  int H, size_t rows_total, float up,
-                                  uint16_t* __restrict__ out) {
-    const size_t m0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (m0 >= rows_total) return;
-    const size_t rows_used = (size_t)meta[0] * kTile;
-    float s[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float v = 0.f;
-        if (m0 + e < rows_used) {
-            const float w = __ldg(&rowmeta[m0 + e].w);
-            if (w != 0.f) v = w * __ldg(pfac + m0 + e) * up;
-        }
-        s[e] = v;
+__global__ void scale_rows_kernel(const uint16_t* __restrict__ a16, const float4* __restrict__ rowmeta,
+                                  const float* __restrict__ pfac, const int* __restrict__ meta, int H, size_t rows_total,
+                                  float up, uint16_t* __restrict__ as, uint16_t* __restrict__ svec) {
+    // thread = 8 joint columns of one lattice row; a warp covers 256 columns of a row (or several rows for H < 256)
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = H / 8;
+    const size_t m = idx / per_row;
+    if (m >= rows_total) return;
+    const int h = (int)(idx - m * per_row) * 8;
+    float sc = 0.f;
+    if (m < (size_t)meta[0] * kTile) {
+        const float w = __ldg(&rowmeta[m].w);
+        if (w != 0.f) sc = w * __ldg(pfac + m) * up;
     }
-    const int h0 = blockIdx.y * kScaleRowsPerBlock;
-    for (int h = h0; h < h0 + kScaleRowsPerBlock; ++h) {
-        uint4 o;
-        if (h < H) {
-            const uint4 in = __ldg(reinterpret_cast<const uint4*>(a16t + ((m0 >> 6) * (size_t)H + h) * 64 + (m0 & 63)));
-            const uint32_t w4[4] = {in.x, in.y, in.z, in.w};
-            uint32_t r4[4];
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (sc != 0.f) {
+        const uint4 in = __ldg(reinterpret_cast<const uint4*>(a16 + m * H + h));
+        const uint32_t w4[4] = {in.x, in.y, in.z, in.w};
+        uint32_t r4[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float a, b;
-                unpk16<BF16>(w4[e], a, b);
-                r4[e] = pack16<BF16>(a * s[2 * e], b * s[2 * e + 1]);
-            }
-            o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
-        } else {
-            o = make_uint4(pack16<BF16>(s[0], s[1]), pack16<BF16>(s[2], s[3]), pack16<BF16>(s[4], s[5]),
-                           pack16<BF16>(s[6], s[7]));
+        for (int e = 0; e < 4; ++e) {
+            float x0, x1;
+            unpk16<BF16>(w4[e], x0, x1);
+            r4[e] = pack16<BF16>(x0 * sc, x1 * sc);
         }
-        // out is stored in 64-column blocks, [rows_total / 64][H + 16][64]: every box the weight-gradient kernel streams
-        // ([128 joint columns x 64 lattice rows]) is 16 KiB of contiguous memory
-        *reinterpret_cast<uint4*>(out + ((m0 >> 6) * (size_t)(H + 16) + h) * 64 + (m0 & 63)) = o;
+        o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
     }
+    *reinterpret_cast<uint4*>(as + m * H + h) = o;
+    if (h == 0) svec[m] = (uint16_t)(pack16<BF16>(sc, 0.f) & 0xffffu);
 }
 
 // The blank and label entries are absent from the kept P' (the forward+gradient launch zeroes them): their exact terms
@@ -1112,19 +1101,19 @@ __global__ void blank_fold_kernel(const float* __restrict__ blank_slots, int H, 
     else atomicAdd(d_b + blank, acc);
 }
 
-int launch_kept_prepare(const void* a16, const void* a16t, const float4* rowmeta, const int* row_label,
+int launch_kept_prepare(const void* a16, const float4* rowmeta, const int* row_label,
                         const float* lpb, const float* lpl, const float* pfac, const float* scal, const int* act_lens,
                         const int* label_lens, const int* meta, int B, int T, int U1, int H, int blank,
                         bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, int parts, cudaStream_t s) {
     if (parts & 1) {                             // the scaled operand copy
         const float up = bf16 ? 1.f : kKeptUp;
-        const dim3 g1((unsigned)((rows_total / 8 + 255) / 256), (H + 16) / kScaleRowsPerBlock);
+        const unsigned g1 = (unsigned)((rows_total * (size_t)(H / 8) + 255) / 256);
+        uint16_t* as = static_cast<uint16_t*>(a16st);
+        uint16_t* svec = as + rows_total * (size_t)H;          // [rows]: behind the matrix (see ttx.h for the layout)
         if (bf16)
-            scale_a16t_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
-                                                       (uint16_t*)a16st);
+            scale_rows_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16, rowmeta, pfac, meta, H, rows_total, up, as, svec);
         else
-            scale_a16t_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16t, rowmeta, pfac, meta, H, rows_total, up,
-                                                        (uint16_t*)a16st);
+            scale_rows_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16, rowmeta, pfac, meta, H, rows_total, up, as, svec);
     }
     if (!(parts & 2)) {
         TTX_CUDA_OK(cudaGetLastError());

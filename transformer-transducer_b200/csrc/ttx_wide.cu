@@ -8,7 +8,7 @@
 //                  overlaps the MMAs of chunk j + 1.  Epilogue: online log-sum-exp statistics (lse, log p(blank), log p(label))
 //                  + P' staged in shared memory and moved by TMA stores to the blocked P' matrix, [Vpad / 64][rows][64].
 //   kp_kernel<PW>  EW = P' . W16 for a 512-column block of H (two 256-column slabs = all of TMEM), K = vocabulary.
-//   kp_kernel<DW>  dW_out += P'^T . As for a 512-column block of H, K = lattice rows; As = scaled A16^T (ttx_small.cu).
+//   kp_kernel<DW>  dW_out += P'^T . As for a 512-column block of H, K = lattice rows; As = row-scaled A16 (ttx_small.cu).
 //
 // P' rows are stored against a per-row reference mref fixed by the first vocabulary chunk; a row whose later logits
 // would overflow the 16-bit range moves its reference (rare, see the range plan in ttx_joint_mma.cu) and flags its tile
@@ -470,9 +470,10 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
 //   PW: rows = lattice rows (pair: two 128-row tiles), K = vocabulary.  A = P' box [128 rows x 64 v] (K-major),
 //       B = W16^T boxes [128 h x 64 v].  Out: EW = G * pfac / w_scale.
 //   DW: rows = vocabulary (pair: two 128-row vocabulary tiles), K = lattice rows.  A = P'^T, read MN-major straight from
-//       the row-major P' blocks (two [64 m x 64 v] boxes), B = scaled A16^T boxes [128 h x 64 m]; + the 16 scale rows
-//       appended to every 64-row block of As^T (H block 0 only), from which the idle epilogue warps form the dense part
-//       of db out of the P' stage in shared memory.  Out: red.add into dW.
+//       the row-major P' blocks (two [64 m x 64 v] boxes), B = As^T, read MN-major from the row-major scaled copy of A16
+//       (two [64 m x 64 h] boxes per slab) -- no transposed copy of either exists; + the 64 row scales of the stage
+//       (H block 0 only), from which the idle epilogue warps form the dense part of db out of the P' stage in shared
+//       memory.  Out: red.add into dW.
 enum { KP_PW = 0, KP_DW = 1 };
 constexpr int kKG = 3;                                  // stages per group = groups in flight
 
@@ -587,13 +588,15 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
                         tma_load_2d_pair(dst + STAGE / 2, &mapP, full, 0, (v0 / kKC + 1) * p.store_rows + m0);
                         const int grp = r.stage / kKG;
                         r.advance(NRING);
-                        // As^T: 64-row blocks of lattice rows, [rows / 64][H + 16][64]
-                        const int hrow = ((row_off + m0) / kKC) * (p.H + 16);
+                        // As: row-major [rows x H] like A16; the CTA's 128 joint columns of a slab = two [64 m x 64 h] boxes
+                        // (the B operand is read MN-major, exactly like P'^T on the A side)
                         for (int s = 0; s < 2; ++s) {
                             const bool with_scale = (s == 0 && hb == 0);
-                            stage_in(full, dst, STAGE + (with_scale ? 1024 : 0));
-                            tma_load_2d_pair(dst, &mapB, full, 0, hrow + hb * 512 + s * 256 + (int)rank * kTile);
-                            if (with_scale) tma_load_2d_pair(sScale + grp * 1024, &mapS, full, 0, hrow + p.H + (int)rank * 8);
+                            stage_in(full, dst, STAGE + (with_scale ? 128 : 0));
+                            const int hcol = hb * 512 + s * 256 + (int)rank * kTile;
+                            tma_load_2d_pair(dst, &mapB, full, hcol, row_off + m0);
+                            tma_load_2d_pair(dst + STAGE / 2, &mapB, full, hcol + kKC, row_off + m0);
+                            if (with_scale) tma_load_2d_pair(sScale + grp * 1024, &mapS, full, 0, (row_off + m0) / kKC);
                             r.advance(NRING);
                         }
                     }
@@ -619,7 +622,7 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
         } else if (warp == kWMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             constexpr int fmt = BF16 ? 1 : 0;
-            const uint32_t idesc = make_idesc(fmt, MODE == KP_DW ? 1 : 0, 0, 256, 256);
+            const uint32_t idesc = make_idesc(fmt, MODE == KP_DW ? 1 : 0, MODE == KP_DW ? 1 : 0, 256, 256);
             const uint32_t xlo = desc_lo(sX);
             // MN-major A (DW): 64-wide blocks 8 KiB apart (LBO), a 16-row k slice = +2 KiB
             const uint32_t amn = (xlo & 0xFFFFu) | (512u << 16);
@@ -632,11 +635,11 @@ kp_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUte
                     tc_fence_after();
                     const uint32_t b0 = xlo + (rstage + 1) * 1024, b1 = b0 + 1024;
                     if (MODE == KP_DW) {
-                        const uint32_t a = amn + rstage * 1024;
+                        const uint32_t a = amn + rstage * 1024, bm0 = a + 1024, bm1 = a + 2048;     // all three MN-major
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_f16_ss_pair_lo(tmem_base, a + 128 * k, b0 + 2 * k, idesc, (i | k) != 0);
-                            umma_f16_ss_pair_lo(tmem_base + 256, a + 128 * k, b1 + 2 * k, idesc, (i | k) != 0);
+                            umma_f16_ss_pair_lo(tmem_base, a + 128 * k, bm0 + 128 * k, idesc, (i | k) != 0);
+                            umma_f16_ss_pair_lo(tmem_base + 256, a + 128 * k, bm1 + 128 * k, idesc, (i | k) != 0);
                         }
                         umma_commit_pair(bar_cons(rstage / kKG));       // the epilogue warps release stages r and r + 1
                         umma_commit_pair(bar_empty(rstage + 2));
@@ -905,8 +908,9 @@ int launch_wide_dw(const void* pstore, uint64_t store_rows, const void* a16st, u
     p.splits = best;
     CUtensorMap mp, mb, ms;
     if (int rc = make_matrix_map(&mp, pstore, store_rows * (uint64_t)(Vpad / kKC), kKC, bf16, 64)) return rc;
-    if (int rc = make_matrix_map(&mb, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, kTile)) return rc;
-    if (int rc = make_matrix_map(&ms, a16st, (uint64_t)(H + 16) * (rows_ub / kKC), kKC, bf16, 8)) return rc;
+    if (int rc = make_tile_map(&mb, a16st, rows_ub, H, bf16, kKC)) return rc;                          // As, boxes [64 m x 64 h]
+    const uint16_t* svec = static_cast<const uint16_t*>(a16st) + rows_ub * (uint64_t)H;                  // [rows / 64][64]
+    if (int rc = make_matrix_map(&ms, svec, rows_ub / kKC, kKC, bf16, 1)) return rc;
     const unsigned grid = 2u * (unsigned)max(1, min(n_vq * p.n_hb * p.splits, pairs));
     return bf16 ? launch_pair(kp_kernel<KP_DW, true>, kWThreads, grid, smem, stream, mp, mb, ms, p)
                 : launch_pair(kp_kernel<KP_DW, false>, kWThreads, grid, smem, stream, mp, mb, ms, p);

@@ -314,7 +314,6 @@ class WideJointRNNT(torch.autograd.Function):
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
             bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
             w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if need_act else None
-            a16t = torch.empty(H * plan.rows, dtype=torch.int16, device=dev) if need_w else None
             _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
                   plan.idx, st)
             a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
@@ -322,7 +321,7 @@ class WideJointRNNT(torch.autograd.Function):
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
                   _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
-                  _p(a16t), plan.idx, st)
+                  None, plan.idx, st)          # (no transposed copy: the weight gradient reads its operands MN-major)
             lse, lpb, lpl, pfac, mref = (plan.rowf() for _ in range(5))
             ew = plan.rowf(H) if need_act else None
             chunks, store_rows, pstore = _wide_pstore(plan, Vpad, dev)
@@ -348,7 +347,7 @@ class WideJointRNNT(torch.autograd.Function):
         ctx.plan, ctx.blank, ctx.bf16, ctx.dims = plan, int(blank), int(bf16), (B, T, U1, H, V)
         ctx.in_dtypes = (eproj.dtype, pproj.dtype, w_out.dtype, b_out.dtype)
         ctx.chunks, ctx.store_rows = chunks, store_rows
-        ctx.ew, ctx.w32, ctx.a16t = ew, (w if need_act else None), a16t
+        ctx.ew, ctx.w32 = ew, (w if need_act else None)
         ctx.pstore = pstore if (need_w and len(chunks) == 1) else None      # kept from forward to backward
         ctx.save_for_backward(ep, pp, bias2, a16, w16, scal, row_label, lse, lpb, lpl, alpha, beta, ll_beta, pfac, mref)
         return costs
@@ -393,7 +392,7 @@ class WideJointRNNT(torch.autograd.Function):
                     hi.wait_stream(main)
 
                 def prepare(parts, stream_ptr):
-                    _call("ttx_kept_prepare", dev, _p(a16), _p(ctx.a16t), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl),
+                    _call("ttx_kept_prepare", dev, _p(a16), _p(rowmeta), _p(row_label), _p(lpb), _p(lpl),
                           _p(pfac), _p(scal), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, plan.ntub, H,
                           ctx.blank, ctx.bf16, _p(a16st), _p(d_w), _p(d_b), parts, plan.idx, stream_ptr,
                           n_kernels=1 if parts == 1 else 2 if parts == 2 else 3,
