@@ -71,7 +71,8 @@ int ttx_joint_lse_fwd(const void* a16, const void* w16, const float* bias2, cons
  * sum_b (T_b + U_b) * pitch(U_b + 1), pitch(n) = n rounded up to a multiple of 4). */
 int64_t ttx_lattice_elems_upper_bound(int B, int T, int U1);
 
-/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried in float64.  One warp per
+/* Anti-diagonal wavefront alpha and beta over every utterance's (T_b, U_b+1) lattice, carried as float + float (48 bits)
+ * and stored as float64.  One warp per
  * (utterance, direction), warp-shuffle hand-off between columns, operand diagonals staged in shared memory by
  * 16-byte asynchronous copies.  alpha / beta (lat_elems doubles each) are DIAGONAL-MAJOR: cell (t, u) of utterance b
  * is element meta[4 + B+1 + n_tiles_ub + b] + (t + u) * pitch(U_b + 1) + u of alpha; beta lives on the mirrored

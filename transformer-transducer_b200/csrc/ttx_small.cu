@@ -268,16 +268,34 @@ int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_
 //     64 columns, through shared memory behind the one block barrier per diagonal).  The operand diagonals are staged
 //     PD - 1 steps ahead in a shared-memory ring by 16-byte cp.async copies (whole diagonals, coalesced), read back as
 //     one vector per lane, and alpha / beta leave as contiguous runs of doubles.
-// The recursion is carried in float64: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
-// ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).  The
+// The recursion needs more than float32: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
+// ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).  It is
+// carried as an unevaluated sum of two floats (hi + lo, ~48 bits -- 2e-11 at 6000; a compensated float32 carrier) and
+// stored as float64.  (Measured: the same time per diagonal as a float64 carrier, 0.25 us at configs[1] -- the step is
+// bound by the staging / shuffle / store sequence around the arithmetic, not by the arithmetic's latency.)  The
 // increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 with ex2 / lg2 (absolute error ~1e-7 per
-// cell, a random walk of ~3e-6 over a 1200-step lattice).  "log 0" is the finite sentinel kLatNeg: no special cases.
-constexpr double kLatNeg = -1.0e30;
-__device__ __forceinline__ double log_add(double a, double b) {
-    const double mx = fmax(a, b), mn = fmin(a, b);
-    const float e = ex2f((float)(mn - mx) * kLog2e);          // both "log 0": e = 1, the sum stays at the sentinel
-    return mx + (double)(lg2f(1.f + e) * kLn2);
+// cell, a random walk of ~3e-6 over a 1200-step lattice).  "log 0" is the finite sentinel kLatNeg.
+constexpr float kLatNeg = -1.0e30f;
+struct df32 {
+    float hi, lo;
+};
+__device__ __forceinline__ df32 df_add(df32 a, float b) {            // (hi + lo) + b, error-free two-sum + renormalisation
+    const float s = __fadd_rn(a.hi, b);
+    const float bb = __fsub_rn(s, a.hi);
+    float e = __fadd_rn(__fsub_rn(a.hi, __fsub_rn(s, bb)), __fsub_rn(b, bb));
+    e = __fadd_rn(e, a.lo);
+    const float hi = __fadd_rn(s, e);
+    return {hi, __fsub_rn(e, __fsub_rn(hi, s))};
 }
+__device__ __forceinline__ df32 log_add(df32 a, df32 b) {
+    const bool a_ge = a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo);
+    const df32 mx = a_ge ? a : b, mn = a_ge ? b : a;
+    // the difference of the high parts is exact whenever it matters (|d| < 30 between values of equal magnitude)
+    const float d = __fadd_rn(__fsub_rn(mn.hi, mx.hi), __fsub_rn(mn.lo, mx.lo));
+    const float e = ex2f(d * kLog2e);                          // both "log 0": e = 1, the sum stays at the sentinel
+    return df_add(mx, lg2f(1.f + e) * kLn2);
+}
+__device__ __forceinline__ double df_value(df32 a) { return (double)a.hi + (double)a.lo; }
 
 // lat_ws = four arrays of lat_elems floats: [0] inB, [1] inL of the alpha lattice, [2] inB, [3] inL of the mirrored
 // (beta) lattice.  Entries that no arc arrives in (first row / first column) stay unwritten and are never used.
@@ -323,7 +341,7 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
     static_assert(PD >= 2 && (K == 1 || K == 2), "ring of at least two diagonals, one or two columns per lane");
     constexpr int PMAX = 32 * K * W;                       // floats per staged diagonal
     __shared__ __align__(16) float stage[PD][2][PMAX];
-    __shared__ double bnd[2][W + 1];
+    __shared__ float2 bnd[2][W + 1];
     if (meta[1] != 0) return;
     const bool is_beta = blockIdx.x >= (unsigned)B;
     const int b = is_beta ? blockIdx.x - B : blockIdx.x;
@@ -349,16 +367,17 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
     };
 #pragma unroll
     for (int s = 0; s < PD - 1; ++s) stage_step(s, s);
-    double v[K];
+    const df32 neg{kLatNeg, 0.f};
+    df32 v[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) v[j] = kLatNeg;
+    for (int j = 0; j < K; ++j) v[j] = neg;
     double* out = (is_beta ? beta_d : alpha_d) + base + u0;
     for (int s0 = 0; s0 < nd; s0 += PD) {
 #pragma unroll
         for (int i = 0; i < PD; ++i) {
             const int s = s0 + i;                          // diagonal of this step; ring slot i
             if (s >= nd) break;
-            if (W > 1 && lane == 31) bnd[i & 1][warp + 1] = v[K - 1];   // boundary column of the previous step
+            if (W > 1 && lane == 31) bnd[i & 1][warp + 1] = make_float2(v[K - 1].hi, v[K - 1].lo);   // boundary column, previous step
             cp_async_wait<PD - 2>();                        // this step's diagonal has landed (own copies) ...
             if (W > 1) __syncthreads();                     // ... everybody's, and the slot refilled below has been read
             else __syncwarp();
@@ -373,21 +392,25 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
                 sl[0] = stage[i][1][u0];
             }
             // left neighbour column's value of the previous step
-            const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v[K - 1]), 1);
-            const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v[K - 1]), 1);
-            double left = (lane > 0) ? __hiloint2double(hi, lo) : kLatNeg;
-            if (W > 1 && lane == 0 && warp > 0) left = bnd[i & 1][warp];
-            double nv[K];
+            df32 left;
+            left.hi = __shfl_up_sync(0xffffffffu, v[K - 1].hi, 1);
+            left.lo = __shfl_up_sync(0xffffffffu, v[K - 1].lo, 1);
+            if (lane == 0) left = neg;
+            if (W > 1 && lane == 0 && warp > 0) {
+                const float2 bv = bnd[i & 1][warp];
+                left = {bv.x, bv.y};
+            }
+            df32 nv[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int u = u0 + j, t = s - u;
                 const bool on = u < U1 && t >= 0 && t < T;
-                const double from_t = v[j] + (double)(t > 0 ? sb[j] : 0.f);          // v = sentinel when there is no cell above
-                const double from_u = (j > 0 ? v[j > 0 ? j - 1 : 0] : left) + (double)(u > 0 ? sl[j] : 0.f);
-                double val = log_add(from_t, from_u);
-                if (s == 0) val = is_beta ? (double)sb[j] : 0.0;                      // x(0,0): beta starts from lp_blank(T-1,U)
-                val = on ? val : kLatNeg;
-                if (on) out[(size_t)s * P + j] = val;
+                const df32 from_t = df_add(v[j], t > 0 ? sb[j] : 0.f);               // v = sentinel when there is no cell above
+                const df32 from_u = df_add(j > 0 ? v[j > 0 ? j - 1 : 0] : left, u > 0 ? sl[j] : 0.f);
+                df32 val = log_add(from_t, from_u);
+                if (s == 0) val = {is_beta ? sb[j] : 0.f, 0.f};                      // x(0,0): beta starts from lp_blank(T-1,U)
+                val = on ? val : neg;
+                if (on) out[(size_t)s * P + j] = df_value(val);
                 nv[j] = val;
             }
 #pragma unroll
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
     // both lattices end in their last cell (T-1, U1-1), alone on diagonal nd - 1
     const int j_last = U1 - 1 - u0;
     if (j_last >= 0 && j_last < K) {
-        const double x = (K == 2 && j_last == 1) ? v[K - 1] : v[0];
+        const double x = df_value((K == 2 && j_last == 1) ? v[K - 1] : v[0]);
         if (is_beta) ll_beta[b] = x;                                                   // beta(0, 0)
         else costs[b] = (float)-(x + (double)__ldg(ws + 2 * lat_elems + base));       // + lp_blank(T-1, U1-1)
     }

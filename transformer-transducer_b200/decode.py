@@ -21,7 +21,8 @@ import torch
 from . import _lib
 from .joint import JointNet, JointNetwork
 
-SCAN_FRAMES = 64
+SCAN_FRAMES = 64        # frames per launch group at most (the kernel's tile)
+SCAN_FIRST = 8          # frames scored right after a label; doubled while only blanks come back
 
 
 def _p(t):
@@ -45,7 +46,9 @@ class _JointParts:
             out = joint.project_layer
         else:
             raise TypeError("unknown joint module %r" % type(joint))
-        self.w_out, self.b_out = out.weight.detach().float().contiguous(), out.bias.detach().float().contiguous()
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731  (once per utterance)
+        self.w_enc, self.b_enc, self.w_dec = f32(self.w_enc), f32(self.b_enc), f32(self.w_dec)
+        self.w_out, self.b_out = f32(out.weight), f32(out.bias)
 
 
 @torch.no_grad()
@@ -64,27 +67,29 @@ def greedy_search(joint, enc_state, length, step_decoder, start_token=0, blank=0
         return tokens[1:]
     with torch.cuda.device(dev):
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc.float(),
-                                           None if parts.b_enc is None else parts.b_enc.float()).contiguous()
+        eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
         scratch = torch.empty(SCAN_FRAMES, dtype=torch.int64, device=dev)
         out = torch.empty(2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
         pvec = None
         t = 0
+        look = SCAN_FIRST
         while t < length:
             if pvec is None:
                 dec = step_decoder(tokens).reshape(-1).float()
-                pvec = torch.nn.functional.linear(dec, parts.w_dec.float()).contiguous()
-            n = min(SCAN_FRAMES, length - t)
+                pvec = torch.nn.functional.linear(dec, parts.w_dec)
+            n = min(look, length - t)
             st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.ttx_decode_scan(_p(eproj[t]), H, _p(pvec), _p(parts.w_out), _p(parts.b_out), n, H, V, int(blank),
                                            _p(scratch), _p(out), idx, st), "ttx_decode_scan")
             first, label = out[:2].tolist()                     # the one host read per emitted label / 64 blank frames
             if first >= n:
                 t += n
+                look = min(SCAN_FRAMES, 2 * look)               # a run of blanks: look further ahead next time
                 continue
             tokens.append(int(label))
             pvec = None
             t += first + 1
+            look = SCAN_FIRST
     return tokens[1:]
 
 
