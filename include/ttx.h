@@ -218,6 +218,21 @@ int ttx_decode_scan(const float* eproj, int ld_e, const float* pvec, const float
 int ttx_spec_mask(float* x, int B, int T, int F, int64_t stride_b, int64_t stride_t, const int32_t* masks_host, int n_masks,
                   int device, void* stream);
 
+/* ---- Banded (streaming) relative-position attention core of the tt encoder: RelLearnableMultiHeadAttn.forward
+ * (tt/transformer.py:121-167) under the context mask of tt/utils.py:242-251 (a query sees `left` frames back and `right`
+ * frames ahead).  fp32.  w_heads (T, B, 3 * n_head * d_head) = qkv_net's output [q | k | v]; r_emb (max_len, n_head, d_head),
+ * r_w_bias (n_head, d_head), r_bias (max_len, n_head); scale = 1 / sqrt(d_head).  prob (T, B, n_head, left + right + 1):
+ * the band's softmax, kept for the backward; out (T, B, n_head * d_head) = attn_vec (transformer.py:165-167).
+ * Backward: ds (like prob) and dq_content (T, B, n_head * d_head) are scratch; d_w_heads is fully written; d_r_emb,
+ * d_r_w_bias, d_r_bias must be zero-filled (they are accumulated). */
+int ttx_band_attn_fwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* r_bias, int T, int B,
+                      int n_head, int d_head, int max_len, int left, int right, float scale, float* prob, float* out,
+                      int device, void* stream);
+int ttx_band_attn_bwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* prob, const float* d_out,
+                      int T, int B, int n_head, int d_head, int max_len, int left, int right, float scale, float* ds,
+                      float* dq_content, float* d_w_heads, float* d_r_emb, float* d_r_w_bias, float* d_r_bias, int device,
+                      void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

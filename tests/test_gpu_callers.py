@@ -352,3 +352,59 @@ def test_mask_augment_launch_is_bit_identical_to_reference_slices():
         assert tu.time_mask_augment is ref_time
         assert torch.equal(got, want) and torch.equal(fused, want)
         assert 0 < int((want == 0).sum()) < want.numel()
+
+
+# ----------------------------------------------------------------------------- banded streaming attention
+@pytest.mark.parametrize("T,max_len,ctx", [(57, 410, (10, 2)), (410, 410, (10, 2)), (45, 30, (10, 2)), (33, 64, (3, 4)),
+                                          (5, 16, (10, 2))])
+def test_banded_attention_equals_reference_under_context_mask(T, max_len, ctx):
+    """tt/transformer.py:106-177 (the reference's own module, dense T x T scores, on cuda:0) vs the rebound forward whose
+    attention core runs on the band, under tt/utils.py:242-251's context mask as tt/model.py:60 would pass it ((T, T, 1)):
+    output and every gradient (input, qkv_net, o_net, LayerNorm, r_emb, r_w_bias, r_bias), including the
+    keys right of the diagonal whose position term _rel_shift wraps around, T > max_len (padded tables), T shorter than the
+    context, another context width.  Tolerance 2e-5 relative L2 (fp32 both sides, different summation order)."""
+    ref_import.prepare(stub_train_deps=True)
+    import tt.transformer as ttr
+    import tt.utils as tu
+    from transformer_transducer_b200 import attention as att
+    _seed(T)
+    B, n_head, d_head, d_model = 3, 4, 64, 256
+    attn = ttr.RelLearnableMultiHeadAttn(n_head, d_model, d_head, dropout=0.0).to(DEV)
+    r_emb = torch.randn(max_len, n_head, d_head, device=DEV).mul_(0.3).requires_grad_()
+    r_w_bias = torch.randn(n_head, d_head, device=DEV).mul_(0.3).requires_grad_()
+    r_bias = torch.randn(max_len, n_head, device=DEV).mul_(0.3).requires_grad_()
+    w = torch.randn(T, B, d_model, device=DEV, requires_grad=True)
+    g = torch.randn(T, B, d_model, device=DEV)
+    mask = tu.context_mask(torch.empty(1, T, 1, device=DEV), left_context=ctx[0], right_context=ctx[1])[:, :, None]
+    leaves = [w, r_emb, r_w_bias, r_bias] + list(attn.parameters())
+
+    def run():
+        for t_ in leaves:
+            t_.grad = None
+        out = attn(w, r_emb, r_w_bias, r_bias, attn_mask=mask)
+        out.backward(g)
+        return out.detach().clone(), [t_.grad.detach().clone() for t_ in leaves]
+
+    want, want_g = run()
+    calls = []
+    orig_apply = att.BandAttnCore.apply
+    try:
+        done = ttb.install(patch_tt=False, patch_espnet=False, patch_decode=False, patch_data=False, streaming_context=ctx)
+        assert "tt.transformer.RelLearnableMultiHeadAttn.forward" in done
+        att.BandAttnCore.apply = staticmethod(lambda *a: (calls.append(1), orig_apply(*a))[1])
+        got, got_g = run()
+        # a mask that is not the context band goes to the reference's forward
+        other = mask.clone()
+        other[0, min(T - 1, 1), 0] = 1 - other[0, min(T - 1, 1), 0]
+        n_calls = len(calls)
+        attn(w, r_emb, r_w_bias, r_bias, attn_mask=other)
+        assert len(calls) == n_calls
+    finally:
+        att.BandAttnCore.apply = orig_apply
+        ttb.uninstall()
+    assert calls, "the band kernel did not run"
+    assert ttr.RelLearnableMultiHeadAttn.forward is not att.banded_forward
+    assert rel(got, want) < 2e-5
+    names = ["w", "r_emb", "r_w_bias", "r_bias"] + [n for n, _ in attn.named_parameters()]
+    for n, a, b in zip(names, got_g, want_g):
+        assert rel(a, b) < 2e-5, (n, rel(a, b))

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libttx.so")
-SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu", "ttx_proj.cu", "ttx_decode.cu"]
+SOURCES = ["ttx_api.cu", "ttx_small.cu", "ttx_joint_mma.cu", "ttx_wide.cu", "ttx_proj.cu", "ttx_decode.cu", "ttx_attn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 _lock = threading.Lock()
@@ -59,6 +59,10 @@ _PROTOS = {
     "ttx_proj_bwd_w": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_p],
     "ttx_decode_scan": [c_p, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_spec_mask": [c_p, c_i32, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_i32, c_p],
+    "ttx_band_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_p, c_p, c_i32,
+                          c_p],
+    "ttx_band_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_p, c_p,
+                          c_p, c_p, c_p, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],

@@ -6,11 +6,14 @@ and ``tt_espnet/model.py:14`` copies ``JointNetwork`` at import, so patching the
 needs no patch: ``from warprnnt_pytorch import RNNTLoss`` (train.py:13) finds the ``warprnnt_pytorch``
 package of this repository once the repository root is on ``sys.path``.  The greedy-search methods
 (``Transducer.decode``, ``TransformerTransducer.decode``) are rebound to decode.py's versions, the mask augmentation
-(``tt.utils.time_mask_augment`` / ``frequency_mask_augment``) to data.py's single-launch versions.
+(``tt.utils.time_mask_augment`` / ``frequency_mask_augment``) to data.py's single-launch versions, and
+``tt.transformer.RelLearnableMultiHeadAttn.forward`` to attention.py's banded version (it only takes calls whose mask
+is the streaming context mask; everything else runs the reference's forward).
 """
 import importlib
 import sys
 
+from . import attention as _attention
 from . import data as _data
 from . import decode as _decode
 from .joint import JointNet, JointNetwork
@@ -41,8 +44,21 @@ def _patch_decode(cls, fn, name, done):
     done.append(name)
 
 
-def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True):
+def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True, patch_attention=True,
+            streaming_context=(10, 2)):
     done = []
+    if patch_attention:
+        # tt/transformer.py:106-177: the attention core on a band when the mask is tt.utils.context_mask(left, right)
+        try:
+            m = importlib.import_module("tt.transformer")
+            cls = m.RelLearnableMultiHeadAttn
+            if cls.forward is not _attention.banded_forward:
+                cls._ttb_reference_forward = cls.forward
+                _set(cls, "forward", _attention.banded_forward)
+                done.append("tt.transformer.RelLearnableMultiHeadAttn.forward")
+            _set(_attention, "CONTEXT", (int(streaming_context[0]), int(streaming_context[1])))
+        except ImportError:
+            pass
     if patch_data:
         # tt/utils.py:297-329; train.py:18 copies the names at import (`from tt.utils import ...`)
         for modname in ("tt.utils", "train"):
