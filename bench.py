@@ -358,10 +358,12 @@ def main():
                  "ttx_wide_dw": 1.0}.get(dom, 1.0)
     unit_flops_dom = unit_flops * alg_units
     achieved = unit_flops_dom / (dom_ms * 1e-3) / 1e12
-    traffic = None
+    traffic = tensor_pct = None
     tpath = os.path.join(ROOT, "profiles", "traffic_bytes.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+    if os.path.exists(tpath):                    # ncu captures of an earlier run of this command (not measured live)
+        tj = json.load(open(tpath))
+        traffic = tj.get(args.workload, {}).get(dom)
+        tensor_pct = tj.get(args.workload + "_tensor_pipe_active_pct", {}).get(dom)
     step_ms = ms / args.steps
     out = {
         "metric": "joint+RNN-T loss fwd+bwd utterances/s",
@@ -381,7 +383,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tflops"], "frac_burst": achieved / pk["burst"], "peak_burst": pk["burst"],
-                     "traffic": traffic, "kernel_ms": dom_ms,
+                     "traffic": traffic, "traffic_source": "profiles/traffic_bytes.json (ncu capture, see its _source)" if traffic else None,
+                     "tensor_pipe_active_pct_ncu": tensor_pct, "kernel_ms": dom_ms,
                      "algorithmic_flops_per_launch": unit_flops_dom, "peak_source": pk["source"]},
         "roofline_step": {"algorithmic_flops": 3 * unit_flops, "achieved": 3 * unit_flops / (step_ms * 1e-3) / 1e12,
                           "frac": 3 * unit_flops / (step_ms * 1e-3) / 1e12 / pk["tflops"],
