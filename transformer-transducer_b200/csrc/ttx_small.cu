@@ -1044,7 +1044,11 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,
                                  const int* __restrict__ meta, int U1, int H, int blank,
                                  int t_chunk, float* __restrict__ d_w, float* __restrict__ d_b,
-                                 float* __restrict__ blank_slots) {
+                                 float* __restrict__ blank_slots, const float* __restrict__ pfac, float up,
+                                 uint16_t* __restrict__ as, uint16_t* __restrict__ svec) {
+    // as != null: the pass also writes the scaled operand copy As = (up * w * pfac) * A16 of the rows it visits (and their
+    // scales) -- it has the row and its weight in registers anyway, so A16 is read once for both (scale_rows_kernel is
+    // the stand-alone version; rows outside the utterances are zeroed by pad_rows_kernel)
     if (meta[1] != 0) return;
     const int u = blockIdx.x, b = blockIdx.y;
     const int Tb = act_lens[b], U1b = label_lens[b] + 1;
@@ -1078,6 +1082,23 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
                 av[e] = __ldg(reinterpret_cast<const uint4*>(a16 + m * H + h));
                 eb[e] = (h == 0) ? w * __expf(__ldg(lpb + m)) : 0.f;
                 el[e] = (h == 0 && has_label) ? w * __expf(__ldg(lpl + m)) : 0.f;
+                if (as != nullptr && in) {
+                    const float sc = (w != 0.f) ? w * __ldg(pfac + m) * up : 0.f;
+                    uint4 o = make_uint4(0, 0, 0, 0);
+                    if (sc != 0.f) {
+                        const uint32_t i4[4] = {av[e].x, av[e].y, av[e].z, av[e].w};
+                        uint32_t r4[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float x0, x1;
+                            unpk16<BF16>(i4[k], x0, x1);
+                            r4[k] = pack16<BF16>(x0 * sc, x1 * sc);
+                        }
+                        o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+                    }
+                    *reinterpret_cast<uint4*>(as + m * H + h) = o;
+                    if (h == 0) svec[m] = (uint16_t)(pack16<BF16>(sc, 0.f) & 0xffffu);
+                }
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -1114,6 +1135,27 @@ __global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4*
     }
 }
 
+// rows of As / svec that belong to no lattice cell -- the tail of every utterance's last tile, and the pad tile of an odd
+// tile count -- must be exact zeros (their P' rows are finite).  grid = B + 1.
+__global__ void pad_rows_kernel(const int* __restrict__ act_lens, const int* __restrict__ label_lens,
+                                const int* __restrict__ meta, int B, int H, uint16_t* __restrict__ as,
+                                uint16_t* __restrict__ svec) {
+    if (meta[1] != 0) return;
+    size_t r0, r1;
+    if ((int)blockIdx.x < B) {
+        const int b = blockIdx.x;
+        r0 = (size_t)meta[kMetaHdr + b] * kTile + (size_t)act_lens[b] * (label_lens[b] + 1);
+        r1 = (size_t)meta[kMetaHdr + b + 1] * kTile;
+    } else {
+        r0 = (size_t)meta[0] * kTile;
+        r1 = (size_t)((meta[0] + 1) & ~1) * kTile;
+    }
+    const size_t n16 = (r1 - r0) * (size_t)(H / 8);                  // 16-byte pieces
+    uint4* dst = reinterpret_cast<uint4*>(as + r0 * H);
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+    for (size_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) svec[r] = 0;
+}
+
 __global__ void blank_fold_kernel(const float* __restrict__ blank_slots, int H, int blank,
                                   float* __restrict__ d_w, float* __restrict__ d_b) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1128,20 +1170,21 @@ int launch_kept_prepare(const void* a16, const float4* rowmeta, const int* row_l
                         const float* lpb, const float* lpl, const float* pfac, const float* scal, const int* act_lens,
                         const int* label_lens, const int* meta, int B, int T, int U1, int H, int blank,
                         bool bf16, size_t rows_total, void* a16st, float* d_w, float* d_b, int parts, cudaStream_t s) {
-    if (parts & 1) {                             // the scaled operand copy
-        const float up = bf16 ? 1.f : kKeptUp;
+    const float up = bf16 ? 1.f : kKeptUp;
+    uint16_t* as = static_cast<uint16_t*>(a16st);
+    uint16_t* svec = as + rows_total * (size_t)H;              // [rows]: behind the matrix (see ttx.h for the layout)
+    if (parts == 1) {                            // the scaled operand copy alone
         const unsigned g1 = (unsigned)((rows_total * (size_t)(H / 8) + 255) / 256);
-        uint16_t* as = static_cast<uint16_t*>(a16st);
-        uint16_t* svec = as + rows_total * (size_t)H;          // [rows]: behind the matrix (see ttx.h for the layout)
         if (bf16)
             scale_rows_kernel<true><<<g1, 256, 0, s>>>((const uint16_t*)a16, rowmeta, pfac, meta, H, rows_total, up, as, svec);
         else
             scale_rows_kernel<false><<<g1, 256, 0, s>>>((const uint16_t*)a16, rowmeta, pfac, meta, H, rows_total, up, as, svec);
-    }
-    if (!(parts & 2)) {
         TTX_CUDA_OK(cudaGetLastError());
         return 0;
     }
+    // the blank / label terms, and (parts == 3) the operand copy in the same pass over A16
+    const bool both = parts == 3;
+    if (both) pad_rows_kernel<<<B + 1, 256, 0, s>>>(act_lens, label_lens, meta, B, H, as, svec);
     const int t_chunk = 64;                      // (longer chunks = fewer atomics were slower: 0.31 -> 0.35 ms at 512)
     const dim3 g2(U1, B, (T + t_chunk - 1) / t_chunk);
     const int threads = 128;                     // two groups of 64 threads x 8 joint columns
@@ -1151,10 +1194,12 @@ int launch_kept_prepare(const void* a16, const float4* rowmeta, const int* row_l
     TTX_CUDA_OK(cudaMemsetAsync(slots, 0, slot_bytes, s));
     if (bf16)
         dw_sparse_kernel<true><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                      label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots);
+                                                      label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots, pfac, up,
+                                                      both ? as : nullptr, svec);
     else
         dw_sparse_kernel<false><<<g2, threads, 0, s>>>((const uint16_t*)a16, rowmeta, row_label, lpb, lpl, scal, act_lens,
-                                                       label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots);
+                                                       label_lens, meta, U1, H, blank, t_chunk, d_w, d_b, slots, pfac, up,
+                                                       both ? as : nullptr, svec);
     blank_fold_kernel<<<(H + 1 + 127) / 128, 128, 0, s>>>(slots, H, blank, d_w, d_b);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
