@@ -244,12 +244,15 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                                        "r"((j * 4 + gg) * p.store_rows + srow0)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        // the PREVIOUS sub-tile's store has read its buffer by now (one store stays in flight)
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        if (n > 0) mbar_arrive(bar_pfree((n - 1) % NSB));
+                        // release the buffer as soon as THIS store has read it (a few hundred cycles; this thread has
+                        // nothing else to do).  Releasing a buffer only when the next sub-tile's store had been issued made
+                        // the warps of buffer 1 wait for the staging of buffer 0 of the same round (13 % of the kernel's
+                        // stall samples); the global writes stay in flight either way.
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(bar_pfree(b));
                     }
             }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (the last buffer is never waited for again)
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else if (warp == kSpMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
