@@ -221,7 +221,6 @@ def main():
                     help="peaked: trained-like output layer (larger weights, boosted blank / label biases)")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel table to stderr")
     ap.add_argument("--no-overlap", action="store_true", help="A/B runs: every kernel on the launching stream")
-    ap.add_argument("--sp-stream", action="store_true", help="A/B runs: the S pass streams both operands also at H = 512")
     ap.add_argument("--route", default="default", choices=["default", "fused", "chunked"],
                     help="A/B runs: fused = the recomputing kernels at H = 512 (nothing V-wide in HBM), chunked = library GEMMs")
     args = ap.parse_args()
@@ -236,8 +235,6 @@ def main():
         F.ROUTE = args.route
     if args.no_overlap:
         F.WideJointRNNT.OVERLAP = False
-    if args.sp_stream:
-        F.WideJointRNNT.SP_VARIANT = 1
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

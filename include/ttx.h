@@ -172,8 +172,7 @@ int ttx_wide_supported_h(int H);
 int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
                 const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
                 float* lse, float* lp_blank, float* lp_label, float* pfac, float* mref, void* pstore, int64_t store_rows,
-                int32_t* flags, int variant /* 0: default (H <= 512: the pair's A16 tiles stay in shared memory, only W16
-                streams); 1: both operands streamed at every width (A/B measurements) */, int device, void* stream);
+                int32_t* flags, int device, void* stream);
 int ttx_wide_pw(const void* pstore, int64_t store_rows, const void* w16t, const float* pfac, const float* scal,
                 const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int bf16, float* ew,
                 int device, void* stream);

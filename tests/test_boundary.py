@@ -57,7 +57,7 @@ def test_kept_matrix_chunking_and_entry_points_reject_bad_arguments():
     null = ctypes.c_void_p(0)
     rc = lib.ttx_joint_fwd_grad(*([null] * 7), 1, 512, 10, 0, 0, *([null] * 5), 0, 0, null)
     assert rc == 1 and b"null pointer" in lib.ttx_last_error()
-    rc = lib.ttx_wide_sp(*([null] * 6), 4, 0, 4, 512, 10, 0, 0, *([null] * 6), 512, null, 0, 0, null)
+    rc = lib.ttx_wide_sp(*([null] * 6), 4, 0, 4, 512, 10, 0, 0, *([null] * 6), 512, null, 0, null)
     assert rc == 1 and b"null pointer" in lib.ttx_last_error()
     x = ctypes.c_void_p(256)                                                          # never dereferenced: checks come first
     rc = lib.ttx_wide_pw(x, 512, x, x, x, x, 4, 1, 4, 512, 10, 0, x, 0, null)           # odd tile_lo

@@ -402,20 +402,17 @@ def test_c_abi_rejects_unsupported_width_with_message():
     assert rc == 1 and b"not supported" in lib.ttx_last_error()
 
 
-@pytest.mark.parametrize("variant", ["wide", "wide-chunked", "wide-sp-stream", "fused", "fused-no-replay", "fused-separate-dA", "generic",
+@pytest.mark.parametrize("variant", ["wide", "wide-chunked", "fused", "fused-no-replay", "fused-separate-dA", "generic",
                                      "chunked"])
 def test_kernel_variants_agree_with_oracle(variant, monkeypatch):
     """Every route of H = 512 meets the tolerance on a batch with an odd number of lattice tiles (the pad tile of the last
-    pair) and a negative grad_output: the default (streamed products around the kept P'; S pass with the stationary A16
-    tile); the same with a budget of one tile pair (several chunks, P' recomputed in the backward); with the S pass that
-    streams both operands (what H >= 1024 runs); the fused recomputing kernels with their bounded P' replay
+    pair) and a negative grad_output: the default (streamed products around the kept P'); the same with a budget of one
+    tile pair (several chunks, P' recomputed in the backward); the fused recomputing kernels with their bounded P' replay
     workspace, without it, and with the separate activation-gradient launch; the generic single-CTA backward kernels
     (no transposed operand copies: what H = 64 / 192 / 384 run); the library-GEMM chunked fallback."""
     from transformer_transducer_b200 import functional as Fn
     if variant == "wide-chunked":
         monkeypatch.setenv("TTX_KEEP_GB", "1e-9")
-    elif variant == "wide-sp-stream":
-        monkeypatch.setattr(Fn.WideJointRNNT, "SP_VARIANT", 1)
     elif variant == "chunked":
         monkeypatch.setattr(Fn, "ROUTE", "chunked")
     elif variant != "wide":

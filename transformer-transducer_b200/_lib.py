@@ -45,7 +45,7 @@ _PROTOS = {
                                c_p, c_p, c_i32, c_p],
     "ttx_wide_supported_h": [c_i32],
     "ttx_wide_sp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p,
-                    c_p, c_i64, c_p, c_i32, c_i32, c_p],
+                    c_p, c_i64, c_p, c_i32, c_p],
     "ttx_wide_pw": [c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_wide_dw": [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_kept_prepare": [c_p] * 10 + [c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_p],

@@ -54,7 +54,7 @@ int launch_joint_bwd(const void*, const void*, const void*, const void*, uint64_
 
 bool wide_supported_h(int H);
 int launch_wide_sp(const void*, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*, const float*,
-                   const int*, int, float*, float*, float*, float*, float*, void*, uint64_t, int*, int, cudaStream_t);
+                   const int*, int, float*, float*, float*, float*, float*, void*, uint64_t, int*, cudaStream_t);
 int launch_wide_pw(const void*, uint64_t, const void*, int, int, int, int, int, bool, const int*, const float*, const float*,
                    float*, cudaStream_t);
 int launch_wide_dw(const void*, uint64_t, const void*, uint64_t, int, int, int, int, int, bool, const int*, const float*,
@@ -282,7 +282,7 @@ static int wide_range_ok(const char* who, int64_t n_tiles_ub, int tile_lo, int t
 int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const float* scal, const int32_t* row_label,
                 const int32_t* meta, int64_t n_tiles_ub, int tile_lo, int tile_cnt, int H, int V, int blank, int bf16,
                 float* lse, float* lp_blank, float* lp_label, float* pfac, float* mref, void* pstore, int64_t store_rows,
-                int32_t* flags, int variant, int device, void* stream) {
+                int32_t* flags, int device, void* stream) {
     TTX_REQUIRE(a16 && w16 && bias2 && scal && row_label && meta && lse && lp_blank && lp_label && pfac && mref && pstore &&
                     flags, "ttx_wide_sp: null pointer");
     TTX_REQUIRE(wide_supported_h(H), "ttx_wide_sp: joint width H=%d is not supported (multiples of 512 up to 4096)", H);
@@ -292,7 +292,7 @@ int ttx_wide_sp(const void* a16, const void* w16, const float* bias2, const floa
     const int Vpad = ((V + 2 * kTile - 1) / (2 * kTile)) * (2 * kTile);
     return launch_wide_sp(a16, w16, (uint64_t)n_tiles_ub * kTile, tile_lo, tile_cnt, H, V, Vpad, bf16 != 0, meta, bias2, scal,
                           row_label, blank, lse, lp_blank, lp_label, pfac, mref, pstore, (uint64_t)store_rows, flags,
-                          variant, (cudaStream_t)stream);
+                          (cudaStream_t)stream);
 }
 
 int ttx_wide_pw(const void* pstore, int64_t store_rows, const void* w16t, const float* pfac, const float* scal,

@@ -129,16 +129,16 @@ struct EventWait {
 
 // =========================================================================================================== S pass
 // With both operands streamed the S pass wants 64 B/cycle/SM through TMA and gets ~42: 256 KiB per 128 x 256 tile take
-// ~6100 cycles against 4096 of MMA time (ncu: tensor pipe 66 %).  XS (H <= 512): the pair's A16 tiles stay in shared memory
-// for the whole unit (128 KiB per CTA, loaded chunk by chunk behind their own barriers) and only W16 streams -- half the
-// bytes.  The stationary tile takes the room of the P' staging buffers, so in this variant the epilogue stores P' straight
-// from registers (64 contiguous bytes per thread and round) and the ring keeps five 16 KiB stages; with the staging
-// buffers and three stages it was latency-bound and slower than streaming (2.23 vs 2.02 ms at configs[1]).
-template <bool BF16, bool XS>
+// ~6100 cycles against 4096 of MMA time (ncu: tensor pipe 66 %).  Keeping the pair's A16 tiles stationary in shared memory
+// (H <= 512: 128 KiB per CTA, only W16 streams) halves the bytes, but the tile takes the room of either the ring or the P'
+// staging buffers, and both trades lose at configs[1] (streaming both: 2.02 - 2.19 ms): staging buffers + three 16 KiB
+// ring stages 2.23 ms (latency-bound ring); five stages + P' stored straight from registers 3.32 ms with 16-byte stores
+// (half-sector writes), 2.87 ms with 32-byte stores.
+template <bool BF16>
 __global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
           const __grid_constant__ CUtensorMap mapP, const WideParams p) {
-    constexpr int STG = XS ? kChunkBytes : kSpStage;       // bytes of one ring stage (W chunk, or A chunk + W chunk)
+    constexpr int STG = kSpStage;                          // bytes of one ring stage (A chunk + W chunk)
     constexpr int NSB = 2;                                 // staging buffers: one 64-column P' sub-tile each, used in turn
     const uint32_t rank = cluster_ctarank();
     const bool leader = (rank == 0);
@@ -157,8 +157,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     }
     const uint32_t sRing = smem_base;
     const uint32_t sStage = sRing + p.NS * STG;            // NSB [128 x 64] 16-bit P' sub-tiles (128B swizzle) for the TMA store
-    const uint32_t sX = sStage;                            // XS: the stationary A16 tile (NKC chunks) instead of the staging buffers
-    const uint32_t sBar = sStage + (XS ? p.NKC : NSB) * kChunkBytes;
+    const uint32_t sBar = sStage + NSB * kChunkBytes;
     const uint32_t sTmemPtr = sBar + 40 * 8;
     const uint32_t sWatch = sTmemPtr + 8;
     const uint32_t sXg = sTmemPtr + 16;                    // [4][128] floats: row maxima of the four column groups
@@ -171,16 +170,12 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
     auto bar_sempty = [&](int b) { return sBar + 8 * (18 + b); };
     auto bar_pwritten = [&](int b) { return sBar + 8 * (20 + b); };   // this CTA's epilogue warps have staged a sub-tile in buffer b
     auto bar_pfree = [&](int b) { return sBar + 8 * (22 + b); };      // ... and the TMA store has read it out of shared memory
-    auto bar_xfull = [&](int c) { return sBar + 8 * (24 + c); };      // XS: chunk c of the stationary tile has landed
-    const uint32_t bar_xempty = sBar + 8 * 32;                        // XS: the unit's last S pass has read the tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kSpProducerWarp && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapP);
-        for (int c = 0; c < 8; ++c) mbar_init(bar_xfull(c), 1);
-        mbar_init(bar_xempty, 1);
         for (int b = 0; b < NSB; ++b) {
             mbar_init(bar_pwritten(b), kSpEpiWarps / 2);     // the eight warps that stage into buffer b
             mbar_init(bar_pfree(b), 1);
@@ -207,33 +202,23 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         if (warp == kSpProducerWarp && lane == 0) {
             // =================================================== TMA producer (each CTA: its rows of A16, its half of W16)
             Ring r;
-            int xt = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
                 const int x_row0 = (p.tile_lo + unit * 2 + (int)rank) * kTile;
-                if (XS) {
-                    if (xt > 0) mbar_wait(bar_xempty, (xt - 1) & 1);
-                    ++xt;
-                    for (int c = 0; c < p.NKC; ++c) {
-                        if (leader) mbar_arrive_expect_tx(bar_xfull(c), 2 * kChunkBytes);
-                        tma_load_2d_pair(sX + c * kChunkBytes, &mapX, bar_xfull(c), c * kKC, x_row0);
-                    }
-                }
                 for (int j = 0; j < p.n_vchunks; ++j)
                     for (int c = 0; c < p.NKC; ++c) {
                         mbar_wait(bar_empty(r.stage), r.phase ^ 1);
                         if (leader) mbar_arrive_expect_tx(bar_full(r.stage), 2 * STG);
                         const uint32_t dst = sRing + r.stage * STG;
-                        if (!XS) tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
-                        tma_load_2d_pair(dst + (XS ? 0 : kChunkBytes), &mapY, bar_full(r.stage), c * kKC,
-                                         j * 256 + (int)rank * kTile);
+                        tma_load_2d_pair(dst, &mapX, bar_full(r.stage), c * kKC, x_row0);
+                        tma_load_2d_pair(dst + kChunkBytes, &mapY, bar_full(r.stage), c * kKC, j * 256 + (int)rank * kTile);
                         r.advance(p.NS);
                     }
             }
         } else if (warp == kSpWatchWarp && lane == 0 && leader) {
             // =================================================== barrier watcher: the issuer's barriers, in its order
             volatile int* ready = reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base));
-            int done = 0, g = 0, xt = 0;
+            int done = 0, g = 0;
             Ring r;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
                 if (skip_unit(unit)) continue;
@@ -241,15 +226,13 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     mbar_wait(bar_sempty(g & 1), ((g >> 1) & 1) ^ 1);
                     *ready = ++done;
                     for (int c = 0; c < p.NKC; ++c) {
-                        if (XS && j == 0) mbar_wait(bar_xfull(c), xt & 1);
                         mbar_wait(bar_full(r.stage), r.phase);
                         *ready = ++done;
                         r.advance(p.NS);
                     }
                 }
-                ++xt;
             }
-        } else if (!XS && warp == kSpWatchWarp + 1 && lane == 0) {
+        } else if (warp == kSpWatchWarp + 1 && lane == 0) {
             // =================================================== storer (each CTA): staged P' tile -> the blocked matrix
             int n = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -276,7 +259,7 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
         } else if (warp == kSpMmaWarp && lane == 0 && leader) {
             // =================================================== MMA issuer
             const uint32_t idescS = make_idesc(BF16 ? 1 : 0, 0, 0, 256, 256);
-            const uint32_t rlo = desc_lo(sRing), xlo = desc_lo(sX);
+            const uint32_t rlo = desc_lo(sRing);
             EventWait ev{reinterpret_cast<volatile int*>(smem_gen + (sWatch - smem_base))};
             int stage = 0, g = 0;
             for (int unit = unit0; unit < n_units; unit += unit_step) {
@@ -288,14 +271,12 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                     for (int c = 0; c < p.NKC; ++c) {
                         ev.wait();                          // ring stage has landed
                         tc_fence_after();
-                        const uint32_t a = XS ? xlo + c * (kChunkBytes >> 4) : rlo + stage * (STG >> 4);
-                        const uint32_t b = XS ? rlo + stage * (STG >> 4) : a + (kChunkBytes >> 4);
+                        const uint32_t a = rlo + stage * (STG >> 4), b = a + (kChunkBytes >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_f16_ss_pair_lo(d, a + 2 * k, b + 2 * k, idescS, (c | k) != 0);
                         umma_commit_pair(bar_empty(stage));
                         if (++stage == p.NS) stage = 0;
                     }
-                    if (XS && j == p.n_vchunks - 1) umma_commit_pair(bar_xempty);   // the next unit's tile may replace this one
                     umma_commit_pair(bar_sfull(g & 1));
                 }
             }
@@ -347,7 +328,6 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
             const int tile = p.tile_lo + unit * 2 + (int)rank;
             const bool valid_x = tile < n_tiles;
             const int grow = tile * kTile + row;
-            const size_t srow = (size_t)(unit * 2 + (int)rank) * kTile + row;      // row of the P' matrix (relative to tile_lo)
             const int label = valid_x ? p.row_label[grow] : -1;
             // (redo: rows of a pad tile have no stored reference -- an unreachable one makes their P' exact zeros)
             float mref = p.redo ? (valid_x ? p.mref[grow] : 1.0e4f) : 0.f;
@@ -424,36 +404,18 @@ sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUte
                         for (int e = 0; e < 32; ++e) v = (e == clb) ? __uint_as_float(acc[e]) : v;
                         zl = v - krow;
                     }
-                    // the blank and label columns are left out of P' (their exact terms are added in fp32 later)
-                    if (XS) {
-                        // straight to the blocked matrix: this thread's 32 columns are 64 contiguous bytes of its row
-                        if (cbl >= 0 && cbl < 32) {
+                    // stage this round's sub-tile (the store of the previous round's has read the buffer); the blank and
+                    // label columns are left out of P' (their exact terms are added in fp32 later)
+                    mbar_wait(bar_pfree(sub), (rd & 1) ^ 1);
 #pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                if (e == (cbl >> 1)) pk[e] &= (cbl & 1) ? 0x0000FFFFu : 0xFFFF0000u;
-                        }
-                        if (clb >= 0 && clb < 32) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                if (e == (clb >> 1)) pk[e] &= (clb & 1) ? 0x0000FFFFu : 0xFFFF0000u;
-                        }
-                        uint4* gp = reinterpret_cast<uint4*>(
-                            p.pstore + ((size_t)(j * 4 + rd * 2 + sub) * p.store_rows + srow) * kKC + hf * 32);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) gp[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    } else {
-                        // stage this round's sub-tile (the store of the previous round's has read the buffer)
-                        mbar_wait(bar_pfree(sub), (rd & 1) ^ 1);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(r0 + (((hf * 4 + c) ^ (row & 7)) << 4)) =
-                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                        if (cbl >= 0 && cbl < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + cbl)) = 0;
-                        if (clb >= 0 && clb < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + clb)) = 0;
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_pwritten(sub));
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(r0 + (((hf * 4 + c) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    if (cbl >= 0 && cbl < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + cbl)) = 0;
+                    if (clb >= 0 && clb < 32) *reinterpret_cast<uint16_t*>(dstP + stile_off(row, hf * 32 + clb)) = 0;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_pwritten(sub));
                 }
                 float part;
                 {
@@ -878,7 +840,7 @@ static WideParams wide_params(int H, int V, int Vpad, int tile_lo, int tile_cnt,
 int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_lo, int tile_cnt, int H, int V, int Vpad,
                    bool bf16, const int* meta, const float* bias2, const float* scal, const int* row_label, int blank,
                    float* lse, float* lpb, float* lpl, float* pfac, float* mref, void* pstore, uint64_t store_rows,
-                   int* flags, int variant, cudaStream_t stream) {
+                   int* flags, cudaStream_t stream) {
     WideParams p = wide_params(H, V, Vpad, tile_lo, tile_cnt, store_rows, meta, scal);
     p.blank = blank;
     p.bias2 = bias2;
@@ -890,12 +852,10 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     p.mref = mref;
     p.pstore = static_cast<uint16_t*>(pstore);
     p.flags = flags;
-    const bool xs = H <= 512 && variant != 1;             // variant 1: stream both operands at every width (A/B runs)
-    const size_t stg = xs ? kChunkBytes : kSpStage;
-    const size_t fixed = (xs ? (size_t)p.NKC : 2) * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16 + 4 * 512 * 4;
+    const size_t fixed = 2 * kChunkBytes + 40 * 8 + 16 + 4 * kTile * 4 + 4 * kTile * 16 + 4 * 512 * 4;
     p.NS = 8;
-    while (p.NS > 2 && (size_t)p.NS * stg + fixed > 232448) --p.NS;
-    const size_t smem = (size_t)p.NS * stg + fixed;
+    while (p.NS > 2 && (size_t)p.NS * kSpStage + fixed > 232448) --p.NS;
+    const size_t smem = (size_t)p.NS * kSpStage + fixed;
     CUtensorMap mx, my, mp;
     if (int rc = make_tile_map(&mx, a16, rows_ub, H, bf16, kTile)) return rc;
     if (int rc = make_tile_map(&my, w16, (uint64_t)Vpad, H, bf16, kTile)) return rc;
@@ -903,10 +863,8 @@ int launch_wide_sp(const void* a16, const void* w16, uint64_t rows_ub, int tile_
     const unsigned grid = 2u * (unsigned)max(1, min((tile_cnt + 1) / 2, wide_sm_count() / 2));
     for (int redo = 0; redo < 2; ++redo) {
         p.redo = redo;
-        int rc = xs ? (bf16 ? launch_pair(sp_kernel<true, true>, kSpThreads, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, true>, kSpThreads, grid, smem, stream, mx, my, mp, p))
-                    : (bf16 ? launch_pair(sp_kernel<true, false>, kSpThreads, grid, smem, stream, mx, my, mp, p)
-                            : launch_pair(sp_kernel<false, false>, kSpThreads, grid, smem, stream, mx, my, mp, p));
+        int rc = bf16 ? launch_pair(sp_kernel<true>, kSpThreads, grid, smem, stream, mx, my, mp, p)
+                      : launch_pair(sp_kernel<false>, kSpThreads, grid, smem, stream, mx, my, mp, p);
         if (rc) return rc;
     }
     return 0;

@@ -290,7 +290,6 @@ class WideJointRNNT(torch.autograd.Function):
     with everything else (operand casts, lattice, coefficients, reductions) shared with the fused path.  No library GEMM."""
 
     OVERLAP = True      # False: everything on the launching stream (A/B runs)
-    SP_VARIANT = 0      # 1: the S pass streams both operands also at H = 512 (A/B runs)
 
     @staticmethod
     def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
@@ -358,7 +357,7 @@ class WideJointRNNT(torch.autograd.Function):
             store_rows, flags):
         _call("ttx_wide_sp", dev, _p(a16), _p(w16), _p(bias2), _p(scal), _p(row_label), _p(plan.meta), plan.ntub, t0, cnt,
               H, V, int(blank), int(bf16), _p(lse), _p(lpb), _p(lpl), _p(pfac), _p(mref), _p(pstore), store_rows,
-              _p(flags), WideJointRNNT.SP_VARIANT, plan.idx, st)
+              _p(flags), plan.idx, st)
 
     @staticmethod
     def backward(ctx, grad_costs):
