@@ -371,7 +371,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": ("bf16 tensor-core operands" if w.get("bf16") else "f16 tensor-core operands") +
-                 ", f32 accumulate/softmax, f64 lattice (%s variant)" % ("bf16-input" if w.get("bf16") else "fp32"),
+                 ", f32 accumulate/softmax, 48-bit (float + float) lattice carrier (%s variant)" % ("bf16-input" if w.get("bf16") else "fp32"),
         "data": "synthetic",
         "config": {"workload": w["desc"], "global_batch": world * w["B"], "parallelism": "dp%d" % world,
                    "logits": args.logits, "route": args.route,
