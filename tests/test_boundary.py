@@ -196,6 +196,7 @@ def test_install_rebinds_reference_classes_and_model_builds_unchanged():
         import tt_espnet.model as tem
         assert tem.JointNetwork is orig_es or tem.JointNetwork is ttb.JointNetwork
     finally:
+        ttb.uninstall()
         tt_model.JointNet = orig_tt
         sys.modules["espnet.nets.pytorch_backend.transducer.joint_network"].JointNetwork = orig_es
 
@@ -239,6 +240,7 @@ def test_unmodified_train_loop_runs_with_the_drop_ins():
         losses = [float(m.split(", Loss:")[1].split(",")[0]) for m in records if "Global Step" in m]
         assert len(losses) == 3 and losses[-1] < losses[0]
     finally:
+        ttb.uninstall()
         tt_model.JointNet = orig
 
 

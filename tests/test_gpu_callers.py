@@ -150,6 +150,7 @@ def test_unmodified_train_loop_drives_product_on_cuda(inner):
             # compared to 1e-3 above and the loss trajectory to 1e-3 here
             assert rel(a.detach().cpu() - init[n], b.detach() - init[n]) < 5e-2, n
     finally:
+        ttb.uninstall()
         tt_model.JointNet = orig
 
 
@@ -179,6 +180,7 @@ def _espnet_models(vocab):
     try:
         model = tem.TransformerTransducer(cfg)
     finally:
+        ttb.uninstall()
         jn.JointNetwork, tem.JointNetwork = orig
     assert isinstance(model.joint, ttb.JointNetwork) and not isinstance(ref_model.joint, ttb.JointNetwork)
     model.load_state_dict(ref_model.state_dict())
