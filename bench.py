@@ -235,6 +235,7 @@ def main():
         F.ROUTE = args.route
     if args.no_overlap:
         F.WideJointRNNT.OVERLAP = False
+        F.MERGE_PROJ_BACKWARD = False
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

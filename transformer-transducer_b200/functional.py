@@ -292,8 +292,15 @@ class WideJointRNNT(torch.autograd.Function):
     OVERLAP = True      # False: everything on the launching stream (A/B runs)
 
     @staticmethod
-    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None):
-        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+    def forward(ctx, eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank, bf16, sizes=None,
+                enc=None, w_enc=None, b_enc=None, dec=None, w_dec=None):
+        """enc .. w_dec (optional, float32): the inputs of the two pre-projections eproj = enc w_enc^T + b_enc,
+        pproj = dec w_dec^T.  When given, eproj / pproj come in detached and THIS node returns the gradients of
+        enc, w_enc, b_enc, dec, w_dec: its backward issues the projection-backward kernels right behind the
+        activation-gradient reduction, i.e. while the weight-gradient product is still running on the other stream
+        (as separate autograd nodes they could only start after the streams have joined)."""
+        pre = enc is not None
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (pre and any(ctx.needs_input_grad[10:15]))
         need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         if not eproj.is_cuda:
             raise RuntimeError("fused_joint_rnnt needs CUDA tensors (there is no CPU fallback)")
@@ -306,6 +313,10 @@ class WideJointRNNT(torch.autograd.Function):
         ep, pp = eproj.detach().float().contiguous(), pproj.detach().float().contiguous()
         w, b = w_out.detach().float().contiguous(), b_out.detach().float().contiguous()
         labels = labels.contiguous()
+        ctx.pre = None
+        if pre:
+            ctx.pre = (enc.detach().reshape(-1, enc.shape[-1]).contiguous(), w_enc.detach(), b_enc is not None,
+                       dec.detach().reshape(-1, dec.shape[-1]).contiguous(), w_dec.detach(), enc.shape, dec.shape)
         with torch.cuda.device(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
@@ -365,9 +376,11 @@ class WideJointRNNT(torch.autograd.Function):
          mref) = ctx.saved_tensors
         plan, (B, T, U1, H, V) = ctx.plan, ctx.dims
         dev = plan.dev
-        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        pre = ctx.pre
+        need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (pre is not None and any(ctx.needs_input_grad[10:15]))
         need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         d_ep = d_pp = d_w = d_b = None
+        pre_grads = [None] * 5
         with torch.cuda.device(dev):
             st = _stream(dev)
             scal = scal.clone()
@@ -416,6 +429,15 @@ class WideJointRNNT(torch.autograd.Function):
                 _call("ttx_reduce_act_grad_ew", dev, _p(ctx.ew), _p(rowmeta), _p(row_label), _p(ctx.w32), _p(scal),
                       ctx.blank, _p(ep), _p(pp), _p(plan.act_lens), _p(plan.label_lens), _p(plan.meta), B, T, U1, H,
                       _p(d_ep), _p(d_pp), plan.idx, st)
+                if pre is not None:
+                    # the pre-projections' backward, here, behind the reduction and next to the weight-gradient product
+                    x_e, w_e, has_b, x_d, w_d, enc_shape, dec_shape = pre
+                    ge = _proj_backward(dev, d_ep.view(-1, H), x_e, w_e, has_b, ctx.needs_input_grad[10],
+                                        ctx.needs_input_grad[11] or ctx.needs_input_grad[12], plan.idx, st)
+                    gd = _proj_backward(dev, d_pp.view(-1, H), x_d, w_d, False, ctx.needs_input_grad[13],
+                                        ctx.needs_input_grad[14], plan.idx, st)
+                    pre_grads = [ge[0].view(enc_shape) if ge[0] is not None else None, ge[1], ge[2],
+                                 gd[0].view(dec_shape) if gd[0] is not None else None, gd[1]]
             if need_w:
                 if hi is not None:
                     main.wait_stream(hi)
@@ -424,7 +446,24 @@ class WideJointRNNT(torch.autograd.Function):
         cast = lambda g, d, need: g.to(d) if (g is not None and need) else None  # noqa: E731
         return (cast(d_ep, dt[0], ctx.needs_input_grad[0]), cast(d_pp, dt[1], ctx.needs_input_grad[1]),
                 cast(d_w, dt[2], ctx.needs_input_grad[2]), cast(d_b, dt[3], ctx.needs_input_grad[3]),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None) + tuple(
+                    g if need else None for g, need in zip(pre_grads, ctx.needs_input_grad[10:15]))
+
+
+def _proj_backward(dev, dy, x, w, has_bias, need_x, need_w, idx, st):
+    """dx, dw, db of y = x w^T (+ b) on the projection kernels (csrc/ttx_proj.cu); dy (M, N) contiguous float32."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dx = dw = db = None
+    if need_x:
+        dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+        _call("ttx_proj_bwd_x", dev, _p(dy), N, _p(w), w.stride(0), M, N, K, _p(dx), K, idx, st)
+    if need_w:
+        dw = torch.zeros(N, K, dtype=torch.float32, device=dev)
+        db = torch.zeros(N, dtype=torch.float32, device=dev) if has_bias else None
+        _call("ttx_proj_bwd_w", dev, _p(dy), N, _p(x), K, M, N, K, _p(dw), K, _p(db), idx, st,
+              n_kernels=2 if db is not None else 1)
+    return dx, dw, db
 
 
 class ChunkedJointRNNT(torch.autograd.Function):
@@ -539,9 +578,10 @@ class ChunkedJointRNNT(torch.autograd.Function):
 # None: the default routing below.  "fused": the recomputing kernels also at H = 512 (nothing V-wide in HBM).  "chunked":
 # the library-GEMM fallback for every width.  (Tests and bench.py A/B the routes through this.)
 ROUTE = None
+MERGE_PROJ_BACKWARD = True      # False: the pre-projections keep their own autograd nodes (A/B runs)
 
 
-def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, sizes=None):
+def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, blank=0, bf16=False, sizes=None, pre=None):
     """costs (B,) fp32 of the transducer loss of logits = tanh(eproj[:, :, None] + pproj[:, None]) @ w_out.T + b_out.
 
     H a multiple of 512: three streamed tcgen05 products around the kept 16-bit softmax numerators (WideJointRNNT);
@@ -555,8 +595,13 @@ def fused_joint_rnnt(eproj, pproj, w_out, b_out, labels, act_lens, label_lens, b
         fn = WideJointRNNT
     else:
         fn = FusedJointRNNT if supported_width(H) else ChunkedJointRNNT
-    return fn.apply(eproj, pproj, w_out, b_out, _i32_cuda(labels, dev, "labels"),
-                    _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"), blank, bf16, sizes)
+    args = (_i32_cuda(labels, dev, "labels"), _i32_cuda(act_lens, dev, "act_lens"), _i32_cuda(label_lens, dev, "label_lens"),
+            blank, bf16, sizes)
+    if fn is WideJointRNNT and pre is not None and MERGE_PROJ_BACKWARD:
+        # pre = (enc, w_enc, b_enc, dec, w_dec): this node owns the pre-projections' backward (see WideJointRNNT.forward);
+        # eproj / pproj go in detached, so their own autograd nodes are never run
+        return fn.apply(eproj.detach(), pproj.detach(), w_out, b_out, *args, *pre)
+    return fn.apply(eproj, pproj, w_out, b_out, *args)
 
 
 class DenseRNNT(torch.autograd.Function):

@@ -69,13 +69,26 @@ class _Proj(torch.autograd.Function):
         return dx, dw, db
 
 
+def _on_kernels(x, w, b=None):
+    return (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and w.stride(1) == 1 and
+            w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0 and w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0 and
+            (b is None or b.dtype == torch.float32) and x.numel() > 0)
+
+
 def _proj(x, w, b=None):
     """The projection on our kernels when the operands allow it (float32 CUDA, 16-byte aligned rows), else torch's."""
-    if (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and w.stride(1) == 1 and
-            w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0 and w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0 and
-            (b is None or b.dtype == torch.float32) and x.numel() > 0):
+    if _on_kernels(x, w, b):
         return _Proj.apply(x, w, b)
     return torch.nn.functional.linear(x, w, b)
+
+
+def _handle(enc, w_enc, b_enc, dec, w_dec, w_out, b_out):
+    """The lazy logits handle of a batched call.  When both pre-projections run on our kernels the handle also carries
+    their inputs, so that the loss node can own their backward (functional.WideJointRNNT)."""
+    h = LazyJointLogits(_proj(enc, w_enc, b_enc), _proj(dec, w_dec), w_out, b_out)
+    if _on_kernels(enc, w_enc, b_enc) and _on_kernels(dec, w_dec):
+        h.pre = (enc, w_enc, b_enc, dec, w_dec)
+    return h
 
 
 def _fusable(x, width):
@@ -97,9 +110,8 @@ class JointNet(torch.nn.Module):
                 _fusable(enc_state, self.forward_layer.out_features)):
             de = enc_state.size(-1)
             w = self.forward_layer.weight
-            eproj = _proj(enc_state, w[:, :de], self.forward_layer.bias)
-            pproj = _proj(dec_state, w[:, de:])
-            return LazyJointLogits(eproj, pproj, self.project_layer.weight, self.project_layer.bias)
+            return _handle(enc_state, w[:, :de], self.forward_layer.bias, dec_state, w[:, de:],
+                           self.project_layer.weight, self.project_layer.bias)
         if enc_state.dim() == 3 and dec_state.dim() == 3:  # tt/model.py:21-29
             t, u = enc_state.size(1), dec_state.size(1)
             enc_state = enc_state.unsqueeze(2).expand(-1, -1, u, -1)
@@ -136,8 +148,7 @@ class JointNetwork(torch.nn.Module):
         if (self.fused and self.joint_activation_type == "tanh" and h_enc.dim() == 4 and h_dec.dim() == 4 and
                 h_enc.size(2) == 1 and h_dec.size(1) == 1 and h_enc.size(0) == h_dec.size(0) and
                 _fusable(h_enc, self.lin_enc.out_features)):
-            eproj = _proj(h_enc.squeeze(2), self.lin_enc.weight, self.lin_enc.bias)
-            pproj = _proj(h_dec.squeeze(1), self.lin_dec.weight)
-            return LazyJointLogits(eproj, pproj, self.lin_out.weight, self.lin_out.bias)
+            return _handle(h_enc.squeeze(2), self.lin_enc.weight, self.lin_enc.bias, h_dec.squeeze(1), self.lin_dec.weight,
+                           self.lin_out.weight, self.lin_out.bias)
         z = self.joint_activation(self.lin_enc(h_enc) + self.lin_dec(h_dec))  # joint_network.py:48-49
         return self.lin_out(z)

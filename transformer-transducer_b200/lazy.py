@@ -32,6 +32,7 @@ class LazyJointLogits(torch.Tensor):
         r = torch.Tensor._make_wrapper_subclass(cls, (B, T, U1, V), dtype=dtype or eproj.dtype, device=eproj.device,
                                                 requires_grad=False)
         r.eproj, r.pproj, r.w_out, r.b_out = eproj, pproj, w_out, b_out
+        r.pre = None        # (enc, w_enc, b_enc, dec, w_dec) when the pre-projections ran on our kernels (joint._handle)
         return r
 
     def __repr__(self):
@@ -79,7 +80,9 @@ class LazyJointLogits(torch.Tensor):
             src = args[0]
             dev = kwargs.get("device", None)
             if dev is None or torch.device(dev) == src.device:
-                return LazyJointLogits(*src.parts, dtype=kwargs.get("dtype", None) or src.dtype)
+                out = LazyJointLogits(*src.parts, dtype=kwargs.get("dtype", None) or src.dtype)
+                out.pre = src.pre
+                return out
 
         def unwrap(x):
             return x.materialize().detach() if isinstance(x, LazyJointLogits) else x

@@ -83,7 +83,8 @@ def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", fas
     if isinstance(acts, LazyJointLogits):
         ep, pp, w, b = acts.parts
         bf16 = ep.dtype == torch.bfloat16
-        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16, sizes=sizes)
+        costs = F.fused_joint_rnnt(ep, pp, w, b, labels, act_lens, label_lens, blank, bf16, sizes=sizes,
+                                   pre=getattr(acts, "pre", None))
     else:
         costs = F.dense_rnnt(acts, labels, act_lens, label_lens, blank, sizes=sizes)
     if reduction in ("sum", "mean"):
