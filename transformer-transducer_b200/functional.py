@@ -325,14 +325,21 @@ class WideJointRNNT(torch.autograd.Function):
             w16 = torch.empty(Vpad * H, dtype=torch.int16, device=dev)
             bias2 = torch.empty(Vpad, dtype=torch.float32, device=dev)
             w16t = torch.empty(H * Vpad, dtype=torch.int16, device=dev) if need_act else None
-            _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
-                  plan.idx, st)
             a16 = torch.empty(plan.rows * H, dtype=torch.int16, device=dev)
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
+            main = torch.cuda.current_stream(dev)
+            side = _hi_stream(dev) if WideJointRNNT.OVERLAP else None
+            if side is not None:               # the weight cast and the activation kernel do not depend on each other
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                _call("ttx_cast_weight", dev, _p(w), _p(b), V, H, int(bf16), _p(scal), _p(w16), _p(bias2), _p(w16t),
+                      plan.idx, _stream(dev))
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
                   _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
                   None, plan.idx, st)          # (no transposed copy: the weight gradient reads its operands MN-major)
+            if side is not None:
+                main.wait_stream(side)
             lse, lpb, lpl, pfac, mref = (plan.rowf() for _ in range(5))
             ew = plan.rowf(H) if need_act else None
             chunks, store_rows, pstore = _wide_pstore(plan, Vpad, dev)
