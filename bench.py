@@ -201,10 +201,21 @@ def run_reference(args, w):
         "impl": "reference", "metric": "joint+RNN-T loss fwd+bwd utterances/s", "value": val, "unit": "utt/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"]},
+        "config": workload_config(w, int(os.environ.get("WORLD_SIZE", "1")), args),      # the same dict as the GPU arm's
         "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def workload_config(w, world, args):
+    """The `config` object of a bench line: the workload only (both arms print the same dict for the same arguments)."""
+    B = w["B"] // world if args.scaling == "strong" else w["B"]
+    _, _, _, act_lens, label_lens = synth(dict(w, B=B), 1234)                # lengths of rank 0's shard
+    M = int((act_lens.long() * (label_lens.long() + 1)).sum())
+    return {"workload": w["desc"] + (" (global batch, sharded)" if args.scaling == "strong" else ""),
+            "global_batch": world * B, "parallelism": "dp%d" % world, "logits": args.logits, "route": args.route,
+            "l2": "per-step working set (A16 %.2f GB + dA %.2f GB) exceeds the 126 MB L2; no explicit flush" %
+                  (M * w["H"] * 2 / 1e9, M * w["H"] * 4 / 1e9)}
 
 
 def main():
@@ -249,6 +260,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    w0 = w
     if args.scaling == "strong":
         if w["B"] % world:
             raise SystemExit("--scaling strong: the workload's batch %d is not divisible by %d GPUs" % (w["B"], world))
@@ -391,10 +403,7 @@ def main():
         "dtype": ("bf16 tensor-core operands" if w.get("bf16") else "f16 tensor-core operands") +
                  ", f32 accumulate/softmax, 48-bit (float + float) lattice carrier (%s variant)" % ("bf16-input" if w.get("bf16") else "fp32"),
         "data": "synthetic",
-        "config": {"workload": w["desc"], "global_batch": world * w["B"], "parallelism": "dp%d" % world,
-                   "logits": args.logits, "route": args.route,
-                   "l2": "per-step working set (A16 %.2f GB + dA %.2f GB) exceeds the 126 MB L2; no explicit flush" %
-                         (M * w["H"] * 2 / 1e9, M * w["H"] * 4 / 1e9)},
+        "config": workload_config(w0, world, args),
         "e2e": {"value": world * w["B"] * args.steps / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
