@@ -271,8 +271,10 @@ int launch_transpose16(const void* in, void* out, int R, int C, const int* meta_
 // The recursion needs more than float32: alpha/beta reach |ll| ~ (T+U) * log V (thousands), where float32 has only
 // ~5e-4 of absolute resolution and exp(alpha + beta - ll) would lose 3 digits (the float32 reference does).  It is
 // carried as an unevaluated sum of two floats (hi + lo, ~48 bits -- 2e-11 at 6000; a compensated float32 carrier) and
-// stored as float64.  (Measured: the same time per diagonal as a float64 carrier, 0.25 us at configs[1] -- the step is
-// bound by the staging / shuffle / store sequence around the arithmetic, not by the arithmetic's latency.)  The
+// stored as float64.  (Measured: the same time per diagonal as a float64 carrier, 0.25 us = ~470 cycles at configs[1]; ncu
+// shows ~210 instructions per step spread evenly over a single warp -- the step is issue-bound, not latency-bound.  Staging
+// the operand diagonals in groups of 16 instead of one per step did not change it either: 0.153 ms, and 0.62 vs 0.54 ms at
+// configs[3].)  The
 // increment log(1 + exp(-d)) lies in (0, ln 2] and is evaluated in float32 with ex2 / lg2 (absolute error ~1e-7 per
 // cell, a random walk of ~3e-6 over a 1200-step lattice).  "log 0" is the finite sentinel kLatNeg.
 constexpr float kLatNeg = -1.0e30f;
@@ -333,16 +335,14 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // grid = 2B: block b computes alpha of utterance b, block B + b its beta (on the mirrored lattice, stored mirrored:
 // beta(t, u) is element (T-1-t + U1-1-u) * P + U1-1-u of the utterance's run).  W warps x 32 lanes x K columns.
-// The operand diagonals arrive in GROUPS of G: one cp.async group per G diagonals, two groups in shared memory, so the
-// wait / barrier / copy-issue sequence is paid once per G steps of the dependent chain instead of every step.
-template <int K, int G, int W>
+template <int K, int PD, int W>
 __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
         const float* __restrict__ ws, size_t lat_elems, const int* __restrict__ act_lens,
         const int* __restrict__ label_lens, const int* __restrict__ meta, int B, double* __restrict__ alpha_d,
         double* __restrict__ beta_d, float* __restrict__ costs, double* __restrict__ ll_beta) {
-    static_assert(G >= 1 && (K == 1 || K == 2), "one or two columns per lane");
+    static_assert(PD >= 2 && (K == 1 || K == 2), "ring of at least two diagonals, one or two columns per lane");
     constexpr int PMAX = 32 * K * W;                       // floats per staged diagonal
-    __shared__ __align__(16) float stage[2][G][2][PMAX];
+    __shared__ __align__(16) float stage[PD][2][PMAX];
     __shared__ float2 bnd[2][W + 1];
     if (meta[1] != 0) return;
     const bool is_beta = blockIdx.x >= (unsigned)B;
@@ -356,58 +356,51 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
     const int u0 = threadIdx.x * K;                        // first column of this lane
     const int nd = T + U1 - 1;
     const int nchunk = P >> 2;                             // 16-byte chunks per diagonal
-    auto stage_group = [&](int g) {                        // operands of diagonals g * G .. g * G + G - 1 into buffer g & 1
-        for (int d = 0; d < G; ++d) {
-            const int s = g * G + d;
-            if (s < nd) {
-                const float* gb = inB + (size_t)s * P;
-                const float* gl = inL + (size_t)s * P;
-                for (int c = threadIdx.x; c < nchunk; c += 32 * W) {
-                    cp_async16(smem_u32(&stage[g & 1][d][0][4 * c]), gb + 4 * c);
-                    cp_async16(smem_u32(&stage[g & 1][d][1][4 * c]), gl + 4 * c);
-                }
+    auto stage_step = [&](int s, int slot) {               // operands of diagonal s into ring slot `slot`
+        if (s < nd) {
+            const float* gb = inB + (size_t)s * P;
+            const float* gl = inL + (size_t)s * P;
+            for (int c = threadIdx.x; c < nchunk; c += 32 * W) {
+                cp_async16(smem_u32(&stage[slot][0][4 * c]), gb + 4 * c);
+                cp_async16(smem_u32(&stage[slot][1][4 * c]), gl + 4 * c);
             }
         }
         cp_async_commit();
     };
-    stage_group(0);
-    stage_group(1);
+#pragma unroll
+    for (int s = 0; s < PD - 1; ++s) stage_step(s, s);
     const df32 neg{kLatNeg, 0.f};
     df32 v[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) v[j] = neg;
     double* out = (is_beta ? beta_d : alpha_d) + base + u0;
-    const int ngroups = (nd + G - 1) / G;
-    for (int g = 0; g < ngroups; ++g) {
-        cp_async_wait<1>();                                 // group g has landed (own copies; g + 1 may still be in flight) ...
-        if (W > 1) __syncthreads();                         // ... everybody's
-        else __syncwarp();
-        const int gb_ = g & 1;
+    for (int s0 = 0; s0 < nd; s0 += PD) {
 #pragma unroll
-        for (int d = 0; d < G; ++d) {
-            const int s = g * G + d;                        // diagonal of this step
+        for (int i = 0; i < PD; ++i) {
+            const int s = s0 + i;                          // diagonal of this step; ring slot i
             if (s >= nd) break;
+            if (W > 1 && lane == 31) bnd[i & 1][warp + 1] = make_float2(v[K - 1].hi, v[K - 1].lo);   // boundary column, previous step
+            cp_async_wait<PD - 2>();                        // this step's diagonal has landed (own copies) ...
+            if (W > 1) __syncthreads();                     // ... everybody's, and the slot refilled below has been read
+            else __syncwarp();
+            stage_step(s + PD - 1, (i + PD - 1) % PD);
             float sb[K], sl[K];
             if (K == 2) {
-                const float2 b2 = *reinterpret_cast<const float2*>(&stage[gb_][d][0][u0]);
-                const float2 l2 = *reinterpret_cast<const float2*>(&stage[gb_][d][1][u0]);
+                const float2 b2 = *reinterpret_cast<const float2*>(&stage[i][0][u0]);
+                const float2 l2 = *reinterpret_cast<const float2*>(&stage[i][1][u0]);
                 sb[0] = b2.x; sb[K - 1] = b2.y; sl[0] = l2.x; sl[K - 1] = l2.y;
             } else {
-                sb[0] = stage[gb_][d][0][u0];
-                sl[0] = stage[gb_][d][1][u0];
+                sb[0] = stage[i][0][u0];
+                sl[0] = stage[i][1][u0];
             }
             // left neighbour column's value of the previous step
             df32 left;
             left.hi = __shfl_up_sync(0xffffffffu, v[K - 1].hi, 1);
             left.lo = __shfl_up_sync(0xffffffffu, v[K - 1].lo, 1);
             if (lane == 0) left = neg;
-            if (W > 1) {                                    // across warps: through shared memory, one barrier per diagonal
-                if (lane == 31) bnd[d & 1][warp + 1] = make_float2(v[K - 1].hi, v[K - 1].lo);
-                __syncthreads();
-                if (lane == 0 && warp > 0) {
-                    const float2 bv = bnd[d & 1][warp];
-                    left = {bv.x, bv.y};
-                }
+            if (W > 1 && lane == 0 && warp > 0) {
+                const float2 bv = bnd[i & 1][warp];
+                left = {bv.x, bv.y};
             }
             df32 nv[K];
 #pragma unroll
@@ -425,9 +418,6 @@ __global__ void __launch_bounds__(32 * W) lattice_wave_kernel(
 #pragma unroll
             for (int j = 0; j < K; ++j) v[j] = nv[j];
         }
-        if (W > 1) __syncthreads();                         // every lane has read buffer g & 1: refill it with group g + 2
-        else __syncwarp();
-        stage_group(g + 2);
     }
     cp_async_wait<0>();
     // both lattices end in their last cell (T-1, U1-1), alone on diagonal nd - 1
@@ -960,15 +950,14 @@ int launch_lattice(const float* lpb, const float* lpl, const int* act_lens, cons
         return 1;
     }
     lattice_skew_kernel<<<n_tiles_ub, kTile, 0, s>>>(lpb, lpl, act_lens, label_lens, meta, B, lat_elems, lat_ws);
-#define TTX_LAT(K, G, W) lattice_launch<K, G, W>(B, s, lat_ws, lat_elems, act_lens, label_lens, meta, alpha, beta, costs, ll_beta)
+#define TTX_LAT(K, PD, W) lattice_launch<K, PD, W>(B, s, lat_ws, lat_elems, act_lens, label_lens, meta, alpha, beta, costs, ll_beta)
     // (one column per lane with twice the warps measured the same: 0.140 vs 0.136 ms at configs[1], 0.45 vs 0.47 at configs[3])
-    // (K columns per lane, G diagonals per staged group, W warps); 2 * G * 2 * 64 * W * 4 bytes of shared memory
-    if (U1 <= 32) TTX_LAT(1, 16, 1);
-    else if (U1 <= 64) TTX_LAT(2, 16, 1);
-    else if (U1 <= 128) TTX_LAT(2, 16, 2);
+    if (U1 <= 32) TTX_LAT(1, 8, 1);
+    else if (U1 <= 64) TTX_LAT(2, 8, 1);
+    else if (U1 <= 128) TTX_LAT(2, 8, 2);
     else if (U1 <= 256) TTX_LAT(2, 8, 4);
-    else if (U1 <= 512) TTX_LAT(2, 4, 8);
-    else TTX_LAT(2, 2, 16);
+    else if (U1 <= 512) TTX_LAT(2, 8, 8);
+    else TTX_LAT(2, 4, 16);
 #undef TTX_LAT
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
