@@ -233,6 +233,12 @@ int ttx_band_attn_bwd(const float* w_heads, const float* r_emb, const float* r_w
                       float* dq_content, float* d_w_heads, float* d_r_emb, float* d_r_w_bias, float* d_r_bias, int device,
                       void* stream);
 
+/* The device side of warprnnt_pytorch's argument checks (certify_inputs) in one launch: out (7 x int64, device) = max T,
+ * max U, min T, min U over the batch, the batch's 128-row lattice tiles, the number of labels outside [0, V) inside their
+ * utterance's label_lens, the elements of the diagonal-major lattice arrays.  labels (B, label_stride) int32. */
+int ttx_check_inputs(const int32_t* labels, int label_stride, const int32_t* act_lens, const int32_t* label_lens, int B, int V,
+                     int64_t* out, int device, void* stream);
+
 /* Dense-logits entry: acts (B,T,U1,V) fp32 contiguous. */
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,
                   const int32_t* meta, int B, int T, int U1, int V, int label_stride, int blank,

@@ -63,6 +63,7 @@ _PROTOS = {
                           c_p],
     "ttx_band_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_p, c_p,
                           c_p, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_check_inputs": [c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_dense_grad": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],

@@ -74,6 +74,8 @@ int launch_band_attn_fwd(const float*, const float*, const float*, const float*,
 int launch_band_attn_bwd(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int, int,
                          float, float*, float*, float*, float*, float*, float*, cudaStream_t);
 
+int launch_check_inputs(const int*, int, const int*, const int*, int, int, long long*, cudaStream_t);
+
 static int enter(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -442,6 +444,14 @@ int ttx_band_attn_bwd(const float* w_heads, const float* r_emb, const float* r_w
     TTX_ENTER(device);
     return launch_band_attn_bwd(w_heads, r_emb, r_w_bias, prob, d_out, T, B, n_head, d_head, max_len, left, right, scale, ds,
                                 dq_content, d_w_heads, d_r_emb, d_r_w_bias, d_r_bias, (cudaStream_t)stream);
+}
+
+int ttx_check_inputs(const int32_t* labels, int label_stride, const int32_t* act_lens, const int32_t* label_lens, int B, int V,
+                     int64_t* out, int device, void* stream) {
+    TTX_REQUIRE(act_lens && label_lens && out && (labels || label_stride == 0), "ttx_check_inputs: null pointer");
+    TTX_REQUIRE(B > 0 && V > 0 && label_stride >= 0, "ttx_check_inputs: bad shape B=%d V=%d", B, V);
+    TTX_ENTER(device);
+    return launch_check_inputs(labels, label_stride, act_lens, label_lens, B, V, (long long*)out, (cudaStream_t)stream);
 }
 
 int ttx_dense_lse(const float* acts, const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens,

@@ -8,6 +8,8 @@
 //                 vocabulary tiles with one 64-bit atomicMax (value bits, then the LOWEST index on ties, like torch.argmax)
 //   pick_kernel   first frame whose argmax is not the blank + that label -> 2 ints the host reads with ONE synchronisation
 // A register-tiled SGEMM: block = 64 vocabulary rows x 64 frames, 256 threads x (4 frames x 4 rows), K chunks of 32.
+#include <limits.h>
+
 #include "ttx_common.cuh"
 
 namespace ttx {
@@ -153,6 +155,59 @@ int launch_spec_mask(float* x, int B, int T, int F, long long ld_b, long long ld
         m.width[i] = masks_host[3 * i + 2];
     }
     spec_mask_kernel<<<dim3(T, B), 128, 0, s>>>(x, B, T, F, ld_b, ld_t, m);
+    TTX_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ttx
+
+// ------------------------------------------------------------------------------------------- argument checks
+// What warprnnt_pytorch's certify_inputs needs from the device (upstream reads max(act_lens), max(label_lens) on the
+// host), plus the batch's real lattice size, in ONE launch and one 56-byte read instead of a dozen small reductions:
+// out[0..6] = max T, max U, min T, min U, 128-row lattice tiles, labels outside [0, V) inside their utterance (count),
+// elements of the diagonal-major lattice arrays.
+namespace ttx {
+
+__global__ void check_inputs_kernel(const int* __restrict__ labels, int label_stride, const int* __restrict__ act_lens,
+                                    const int* __restrict__ label_lens, int B, int V, long long* __restrict__ out) {
+    __shared__ long long red[7][8];
+    long long v[7] = {LLONG_MIN, LLONG_MIN, LLONG_MAX, LLONG_MAX, 0, 0, 0};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const long long t = act_lens[b], u = label_lens[b];
+        v[0] = max(v[0], t); v[1] = max(v[1], u); v[2] = min(v[2], t); v[3] = min(v[3], u);
+        v[4] += (t * (u + 1) + 127) / 128;
+        v[6] += (t + u) * ((u + 4) / 4 * 4);                  // (T + U1 - 1) * pitch(U1)
+    }
+    if (labels != nullptr && label_stride > 0)
+        for (long long i = threadIdx.x; i < (long long)B * label_stride; i += blockDim.x) {
+            const int b = (int)(i / label_stride), u = (int)(i - (long long)b * label_stride);
+            if (u < label_lens[b]) {
+                const int l = labels[i];
+                v[5] += (l < 0 || l >= V) ? 1 : 0;
+            }
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        long long x = v[k];
+        for (int o = 16; o; o >>= 1) {
+            const long long y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = k < 2 ? max(x, y) : k < 4 ? min(x, y) : x + y;
+        }
+        if (lane == 0) red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x;
+        long long x = red[k][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) x = k < 2 ? max(x, red[k][w]) : k < 4 ? min(x, red[k][w]) : x + red[k][w];
+        out[k] = x;
+    }
+}
+
+int launch_check_inputs(const int* labels, int label_stride, const int* act_lens, const int* label_lens, int B, int V,
+                        long long* out, cudaStream_t s) {
+    check_inputs_kernel<<<1, 256, 0, s>>>(labels, label_stride, act_lens, label_lens, B, V, out);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;
 }

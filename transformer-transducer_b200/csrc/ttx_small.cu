@@ -1040,7 +1040,7 @@ __global__ void scale_rows_kernel(const uint16_t* __restrict__ a16, const float4
 //   db[blank] += gmax * sum_m w p_b,              db[label_m] += gmax * w p_l               (dense part they left out)
 // are added here.  grid = (U1, B, t-chunks) like reduce_pred_kernel: the label depends on (b, u) only.
 template <bool BF16>
-__global__ void dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4* __restrict__ rowmeta,
+__global__ void __launch_bounds__(128, 5) dw_sparse_kernel(const uint16_t* __restrict__ a16, const float4* __restrict__ rowmeta,
                                  const int* __restrict__ row_label, const float* __restrict__ lpb,
                                  const float* __restrict__ lpl, const float* __restrict__ scal,
                                  const int* __restrict__ act_lens, const int* __restrict__ label_lens,

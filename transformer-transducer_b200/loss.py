@@ -6,10 +6,12 @@ size, ``'mean'``/``'sum'`` return shape ``(1,)``, labels / lengths must be int32
 and ``U + 1 == max(label_lens) + 1`` are checked on the host.  CUDA only -- the CPU path is the oracle,
 which is test infrastructure and not part of the product.
 """
+import ctypes
 import os
 
 import torch
 
+from . import _lib
 from . import functional as F
 from .lazy import LazyJointLogits
 
@@ -45,17 +47,32 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         (tuple(acts.shape),)
     if _checked.get("key") == key:
         return _checked["sizes"]
-    al, ll = act_lens.long(), label_lens.long().to(act_lens.device)
-    tiles = ((al * (ll + 1) + 127) // 128).sum()
-    lat = ((al + ll) * ((ll + 4) // 4 * 4)).sum()            # (T + U1 - 1) * pitch(U1), pitch = U1 rounded up to 4
-    # labels inside the valid region must index the vocabulary (the kernels gather W_out rows / scatter into them)
-    if labels.shape[1] > 0:
-        lab = labels.to(act_lens.device)
-        valid = torch.arange(labels.shape[1], device=lab.device)[None, :] < ll[:, None]
-        bad = (valid & ((lab < 0) | (lab >= acts.shape[3]))).any().long()
+    if acts.is_cuda:
+        # one launch + one 56-byte read (the values upstream's checks need, the batch's real lattice size, the label range)
+        dev = acts.device
+        lab = labels.to(dev).contiguous()
+        al, ll = act_lens.to(dev).contiguous(), label_lens.to(dev).contiguous()
+        out = torch.empty(7, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None  # noqa: E731
+            _lib.check(_lib.get().ttx_check_inputs(p(lab), lab.shape[1], p(al), p(ll), B, acts.shape[3], p(out), idx,
+                                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "ttx_check_inputs")
+        m = out.tolist()                                         # the synchronisation
+        mx = [m[0], m[1], m[2], m[3], m[4], m[5], m[6]]
     else:
-        bad = tiles.new_zeros(())
-    mx = torch.stack((al.max(), ll.max(), al.min(), ll.min(), tiles, bad, lat)).tolist()  # one sync
+        al, ll = act_lens.long(), label_lens.long().to(act_lens.device)
+        tiles = ((al * (ll + 1) + 127) // 128).sum()
+        lat = ((al + ll) * ((ll + 4) // 4 * 4)).sum()            # (T + U1 - 1) * pitch(U1), pitch = U1 rounded up to 4
+        # labels inside the valid region must index the vocabulary (the kernels gather W_out rows / scatter into them)
+        if labels.shape[1] > 0:
+            lab = labels.to(act_lens.device)
+            valid = torch.arange(labels.shape[1], device=lab.device)[None, :] < ll[:, None]
+            bad = (valid & ((lab < 0) | (lab >= acts.shape[3]))).any().long()
+        else:
+            bad = tiles.new_zeros(())
+        mx = torch.stack((al.max(), ll.max(), al.min(), ll.min(), tiles, bad, lat)).tolist()  # one sync
     if mx[0] != acts.shape[1]:
         raise ValueError("Input length mismatch")
     if mx[1] + 1 != acts.shape[2]:
