@@ -31,3 +31,14 @@ for e in ev:
     busy += t - s
     t_end = max(t_end, t)
 print("GPU span us", t_end - first, "busy", busy, "gaps", gaps, "per step gaps", gaps / 3)
+# the largest idle intervals of the timeline (all streams merged), with the kernels on either side
+iv = []
+t_end, prev = 0, None
+for e in ev:
+    s_, t_ = e.time_range.start, e.time_range.end
+    if t_end and s_ > t_end:
+        iv.append((s_ - t_end, prev, e.name))
+    if t_ > t_end:
+        t_end, prev = t_, e.name
+for gap, a, b in sorted(iv, reverse=True)[:24]:
+    print("%8.1f us   %-50s -> %s" % (gap, a[:50], b[:60]))
