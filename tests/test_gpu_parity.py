@@ -242,8 +242,10 @@ def test_fused_forward_grad_rescale_path_with_outlier_logits(H):
     _check(errs)
 
 
-def test_fused_edge_lengths_t1_u0_and_zero_grads_outside():
-    case = _espnet_case(4, 20, 5, 150, 32, 128, [20, 1, 1, 7], [5, 0, 3, 0], seed=3)
+@pytest.mark.parametrize("H,V", [(128, 150), (512, 150), (512, 97), (1024, 300)])     # fused kernels / streamed products
+def test_fused_edge_lengths_t1_u0_and_zero_grads_outside(H, V):
+    """T = 1 and U = 0 utterances, a vocabulary smaller than one 256-column chunk, exact zeros outside the ragged region."""
+    case = _espnet_case(4, 20, 5, V, 32, H, [20, 1, 1, 7], [5, 0, 3, 0], seed=3)
     errs, (e1, p1, _) = _run_pair(*case)
     _check(errs)
     assert e1.grad[1, 1:].abs().max() == 0 and p1.grad[1, 1:].abs().max() == 0      # T_b = 1, U_b = 0
