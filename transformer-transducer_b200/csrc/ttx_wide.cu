@@ -128,12 +128,14 @@ struct EventWait {
 };
 
 // =========================================================================================================== S pass
-// With both operands streamed the S pass wants 64 B/cycle/SM through TMA and gets ~42: 256 KiB per 128 x 256 tile take
-// ~6100 cycles against 4096 of MMA time (ncu: tensor pipe 66 %).  Keeping the pair's A16 tiles stationary in shared memory
+// With both operands streamed the S pass moves 256 KiB per 128 x 256 tile through TMA in ~6100 cycles, against 4096 cycles of
+// MMA time (ncu: tensor pipe 66 %).  Keeping the pair's A16 tiles stationary in shared memory
 // (H <= 512: 128 KiB per CTA, only W16 streams) halves the bytes, but the tile takes the room of either the ring or the P'
 // staging buffers, and both trades lose at configs[1] (streaming both: 2.02 - 2.19 ms): staging buffers + three 16 KiB
 // ring stages 2.23 ms (latency-bound ring); five stages + P' stored straight from registers 3.32 ms with 16-byte stores
-// (half-sector writes), 2.87 ms with 32-byte stores.
+// (half-sector writes), 2.87 ms with 32-byte stores; HALF of the tile stationary (192 KiB per tile through TMA, staging
+// buffers and seven 16 KiB stages kept) 2.42 ms against 2.21 ms -- fewer bytes do not help: the S pass is bound by its
+// epilogue's latency (ncu: issue slots 44 %, MUFU 33 %, tensor pipe 65 % -- ~6100 cycles per 128 x 256 tile and SM).
 template <bool BF16>
 __global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
