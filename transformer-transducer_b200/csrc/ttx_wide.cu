@@ -135,7 +135,9 @@ struct EventWait {
 // ring stages 2.23 ms (latency-bound ring); five stages + P' stored straight from registers 3.32 ms with 16-byte stores
 // (half-sector writes), 2.87 ms with 32-byte stores; HALF of the tile stationary (192 KiB per tile through TMA, staging
 // buffers and seven 16 KiB stages kept) 2.42 ms against 2.21 ms -- fewer bytes do not help: the S pass is bound by its
-// epilogue's latency (ncu: issue slots 44 %, MUFU 33 %, tensor pipe 65 % -- ~6100 cycles per 128 x 256 tile and SM).
+// epilogue's latency (ncu: issue slots 44 %, MUFU 33 %, tensor pipe 65 % -- ~6100 cycles per 128 x 256 tile and SM) --
+// and at full chip by the board's power cap: on 148 SMs the clock sits at ~1515 of 1965 MHz, on 74 SMs the kernel loses only
+// 1.5x (profiles/r2_summary.md), so per-SM cycle tuning no longer moves it.
 template <bool BF16>
 __global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
