@@ -308,6 +308,35 @@ def test_tt_greedy_decode_equals_reference_decode(inner):
     assert all(0 < len(w) < n for w, n in zip(want, lengths))    # labels were emitted, and blanks in between
 
 
+@pytest.mark.parametrize("beam", [5, 3])
+def test_tt_beam_search_equals_reference_beam_search(beam):
+    """tt/model.py:110-179: the reference's beam search (per-frame joint, top-k expansion of every hypothesis, its own
+    child-table bookkeeping) on cuda:0 vs the rebound `Transducer.beam_search`: identical label sequences, directly and
+    through `recognize_beam_search()` (tt/model.py:181-198, beam width 5)."""
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    V = 173
+    cfg = _tt_config(512, V)
+    _seed(33)
+    model = tt_model.Transducer(cfg.model).to(DEV).eval()
+    _boost_blank(model.joint.project_layer, 0.35)
+    inputs = torch.randn(2, 70, 512, device=DEV)
+    lengths = [70, 38]
+    with torch.no_grad():
+        enc = model.encoder(inputs, None)
+        want = [model.beam_search(enc[b], lengths[b], beam_width=beam) for b in range(2)]
+        want_rec = model.recognize_beam_search(inputs, lengths) if beam == 5 else None
+        try:
+            done = ttb.install(patch_espnet=False)
+            assert "tt.model.Transducer.beam_search" in done
+            got = [model.beam_search(enc[b], lengths[b], beam_width=beam) for b in range(2)]
+            got_rec = model.recognize_beam_search(inputs, lengths) if beam == 5 else None
+        finally:
+            ttb.uninstall()
+    assert got == want and got_rec == want_rec
+    assert any(len(w) > 1 for w in want), want
+
+
 def test_espnet_greedy_decode_equals_reference_decode():
     """tt_espnet/model.py:83-121: same check for TransformerTransducer.decode / recognize."""
     V = 333

@@ -1,0 +1,63 @@
+"""Host-side bookkeeping of decode.beam_search against the reference's own beam search (tt/model.py:110-179) on the CPU.
+
+The frame scanner (the CUDA part) is replaced by a plain-torch stand-in with the same interface, so what is compared is
+the search logic: leader selection, skipped blank frames, top-k expansion with the blank removed, the reference's
+child table (appended to at every label frame, filled column-wise the first time) and the survivor selection.  The GPU
+run of the same comparison, with the real scanner, is tests/test_gpu_callers.py.
+"""
+import contextlib
+import os
+
+import pytest
+import torch
+import yaml
+
+import transformer_transducer_b200  # noqa: F401  (registers the package under its importable name)
+from oracle import ref_import
+from transformer_transducer_b200 import decode as D
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="baseline/_ref (staged reference) is missing")
+
+
+class _TorchScanner:
+    def __init__(self, joint, enc_state, length):
+        self.joint, self.enc, self.length = joint, enc_state, length
+
+    def decoder_half(self, dec_out):
+        return dec_out.reshape(-1)
+
+    def posterior(self, t, pvec):
+        return torch.softmax(self.joint(self.enc[t].view(-1), pvec), dim=0)
+
+    def next_label(self, t, pvec, blank):
+        while t < self.length:
+            label = int(self.posterior(t, pvec).argmax())
+            if label != blank:
+                return t, label
+            t += 1
+        return self.length, blank
+
+
+@pytest.mark.parametrize("seed,boost", [(2, 0.5), (1, 0.9), (3, 1.3), (4, 0.0)])
+def test_beam_search_bookkeeping_equals_reference(monkeypatch, seed, boost):
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    from tt.utils import AttrDict
+    cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "aishell.yaml"))))
+    cfg.model.enc.n_layer = 1
+    cfg.model.dec.n_layer = 1
+    cfg.model.vocab_size = 97
+    cfg.model.joint.inner_size = 128
+    cfg.model.dropout = 0.0
+    torch.manual_seed(seed)
+    model = tt_model.Transducer(cfg.model).eval()
+    monkeypatch.setattr(D, "_FrameScanner", _TorchScanner)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    with torch.no_grad():
+        model.joint.project_layer.bias[0] += boost
+        enc = model.encoder(torch.randn(1, 40, 512), None)[0]
+        step = lambda toks: model.decoder(torch.tensor([toks]))[:, -1, :]  # noqa: E731
+        for width in (5, 3, 2):
+            want = model.beam_search(enc, 40, beam_width=width)
+            got = D.beam_search(model.joint, enc, 40, step, beam_width=width)
+            assert got == want

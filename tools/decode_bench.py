@@ -1,4 +1,4 @@
-"""Greedy-search timing on cuda:0: the reference's per-frame loop (tt/model.py:70-90) vs the rebound decode
+"""Greedy- and beam-search timing on cuda:0: the reference's per-frame loops (tt/model.py:70-90, :110-179) vs the rebound ones
 (transformer_transducer_b200/decode.py) on the same model and encoder states.  Needs baseline/_ref (staged reference).
 Prints one JSON line; run under gpurun."""
 import json
@@ -25,21 +25,24 @@ inputs = torch.randn(B, T, 512, device="cuda")
 lengths = [T] * B
 
 
-def run():
+def run(beam=False):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.no_grad():
-        out = model.recognize(inputs, lengths)
+        out = model.recognize_beam_search(inputs, lengths) if beam else model.recognize(inputs, lengths)
     torch.cuda.synchronize()
     return time.perf_counter() - t0, out
 
 
-run()
-ref_s, want = min((run() for _ in range(3)), key=lambda r: r[0])
-ttb.install(patch_espnet=False)
-run()
-our_s, got = min((run() for _ in range(3)), key=lambda r: r[0])
-ttb.uninstall()
-print(json.dumps({"workload": "greedy recognize B=%d T=%d V=%d joint 1024 (1-layer encoder / decoder)" % (B, T, V),
-                  "labels_emitted": [len(x) for x in want], "identical": got == want,
-                  "reference_ms_per_utt": 1e3 * ref_s / B, "ours_ms_per_utt": 1e3 * our_s / B, "speedup": ref_s / our_s}))
+for beam in (False, True):                            # tt/model.py:92-108 ; :181-198 (beam width 5)
+    run(beam)
+    ref_s, want = min((run(beam) for _ in range(3)), key=lambda r: r[0])
+    ttb.install(patch_espnet=False)
+    run(beam)
+    our_s, got = min((run(beam) for _ in range(3)), key=lambda r: r[0])
+    ttb.uninstall()
+    print(json.dumps({"workload": "%s B=%d T=%d V=%d joint 1024 (1-layer encoder / decoder)"
+                      % ("recognize_beam_search (width 5)" if beam else "greedy recognize", B, T, V),
+                      "labels_emitted": [len(x) for x in want], "identical": got == want,
+                      "reference_ms_per_utt": 1e3 * ref_s / B, "ours_ms_per_utt": 1e3 * our_s / B,
+                      "speedup": ref_s / our_s}))

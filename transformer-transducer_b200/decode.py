@@ -1,7 +1,8 @@
 """Greedy transducer search with the decode-time joint on the GPU (csrc/ttx_decode.cu).
 
-Drop-in for the reference's per-utterance greedy loops
+Drop-in for the reference's per-utterance search loops
   tt.model.Transducer.decode                      /root/reference/tt/model.py:70-90
+  tt.model.Transducer.beam_search                 /root/reference/tt/model.py:110-179
   tt_espnet.model.TransformerTransducer.decode    /root/reference/tt_espnet/model.py:83-106
 (same arguments, same return value: the label sequence without the start symbol).  The reference evaluates
 ``joint(enc_state[t].view(-1), dec_state.view(-1)) -> softmax -> argmax -> .item()`` once per frame; the decoder state
@@ -51,46 +52,131 @@ class _JointParts:
         self.w_out, self.b_out = f32(out.weight), f32(out.bias)
 
 
+class _FrameScanner:
+    """One utterance's decode-time joint: encoder half of the first layer for all frames (once), decoder half per label
+    history, and the launch group that scores a run of frames against one decoder state."""
+
+    def __init__(self, joint, enc_state, length):
+        if not enc_state.is_cuda:
+            raise RuntimeError("the decode-time joint kernel needs CUDA tensors (there is no CPU fallback)")
+        self.lib = _lib.get()
+        self.dev = dev = enc_state.device
+        self.length = length
+        self.parts = parts = _JointParts(joint, enc_state.size(-1))
+        self.H, self.V = parts.w_out.shape[1], parts.w_out.shape[0]
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
+        self.scratch = torch.empty(SCAN_FRAMES, dtype=torch.int64, device=dev)
+        self.out = torch.empty(2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
+
+    def decoder_half(self, dec_out):
+        return torch.nn.functional.linear(dec_out.reshape(-1).float(), self.parts.w_dec)
+
+    def scan(self, t, n, pvec, blank):
+        """Frames t .. t + n - 1 against pvec: (offset of the first frame whose argmax is not blank -- n if none --, its
+        label).  The one host read per emitted label / run of blank frames."""
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(self.lib.ttx_decode_scan(_p(self.eproj[t]), self.H, _p(pvec), _p(self.parts.w_out), _p(self.parts.b_out),
+                                            n, self.H, self.V, int(blank), _p(self.scratch), _p(self.out), self.idx, st),
+                   "ttx_decode_scan")
+        first, label = self.out[:2].tolist()
+        return first, label
+
+    def next_label(self, t, pvec, blank):
+        """First frame >= t whose prediction against pvec is a label, with doubling look-ahead: (frame, label), or
+        (length, blank) when only blanks are left."""
+        look = SCAN_FIRST
+        while t < self.length:
+            n = min(look, self.length - t)
+            first, label = self.scan(t, n, pvec, blank)
+            if first < n:
+                return t + first, int(label)
+            t += n
+            look = min(SCAN_FRAMES, 2 * look)           # a run of blanks: look further ahead next time
+        return self.length, int(blank)
+
+    def posterior(self, t, pvec):
+        """softmax over the vocabulary at frame t (fp32), for the searches that rank more than the best label."""
+        hidden = torch.tanh(self.eproj[t] + pvec)
+        return torch.softmax(torch.nn.functional.linear(hidden, self.parts.w_out, self.parts.b_out), dim=0)
+
+
 @torch.no_grad()
 def greedy_search(joint, enc_state, length, step_decoder, start_token=0, blank=0):
     """enc_state (T, D_enc) CUDA tensor of one utterance, length = frames to decode, step_decoder(token_list) -> the
     decoder's last output (D_dec) for that label history.  Returns the emitted labels (start symbol excluded)."""
     if not enc_state.is_cuda:
         raise RuntimeError("greedy_search needs CUDA tensors (there is no CPU fallback)")
-    lib = _lib.get()
-    dev = enc_state.device
     length = int(length)
-    parts = _JointParts(joint, enc_state.size(-1))
-    H, V = parts.w_out.shape[1], parts.w_out.shape[0]
     tokens = [int(start_token)]
     if length <= 0:
         return tokens[1:]
-    with torch.cuda.device(dev):
-        idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
-        scratch = torch.empty(SCAN_FRAMES, dtype=torch.int64, device=dev)
-        out = torch.empty(2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
-        pvec = None
+    with torch.cuda.device(enc_state.device):
+        scanner = _FrameScanner(joint, enc_state, length)
         t = 0
-        look = SCAN_FIRST
         while t < length:
-            if pvec is None:
-                dec = step_decoder(tokens).reshape(-1).float()
-                pvec = torch.nn.functional.linear(dec, parts.w_dec)
-            n = min(look, length - t)
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(lib.ttx_decode_scan(_p(eproj[t]), H, _p(pvec), _p(parts.w_out), _p(parts.b_out), n, H, V, int(blank),
-                                           _p(scratch), _p(out), idx, st), "ttx_decode_scan")
-            first, label = out[:2].tolist()                     # the one host read per emitted label / 64 blank frames
-            if first >= n:
-                t += n
-                look = min(SCAN_FRAMES, 2 * look)               # a run of blanks: look further ahead next time
-                continue
-            tokens.append(int(label))
-            pvec = None
-            t += first + 1
-            look = SCAN_FIRST
+            pvec = scanner.decoder_half(step_decoder(tokens))
+            t, label = scanner.next_label(t, pvec, blank)
+            if t >= length:
+                break
+            tokens.append(label)
+            t += 1
     return tokens[1:]
+
+
+@torch.no_grad()
+def beam_search(joint, enc_state, length, step_decoder, beam_width=5, start_token=0, blank=0):
+    """The reference's beam search (tt/model.py:110-179), same bookkeeping and therefore the same result: the hypothesis
+    with the best score leads; frames on which the leader predicts the blank change nothing, so they are skipped by the
+    frame scan; on a label frame every hypothesis is expanded by its `beam_width` best non-blank labels (scores = log
+    posteriors, accumulated per parent) and the best `beam_width` children survive.  The child lists are the
+    reference's: one (beam_width x beam_width) table that is appended to at every label frame and never reset, the
+    first label frame filling it column-wise."""
+    import heapq
+    import numpy as np
+    length = int(length)
+    W = int(beam_width)
+    hyps = [[int(start_token)] for _ in range(W)]
+    score = np.zeros((W,), dtype=float)
+    child = [[[int(start_token)] for _ in range(W)] for _ in range(W)]
+    child_score = np.zeros((W, W), dtype=float)
+    if length <= 0:
+        return hyps[0][1:]
+    with torch.cuda.device(enc_state.device):
+        scanner = _FrameScanner(joint, enc_state, length)
+        fresh = True
+        t = 0
+        while t < length:
+            lead = int(score.argmax())
+            t, _ = scanner.next_label(t, scanner.decoder_half(step_decoder(hyps[lead])), blank)
+            if t >= length:
+                break
+            for k in range(W):
+                post = scanner.posterior(t, scanner.decoder_half(step_decoder(hyps[k])))
+                top = torch.topk(post, k=W + 1, dim=0)
+                values, labels = top.values.tolist(), top.indices.tolist()
+                drop = labels.index(blank) if blank in labels else W        # the blank if it made the list, else the last
+                del values[drop], labels[drop]
+                logs = np.log(values)
+                if fresh:
+                    for i, lab in enumerate(labels):
+                        child[i][k].append(lab)
+                    child_score[:, k] = logs
+                else:
+                    for i, lab in enumerate(labels):
+                        child[k][i].append(lab)
+                    child_score[k] = score[k] + logs
+            if fresh:
+                fresh = False
+                for i in range(W):
+                    hyps[i] = list(child[i][0])
+                    score[i] = child_score[i, 0]
+            else:
+                for i, flat in enumerate(heapq.nlargest(W, range(W * W), child_score.take)):
+                    score[i] = child_score[flat // W, flat % W]
+                    hyps[i] = list(child[flat // W][flat % W])
+            t += 1
+    return hyps[int(score.argmax())][1:]
 
 
 def tt_decode(self, enc_state, lengths):
@@ -104,6 +190,19 @@ def tt_decode(self, enc_state, lengths):
         return self.decoder(token)[:, -1, :]                     # tt/model.py:75,88: full history, last output
 
     return greedy_search(self.joint, enc_state, lengths, step, start_token=0, blank=0)
+
+
+def tt_beam_search(self, enc_state, lengths, beam_width=5):
+    """tt.model.Transducer.beam_search (tt/model.py:110-179) with the leader's frame scan on the GPU."""
+    if not enc_state.is_cuda:
+        return type(self)._ttb_reference_beam_search(self, enc_state, lengths, beam_width)
+    dev = enc_state.device
+
+    def step(tokens):
+        token = torch.tensor([tokens], dtype=torch.long, device=dev)
+        return self.decoder(token)[:, -1, :]                     # tt/model.py:135-136,141
+
+    return beam_search(self.joint, enc_state, lengths, step, beam_width=beam_width, start_token=0, blank=0)
 
 
 def espnet_decode(self, enc_state, lengths):

@@ -34,13 +34,13 @@ def uninstall():
         setattr(obj, attr, value)
 
 
-def _patch_decode(cls, fn, name, done):
-    """Greedy search (decode): same signature, the per-frame joint loop replaced by the GPU scan (decode.py); the
+def _patch_decode(cls, fn, name, done, attr="decode"):
+    """Greedy / beam search: same signature, the per-frame joint loop replaced by the GPU scan (decode.py); the
     reference's method stays reachable (CPU tensors fall back to it)."""
-    if cls.decode is fn:
+    if getattr(cls, attr) is fn:
         return
-    cls._ttb_reference_decode = cls.decode
-    _set(cls, "decode", fn)
+    setattr(cls, "_ttb_reference_" + attr, getattr(cls, attr))
+    _set(cls, attr, fn)
     done.append(name)
 
 
@@ -79,6 +79,8 @@ def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True
             done.append("tt.model.JointNet")
             if patch_decode:
                 _patch_decode(m.Transducer, _decode.tt_decode, "tt.model.Transducer.decode", done)
+                _patch_decode(m.Transducer, _decode.tt_beam_search, "tt.model.Transducer.beam_search", done,
+                              attr="beam_search")
         except ImportError:
             pass
     if patch_espnet:
