@@ -81,12 +81,48 @@ def synth(w, seed, device=None, pin=False):
 
 
 class ClockSampler:
+    """SM clock, board power and throttle reasons DURING the timed region: NVML polled from a thread every 5 ms (the
+    default timed region is ~150 ms, `nvidia-smi -lms 100` sees one or two samples of it); `nvidia-smi` when NVML's
+    Python binding is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.proc = None
+        self.thread = None
+        self.rows = []                       # (sm MHz, power W, reason bits)
+        self.maxc = None
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.maxc = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+            self.halt = threading.Event()
+
+            def poll():
+                while not self.halt.is_set():
+                    try:
+                        self.rows.append((float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)),
+                                          nv.nvmlDeviceGetPowerUsage(handle) / 1000.0,
+                                          int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))))
+                    except Exception:
+                        pass
+                    self.halt.wait(0.005)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -94,7 +130,18 @@ class ClockSampler:
         except OSError:
             pass
 
+    def _summary(self, clocks, power, reasons, maxc, source):
+        load = [c for c, p in zip(clocks, power) if p > 300.0] or clocks
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": maxc,
+                "reasons": sorted(reasons), "samples": len(clocks), "power_w_max": max(power) if power else None,
+                "source": source}
+
     def stop(self):
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            reasons = {n for _, _, r in self.rows for n, b in zip(self.NAMES, self.bits) if r & b}
+            return self._summary([r[0] for r in self.rows], [r[1] for r in self.rows], reasons, self.maxc, "nvml, 5 ms")
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +151,6 @@ class ClockSampler:
             self.proc.kill()
             out, _ = self.proc.communicate()
         clocks, maxc, reasons, power = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -115,12 +161,10 @@ class ClockSampler:
                 power.append(float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        load = [c for c, p in zip(clocks, power) if p > 300.0] or clocks
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": maxc,
-                "reasons": sorted(reasons), "samples": len(clocks), "power_w_max": max(power) if power else None}
+        return self._summary(clocks, power, reasons, maxc, "nvidia-smi -lms 100")
 
 
 def _cpu_joint(w):
