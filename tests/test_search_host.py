@@ -23,15 +23,15 @@ class _TorchScanner:
     def __init__(self, joint, enc_state, length):
         self.joint, self.enc, self.length = joint, enc_state, length
 
-    def decoder_half(self, dec_out):
-        return dec_out.reshape(-1)
+    def decoder_halves(self, dec_outs):
+        return dec_outs
 
-    def posterior(self, t, pvec):
-        return torch.softmax(self.joint(self.enc[t].view(-1), pvec), dim=0)
+    def posteriors(self, t, pvecs):
+        return torch.stack([torch.softmax(self.joint(self.enc[t].view(-1), pv), dim=0) for pv in pvecs])
 
     def next_label(self, t, pvec, blank):
         while t < self.length:
-            label = int(self.posterior(t, pvec).argmax())
+            label = int(self.posteriors(t, pvec[None])[0].argmax())
             if label != blank:
                 return t, label
             t += 1
@@ -56,7 +56,7 @@ def test_beam_search_bookkeeping_equals_reference(monkeypatch, seed, boost):
     with torch.no_grad():
         model.joint.project_layer.bias[0] += boost
         enc = model.encoder(torch.randn(1, 40, 512), None)[0]
-        step = lambda toks: model.decoder(torch.tensor([toks]))[:, -1, :]  # noqa: E731
+        step = lambda hyps: model.decoder(torch.tensor(hyps))[:, -1, :]  # noqa: E731
         for width in (5, 3, 2):
             want = model.beam_search(enc, 40, beam_width=width)
             got = D.beam_search(model.joint, enc, 40, step, beam_width=width)

@@ -95,10 +95,14 @@ class _FrameScanner:
             look = min(SCAN_FRAMES, 2 * look)           # a run of blanks: look further ahead next time
         return self.length, int(blank)
 
-    def posterior(self, t, pvec):
-        """softmax over the vocabulary at frame t (fp32), for the searches that rank more than the best label."""
-        hidden = torch.tanh(self.eproj[t] + pvec)
-        return torch.softmax(torch.nn.functional.linear(hidden, self.parts.w_out, self.parts.b_out), dim=0)
+    def decoder_halves(self, dec_outs):
+        return torch.nn.functional.linear(dec_outs.float(), self.parts.w_dec).contiguous()        # (n, H)
+
+    def posteriors(self, t, pvecs):
+        """softmax over the vocabulary at frame t (fp32) for n decoder states (n, H) -> (n, V), for the searches that
+        rank more than the best label."""
+        hidden = torch.tanh(self.eproj[t] + pvecs)
+        return torch.softmax(torch.nn.functional.linear(hidden, self.parts.w_out, self.parts.b_out), dim=-1)
 
 
 @torch.no_grad()
@@ -131,7 +135,11 @@ def beam_search(joint, enc_state, length, step_decoder, beam_width=5, start_toke
     frame scan; on a label frame every hypothesis is expanded by its `beam_width` best non-blank labels (scores = log
     posteriors, accumulated per parent) and the best `beam_width` children survive.  The child lists are the
     reference's: one (beam_width x beam_width) table that is appended to at every label frame and never reset, the
-    first label frame filling it column-wise."""
+    first label frame filling it column-wise.
+
+    step_decoder(list of label histories) -> (n, D_dec) last decoder outputs.  All hypotheses have the same length (the
+    child lists grow together), so the reference's 1 + beam_width decoder runs and beam_width joint / top-k / host reads
+    per label frame are ONE batched decoder run, one posterior GEMM and one host read here."""
     import heapq
     import numpy as np
     length = int(length)
@@ -147,14 +155,14 @@ def beam_search(joint, enc_state, length, step_decoder, beam_width=5, start_toke
         fresh = True
         t = 0
         while t < length:
-            lead = int(score.argmax())
-            t, _ = scanner.next_label(t, scanner.decoder_half(step_decoder(hyps[lead])), blank)
+            pvecs = scanner.decoder_halves(step_decoder(hyps))               # (W, H): valid until the next label frame
+            t, _ = scanner.next_label(t, pvecs[int(score.argmax())], blank)
             if t >= length:
                 break
+            top = torch.topk(scanner.posteriors(t, pvecs), k=W + 1, dim=-1)
+            both = torch.cat([top.values, top.indices.to(top.values.dtype)], dim=1).tolist()     # labels < 2^24: exact
             for k in range(W):
-                post = scanner.posterior(t, scanner.decoder_half(step_decoder(hyps[k])))
-                top = torch.topk(post, k=W + 1, dim=0)
-                values, labels = top.values.tolist(), top.indices.tolist()
+                values, labels = both[k][:W + 1], [int(x) for x in both[k][W + 1:]]
                 drop = labels.index(blank) if blank in labels else W        # the blank if it made the list, else the last
                 del values[drop], labels[drop]
                 logs = np.log(values)
@@ -198,9 +206,9 @@ def tt_beam_search(self, enc_state, lengths, beam_width=5):
         return type(self)._ttb_reference_beam_search(self, enc_state, lengths, beam_width)
     dev = enc_state.device
 
-    def step(tokens):
-        token = torch.tensor([tokens], dtype=torch.long, device=dev)
-        return self.decoder(token)[:, -1, :]                     # tt/model.py:135-136,141
+    def step(histories):
+        tokens = torch.tensor(histories, dtype=torch.long, device=dev)
+        return self.decoder(tokens)[:, -1, :]                    # tt/model.py:135-136,141, all hypotheses in one batch
 
     return beam_search(self.joint, enc_state, lengths, step, beam_width=beam_width, start_token=0, blank=0)
 
