@@ -337,6 +337,40 @@ def test_tt_beam_search_equals_reference_beam_search(beam):
     assert any(len(w) > 1 for w in want), want
 
 
+def test_streaming_window_search_equals_demo_loop():
+    """audio/streamRec_unlimit_dynamic_window.py:113-115,186-211 (the demo's per-frame loop, restated here around the
+    reference's own joint / decoder because it lives inside a tkinter class) vs decode.StreamingGreedy fed the same
+    windows: same labels, same blank-frame counts at every label, state carried across windows, 40-label history."""
+    from transformer_transducer_b200.decode import StreamingGreedy
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    cfg = _tt_config(1024, 211)
+    _seed(9)
+    model = tt_model.Transducer(cfg.model).to(DEV).eval()
+    _boost_blank(model.joint.project_layer, 0.25)
+    windows = [torch.randn(n, 512, device=DEV) for n in (37, 1, 64, 90, 5, 130)]
+    with torch.no_grad():
+        enc = [model.encoder(w[None], None)[0] for w in windows]
+        dec_state = model.decoder(torch.tensor([[0]], device=DEV))
+        result, blank_frame, want = [], 0, []
+        for e in enc:
+            events = []
+            for t in range(e.shape[0]):
+                pred = int(torch.argmax(torch.softmax(model.joint(e[t].view(-1), dec_state.view(-1)), dim=0), dim=0).item())
+                if pred != 0:
+                    events.append((pred, blank_frame))
+                    result.append(pred)
+                    dec_state = model.decoder(torch.tensor([result[-40:]], device=DEV))[:, -1, :]
+                    blank_frame = 0
+                elif result:
+                    blank_frame += 1
+            want.append(events)
+        search = StreamingGreedy(model.joint, model.decoder)
+        got = [search.feed(e) for e in enc]
+    assert got == want and search.result == result and search.blank_frame == blank_frame
+    assert len(result) > 40                          # the history window was exercised
+
+
 def test_espnet_greedy_decode_equals_reference_decode():
     """tt_espnet/model.py:83-121: same check for TransformerTransducer.decode / recognize."""
     V = 333

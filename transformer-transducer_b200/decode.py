@@ -4,7 +4,8 @@ Drop-in for the reference's per-utterance search loops
   tt.model.Transducer.decode                      /root/reference/tt/model.py:70-90
   tt.model.Transducer.beam_search                 /root/reference/tt/model.py:110-179
   tt_espnet.model.TransformerTransducer.decode    /root/reference/tt_espnet/model.py:83-106
-(same arguments, same return value: the label sequence without the start symbol).  The reference evaluates
+(same arguments, same return value: the label sequence without the start symbol), and `StreamingGreedy` for the
+streaming demo's window-by-window loop (/root/reference/audio/streamRec_unlimit_dynamic_window.py:186-211).  The reference evaluates
 ``joint(enc_state[t].view(-1), dec_state.view(-1)) -> softmax -> argmax -> .item()`` once per frame; the decoder state
 only changes when a label is emitted, so here every frame up to the next non-blank prediction is scored against the
 current decoder state in one launch group (64 frames at a time) and the host reads two integers per emitted label.
@@ -56,13 +57,13 @@ class _FrameScanner:
     """One utterance's decode-time joint: encoder half of the first layer for all frames (once), decoder half per label
     history, and the launch group that scores a run of frames against one decoder state."""
 
-    def __init__(self, joint, enc_state, length):
+    def __init__(self, joint, enc_state, length, parts=None):
         if not enc_state.is_cuda:
             raise RuntimeError("the decode-time joint kernel needs CUDA tensors (there is no CPU fallback)")
         self.lib = _lib.get()
         self.dev = dev = enc_state.device
         self.length = length
-        self.parts = parts = _JointParts(joint, enc_state.size(-1))
+        self.parts = parts = parts if parts is not None else _JointParts(joint, enc_state.size(-1))
         self.H, self.V = parts.w_out.shape[1], parts.w_out.shape[0]
         self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
         self.eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
@@ -185,6 +186,51 @@ def beam_search(joint, enc_state, length, step_decoder, beam_width=5, start_toke
                     hyps[i] = list(child[flat // W][flat % W])
             t += 1
     return hyps[int(score.argmax())][1:]
+
+
+class StreamingGreedy:
+    """The streaming demo's recognition loop (audio/streamRec_unlimit_dynamic_window.py:113-115,186-211) without its
+    per-frame host read: encoder states arrive window by window, the decoder state, the label history (the decoder sees
+    the last `history` labels, :201-207) and the count of blank frames since the last label (the demo starts a new line
+    at >= 15, :193) carry over from one window to the next."""
+
+    def __init__(self, joint, decoder, history=40, start_token=0, blank=0):
+        self.joint, self.decoder = joint, decoder
+        self.history, self.blank, self.start_token = int(history), int(blank), int(start_token)
+        self.result = []
+        self.blank_frame = 0
+        self.dec_state = None
+        self._parts = None
+
+    @torch.no_grad()
+    def feed(self, enc_states):
+        """enc_states (n, D_enc) CUDA: the effective frames of one window.  Returns [(label, blank frames since the
+        previous label)] for the labels emitted in it; `self.result` holds everything emitted so far."""
+        n = int(enc_states.shape[0])
+        events = []
+        if n == 0:
+            return events
+        dev = enc_states.device
+        with torch.cuda.device(dev):
+            if self.dec_state is None:
+                self.dec_state = self.decoder(torch.tensor([[self.start_token]], dtype=torch.long, device=dev))   # :112-113
+            if self._parts is None:
+                self._parts = _JointParts(self.joint, enc_states.size(-1))        # (weights are read once per stream)
+            scanner = _FrameScanner(self.joint, enc_states, n, parts=self._parts)
+            t = 0
+            while t < n:
+                hit, label = scanner.next_label(t, scanner.decoder_half(self.dec_state), self.blank)
+                if self.result:
+                    self.blank_frame += hit - t                                    # :210-211
+                if hit >= n:
+                    break
+                events.append((label, self.blank_frame))
+                self.result.append(label)
+                token = torch.tensor([self.result[-self.history:]], dtype=torch.long, device=dev)
+                self.dec_state = self.decoder(token)[:, -1, :]                     # :201-207
+                self.blank_frame = 0
+                t = hit + 1
+        return events
 
 
 def tt_decode(self, enc_state, lengths):
