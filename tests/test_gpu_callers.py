@@ -300,11 +300,13 @@ def test_tt_greedy_decode_equals_reference_decode(inner):
         want = model.recognize(inputs, lengths)
         try:
             done = ttb.install(patch_espnet=False)
-            assert "tt.model.Transducer.decode" in done
-            got = model.recognize(inputs, lengths)        # tt/model.py:92-108 unchanged, decode rebound
+            assert "tt.model.Transducer.decode" in done and "tt.model.Transducer.recognize" in done
+            got = model.recognize(inputs, lengths)        # tt/model.py:92-108 rebound: batched search over the utterances
+            enc = model.encoder(inputs, None)
+            got_single = [model.decode(enc[b], lengths[b]) for b in range(3)]      # tt/model.py:70-90 rebound
         finally:
             ttb.uninstall()
-    assert got == want
+    assert got == want and got_single == want
     assert all(0 < len(w) < n for w, n in zip(want, lengths))    # labels were emitted, and blanks in between
 
 
@@ -385,10 +387,14 @@ def test_espnet_greedy_decode_equals_reference_decode():
     try:
         ttb.install(patch_tt=False)
         assert tem.TransformerTransducer.decode is not tem.TransformerTransducer._ttb_reference_decode
-        got = model.recognize(speech, slen)
+        assert tem.TransformerTransducer.recognize is not tem.TransformerTransducer._ttb_reference_recognize
+        got = model.recognize(speech, slen)               # batched search
+        with torch.no_grad():
+            enc, _, _ = model.encoder(speech, slen, left_mask=model.encoder_left_mask, right_mask=model.encoder_right_mask)
+            got_single = [model.decode(enc[b], slen[b]) for b in range(2)]
     finally:
         ttb.uninstall()
-    assert got == want
+    assert got == want and got_single == want
     assert all(len(w) > 0 for w in want)
 
 

@@ -4,7 +4,8 @@ Drop-in for the reference's per-utterance search loops
   tt.model.Transducer.decode                      /root/reference/tt/model.py:70-90
   tt.model.Transducer.beam_search                 /root/reference/tt/model.py:110-179
   tt_espnet.model.TransformerTransducer.decode    /root/reference/tt_espnet/model.py:83-106
-(same arguments, same return value: the label sequence without the start symbol), and `StreamingGreedy` for the
+(same arguments, same return value: the label sequence without the start symbol), the two `recognize` methods
+(tt/model.py:92-108, tt_espnet/model.py:108-121) as one batched search, and `StreamingGreedy` for the
 streaming demo's window-by-window loop (/root/reference/audio/streamRec_unlimit_dynamic_window.py:186-211).  The reference evaluates
 ``joint(enc_state[t].view(-1), dec_state.view(-1)) -> softmax -> argmax -> .item()`` once per frame; the decoder state
 only changes when a label is emitted, so here every frame up to the next non-blank prediction is scored against the
@@ -57,7 +58,7 @@ class _FrameScanner:
     """One utterance's decode-time joint: encoder half of the first layer for all frames (once), decoder half per label
     history, and the launch group that scores a run of frames against one decoder state."""
 
-    def __init__(self, joint, enc_state, length, parts=None):
+    def __init__(self, joint, enc_state, length, parts=None, eproj=None, out=None):
         if not enc_state.is_cuda:
             raise RuntimeError("the decode-time joint kernel needs CUDA tensors (there is no CPU fallback)")
         self.lib = _lib.get()
@@ -66,20 +67,26 @@ class _FrameScanner:
         self.parts = parts = parts if parts is not None else _JointParts(joint, enc_state.size(-1))
         self.H, self.V = parts.w_out.shape[1], parts.w_out.shape[0]
         self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        self.eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
+        if eproj is None:
+            eproj = torch.nn.functional.linear(enc_state[:length].float(), parts.w_enc, parts.b_enc).contiguous()
+        self.eproj = eproj                                  # (>= length, H), rows contiguous
         self.scratch = torch.empty(SCAN_FRAMES, dtype=torch.int64, device=dev)
-        self.out = torch.empty(2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
+        self.out = out if out is not None else torch.empty(2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
 
     def decoder_half(self, dec_out):
         return torch.nn.functional.linear(dec_out.reshape(-1).float(), self.parts.w_dec)
 
-    def scan(self, t, n, pvec, blank):
-        """Frames t .. t + n - 1 against pvec: (offset of the first frame whose argmax is not blank -- n if none --, its
-        label).  The one host read per emitted label / run of blank frames."""
+    def launch(self, t, n, pvec, blank):
+        """Frames t .. t + n - 1 against pvec, stream-ordered: out[0] = offset of the first frame whose argmax is not
+        blank (n if none), out[1] = its label."""
         st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-        _lib.check(self.lib.ttx_decode_scan(_p(self.eproj[t]), self.H, _p(pvec), _p(self.parts.w_out), _p(self.parts.b_out),
-                                            n, self.H, self.V, int(blank), _p(self.scratch), _p(self.out), self.idx, st),
-                   "ttx_decode_scan")
+        _lib.check(self.lib.ttx_decode_scan(_p(self.eproj[t]), self.eproj.stride(0), _p(pvec), _p(self.parts.w_out),
+                                            _p(self.parts.b_out), n, self.H, self.V, int(blank), _p(self.scratch),
+                                            _p(self.out), self.idx, st), "ttx_decode_scan")
+
+    def scan(self, t, n, pvec, blank):
+        """launch() + the one host read per emitted label / run of blank frames: (offset, label)."""
+        self.launch(t, n, pvec, blank)
         first, label = self.out[:2].tolist()
         return first, label
 
@@ -127,6 +134,58 @@ def greedy_search(joint, enc_state, length, step_decoder, start_token=0, blank=0
             tokens.append(label)
             t += 1
     return tokens[1:]
+
+
+@torch.no_grad()
+def greedy_search_batch(joint, enc_states, lengths, step_decoder, start_token=0, blank=0):
+    """Greedy search over a whole batch: enc_states (B, T, D_enc) CUDA, lengths[b] frames each, step_decoder(list of
+    EQUAL-LENGTH label histories) -> (n, D_dec) last decoder outputs.  Returns B label lists, the ones the reference's
+    per-utterance loop (`recognize`: tt/model.py:92-108, tt_espnet/model.py:108-121) produces.
+
+    Round r: every utterance still running has emitted exactly r labels, so their r + 1 long histories go through the
+    decoder as ONE batch; then each utterance's frames are scanned from its own position to its next label (launches
+    only; one host read per round for all of them, plus one per extra look-ahead group on long runs of blanks)."""
+    if not enc_states.is_cuda:
+        raise RuntimeError("greedy_search_batch needs CUDA tensors (there is no CPU fallback)")
+    B = int(enc_states.shape[0])
+    lengths = [int(x) for x in lengths]
+    tokens = [[int(start_token)] for _ in range(B)]
+    active = [b for b in range(B) if lengths[b] > 0]
+    if not active:
+        return [t[1:] for t in tokens]
+    dev = enc_states.device
+    with torch.cuda.device(dev):
+        parts = _JointParts(joint, enc_states.size(-1))
+        eproj = torch.nn.functional.linear(enc_states.float(), parts.w_enc, parts.b_enc).contiguous()      # (B, T, H)
+        outs = torch.zeros(B, 2 + SCAN_FRAMES, dtype=torch.int32, device=dev)
+        scanners = [_FrameScanner(joint, enc_states[b], lengths[b], parts=parts, eproj=eproj[b], out=outs[b])
+                    for b in range(B)]
+        pos = [0] * B
+        while active:
+            pvecs = scanners[0].decoder_halves(step_decoder([tokens[b] for b in active]))
+            row = {b: i for i, b in enumerate(active)}
+            look = {b: SCAN_FIRST for b in active}
+            pending = list(active)
+            while pending:
+                count = {}
+                for b in pending:
+                    count[b] = min(look[b], lengths[b] - pos[b])
+                    scanners[b].launch(pos[b], count[b], pvecs[row[b]], blank)
+                found = outs[:, :2].tolist()                                  # the round's host read
+                still = []
+                for b in pending:
+                    first, label = found[b]
+                    if first < count[b]:
+                        tokens[b].append(int(label))
+                        pos[b] += first + 1
+                        continue
+                    pos[b] += count[b]
+                    look[b] = min(SCAN_FRAMES, 2 * look[b])
+                    if pos[b] < lengths[b]:
+                        still.append(b)
+                pending = still
+            active = [b for b in active if pos[b] < lengths[b]]
+    return [t[1:] for t in tokens]
 
 
 @torch.no_grad()
@@ -246,6 +305,20 @@ def tt_decode(self, enc_state, lengths):
     return greedy_search(self.joint, enc_state, lengths, step, start_token=0, blank=0)
 
 
+def tt_recognize(self, inputs, inputs_length=None, audio_mask=None):
+    """tt.model.Transducer.recognize (tt/model.py:92-108): same encoder call, the per-utterance decode loop replaced by
+    the batched search."""
+    enc_states = self.encoder(inputs, audio_mask)
+    if not enc_states.is_cuda:
+        return [self.decode(enc_states[b], inputs_length[b]) for b in range(inputs.size(0))]
+    dev = enc_states.device
+
+    def step(histories):
+        return self.decoder(torch.tensor(histories, dtype=torch.long, device=dev))[:, -1, :]
+
+    return greedy_search_batch(self.joint, enc_states, [int(x) for x in inputs_length], step, start_token=0, blank=0)
+
+
 def tt_beam_search(self, enc_state, lengths, beam_width=5):
     """tt.model.Transducer.beam_search (tt/model.py:110-179) with the leader's frame scan on the GPU."""
     if not enc_state.is_cuda:
@@ -276,3 +349,26 @@ def espnet_decode(self, enc_state, lengths):
         return out[:, -1, :]
 
     return greedy_search(self.joint, enc_state, lengths, step, start_token=self.sos, blank=0)
+
+
+@torch.no_grad()
+def espnet_recognize(self, speech, speech_lengths):
+    """tt_espnet.model.TransformerTransducer.recognize (tt_espnet/model.py:108-121), batched search."""
+    encoder_out, _, _ = self.encoder(speech, speech_lengths, left_mask=self.encoder_left_mask,
+                                     right_mask=self.encoder_right_mask)
+    if not encoder_out.is_cuda:
+        return [self.decode(encoder_out[b], speech_lengths[b]) for b in range(speech.size(0))]
+    dev = encoder_out.device
+    first = [True]
+
+    def step(histories):
+        token = torch.tensor(histories, dtype=torch.long, device=dev)
+        if first[0]:                                             # model.py:89-90: the left mask on the first call only
+            first[0] = False
+            out, _, _ = self.decoder.forward_one_step(token, self.decoder_left_mask)
+        else:
+            out, _, _ = self.decoder.forward_one_step(token)
+        return out[:, -1, :]
+
+    return greedy_search_batch(self.joint, encoder_out, [int(x) for x in speech_lengths], step, start_token=self.sos,
+                               blank=0)

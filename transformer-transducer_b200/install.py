@@ -81,6 +81,8 @@ def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True
                 _patch_decode(m.Transducer, _decode.tt_decode, "tt.model.Transducer.decode", done)
                 _patch_decode(m.Transducer, _decode.tt_beam_search, "tt.model.Transducer.beam_search", done,
                               attr="beam_search")
+                _patch_decode(m.Transducer, _decode.tt_recognize, "tt.model.Transducer.recognize", done,
+                              attr="recognize")
         except ImportError:
             pass
     if patch_espnet:
@@ -96,4 +98,6 @@ def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True
             if patch_decode:
                 _patch_decode(sys.modules["tt_espnet.model"].TransformerTransducer, _decode.espnet_decode,
                               "tt_espnet.model.TransformerTransducer.decode", done)
+                _patch_decode(sys.modules["tt_espnet.model"].TransformerTransducer, _decode.espnet_recognize,
+                              "tt_espnet.model.TransformerTransducer.recognize", done, attr="recognize")
     return done
