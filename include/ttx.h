@@ -224,14 +224,20 @@ int ttx_spec_mask(float* x, int B, int T, int F, int64_t stride_b, int64_t strid
  * r_w_bias (n_head, d_head), r_bias (max_len, n_head); scale = 1 / sqrt(d_head).  prob (T, B, n_head, left + right + 1):
  * the band's softmax, kept for the backward; out (T, B, n_head * d_head) = attn_vec (transformer.py:165-167).
  * Backward: ds (like prob) and dq_content (T, B, n_head * d_head) are scratch; d_w_heads is fully written; d_r_emb,
- * d_r_w_bias, d_r_bias must be zero-filled (they are accumulated). */
+ * d_r_w_bias, d_r_bias must be zero-filled (they are accumulated).
+ * mode 0 = the tt module above (its _rel_shift, transformer.py:82-95, wraps right of the diagonal; key_lens = NULL).
+ * mode 1 = the espnet side: RelPositionMultiHeadedAttention.forward (espnet/nets/pytorch_backend/transformer/
+ * attention.py:264-308) under make_attention_mask (nets_utils.py:268-281) and the padding mask (espnet2/asr/encoder/
+ * transformer_encoder.py:205-210): r_emb = linear_pos(pos_emb) with max_len = 2T - 1 rows, r_w_bias = pos_bias_u,
+ * r_bias[r, h] = pos_bias_v[h] . r_emb[r, h] (folded by the caller), key j of batch entry b is masked when
+ * j >= key_lens[b] (device, int32, B entries; NULL = no padding); a query without any key gets zeros. */
 int ttx_band_attn_fwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* r_bias, int T, int B,
-                      int n_head, int d_head, int max_len, int left, int right, float scale, float* prob, float* out,
-                      int device, void* stream);
+                      int n_head, int d_head, int max_len, int left, int right, float scale, int mode,
+                      const int32_t* key_lens, float* prob, float* out, int device, void* stream);
 int ttx_band_attn_bwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* prob, const float* d_out,
-                      int T, int B, int n_head, int d_head, int max_len, int left, int right, float scale, float* ds,
-                      float* dq_content, float* d_w_heads, float* d_r_emb, float* d_r_w_bias, float* d_r_bias, int device,
-                      void* stream);
+                      int T, int B, int n_head, int d_head, int max_len, int left, int right, float scale, int mode,
+                      const int32_t* key_lens, float* ds, float* dq_content, float* d_w_heads, float* d_r_emb,
+                      float* d_r_w_bias, float* d_r_bias, int device, void* stream);
 
 /* The device side of warprnnt_pytorch's argument checks (certify_inputs) in one launch: out (7 x int64, device) = max T,
  * max U, min T, min U over the batch, the batch's 128-row lattice tiles, the number of labels outside [0, V) inside their

@@ -121,7 +121,7 @@ def test_unmodified_train_loop_drives_product_on_cuda(inner):
         assert isinstance(logits, ttb.LazyJointLogits)
         got = ref_train.RNNTLoss()(logits, targets.int().to(DEV), ilen.int().to(DEV), tlen.int().to(DEV))
         got.backward()
-        assert abs(float(got) - float(want)) / abs(float(want)) < LOSS_TOL
+        assert abs(float(got.detach()) - float(want.detach())) / abs(float(want.detach())) < LOSS_TOL
         for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
             assert b.grad is not None and a.grad is not None, n
             assert rel(a.grad, b.grad) < GRAD_TOL, (n, rel(a.grad, b.grad))
@@ -213,7 +213,7 @@ def test_espnet_transformer_transducer_forward_backward_fp32():
     got = model(speech.to(DEV), slen.to(DEV), text.to(DEV), tlen.to(DEV))
     assert got.dtype == torch.float32 and got.shape == (1,)
     got.backward()
-    assert abs(float(got) - float(want)) / abs(float(want)) < LOSS_TOL
+    assert abs(float(got.detach()) - float(want.detach())) / abs(float(want.detach())) < LOSS_TOL
     _assert_grads_close(model, ref_model, GRAD_TOL)
 
 
@@ -478,4 +478,63 @@ def test_banded_attention_equals_reference_under_context_mask(T, max_len, ctx):
     assert rel(got, want) < 2e-5
     names = ["w", "r_emb", "r_w_bias", "r_bias"] + [n for n, _ in attn.named_parameters()]
     for n, a, b in zip(names, got_g, want_g):
+        assert rel(a, b) < 2e-5, (n, rel(a, b))
+
+
+@pytest.mark.parametrize("T,lens,ctx", [(57, [57, 40, 9], (10, 2)), (130, [130, 130], (10, 2)), (9, [9, 4, 1], (2, 0)),
+                                        (6, [6, 2], (10, 2)), (40, [40, 31], (3, 4))])
+def test_espnet_banded_attention_equals_reference_under_padding_and_context_mask(T, lens, ctx):
+    """espnet/nets/pytorch_backend/transformer/attention.py:212-308 (RelPositionMultiHeadedAttention, the reference's own
+    module with dense T x T scores, on cuda:0) vs the rebound forward on the band kernels (mode 1), under the mask
+    tt_espnet's encoders build (espnet2/asr/encoder/transformer_encoder.py:205-210: padding mask AND
+    ~make_attention_mask, nets_utils.py:268-281): the encoder's (10, 2) band, the label encoder's (2, 0), T shorter than
+    the band, queries beyond a short utterance's length (no key left: zeros), another width.  Output and every gradient
+    (input, the four projections, linear_pos, pos_bias_u / _v).  Tolerance 2e-5 relative L2."""
+    ref_import.prepare(stub_train_deps=True)
+    from espnet.nets.pytorch_backend.nets_utils import make_attention_mask, make_pad_mask
+    from espnet.nets.pytorch_backend.transformer import attention as eatt
+    from espnet.nets.pytorch_backend.transformer.embedding import RelPositionalEncoding
+    from transformer_transducer_b200 import attention as att
+    _seed(T + len(lens))
+    B, n_head, d_model = len(lens), 4, 256
+    attn = eatt.RelPositionMultiHeadedAttention(n_head, d_model, 0.0).to(DEV)
+    posenc = RelPositionalEncoding(d_model, 0.0).to(DEV)
+    x = torch.randn(B, T, d_model, device=DEV, requires_grad=True)
+    g = torch.randn(B, T, d_model, device=DEV)
+    _, pos_emb = posenc(x.detach())
+    ilens = torch.tensor(lens, device=DEV)
+    mask = (~make_pad_mask(ilens)[:, None, :]).to(DEV) & ~make_attention_mask(x, ctx[0], ctx[1])[None, :, :]
+    leaves = [x] + list(attn.parameters())
+
+    def run(m):
+        for t_ in leaves:
+            t_.grad = None
+        out = attn(x, x, x, pos_emb, m)
+        out.backward(g)
+        return out.detach().clone(), [t_.grad.detach().clone() for t_ in leaves]
+
+    want, want_g = run(mask)
+    calls = []
+    orig_apply = att.BandAttnCore.apply
+    try:
+        done = ttb.install(patch_tt=False, patch_espnet=False, patch_decode=False, patch_data=False)
+        assert "espnet...attention.RelPositionMultiHeadedAttention.forward" in done
+        att.BandAttnCore.apply = staticmethod(lambda *a: (calls.append(1), orig_apply(*a))[1])
+        got, got_g = run(mask)
+        other = mask.clone()                                  # not a band: the reference's own forward
+        other[0, 0, 0] = ~other[0, 0, 0]
+        n_calls = len(calls)
+        attn(x, x, x, pos_emb, other)
+        assert len(calls) == n_calls
+    finally:
+        att.BandAttnCore.apply = orig_apply
+        ttb.uninstall()
+    assert calls, "the band kernel did not run"
+    assert eatt.RelPositionMultiHeadedAttention.forward is not att.espnet_banded_forward
+    assert rel(got, want) < 2e-5
+    names = ["x"] + [n for n, _ in attn.named_parameters()]
+    for n, a, b in zip(names, got_g, want_g):
+        if n == "linear_k.bias":          # shifts every score of a query alike: the gradient is zero, both sides hold rounding
+            assert float(a.abs().max()) < 1e-5 and float(b.abs().max()) < 1e-5
+            continue
         assert rel(a, b) < 2e-5, (n, rel(a, b))

@@ -56,3 +56,35 @@ err = float((got - want).norm() / want.norm())
 print(json.dumps({"workload": "RelLearnableMultiHeadAttn fwd+bwd T=%d B=%d heads=%dx%d context=(10,2)" % (T, B, n_head, d_head),
                   "reference_ms": ref_ms, "ours_ms": our_ms, "speedup": ref_ms / our_ms, "reference_peak_MiB": ref_mb,
                   "ours_peak_MiB": our_mb, "rel_l2_output": err}))
+
+# ---- espnet side: RelPositionMultiHeadedAttention (attention.py:212-308) under padding + context mask, espnet_aishell.yaml's
+# encoder dims (512, 8 heads), same T / B
+from espnet.nets.pytorch_backend.nets_utils import make_attention_mask, make_pad_mask  # noqa: E402
+from espnet.nets.pytorch_backend.transformer import attention as eatt  # noqa: E402
+from espnet.nets.pytorch_backend.transformer.embedding import RelPositionalEncoding  # noqa: E402
+
+torch.manual_seed(1)
+eattn = eatt.RelPositionMultiHeadedAttention(n_head, d_model, 0.0).cuda()
+x = torch.randn(B, T, d_model, device="cuda", requires_grad=True)
+ge = torch.randn(B, T, d_model, device="cuda")
+_, pos_emb = RelPositionalEncoding(d_model, 0.0).cuda()(x.detach())
+ilens = torch.randint(T // 2, T + 1, (B,), device="cuda")
+ilens[0] = T
+emask = (~make_pad_mask(ilens)[:, None, :]).cuda() & ~make_attention_mask(x, 10, 2)[None, :, :]
+
+
+def step():  # noqa: F811
+    out = eattn(x, x, x, pos_emb, emask)
+    out.backward(ge)
+    return out
+
+
+ref_ms, ref_mb, want = timed()
+ttb.install(patch_tt=False, patch_espnet=False, patch_decode=False, patch_data=False)
+our_ms, our_mb, got = timed()
+ttb.uninstall()
+err = float((got - want).norm() / want.norm())
+print(json.dumps({"workload": "espnet RelPositionMultiHeadedAttention fwd+bwd T=%d B=%d heads=%dx%d padding + context=(10,2)"
+                  % (T, B, n_head, d_model // n_head),
+                  "reference_ms": ref_ms, "ours_ms": our_ms, "speedup": ref_ms / our_ms, "reference_peak_MiB": ref_mb,
+                  "ours_peak_MiB": our_mb, "rel_l2_output": err}))

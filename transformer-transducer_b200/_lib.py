@@ -59,10 +59,10 @@ _PROTOS = {
     "ttx_proj_bwd_w": [c_p, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_p],
     "ttx_decode_scan": [c_p, c_i32, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_p],
     "ttx_spec_mask": [c_p, c_i32, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_i32, c_p],
-    "ttx_band_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_p, c_p, c_i32,
-                          c_p],
-    "ttx_band_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_p, c_p,
-                          c_p, c_p, c_p, c_p, c_i32, c_p],
+    "ttx_band_attn_fwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_i32, c_p,
+                          c_p, c_p, c_i32, c_p],
+    "ttx_band_attn_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_i32, c_p,
+                          c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p],
     "ttx_check_inputs": [c_p, c_i32, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
     "ttx_dense_lse": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p,
                       c_i32, c_p],

@@ -69,10 +69,10 @@ int launch_decode_scan(const float*, int, const float*, const float*, const floa
 
 int launch_spec_mask(float*, int, int, int, long long, long long, const int*, int, cudaStream_t);
 
-int launch_band_attn_fwd(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, float, float*,
-                         float*, cudaStream_t);
+int launch_band_attn_fwd(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, float, int,
+                         const int*, float*, float*, cudaStream_t);
 int launch_band_attn_bwd(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int, int,
-                         float, float*, float*, float*, float*, float*, float*, cudaStream_t);
+                         float, int, const int*, float*, float*, float*, float*, float*, float*, cudaStream_t);
 
 int launch_check_inputs(const int*, int, const int*, const int*, int, int, long long*, cudaStream_t);
 
@@ -414,7 +414,16 @@ int ttx_spec_mask(float* x, int B, int T, int F, int64_t stride_b, int64_t strid
     return launch_spec_mask(x, B, T, F, stride_b, stride_t, masks_host, n_masks, (cudaStream_t)stream);
 }
 
-static int band_attn_shape_ok(const char* who, int T, int B, int n_head, int d_head, int max_len, int left, int right) {
+static int band_attn_shape_ok(const char* who, int T, int B, int n_head, int d_head, int max_len, int left, int right,
+                              int mode) {
+    if (mode != 0 && mode != 1) {
+        set_error("%s: mode %d (0 = tt, 1 = espnet)", who, mode);
+        return 1;
+    }
+    if (mode == 1 && max_len != 2 * T - 1) {
+        set_error("%s: mode 1 takes a position table of 2T - 1 = %d rows, got %d", who, 2 * T - 1, max_len);
+        return 1;
+    }
     if (T < 1 || B < 1 || n_head < 1 || d_head < 32 || d_head > 128 || d_head % 32 || max_len < 1 || left < 0 || right < 0 ||
         left + right + 1 > 32 || (long long)T * B * n_head > (1ll << 30)) {
         set_error("%s: bad shape T=%d B=%d heads=%d d_head=%d (multiple of 32 up to 128) max_len=%d context=(%d, %d) (at most "
@@ -425,25 +434,25 @@ static int band_attn_shape_ok(const char* who, int T, int B, int n_head, int d_h
 }
 
 int ttx_band_attn_fwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* r_bias, int T, int B,
-                      int n_head, int d_head, int max_len, int left, int right, float scale, float* prob, float* out,
-                      int device, void* stream) {
+                      int n_head, int d_head, int max_len, int left, int right, float scale, int mode, const int32_t* key_lens,
+                      float* prob, float* out, int device, void* stream) {
     TTX_REQUIRE(w_heads && r_emb && r_w_bias && r_bias && prob && out, "ttx_band_attn_fwd: null pointer");
-    if (int rc = band_attn_shape_ok("ttx_band_attn_fwd", T, B, n_head, d_head, max_len, left, right)) return rc;
+    if (int rc = band_attn_shape_ok("ttx_band_attn_fwd", T, B, n_head, d_head, max_len, left, right, mode)) return rc;
     TTX_ENTER(device);
-    return launch_band_attn_fwd(w_heads, r_emb, r_w_bias, r_bias, T, B, n_head, d_head, max_len, left, right, scale, prob, out,
-                                (cudaStream_t)stream);
+    return launch_band_attn_fwd(w_heads, r_emb, r_w_bias, r_bias, T, B, n_head, d_head, max_len, left, right, scale, mode,
+                                key_lens, prob, out, (cudaStream_t)stream);
 }
 
 int ttx_band_attn_bwd(const float* w_heads, const float* r_emb, const float* r_w_bias, const float* prob, const float* d_out,
-                      int T, int B, int n_head, int d_head, int max_len, int left, int right, float scale, float* ds,
-                      float* dq_content, float* d_w_heads, float* d_r_emb, float* d_r_w_bias, float* d_r_bias, int device,
-                      void* stream) {
+                      int T, int B, int n_head, int d_head, int max_len, int left, int right, float scale, int mode,
+                      const int32_t* key_lens, float* ds, float* dq_content, float* d_w_heads, float* d_r_emb,
+                      float* d_r_w_bias, float* d_r_bias, int device, void* stream) {
     TTX_REQUIRE(w_heads && r_emb && r_w_bias && prob && d_out && ds && dq_content && d_w_heads && d_r_emb && d_r_w_bias &&
                     d_r_bias, "ttx_band_attn_bwd: null pointer");
-    if (int rc = band_attn_shape_ok("ttx_band_attn_bwd", T, B, n_head, d_head, max_len, left, right)) return rc;
+    if (int rc = band_attn_shape_ok("ttx_band_attn_bwd", T, B, n_head, d_head, max_len, left, right, mode)) return rc;
     TTX_ENTER(device);
-    return launch_band_attn_bwd(w_heads, r_emb, r_w_bias, prob, d_out, T, B, n_head, d_head, max_len, left, right, scale, ds,
-                                dq_content, d_w_heads, d_r_emb, d_r_w_bias, d_r_bias, (cudaStream_t)stream);
+    return launch_band_attn_bwd(w_heads, r_emb, r_w_bias, prob, d_out, T, B, n_head, d_head, max_len, left, right, scale, mode,
+                                key_lens, ds, dq_content, d_w_heads, d_r_emb, d_r_w_bias, d_r_bias, (cudaStream_t)stream);
 }
 
 int ttx_check_inputs(const int32_t* labels, int label_stride, const int32_t* act_lens, const int32_t* label_lens, int B, int V,

@@ -14,6 +14,13 @@
 // One warp per (i, b, head): lanes over d_head, a slot's score stays on lane s.  The backward is three gather passes (no
 // atomics on activations): ds from the stored probabilities; dq / dk / dv per position; one accumulation pass for the
 // position tables and biases (atomics on max_len x n_head x d_head entries only).
+//
+// mode 1 = the espnet side, RelPositionMultiHeadedAttention (/root/reference/espnet/nets/pytorch_backend/transformer/
+// attention.py:212-308) under the context mask of nets_utils.py:268-281 AND the padding mask (encoder: espnet2/asr/encoder/
+// transformer_encoder.py:205-210): the position table has 2T - 1 rows (relative positions T-1 ... -(T-1)), its rel_shift
+// has no wrap -- key j uses row T - 1 + j - i with the query's own vector --, and keys at or beyond key_lens[b] are masked
+// (a query with no key left gets zeros, like softmax(...).masked_fill(mask, 0) there).  The caller folds pos_bias_v into the
+// bias table: (q + v) . p = q . p + (v . p).
 #include "ttx_common.cuh"
 
 namespace ttx {
@@ -23,6 +30,8 @@ constexpr int kAttnMaxDL = 4;          // d_head <= 128
 
 struct AttnParams {
     int T, B, NH, D, L, R, S, maxlen;
+    int mode;              // 0: tt (_rel_shift with its wrap), 1: espnet (2T - 1 rows, no wrap)
+    const int* klen;       // (B) keys per batch entry, or null: all T
     float scale;
     const float* wh;       // (T, B, 3 * NH * D)
     const float* remb;     // (maxlen, NH, D)
@@ -52,6 +61,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // row of the (possibly front-padded) position table that slot offset delta = j - i uses, or -1 when the slot has no
 // position term (delta = 1); `next` = the term is taken with the NEXT query's vector
 __device__ __forceinline__ int rel_row(const AttnParams& p, int delta, bool& next) {
+    if (p.mode == 1) {
+        next = false;
+        return (p.maxlen - 1) / 2 + delta;
+    }
     next = delta >= 2;
     if (delta == 1) return -1;
     const int x = delta <= 0 ? p.T - 1 + delta : delta - 2;
@@ -75,10 +88,11 @@ __global__ void __launch_bounds__(128) band_attn_fwd_kernel(const AttnParams p) 
             rw[c] = p.rwb[n * p.D + e];
         }
     }
+    const int kend = p.klen ? min(p.T, p.klen[b]) : p.T;    // keys [0, kend)
     float my = -INFINITY;                                   // lane s keeps the score of slot s
     for (int s = 0; s < p.S; ++s) {
         const int j = i + s - p.L;
-        if (j < 0 || j >= p.T) continue;                     // (whole warp alike)
+        if (j < 0 || j >= kend) continue;                    // (whole warp alike)
         const float* krow = p.wh + ((size_t)j * p.B + b) * ld + HD + n * p.D;
         bool next;
         const int g = rel_row(p, s - p.L, next);
@@ -96,7 +110,8 @@ __global__ void __launch_bounds__(128) band_attn_fwd_kernel(const AttnParams p) 
     }
     const float mx = warp_max(my);
     const float ex = (my == -INFINITY) ? 0.f : __expf(my - mx);
-    const float pr = ex / warp_sum(ex);
+    const float den = warp_sum(ex);
+    const float pr = den > 0.f ? ex / den : 0.f;            // (no key left: zeros)
     if (lane < p.S) p.prob[(size_t)w * p.S + lane] = pr;
     float acc[kAttnMaxDL];
 #pragma unroll
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(128) band_attn_fwd_kernel(const AttnParams p) 
     for (int s = 0; s < p.S; ++s) {
         const int j = i + s - p.L;
         const float ps = __shfl_sync(0xffffffffu, pr, s);
-        if (j < 0 || j >= p.T) continue;
+        if (j < 0 || j >= kend) continue;
         const float* vrow = p.wh + ((size_t)j * p.B + b) * ld + 2 * HD + n * p.D;
 #pragma unroll
         for (int c = 0; c < kAttnMaxDL; ++c)
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(128) band_attn_dqkv_kernel(const AttnParams p)
             }
     }
     // ... and the previous query's slots right of the diagonal, whose position term was taken with q_i
-    if (i >= 1) {
+    if (p.mode == 0 && i >= 1) {
         const float dsp = lane < p.S ? p.ds[((size_t)w - wstep) * p.S + lane] : 0.f;
         for (int delta = 2; delta <= p.R; ++delta) {
             const float x = __shfl_sync(0xffffffffu, dsp, p.L + delta);
@@ -235,7 +250,7 @@ __global__ void band_attn_dparam_kernel(const AttnParams p, int rows_per_block) 
         for (int s = 0; s < kAttnMaxSlots; ++s)
             if (s < p.S) {
                 const float x = dsr[s];                      // 0 for slots outside the sequence
-                acc[s] = fmaf(x, (s - p.L >= 2) ? qn : qi, acc[s]);
+                acc[s] = fmaf(x, (p.mode == 0 && s - p.L >= 2) ? qn : qi, acc[s]);
                 bacc[s] += x;
             }
     }
@@ -253,17 +268,20 @@ __global__ void band_attn_dparam_kernel(const AttnParams p, int rows_per_block) 
 }
 
 static AttnParams attn_params(const float* wh, const float* remb, const float* rwb, const float* rbias, int T, int B, int NH,
-                              int D, int maxlen, int L, int R, float scale) {
+                              int D, int maxlen, int L, int R, float scale, int mode, const int* klen) {
     AttnParams p{};
     p.T = T; p.B = B; p.NH = NH; p.D = D; p.L = L; p.R = R; p.S = L + R + 1; p.maxlen = maxlen;
+    p.mode = mode;
+    p.klen = klen;
     p.scale = scale;
     p.wh = wh; p.remb = remb; p.rwb = rwb; p.rbias = rbias;
     return p;
 }
 
 int launch_band_attn_fwd(const float* wh, const float* remb, const float* rwb, const float* rbias, int T, int B, int NH, int D,
-                         int maxlen, int L, int R, float scale, float* prob, float* out, cudaStream_t s) {
-    AttnParams p = attn_params(wh, remb, rwb, rbias, T, B, NH, D, maxlen, L, R, scale);
+                         int maxlen, int L, int R, float scale, int mode, const int* klen, float* prob, float* out,
+                         cudaStream_t s) {
+    AttnParams p = attn_params(wh, remb, rwb, rbias, T, B, NH, D, maxlen, L, R, scale, mode, klen);
     p.prob = prob;
     p.out = out;
     const long long warps = (long long)T * B * NH;
@@ -273,9 +291,9 @@ int launch_band_attn_fwd(const float* wh, const float* remb, const float* rwb, c
 }
 
 int launch_band_attn_bwd(const float* wh, const float* remb, const float* rwb, const float* prob, const float* dout, int T,
-                         int B, int NH, int D, int maxlen, int L, int R, float scale, float* ds, float* dq_ac, float* dwh,
-                         float* d_remb, float* d_rwb, float* d_rbias, cudaStream_t s) {
-    AttnParams p = attn_params(wh, remb, rwb, nullptr, T, B, NH, D, maxlen, L, R, scale);
+                         int B, int NH, int D, int maxlen, int L, int R, float scale, int mode, const int* klen, float* ds,
+                         float* dq_ac, float* dwh, float* d_remb, float* d_rwb, float* d_rbias, cudaStream_t s) {
+    AttnParams p = attn_params(wh, remb, rwb, nullptr, T, B, NH, D, maxlen, L, R, scale, mode, klen);
     p.prob = const_cast<float*>(prob);
     p.dout = dout;
     p.ds = ds;

@@ -59,6 +59,17 @@ def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True
             _set(_attention, "CONTEXT", (int(streaming_context[0]), int(streaming_context[1])))
         except ImportError:
             pass
+        # espnet/nets/pytorch_backend/transformer/attention.py:264-308, same band (tt_espnet's encoder: 10 / 2)
+        try:
+            m = importlib.import_module("espnet.nets.pytorch_backend.transformer.attention")
+            cls = m.RelPositionMultiHeadedAttention
+            if cls.forward is not _attention.espnet_banded_forward:
+                cls._ttb_reference_forward = cls.forward
+                _set(cls, "forward", _attention.espnet_banded_forward)
+                done.append("espnet...attention.RelPositionMultiHeadedAttention.forward")
+            _set(_attention, "CONTEXT", (int(streaming_context[0]), int(streaming_context[1])))
+        except ImportError:
+            pass
     if patch_data:
         # tt/utils.py:297-329; train.py:18 copies the names at import (`from tt.utils import ...`)
         for modname in ("tt.utils", "train"):
