@@ -203,7 +203,7 @@ def _run_pair(ref, mine, enc, pred, labels, al, ll, weights=None, dtype=torch.fl
     got = ttb.rnnt_loss(z, labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")
     (got.float() * wts.to(DEV)).sum().backward()
     torch.cuda.synchronize()
-    errs = {"loss": float(((got.double().cpu() - want.detach().double()) / want.detach().double()).abs().max()),
+    errs = {"loss": float(((got.detach().double().cpu() - want.detach().double()) / want.detach().double()).abs().max()),
             "d_enc": rel(e1.grad, e0.grad), "d_pred": rel(p1.grad, p0.grad)}
     for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
         errs["d_" + n] = rel(a.grad, b.grad)
@@ -558,3 +558,28 @@ def test_full_size_properties_cfg2():
     ttb.rnnt_loss(joint(e3[:, :, None], p3[:, None]), labels[sub], al[sub], ll[sub], 0, "none").sum().backward()
     assert rel(e3.grad, e.grad) < GRAD_TOL and rel(p3.grad, p_.grad) < GRAD_TOL
     assert rel(joint.lin_out.weight.grad, gw_dense) < GRAD_TOL
+
+
+def test_random_shape_sweep_matches_oracle():
+    """Sixteen random shapes (tools/parity_sweep.py, seed 0): every route's widths, V from 2 to 1025, ragged lengths down to
+    T = 1 / U = 0, bf16 and fp32 inputs, grad_output weights spread over 1e-2 .. 1e2 with both signs."""
+    import random
+    rng = random.Random(0)
+    for case in range(16):
+        H = rng.choice([64, 128, 256, 384, 512, 512, 512, 1024, 1024, 1536, 768])
+        V = rng.choice([2, 3, 17, 63, 64, 65, 127, 129, 255, 256, 257, 300, 511, 513, 700, 1000, 1025])
+        B = rng.randint(1, 5)
+        T = rng.randint(1, 70)
+        U = rng.randint(0, 12)
+        D = rng.choice([32, 64, 512])
+        al = [rng.randint(1, T) for _ in range(B)]
+        al[rng.randrange(B)] = T
+        ll = [rng.randint(0, U) for _ in range(B)]
+        ll[rng.randrange(B)] = U
+        dtype = torch.bfloat16 if rng.random() < 0.25 else torch.float32
+        wts = torch.tensor([10.0 ** rng.uniform(-2, 2) * rng.choice([1, 1, -1]) for _ in range(B)])
+        errs, _ = _run_pair(*_espnet_case(B, T, U, V, D, H, al, ll, seed=case), weights=wts, dtype=dtype)
+        if dtype == torch.float32:
+            _check(errs)
+        else:
+            _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)

@@ -2,17 +2,18 @@ import sys, os, torch, time
 sys.path.insert(0, '/root/repo')
 import bench
 import transformer_transducer_b200 as ttb
-w = bench.WORKLOADS["cfg2"]
+w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)
-joint = ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh").to(dev)
+joint = (ttb.JointNet(2 * w["D"], w["H"], w["V"]) if w["joint"] == "tt" else
+         ttb.JointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh")).to(dev)
 crit = ttb.RNNTLoss(blank=0, reduction="mean")
 enc, pred, labels, al, ll = bench.synth(w, 1234, device=dev)
 enc.requires_grad_(); pred.requires_grad_()
 def step():
     for p_ in joint.parameters(): p_.grad = None
     enc.grad = None; pred.grad = None
-    loss = crit(joint(enc[:, :, None], pred[:, None]), labels, al, ll)
+    loss = crit(joint(enc, pred) if w["joint"] == "tt" else joint(enc[:, :, None], pred[:, None]), labels, al, ll)
     loss.backward()
 for _ in range(3): step()
 torch.cuda.synchronize()
