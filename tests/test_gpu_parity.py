@@ -583,3 +583,38 @@ def test_random_shape_sweep_matches_oracle():
             _check(errs)
         else:
             _check(errs, BF16_LOSS_TOL, BF16_GRAD_TOL)
+
+
+def test_dense_logits_entry_random_sweep_matches_oracle():
+    """warprnnt_pytorch.rnnt_loss on DENSE (B, T, U1, V) logits (the upstream calling convention, train.py:53 without the
+    lazy handle) over twenty random ragged shapes, V from 2 to 4233, logit scales 0.1 .. 5, all three reductions, random
+    grad_output: fp32 arithmetic -- loss 1e-5, gradient 1e-4, exact zeros outside each utterance's lattice."""
+    import random
+    rng = random.Random(5)
+    for case in range(20):
+        B, T, U = rng.randint(1, 6), rng.randint(1, 90), rng.randint(0, 15)
+        V = rng.choice([2, 3, 5, 31, 32, 33, 100, 255, 256, 257, 1000, 4233])
+        al = [rng.randint(1, T) for _ in range(B)]
+        al[rng.randrange(B)] = T
+        ll = [rng.randint(0, U) for _ in range(B)]
+        ll[rng.randrange(B)] = U
+        torch.manual_seed(case)
+        acts = torch.randn(B, T, U + 1, V) * rng.choice([0.1, 1.0, 5.0])
+        labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+        for i, n in enumerate(ll):
+            labels[i, n:] = -1
+        red = rng.choice(["none", "mean", "sum"])
+        a0 = acts.clone().requires_grad_()
+        want = rnnt_oracle.rnnt_loss(a0, labels, _i32(al), _i32(ll), 0, red)
+        wts = torch.randn_like(want)
+        (want * wts).sum().backward()
+        a1 = acts.to(DEV).requires_grad_()
+        got = ttb.rnnt_loss(a1, labels.to(DEV), _i32(al).to(DEV), _i32(ll).to(DEV), 0, red)
+        (got * wts.to(DEV)).sum().backward()
+        assert got.shape == want.shape
+        err = (got.detach().cpu().double() - want.detach().double()).abs() / want.detach().double().abs().clamp_min(1e-6)
+        assert float(err.max()) < 1e-5, (case, float(err.max()))
+        assert rel(a1.grad, a0.grad) < 1e-4, (case, rel(a1.grad, a0.grad))
+        for b in range(B):
+            assert al[b] == T or float(a1.grad[b, al[b]:].abs().max()) == 0
+            assert ll[b] == U or float(a1.grad[b, :, ll[b] + 1:].abs().max()) == 0
