@@ -618,3 +618,54 @@ def test_dense_logits_entry_random_sweep_matches_oracle():
         for b in range(B):
             assert al[b] == T or float(a1.grad[b, al[b]:].abs().max()) == 0
             assert ll[b] == U or float(a1.grad[b, :, ll[b] + 1:].abs().max()) == 0
+
+
+def test_autograd_usage_patterns():
+    """What a training script may do around the drop-in: backward twice with retain_graph, one handle through the loss
+    twice, gradient accumulation over steps, a combined objective, a non-default stream, materialising the handle."""
+    torch.manual_seed(0)
+    B, T, U, V, D, H = 3, 30, 6, 211, 64, 512
+    joint = ttb.JointNetwork(V, D, D, H, "tanh").to(DEV)
+    crit = ttb.RNNTLoss()
+    enc = torch.randn(B, T, 1, D, device=DEV, requires_grad=True)
+    pred = torch.randn(B, 1, U + 1, D, device=DEV, requires_grad=True)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32, device=DEV)
+    al, ll = _i32([T, T - 4, 9]).to(DEV), _i32([U, 3, 0]).to(DEV)
+
+    def grads():
+        g = [enc.grad.clone(), pred.grad.clone()] + [p.grad.clone() for p in joint.parameters()]
+        enc.grad = pred.grad = None
+        for p in joint.parameters():
+            p.grad = None
+        return g
+
+    def close(a, b, tol=1e-5):
+        return all(float((x - y).abs().max()) <= tol * (1 + float(y.abs().max())) for x, y in zip(a, b))
+
+    loss = crit(joint(enc, pred), labels, al, ll)
+    loss.backward()
+    g0, l0 = grads(), float(loss.detach())
+    loss = crit(joint(enc, pred), labels, al, ll)
+    loss.backward(retain_graph=True)
+    loss.backward()
+    assert close(grads(), [2 * x for x in g0])
+    z = joint(enc, pred)
+    l1, l2 = crit(z, labels, al, ll), crit(z, labels, al, ll)
+    (l1 + l2).backward()
+    assert abs(float(l1.detach()) - l0) < 1e-6 * abs(l0) and close(grads(), [2 * x for x in g0])
+    for _ in range(2):
+        crit(joint(enc, pred), labels, al, ll).backward()
+    assert close(grads(), [2 * x for x in g0])
+    (0.3 * crit(joint(enc, pred), labels, al, ll) + 1e-3 * enc.pow(2).sum()).backward()
+    gf = grads()
+    assert close([gf[1]], [0.3 * g0[1]]) and close([gf[0]], [0.3 * g0[0] + 2e-3 * enc.detach()])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        loss = crit(joint(enc, pred), labels, al, ll)
+        loss.backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - l0) < 1e-6 * abs(l0) and close(grads(), g0)
+    dense = joint(enc, pred).materialize()
+    assert tuple(dense.shape) == (B, T, U + 1, V) and dense.requires_grad
