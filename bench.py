@@ -186,9 +186,9 @@ def _cpu_joint(w):
     return joint_ref.EspnetJointNetwork(w["V"], w["D"], w["D"], w["H"], "tanh"), "oracle/joint_ref.EspnetJointNetwork"
 
 
-def cpu_port_step(w, B_s, seed=1234):
+def cpu_port_step(w, B_s, seed=1234, loss_impl="port"):
     """One step of the reference's CPU path on B_s utterances of workload w (reference joint + the oracle's port of the
-    un-vendored warprnnt_pytorch loss); returns seconds."""
+    un-vendored warprnnt_pytorch loss, or torchaudio's independent CPU rnnt_loss); returns seconds."""
     from oracle import rnnt_oracle
     ws = dict(w, B=B_s, bf16=False)
     enc, pred, labels, act_lens, label_lens = synth(ws, seed)
@@ -196,6 +196,12 @@ def cpu_port_step(w, B_s, seed=1234):
     tt = w.get("joint") == "tt"
     joint, cpu_port_step.joint_name = _cpu_joint(w)
     crit = rnnt_oracle.RNNTLoss(blank=0)
+    if loss_impl == "torchaudio":
+        import torchaudio
+
+        def crit(logits, labels, act_lens, label_lens):                     # noqa: F811
+            return torchaudio.functional.rnnt_loss(logits, labels.clamp_min(0), act_lens, label_lens, blank=0,
+                                                   reduction="mean")
     enc.requires_grad_()
     pred.requires_grad_()
     t0 = time.perf_counter()
@@ -214,10 +220,18 @@ def cpu_baseline(w, budget_s=12.0):
     B_s = int(max(1, min(w["B"], budget_s / 2 / max(t1, 1e-3))))
     ts = [cpu_port_step(w, B_s) for _ in range(2)]
     t = min(ts)
-    return {"value": B_s / t, "unit": "utt/s", "cores": cores, "kind": "port",
-            "sample": "%d utterances of the workload per step (T=%d U=%d V=%d H=%d), best of 2 steps, %s + "
-                      "oracle/rnnt_cpu.c (OpenMP port of warprnnt_pytorch)" %
-                      (B_s, w["T"], w["U"], w["V"], w["H"], cpu_port_step.joint_name)}
+    out = {"value": B_s / t, "unit": "utt/s", "cores": cores, "kind": "port",
+           "sample": "%d utterances of the workload per step (T=%d U=%d V=%d H=%d), best of 2 steps, %s + "
+                     "oracle/rnnt_cpu.c (OpenMP port of warprnnt_pytorch)" %
+                     (B_s, w["T"], w["U"], w["V"], w["H"], cpu_port_step.joint_name)}
+    try:        # a second, independent CPU number: the same joint with torchaudio's CPU rnnt_loss
+        cpu_port_step(w, 1, loss_impl="torchaudio")
+        t2 = min(cpu_port_step(w, B_s, loss_impl="torchaudio") for _ in range(2))
+        out["torchaudio_rnnt_loss"] = {"value": B_s / t2, "unit": "utt/s", "sample": "same joint and sample, "
+                                       "torchaudio.functional.rnnt_loss (CPU) as the loss"}
+    except Exception as e:                        # torchaudio missing or without its CPU op
+        out["torchaudio_rnnt_loss"] = {"unavailable": repr(e)[:120]}
+    return out
 
 
 def run_reference(args, w):
