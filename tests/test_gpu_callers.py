@@ -308,6 +308,8 @@ def test_tt_greedy_decode_equals_reference_decode(inner):
             ttb.uninstall()
     assert got == want and got_single == want
     assert all(0 < len(w) < n for w, n in zip(want, lengths))    # labels were emitted, and blanks in between
+    with pytest.raises(IndexError):                              # like enc_state[t] past the end in the reference's loop
+        ttb.greedy_search(model.joint, enc[0], 91, lambda toks: model.decoder(torch.tensor([toks], device=DEV))[:, -1, :])
 
 
 @pytest.mark.parametrize("beam", [5, 3])

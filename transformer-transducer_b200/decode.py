@@ -61,6 +61,8 @@ class _FrameScanner:
     def __init__(self, joint, enc_state, length, parts=None, eproj=None, out=None):
         if not enc_state.is_cuda:
             raise RuntimeError("the decode-time joint kernel needs CUDA tensors (there is no CPU fallback)")
+        if length > enc_state.shape[0]:           # the reference's loop would index enc_state[t] past its end
+            raise IndexError("decode length %d exceeds the %d encoder frames" % (length, enc_state.shape[0]))
         self.lib = _lib.get()
         self.dev = dev = enc_state.device
         self.length = length
