@@ -381,10 +381,10 @@ def main():
             p_.grad = None
         (e, p_, lab, al, ll), ev = pending.pop() if pending else fetch()
         torch.cuda.current_stream(dev).wait_event(ev)
-        pending.append(fetch())                                   # the next step's inputs, behind this step's kernels
         e.requires_grad_()
         p_.requires_grad_()
         loss = crit(logits_of(e, p_), lab, al, ll)
+        pending.append(fetch())                                   # the next step's inputs, copied under this step's kernels
         loss.backward()
         return loss.item()          # device -> host read of the step's result
 
