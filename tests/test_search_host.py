@@ -61,3 +61,45 @@ def test_beam_search_bookkeeping_equals_reference(monkeypatch, seed, boost):
             want = model.beam_search(enc, 40, beam_width=width)
             got = D.beam_search(model.joint, enc, 40, step, beam_width=width)
             assert got == want
+
+
+def test_install_is_idempotent_uninstall_restores_and_cpu_calls_take_the_reference_path():
+    """install() twice then uninstall(): every rebound name is the reference's again; while installed, CPU tensors go
+    through the reference's own decode / recognize / beam_search / attention forward (the product has no CPU kernels)."""
+    import transformer_transducer_b200 as ttb
+    ref_import.prepare(stub_train_deps=True)
+    tt_model = ref_import.tt_model()
+    import tt.transformer as ttr
+    import tt.utils as tu
+    from espnet.nets.pytorch_backend.transformer import attention as eatt
+    from tt.utils import AttrDict
+    names = [(tt_model, "JointNet"), (tt_model.Transducer, "decode"), (tt_model.Transducer, "recognize"),
+             (tt_model.Transducer, "beam_search"), (ttr.RelLearnableMultiHeadAttn, "forward"),
+             (eatt.RelPositionMultiHeadedAttention, "forward"), (tu, "time_mask_augment"), (tu, "frequency_mask_augment")]
+    before = [getattr(o, a) for o, a in names]
+    cfg = AttrDict(yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "config", "aishell.yaml"))))
+    cfg.model.enc.n_layer = 1
+    cfg.model.dec.n_layer = 1
+    cfg.model.vocab_size = 53
+    cfg.model.joint.inner_size = 64
+    cfg.model.dropout = 0.0
+    torch.manual_seed(11)
+    model = tt_model.Transducer(cfg.model).eval()
+    x = torch.randn(2, 30, 512)
+    with torch.no_grad():
+        model.joint.project_layer.bias[0] += 0.4
+        want = model.recognize(x, [30, 17])
+        want_beam = model.beam_search(model.encoder(x, None)[0], 30, beam_width=3)
+        want_enc = model.encoder(x, tu.context_mask(x)[:, :, None])
+    try:
+        first = ttb.install()
+        second = ttb.install()
+        assert "tt.model.Transducer.recognize" in first and not [n for n in second if "Transducer" in n]
+        assert all(getattr(o, a) is not b for (o, a), b in zip(names, before))
+        with torch.no_grad():
+            assert model.recognize(x, [30, 17]) == want
+            assert model.beam_search(model.encoder(x, None)[0], 30, beam_width=3) == want_beam
+            assert torch.equal(model.encoder(x, tu.context_mask(x)[:, :, None]), want_enc)
+    finally:
+        ttb.uninstall()
+    assert all(getattr(o, a) is b for (o, a), b in zip(names, before))
