@@ -146,6 +146,29 @@ def test_lazy_handle_looks_like_the_logits():
         del os.environ["TTX_MATERIALIZE_LIMIT_GB"]
     h.materialize().sum().backward()                      # materialisation is differentiable w.r.t. the parts
     assert ep.grad is not None and lin.weight.grad is not None
+    # transducer/loss.py:61-62 ("warp-rnnt" branch): log_softmax over the vocabulary keeps the handle lazy
+    for lp in (torch.log_softmax(h, dim=-1), torch.nn.functional.log_softmax(h, -1), h.log_softmax(3)):
+        assert isinstance(lp, ttb.LazyJointLogits) and lp.normalised and lp.parts[0] is ep
+        assert torch.allclose(lp.materialize(), torch.log_softmax(dense, -1), atol=1e-6)
+    assert lp.detach().normalised and lp.to(dtype=torch.bfloat16).normalised and not h.normalised
+    other = torch.log_softmax(h, dim=1)                   # any other dimension is an ordinary (dense) tensor operation
+    assert not isinstance(other, ttb.LazyJointLogits) and torch.allclose(other, torch.log_softmax(dense, 1), atol=1e-6)
+
+
+def test_warp_rnnt_surface():
+    """espnet's TransLoss("warp-rnnt") imports `from warp_rnnt import rnnt_loss` (transducer/loss.py:29) and calls it with
+    reduction="mean", blank=..., gather=True (:64-72)."""
+    import inspect
+    import warp_rnnt
+    params = list(inspect.signature(warp_rnnt.rnnt_loss).parameters)
+    assert params[:4] == ["log_probs", "labels", "frames_lengths", "labels_lengths"]
+    assert {"average_frames", "reduction", "blank", "gather", "fastemit_lambda"} <= set(params)
+    with pytest.raises(ValueError):
+        warp_rnnt.rnnt_loss(torch.zeros(1, 1, 1, 2), torch.zeros(1, 0, dtype=torch.int32), torch.ones(1, dtype=torch.int32),
+                            torch.zeros(1, dtype=torch.int32), reduction="average")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        warp_rnnt.rnnt_loss(torch.zeros(1, 1, 1, 2), torch.zeros(1, 0, dtype=torch.int32), torch.ones(1, dtype=torch.int32),
+                            torch.zeros(1, dtype=torch.int32))
 
 
 def test_algorithm_model_with_rounding_meets_tolerances_against_oracle():

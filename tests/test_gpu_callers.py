@@ -242,11 +242,55 @@ def test_espnet_transformer_transducer_forward_backward_bf16_joint():
         loss.backward()
         outs.append(loss)
     want, got = outs
-    assert abs(float(got) - float(want)) / abs(float(want)) < 1e-2
+    assert abs(float(got.detach()) - float(want.detach())) / abs(float(want.detach())) < 1e-2
     _assert_grads_close(model, ref_model, 5e-2)
 
 
 # ----------------------------------------------------------------------------- greedy search (decode-time joint)
+def test_espnet_transloss_warp_rnnt_branch_stays_on_the_fused_path():
+    """espnet/nets/pytorch_backend/transducer/loss.py:27-31,61-72: TransLoss("warp-rnnt") takes log_softmax of the joint's
+    output and calls warp_rnnt.rnnt_loss(log_probs, ..., reduction="mean", gather=True).  With our JointNetwork the handle
+    stays lazy through the log_softmax; loss and gradients equal the oracle's; a dense tensor of log-probabilities works
+    too (costs, reductions, average_frames)."""
+    import warp_rnnt
+    ref_import.prepare(stub_train_deps=True)
+    from espnet.nets.pytorch_backend.transducer.loss import TransLoss
+    from oracle import joint_ref
+    torch.manual_seed(2)
+    B, T, U, V, D, H = 3, 21, 5, 97, 32, 512
+    ref = joint_ref.EspnetJointNetwork(V, D, D, H, "tanh")
+    mine = ttb.JointNetwork(V, D, D, H, "tanh")
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    enc, pred = torch.randn(B, T, 1, D), torch.randn(B, 1, U + 1, D)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    al, ll = torch.tensor([T, 15, 4], dtype=torch.int32), torch.tensor([U, 2, 0], dtype=torch.int32)
+    e0, p0 = enc.clone().requires_grad_(), pred.clone().requires_grad_()
+    want_costs = rnnt_oracle.rnnt_loss(ref(e0, p0), labels, al, ll, 0, "none")
+    want_costs.mean().backward()
+    crit = TransLoss("warp-rnnt", 0)
+    assert crit.trans_loss is warp_rnnt.rnnt_loss
+    e1, p1 = enc.to(DEV).requires_grad_(), pred.to(DEV).requires_grad_()
+    seen = []
+    orig = warp_rnnt.rnnt_loss
+    crit.trans_loss = lambda lp, *a, **k: (seen.append(type(lp)), orig(lp, *a, **k))[1]
+    got = crit(mine(e1, p1), labels.to(DEV), al.to(DEV), ll.to(DEV))
+    got.backward()
+    assert seen == [ttb.LazyJointLogits]
+    assert abs(float(got.detach()) - float(want_costs.mean())) / float(want_costs.mean()) < LOSS_TOL
+    assert rel(e1.grad, e0.grad) < GRAD_TOL and rel(p1.grad, p0.grad) < GRAD_TOL
+    for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert rel(a.grad, b.grad) < GRAD_TOL, n
+    # dense log-probabilities, every reduction, average_frames
+    lp = torch.log_softmax(ref(enc, pred).detach(), -1).to(DEV)
+    args = (labels.to(DEV), al.to(DEV), ll.to(DEV))
+    costs = warp_rnnt.rnnt_loss(lp, *args)
+    assert costs.shape == (B,) and float(((costs.cpu() - want_costs.detach()) / want_costs.detach()).abs().max()) < 1e-5
+    assert abs(float(warp_rnnt.rnnt_loss(lp, *args, reduction="sum")) - float(want_costs.sum())) < 1e-4 * float(want_costs.sum())
+    avg = warp_rnnt.rnnt_loss(lp, *args, average_frames=True, reduction="mean")
+    assert avg.dim() == 0 and abs(float(avg) - float((want_costs.detach() / al).mean())) < 1e-5 * float(want_costs.mean())
+
+
 def test_decode_scan_kernel_matches_torch_argmax():
     """ttx_decode_scan through the C ABI: per-frame argmax of tanh(eproj + pvec) . W^T + b, first non-blank frame and
     its label, against float64 torch (frames whose two best logits are closer than 1e-4 are not compared: fp32

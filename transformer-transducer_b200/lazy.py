@@ -25,7 +25,7 @@ def _limit_bytes():
 
 class LazyJointLogits(torch.Tensor):
     @staticmethod
-    def __new__(cls, eproj, pproj, w_out, b_out, dtype=None):
+    def __new__(cls, eproj, pproj, w_out, b_out, dtype=None, normalised=False):
         B, T, _ = eproj.shape
         U1 = pproj.shape[1]
         V = w_out.shape[0]
@@ -33,10 +33,20 @@ class LazyJointLogits(torch.Tensor):
                                                 requires_grad=False)
         r.eproj, r.pproj, r.w_out, r.b_out = eproj, pproj, w_out, b_out
         r.pre = None        # (enc, w_enc, b_enc, dec, w_dec) when the pre-projections ran on our kernels (joint._handle)
+        # True: the handle stands for log_softmax(logits, -1) (espnet's "warp-rnnt" branch, transducer/loss.py:61-62).  The
+        # loss normalises its input anyway, so the kernels see no difference; materialize() applies the log_softmax.
+        r.normalised = bool(normalised)
         return r
 
     def __repr__(self):
-        return "LazyJointLogits(shape=%s, dtype=%s, device=%s)" % (tuple(self.shape), self.dtype, self.device)
+        return "LazyJointLogits(shape=%s, dtype=%s, device=%s%s)" % (tuple(self.shape), self.dtype, self.device,
+                                                                   ", log_softmax" if self.normalised else "")
+
+    def _like(self, parts=None, dtype=None, normalised=None):
+        out = LazyJointLogits(*(parts or self.parts), dtype=dtype or self.dtype,
+                              normalised=self.normalised if normalised is None else normalised)
+        out.pre = self.pre if parts is None else None
+        return out
 
     @property
     def parts(self):
@@ -49,7 +59,10 @@ class LazyJointLogits(torch.Tensor):
             raise RuntimeError("refusing to materialise %.1f GB of joint logits (set TTX_MATERIALIZE_LIMIT_GB to "
                                "override); pass the handle to RNNTLoss instead" % (nbytes / (1 << 30)))
         h = torch.tanh(self.eproj.unsqueeze(2) + self.pproj.unsqueeze(1))
-        return torch.nn.functional.linear(h, self.w_out, self.b_out).to(self.dtype)
+        z = torch.nn.functional.linear(h, self.w_out, self.b_out)
+        if self.normalised:
+            z = torch.log_softmax(z.float(), dim=-1)
+        return z.to(self.dtype)
 
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
@@ -62,7 +75,13 @@ class LazyJointLogits(torch.Tensor):
             return super().__torch_function__(func, types, args, kwargs)
         if name == "detach":
             src = args[0]
-            return LazyJointLogits(*[t.detach() for t in src.parts], dtype=src.dtype)
+            return src._like(parts=[t.detach() for t in src.parts])
+        if name == "log_softmax" and args and isinstance(args[0], LazyJointLogits):
+            # log_softmax over the vocabulary keeps the handle lazy (transducer/loss.py:61-62 in front of warp_rnnt)
+            src = args[0]
+            dim = kwargs.get("dim", args[1] if len(args) > 1 else None)
+            if dim in (-1, src.dim() - 1) and len(args) <= 2:
+                return src._like(dtype=kwargs.get("dtype", None), normalised=True)
 
         def unwrap(x):
             return x.materialize() if isinstance(x, LazyJointLogits) else x
@@ -80,9 +99,7 @@ class LazyJointLogits(torch.Tensor):
             src = args[0]
             dev = kwargs.get("device", None)
             if dev is None or torch.device(dev) == src.device:
-                out = LazyJointLogits(*src.parts, dtype=kwargs.get("dtype", None) or src.dtype)
-                out.pre = src.pre
-                return out
+                return src._like(dtype=kwargs.get("dtype", None) or src.dtype)
 
         def unwrap(x):
             return x.materialize().detach() if isinstance(x, LazyJointLogits) else x
