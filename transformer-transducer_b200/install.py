@@ -103,6 +103,12 @@ def install(patch_tt=True, patch_espnet=True, patch_decode=True, patch_data=True
             done.append("espnet...joint_network.JointNetwork")
         except ImportError:
             pass
+        # modules that copied the name at import (`from ...joint_network import JointNetwork`): tt_espnet/model.py:14 and the
+        # upstream-style caller espnet/nets/pytorch_backend/e2e_asr_transducer.py:21
+        other = "espnet.nets.pytorch_backend.e2e_asr_transducer"
+        if other in sys.modules and hasattr(sys.modules[other], "JointNetwork"):
+            _set(sys.modules[other], "JointNetwork", JointNetwork)
+            done.append("espnet...e2e_asr_transducer.JointNetwork")
         if "tt_espnet.model" in sys.modules:
             _set(sys.modules["tt_espnet.model"], "JointNetwork", JointNetwork)
             done.append("tt_espnet.model.JointNetwork")
