@@ -26,7 +26,7 @@ _verified = {}               # id(mask) -> (weakref to the mask, bool): one chec
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    return t.data_ptr() if t is not None else None
 
 
 def _is_context_band(attn_mask, T, left, right):
@@ -65,7 +65,7 @@ class BandAttnCore(torch.autograd.Function):
         out = torch.empty(T, B, n_head * d_head, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            st = torch._C._cuda_getCurrentRawStream(idx)
             _lib.check(lib.ttx_band_attn_fwd(_p(wh), _p(re), _p(rw), _p(rb), T, B, n_head, d_head, re.shape[0], left, right,
                                              ctypes.c_float(scale), mode, _p(key_lens), _p(prob), _p(out), idx, st),
                        "ttx_band_attn_fwd")
@@ -88,7 +88,7 @@ class BandAttnCore(torch.autograd.Function):
         d_rb = torch.zeros(re.shape[0], n_head, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            st = torch._C._cuda_getCurrentRawStream(idx)
             _lib.check(lib.ttx_band_attn_bwd(_p(wh), _p(re), _p(rw), _p(prob), _p(d_out), T, B, n_head, d_head, re.shape[0],
                                              left, right, ctypes.c_float(scale), mode, _p(key_lens), _p(ds), _p(dq_ac),
                                              _p(d_wh), _p(d_re), _p(d_rw), _p(d_rb), idx, st), "ttx_band_attn_bwd")

@@ -55,7 +55,7 @@ def _apply(inputs, masks):
                 idx = dev.index if dev.index is not None else torch.cuda.current_device()
                 _lib.check(lib.ttx_spec_mask(ctypes.c_void_p(inputs.data_ptr()), inputs.size(0), inputs.size(1),
                                              inputs.size(2), inputs.stride(0), inputs.stride(1), arr, len(part), idx,
-                                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "ttx_spec_mask")
+                                             torch._C._cuda_getCurrentRawStream(idx)), "ttx_spec_mask")
         return inputs
     for axis, start, width in masks:
         if axis == 1:

@@ -17,7 +17,6 @@ half once per emitted label, both fp32 ``torch.nn.functional.linear``), tanh, ou
 kernel -- decoding compares logits, so none of the 16-bit tensor-core operands of the training path are used here.
 Equal to the reference up to fp32 summation order; ``install()`` rebinds the two methods.
 """
-import ctypes
 
 import torch
 
@@ -29,7 +28,7 @@ SCAN_FIRST = 8          # frames scored right after a label; doubled while only 
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr())
+    return t.data_ptr()
 
 
 class _JointParts:
@@ -81,7 +80,7 @@ class _FrameScanner:
     def launch(self, t, n, pvec, blank):
         """Frames t .. t + n - 1 against pvec, stream-ordered: out[0] = offset of the first frame whose argmax is not
         blank (n if none), out[1] = its label."""
-        st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        st = torch._C._cuda_getCurrentRawStream(self.idx)
         _lib.check(self.lib.ttx_decode_scan(_p(self.eproj[t]), self.eproj.stride(0), _p(pvec), _p(self.parts.w_out),
                                             _p(self.parts.b_out), n, self.H, self.V, int(blank), _p(self.scratch),
                                             _p(self.out), self.idx, st), "ttx_decode_scan")

@@ -7,7 +7,7 @@
 ``dense_rnnt``        the same loss on an already materialised logits tensor (train.py:53 when the
                       joint is not ours).
 """
-import ctypes
+import contextlib
 import os
 
 import torch
@@ -16,11 +16,25 @@ from . import _lib
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """Device address for a c_void_p argument (a plain int: ctypes converts it; None = NULL)."""
+    return t.data_ptr() if t is not None else None
+
+
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def _guard(dev):
+    """`with torch.cuda.device(dev)` only when dev is not already the current device (the usual one-process-per-GPU case
+    enters nothing: the context manager costs more than a kernel launch)."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(dev)
 
 
 def _stream(dev):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    """The current stream's raw handle on dev (an int; 0 = the legacy default stream).  The private accessor skips
+    torch.cuda.current_stream()'s Stream object: this runs once per kernel launch."""
+    return torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())
 
 
 # name -> number of kernels one call launches (bench.py's gpu_launches / per-kernel timing)
@@ -151,7 +165,7 @@ class FusedJointRNNT(torch.autograd.Function):
         w = w_out.detach().float().contiguous()
         b = b_out.detach().float().contiguous()
         labels = labels.contiguous()
-        with torch.cuda.device(dev):
+        with _guard(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
@@ -200,7 +214,7 @@ class FusedJointRNNT(torch.autograd.Function):
         need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         d_ep = d_pp = d_w = d_b = None
-        with torch.cuda.device(dev):
+        with _guard(dev):
             st = _stream(dev)
             scal = scal.clone()
             if need_w:
@@ -317,7 +331,7 @@ class WideJointRNNT(torch.autograd.Function):
         if pre:
             ctx.pre = (enc.detach().reshape(-1, enc.shape[-1]).contiguous(), w_enc.detach(), b_enc is not None,
                        dec.detach().reshape(-1, dec.shape[-1]).contiguous(), w_dec.detach(), enc.shape, dec.shape)
-        with torch.cuda.device(dev):
+        with _guard(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
@@ -388,7 +402,7 @@ class WideJointRNNT(torch.autograd.Function):
         need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         d_ep = d_pp = d_w = d_b = None
         pre_grads = [None] * 5
-        with torch.cuda.device(dev):
+        with _guard(dev):
             st = _stream(dev)
             scal = scal.clone()
             Vpad = w16.numel() // H
@@ -500,7 +514,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         w, b = w_out.detach().float().contiguous(), b_out.detach().float().contiguous()
         labels = labels.contiguous()
         dt16 = torch.bfloat16 if bf16 else torch.float16
-        with torch.cuda.device(dev):
+        with _guard(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             st = _stream(dev)
             Vpad = (V + 255) // 256 * 256
@@ -537,7 +551,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
         need_act = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         d_ep = d_pp = d_w = d_b = None
-        with torch.cuda.device(dev):
+        with _guard(dev):
             st = _stream(dev)
             scal = scal.clone()
             Vpad = w16.numel() // H
@@ -621,7 +635,7 @@ class DenseRNNT(torch.autograd.Function):
         a = acts.detach().float().contiguous()
         labels = labels.contiguous()
         lib = _lib.get()
-        with torch.cuda.device(dev):
+        with _guard(dev):
             plan = _Plan(B, T, U1, dev, act_lens, label_lens, sizes)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
@@ -639,7 +653,7 @@ class DenseRNNT(torch.autograd.Function):
         a, row_label, lse, lpb, lpl, alpha, beta, ll_beta = ctx.saved_tensors
         plan = ctx.plan
         B, T, U1, V = a.shape
-        with torch.cuda.device(plan.dev):
+        with _guard(plan.dev):
             scal = torch.zeros(8, dtype=torch.float32, device=plan.dev)
             rowmeta = plan.grad_coeffs(lse, lpb, lpl, alpha, beta, ll_beta, grad_costs, scal, row_label, ctx.blank)
             grads = torch.empty_like(a)

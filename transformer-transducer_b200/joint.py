@@ -10,7 +10,6 @@ B*T + B*U rows instead of the reference's B*T*U).  Everything else -- 1-D decode
 (tt/model.py:77), CPU tensors, other activations, widths that are not a multiple of 64 -- is the reference's
 dense math.
 """
-import ctypes
 
 import torch
 
@@ -20,7 +19,7 @@ from .lazy import LazyJointLogits
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    return t.data_ptr() if t is not None else None
 
 
 class _Proj(torch.autograd.Function):
@@ -37,9 +36,9 @@ class _Proj(torch.autograd.Function):
         x2 = x.detach().reshape(-1, K).contiguous()
         M = x2.shape[0]
         y = torch.empty(M, N, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with F._guard(dev):
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            st = torch._C._cuda_getCurrentRawStream(idx)
             bb = b.detach().contiguous() if b is not None else None
             F._call("ttx_proj_fwd", dev, _p(x2), K, _p(w), w.stride(0), _p(bb), M, N, K, _p(y), N, idx, st)
         ctx.save_for_backward(x2, w)
@@ -54,9 +53,9 @@ class _Proj(torch.autograd.Function):
         M = x2.shape[0]
         dy2 = dy.reshape(M, N).contiguous()
         dx = dw = db = None
-        with torch.cuda.device(dev):
+        with F._guard(dev):
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            st = torch._C._cuda_getCurrentRawStream(idx)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty(M, K, dtype=torch.float32, device=dev)
                 F._call("ttx_proj_bwd_x", dev, _p(dy2), N, _p(w), w.stride(0), M, N, K, _p(dx), K, idx, st)

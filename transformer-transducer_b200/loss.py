@@ -6,7 +6,6 @@ size, ``'mean'``/``'sum'`` return shape ``(1,)``, labels / lengths must be int32
 and ``U + 1 == max(label_lens) + 1`` are checked on the host.  CUDA only -- the CPU path is the oracle,
 which is test infrastructure and not part of the product.
 """
-import ctypes
 import os
 
 import torch
@@ -53,12 +52,11 @@ def certify_inputs(acts, labels, act_lens, label_lens):
         lab = labels.to(dev).contiguous()
         al, ll = act_lens.to(dev).contiguous(), label_lens.to(dev).contiguous()
         out = torch.empty(7, dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
+        with F._guard(dev):
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None  # noqa: E731
+            p = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
             _lib.check(_lib.get().ttx_check_inputs(p(lab), lab.shape[1], p(al), p(ll), B, acts.shape[3], p(out), idx,
-                                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                       "ttx_check_inputs")
+                                                   torch._C._cuda_getCurrentRawStream(idx)), "ttx_check_inputs")
         m = out.tolist()                                         # the synchronisation
         mx = [m[0], m[1], m[2], m[3], m[4], m[5], m[6]]
     else:
