@@ -1,3 +1,5 @@
+"""Host-side cost of one joint + loss step: issue time per step (no synchronisation) and a cProfile of the Python front end.
+    python tools/host_prof.py [cfg1|cfg2|...]      (run under gpurun)"""
 import os, sys, cProfile, pstats, io, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
