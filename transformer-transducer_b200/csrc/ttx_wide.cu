@@ -128,16 +128,21 @@ struct EventWait {
 };
 
 // =========================================================================================================== S pass
-// With both operands streamed the S pass moves 256 KiB per 128 x 256 tile through TMA in ~6100 cycles, against 4096 cycles of
-// MMA time (ncu: tensor pipe 66 %).  Keeping the pair's A16 tiles stationary in shared memory
-// (H <= 512: 128 KiB per CTA, only W16 streams) halves the bytes, but the tile takes the room of either the ring or the P'
-// staging buffers, and both trades lose at configs[1] (streaming both: 2.02 - 2.19 ms): staging buffers + three 16 KiB
-// ring stages 2.23 ms (latency-bound ring); five stages + P' stored straight from registers 3.32 ms with 16-byte stores
-// (half-sector writes), 2.87 ms with 32-byte stores; HALF of the tile stationary (192 KiB per tile through TMA, staging
-// buffers and seven 16 KiB stages kept) 2.42 ms against 2.21 ms -- fewer bytes do not help: the S pass is bound by its
-// epilogue's latency (ncu: issue slots 44 %, MUFU 33 %, tensor pipe 65 % -- ~6100 cycles per 128 x 256 tile and SM) --
-// and at full chip by the board's power cap: on 148 SMs the clock sits at ~1515 of 1965 MHz, on 74 SMs the kernel loses only
-// 1.5x (profiles/r2_summary.md), so per-SM cycle tuning no longer moves it.
+// With both operands streamed the S pass moves 256 KiB per 128 x 256 tile through TMA in 6100 - 7300 cycles, against 4096
+// cycles of MMA time (ncu: tensor pipe 66 %).  Timing decomposition at configs[1] (profiles/r2_summary.md): 1.55 ms with the
+// epilogue switched off -- the operand stream at the SM's TMA receive limit (~40 B/cycle/SM; full-rate MMAs want 64) --
+// + ~0.25 ms for the P' store (same port) + ~0.25 ms for the epilogue's math (issue slots / shared memory next to the
+// single-thread roles) = 2.05 - 2.2 ms.  Variants that cut the TMA bytes, all measured and removed:
+//   A16 tiles stationary in shared memory (H <= 512: 128 KiB per CTA, only W16 streams): the tile takes the room of either
+//     the ring or the P' staging buffers -- staging buffers + three 16 KiB ring stages 2.23 ms (latency-bound ring); five
+//     stages + P' stored straight from registers 3.32 ms with 16-byte stores (half-sector writes), 2.87 ms with 32-byte
+//     stores; HALF of the tile stationary (192 KiB per tile, seven 16 KiB stages) 2.42 ms against 2.21 ms;
+//   A16 tiles stationary in TENSOR memory (TS-mode tcgen05.mma, tile copied ring -> tcgen05.st, eleven 16 KiB W16 stages):
+//     256 columns of A leave ONE accumulator, and its hand-over chain (commit -> 16 warps wake -> tcgen05.ld -> 32 remote
+//     arrivals -> issuer, ~2300 cycles per tile) costs what the halved stream saves: 2.25 - 2.31 ms against 2.05 - 2.20 ms,
+//     parity-green (lane = row, a 32-bit column = two consecutive K elements, low half first).
+// At full chip the board's power cap is the next limit anyway: on 148 SMs the clock sits at ~1515 of 1965 MHz, on 74 SMs
+// the kernel loses only 1.5x (profiles/r2_summary.md).
 template <bool BF16>
 __global__ void __launch_bounds__(kSpThreads, 1)
 sp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
