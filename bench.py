@@ -375,6 +375,7 @@ def main():
         return ts, ev
 
     pending = []
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def step_e2e():
         for p_ in joint.parameters():
@@ -384,9 +385,15 @@ def main():
         e.requires_grad_()
         p_.requires_grad_()
         loss = crit(logits_of(e, p_), lab, al, ll)
+        # device -> host read of the step's result: the loss is final when the forward is, so its copy is queued here and
+        # waited for once the backward has been launched -- the host then prepares the next step while the backward runs
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        read = torch.cuda.Event()
+        read.record()
         pending.append(fetch())                                   # the next step's inputs, copied under this step's kernels
         loss.backward()
-        return loss.item()          # device -> host read of the step's result
+        read.synchronize()
+        return float(loss_host[0])
 
     def barrier():
         if dist is not None:
