@@ -55,10 +55,13 @@ int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf
 
 /* A16[row,:] = 16-bit(tanh(eproj[b,t,:] + pproj[b,u,:])) for every lattice cell; row_label[row] = label
  * emitted from the cell's u (labels[b,u]) or -1.  eproj (B,T,H), pproj (B,U1,H) fp32 contiguous;
- * labels (B, label_stride) int32, entries at u >= label_lens[b] are never read. */
+ * labels (B, label_stride) int32, entries at u >= label_lens[b] are never read.  V = vocabulary size: a label
+ * >= V is stored as -1 (row_label is what the later calls gather W_out rows and scatter gradient rows through, so
+ * they stay inside their buffers whatever the labels hold; the Python front end raises ValueError for such input,
+ * as for negative labels inside label_lens); 0 = labels are trusted. */
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
-                  int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label,
+                  int V, int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label,
                   void* a16t /* NULL or the transposed copy for the gradient pass, H x rows values stored in blocks of 64 rows: [rows / 64][H][64] */, int device, void* stream);
 
 /* tcgen05 projection A16 . W16^T + b_out fused with log-softmax statistics: per row lse, log p(blank),

@@ -86,7 +86,7 @@ def run(stage, B, T, U, V, H):
     a16 = torch.empty(rows * H, dtype=torch.int16, device=dev)
     row_label = torch.empty(rows, dtype=torch.int32, device=dev)
     a16t = torch.empty(H * rows, dtype=torch.int16, device=dev) if use_t else None
-    _lib.check(lib.ttx_joint_act(_p(Ed), _p(Pd), _p(labd), _p(ald), _p(lld), _p(meta), B, T, U1, H, U, ntub, 0,
+    _lib.check(lib.ttx_joint_act(_p(Ed), _p(Pd), _p(labd), _p(ald), _p(lld), _p(meta), B, T, U1, H, U, V, ntub, 0,
                                  _p(a16), _p(row_label), _p(a16t), 0, st), "act")
     torch.cuda.synchronize()
     ws = float(scal[0])

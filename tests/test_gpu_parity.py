@@ -669,3 +669,24 @@ def test_autograd_usage_patterns():
     assert abs(float(loss.detach()) - l0) < 1e-6 * abs(l0) and close(grads(), g0)
     dense = joint(enc, pred).materialize()
     assert tuple(dense.shape) == (B, T, U + 1, V) and dense.requires_grad
+
+
+def test_out_of_vocabulary_label_stays_inside_the_buffers_when_the_host_check_is_skipped(monkeypatch):
+    """ttx_joint_act stores a label >= V as 'none' (include/ttx.h), so a caller that bypasses certify_inputs
+    (TTX_SKIP_LENGTH_CHECKS=1, or the C ABI directly) gets finite numbers and no out-of-bounds gather / scatter; with the
+    check in place the same input raises ValueError."""
+    case = _espnet_case(2, 20, 5, 150, 64, 512, [20, 13], [5, 2], seed=11)
+    _, mine, enc, pred, labels, al, ll = case
+    labels = labels.clone()
+    labels[0, 2] = 150 + 77
+    mine = mine.to(DEV)
+    e1, p1 = enc.to(DEV).requires_grad_(), pred.to(DEV).requires_grad_()
+    with pytest.raises(ValueError):
+        ttb.rnnt_loss(mine(e1[:, :, None], p1[:, None]), labels.to(DEV), al.to(DEV), ll.to(DEV))
+    monkeypatch.setenv("TTX_SKIP_LENGTH_CHECKS", "1")
+    guard = torch.zeros(4096, device=DEV)                   # (something for a stray scatter to hit)
+    costs = ttb.rnnt_loss(mine(e1[:, :, None], p1[:, None]), labels.to(DEV), al.to(DEV), ll.to(DEV), 0, "none")
+    costs.sum().backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(costs).all() and torch.isfinite(mine.lin_out.weight.grad).all()
+    assert torch.isfinite(e1.grad).all() and float(guard.abs().max()) == 0

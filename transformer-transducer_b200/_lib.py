@@ -29,7 +29,7 @@ _PROTOS = {
     "ttx_meta_ints": [c_i32, c_i64],
     "ttx_prepare": [c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_i32, c_p],
     "ttx_cast_weight": [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_p],
-    "ttx_joint_act": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_p, c_p, c_p,
+    "ttx_joint_act": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, c_p, c_p, c_p,
                       c_i32, c_p],
     "ttx_joint_lse_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_i32, c_p],
     "ttx_lattice_elems_upper_bound": [c_i32, c_i32, c_i32],

@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...) {
 int launch_prep(const int*, const int*, int, int, int, int, int*, cudaStream_t);
 int launch_cast_w(const float*, const float*, int, int, int, bool, float*, void*, float*, void*, cudaStream_t);
 int launch_joint_act(const float*, const float*, const int*, const int*, const int*, const int*, int, int, int, int,
-                     int, int, bool, void*, int*, void*, cudaStream_t);
+                     int, int, int, bool, void*, int*, void*, cudaStream_t);
 int launch_lattice(const float*, const float*, const int*, const int*, const int*, int, int, int, size_t, float*, double*,
                    double*, float*, double*, cudaStream_t);
 int launch_grad_prep(const float*, const float*, const float*, const double*, const double*, const double*,
@@ -143,13 +143,14 @@ int ttx_cast_weight(const float* w_out, const float* b_out, int V, int H, int bf
 }
 
 int ttx_joint_act(const float* eproj, const float* pproj, const int32_t* labels, const int32_t* act_lens,
-                  const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride,
+                  const int32_t* label_lens, const int32_t* meta, int B, int T, int U1, int H, int label_stride, int V,
                   int64_t n_tiles_ub, int bf16, void* a16, int32_t* row_label, void* a16t, int device, void* stream) {
     TTX_REQUIRE(eproj && pproj && act_lens && label_lens && meta && a16 && row_label, "ttx_joint_act: null pointer");
     TTX_REQUIRE(labels || U1 == 1, "ttx_joint_act: labels is null");
     TTX_REQUIRE(H > 0 && H % 64 == 0, "ttx_joint_act: H=%d must be a positive multiple of 64", H);
     TTX_ENTER(device);
-    return launch_joint_act(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1, H, label_stride,
+    TTX_REQUIRE(V >= 0, "ttx_joint_act: V=%d", V);
+    return launch_joint_act(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1, H, label_stride, V,
                             (int)n_tiles_ub, bf16 != 0, a16, row_label, a16t, (cudaStream_t)stream);
 }
 

@@ -143,7 +143,7 @@ template <bool BF16>
 __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* __restrict__ pproj,
                                  const int* __restrict__ labels, const int* __restrict__ act_lens,
                                  const int* __restrict__ label_lens, const int* __restrict__ meta, int B, int T,
-                                 int U1, int H, int label_stride, uint16_t* __restrict__ a16,
+                                 int U1, int H, int label_stride, int V, uint16_t* __restrict__ a16,
                                  int* __restrict__ row_label, uint16_t* __restrict__ a16t, size_t rows_total) {
     __shared__ uint32_t tr[kTile][33];           // one 64-column slab of the tile (row-major, 33-word rows), for the transposed copy
     const int tile = blockIdx.x;
@@ -218,6 +218,10 @@ __global__ void joint_act_kernel(const float* __restrict__ eproj, const float* _
         if (r < nrows) {
             const int u = r % U1b;
             if (u < U1b - 1) lab = labels[(size_t)b * label_stride + u];
+            // a label outside the vocabulary is stored as "none": row_label is what every later kernel gathers W_out rows
+            // and scatters gradient rows through (the host-side check raises for such input; this keeps a caller that
+            // skipped it inside its buffers)
+            if (V > 0 && lab >= V) lab = -1;
         }
         row_label[(size_t)tile * kTile + lr] = lab;
     }
@@ -762,7 +766,8 @@ __global__ void dense_lse_kernel(const float* __restrict__ acts, const int* __re
         }
         if (lane == 0) {
             const float l = m + __logf(s);
-            const int lab = (u < U1b - 1) ? labels[(size_t)b * label_stride + u] : -1;
+            int lab = (u < U1b - 1) ? labels[(size_t)b * label_stride + u] : -1;
+            if (lab >= V) lab = -1;                        // (as joint_act_kernel: nothing gathers or scatters through it)
             lse[grow] = l;
             lpb[grow] = row[blank] - l;
             lpl[grow] = (lab >= 0) ? row[lab] - l : 0.f;
@@ -918,16 +923,16 @@ int launch_cast_w(const float* w, const float* b_out, int V, int Vpad, int H, bo
 }
 
 int launch_joint_act(const float* eproj, const float* pproj, const int* labels, const int* act_lens,
-                     const int* label_lens, const int* meta, int B, int T, int U1, int H, int label_stride,
+                     const int* label_lens, const int* meta, int B, int T, int U1, int H, int label_stride, int V,
                      int n_tiles_ub, bool bf16, void* a16, int* row_label, void* a16t, cudaStream_t s) {
     const size_t rows_total = (size_t)n_tiles_ub * kTile;
     if (bf16)
         joint_act_kernel<true><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T, U1,
-                                                         H, label_stride, (uint16_t*)a16, row_label, (uint16_t*)a16t,
+                                                         H, label_stride, V, (uint16_t*)a16, row_label, (uint16_t*)a16t,
                                                          rows_total);
     else
         joint_act_kernel<false><<<n_tiles_ub, 256, 0, s>>>(eproj, pproj, labels, act_lens, label_lens, meta, B, T,
-                                                          U1, H, label_stride, (uint16_t*)a16, row_label,
+                                                          U1, H, label_stride, V, (uint16_t*)a16, row_label,
                                                           (uint16_t*)a16t, rows_total);
     TTX_CUDA_OK(cudaGetLastError());
     return 0;

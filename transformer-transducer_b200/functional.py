@@ -182,7 +182,7 @@ class FusedJointRNNT(torch.autograd.Function):
             row_label = torch.empty(plan.rows, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
-                                         _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16),
+                                         _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, V, plan.ntub, int(bf16),
                                          _p(a16), _p(row_label), _p(a16t), plan.idx, st)
             lse, lpb, lpl = plan.rowf(), plan.rowf(), plan.rowf()
             # When the activations need gradients the forward also accumulates EW = sum_v p_v W_out[v] (minus the
@@ -350,7 +350,7 @@ class WideJointRNNT(torch.autograd.Function):
                       plan.idx, _stream(dev))
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
-                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
+                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, V, plan.ntub, int(bf16), _p(a16), _p(row_label),
                   None, plan.idx, st)          # (no transposed copy: the weight gradient reads its operands MN-major)
             if side is not None:
                 main.wait_stream(side)
@@ -526,7 +526,7 @@ class ChunkedJointRNNT(torch.autograd.Function):
             row_label = torch.full((plan.rows,), -1, dtype=torch.int32, device=dev)
             lstride = labels.shape[1] if labels.dim() == 2 else 0
             _call("ttx_joint_act", dev, _p(ep), _p(pp), _p(labels) if labels.numel() else None, _p(act_lens),
-                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, plan.ntub, int(bf16), _p(a16), _p(row_label),
+                  _p(label_lens), _p(plan.meta), B, T, U1, H, lstride, V, plan.ntub, int(bf16), _p(a16), _p(row_label),
                   None, plan.idx, st)
             lse, lpb, lpl = (torch.zeros(plan.rows, dtype=torch.float32, device=dev) for _ in range(3))
             a2, w2 = a16.view(dt16).view(plan.rows, H), w16.view(dt16).view(Vpad, H)
