@@ -420,9 +420,13 @@ def main():
         alone = {k: sum(v) / len(v) for k, v in alone.items()}
         step_resident()
         barrier()
+    # (everything only one rank does goes IN FRONT of the barrier: a rank that enters the timed region late keeps the others
+    # waiting in their first all-reduce, and the max over ranks then carries that wait -- 0.3 - 0.5 ms per step over 20 steps
+    # when the sampler's start-up sat behind the barrier)
     sampler = ClockSampler(local) if rank == 0 else None
-    F.PROFILE = prof = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    F.PROFILE = prof = []
     ev0.record()
     for _ in range(args.steps):
         step_resident()
@@ -508,6 +512,15 @@ def main():
         out["roofline_lattice"] = {"bound": "hbm (latency-bound in practice)", "achieved": gbs, "peak": pk["hbm"],
                                    "unit": "GB/s", "frac": gbs / pk["hbm"], "kernel_ms": lat_ms,
                                    "dependent_steps": int(w["T"] + w["U"])}
+    if dist is not None:
+        # DDP keeps the ranks in lockstep: the step time is the slowest GPU's.  Each rank's own product time (events around
+        # its launches) shows which one that is.
+        mine = {"rank": rank, "products_ms": sum(v["avg_ms"] for k, v in table.items() if k.startswith("ttx_wide_")
+                                                 or k.startswith("ttx_joint_")),
+                "kernels_ms": sum(v["avg_ms"] * v["calls"] for v in table.values()) / max(1, args.steps)}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        out["ranks"] = allr
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w)
