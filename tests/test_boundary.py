@@ -96,6 +96,30 @@ def test_certify_inputs_matches_upstream_conventions():
             rnnt_oracle.certify_inputs(*bad)
 
 
+def test_certify_inputs_cache_follows_in_place_edits_and_label_range():
+    """The length check is skipped only for the very same tensors at the same version: an in-place edit of the lengths or
+    labels is seen by the next call.  Labels inside label_lens must index the vocabulary; the padding beyond may hold
+    anything (tt/dataset.py:46-48 pads with -1)."""
+    acts = torch.zeros(2, 3, 3, 5)
+    lab, al, ll = _i32([[1, 4], [2, -1]]), _i32([3, 2]), _i32([2, 1])
+    sizes = ttb.certify_inputs(acts, lab, al, ll)
+    assert sizes == ttb.certify_inputs(acts, lab, al, ll) and sizes[0] == 2          # one 128-row tile per utterance
+    al[0] = 2                                                                       # in place: T no longer max(act_lens)
+    with pytest.raises(ValueError, match="Input length mismatch"):
+        ttb.certify_inputs(acts, lab, al, ll)
+    al[0] = 3
+    ttb.certify_inputs(acts, lab, al, ll)
+    lab[0, 1] = 5                                                                   # == V, inside label_lens[0] = 2
+    with pytest.raises(ValueError, match="labels must lie"):
+        ttb.certify_inputs(acts, lab, al, ll)
+    lab[0, 1] = -1
+    with pytest.raises(ValueError, match="labels must lie"):
+        ttb.certify_inputs(acts, lab, al, ll)
+    lab[0, 1] = 4
+    lab[1, 1] = 77                                                                  # beyond label_lens[1] = 1: never read
+    ttb.certify_inputs(acts, lab, al, ll)
+
+
 def _load_sd(module, g):
     module.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd_")})
 
