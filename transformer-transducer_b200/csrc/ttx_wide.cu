@@ -25,7 +25,7 @@ int make_matrix_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 struct WideParams {
     int H, NKC;              // joint width, H / 64
     int V, n_vchunks;        // vocabulary size, 256-column chunks of it
-    int n_k64;               // Vpad / 64
+    int n_k64;               // ceil(V / 64): K groups of the EW product
     int blank;
     int NS;                  // sp: ring stages (32 KiB each)
     int tile_lo, tile_cnt;   // lattice tiles [tile_lo, tile_lo + tile_cnt) (clipped to the tiles in use); tile_lo even
@@ -834,7 +834,7 @@ static WideParams wide_params(int H, int V, int Vpad, int tile_lo, int tile_cnt,
     p.NKC = H / kKC;
     p.V = V;
     p.n_vchunks = Vpad / 256;
-    p.n_k64 = Vpad / kKC;
+    p.n_k64 = (V + kKC - 1) / kKC;          // (64-column groups that hold vocabulary: the padding beyond has P' = 0)
     p.tile_lo = tile_lo;
     p.tile_cnt = tile_cnt;
     p.store_rows = (int)store_rows;
